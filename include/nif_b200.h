@@ -1,0 +1,135 @@
+/* nif_b200 — C ABI of the B200-native NIF hot path (libnif_b200.so).
+ *
+ * The reference (pswpswpsw/nif) has no FFI: its hot path is Python/TF graph code.
+ * Each entry point below names the reference interface it replaces
+ * (file:line under /root/reference).  Conventions:
+ *   - every pointer is a DEVICE pointer owned by the caller (16-byte aligned,
+ *     contiguous row-major fp32 unless stated); nothing is allocated or freed;
+ *   - every call only enqueues work on `stream` (a cudaStream_t passed as
+ *     void*); no call synchronises;
+ *   - return 0 on success, a negative NIF_E_* otherwise; nif_last_error()
+ *     returns a thread-local message for the last failure.
+ *
+ * ShapeNet weights are never materialised per sample.  The last linear layer of
+ * the ParameterNet (w_h [K,P], b_h [P]) is re-laid once per step into a
+ * kernel-friendly "packed" image (nif_pack) and all kernels work from that.
+ */
+#ifndef NIF_B200_H
+#define NIF_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+  NIF_OK = 0,
+  NIF_E_BAD_DESC = -1,    /* inconsistent / unsupported descriptor */
+  NIF_E_BAD_ARG = -2,     /* null / misaligned pointer, negative size */
+  NIF_E_UNSUPPORTED = -3, /* valid but not implemented for this build */
+  NIF_E_CUDA = -4         /* CUDA runtime error; text in nif_last_error() */
+};
+
+enum { NIF_VARIANT_NIF = 0, NIF_VARIANT_SIREN = 1, NIF_VARIANT_SIREN_RES = 2 };
+enum { NIF_ACT_LINEAR = 0, NIF_ACT_SINE = 1, NIF_ACT_SWISH = 2, NIF_ACT_TANH = 3,
+       NIF_ACT_RELU = 4, NIF_ACT_SIGMOID = 5 };
+
+/* Static description of one hyper-network head + ShapeNet.
+ * variant: NIF._call_shape_net (nif/model.py:233-324, act + residual),
+ *          NIFMultiScale._call_shape_net_mres plain (:880-954) / res-block (:767-879).
+ * act    : tf.keras.activations.get(cfg_shape_net["activation"]) (:303); SIREN variants use sine.
+ * si,so,n,l : cfg_shape_net input_dim/output_dim/units/nlayers (:84-87); K = latent_dim (:89).
+ * omega0 : cfg_shape_net["omega_0"] (:533); 1.0 for NIF_VARIANT_NIF. */
+typedef struct nif_desc {
+  int32_t variant;
+  int32_t act;
+  int32_t si, so, n, l, K;
+  float omega0;
+  int32_t dtype_compute; /* 0 = fp32 CUDA-core path (parity path) */
+  int32_t reserved;
+} nif_desc_t;
+
+/* Sizes derived from a descriptor. */
+typedef struct nif_sizes {
+  int64_t po_dim;        /* P: columns of pnet_output (nif/model.py:169-173, 569-587) */
+  int64_t n_layers;      /* ShapeNet matrices: l+2, or 2l+2 with res-blocks */
+  int64_t np;            /* padded width used on chip (32/64/128) */
+  int64_t packed_floats; /* floats of one packed weight image (nif_pack output) */
+  int64_t save_floats_per_row;  /* floats/row of the activation stash written by forward for backward */
+  int64_t grad_ws_floats;       /* floats of the partial-gradient workspace for batch size B (see nif_sizes B) */
+  int64_t tile_rows;     /* rows per CTA tile */
+} nif_sizes_t;
+
+const char* nif_last_error(void);
+int nif_version(void);
+
+/* Fill `out` for batch size B (B only affects grad_ws_floats). */
+int nif_query_sizes(const nif_desc_t* d, int64_t B, nif_sizes_t* out);
+
+/* Re-lay the last linear layer for the kernels.  Replaces the slicing/reshape
+ * of pnet_output columns (nif/model.py:253-300, 769-846, 883-933), applied once
+ * to the shared [K,P] matrix instead of to the (B,P) activations.
+ * w_h [K,P], b_h [P]  ->  packed [packed_floats].  G>1 packs G independent
+ * heads: w_h may be NULL (K must then be 0) and b_h is [G,P] — used by the
+ * grouped inference path where each group's full weight vector is given. */
+int nif_pack(const nif_desc_t* d, int64_t G, const float* w_h, const float* b_h,
+             float* packed, void* stream);
+
+/* Fused forward: u[b,:] = ShapeNet(x[b,:]; weights = z[b,:] @ w_h + b_h).
+ * Replaces HyperLinearForSIREN.call (nif/layers/siren.py:514-522) / Dense(po_dim)
+ * (nif/model.py:220-230) + _call_shape_net / _call_shape_net_mres
+ * (nif/model.py:233-324, 738-954) + EinsumLayer (nif/layers/mlp.py:209-219).
+ * z [G*B,K] (ignored when K==0), x [G*B,si] or, if x_shared!=0, [B,si] shared by
+ * all groups; packed [G*packed_floats]; u [G*B,so].
+ * save: NULL for inference, else [save_floats_per_row * B] (G must be 1). */
+int nif_forward(const nif_desc_t* d, int64_t G, int64_t B, const float* z, const float* x,
+                int32_t x_shared, const float* packed, float* u, float* save, void* stream);
+
+/* Forward with forward-mode tangents (JacobianLayer, nif/layers/gradient.py:36-49,
+ * 207-231, realised as tangents instead of one reverse pass per output).
+ * n_dir directions; zdot [n_dir,B,K] (may be NULL = 0), xdot [n_dir,B,si] (may be
+ * NULL = 0); udot [n_dir,B,so]. */
+int nif_forward_tangent(const nif_desc_t* d, int64_t B, const float* z, const float* x,
+                        const float* packed, int32_t n_dir, const float* zdot, const float* xdot,
+                        float* u, float* udot, void* stream);
+
+/* model_x_to_u_given_w (nif/model.py:435-464, 956-986): every row brings its own
+ * full weight vector.  x [B,si], w [B,P] (reference column layout), u [B,so]. */
+int nif_forward_given_w(const nif_desc_t* d, int64_t B, const float* x, const float* w,
+                        float* u, void* stream);
+
+/* Keras 'mse' (+ optional sample_weight) and its reverse pass through the fused
+ * path (what Keras train_step does with GradientTape over the graph above).
+ * loss   [1]  = sum_b sw[b] * mean_c (u-target)^2 * inv_global_batch   (accumulated, +=)
+ * du seed     = 2 (u-target) sw[b] inv_global_batch / so
+ * dw_h [K,P], db_h [P]: gradients in the REFERENCE layout; written if beta==0,
+ * accumulated (+=) if beta==1.   dz [B,K]: written.
+ * `u`, `save` come from nif_forward(..., save) on the same inputs.
+ * ws: [grad_ws_floats] scratch. */
+int nif_mse_backward(const nif_desc_t* d, int64_t B, const float* z, const float* x,
+                     const float* packed, const float* u, const float* save,
+                     const float* target, const float* sample_weight, float inv_global_batch,
+                     float* loss, float* dw_h, float* db_h, float beta, float* dz,
+                     float* ws, void* stream);
+
+/* Same reverse pass with a caller-supplied seed du [B,so] (for custom losses). */
+int nif_backward(const nif_desc_t* d, int64_t B, const float* z, const float* x,
+                 const float* packed, const float* save, const float* du,
+                 float* dw_h, float* db_h, float beta, float* dz, float* ws, void* stream);
+
+/* tf.keras.optimizers.Adam update (third-party in the reference):
+ * m += (g-m)(1-b1); v += (g*g-v)(1-b2); p -= lr*sqrt(1-b2^t)/(1-b1^t) * m/(sqrt(v)+eps).
+ * Optional kernel regularisers (nif/model.py:107-125): g += l1*sign(p) + 2*l2*p.
+ * g_scale multiplies g first (e.g. 1/world_size). */
+int nif_adam_step(int64_t n, float* p, const float* g, float* m, float* v, float lr,
+                  float b1, float b2, float eps, int64_t t, float l1, float l2, float g_scale,
+                  void* stream);
+
+/* Utility used by the benchmark: sustained FP32 FMA rate of this GPU (TFLOP/s),
+ * measured with CUDA events; blocks until done. */
+int nif_measure_fp32_peak(double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,160 @@
+// extern "C" surface of libnif_b200.so (see include/nif_b200.h).  Pure argument checking and
+// dispatch; nothing here allocates, synchronises or touches the host copy of any tensor.
+#include "nif_common.cuh"
+
+int nif_pack_impl(const Plan& pl, long long G, const float* w_h, const float* b_h, float* packed, cudaStream_t st);
+int nif_forward_impl(const Plan& pl, long long G, long long B, const float* z, const float* x, int x_shared,
+                     const float* packed, float* u, float* save, cudaStream_t st);
+int nif_tangent_impl(const Plan& pl, long long B, const float* z, const float* x, const float* packed, int n_dir,
+                     const float* zdot, const float* xdot, float* u, float* udot, cudaStream_t st);
+int nif_given_w_impl(const Plan& pl, long long B, const float* x, const float* w, float* u, cudaStream_t st);
+int nif_backward_impl(const Plan& pl, long long B, const float* z, const float* x, const float* packed,
+                      const float* save, const float* du, float* dw_h, float* db_h, float beta, float* dz,
+                      float* ws, cudaStream_t st);
+int nif_mse_backward_impl(const Plan& pl, long long B, const float* z, const float* x, const float* packed,
+                          const float* u, const float* save, const float* target, const float* sw, float inv_gb,
+                          float* loss, float* dw_h, float* db_h, float beta, float* dz, float* ws, cudaStream_t st);
+int nif_adam_impl(long long n, float* p, const float* g, float* m, float* v, float lr, float b1, float b2, float eps,
+                  long long t, float l1, float l2, float gs, cudaStream_t st);
+struct GradWs {
+  long long da, du, part_h, part_e, loss_part, total;
+  int S_h, S_e, Q;
+  long long rows_h, rows_e;
+};
+GradWs nif_grad_ws_layout(const Plan& pl, long long B);
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+#define NIF_REQUIRE_PTR(p)                                               \
+  do {                                                                   \
+    if (!(p) || !aligned16(p)) {                                         \
+      nif_set_error("%s: argument `%s` is null or not 16-byte aligned", __func__, #p); \
+      return NIF_E_BAD_ARG;                                              \
+    }                                                                    \
+  } while (0)
+#define NIF_OPTIONAL_PTR(p)                                              \
+  do {                                                                   \
+    if ((p) && !aligned16(p)) {                                          \
+      nif_set_error("%s: argument `%s` is not 16-byte aligned", __func__, #p); \
+      return NIF_E_BAD_ARG;                                              \
+    }                                                                    \
+  } while (0)
+
+extern "C" int nif_query_sizes(const nif_desc_t* d, int64_t B, nif_sizes_t* out) {
+  Plan pl;
+  int rc = nif_make_plan(d, &pl);
+  if (rc) return rc;
+  if (!out || B < 0) { nif_set_error("nif_query_sizes: bad argument"); return NIF_E_BAD_ARG; }
+  out->po_dim = pl.P;
+  out->n_layers = pl.Lm;
+  out->np = pl.NP;
+  out->packed_floats = pl.packed_floats;
+  out->save_floats_per_row = 2LL * (pl.H + 1) * pl.NP;
+  out->grad_ws_floats = nif_grad_ws_layout(pl, B).total;
+  out->tile_rows = pl.NP == 128 ? 64 : 128;
+  return NIF_OK;
+}
+
+extern "C" int nif_pack(const nif_desc_t* d, int64_t G, const float* w_h, const float* b_h, float* packed,
+                        void* stream) {
+  Plan pl;
+  int rc = nif_make_plan(d, &pl);
+  if (rc) return rc;
+  if (G < 1) { nif_set_error("nif_pack: G=%lld", (long long)G); return NIF_E_BAD_ARG; }
+  if (pl.K > 0) NIF_REQUIRE_PTR(w_h);
+  if (pl.K > 0 && G != 1) { nif_set_error("nif_pack: G>1 requires K==0 (explicit weight vectors in b_h)"); return NIF_E_BAD_ARG; }
+  NIF_REQUIRE_PTR(b_h);
+  NIF_REQUIRE_PTR(packed);
+  return nif_pack_impl(pl, G, w_h, b_h, packed, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int nif_forward(const nif_desc_t* d, int64_t G, int64_t B, const float* z, const float* x,
+                           int32_t x_shared, const float* packed, float* u, float* save, void* stream) {
+  Plan pl;
+  int rc = nif_make_plan(d, &pl);
+  if (rc) return rc;
+  if (G < 1 || B < 0) { nif_set_error("nif_forward: G=%lld B=%lld", (long long)G, (long long)B); return NIF_E_BAD_ARG; }
+  if (B == 0) return NIF_OK;
+  if (pl.K > 0) NIF_REQUIRE_PTR(z);
+  NIF_REQUIRE_PTR(x);
+  NIF_REQUIRE_PTR(packed);
+  NIF_REQUIRE_PTR(u);
+  NIF_OPTIONAL_PTR(save);
+  if (save && G != 1) { nif_set_error("nif_forward: the activation stash needs G==1"); return NIF_E_BAD_ARG; }
+  return nif_forward_impl(pl, G, B, z, x, x_shared, packed, u, save, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int nif_forward_tangent(const nif_desc_t* d, int64_t B, const float* z, const float* x,
+                                   const float* packed, int32_t n_dir, const float* zdot, const float* xdot,
+                                   float* u, float* udot, void* stream) {
+  Plan pl;
+  int rc = nif_make_plan(d, &pl);
+  if (rc) return rc;
+  if (B < 0 || n_dir < 1 || n_dir > NIF_MAX_DIR) {
+    nif_set_error("nif_forward_tangent: B=%lld n_dir=%d (max %d)", (long long)B, n_dir, NIF_MAX_DIR);
+    return NIF_E_BAD_ARG;
+  }
+  if (B == 0) return NIF_OK;
+  if (pl.K > 0) NIF_REQUIRE_PTR(z);
+  NIF_REQUIRE_PTR(x);
+  NIF_REQUIRE_PTR(packed);
+  NIF_REQUIRE_PTR(u);
+  NIF_REQUIRE_PTR(udot);
+  NIF_OPTIONAL_PTR(zdot);
+  NIF_OPTIONAL_PTR(xdot);
+  return nif_tangent_impl(pl, B, z, x, packed, n_dir, zdot, xdot, u, udot, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int nif_forward_given_w(const nif_desc_t* d, int64_t B, const float* x, const float* w, float* u,
+                                   void* stream) {
+  Plan pl;
+  int rc = nif_make_plan(d, &pl);
+  if (rc) return rc;
+  if (B < 0) { nif_set_error("nif_forward_given_w: B=%lld", (long long)B); return NIF_E_BAD_ARG; }
+  if (B == 0) return NIF_OK;
+  NIF_REQUIRE_PTR(x);
+  NIF_REQUIRE_PTR(w);
+  NIF_REQUIRE_PTR(u);
+  return nif_given_w_impl(pl, B, x, w, u, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int nif_mse_backward(const nif_desc_t* d, int64_t B, const float* z, const float* x, const float* packed,
+                                const float* u, const float* save, const float* target, const float* sample_weight,
+                                float inv_global_batch, float* loss, float* dw_h, float* db_h, float beta,
+                                float* dz, float* ws, void* stream) {
+  Plan pl;
+  int rc = nif_make_plan(d, &pl);
+  if (rc) return rc;
+  if (B < 0) { nif_set_error("nif_mse_backward: B=%lld", (long long)B); return NIF_E_BAD_ARG; }
+  if (B == 0) return NIF_OK;
+  if (pl.K > 0) { NIF_REQUIRE_PTR(z); NIF_REQUIRE_PTR(dw_h); NIF_REQUIRE_PTR(dz); }
+  NIF_REQUIRE_PTR(x); NIF_REQUIRE_PTR(packed); NIF_REQUIRE_PTR(u); NIF_REQUIRE_PTR(save);
+  NIF_REQUIRE_PTR(target); NIF_OPTIONAL_PTR(sample_weight);
+  if (!loss) { nif_set_error("nif_mse_backward: loss is null"); return NIF_E_BAD_ARG; }
+  NIF_REQUIRE_PTR(db_h); NIF_REQUIRE_PTR(ws);
+  return nif_mse_backward_impl(pl, B, z, x, packed, u, save, target, sample_weight, inv_global_batch, loss, dw_h,
+                               db_h, beta, dz, ws, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int nif_backward(const nif_desc_t* d, int64_t B, const float* z, const float* x, const float* packed,
+                            const float* save, const float* du, float* dw_h, float* db_h, float beta, float* dz,
+                            float* ws, void* stream) {
+  Plan pl;
+  int rc = nif_make_plan(d, &pl);
+  if (rc) return rc;
+  if (B < 0) { nif_set_error("nif_backward: B=%lld", (long long)B); return NIF_E_BAD_ARG; }
+  if (B == 0) return NIF_OK;
+  if (pl.K > 0) { NIF_REQUIRE_PTR(z); NIF_REQUIRE_PTR(dw_h); NIF_REQUIRE_PTR(dz); }
+  NIF_REQUIRE_PTR(x); NIF_REQUIRE_PTR(packed); NIF_REQUIRE_PTR(save); NIF_REQUIRE_PTR(du);
+  NIF_REQUIRE_PTR(db_h); NIF_REQUIRE_PTR(ws);
+  return nif_backward_impl(pl, B, z, x, packed, save, du, dw_h, db_h, beta, dz, ws,
+                           static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int nif_adam_step(int64_t n, float* p, const float* g, float* m, float* v, float lr, float b1, float b2,
+                             float eps, int64_t t, float l1, float l2, float g_scale, void* stream) {
+  if (n < 0 || t < 1) { nif_set_error("nif_adam_step: n=%lld t=%lld", (long long)n, (long long)t); return NIF_E_BAD_ARG; }
+  if (n == 0) return NIF_OK;
+  NIF_REQUIRE_PTR(p); NIF_REQUIRE_PTR(g); NIF_REQUIRE_PTR(m); NIF_REQUIRE_PTR(v);
+  return nif_adam_impl(n, p, g, m, v, lr, b1, b2, eps, t, l1, l2, g_scale, static_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,672 @@
+// Reverse pass of the fused NIF hot path (fp32 CUDA-core parity path).
+//
+// What Keras' GradientTape does for the graph of nif/model.py:130-154 / 510-539, done
+// without the (B, po_dim) tensor and without the zero-padded (B, po_dim) slice gradients:
+//
+//   1. nif_bwd_data_kernel   per row tile, layers last -> first:
+//        da_m = dh_{m+1} * act'(pre_m)                       (stashed for step 2)
+//        T[b][kappa][i] = sum_j da_m[b][j] M_m[kappa][i][j]  (GEMM, shared transposed weights)
+//        dh_m[b][i]  = omega * sum_kappa zt[b][kappa] T[b][kappa][i]
+//        dz[b][kappa] += omega * sum_i T[b][kappa][i] h_m[b][i] + sum_j C_m[kappa][j] da_m[b][j]
+//   2. nif_bwd_weight_kernel  dM_m[kappa][i][j] = omega * sum_b zt[b][kappa] h_m[b][i] da_m[b][j]
+//        a batch-reduction GEMM; the rank-1 update h (x) da is formed once per row in registers and
+//        scaled by 4 latent coordinates.  Batch splits write partials (deterministic, no atomics).
+//   3. nif_bwd_edge_kernel    the thin terms (all bias rows, first and last matrix) as
+//        out[kappa][q] = sum_b zt[b][kappa] F[b][q]  with on-the-fly features F.
+//   4. nif_unpack_grad (nif_pack.cu) sums the partials into dw_h [K,P], db_h [P] (reference layout).
+#include "nif_tile.cuh"
+
+struct BwdArgs {
+  long long B, total_tiles;
+  const float *z, *x, *packed, *save, *du;
+  float* da;  // [(H+1)][B][NP]
+  float* dz;  // [B][K]
+};
+
+template <class C>
+__host__ __device__ inline size_t bwd_smem_bytes(int K, int si, int so) {
+  size_t f = 2 * (size_t)C::STAGE_FLOATS + (size_t)C::NP * C::TB + 2 * (size_t)(K + 1) * C::TB + (size_t)si * C::TB +
+             (size_t)so * C::TB;
+  return f * 4 + 64;
+}
+
+template <class C, bool RES>
+__global__ void __launch_bounds__(C::NT, 1) nif_bwd_data_kernel(const Plan pl, const BwdArgs a) {
+  constexpr int NP = C::NP, TB = C::TB, MP = C::MP, MJ = C::MJ, NT = C::NT;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* stage = reinterpret_cast<float*>(smem_raw);
+  float* dact = stage + 2 * C::STAGE_FLOATS;  // da_m, k-major swizzled (GEMM A operand)
+  float* zs = dact + NP * TB;                 // [K+1][TB]
+  float* dzs = zs + (pl.K + 1) * TB;          // [K+1][TB]
+  float* xs = dzs + (pl.K + 1) * TB;          // [si][TB]
+  float* dys = xs + pl.si * TB;               // [so][TB]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(dys + pl.so * TB);
+  bar = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(bar) + 7) & ~uintptr_t(7));
+
+  const int tid = threadIdx.x;
+  const int tj = tid % C::TY, tp = tid / C::TY;
+  const int K = pl.K, K1 = pl.K + 1, H = pl.H, si = pl.si, so = pl.so;
+
+  if (tid == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  long long my_tiles = 0;
+  if ((long long)blockIdx.x < a.total_tiles) my_tiles = (a.total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+
+  WeightStream<C> ws;
+  ws.stage = stage;
+  ws.bar = bar;
+  ws.chunks_per_tile = H * K1 * C::NH;
+  ws.total = my_tiles * ws.chunks_per_tile;
+  ws.issued = 0;
+  ws.consumed = 0;
+  ws.H = H;
+  ws.K1 = K1;
+  ws.packed = a.packed;
+  ws.packed_floats = pl.packed_floats;
+  ws.sec_off = pl.off_MHT;
+  ws.tiles_per_group = a.total_tiles;  // single group
+  ws.reverse = true;
+  if (tid == 0) {
+    while (ws.issued < 2 && ws.issued < ws.total) ws.issue_one();
+  }
+
+  const float* C_all = a.packed + pl.off_C;
+
+  // sum s[r] over the TY lanes that share a row group, then lane tj == 0 accumulates into dzs[kk]
+  auto dz_commit = [&](float (&s)[MP], int kk) {
+#pragma unroll
+    for (int off = C::TY / 2; off >= 1; off >>= 1)
+#pragma unroll
+      for (int r = 0; r < MP; ++r) s[r] += __shfl_xor_sync(0xffffffffu, s[r], off);
+    if (tj == 0) {
+#pragma unroll
+      for (int r = 0; r < MP; ++r) dzs[kk * TB + row_of<C>(tp, r)] += s[r];
+    }
+  };
+
+  for (long long t = 0; t < my_tiles; ++t) {
+    const long long tile = blockIdx.x + t * gridDim.x;
+    const long long row0 = tile * TB;
+
+    for (int idx = tid; idx < TB * K; idx += NT) {
+      const int p = idx / K, kk = idx - p * K;
+      const long long b = row0 + p;
+      zs[kk * TB + p] = (b < a.B) ? __ldg(&a.z[b * K + kk]) : 0.f;
+    }
+    for (int p = tid; p < TB; p += NT) zs[K * TB + p] = 1.f;
+    for (int idx = tid; idx < TB * K1; idx += NT) dzs[idx] = 0.f;
+    for (int idx = tid; idx < TB * si; idx += NT) {
+      const int p = idx / si, i = idx - p * si;
+      const long long b = row0 + p;
+      xs[i * TB + p] = (b < a.B) ? __ldg(&a.x[b * si + i]) : 0.f;
+    }
+    for (int idx = tid; idx < TB * so; idx += NT) {
+      const int p = idx / so, c = idx - p * so;
+      const long long b = row0 + p;
+      dys[c * TB + p] = (b < a.B) ? __ldg(&a.du[b * so + c]) : 0.f;
+    }
+    __syncthreads();
+
+    long long brow[MP];
+#pragma unroll
+    for (int r = 0; r < MP; ++r) brow[r] = row0 + row_of<C>(tp, r);
+
+    float acc[MP][MJ];
+    float carry[RES ? MP : 1][RES ? MJ : 1];
+
+    // ---- last layer (matrix H+1): n -> so --------------------------------------------------------------
+    {
+      const float* ML = a.packed + pl.off_ML;
+      const float* CL = C_all + (long long)(H + 1) * K1 * NP;
+      const float* hL = a.save + (long long)H * a.B * NP;  // h_{H+1}
+#pragma unroll
+      for (int r = 0; r < MP; ++r)
+#pragma unroll
+        for (int c = 0; c < MJ; ++c) acc[r][c] = 0.f;
+      for (int kk = 0; kk < K1; ++kk) {
+        float tmp[MP][MJ];
+#pragma unroll
+        for (int r = 0; r < MP; ++r)
+#pragma unroll
+          for (int c = 0; c < MJ; ++c) tmp[r][c] = 0.f;
+        float s[MP];
+#pragma unroll
+        for (int r = 0; r < MP; ++r) s[r] = 0.f;
+        for (int cc = 0; cc < so; ++cc) {
+          float dyv[MP];
+#pragma unroll
+          for (int r = 0; r < MP; ++r) dyv[r] = dys[cc * TB + row_of<C>(tp, r)];
+#pragma unroll
+          for (int c = 0; c < MJ; ++c) {
+            const float w = __ldg(&ML[((long long)kk * NP + col_of<C>(tj, c)) * so + cc]);
+#pragma unroll
+            for (int r = 0; r < MP; ++r) tmp[r][c] = fmaf(dyv[r], w, tmp[r][c]);
+          }
+          if (tj == 0) {
+            const float cb = __ldg(&CL[(long long)kk * NP + cc]);
+#pragma unroll
+            for (int r = 0; r < MP; ++r) s[r] = fmaf(cb, dyv[r], s[r]);
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < MP; ++r) {
+          const float zk = zs[kk * TB + row_of<C>(tp, r)];
+#pragma unroll
+          for (int gj = 0; gj < C::GJ; ++gj) {
+            float4 hv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (brow[r] < a.B) hv = ldg4(&hL[brow[r] * NP + gj * C::JSTR + tj * 4]);
+            const float hvv[4] = {hv.x, hv.y, hv.z, hv.w};
+#pragma unroll
+            for (int f = 0; f < 4; ++f) {
+              acc[r][gj * 4 + f] = fmaf(zk, tmp[r][gj * 4 + f], acc[r][gj * 4 + f]);
+              s[r] = fmaf(tmp[r][gj * 4 + f], hvv[f], s[r]);
+            }
+          }
+        }
+        dz_commit(s, kk);
+      }
+    }
+
+    // ---- layers H .. 0 --------------------------------------------------------------------------------
+    for (int m = H; m >= 0; --m) {
+      const float om = plan_omega(pl, m);
+      const int res = plan_res(pl, m);
+      const float* dsv = a.save + (long long)(H + 1 + m) * a.B * NP;  // d_m
+      float* dag = a.da + (long long)m * a.B * NP;
+      float daf[MP][MJ];
+#pragma unroll
+      for (int r = 0; r < MP; ++r) {
+#pragma unroll
+        for (int gj = 0; gj < C::GJ; ++gj) {
+          float4 dv = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (brow[r] < a.B) dv = ldg4(&dsv[brow[r] * NP + gj * C::JSTR + tj * 4]);
+          daf[r][gj * 4 + 0] = acc[r][gj * 4 + 0] * dv.x;
+          daf[r][gj * 4 + 1] = acc[r][gj * 4 + 1] * dv.y;
+          daf[r][gj * 4 + 2] = acc[r][gj * 4 + 2] * dv.z;
+          daf[r][gj * 4 + 3] = acc[r][gj * 4 + 3] * dv.w;
+          if (brow[r] < a.B)
+            *reinterpret_cast<float4*>(&dag[brow[r] * NP + gj * C::JSTR + tj * 4]) =
+                make_float4(daf[r][gj * 4], daf[r][gj * 4 + 1], daf[r][gj * 4 + 2], daf[r][gj * 4 + 3]);
+        }
+      }
+      if (m >= 1) {
+        // residual bookkeeping (mirror of the forward epilogue)
+#pragma unroll
+        for (int r = 0; r < MP; ++r)
+#pragma unroll
+          for (int c = 0; c < MJ; ++c) {
+            if (RES) {
+              if (res == 3) { carry[RES ? r : 0][RES ? c : 0] = 0.5f * acc[r][c]; acc[r][c] = 0.f; }
+              else if (res == 2) acc[r][c] = carry[RES ? r : 0][RES ? c : 0];
+              else acc[r][c] = 0.f;
+            } else {
+              if (res != 1) acc[r][c] = 0.f;  // res == 1: dh_m = T + dh_{m+1}
+            }
+          }
+        // da_m -> shared (k-major) as the GEMM A operand.  All reads of the previous contents are
+        // behind the barrier of the last ws.release() / the tile prologue.
+#pragma unroll
+        for (int c = 0; c < MJ; ++c) {
+          const int j = col_of<C>(tj, c);
+#pragma unroll
+          for (int gp = 0; gp < C::GP; ++gp) {
+            const int p0 = gp * C::PSTR + tp * 4;
+            *reinterpret_cast<float4*>(&dact[act_idx<C>(j, p0)]) =
+                make_float4(daf[gp * 4][c], daf[gp * 4 + 1][c], daf[gp * 4 + 2][c], daf[gp * 4 + 3][c]);
+          }
+        }
+        __syncthreads();
+        const float* hm = a.save + (long long)(m - 1) * a.B * NP;  // h_m
+        for (int kk = 0; kk < K1; ++kk) {
+          float tmp[MP][MJ];
+#pragma unroll
+          for (int r = 0; r < MP; ++r)
+#pragma unroll
+            for (int c = 0; c < MJ; ++c) tmp[r][c] = 0.f;
+#pragma unroll 1
+          for (int hf = 0; hf < C::NH; ++hf) {
+            const float* st = ws.acquire();
+            mk_gemm<C>(dact, st, hf * C::NIS, tmp, tp, tj);
+            // the last chunk of this layer must not release before dact has been re-read below
+            if (!(kk == K1 - 1 && hf == C::NH - 1)) ws.release();
+          }
+          float s[MP];
+#pragma unroll
+          for (int r = 0; r < MP; ++r) {
+            const float zk = zs[kk * TB + row_of<C>(tp, r)];
+            float sr = 0.f;
+#pragma unroll
+            for (int gj = 0; gj < C::GJ; ++gj) {
+              float4 hv = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (brow[r] < a.B) hv = ldg4(&hm[brow[r] * NP + gj * C::JSTR + tj * 4]);
+              const float4 cb = ldg4(&C_all[((long long)m * K1 + kk) * NP + gj * C::JSTR + tj * 4]);
+              const float hvv[4] = {hv.x, hv.y, hv.z, hv.w};
+              const float cvv[4] = {cb.x, cb.y, cb.z, cb.w};
+#pragma unroll
+              for (int f = 0; f < 4; ++f) {
+                const int c = gj * 4 + f;
+                const float tv = om * tmp[r][c];
+                acc[r][c] = fmaf(zk, tv, acc[r][c]);
+                sr = fmaf(tv, hvv[f], sr);
+                sr = fmaf(cvv[f], dact[act_idx<C>(col_of<C>(tj, c), row_of<C>(tp, r))], sr);
+              }
+            }
+            s[r] = sr;
+          }
+          dz_commit(s, kk);
+          if (kk == K1 - 1) ws.release();
+        }
+      } else {
+        // first matrix: only dz is needed (no gradient w.r.t. the coordinates on this path)
+        const float* M0 = a.packed + pl.off_M0;
+        for (int kk = 0; kk < K1; ++kk) {
+          float s[MP];
+#pragma unroll
+          for (int r = 0; r < MP; ++r) s[r] = 0.f;
+#pragma unroll
+          for (int c = 0; c < MJ; ++c) {
+            const int j = col_of<C>(tj, c);
+            const float cb = __ldg(&C_all[((long long)0 * K1 + kk) * NP + j]);
+            float wv[NIF_MAX_SI];
+#pragma unroll
+            for (int i = 0; i < NIF_MAX_SI; ++i) wv[i] = (i < si) ? __ldg(&M0[((long long)kk * si + i) * NP + j]) : 0.f;
+#pragma unroll
+            for (int r = 0; r < MP; ++r) {
+              float lin = 0.f;
+#pragma unroll
+              for (int i = 0; i < NIF_MAX_SI; ++i)
+                if (i < si) lin = fmaf(xs[i * TB + row_of<C>(tp, r)], wv[i], lin);
+              s[r] = fmaf(daf[r][c], fmaf(om, lin, cb), s[r]);
+            }
+          }
+          dz_commit(s, kk);
+        }
+      }
+    }
+    __syncthreads();
+    for (int idx = tid; idx < TB * K; idx += NT) {
+      const int p = idx / K, kk = idx - p * K;
+      const long long b = row0 + p;
+      if (b < a.B) a.dz[b * K + kk] = dzs[kk * TB + p];
+    }
+    __syncthreads();
+  }
+}
+
+template <class C>
+static int launch_bwd_data(const Plan& pl, const BwdArgs& a, cudaStream_t st) {
+  const size_t smem = bwd_smem_bytes<C>(pl.K, pl.si, pl.so);
+  if (smem > 227 * 1024) {
+    nif_set_error("reverse tile needs %zu B of shared memory (latent_dim too large for this build)", smem);
+    return NIF_E_UNSUPPORTED;
+  }
+  const bool res = pl.variant == NIF_VARIANT_SIREN_RES;
+  auto kern = res ? nif_bwd_data_kernel<C, true> : nif_bwd_data_kernel<C, false>;
+  NIF_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int dev = 0, sms = 0, occ = 0;
+  NIF_CUDA_CHECK(cudaGetDevice(&dev));
+  NIF_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  NIF_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, C::NT, smem));
+  if (occ < 1) occ = 1;
+  long long grid = (long long)sms * occ;
+  if (grid > a.total_tiles) grid = a.total_tiles;
+  if (grid < 1) return NIF_OK;
+  kern<<<(unsigned)grid, C::NT, smem, st>>>(pl, a);
+  NIF_CUDA_CHECK(cudaGetLastError());
+  return NIF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// weight-gradient GEMM for the hidden matrices
+// ---------------------------------------------------------------------------------------------------
+struct WgtArgs {
+  long long B, rows_per_split;
+  int S;
+  const float *z, *save, *da;
+  float* part;  // [S][H][K+1][NP][NP]
+};
+
+template <int TS>
+__global__ void __launch_bounds__((TS / 4) * (TS / 4)) nif_bwd_weight_kernel(const Plan pl, const WgtArgs a) {
+  constexpr int TT = TS / 4, NTW = TT * TT, RC = 32;  // RC rows per chunk
+  constexpr int LD4 = (RC * TS / 4) / NTW;            // float4 loads per thread per operand per chunk
+  __shared__ __align__(16) float hs[RC][TS];
+  __shared__ __align__(16) float ds[RC][TS];
+  __shared__ __align__(16) float zq[RC][4];
+  const int NP = pl.NP, K = pl.K, K1 = pl.K + 1, H = pl.H;
+  const int nb = NP / TS;
+  const int KGN = (K1 + 3) / 4;
+  int bx = blockIdx.x;
+  const int jb = bx % nb; bx /= nb;
+  const int ib = bx % nb; bx /= nb;
+  const int kg = bx % KGN; bx /= KGN;
+  const int h = bx;  // hidden matrix index, layer m = h + 1
+  const int s = blockIdx.y;
+  const int tid = threadIdx.x, ti = tid / TT, tj = tid % TT;
+  const float* hsrc = a.save + (long long)h * a.B * NP + ib * TS;        // h_m, m = h + 1 -> slot h
+  const float* dsrc = a.da + (long long)(h + 1) * a.B * NP + jb * TS;    // da_m
+  const long long r0 = (long long)s * a.rows_per_split;
+  long long r1 = r0 + a.rows_per_split;
+  if (r1 > a.B) r1 = a.B;
+
+  float acc[4][4][4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+#pragma unroll
+      for (int f = 0; f < 4; ++f) acc[q][e][f] = 0.f;
+
+  constexpr int ZL = (RC * 4 + NTW - 1) / NTW;     // latent values per thread per chunk
+  float4 ph[LD4], pd[LD4];
+  float pz[ZL];
+  auto fetch = [&](long long rb) {
+#pragma unroll
+    for (int u = 0; u < LD4; ++u) {
+      const int e = tid + u * NTW;  // float4 index in the chunk
+      const int rr = e / (TS / 4), c4 = e % (TS / 4);
+      const long long b = rb + rr;
+      ph[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      pd[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (b < r1) {
+        ph[u] = ldg4(&hsrc[b * NP + c4 * 4]);
+        pd[u] = ldg4(&dsrc[b * NP + c4 * 4]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < ZL; ++u) {
+      const int e = tid + u * NTW;
+      pz[u] = 0.f;
+      if (e < RC * 4) {
+        const int rr = e / 4, q = e % 4;
+        const long long b = rb + rr;
+        const int kk = kg * 4 + q;
+        if (b < r1) pz[u] = (kk < K) ? __ldg(&a.z[b * K + kk]) : (kk == K ? 1.f : 0.f);
+      }
+    }
+  };
+  auto stash = [&]() {
+#pragma unroll
+    for (int u = 0; u < LD4; ++u) {
+      const int e = tid + u * NTW;
+      const int rr = e / (TS / 4), c4 = e % (TS / 4);
+      *reinterpret_cast<float4*>(&hs[rr][c4 * 4]) = ph[u];
+      *reinterpret_cast<float4*>(&ds[rr][c4 * 4]) = pd[u];
+    }
+#pragma unroll
+    for (int u = 0; u < ZL; ++u) {
+      const int e = tid + u * NTW;
+      if (e < RC * 4) zq[e / 4][e % 4] = pz[u];
+    }
+  };
+
+  if (r0 < r1) fetch(r0);
+  for (long long rb = r0; rb < r1; rb += RC) {
+    __syncthreads();  // previous chunk fully consumed
+    stash();
+    __syncthreads();
+    if (rb + RC < r1) fetch(rb + RC);
+#pragma unroll 4
+    for (int rr = 0; rr < RC; ++rr) {
+      const float4 h4 = *reinterpret_cast<const float4*>(&hs[rr][ti * 4]);
+      const float4 d4 = *reinterpret_cast<const float4*>(&ds[rr][tj * 4]);
+      const float4 z4 = *reinterpret_cast<const float4*>(&zq[rr][0]);
+      const float hv[4] = {h4.x, h4.y, h4.z, h4.w};
+      const float dv[4] = {d4.x, d4.y, d4.z, d4.w};
+      const float zv[4] = {z4.x, z4.y, z4.z, z4.w};
+      float o[4][4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+#pragma unroll
+        for (int f = 0; f < 4; ++f) o[e][f] = hv[e] * dv[f];
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+#pragma unroll
+          for (int f = 0; f < 4; ++f) acc[q][e][f] = fmaf(zv[q], o[e][f], acc[q][e][f]);
+    }
+  }
+  const float om = plan_omega(pl, h + 1);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int kk = kg * 4 + q;
+    if (kk < K1) {
+      float* dst = a.part + ((((long long)s * H + h) * K1 + kk) * NP + ib * TS + ti * 4) * NP + jb * TS + tj * 4;
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        *reinterpret_cast<float4*>(&dst[(long long)e * NP]) =
+            make_float4(om * acc[q][e][0], om * acc[q][e][1], om * acc[q][e][2], om * acc[q][e][3]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// thin terms: bias rows of every layer, first matrix, last matrix
+//   column space Q:  [0,(H+1)NP) dC_m[j] | so: dC_last[c] | si*NP: dM_0[i][j] | NP*so: dM_last[i][c]
+// ---------------------------------------------------------------------------------------------------
+struct EdgeArgs {
+  long long B, rows_per_split;
+  int S, Q;
+  const float *z, *x, *save, *da, *du;
+  float* part;  // [S][K+1][Q]
+};
+
+#define NIF_EDGE_KE 17  // latent coordinates per thread; 4 * 17 = 68 per pass over the batch
+
+__global__ void __launch_bounds__(256) nif_bwd_edge_kernel(const Plan pl, const EdgeArgs a) {
+  constexpr int RC = 64, KC = 4 * NIF_EDGE_KE;
+  __shared__ float zsm[RC][KC + 1];
+  const int NP = pl.NP, K = pl.K, K1 = pl.K + 1, H = pl.H, si = pl.si, so = pl.so;
+  const int tid = threadIdx.x, ql = tid % 64, ks = tid / 64;
+  const int q = blockIdx.x * 64 + ql;
+  const int s = blockIdx.y;
+  const int k0 = blockIdx.z * KC;  // first latent coordinate of this pass
+  const long long r0 = (long long)s * a.rows_per_split;
+  long long r1 = r0 + a.rows_per_split;
+  if (r1 > a.B) r1 = a.B;
+
+  // decode the feature this thread owns:  F[b] = scale * A[b*sA] * (Bp ? Bp[b*sB] : 1)
+  const float* Ap = nullptr;
+  const float* Bp = nullptr;
+  long long sA = 0, sB = 0;
+  float scale = 1.f;
+  if (q < a.Q) {
+    int r = q;
+    if (r < (H + 1) * NP) {
+      const int m = r / NP, j = r % NP;
+      Ap = a.da + (long long)m * a.B * NP + j; sA = NP;
+    } else if ((r -= (H + 1) * NP) < so) {
+      Ap = a.du + r; sA = so;
+    } else if ((r -= so) < si * NP) {
+      const int i = r / NP, j = r % NP;
+      Ap = a.da + j; sA = NP; Bp = a.x + i; sB = si; scale = plan_omega(pl, 0);
+    } else {
+      r -= si * NP;
+      const int i = r / so, c = r % so;
+      Ap = a.save + (long long)H * a.B * NP + i; sA = NP; Bp = a.du + c; sB = so;
+    }
+  }
+  float acc[NIF_EDGE_KE];
+#pragma unroll
+  for (int e = 0; e < NIF_EDGE_KE; ++e) acc[e] = 0.f;
+
+  for (long long rb = r0; rb < r1; rb += RC) {
+    __syncthreads();
+    for (int idx = tid; idx < RC * KC; idx += 256) {
+      const int rr = idx / KC, kc = idx % KC;
+      const long long b = rb + rr;
+      const int kk = k0 + kc;
+      float v = 0.f;
+      if (b < r1) v = (kk < K) ? __ldg(&a.z[b * K + kk]) : (kk == K ? 1.f : 0.f);
+      zsm[rr][kc] = v;
+    }
+    __syncthreads();
+    if (Ap) {
+      const int nr = (int)((r1 - rb) < RC ? (r1 - rb) : RC);
+      for (int rr = 0; rr < nr; ++rr) {
+        const long long b = rb + rr;
+        float f = scale * __ldg(&Ap[b * sA]);
+        if (Bp) f *= __ldg(&Bp[b * sB]);
+#pragma unroll
+        for (int e = 0; e < NIF_EDGE_KE; ++e) acc[e] = fmaf(zsm[rr][ks + 4 * e], f, acc[e]);
+      }
+    }
+  }
+  if (q < a.Q) {
+#pragma unroll
+    for (int e = 0; e < NIF_EDGE_KE; ++e) {
+      const int kk = k0 + ks + 4 * e;
+      if (kk < K1) a.part[((long long)s * K1 + kk) * a.Q + q] = acc[e];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Keras 'mse' seed:  du = 2 (u - t) sw inv_gb / so ;  loss += sum_b sw[b] mean_c (u-t)^2 inv_gb
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) nif_mse_seed_kernel(long long B, int so, const float* __restrict__ u,
+                                                           const float* __restrict__ t, const float* __restrict__ sw,
+                                                           float inv_gb, float* __restrict__ du,
+                                                           float* __restrict__ part) {
+  float local = 0.f;
+  const float c2 = 2.f * inv_gb / so;
+  for (long long b = blockIdx.x * 256LL + threadIdx.x; b < B; b += 256LL * gridDim.x) {
+    const float w = sw ? sw[b] : 1.f;
+    float e2 = 0.f;
+    for (int c = 0; c < so; ++c) {
+      const float e = u[b * so + c] - t[b * so + c];
+      e2 = fmaf(e, e, e2);
+      du[b * so + c] = c2 * w * e;
+    }
+    local = fmaf(w * inv_gb / so, e2, local);
+  }
+  __shared__ float red[256];
+  red[threadIdx.x] = local;
+  __syncthreads();
+  for (int o = 128; o >= 1; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) part[blockIdx.x] = red[0];
+}
+__global__ void nif_loss_final_kernel(int nparts, const float* __restrict__ part, float* __restrict__ loss) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    float sacc = 0.f;
+    for (int i = 0; i < nparts; ++i) sacc += part[i];
+    *loss += sacc;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+int nif_unpack_grad_impl(const Plan& pl, int S_h, const float* part_h, int S_e, const float* part_e, int Q,
+                         float* dw_h, float* db_h, float beta, cudaStream_t st);
+
+struct GradWs {
+  long long da, du, part_h, part_e, loss_part, total;
+  int S_h, S_e, Q;
+  long long rows_h, rows_e;
+};
+
+static long long round_up(long long v, long long m) { return (v + m - 1) / m * m; }
+
+GradWs nif_grad_ws_layout(const Plan& pl, long long B) {
+  GradWs w;
+  const long long NP = pl.NP, K1 = pl.K + 1, H = pl.H;
+  w.Q = (int)((H + 1) * NP + pl.so + pl.si * NP + NP * pl.so);
+  // batch splits: enough CTAs to fill the chip, but at least 256 rows per split
+  const long long TS = NP >= 64 ? 64 : 32;
+  const long long base_h = H * ((K1 + 3) / 4) * (NP / TS) * (NP / TS);
+  long long S_h = base_h > 0 ? (2 * 148 + base_h - 1) / base_h : 1;
+  long long maxs = (B + 255) / 256;
+  if (maxs < 1) maxs = 1;
+  if (S_h > maxs) S_h = maxs;
+  if (S_h < 1) S_h = 1;
+  w.rows_h = round_up((B + S_h - 1) / S_h, 32);
+  if (w.rows_h < 32) w.rows_h = 32;
+  w.S_h = (int)((B + w.rows_h - 1) / w.rows_h);
+  if (w.S_h < 1) w.S_h = 1;
+  const long long base_e = (w.Q + 63) / 64 * ((K1 + 67) / 68);
+  long long S_e = (4 * 148 + base_e - 1) / base_e;
+  if (S_e > maxs) S_e = maxs;
+  if (S_e < 1) S_e = 1;
+  w.rows_e = round_up((B + S_e - 1) / S_e, 64);
+  if (w.rows_e < 64) w.rows_e = 64;
+  w.S_e = (int)((B + w.rows_e - 1) / w.rows_e);
+  if (w.S_e < 1) w.S_e = 1;
+  long long off = 0;
+  w.da = off; off += round_up((H + 1) * B * NP, 4);
+  w.du = off; off += round_up(B * pl.so, 4);
+  w.part_h = off; off += round_up((long long)w.S_h * H * K1 * NP * NP, 4);
+  w.part_e = off; off += round_up((long long)w.S_e * K1 * w.Q, 4);
+  w.loss_part = off; off += 1024;
+  w.total = off;
+  return w;
+}
+
+int nif_backward_impl(const Plan& pl, long long B, const float* z, const float* x, const float* packed,
+                      const float* save, const float* du, float* dw_h, float* db_h, float beta, float* dz,
+                      float* ws, cudaStream_t st) {
+  const GradWs w = nif_grad_ws_layout(pl, B);
+  if (B <= 0) return NIF_OK;
+  BwdArgs a;
+  a.B = B;
+  a.z = z; a.x = x; a.packed = packed; a.save = save; a.du = du;
+  a.da = ws + w.da;
+  a.dz = dz;
+  int rc;
+  switch (pl.NP) {
+    case 32: a.total_tiles = (B + Cfg32::TB - 1) / Cfg32::TB; rc = launch_bwd_data<Cfg32>(pl, a, st); break;
+    case 64: a.total_tiles = (B + Cfg64::TB - 1) / Cfg64::TB; rc = launch_bwd_data<Cfg64>(pl, a, st); break;
+    case 128: a.total_tiles = (B + Cfg128::TB - 1) / Cfg128::TB; rc = launch_bwd_data<Cfg128>(pl, a, st); break;
+    default: nif_set_error("unsupported padded width %d", pl.NP); return NIF_E_UNSUPPORTED;
+  }
+  if (rc != NIF_OK) return rc;
+
+  if (pl.H > 0) {
+    WgtArgs g;
+    g.B = B; g.rows_per_split = w.rows_h; g.S = w.S_h;
+    g.z = z; g.save = save; g.da = ws + w.da; g.part = ws + w.part_h;
+    const int K1 = pl.K + 1;
+    if (pl.NP >= 64) {
+      const int nb = pl.NP / 64;
+      dim3 grid((unsigned)(pl.H * ((K1 + 3) / 4) * nb * nb), (unsigned)w.S_h);
+      nif_bwd_weight_kernel<64><<<grid, 256, 0, st>>>(pl, g);
+    } else {
+      dim3 grid((unsigned)(pl.H * ((K1 + 3) / 4)), (unsigned)w.S_h);
+      nif_bwd_weight_kernel<32><<<grid, 64, 0, st>>>(pl, g);
+    }
+    NIF_CUDA_CHECK(cudaGetLastError());
+  }
+  {
+    EdgeArgs e;
+    e.B = B; e.rows_per_split = w.rows_e; e.S = w.S_e; e.Q = w.Q;
+    e.z = z; e.x = x; e.save = save; e.da = ws + w.da; e.du = du; e.part = ws + w.part_e;
+    dim3 grid((unsigned)((w.Q + 63) / 64), (unsigned)w.S_e, (unsigned)((pl.K + 1 + 67) / 68));
+    nif_bwd_edge_kernel<<<grid, 256, 0, st>>>(pl, e);
+    NIF_CUDA_CHECK(cudaGetLastError());
+  }
+  return nif_unpack_grad_impl(pl, w.S_h, ws + w.part_h, w.S_e, ws + w.part_e, w.Q, dw_h, db_h, beta, st);
+}
+
+int nif_mse_backward_impl(const Plan& pl, long long B, const float* z, const float* x, const float* packed,
+                          const float* u, const float* save, const float* target, const float* sw, float inv_gb,
+                          float* loss, float* dw_h, float* db_h, float beta, float* dz, float* ws,
+                          cudaStream_t st) {
+  const GradWs w = nif_grad_ws_layout(pl, B);
+  if (B <= 0) return NIF_OK;
+  int nblk = (int)((B + 255) / 256);
+  if (nblk > 1024) nblk = 1024;
+  nif_mse_seed_kernel<<<nblk, 256, 0, st>>>(B, pl.so, u, target, sw, inv_gb, ws + w.du, ws + w.loss_part);
+  NIF_CUDA_CHECK(cudaGetLastError());
+  nif_loss_final_kernel<<<1, 32, 0, st>>>(nblk, ws + w.loss_part, loss);
+  NIF_CUDA_CHECK(cudaGetLastError());
+  return nif_backward_impl(pl, B, z, x, packed, save, ws + w.du, dw_h, db_h, beta, dz, ws, st);
+}

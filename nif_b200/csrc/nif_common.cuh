@@ -1,0 +1,136 @@
+// nif_b200 — shared device/host definitions for the fused NIF kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/nif_b200.h"
+
+#define NIF_MAX_SO 8        // max ShapeNet output width handled in registers
+#define NIF_MAX_SI 8        // max ShapeNet input width
+#define NIF_MAX_DIR 4       // max tangent directions per launch
+
+// ---------------------------------------------------------------------------------------------
+// Plan: everything the kernels need to know about one descriptor, computed on the host.
+//
+// Packed weight image (one per group), all fp32, every section 16-byte aligned:
+//   MH  [H][K+1][NP][NP]   hidden matrices, M[kappa][i][j]  (i = input index, j = output index)
+//   MHT [H][K+1][NP][NP]   the same, transposed per matrix: MT[kappa][j][i]   (for the reverse pass)
+//   M0  [K+1][si][NP]      first matrix
+//   ML  [K+1][NP][so]      last matrix
+//   C   [Lm][K+1][NP]      bias rows of every layer (last layer uses the first `so` entries)
+// kappa < K indexes rows of w_h; kappa == K is the row taken from b_h (its latent coordinate is 1).
+// Padding (i,j >= n) is zero.
+// ---------------------------------------------------------------------------------------------
+struct Plan {
+  int variant, act, si, so, n, l, K;
+  int H;    // hidden matrices (l or 2l)
+  int Lm;   // total matrices H + 2
+  int NP;   // padded width
+  int P;    // po_dim
+  float omega0;
+  long long off_MH, off_MHT, off_M0, off_ML, off_C, packed_floats;
+};
+
+__host__ __device__ inline int plan_w_off(const Plan& p, int m) {  // reference column offset of matrix m
+  if (m == 0) return 0;
+  if (m <= p.H) return p.si * p.n + (m - 1) * p.n * p.n;
+  return p.si * p.n + p.H * p.n * p.n;
+}
+__host__ __device__ inline int plan_b_off(const Plan& p, int m) {  // reference column offset of bias m
+  int nW = p.si * p.n + p.H * p.n * p.n + p.n * p.so;
+  return nW + m * p.n;
+}
+
+// layer semantics shared by forward and backward ------------------------------------------------
+// out_m = alpha * act(pre_m) + (residual), pre_m = omega * lin + bias
+__host__ __device__ inline float plan_omega(const Plan& p, int m) {
+  return (p.variant == NIF_VARIANT_NIF || m == p.Lm - 1) ? 1.0f : p.omega0;
+}
+__host__ __device__ inline float plan_alpha(const Plan& p, int m) {
+  // second layer of a res-block: 0.5 * (u + sin(...))
+  return (p.variant == NIF_VARIANT_SIREN_RES && m >= 2 && m <= p.H && (m & 1) == 0) ? 0.5f : 1.0f;
+}
+// residual bookkeeping: 0 none, 1 "out += in" (NIF hidden), 2 "remember input" (first of res-block),
+// 3 "out += 0.5 * remembered" (second of res-block)
+__host__ __device__ inline int plan_res(const Plan& p, int m) {
+  if (m < 1 || m > p.H) return 0;
+  if (p.variant == NIF_VARIANT_NIF) return 1;
+  if (p.variant == NIF_VARIANT_SIREN_RES) return (m & 1) ? 2 : 3;
+  return 0;
+}
+
+// activations -----------------------------------------------------------------------------------
+__device__ __forceinline__ float sigmoidf_(float v) { return 1.0f / (1.0f + expf(-v)); }
+
+// value and first derivative
+__device__ __forceinline__ void act_fd(int act, float v, float& f, float& d) {
+  switch (act) {
+    case NIF_ACT_SINE: { float s, c; sincosf(v, &s, &c); f = s; d = c; } break;
+    case NIF_ACT_SWISH: { float sg = sigmoidf_(v); f = v * sg; d = sg * (1.0f + v * (1.0f - sg)); } break;
+    case NIF_ACT_TANH: { float t = tanhf(v); f = t; d = 1.0f - t * t; } break;
+    case NIF_ACT_RELU: f = v > 0.f ? v : 0.f; d = v > 0.f ? 1.f : 0.f; break;
+    case NIF_ACT_SIGMOID: { float sg = sigmoidf_(v); f = sg; d = sg * (1.0f - sg); } break;
+    default: f = v; d = 1.0f; break;
+  }
+}
+__device__ __forceinline__ float act_f(int act, float v) {
+  switch (act) {
+    case NIF_ACT_SINE: return sinf(v);
+    case NIF_ACT_SWISH: return v * sigmoidf_(v);
+    case NIF_ACT_TANH: return tanhf(v);
+    case NIF_ACT_RELU: return v > 0.f ? v : 0.f;
+    case NIF_ACT_SIGMOID: return sigmoidf_(v);
+    default: return v;
+  }
+}
+
+// PTX helpers: mbarrier + 1-D bulk async copy (TMA unit, no tensor map needed) --------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// global -> shared bulk copy; bytes multiple of 16, both addresses 16-byte aligned
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+// host-side error plumbing ------------------------------------------------------------------------
+void nif_set_error(const char* fmt, ...);
+int nif_make_plan(const nif_desc_t* d, Plan* out);
+
+#define NIF_CUDA_CHECK(expr)                                                            \
+  do {                                                                                  \
+    cudaError_t _e = (expr);                                                            \
+    if (_e != cudaSuccess) {                                                            \
+      nif_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return NIF_E_CUDA;                                                                \
+    }                                                                                   \
+  } while (0)

@@ -1,0 +1,167 @@
+// Plan construction, weight packing (reference column layout -> kernel layout) and gradient
+// un-packing (kernel partials -> reference layout).
+//
+// The reference slices pnet_output[:, a:b] into per-sample matrices (nif/model.py:253-300,
+// 769-846, 883-933).  Here the same offsets are applied ONCE to the shared [K,P] / [P] parameters.
+#include <cstdarg>
+#include <cstdio>
+#include "nif_common.cuh"
+
+static thread_local char g_err[512] = "";
+void nif_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+extern "C" const char* nif_last_error(void) { return g_err; }
+extern "C" int nif_version(void) { return 100; }
+
+static long long up4(long long v) { return (v + 3) / 4 * 4; }
+
+int nif_make_plan(const nif_desc_t* d, Plan* out) {
+  if (!d) { nif_set_error("null descriptor"); return NIF_E_BAD_DESC; }
+  if (d->variant < 0 || d->variant > 2) { nif_set_error("variant %d not in {0,1,2}", d->variant); return NIF_E_BAD_DESC; }
+  if (d->si < 1 || d->si > NIF_MAX_SI) { nif_set_error("si=%d outside [1,%d]", d->si, NIF_MAX_SI); return NIF_E_BAD_DESC; }
+  if (d->so < 1 || d->so > NIF_MAX_SO) { nif_set_error("so=%d outside [1,%d]", d->so, NIF_MAX_SO); return NIF_E_BAD_DESC; }
+  if (d->n < 1 || d->n > 128) { nif_set_error("units=%d outside [1,128]", d->n); return NIF_E_BAD_DESC; }
+  if (d->l < 0 || d->l > 64) { nif_set_error("nlayers=%d outside [0,64]", d->l); return NIF_E_BAD_DESC; }
+  if (d->K < 0 || d->K > 256) { nif_set_error("latent_dim=%d outside [0,256]", d->K); return NIF_E_BAD_DESC; }
+  if (d->act < 0 || d->act > NIF_ACT_SIGMOID) { nif_set_error("activation id %d unknown", d->act); return NIF_E_BAD_DESC; }
+  if (d->dtype_compute != 0) { nif_set_error("dtype_compute=%d: only the fp32 path is built", d->dtype_compute); return NIF_E_UNSUPPORTED; }
+  Plan p;
+  p.variant = d->variant;
+  p.act = d->variant == NIF_VARIANT_NIF ? d->act : NIF_ACT_SINE;
+  p.si = d->si; p.so = d->so; p.n = d->n; p.l = d->l; p.K = d->K;
+  p.omega0 = d->variant == NIF_VARIANT_NIF ? 1.0f : d->omega0;
+  p.H = d->variant == NIF_VARIANT_SIREN_RES ? 2 * d->l : d->l;
+  p.Lm = p.H + 2;
+  p.NP = d->n <= 32 ? 32 : (d->n <= 64 ? 64 : 128);
+  p.P = p.H * p.n * p.n + (p.si + p.so + 1 + p.H) * p.n + p.so;
+  const long long K1 = p.K + 1, NP = p.NP;
+  long long off = 0;
+  p.off_MH = off;  off += up4((long long)p.H * K1 * NP * NP);
+  p.off_MHT = off; off += up4((long long)p.H * K1 * NP * NP);
+  p.off_M0 = off;  off += up4(K1 * p.si * NP);
+  p.off_ML = off;  off += up4(K1 * NP * p.so);
+  p.off_C = off;   off += up4((long long)p.Lm * K1 * NP);
+  p.packed_floats = (off + 31) / 32 * 32;  // keep every image 128-byte aligned
+  *out = p;
+  return NIF_OK;
+}
+
+// value of [w_h; b_h] at (kappa, reference column col) for group g
+__device__ __forceinline__ float src_at(const Plan& pl, const float* __restrict__ w_h, const float* __restrict__ b_h,
+                                        long long g, int kappa, int col) {
+  return (kappa < pl.K) ? w_h[(long long)kappa * pl.P + col] : b_h[g * pl.P + col];
+}
+
+__global__ void __launch_bounds__(256) nif_pack_kernel(const Plan pl, long long G, const float* __restrict__ w_h,
+                                                       const float* __restrict__ b_h, float* __restrict__ packed) {
+  const long long total = G * pl.packed_floats;
+  const int K1 = pl.K + 1, NP = pl.NP, n = pl.n, H = pl.H;
+  for (long long e = blockIdx.x * 256LL + threadIdx.x; e < total; e += 256LL * gridDim.x) {
+    const long long g = e / pl.packed_floats;
+    long long r = e - g * pl.packed_floats;
+    float v = 0.f;
+    if (r < pl.off_MHT) {  // MH [H][K1][NP][NP]
+      if (r < (long long)H * K1 * NP * NP) {
+        const int j = r % NP; r /= NP;
+        const int i = r % NP; r /= NP;
+        const int kk = r % K1; const int h = (int)(r / K1);
+        if (i < n && j < n) v = src_at(pl, w_h, b_h, g, kk, plan_w_off(pl, h + 1) + i * n + j);
+      }
+    } else if (r < pl.off_M0) {  // MHT [H][K1][NP(j)][NP(i)]
+      r -= pl.off_MHT;
+      if (r < (long long)H * K1 * NP * NP) {
+        const int i = r % NP; r /= NP;
+        const int j = r % NP; r /= NP;
+        const int kk = r % K1; const int h = (int)(r / K1);
+        if (i < n && j < n) v = src_at(pl, w_h, b_h, g, kk, plan_w_off(pl, h + 1) + i * n + j);
+      }
+    } else if (r < pl.off_ML) {  // M0 [K1][si][NP]
+      r -= pl.off_M0;
+      if (r < (long long)K1 * pl.si * NP) {
+        const int j = r % NP; r /= NP;
+        const int i = r % pl.si; const int kk = (int)(r / pl.si);
+        if (j < n) v = src_at(pl, w_h, b_h, g, kk, i * n + j);
+      }
+    } else if (r < pl.off_C) {  // ML [K1][NP][so]
+      r -= pl.off_ML;
+      if (r < (long long)K1 * NP * pl.so) {
+        const int c = r % pl.so; r /= pl.so;
+        const int i = r % NP; const int kk = (int)(r / NP);
+        if (i < n) v = src_at(pl, w_h, b_h, g, kk, plan_w_off(pl, H + 1) + i * pl.so + c);
+      }
+    } else {  // C [Lm][K1][NP]
+      r -= pl.off_C;
+      if (r < (long long)pl.Lm * K1 * NP) {
+        const int j = r % NP; r /= NP;
+        const int kk = r % K1; const int m = (int)(r / K1);
+        const int width = (m == pl.Lm - 1) ? pl.so : n;
+        if (j < width) v = src_at(pl, w_h, b_h, g, kk, plan_b_off(pl, m) + j);
+      }
+    }
+    packed[e] = v;
+  }
+}
+
+int nif_pack_impl(const Plan& pl, long long G, const float* w_h, const float* b_h, float* packed, cudaStream_t st) {
+  const long long total = G * pl.packed_floats;
+  long long nblk = (total + 255) / 256;
+  if (nblk > 148 * 16) nblk = 148 * 16;
+  nif_pack_kernel<<<(unsigned)nblk, 256, 0, st>>>(pl, G, w_h, b_h, packed);
+  NIF_CUDA_CHECK(cudaGetLastError());
+  return NIF_OK;
+}
+
+// one thread per (kappa, reference column): sum the batch-split partials, write dw_h / db_h
+__global__ void __launch_bounds__(256) nif_unpack_grad_kernel(const Plan pl, int S_h, const float* __restrict__ part_h,
+                                                              int S_e, const float* __restrict__ part_e, int Q,
+                                                              float* __restrict__ dw_h, float* __restrict__ db_h,
+                                                              float beta) {
+  const int K1 = pl.K + 1, NP = pl.NP, n = pl.n, H = pl.H, P = pl.P;
+  const long long total = (long long)K1 * P;
+  for (long long e = blockIdx.x * 256LL + threadIdx.x; e < total; e += 256LL * gridDim.x) {
+    const int kk = (int)(e / P);
+    const int col = (int)(e - (long long)kk * P);
+    const int w_hid0 = pl.si * n, w_last0 = w_hid0 + H * n * n, b0 = w_last0 + n * pl.so;
+    float v = 0.f;
+    if (col >= w_hid0 && col < w_last0) {
+      const int r = col - w_hid0;
+      const int h = r / (n * n), ij = r % (n * n), i = ij / n, j = ij % n;
+      const long long stride = (long long)H * K1 * NP * NP;
+      const float* src = part_h + (((long long)h * K1 + kk) * NP + i) * NP + j;
+      for (int s = 0; s < S_h; ++s) v += src[s * stride];
+    } else {
+      int q;
+      if (col < w_hid0) {  // first matrix
+        const int i = col / n, j = col % n;
+        q = (H + 1) * NP + pl.so + i * NP + j;
+      } else if (col < b0) {  // last matrix
+        const int r = col - w_last0;
+        q = (H + 1) * NP + pl.so + pl.si * NP + r;  // r = i * so + c
+      } else {
+        const int r = col - b0;
+        const int m = r / n;
+        if (m <= H) q = m * NP + (r - m * n);
+        else q = (H + 1) * NP + (r - (H + 1) * n);
+      }
+      const long long stride = (long long)K1 * Q;
+      const float* src = part_e + (long long)kk * Q + q;
+      for (int s = 0; s < S_e; ++s) v += src[s * stride];
+    }
+    float* dst = (kk < pl.K) ? &dw_h[(long long)kk * P + col] : &db_h[col];
+    *dst = (beta != 0.f) ? (*dst * beta + v) : v;
+  }
+}
+
+int nif_unpack_grad_impl(const Plan& pl, int S_h, const float* part_h, int S_e, const float* part_e, int Q,
+                         float* dw_h, float* db_h, float beta, cudaStream_t st) {
+  const long long total = (long long)(pl.K + 1) * pl.P;
+  long long nblk = (total + 255) / 256;
+  if (nblk > 148 * 16) nblk = 148 * 16;
+  nif_unpack_grad_kernel<<<(unsigned)nblk, 256, 0, st>>>(pl, S_h, part_h, S_e, part_e, Q, dw_h, db_h, beta);
+  NIF_CUDA_CHECK(cudaGetLastError());
+  return NIF_OK;
+}

@@ -1,0 +1,399 @@
+"""Host-side mirror of `nif/model.py` (pswpswpsw/nif): NIF and NIFMultiScale.
+
+Same constructor arguments, cfg-dict schema, method names, validation errors and variable names
+as the reference (nif/model.py:48-480, 483-986), but nothing here builds a graph: the objects own
+one flat fp32 parameter buffer in HBM and hand the hot path to libnif_b200.so.  The (B, po_dim)
+tensor `pnet_output` of the reference is never formed unless the caller explicitly asks for it
+through model_p_to_w() / model_lr_to_w().
+"""
+from __future__ import annotations
+
+import json
+import math
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from ._lib import ACT, NifError
+from .keras_like import Model
+from .ops import FusedShapeNet
+
+__all__ = ["NIF", "NIFMultiScale"]
+
+_POLICIES = ("float32", "mixed_float16", "mixed_bfloat16")
+
+
+def _trunc_normal(shape, std, gen):
+    t = torch.empty(shape, dtype=torch.float64)
+    torch.nn.init.trunc_normal_(t, 0.0, std, -2 * std, 2 * std, generator=gen)
+    return t.float()
+
+
+def _uniform(shape, bound, gen):
+    b = torch.as_tensor(bound, dtype=torch.float64)
+    return ((torch.rand(shape, dtype=torch.float64, generator=gen) * 2 - 1) * b).float()
+
+
+class NIF(object):
+    """Neural Implicit Flow with a swish/tanh/... ShapeNet with residual hidden layers
+    (reference: class NIF, nif/model.py:48-480).
+
+    Args follow the reference: cfg_shape_net {input_dim, output_dim, units, nlayers, activation},
+    cfg_parameter_net {input_dim, latent_dim, units, nlayers, activation, [l1_reg|l2_reg]},
+    mixed_policy (Keras policy name).  Extra keyword-only arguments are ours: `seed` for the
+    initialisers and `device`.
+    """
+
+    _variant = "nif"
+
+    def __init__(self, cfg_shape_net, cfg_parameter_net, mixed_policy="float32", *, seed: Optional[int] = None,
+                 device=None):
+        self.cfg_shape_net = cfg_shape_net
+        self.cfg_parameter_net = cfg_parameter_net
+        self._validate_cfg(cfg_shape_net, cfg_parameter_net)
+        self.si_dim = cfg_shape_net["input_dim"]
+        self.so_dim = cfg_shape_net["output_dim"]
+        self.n_sx = cfg_shape_net["units"]
+        self.l_sx = cfg_shape_net["nlayers"]
+        self.pi_dim = cfg_parameter_net["input_dim"]
+        self.pi_hidden = cfg_parameter_net["latent_dim"]
+        self.n_st = cfg_parameter_net["units"]
+        self.l_st = cfg_parameter_net["nlayers"]
+        # regularisation knobs (nif/model.py:95-125)
+        self.p_jac_reg = cfg_parameter_net.get("jac_reg", None)
+        self.p_l1_reg = cfg_parameter_net.get("l1_reg", None)
+        self.p_l2_reg = cfg_parameter_net.get("l2_reg", None)
+        self.p_act_l1_reg = cfg_parameter_net.get("act_l1_reg", None)
+        self.p_act_l2_reg = cfg_parameter_net.get("act_l2_reg", None)
+        if isinstance(self.p_jac_reg, (float, int)) or isinstance(self.p_act_l1_reg, (float, int)) or isinstance(
+                self.p_act_l2_reg, (float, int)):
+            raise NotImplementedError("jac_reg / act_l1_reg / act_l2_reg are outside the B200 hot-path scope")
+        if mixed_policy not in _POLICIES:
+            raise ValueError(f"mixed_policy must be one of {_POLICIES} (float64 has no GPU path)")
+        self.mixed_policy_name = mixed_policy
+        self.variable_Dtype = "float32"
+        self.compute_Dtype = "float32"  # the fp32 kernels serve every policy in this build
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
+        self.device = torch.device(device)
+        self._gen = torch.Generator().manual_seed(int(seed) if seed is not None else int(torch.seed() % (2**31)))
+        self.po_dim = self._po_dim()
+        self._engine = None
+        self._init_parameters()
+
+    # ---- configuration ---------------------------------------------------------------------------
+    def _validate_cfg(self, cfg_shape_net, cfg_parameter_net):
+        if not isinstance(cfg_parameter_net, dict):
+            raise TypeError("cfg_parameter_net must be a dictionary")
+        if not isinstance(cfg_shape_net, dict):
+            raise TypeError("cfg_shape_net must be a dictionary")
+        act = cfg_shape_net.get("activation")
+        if act not in ACT:
+            raise ValueError(f"cfg_shape_net['activation']={act!r} is not supported by the fused kernels {sorted(k for k in ACT if k)}")
+
+    def _po_dim(self) -> int:
+        # nif/model.py:169-173
+        return self.l_sx * self.n_sx**2 + (self.si_dim + self.so_dim + 1 + self.l_sx) * self.n_sx + self.so_dim
+
+    @property
+    def _omega0(self) -> float:
+        return 1.0
+
+    @property
+    def engine(self) -> FusedShapeNet:
+        if self._engine is None:
+            self._engine = FusedShapeNet(self._variant, self.si_dim, self.so_dim, self.n_sx, self.l_sx, self.pi_hidden,
+                                         self.cfg_shape_net.get("activation"), self._omega0)
+            if self._engine.po_dim != self.po_dim:
+                raise NifError("po_dim mismatch between host and library")
+        return self._engine
+
+    # ---- parameters --------------------------------------------------------------------------------
+    def _trunk_layout(self) -> List[Tuple[str, Tuple[int, ...]]]:
+        """[(variable name, shape)] in creation order; names follow nif/model.py:186-229."""
+        L = [("first_dense_pnet/kernel", (self.pi_dim, self.n_st)), ("first_dense_pnet/bias", (self.n_st,))]
+        for i in range(self.l_st):
+            q = f"hidden_mlpshortcut_pnet_{i}"
+            L += [(q + "/kernel", (self.n_st, self.n_st)), (q + "/bias", (self.n_st,))]
+        L += [("bottleneck_pnet/kernel", (self.n_st, self.pi_hidden)), ("bottleneck_pnet/bias", (self.pi_hidden,))]
+        return L
+
+    _last_names = ("last_pnet/kernel", "last_pnet/bias")
+
+    def _draw(self, name: str, shape) -> torch.Tensor:
+        # every Dense of class NIF: TruncatedNormal(stddev=0.1) kernel and bias (nif/model.py:181-182, 222-223)
+        return _trunc_normal(shape, 0.1, self._gen)
+
+    def _init_parameters(self):
+        layout = self._trunk_layout() + [(self._last_names[0], (self.pi_hidden, self.po_dim)),
+                                         (self._last_names[1], (self.po_dim,))]
+        self._layout: Dict[str, Tuple[int, Tuple[int, ...]]] = {}
+        off = 0
+        for name, shape in layout:
+            n = int(np.prod(shape))
+            self._layout[name] = (off, shape)
+            off += (n + 3) // 4 * 4  # keep every variable 16-byte aligned inside the flat buffer
+        self.n_flat = off
+        host = torch.zeros(off, dtype=torch.float32)
+        for name, shape in layout:
+            o, _ = self._layout[name]
+            host[o:o + int(np.prod(shape))] = self._draw(name, shape).reshape(-1)
+        self.theta = host.to(self.device)
+        self.grad = torch.zeros_like(self.theta)
+        self._views: Dict[str, torch.Tensor] = {}
+        self._gviews: Dict[str, torch.Tensor] = {}
+        for name, (o, shape) in self._layout.items():
+            n = int(np.prod(shape))
+            v = self.theta[o:o + n].view(shape)
+            v.requires_grad_(True)
+            g = self.grad[o:o + n].view(shape)
+            v.grad = g
+            self._views[name], self._gviews[name] = v, g
+
+    @property
+    def variables(self) -> Dict[str, torch.Tensor]:
+        """name -> tensor view into the flat parameter buffer (shared by every derived model, like the
+        shared layer objects of the reference, tutorial/1_simple_1d_wave.ipynb cell 22)."""
+        return self._views
+
+    @property
+    def trainable_variables(self) -> List[torch.Tensor]:
+        return list(self._views.values())
+
+    def count_params(self) -> int:
+        return sum(int(np.prod(s)) for _, s in self._layout.values())
+
+    def to(self, device):
+        device = torch.device(device)
+        if device == self.device:
+            return self
+        data = {k: v.detach().cpu().clone() for k, v in self._views.items()}
+        self.device = device
+        self.theta = torch.zeros(self.n_flat, dtype=torch.float32, device=device)
+        self.grad = torch.zeros_like(self.theta)
+        self._views, self._gviews = {}, {}
+        for name, (o, shape) in self._layout.items():
+            n = int(np.prod(shape))
+            self.theta[o:o + n] = data[name].reshape(-1).to(device)
+            v = self.theta[o:o + n].view(shape)
+            v.requires_grad_(True)
+            g = self.grad[o:o + n].view(shape)
+            v.grad = g
+            self._views[name], self._gviews[name] = v, g
+        self._engine = None
+        return self
+
+    def set_weights(self, named: Dict[str, "np.ndarray"]):
+        with torch.no_grad():
+            for k, a in named.items():
+                if k not in self._views:
+                    raise KeyError(f"unknown variable {k!r}")
+                t = torch.as_tensor(np.asarray(a), dtype=torch.float32)
+                if tuple(t.shape) != tuple(self._views[k].shape):
+                    raise ValueError(f"{k}: shape {tuple(t.shape)} != {tuple(self._views[k].shape)}")
+                self._views[k].copy_(t.to(self.device))
+
+    def get_weights(self) -> Dict[str, "np.ndarray"]:
+        return {k: v.detach().cpu().numpy().copy() for k, v in self._views.items()}
+
+    # ---- ParameterNet trunk (everything before the last linear; plain torch ops) ----------------------
+    def _act(self, name):
+        if name == "swish":
+            return lambda v: v * torch.sigmoid(v)
+        if name == "tanh":
+            return torch.tanh
+        if name == "relu":
+            return torch.relu
+        if name == "sigmoid":
+            return torch.sigmoid
+        if name in (None, "linear"):
+            return lambda v: v
+        raise ValueError(f"ParameterNet activation {name!r} is not supported")
+
+    def _latent(self, input_p: torch.Tensor) -> torch.Tensor:
+        """_call_parameter_net up to the bottleneck (nif/model.py:326-343; MLP_SimpleShortCut mlp.py:148-160)."""
+        V = self._views
+        f = self._act(self.cfg_parameter_net["activation"])
+        h = f(input_p @ V["first_dense_pnet/kernel"] + V["first_dense_pnet/bias"])
+        for i in range(self.l_st):
+            q = f"hidden_mlpshortcut_pnet_{i}"
+            h = h + f(h @ V[q + "/kernel"] + V[q + "/bias"])
+        return h @ V["bottleneck_pnet/kernel"] + V["bottleneck_pnet/bias"]
+
+    @property
+    def w_h(self) -> torch.Tensor:
+        return self._views[self._last_names[0]]
+
+    @property
+    def b_h(self) -> torch.Tensor:
+        return self._views[self._last_names[1]]
+
+    def _kernel_regulariser(self) -> Tuple[float, float]:
+        """(l1, l2) applied to every ParameterNet kernel and bias (nif/model.py:107-117); l2 wins."""
+        if isinstance(self.p_l2_reg, (float, int)):
+            return 0.0, float(self.p_l2_reg)
+        if isinstance(self.p_l1_reg, (float, int)):
+            return float(self.p_l1_reg), 0.0
+        return 0.0, 0.0
+
+    # ---- the reference's public surface ------------------------------------------------------------------
+    def call(self, inputs, training=None, mask=None) -> torch.Tensor:
+        """Forward pass on a (B, pi_dim + si_dim) batch (nif/model.py:130-154 / 510-539)."""
+        return self.model()(inputs, training=bool(training))
+
+    def build(self) -> Model:
+        """nif/model.py:345-377 (jac_reg is rejected in __init__, so this is `.model()`)."""
+        return self.model()
+
+    def model(self) -> Model:
+        return Model(self, "full")
+
+    def model_p_to_w(self) -> Model:
+        return Model(self, "p_to_w")
+
+    def model_p_to_lr(self) -> Model:
+        return Model(self, "p_to_lr")
+
+    def model_lr_to_w(self) -> Model:
+        return Model(self, "lr_to_w")
+
+    def model_x_to_u_given_w(self) -> Model:
+        return Model(self, "x_to_u_given_w")
+
+    def save_config(self, filename="config.json"):
+        """nif/model.py:466-480: the two cfg dicts and the policy name, as JSON."""
+        config = {
+            "cfg_shape_net": self.cfg_shape_net,
+            "cfg_parameter_net": self.cfg_parameter_net,
+            "mixed_policy": self.mixed_policy_name,
+        }
+        with open(filename, "w") as write_file:
+            json.dump(config, write_file, indent=4)
+
+
+class NIFMultiScale(NIF):
+    """SIREN ShapeNet (omega_0-scaled sine, optional 2-layer res-blocks) with a swish-MLP or SIREN
+    ParameterNet (reference: class NIFMultiScale, nif/model.py:483-986)."""
+
+    def _validate_cfg(self, cfg_shape_net, cfg_parameter_net):
+        # same checks and messages as nif/model.py:555-587
+        if not isinstance(cfg_parameter_net, dict):
+            raise TypeError("cfg_parameter_net must be a dictionary")
+        if not isinstance(cfg_shape_net, dict):
+            raise TypeError("cfg_shape_net must be a dictionary")
+        assert "use_resblock" in cfg_shape_net.keys(), "`use_resblock` should be in cfg_shape_net"
+        assert type(cfg_shape_net["use_resblock"]) == bool, "cfg_shape_net['use_resblock'] must be a bool"
+        conn = cfg_shape_net.get("connectivity")
+        if conn == "last_layer":
+            raise NotImplementedError("connectivity='last_layer' (NIFMultiScaleLastLayerParameterized) is outside the hot path")
+        if conn != "full":
+            raise ValueError("cfg_shape_net missing correct `connectivity`")
+        self._variant = "siren_res" if cfg_shape_net["use_resblock"] else "siren"
+
+    def _po_dim(self) -> int:
+        # nif/model.py:572-582
+        h = 2 * self.l_sx if self.cfg_shape_net["use_resblock"] else self.l_sx
+        return h * self.n_sx**2 + (self.si_dim + self.so_dim + 1 + h) * self.n_sx + self.so_dim
+
+    @property
+    def _omega0(self) -> float:
+        return float(self.cfg_shape_net["omega_0"])
+
+    _last_names = ("HyperLinearForSIREN_w", "HyperLinearForSIREN_b")
+
+    @property
+    def _sine_trunk(self) -> bool:
+        return self.cfg_parameter_net["activation"] == "sine"
+
+    def _trunk_layout(self):
+        p = self.cfg_parameter_net
+        res = bool(p.get("use_resblock", False))
+        L = []
+        if self._sine_trunk:  # nif/model.py:591-648
+            L += [("siren_first_pnet_w", (self.pi_dim, self.n_st)), ("siren_first_pnet_b", (self.n_st,))]
+            for i in range(self.l_st):
+                if res:
+                    q = f"siren_hidden_resblock_pnet_{i}"
+                    L += [(q + "_w", (self.n_st, self.n_st)), (q + "_b", (self.n_st,)),
+                          (q + "_w2", (self.n_st, self.n_st)), (q + "_b2", (self.n_st,))]
+                else:
+                    q = f"siren_hidden_pnet_{i}"
+                    L += [(q + "_w", (self.n_st, self.n_st)), (q + "_b", (self.n_st,))]
+            L += [("siren_bottleneck_pnet_w", (self.n_st, self.pi_hidden)), ("siren_bottleneck_pnet_b", (self.pi_hidden,))]
+        else:  # nif/model.py:665-720
+            L += [("mlp_first_pnet/kernel", (self.pi_dim, self.n_st)), ("mlp_first_pnet/bias", (self.n_st,))]
+            for i in range(self.l_st):
+                if res:
+                    q = f"mlp_hidden_resblock_pnet_{i}"
+                    L += [(q + "_dense_1/kernel", (self.n_st, self.n_st)), (q + "_dense_1/bias", (self.n_st,)),
+                          (q + "_dense_2/kernel", (self.n_st, self.n_st)), (q + "_dense_2/bias", (self.n_st,))]
+                else:
+                    q = f"mlp_hidden_pnet_{i}"
+                    L += [(q + "/kernel", (self.n_st, self.n_st)), (q + "/bias", (self.n_st,))]
+            L += [("bottleneck_pnet/kernel", (self.n_st, self.pi_hidden)), ("bottleneck_pnet/bias", (self.pi_hidden,))]
+        return L
+
+    def _draw(self, name: str, shape):
+        s, p = self.cfg_shape_net, self.cfg_parameter_net
+        if name == "HyperLinearForSIREN_w":
+            # gen_hypernetwork_weights_bias_for_siren_shapenet (nif/layers/siren.py:36-40)
+            return _uniform(shape, math.sqrt(6.0 / self.pi_hidden) * s["weight_init_factor"], self._gen)
+        if name == "HyperLinearForSIREN_b":
+            # per-column bounds (nif/layers/siren.py:42-62)
+            n, si, so = self.n_sx, self.si_dim, self.so_dim
+            H = 2 * self.l_sx if s["use_resblock"] else self.l_sx
+            bound = np.ones(self.po_dim)
+            n1, nh, nl = si * n, H * n * n, so * n
+            bound[:n1] /= si
+            bound[n1:n1 + nh] *= math.sqrt(6.0 / n) / s["omega_0"]
+            bound[n1 + nh:n1 + nh + nl] *= math.sqrt(6.0 / (2 * n))
+            bound[n1 + nh + nl:] /= n
+            return _uniform(shape, bound, self._gen)
+        if name.startswith("siren_"):
+            # SIREN layer rules (nif/layers/siren.py:178-204); SIREN_ResNet copies w/b into w2/b2 (:370-379)
+            w0 = float(p["omega_0"])
+            if name.endswith("_w2") or name.endswith("_b2"):
+                return self._drawn[name[:-1]].clone()
+            first = name.startswith("siren_first")
+            fan_in = self.pi_dim if first else self.n_st
+            if name.endswith("_w"):
+                t = _uniform(shape, 1.0 / fan_in if first else math.sqrt(6.0 / fan_in) / w0, self._gen)
+            else:
+                t = _uniform(shape, 1.0 / math.sqrt(fan_in), self._gen)
+            self._drawn[name] = t
+            return t
+        return _trunc_normal(shape, 0.1, self._gen)
+
+    def _init_parameters(self):
+        self._drawn: Dict[str, torch.Tensor] = {}
+        super()._init_parameters()
+        self._drawn = {}
+
+    def _latent(self, input_p: torch.Tensor) -> torch.Tensor:
+        V = self._views
+        p = self.cfg_parameter_net
+        res = bool(p.get("use_resblock", False))
+        if self._sine_trunk:  # SIREN / SIREN_ResNet (nif/layers/siren.py:256-281, 381-410)
+            w0 = float(p["omega_0"])
+            h = torch.sin(w0 * (input_p @ V["siren_first_pnet_w"]) + V["siren_first_pnet_b"])
+            for i in range(self.l_st):
+                if res:
+                    q = f"siren_hidden_resblock_pnet_{i}"
+                    g = torch.sin(w0 * (h @ V[q + "_w"]) + V[q + "_b"])
+                    h = 0.5 * (h + torch.sin(w0 * (g @ V[q + "_w2"]) + V[q + "_b2"]))
+                else:
+                    q = f"siren_hidden_pnet_{i}"
+                    h = torch.sin(w0 * (h @ V[q + "_w"]) + V[q + "_b"])
+            return h @ V["siren_bottleneck_pnet_w"] + V["siren_bottleneck_pnet_b"]
+        f = self._act(p["activation"])
+        h = f(input_p @ V["mlp_first_pnet/kernel"] + V["mlp_first_pnet/bias"])
+        for i in range(self.l_st):
+            if res:  # MLP_ResNet (nif/layers/mlp.py:62-79)
+                q = f"mlp_hidden_resblock_pnet_{i}"
+                h1 = f(h @ V[q + "_dense_1/kernel"] + V[q + "_dense_1/bias"])
+                h = f(h + h1 @ V[q + "_dense_2/kernel"] + V[q + "_dense_2/bias"])
+            else:  # MLP_SimpleShortCut (nif/layers/mlp.py:148-160)
+                q = f"mlp_hidden_pnet_{i}"
+                h = h + f(h @ V[q + "/kernel"] + V[q + "/bias"])
+        return h @ V["bottleneck_pnet/kernel"] + V["bottleneck_pnet/bias"]

@@ -1,0 +1,204 @@
+"""Host-side operators over the C ABI: torch tensors in, torch tensors out.
+
+torch is used for device memory, streams and autograd plumbing only; every
+number on the hot path is produced by libnif_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import ACT, VARIANT, Desc, NifError, Sizes, check
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise NifError(f"{name} must be a CUDA tensor (nif_b200 has no CPU path)")
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+class FusedShapeNet:
+    """The hyper-network head + ShapeNet of one model, bound to a descriptor.
+
+    Mirrors the static kernels of the reference:
+      NIF._call_shape_net(input_s, pnet_output, si_dim, so_dim, n_sx, l_sx, activation, variable_dtype)
+        (nif/model.py:233-236)
+      NIFMultiScale._call_shape_net_mres(input_s, pnet_output, flag_resblock, omega_0, si_dim, so_dim,
+        n_sx, l_sx, variable_dtype)   (nif/model.py:738-749)
+    except that `pnet_output` is never formed: the operator takes the latent z and the last
+    linear layer (w_h, b_h) instead.
+    """
+
+    def __init__(self, variant: str, si: int, so: int, n: int, l: int, K: int,
+                 activation: Optional[str] = "swish", omega0: float = 1.0):
+        if variant not in VARIANT:
+            raise ValueError(f"variant must be one of {list(VARIANT)}")
+        if variant == "nif" and activation not in ACT:
+            raise ValueError(f"activation {activation!r} is not supported by the fused kernels {list(ACT)}")
+        self.variant, self.si, self.so, self.n, self.l, self.K = variant, si, so, n, l, K
+        self.activation, self.omega0 = activation, float(omega0)
+        self.desc = Desc(VARIANT[variant], ACT[activation] if variant == "nif" else ACT["sine"], si, so, n, l, K,
+                         float(omega0) if variant != "nif" else 1.0, 0, 0)
+        s = Sizes()
+        check(_lib.lib().nif_query_sizes(C.byref(self.desc), 0, C.byref(s)), "nif_query_sizes")
+        self.po_dim, self.np, self.packed_floats = int(s.po_dim), int(s.np), int(s.packed_floats)
+        self.save_floats_per_row, self.tile_rows = int(s.save_floats_per_row), int(s.tile_rows)
+        self._ws = None
+
+    def with_latent(self, K: int) -> "FusedShapeNet":
+        return FusedShapeNet(self.variant, self.si, self.so, self.n, self.l, K, self.activation, self.omega0)
+
+    # ------------------------------------------------------------------------------------------
+    def grad_ws_floats(self, B: int) -> int:
+        s = Sizes()
+        check(_lib.lib().nif_query_sizes(C.byref(self.desc), B, C.byref(s)), "nif_query_sizes")
+        return int(s.grad_ws_floats)
+
+    def _workspace(self, B: int, device) -> torch.Tensor:
+        need = self.grad_ws_floats(B)
+        if self._ws is None or self._ws.numel() < need or self._ws.device != device:
+            self._ws = torch.empty(need, dtype=torch.float32, device=device)
+        return self._ws
+
+    def pack(self, w_h: Optional[torch.Tensor], b_h: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Re-lay (w_h [K,P], b_h [P] or [G,P]) for the kernels."""
+        b_h = _f32c(b_h, "b_h")
+        G = 1 if b_h.dim() == 1 else b_h.shape[0]
+        if b_h.shape[-1] != self.po_dim:
+            raise NifError(f"b_h has {b_h.shape[-1]} columns, po_dim is {self.po_dim}")
+        if self.K > 0:
+            w_h = _f32c(w_h, "w_h")
+            if tuple(w_h.shape) != (self.K, self.po_dim):
+                raise NifError(f"w_h must be [{self.K},{self.po_dim}], got {tuple(w_h.shape)}")
+        if out is None:
+            out = torch.empty(G * self.packed_floats, dtype=torch.float32, device=b_h.device)
+        check(_lib.lib().nif_pack(C.byref(self.desc), G, _ptr(w_h) if self.K > 0 else None, _ptr(b_h), _ptr(out),
+                                  _stream()), "nif_pack")
+        return out
+
+    def forward(self, z: Optional[torch.Tensor], x: torch.Tensor, packed: torch.Tensor, save: bool = False,
+                groups: int = 1, x_shared: bool = False):
+        """u = ShapeNet(x; z @ w_h + b_h).  Returns u, or (u, stash) when save=True."""
+        x = _f32c(x, "x")
+        if x_shared:
+            B = x.shape[0]
+        else:
+            B = x.shape[0] // groups
+        if self.K > 0:
+            z = _f32c(z, "z")
+            if z.shape[0] != groups * B or z.shape[1] != self.K:
+                raise NifError(f"z must be [{groups * B},{self.K}], got {tuple(z.shape)}")
+        if x.shape[-1] != self.si:
+            raise NifError(f"x must have {self.si} columns")
+        u = torch.empty(groups * B, self.so, dtype=torch.float32, device=x.device)
+        stash = torch.empty(self.save_floats_per_row * B, dtype=torch.float32, device=x.device) if save else None
+        check(_lib.lib().nif_forward(C.byref(self.desc), groups, B, _ptr(z) if self.K > 0 else None, _ptr(x),
+                                     1 if x_shared else 0, _ptr(packed), _ptr(u), _ptr(stash), _stream()),
+              "nif_forward")
+        return (u, stash) if save else u
+
+    def forward_tangent(self, z, x, packed, zdot: Optional[torch.Tensor], xdot: Optional[torch.Tensor]):
+        """(u, udot[n_dir,B,so]) for tangent directions zdot [n_dir,B,K] / xdot [n_dir,B,si]."""
+        x = _f32c(x, "x")
+        B = x.shape[0]
+        z = _f32c(z, "z") if self.K > 0 else None
+        n_dir = (zdot if zdot is not None else xdot).shape[0]
+        zdot = _f32c(zdot, "zdot") if zdot is not None else None
+        xdot = _f32c(xdot, "xdot") if xdot is not None else None
+        u = torch.empty(B, self.so, dtype=torch.float32, device=x.device)
+        udot = torch.empty(n_dir, B, self.so, dtype=torch.float32, device=x.device)
+        check(_lib.lib().nif_forward_tangent(C.byref(self.desc), B, _ptr(z), _ptr(x), _ptr(packed), n_dir,
+                                             _ptr(zdot), _ptr(xdot), _ptr(u), _ptr(udot), _stream()),
+              "nif_forward_tangent")
+        return u, udot
+
+    def given_w(self, x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+        """model_x_to_u_given_w: every row of `w` is a full weight vector (nif/model.py:435-464, 956-986)."""
+        x, w = _f32c(x, "x"), _f32c(w, "w")
+        if w.shape != (x.shape[0], self.po_dim):
+            raise NifError(f"w must be [{x.shape[0]},{self.po_dim}], got {tuple(w.shape)}")
+        u = torch.empty(x.shape[0], self.so, dtype=torch.float32, device=x.device)
+        check(_lib.lib().nif_forward_given_w(C.byref(self.desc), x.shape[0], _ptr(x), _ptr(w), _ptr(u), _stream()),
+              "nif_forward_given_w")
+        return u
+
+    def backward(self, z, x, packed, stash, du, dw_h, db_h, beta: float = 0.0):
+        """Reverse pass for a caller-supplied seed du [B,so]; fills dw_h/db_h, returns dz."""
+        B = x.shape[0]
+        du = _f32c(du, "du")
+        dz = torch.empty(B, self.K, dtype=torch.float32, device=x.device) if self.K > 0 else None
+        ws = self._workspace(B, x.device)
+        check(_lib.lib().nif_backward(C.byref(self.desc), B, _ptr(z), _ptr(x), _ptr(packed), _ptr(stash), _ptr(du),
+                                      _ptr(dw_h), _ptr(db_h), float(beta), _ptr(dz), _ptr(ws), _stream()),
+              "nif_backward")
+        return dz
+
+    def mse_backward(self, z, x, packed, u, stash, target, sample_weight, inv_global_batch: float, loss, dw_h, db_h,
+                     beta: float = 0.0):
+        """Keras 'mse' + reverse pass.  `loss` is a 1-element tensor that is accumulated into."""
+        B = x.shape[0]
+        target = _f32c(target, "target")
+        sw = _f32c(sample_weight, "sample_weight") if sample_weight is not None else None
+        dz = torch.empty(B, self.K, dtype=torch.float32, device=x.device) if self.K > 0 else None
+        ws = self._workspace(B, x.device)
+        check(_lib.lib().nif_mse_backward(C.byref(self.desc), B, _ptr(z), _ptr(x), _ptr(packed), _ptr(u), _ptr(stash),
+                                          _ptr(target), _ptr(sw), float(inv_global_batch), _ptr(loss), _ptr(dw_h),
+                                          _ptr(db_h), float(beta), _ptr(dz), _ptr(ws), _stream()),
+              "nif_mse_backward")
+        return dz
+
+
+class _FusedFn(torch.autograd.Function):
+    """autograd bridge: (z, x, w_h, b_h) -> u with the fused forward / reverse kernels."""
+
+    @staticmethod
+    def forward(ctx, z, x, w_h, b_h, engine: FusedShapeNet):
+        packed = engine.pack(w_h, b_h)
+        need = any(ctx.needs_input_grad[:4])
+        if need:
+            u, stash = engine.forward(z, x, packed, save=True)
+            ctx.save_for_backward(z, x, packed, stash)
+            ctx.engine = engine
+            ctx.shapes = (w_h.shape, b_h.shape)
+        else:
+            u = engine.forward(z, x, packed)
+        return u
+
+    @staticmethod
+    def backward(ctx, du):
+        z, x, packed, stash = ctx.saved_tensors
+        e = ctx.engine
+        dw = torch.empty(ctx.shapes[0], dtype=torch.float32, device=x.device)
+        db = torch.empty(ctx.shapes[1], dtype=torch.float32, device=x.device)
+        dz = e.backward(z, x, packed, stash, du.contiguous(), dw, db, 0.0)
+        return dz, None, dw, db, None
+
+
+def fused_shapenet(z, x, w_h, b_h, engine: FusedShapeNet):
+    return _FusedFn.apply(z, x, w_h, b_h, engine)
+
+
+def adam_step(p, g, m, v, lr, t, b1=0.9, b2=0.999, eps=1e-7, l1=0.0, l2=0.0, g_scale=1.0):
+    """tf.keras Adam on flat fp32 buffers, in place."""
+    check(_lib.lib().nif_adam_step(p.numel(), _ptr(p), _ptr(g), _ptr(m), _ptr(v), float(lr), float(b1), float(b2),
+                                   float(eps), int(t), float(l1), float(l2), float(g_scale), _stream()),
+          "nif_adam_step")
+
+
+def measure_fp32_peak() -> float:
+    v = C.c_double(0.0)
+    check(_lib.lib().nif_measure_fp32_peak(C.byref(v)), "nif_measure_fp32_peak")
+    return float(v.value)

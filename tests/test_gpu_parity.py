@@ -1,0 +1,247 @@
+"""Parity of the CUDA hot path against the oracle, through the C ABI (ctypes).
+
+Tolerance (BASELINE.md section 5 / north_star "within 1e-5 rel-fp32"):
+    err = max|a - b| / max|b|  per tensor, against the fp64 oracle;
+    gate  err_gpu <= max(1e-5, 2 * err_cpu_fp32)
+where err_cpu_fp32 is the error of the fp32 CPU oracle against the same fp64 truth.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import nif_oracle as O
+from tests.helpers import golden_cases, load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine(spec):
+    from nif_b200.ops import FusedShapeNet
+    return FusedShapeNet(spec.variant, spec.si, spec.so, spec.n, spec.l, spec.K, spec.s_act, spec.omega0)
+
+
+def _gate(err_gpu, err_cpu32, floor=1e-5):
+    return err_gpu <= max(floor, 2.0 * err_cpu32)
+
+
+def _run_case(spec, prm64, inputs64, target64, sw64, floor=1e-5):
+    """forward + mse backward on the GPU vs fp64 oracle (and fp32 oracle for the gate)."""
+    dev = torch.device("cuda:0")
+    wn, bn = O.last_layer_names(spec)
+    loss64, g64, gz64, y64 = O.loss_and_grads(spec, prm64, inputs64, target64, sw64)
+    prm32 = {k: v.float() for k, v in prm64.items()}
+    loss32, g32, gz32, y32 = O.loss_and_grads(spec, prm32, inputs64.float(), target64.float(),
+                                              None if sw64 is None else sw64.float())
+    z64 = O.latent(spec, prm64, inputs64[:, : spec.pi])
+    eng = _engine(spec)
+    z = z64.float().to(dev)
+    x = inputs64[:, spec.pi: spec.pi + spec.si].float().contiguous().to(dev)
+    w_h, b_h = prm64[wn].float().to(dev), prm64[bn].float().to(dev)
+    packed = eng.pack(w_h, b_h)
+    u, stash = eng.forward(z, x, packed, save=True)
+    u_inf = eng.forward(z, x, packed)
+    assert torch.equal(u, u_inf), "stash on/off must not change the output"
+    e_u = rel_err(u.cpu(), y64)
+    assert _gate(e_u, rel_err(y32, y64), floor), f"forward err {e_u:.3e} (cpu32 {rel_err(y32, y64):.3e})"
+    B = inputs64.shape[0]
+    loss = torch.zeros(1, device=dev)
+    dw = torch.full_like(w_h, float("nan"))
+    db = torch.full_like(b_h, float("nan"))
+    dz = eng.mse_backward(z, x, packed, u, stash, target64.float().to(dev),
+                          None if sw64 is None else sw64.float().to(dev), 1.0 / B, loss, dw, db, 0.0)
+    torch.cuda.synchronize()
+    assert abs(float(loss) - float(loss64)) <= 1e-5 * max(1.0, abs(float(loss64)))
+    for name, got, ref64, ref32 in (("dz", dz, gz64, gz32), ("dw_h", dw, g64[wn], g32[wn]), ("db_h", db, g64[bn], g32[bn])):
+        e = rel_err(got.cpu(), ref64)
+        assert _gate(e, rel_err(ref32, ref64), floor), f"{name} err {e:.3e} (cpu32 {rel_err(ref32, ref64):.3e})"
+    # accumulate semantics: beta = 1 doubles the gradient
+    dz2 = eng.mse_backward(z, x, packed, u, stash, target64.float().to(dev),
+                           None if sw64 is None else sw64.float().to(dev), 1.0 / B, loss, dw, db, 1.0)
+    assert rel_err(dw.cpu(), 2 * g64[wn]) < 1e-4 and rel_err(db.cpu(), 2 * g64[bn]) < 1e-4
+    return eng, packed
+
+
+@pytest.mark.parametrize("case", golden_cases())
+def test_golden_forward_backward(case):
+    d, cls, cfg_s, cfg_p, spec, prm, grads = load_golden(case)
+    if spec.variant == "nif" and spec.s_act not in ("swish", "tanh", "relu", "sigmoid", "sine", "linear"):
+        pytest.skip("activation not in the fused set")
+    _run_case(spec, prm, torch.as_tensor(d["inputs"]), torch.as_tensor(d["target"]), torch.as_tensor(d["sample_weight"]))
+    # and against the committed reference outputs themselves
+    dev = torch.device("cuda:0")
+    eng = _engine(spec)
+    wn, bn = O.last_layer_names(spec)
+    packed = eng.pack(prm[wn].float().to(dev), prm[bn].float().to(dev))
+    x = torch.as_tensor(d["inputs"])[:, spec.pi:].float().contiguous().to(dev)
+    u = eng.forward(torch.as_tensor(d["latent"]).float().to(dev), x, packed)
+    assert rel_err(u.cpu(), d["y"]) <= max(1e-5, 2 * rel_err(d["y32"], d["y"]))
+
+
+def _random_problem(variant, si, so, n, l, K, B, seed, act="swish", omega0=30.0, wif=0.05):
+    if variant == "nif":
+        spec = O.Spec(variant="nif", pi=1, si=si, so=so, n=n, l=l, K=K, n_st=16, l_st=1, p_act="swish", s_act=act)
+    else:
+        spec = O.Spec(variant=variant, pi=1, si=si, so=so, n=n, l=l, K=K, n_st=16, l_st=1, p_act="swish",
+                      omega0=omega0, weight_init_factor=wif)
+    prm = {k: v.double() for k, v in O.init_params(spec, seed).items()}
+    if variant == "nif":
+        # TruncatedNormal(0.1) on a wide last layer saturates swish; scale to keep the test well conditioned
+        prm["last_pnet/kernel"] *= 0.5
+    rng = np.random.default_rng(seed)
+    inputs = torch.as_tensor(rng.uniform(-1, 1, (B, 1 + si)))
+    target = torch.as_tensor(rng.uniform(-1, 1, (B, so)))
+    sw = torch.as_tensor(rng.uniform(0.5, 1.5, (B,)))
+    return spec, prm, inputs, target, sw
+
+
+@pytest.mark.parametrize(
+    "variant,si,so,n,l,K,B",
+    [
+        ("siren", 2, 1, 64, 4, 32, 300),      # C2 shape, ragged batch
+        ("siren", 2, 1, 64, 4, 32, 128),      # exactly one tile
+        ("siren", 1, 1, 64, 4, 32, 257),      # C4 shape
+        ("siren", 3, 3, 128, 2, 8, 200),      # width 128 path
+        ("siren", 3, 1, 100, 1, 5, 77),       # padded to 128
+        ("siren_res", 2, 2, 64, 2, 6, 150),   # res-blocks
+        ("siren_res", 1, 1, 20, 3, 2, 130),
+        ("nif", 1, 1, 30, 2, 1, 512),         # C1
+        ("nif", 2, 2, 48, 3, 7, 90),
+        ("siren", 1, 1, 30, 0, 3, 64),        # no hidden layer
+        ("siren", 2, 1, 64, 1, 70, 140),      # latent > 68 (two edge passes)
+        ("siren", 1, 1, 8, 2, 1, 1),          # single row
+    ],
+)
+def test_random_forward_backward(variant, si, so, n, l, K, B):
+    spec, prm, inputs, target, sw = _random_problem(variant, si, so, n, l, K, B, seed=si * 100 + n + K)
+    _run_case(spec, prm, inputs, target, sw)
+
+
+def test_no_sample_weight_and_large_batch_splits():
+    spec, prm, inputs, target, _ = _random_problem("siren", 2, 1, 64, 2, 4, 5000, seed=5)
+    _run_case(spec, prm, inputs, target, None)
+
+
+def test_autograd_bridge_matches_oracle():
+    from nif_b200.ops import fused_shapenet
+    spec, prm, inputs, target, sw = _random_problem("siren", 2, 1, 32, 2, 3, 100, seed=9)
+    dev = torch.device("cuda:0")
+    wn, bn = O.last_layer_names(spec)
+    eng = _engine(spec)
+    z = O.latent(spec, prm, inputs[:, :1]).float().to(dev).requires_grad_(True)
+    x = inputs[:, 1:].float().contiguous().to(dev)
+    w = prm[wn].float().to(dev).requires_grad_(True)
+    b = prm[bn].float().to(dev).requires_grad_(True)
+    u = fused_shapenet(z, x, w, b, eng)
+    loss = ((u - target.float().to(dev)) ** 2).mean()
+    loss.backward()
+    l64, g64, gz64, _ = O.loss_and_grads(spec, prm, inputs, target, None)
+    assert abs(float(loss) - float(l64)) < 1e-5
+    assert rel_err(w.grad.cpu(), g64[wn]) < 1e-4 and rel_err(b.grad.cpu(), g64[bn]) < 1e-4
+    assert rel_err(z.grad.cpu(), gz64) < 1e-4
+
+
+@pytest.mark.parametrize("variant,n,l", [("siren", 64, 4), ("siren_res", 30, 2), ("nif", 30, 2), ("siren", 128, 1)])
+def test_given_w_matches_oracle(variant, n, l):
+    spec, prm, inputs, _, _ = _random_problem(variant, 2, 2, n, l, 3, 333, seed=n + l)
+    dev = torch.device("cuda:0")
+    wn, bn = O.last_layer_names(spec)
+    z = O.latent(spec, prm, inputs[:, :1])
+    w = O.hyper_linear(z, prm[wn], prm[bn])  # (B, P) per-row weights, the reference's materialised tensor
+    y64 = O.shape_net(spec, inputs[:, 1:], w)
+    y32 = O.shape_net(spec, inputs[:, 1:].float(), w.float())
+    eng = _engine(spec)
+    u = eng.given_w(inputs[:, 1:].float().contiguous().to(dev), w.float().to(dev))
+    assert _gate(rel_err(u.cpu(), y64), rel_err(y32, y64))
+
+
+def test_grouped_inference_latent_by_grid():
+    """C5 shape in miniature: G latents x N shared grid points, weights packed per latent (K=0 heads)."""
+    spec, prm, inputs, _, _ = _random_problem("siren", 3, 1, 64, 2, 6, 50, seed=1)
+    dev = torch.device("cuda:0")
+    wn, bn = O.last_layer_names(spec)
+    G, N = 5, 333
+    rng = np.random.default_rng(0)
+    zg = torch.as_tensor(rng.normal(size=(G, spec.K)))
+    grid = torch.as_tensor(rng.uniform(-1, 1, (N, spec.si)))
+    wg = O.hyper_linear(zg, prm[wn], prm[bn])  # (G, P)
+    ref = torch.stack([O.shape_net(spec, grid, wg[g: g + 1].expand(N, -1)) for g in range(G)])  # (G, N, so)
+    ref32 = torch.stack([O.shape_net(spec, grid.float(), wg[g: g + 1].float().expand(N, -1)) for g in range(G)])
+    eng0 = _engine(spec).with_latent(0)
+    packed = eng0.pack(None, wg.float().to(dev))
+    u = eng0.forward(None, grid.float().to(dev), packed, groups=G, x_shared=True).reshape(G, N, spec.so)
+    assert _gate(rel_err(u.cpu(), ref), rel_err(ref32, ref))
+
+
+def test_adam_matches_tf_semantics():
+    from nif_b200.ops import adam_step
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(0)
+    n = 100003
+    p = torch.as_tensor(rng.normal(size=n)).float()
+    m = torch.zeros(n)
+    v = torch.zeros(n)
+    pg, mg, vg = p.to(dev), m.to(dev), v.to(dev)
+    p64, m64, v64 = p.double(), m.double(), v.double()
+    for t in range(1, 4):
+        g = torch.as_tensor(rng.normal(size=n)).float()
+        adam_step(pg, g.to(dev), mg, vg, 1e-3, t)
+        O.adam_tf(p64, g.double(), m64, v64, t, 1e-3)
+    assert rel_err(pg.cpu(), p64) < 1e-6 and rel_err(mg.cpu(), m64) < 1e-6 and rel_err(vg.cpu(), v64) < 1e-6
+
+
+def test_empty_batch_and_bad_arguments():
+    from nif_b200 import _lib
+    from nif_b200.ops import FusedShapeNet
+    dev = torch.device("cuda:0")
+    eng = FusedShapeNet("siren", 2, 1, 16, 1, 2, omega0=30.0)
+    packed = eng.pack(torch.zeros(2, eng.po_dim, device=dev), torch.zeros(eng.po_dim, device=dev))
+    u = eng.forward(torch.zeros(0, 2, device=dev), torch.zeros(0, 2, device=dev), packed)
+    assert u.shape == (0, 1)
+    with pytest.raises(_lib.NifError):
+        eng.pack(torch.zeros(3, eng.po_dim, device=dev), torch.zeros(eng.po_dim, device=dev))
+    with pytest.raises(_lib.NifError):
+        FusedShapeNet("siren", 2, 1, 500, 1, 2)  # units > 128: rejected by the library
+    with pytest.raises(_lib.NifError):
+        eng.forward(torch.zeros(4, 2), torch.zeros(4, 2), packed)  # CPU tensors: no fallback
+
+
+def test_full_size_properties_c2():
+    """BASELINE config 2 at full batch: size-independent checks (determinism, row independence,
+    gradient linearity in the seed)."""
+    spec, prm, _, _, _ = _random_problem("siren", 2, 1, 64, 4, 32, 8, seed=2)
+    dev = torch.device("cuda:0")
+    wn, bn = O.last_layer_names(spec)
+    eng = _engine(spec)
+    B = 65536
+    g = torch.Generator(device="cpu").manual_seed(0)
+    z = (torch.rand(B, 32, generator=g) - 0.5).to(dev)
+    x = (torch.rand(B, 2, generator=g) * 2 - 1).to(dev)
+    w_h, b_h = prm[wn].float().to(dev), prm[bn].float().to(dev)
+    packed = eng.pack(w_h, b_h)
+    u1, stash = eng.forward(z, x, packed, save=True)
+    u2 = eng.forward(z, x, packed)
+    assert torch.equal(u1, u2)
+    # row independence: a permuted batch gives the permuted output, bit for bit
+    perm = torch.randperm(B, generator=g).to(dev)
+    assert torch.equal(eng.forward(z[perm], x[perm], packed), u1[perm])
+    # oracle on a sample of rows
+    idx = torch.arange(0, B, 997)
+    y64 = O.shape_net(spec, x[idx].cpu().double(), O.hyper_linear(z[idx].cpu().double(), prm[wn], prm[bn]))
+    assert rel_err(u1[idx].cpu(), y64) < 1e-5
+    # reverse pass: deterministic, and linear in the seed
+    du = torch.randn(B, 1, generator=g).to(dev)
+    dw1, db1 = torch.empty_like(w_h), torch.empty_like(b_h)
+    dw2, db2 = torch.empty_like(w_h), torch.empty_like(b_h)
+    dz1 = eng.backward(z, x, packed, stash, du, dw1, db1)
+    dz2 = eng.backward(z, x, packed, stash, du, dw2, db2)
+    assert torch.equal(dw1, dw2) and torch.equal(db1, db2) and torch.equal(dz1, dz2)
+    dz3 = eng.backward(z, x, packed, stash, 2 * du, dw2, db2)
+    assert rel_err(dw2.cpu(), 2 * dw1.cpu()) < 1e-6 and rel_err(dz3.cpu(), 2 * dz1.cpu()) < 1e-6
+    # sum of two half batches == whole batch (what data parallel relies on)
+    h = B // 2
+    _, st_a = eng.forward(z[:h], x[:h], packed, save=True)
+    _, st_b = eng.forward(z[h:], x[h:], packed, save=True)
+    dwa, dba = torch.empty_like(w_h), torch.empty_like(b_h)
+    eng.backward(z[:h].contiguous(), x[:h].contiguous(), packed, st_a, du[:h].contiguous(), dwa, dba)
+    eng.backward(z[h:].contiguous(), x[h:].contiguous(), packed, st_b, du[h:].contiguous(), dwa, dba, beta=1.0)
+    assert rel_err(dwa.cpu(), dw1.cpu()) < 1e-5 and rel_err(dba.cpu(), db1.cpu()) < 1e-5
