@@ -1,0 +1,65 @@
+"""Data parallelism: one process per GPU, gradient all-reduce over NCCL (NVLink 5 / NVSwitch).
+
+Replaces `tf.distribute.MirroredStrategy().scope()` of the reference snippets (README.md:39-49,
+tutorial/2_multi_scale_NIF.ipynb:493): the global batch is split evenly by rows, every rank runs the
+fused forward / reverse kernels on its rows with the loss already divided by the GLOBAL batch, the
+flat fp32 gradient buffer is summed across ranks (one all-reduce per step), and every rank applies
+the identical Adam update to its replica.  Rows are independent, so there is no other exchange.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+import torch.distributed as dist
+
+
+class DataParallel:
+    def __init__(self, backend: str | None = None):
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.backend = backend or ("nccl" if torch.cuda.is_available() else "gloo")
+        if self.world > 1 and not dist.is_initialized():
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            os.environ.setdefault("MASTER_PORT", "29500")
+            if self.backend == "nccl":
+                torch.cuda.set_device(self.local_rank)
+                dist.init_process_group("nccl", rank=self.rank, world_size=self.world,
+                                        device_id=torch.device("cuda", self.local_rank))
+            else:
+                dist.init_process_group(self.backend, rank=self.rank, world_size=self.world)
+
+    @property
+    def device(self) -> torch.device:
+        return torch.device("cuda", self.local_rank) if torch.cuda.is_available() else torch.device("cpu")
+
+    def allreduce_(self, t: torch.Tensor) -> torch.Tensor:
+        """In-place sum over ranks (no-op for a single process)."""
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return t
+
+    def max_(self, t: torch.Tensor) -> torch.Tensor:
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t
+
+    def broadcast_(self, t: torch.Tensor, src: int = 0) -> torch.Tensor:
+        if self.world > 1:
+            dist.broadcast(t, src)
+        return t
+
+    def barrier(self):
+        if self.world > 1:
+            dist.barrier()
+
+    def attach(self, model):
+        """Make `model` (a nif_b200 Model) data parallel: replicas start from rank 0's parameters."""
+        self.broadcast_(model.net.theta)
+        model.dist = self
+        return model
+
+    def shutdown(self):
+        if self.world > 1 and dist.is_initialized():
+            dist.destroy_process_group()

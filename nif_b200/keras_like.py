@@ -1,0 +1,402 @@
+"""Keras-shaped training / inference runtime around the fused kernels.
+
+The reference hands its functional graph to Keras (`Model.compile / fit / predict / save_weights`,
+tutorial/2_multi_scale_NIF.ipynb:643-656).  Keras itself is third-party there (tensorflow==2.11.1);
+the semantics kept here are the ones SURVEY A.6 lists: 'mse' = mean over outputs then (weighted)
+mean over the global batch, Adam with epsilon outside the bias correction, LearningRateScheduler
+called at the start of every epoch, short last batch kept, predict() batched.
+"""
+from __future__ import annotations
+
+import os
+import time
+from typing import Callable, Dict, Iterable, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from ._lib import NifError
+from . import ops
+
+
+# --------------------------------------------------------------------------------------------------
+# optimiser / callbacks / dataset
+# --------------------------------------------------------------------------------------------------
+class Adam:
+    """tf.keras.optimizers.Adam(learning_rate=1e-3, beta_1=0.9, beta_2=0.999, epsilon=1e-7)."""
+
+    def __init__(self, learning_rate=1e-3, beta_1=0.9, beta_2=0.999, epsilon=1e-7):
+        self.learning_rate = float(learning_rate)
+        self.beta_1, self.beta_2, self.epsilon = float(beta_1), float(beta_2), float(epsilon)
+        self.iterations = 0
+        self._m = None
+        self._v = None
+
+    @property
+    def lr(self):
+        return self.learning_rate
+
+    @lr.setter
+    def lr(self, v):
+        self.learning_rate = float(v)
+
+    def _ensure(self, theta):
+        if self._m is None or self._m.shape != theta.shape or self._m.device != theta.device:
+            self._m = torch.zeros_like(theta)
+            self._v = torch.zeros_like(theta)
+
+    def apply(self, theta: torch.Tensor, grad: torch.Tensor, l1=0.0, l2=0.0, g_scale=1.0):
+        self._ensure(theta)
+        self.iterations += 1
+        ops.adam_step(theta, grad, self._m, self._v, self.learning_rate, self.iterations, self.beta_1, self.beta_2,
+                      self.epsilon, l1, l2, g_scale)
+
+
+class Callback:
+    model = None
+
+    def set_model(self, model):
+        self.model = model
+
+    def on_train_begin(self, logs=None): ...
+    def on_train_end(self, logs=None): ...
+    def on_epoch_begin(self, epoch, logs=None): ...
+    def on_epoch_end(self, epoch, logs=None): ...
+    def on_train_batch_end(self, batch, logs=None): ...
+
+
+class LearningRateScheduler(Callback):
+    """tf.keras.callbacks.LearningRateScheduler(schedule): lr = schedule(epoch, lr) at epoch begin
+    (tutorial/2_multi_scale_NIF.ipynb:631-641)."""
+
+    def __init__(self, schedule: Callable[[int, float], float], verbose=0):
+        self.schedule = schedule
+        self.verbose = verbose
+
+    def on_epoch_begin(self, epoch, logs=None):
+        opt = self.model.optimizer
+        opt.learning_rate = float(self.schedule(epoch, opt.learning_rate))
+
+
+class History(Callback):
+    def on_train_begin(self, logs=None):
+        self.history: Dict[str, List[float]] = {}
+        self.epoch: List[int] = []
+
+    def on_epoch_end(self, epoch, logs=None):
+        self.epoch.append(epoch)
+        for k, v in (logs or {}).items():
+            self.history.setdefault(k, []).append(v)
+
+
+class Dataset:
+    """The slice of tf.data the tutorials use: from_tensor_slices(...).shuffle(N).batch(B).prefetch(...)
+    (tutorial/2_multi_scale_NIF.ipynb:222-224).  Arrays are staged once in pinned host memory;
+    every epoch draws a fresh permutation when shuffle() was requested; the short last batch is kept."""
+
+    def __init__(self, arrays: Sequence[np.ndarray]):
+        self.arrays = [torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float32) for a in arrays]
+        n = {a.shape[0] for a in self.arrays}
+        if len(n) != 1:
+            raise ValueError("all arrays must have the same first dimension")
+        self.n = n.pop()
+        self._shuffle = False
+        self._batch = None
+        self._seed = 0
+        self._rank, self._world = 0, 1
+
+    @staticmethod
+    def from_tensor_slices(arrays) -> "Dataset":
+        if isinstance(arrays, (tuple, list)):
+            return Dataset(list(arrays))
+        return Dataset([arrays])
+
+    def shuffle(self, buffer_size=None, seed=None) -> "Dataset":
+        self._shuffle = True
+        if seed is not None:
+            self._seed = int(seed)
+        return self
+
+    def batch(self, batch_size) -> "Dataset":
+        self._batch = int(batch_size)
+        return self
+
+    def prefetch(self, *_a) -> "Dataset":
+        return self
+
+    def shard(self, world: int, rank: int) -> "Dataset":
+        """Data parallel: every rank sees rows rank::world of every global batch."""
+        self._world, self._rank = int(world), int(rank)
+        return self
+
+    def pin(self):
+        if torch.cuda.is_available():
+            self.arrays = [a if a.is_pinned() else a.pin_memory() for a in self.arrays]
+        return self
+
+    def batches(self, epoch: int):
+        bs = self._batch or self.n
+        if self._shuffle:
+            g = torch.Generator().manual_seed(self._seed * 1000003 + epoch)
+            perm = torch.randperm(self.n, generator=g)
+        else:
+            perm = None
+        for s in range(0, self.n, bs):
+            e = min(self.n, s + bs)
+            idx = slice(s, e) if perm is None else perm[s:e]
+            rows = [a[idx] for a in self.arrays]
+            gb = e - s
+            if self._world > 1:
+                rows = [r[self._rank::self._world] for r in rows]
+            yield gb, rows
+
+
+# --------------------------------------------------------------------------------------------------
+# the model object returned by NIF.build() / .model() / .model_*()
+# --------------------------------------------------------------------------------------------------
+class Model:
+    """What `nif.NIF(...).build()` returns in the reference is a tf.keras.Model; this is the same
+    surface: __call__/predict, compile, fit, train_on_batch, save_weights/load_weights, summary,
+    trainable_variables.  `kind` selects the (sub-)graph (nif/model.py:379-464, 956-986)."""
+
+    def __init__(self, net, kind: str):
+        self.net = net
+        self.kind = kind
+        self.optimizer: Optional[Adam] = None
+        self.loss = None
+        self.metrics_fns: list = []
+        self.stop_training = False
+        self.history = None
+        self._loss_buf = None
+        self._packed = None
+        self.dist = None  # set by nif_b200.distributed.DataParallel
+
+    # ---- plumbing -----------------------------------------------------------------------------------
+    def _dev(self, a, pinned_ok=True) -> torch.Tensor:
+        if isinstance(a, torch.Tensor):
+            t = a
+        else:
+            t = torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float32)
+        if t.dtype != torch.float32:
+            t = t.float()
+        if self.net.device.type != "cuda":
+            raise NifError("nif_b200 needs a CUDA device: there is no CPU fallback for the hot path")
+        return t.to(self.net.device, non_blocking=True)
+
+    @property
+    def trainable_variables(self):
+        return self.net.trainable_variables
+
+    @property
+    def inputs(self):
+        n = self.net
+        return {"full": [("input_tot", n.pi_dim + n.si_dim)], "p_to_w": [("input_p_to_w", n.pi_dim)],
+                "p_to_lr": [("input_p_to_lr", n.pi_dim)], "lr_to_w": [("input_lr_to_w", n.pi_hidden)],
+                "x_to_u_given_w": [("input_x_to_u_given_w", n.si_dim), ("input_w_and_b_from_pnet", n.po_dim)]}[self.kind]
+
+    def count_params(self) -> int:
+        n = self.net
+        last = n.pi_hidden * n.po_dim + n.po_dim
+        return {"full": n.count_params(), "p_to_w": n.count_params(), "p_to_lr": n.count_params() - last,
+                "lr_to_w": last, "x_to_u_given_w": 0}[self.kind]
+
+    def summary(self, print_fn=print):
+        n = self.net
+        print_fn(f'Model: "{type(n).__name__}.{self.kind}"')
+        print_fn("_" * 65)
+        names = list(n.variables)
+        if self.kind == "p_to_lr":
+            names = names[:-2]
+        elif self.kind == "lr_to_w":
+            names = names[-2:]
+        elif self.kind == "x_to_u_given_w":
+            names = []
+        for k in names:
+            v = n.variables[k]
+            print_fn(f"{k:45s} {str(tuple(v.shape)):>12s} {v.numel():>7d}")
+        print_fn("=" * 65)
+        print_fn(f"Total params: {self.count_params():,}")
+        print_fn(f"Trainable params: {self.count_params():,}")
+
+    def _packed_weights(self) -> torch.Tensor:
+        n = self.net
+        self._packed = n.engine.pack(n.w_h.detach(), n.b_h.detach(), out=self._packed)
+        return self._packed
+
+    # ---- forward ------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def _forward_batch(self, x):
+        n = self.net
+        if self.kind == "full":
+            inp = self._dev(x)
+            z = n._latent(inp[:, : n.pi_dim])
+            xs = inp[:, n.pi_dim: n.pi_dim + n.si_dim].contiguous()
+            return n.engine.forward(z.contiguous(), xs, self._packed_weights())
+        if self.kind == "p_to_lr":
+            return n._latent(self._dev(x))
+        if self.kind == "p_to_w":
+            z = n._latent(self._dev(x))
+            return torch.addmm(n.b_h.detach(), z, n.w_h.detach())
+        if self.kind == "lr_to_w":
+            return torch.addmm(n.b_h.detach(), self._dev(x), n.w_h.detach())
+        if self.kind == "x_to_u_given_w":
+            xs, w = x
+            return n.engine.given_w(self._dev(xs), self._dev(w))
+        raise ValueError(self.kind)
+
+    def __call__(self, x, training=False):
+        return self._forward_batch(x)
+
+    def predict(self, x, batch_size=None, verbose=0, **_kw) -> np.ndarray:
+        """Keras predict: batched forward, numpy out.  (Keras' default batch of 32 only affects speed;
+        rows are independent, so a larger internal batch returns the same values.)"""
+        bs = int(batch_size) if batch_size else 65536
+        first = x[0] if isinstance(x, (tuple, list)) else x
+        N = first.shape[0]
+        outs = []
+        for s in range(0, N, bs):
+            xb = [a[s:s + bs] for a in x] if isinstance(x, (tuple, list)) else x[s:s + bs]
+            outs.append(self._forward_batch(xb).cpu())
+        if not outs:
+            return np.zeros((0, self.net.so_dim), np.float32)
+        return torch.cat(outs, 0).numpy()
+
+    def predict_latent_grid(self, latents, coords) -> torch.Tensor:
+        """Factored form of model_x_to_u_given_w for sweeps:
+        latents [G,K] x coords [N,si] -> u [G,N,so]; per-latent weights are generated once
+        (G x P, a plain GEMM) and the G ShapeNets run as grouped launches over the shared grid."""
+        n = self.net
+        with torch.no_grad():
+            zg = self._dev(latents)
+            w = torch.addmm(n.b_h.detach(), zg, n.w_h.detach())  # [G,P]
+            eng0 = getattr(self, "_eng0", None)
+            if eng0 is None:
+                eng0 = self._eng0 = n.engine.with_latent(0)
+            packed = eng0.pack(None, w)
+            xs = self._dev(coords)
+            u = eng0.forward(None, xs, packed, groups=zg.shape[0], x_shared=True)
+        return u.view(zg.shape[0], xs.shape[0], n.so_dim)
+
+    # ---- training -----------------------------------------------------------------------------------
+    def compile(self, optimizer=None, loss="mse", metrics=None, **_kw):
+        if self.kind != "full":
+            raise NifError("only the full model is trainable")
+        if optimizer is None:
+            optimizer = Adam()
+        if not isinstance(optimizer, Adam):
+            raise NifError("nif_b200 ships Adam (tf.keras semantics); other optimisers are outside the hot path")
+        if not (loss in ("mse", "mean_squared_error") or callable(loss)):
+            raise NifError("loss must be 'mse' or a callable(y_true, y_pred) -> scalar tensor")
+        self.optimizer, self.loss = optimizer, loss
+        self.metrics_fns = list(metrics or [])
+
+    def train_on_batch(self, x, y, sample_weight=None, global_batch: Optional[int] = None) -> float:
+        """One optimisation step (what Keras' train_step + apply_gradients do).  Returns the loss of this
+        process's rows already divided by the global batch (sum over ranks = global loss)."""
+        loss = self._train_step(self._dev(x), self._dev(y), None if sample_weight is None else self._dev(sample_weight),
+                                global_batch)
+        return float(loss)
+
+    def _train_step(self, inp: torch.Tensor, tgt: torch.Tensor, sw: Optional[torch.Tensor],
+                    global_batch: Optional[int]) -> torch.Tensor:
+        n = self.net
+        eng = n.engine
+        B = inp.shape[0]
+        gb = int(global_batch) if global_batch else B
+        n.grad.zero_()
+        if self._loss_buf is None:
+            self._loss_buf = torch.zeros(1, dtype=torch.float32, device=n.device)
+        self._loss_buf.zero_()
+        z = n._latent(inp[:, : n.pi_dim])
+        xs = inp[:, n.pi_dim: n.pi_dim + n.si_dim].contiguous()
+        if not callable(self.loss):
+            packed = self._packed_weights()
+            zc = z.detach().contiguous()
+            u, stash = eng.forward(zc, xs, packed, save=True)
+            dz = eng.mse_backward(zc, xs, packed, u, stash, tgt, sw, 1.0 / gb, self._loss_buf,
+                                  n._gviews[n._last_names[0]], n._gviews[n._last_names[1]], 0.0)
+            z.backward(dz)
+            loss = self._loss_buf
+        else:
+            u = ops.fused_shapenet(z, xs, n.w_h, n.b_h, eng)
+            lv = self.loss(tgt, u) * (B / gb)
+            lv.backward()
+            loss = lv.detach().reshape(1)
+        if self.dist is not None:
+            self.dist.allreduce_(n.grad)
+        l1, l2 = n._kernel_regulariser()
+        self.optimizer.apply(n.theta, n.grad, l1, l2)
+        return loss
+
+    def fit(self, x=None, y=None, batch_size=None, epochs=1, verbose=0, callbacks=None, shuffle=True,
+            sample_weight=None, initial_epoch=0, **_kw):
+        if self.optimizer is None:
+            raise NifError("call compile() before fit()")
+        if isinstance(x, Dataset):
+            ds = x  # like Keras, batch_size / shuffle arguments are ignored for a dataset
+        else:
+            arrays = [np.asarray(x), np.asarray(y)] + ([np.asarray(sample_weight)] if sample_weight is not None else [])
+            ds = Dataset(arrays).batch(batch_size or 32)
+            if shuffle:
+                ds.shuffle(arrays[0].shape[0])
+        if self.dist is not None:
+            ds.shard(self.dist.world, self.dist.rank)
+        ds.pin()
+        hist = History()
+        cbs: List[Callback] = [hist] + list(callbacks or [])
+        for cb in cbs:
+            cb.set_model(self)
+            cb.on_train_begin({})
+        self.stop_training = False
+        for epoch in range(initial_epoch, epochs):
+            for cb in cbs:
+                cb.on_epoch_begin(epoch, {})
+            t0 = time.time()
+            tot = torch.zeros(1, dtype=torch.float64, device=self.net.device)
+            rows = 0
+            for bi, (gb, parts) in enumerate(ds.batches(epoch)):
+                inp = parts[0].to(self.net.device, non_blocking=True)
+                tgt = parts[1].to(self.net.device, non_blocking=True)
+                sw = parts[2].to(self.net.device, non_blocking=True).reshape(-1) if len(parts) > 2 else None
+                loss = self._train_step(inp, tgt, sw, gb)
+                tot += loss.double() * gb  # Keras reports the sample-weighted running mean of batch losses
+                rows += gb
+            if self.dist is not None:
+                self.dist.allreduce_(tot)
+            logs = {"loss": float(tot) / max(rows, 1), "lr": self.optimizer.learning_rate}
+            if verbose:
+                print(f"Epoch {epoch + 1}/{epochs} - {time.time() - t0:.2f}s - loss: {logs['loss']:.4e}")
+            for cb in cbs:
+                cb.on_epoch_end(epoch, logs)
+            if self.stop_training:
+                break
+        for cb in cbs:
+            cb.on_train_end({})
+        self.history = hist
+        return hist
+
+    def evaluate(self, x, y, batch_size=None, sample_weight=None, **_kw) -> float:
+        pred = self.predict(x, batch_size)
+        per_row = ((pred - np.asarray(y, np.float32)) ** 2).mean(-1)
+        if sample_weight is not None:
+            per_row = per_row * np.asarray(sample_weight, np.float32).reshape(-1)
+        return float(per_row.mean())
+
+    # ---- checkpoints ------------------------------------------------------------------------------------
+    @staticmethod
+    def _ckpt_file(path: str) -> str:
+        return path if path.endswith(".npz") else path + ".npz"
+
+    def save_weights(self, path: str):
+        """Keras `save_weights(prefix)` (tutorial/2_multi_scale_NIF.ipynb:629): here one .npz keyed by the
+        reference variable names."""
+        f = self._ckpt_file(path)
+        d = os.path.dirname(f)
+        if d:
+            os.makedirs(d, exist_ok=True)
+        np.savez(f, **{k.replace("/", "|"): v for k, v in self.net.get_weights().items()})
+
+    def load_weights(self, path: str):
+        with np.load(self._ckpt_file(path)) as d:
+            self.net.set_weights({k.replace("|", "/"): d[k] for k in d.files})
+        return self

@@ -496,7 +496,7 @@ class MaterialisedTrainer:
         with torch.no_grad():
             for k, p in self.prm.items():
                 adam_tf(p, p.grad, self.m[k], self.v[k], self.t, self.lr)
-        return float(loss)
+        return float(loss.detach())
 
 
 # ----------------------------------------------------------------------------

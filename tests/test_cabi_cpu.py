@@ -1,0 +1,69 @@
+"""The C-ABI library loads without a GPU and exports every symbol include/nif_b200.h declares;
+descriptor validation and size queries are host-only and are checked here."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from oracle import nif_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "nif_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(nif_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported():
+    from nif_b200 import _lib
+    L = _lib.lib()
+    names = _declared()
+    assert len(names) >= 10
+    assert sorted(_lib.SYMBOLS) == names
+    for n in names:
+        assert getattr(L, n) is not None
+
+
+@pytest.mark.parametrize("variant,si,so,n,l,K", [(1, 2, 1, 64, 4, 32), (1, 3, 3, 128, 6, 64), (0, 1, 1, 30, 2, 1),
+                                                 (2, 2, 3, 12, 2, 3), (1, 1, 1, 64, 4, 32), (1, 3, 1, 128, 6, 64)])
+def test_query_sizes(variant, si, so, n, l, K):
+    from nif_b200 import _lib
+    L = _lib.lib()
+    d = _lib.Desc(variant, 2, si, so, n, l, K, 30.0, 0, 0)
+    s = _lib.Sizes()
+    assert L.nif_query_sizes(C.byref(d), 4096, C.byref(s)) == 0
+    H = 2 * l if variant == 2 else l
+    assert s.po_dim == O.po_dim(si, so, n, l, variant == 2)
+    assert s.n_layers == H + 2
+    assert s.np == (32 if n <= 32 else 64 if n <= 64 else 128)
+    assert s.save_floats_per_row == 2 * (H + 1) * s.np
+    assert s.packed_floats % 32 == 0
+    assert s.packed_floats >= (2 * H * s.np * s.np + si * s.np + s.np * so + (H + 2) * s.np) * (K + 1)
+    assert s.grad_ws_floats > (H + 1) * 4096 * s.np
+
+
+@pytest.mark.parametrize("field,value", [("variant", 7), ("si", 0), ("si", 99), ("so", 0), ("so", 99), ("n", 0),
+                                         ("n", 129), ("l", -1), ("K", -1), ("act", 42), ("dtype_compute", 3)])
+def test_bad_descriptor_is_rejected(field, value):
+    from nif_b200 import _lib
+    L = _lib.lib()
+    d = _lib.Desc(1, 1, 2, 1, 64, 4, 32, 30.0, 0, 0)
+    setattr(d, field, value)
+    s = _lib.Sizes()
+    rc = L.nif_query_sizes(C.byref(d), 1, C.byref(s))
+    assert rc in (-1, -3)
+    assert len(L.nif_last_error()) > 0
+
+
+def test_null_arguments_fail_before_touching_the_device():
+    from nif_b200 import _lib
+    L = _lib.lib()
+    d = _lib.Desc(1, 1, 2, 1, 64, 4, 32, 30.0, 0, 0)
+    assert L.nif_pack(C.byref(d), 1, None, None, None, None) == -2
+    assert L.nif_forward(C.byref(d), 1, 16, None, None, 0, None, None, None, None) == -2
+    assert L.nif_adam_step(16, None, None, None, None, 1e-3, 0.9, 0.999, 1e-7, 1, 0.0, 0.0, 1.0, None) == -2
+    assert L.nif_adam_step(16, None, None, None, None, 1e-3, 0.9, 0.999, 1e-7, 0, 0.0, 0.0, 1.0, None) == -2  # t >= 1
+    assert L.nif_forward(C.byref(d), 1, 0, None, None, 0, None, None, None, None) == 0  # empty batch is a no-op
