@@ -120,9 +120,10 @@ int nif_backward(const nif_desc_t* d, int64_t B, const float* z, const float* x,
 /* tf.keras.optimizers.Adam update (third-party in the reference):
  * m += (g-m)(1-b1); v += (g*g-v)(1-b2); p -= lr*sqrt(1-b2^t)/(1-b1^t) * m/(sqrt(v)+eps).
  * Optional kernel regularisers (nif/model.py:107-125): g += l1*sign(p) + 2*l2*p.
- * g_scale multiplies g first (e.g. 1/world_size). */
-int nif_adam_step(int64_t n, float* p, const float* g, float* m, float* v, float lr,
-                  float b1, float b2, float eps, int64_t t, float l1, float l2, float g_scale,
+ * g_scale multiplies g first (e.g. 1/world_size).  lr, b1, b2, eps are doubles because Keras forms
+ * 1-b1, 1-b2 and the bias-corrected step in Python floats before casting to the variable dtype. */
+int nif_adam_step(int64_t n, float* p, const float* g, float* m, float* v, double lr,
+                  double b1, double b2, double eps, int64_t t, float l1, float l2, float g_scale,
                   void* stream);
 
 /* Utility used by the benchmark: sustained FP32 FMA rate of this GPU (TFLOP/s),

@@ -78,7 +78,7 @@ def lib() -> C.CDLL:
     L.nif_forward_given_w.argtypes = [DP, I64, VP, VP, VP, VP]
     L.nif_mse_backward.argtypes = [DP, I64, VP, VP, VP, VP, VP, VP, VP, F, VP, VP, VP, F, VP, VP, VP]
     L.nif_backward.argtypes = [DP, I64, VP, VP, VP, VP, VP, VP, VP, F, VP, VP, VP]
-    L.nif_adam_step.argtypes = [I64, VP, VP, VP, VP, F, F, F, F, I64, F, F, F, VP]
+    L.nif_adam_step.argtypes = [I64, VP, VP, VP, VP, C.c_double, C.c_double, C.c_double, C.c_double, I64, F, F, F, VP]
     L.nif_measure_fp32_peak.argtypes = [C.POINTER(C.c_double)]
     for name in SYMBOLS:
         getattr(L, name)  # raises AttributeError if the build is stale

@@ -14,8 +14,8 @@ int nif_backward_impl(const Plan& pl, long long B, const float* z, const float* 
 int nif_mse_backward_impl(const Plan& pl, long long B, const float* z, const float* x, const float* packed,
                           const float* u, const float* save, const float* target, const float* sw, float inv_gb,
                           float* loss, float* dw_h, float* db_h, float beta, float* dz, float* ws, cudaStream_t st);
-int nif_adam_impl(long long n, float* p, const float* g, float* m, float* v, float lr, float b1, float b2, float eps,
-                  long long t, float l1, float l2, float gs, cudaStream_t st);
+int nif_adam_impl(long long n, float* p, const float* g, float* m, float* v, double lr, double b1, double b2,
+                  double eps, long long t, float l1, float l2, float gs, cudaStream_t st);
 struct GradWs {
   long long da, du, part_h, part_e, loss_part, total;
   int S_h, S_e, Q;
@@ -151,8 +151,8 @@ extern "C" int nif_backward(const nif_desc_t* d, int64_t B, const float* z, cons
                            static_cast<cudaStream_t>(stream));
 }
 
-extern "C" int nif_adam_step(int64_t n, float* p, const float* g, float* m, float* v, float lr, float b1, float b2,
-                             float eps, int64_t t, float l1, float l2, float g_scale, void* stream) {
+extern "C" int nif_adam_step(int64_t n, float* p, const float* g, float* m, float* v, double lr, double b1,
+                             double b2, double eps, int64_t t, float l1, float l2, float g_scale, void* stream) {
   if (n < 0 || t < 1) { nif_set_error("nif_adam_step: n=%lld t=%lld", (long long)n, (long long)t); return NIF_E_BAD_ARG; }
   if (n == 0) return NIF_OK;
   NIF_REQUIRE_PTR(p); NIF_REQUIRE_PTR(g); NIF_REQUIRE_PTR(m); NIF_REQUIRE_PTR(v);

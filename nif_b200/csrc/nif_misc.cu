@@ -124,13 +124,14 @@ int nif_given_w_impl(const Plan& pl, long long B, const float* x, const float* w
 // ---------------------------------------------------------------------------------------------------
 // Adam with tf.keras semantics (epsilon outside the bias correction); HBM-bound: 28 B / parameter.
 // ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, float alpha, float b1, float b2,
+// omb1 = 1 - beta_1, omb2 = 1 - beta_2 are formed in double on the host (Keras forms them in Python floats)
+__device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, float alpha, float omb1, float omb2,
                                          float eps, float l1, float l2, float gs) {
   g *= gs;
   if (l1 != 0.f) g += l1 * (p > 0.f ? 1.f : (p < 0.f ? -1.f : 0.f));
   if (l2 != 0.f) g += 2.f * l2 * p;
-  m += (g - m) * (1.f - b1);
-  v += (g * g - v) * (1.f - b2);
+  m += (g - m) * omb1;
+  v += (g * g - v) * omb2;
   p -= alpha * m / (sqrtf(v) + eps);
 }
 
@@ -156,15 +157,15 @@ __global__ void __launch_bounds__(256) nif_adam_kernel(long long n, float* __res
     adam_one(p[i], g[i], m[i], v[i], alpha, b1, b2, eps, l1, l2, gs);
 }
 
-int nif_adam_impl(long long n, float* p, const float* g, float* m, float* v, float lr, float b1, float b2, float eps,
-                  long long t, float l1, float l2, float gs, cudaStream_t st) {
+int nif_adam_impl(long long n, float* p, const float* g, float* m, float* v, double lr, double b1, double b2,
+                  double eps, long long t, float l1, float l2, float gs, cudaStream_t st) {
   if (n <= 0) return NIF_OK;
-  const double alpha = (double)lr * std::sqrt(1.0 - std::pow((double)b2, (double)t)) /
-                       (1.0 - std::pow((double)b1, (double)t));
+  const double alpha = lr * std::sqrt(1.0 - std::pow(b2, (double)t)) / (1.0 - std::pow(b1, (double)t));
   long long nblk = (n / 4 + 255) / 256;
   if (nblk < 1) nblk = 1;
   if (nblk > 148 * 8) nblk = 148 * 8;
-  nif_adam_kernel<<<(unsigned)nblk, 256, 0, st>>>(n, p, g, m, v, (float)alpha, b1, b2, eps, l1, l2, gs);
+  nif_adam_kernel<<<(unsigned)nblk, 256, 0, st>>>(n, p, g, m, v, (float)alpha, (float)(1.0 - b1),
+                                                  (float)(1.0 - b2), (float)eps, l1, l2, gs);
   NIF_CUDA_CHECK(cudaGetLastError());
   return NIF_OK;
 }

@@ -1,8 +1,363 @@
-// Forward-mode tangents through the fused path (JacobianLayer replacement) -- filled in below.
+// Forward-mode tangents through the fused path: the B200 realisation of JacobianLayer
+// (nif/layers/gradient.py:36-49, 207-231), which in the reference costs one reverse pass per output.
+//
+// For a direction d with latent tangent zd (from the ParameterNet trunk, zero for a pure coordinate
+// direction) and coordinate tangent xd:
+//   pre_m    = sum_k zt[k] (omega h M_m[k] + C_m[k])
+//   pre_m'   = sum_k zt[k] omega (h' M_m[k])  +  sum_k zd[k] (omega h M_m[k] + C_m[k])
+//   h_{m+1}  = alpha act(pre_m) (+ residual),   h_{m+1}' = alpha act'(pre_m) pre_m' (+ residual')
+// The weight stream is shared: every staged chunk M_m[k] is used by the primal GEMM and by one GEMM
+// per direction, and the primal product is reused for the zd term.
 #include "nif_tile.cuh"
+
+struct TanArgs {
+  long long B, total_tiles;
+  const float *z, *x, *packed, *zdot, *xdot;  // zdot [ND][B][K], xdot [ND][B][si] (either may be null)
+  float *u, *udot;                            // udot [ND][B][so]
+};
+
+using TCfg32 = TileCfg<32, 128, 1, 1>;
+using TCfg64 = TileCfg<64, 64, 1, 1>;
+using TCfg128 = TileCfg<128, 64, 1, 2>;
+
+template <class C, int ND>
+__host__ __device__ inline size_t tan_smem_bytes(int K, int si, int so) {
+  size_t f = 2 * (size_t)C::STAGE_FLOATS + (size_t)(1 + ND) * C::NP * C::TB + (size_t)(1 + ND) * (K + 1) * C::TB +
+             (size_t)(1 + ND) * si * C::TB + (size_t)(1 + ND) * so * C::NT;
+  return f * 4 + 64;
+}
+
+template <class C, int ND, bool RES>
+__global__ void __launch_bounds__(C::NT, 1) nif_tangent_kernel(const Plan pl, const TanArgs a) {
+  constexpr int NP = C::NP, TB = C::TB, MP = C::MP, MJ = C::MJ, NT = C::NT, NS = 1 + ND;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* stage = reinterpret_cast<float*>(smem_raw);
+  float* act = stage + 2 * C::STAGE_FLOATS;          // [NS][NP][TB]  stream 0 = primal
+  float* zs = act + NS * NP * TB;                    // [NS][K+1][TB]
+  float* xs = zs + NS * (pl.K + 1) * TB;             // [NS][si][TB]
+  float* ys = xs + NS * pl.si * TB;                  // [NS][so][NT] scratch of the last layer
+  uint64_t* bar = reinterpret_cast<uint64_t*>(ys + NS * pl.so * NT);
+  bar = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(bar) + 7) & ~uintptr_t(7));
+
+  const int tid = threadIdx.x;
+  const int tj = tid % C::TY, tp = tid / C::TY;
+  const int K = pl.K, K1 = pl.K + 1, H = pl.H, n = pl.n, si = pl.si, so = pl.so;
+
+  if (tid == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  long long my_tiles = 0;
+  if ((long long)blockIdx.x < a.total_tiles) my_tiles = (a.total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+  WeightStream<C> ws;
+  ws.stage = stage;
+  ws.bar = bar;
+  ws.chunks_per_tile = H * K1 * C::NH;
+  ws.total = my_tiles * ws.chunks_per_tile;
+  ws.issued = 0;
+  ws.consumed = 0;
+  ws.H = H;
+  ws.K1 = K1;
+  ws.packed = a.packed;
+  ws.packed_floats = pl.packed_floats;
+  ws.sec_off = pl.off_MH;
+  ws.tiles_per_group = a.total_tiles;
+  ws.reverse = false;
+  if (tid == 0) {
+    while (ws.issued < 2 && ws.issued < ws.total) ws.issue_one();
+  }
+  const float* C_all = a.packed + pl.off_C;
+
+  auto load_rows4 = [&](const float* base, float (&v)[MP]) {  // MP consecutive-group rows from a [..][TB] row
+#pragma unroll
+    for (int gp = 0; gp < C::GP; ++gp) {
+      const float4 q = *reinterpret_cast<const float4*>(&base[gp * C::PSTR + tp * 4]);
+      v[gp * 4] = q.x; v[gp * 4 + 1] = q.y; v[gp * 4 + 2] = q.z; v[gp * 4 + 3] = q.w;
+    }
+  };
+
+  for (long long t = 0; t < my_tiles; ++t) {
+    const long long tile = blockIdx.x + t * gridDim.x;
+    const long long row0 = tile * TB;
+    // ---- stage z, zdot, x, xdot --------------------------------------------------------------------
+    for (int s = 0; s < NS; ++s) {
+      const float* zsrc = (s == 0) ? a.z : (a.zdot ? a.zdot + (long long)(s - 1) * a.B * K : nullptr);
+      for (int idx = tid; idx < TB * K; idx += NT) {
+        const int p = idx / K, kk = idx - p * K;
+        const long long b = row0 + p;
+        zs[(s * K1 + kk) * TB + p] = (zsrc && b < a.B) ? __ldg(&zsrc[b * K + kk]) : 0.f;
+      }
+      for (int p = tid; p < TB; p += NT) zs[(s * K1 + K) * TB + p] = (s == 0) ? 1.f : 0.f;
+      const float* xsrc = (s == 0) ? a.x : (a.xdot ? a.xdot + (long long)(s - 1) * a.B * si : nullptr);
+      for (int idx = tid; idx < TB * si; idx += NT) {
+        const int p = idx / si, i = idx - p * si;
+        const long long b = row0 + p;
+        xs[(s * si + i) * TB + p] = (xsrc && b < a.B) ? __ldg(&xsrc[b * si + i]) : 0.f;
+      }
+    }
+    __syncthreads();
+
+    float acc[NS][MP][MJ];
+    float carry[RES ? NS : 1][RES ? MP : 1][RES ? MJ : 1];
+
+    auto zero_acc = [&]() {
+#pragma unroll
+      for (int s = 0; s < NS; ++s)
+#pragma unroll
+        for (int r = 0; r < MP; ++r)
+#pragma unroll
+          for (int c = 0; c < MJ; ++c) acc[s][r][c] = 0.f;
+    };
+
+    // fold one partial product into the accumulators.  stream 0 product (from h): goes to acc[0] scaled
+    // by zt and to acc[d] scaled by zd_d; stream d product (from h'_d): goes to acc[d] scaled by zt.
+    auto fold = [&](int s, const float (&tmp)[MP][MJ], int m, int kk, float om, bool with_bias) {
+      float cv[MJ];
+#pragma unroll
+      for (int gj = 0; gj < C::GJ; ++gj) {
+        float4 cb = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (with_bias && s == 0) cb = ldg4(&C_all[((long long)m * K1 + kk) * NP + gj * C::JSTR + tj * 4]);
+        cv[gj * 4] = cb.x; cv[gj * 4 + 1] = cb.y; cv[gj * 4 + 2] = cb.z; cv[gj * 4 + 3] = cb.w;
+      }
+      float zv[MP];
+      load_rows4(&zs[(0 * K1 + kk) * TB], zv);
+#pragma unroll
+      for (int r = 0; r < MP; ++r)
+#pragma unroll
+        for (int c = 0; c < MJ; ++c) acc[s][r][c] = fmaf(zv[r], fmaf(om, tmp[r][c], cv[c]), acc[s][r][c]);
+      if (s == 0) {
+#pragma unroll
+        for (int d = 1; d < NS; ++d) {
+          float zd[MP];
+          load_rows4(&zs[(d * K1 + kk) * TB], zd);
+#pragma unroll
+          for (int r = 0; r < MP; ++r)
+#pragma unroll
+            for (int c = 0; c < MJ; ++c) acc[d][r][c] = fmaf(zd[r], fmaf(om, tmp[r][c], cv[c]), acc[d][r][c]);
+        }
+      }
+    };
+
+    auto epilogue = [&](int m) {
+      const float alpha = plan_alpha(pl, m);
+      const int res = plan_res(pl, m);
+      float outv[NS][MP][MJ];
+#pragma unroll
+      for (int r = 0; r < MP; ++r)
+#pragma unroll
+        for (int c = 0; c < MJ; ++c) {
+          float f, d;
+          act_fd(pl.act, acc[0][r][c], f, d);
+          const int j = col_of<C>(tj, c);
+          const int ai = act_idx<C>(j, row_of<C>(tp, r));
+#pragma unroll
+          for (int s = 0; s < NS; ++s) {
+            float o = (s == 0) ? alpha * f : alpha * d * acc[s][r][c];
+            if (res == 1) o += act[s * NP * TB + ai];
+            if (RES) {
+              if (res == 2) carry[RES ? s : 0][RES ? r : 0][RES ? c : 0] = act[s * NP * TB + ai];
+              if (res == 3) o += 0.5f * carry[RES ? s : 0][RES ? r : 0][RES ? c : 0];
+            }
+            if (j >= n) o = 0.f;
+            outv[s][r][c] = o;
+          }
+        }
+#pragma unroll
+      for (int s = 0; s < NS; ++s)
+#pragma unroll
+        for (int c = 0; c < MJ; ++c) {
+          const int j = col_of<C>(tj, c);
+#pragma unroll
+          for (int gp = 0; gp < C::GP; ++gp) {
+            const int p0 = gp * C::PSTR + tp * 4;
+            *reinterpret_cast<float4*>(&act[s * NP * TB + act_idx<C>(j, p0)]) = make_float4(
+                outv[s][gp * 4][c], outv[s][gp * 4 + 1][c], outv[s][gp * 4 + 2][c], outv[s][gp * 4 + 3][c]);
+          }
+        }
+      __syncthreads();
+    };
+
+    // ---- layer 0 ----------------------------------------------------------------------------------------
+    {
+      const float om = plan_omega(pl, 0);
+      const float* M0 = a.packed + pl.off_M0;
+      zero_acc();
+      for (int kk = 0; kk < K1; ++kk) {
+#pragma unroll 1
+        for (int s = 0; s < NS; ++s) {
+          float tmp[MP][MJ];
+#pragma unroll
+          for (int r = 0; r < MP; ++r)
+#pragma unroll
+            for (int c = 0; c < MJ; ++c) tmp[r][c] = 0.f;
+          for (int i = 0; i < si; ++i) {
+            float xv[MP];
+            load_rows4(&xs[(s * si + i) * TB], xv);
+#pragma unroll
+            for (int gj = 0; gj < C::GJ; ++gj) {
+              const float4 w = ldg4(&M0[((long long)kk * si + i) * NP + gj * C::JSTR + tj * 4]);
+              const float wv[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+              for (int r = 0; r < MP; ++r)
+#pragma unroll
+                for (int f = 0; f < 4; ++f) tmp[r][gj * 4 + f] = fmaf(xv[r], wv[f], tmp[r][gj * 4 + f]);
+            }
+          }
+          if (s == 0) fold(0, tmp, 0, kk, om, true);
+          else if (s == 1) fold(1, tmp, 0, kk, om, false);
+          else if (ND >= 2 && s == 2) fold(ND >= 2 ? 2 : 0, tmp, 0, kk, om, false);
+        }
+      }
+      epilogue(0);
+    }
+
+    // ---- hidden layers --------------------------------------------------------------------------------------
+    for (int m = 1; m <= H; ++m) {
+      const float om = plan_omega(pl, m);
+      zero_acc();
+      for (int kk = 0; kk < K1; ++kk) {
+#pragma unroll 1
+        for (int hf = 0; hf < C::NH; ++hf) {
+          const float* st = ws.acquire();
+#pragma unroll 1
+          for (int s = 0; s < NS; ++s) {
+            float tmp[MP][MJ];
+#pragma unroll
+            for (int r = 0; r < MP; ++r)
+#pragma unroll
+              for (int c = 0; c < MJ; ++c) tmp[r][c] = 0.f;
+            mk_gemm<C>(act + s * NP * TB, st, hf * C::NIS, tmp, tp, tj);
+            if (s == 0) fold(0, tmp, m, kk, om, hf == 0);
+            else if (s == 1) fold(1, tmp, m, kk, om, false);
+            else if (ND >= 2 && s == 2) fold(ND >= 2 ? 2 : 0, tmp, m, kk, om, false);
+          }
+          ws.release();
+        }
+      }
+      epilogue(m);
+    }
+
+    // ---- last layer: one thread per (row, kappa slice), all streams -------------------------------------------
+    {
+      const float* ML = a.packed + pl.off_ML;
+      const float* CL = C_all + (long long)(H + 1) * K1 * NP;
+      const int nsl = NT / TB;
+      const int p = tid % TB, q = tid / TB;
+      float y[NS][NIF_MAX_SO];
+#pragma unroll
+      for (int s = 0; s < NS; ++s)
+#pragma unroll
+        for (int c = 0; c < NIF_MAX_SO; ++c) y[s][c] = 0.f;
+      for (int kk = q; kk < K1; kk += nsl) {
+        float sacc[NS][NIF_MAX_SO];
+#pragma unroll
+        for (int s = 0; s < NS; ++s)
+#pragma unroll
+          for (int c = 0; c < NIF_MAX_SO; ++c) sacc[s][c] = (s == 0 && c < so) ? __ldg(&CL[(long long)kk * NP + c]) : 0.f;
+        const float* Mk = ML + (long long)kk * NP * so;
+        for (int i = 0; i < n; ++i) {
+          float hv[NS];
+#pragma unroll
+          for (int s = 0; s < NS; ++s) hv[s] = act[s * NP * TB + act_idx<C>(i, p)];
+#pragma unroll
+          for (int c = 0; c < NIF_MAX_SO; ++c)
+            if (c < so) {
+              const float w = __ldg(&Mk[i * so + c]);
+#pragma unroll
+              for (int s = 0; s < NS; ++s) sacc[s][c] = fmaf(hv[s], w, sacc[s][c]);
+            }
+        }
+        const float zk = zs[(0 * K1 + kk) * TB + p];
+#pragma unroll
+        for (int c = 0; c < NIF_MAX_SO; ++c) {
+          y[0][c] = fmaf(zk, sacc[0][c], y[0][c]);
+#pragma unroll
+          for (int d = 1; d < NS; ++d) {
+            y[d][c] = fmaf(zk, sacc[d][c], y[d][c]);
+            y[d][c] = fmaf(zs[(d * K1 + kk) * TB + p], sacc[0][c], y[d][c]);
+          }
+        }
+      }
+      // combine the kappa slices through shared memory (slot q of thread p)
+#pragma unroll
+      for (int s = 0; s < NS; ++s)
+#pragma unroll
+        for (int c = 0; c < NIF_MAX_SO; ++c)
+          if (c < so) ys[(s * so + c) * NT + q * TB + p] = y[s][c];
+      __syncthreads();
+      if (q == 0) {
+        const long long b = row0 + p;
+        if (b < a.B) {
+#pragma unroll
+          for (int s = 0; s < NS; ++s)
+#pragma unroll
+            for (int c = 0; c < NIF_MAX_SO; ++c)
+              if (c < so) {
+                float v = 0.f;
+                for (int qq = 0; qq < nsl; ++qq) v += ys[(s * so + c) * NT + qq * TB + p];
+                if (s == 0) a.u[b * so + c] = v;
+                else a.udot[((long long)(s - 1) * a.B + b) * so + c] = v;
+              }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+template <class C, int ND>
+static int launch_tan(const Plan& pl, TanArgs a, cudaStream_t st) {
+  const size_t smem = tan_smem_bytes<C, ND>(pl.K, pl.si, pl.so);
+  if (smem > 227 * 1024) {
+    nif_set_error("tangent tile needs %zu B of shared memory (latent_dim too large for this build)", smem);
+    return NIF_E_UNSUPPORTED;
+  }
+  const bool res = pl.variant == NIF_VARIANT_SIREN_RES;
+  auto kern = res ? nif_tangent_kernel<C, ND, true> : nif_tangent_kernel<C, ND, false>;
+  NIF_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int dev = 0, sms = 0, occ = 0;
+  NIF_CUDA_CHECK(cudaGetDevice(&dev));
+  NIF_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  NIF_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, C::NT, smem));
+  if (occ < 1) occ = 1;
+  a.total_tiles = (a.B + C::TB - 1) / C::TB;
+  long long grid = (long long)sms * occ;
+  if (grid > a.total_tiles) grid = a.total_tiles;
+  if (grid < 1) return NIF_OK;
+  kern<<<(unsigned)grid, C::NT, smem, st>>>(pl, a);
+  NIF_CUDA_CHECK(cudaGetLastError());
+  return NIF_OK;
+}
+
+template <int ND>
+static int dispatch_tan(const Plan& pl, const TanArgs& a, cudaStream_t st) {
+  switch (pl.NP) {
+    case 32: return launch_tan<TCfg32, ND>(pl, a, st);
+    case 64: return launch_tan<TCfg64, ND>(pl, a, st);
+    case 128: return launch_tan<TCfg128, ND>(pl, a, st);
+  }
+  nif_set_error("unsupported padded width %d", pl.NP);
+  return NIF_E_UNSUPPORTED;
+}
 
 int nif_tangent_impl(const Plan& pl, long long B, const float* z, const float* x, const float* packed, int n_dir,
                      const float* zdot, const float* xdot, float* u, float* udot, cudaStream_t st) {
-  nif_set_error("nif_forward_tangent: not built yet");
-  return NIF_E_UNSUPPORTED;
+  // directions are processed two at a time (the primal is recomputed per pair)
+  for (int d0 = 0; d0 < n_dir; d0 += 2) {
+    TanArgs a;
+    a.B = B;
+    a.total_tiles = 0;
+    a.z = z; a.x = x; a.packed = packed;
+    a.zdot = zdot ? zdot + (long long)d0 * B * pl.K : nullptr;
+    a.xdot = xdot ? xdot + (long long)d0 * B * pl.si : nullptr;
+    a.u = u;
+    a.udot = udot + (long long)d0 * B * pl.so;
+    const int nd = (n_dir - d0) >= 2 ? 2 : 1;
+    const int rc = nd == 2 ? dispatch_tan<2>(pl, a, st) : dispatch_tan<1>(pl, a, st);
+    if (rc != NIF_OK) return rc;
+  }
+  return NIF_OK;
 }

@@ -227,7 +227,8 @@ def test_full_size_properties_c2():
     # oracle on a sample of rows
     idx = torch.arange(0, B, 997)
     y64 = O.shape_net(spec, x[idx].cpu().double(), O.hyper_linear(z[idx].cpu().double(), prm[wn], prm[bn]))
-    assert rel_err(u1[idx].cpu(), y64) < 1e-5
+    y32 = O.shape_net(spec, x[idx].cpu(), O.hyper_linear(z[idx].cpu(), prm[wn].float(), prm[bn].float()))
+    assert _gate(rel_err(u1[idx].cpu(), y64), rel_err(y32, y64))
     # reverse pass: deterministic, and linear in the seed
     du = torch.randn(B, 1, generator=g).to(dev)
     dw1, db1 = torch.empty_like(w_h), torch.empty_like(b_h)
@@ -245,3 +246,52 @@ def test_full_size_properties_c2():
     eng.backward(z[:h].contiguous(), x[:h].contiguous(), packed, st_a, du[:h].contiguous(), dwa, dba)
     eng.backward(z[h:].contiguous(), x[h:].contiguous(), packed, st_b, du[h:].contiguous(), dwa, dba, beta=1.0)
     assert rel_err(dwa.cpu(), dw1.cpu()) < 1e-5 and rel_err(dba.cpu(), db1.cpu()) < 1e-5
+
+
+@pytest.mark.parametrize("case", ["siren_2x30", "nif_tanh_si3_so2", "siren_res_so3_n12_K3_sine"])
+def test_jacobian_layer_matches_reference_golden(case):
+    """JacobianLayer via forward tangents vs the reference's compute_output_and_grad (golden `jac`)."""
+    import nif_b200
+    from nif_b200.layers import JacobianLayer
+    d, cls, cfg_s, cfg_p, spec, prm, _ = load_golden(case)
+    net = getattr(nif_b200, cls)(cfg_s, cfg_p, seed=0, device="cuda:0")
+    net.set_weights({k: v.float().numpy() for k, v in prm.items()})
+    yi, xi = list(d["jac_y_index"]), list(d["jac_x_index"])
+    y, J = JacobianLayer(net.build(), yi, xi)(d["inputs"].astype(np.float32))
+    assert tuple(J.shape) == d["jac"].shape
+    prm32 = {k: v.float() for k, v in prm.items()}
+    _, J32 = O.jacobian(spec, prm32, torch.as_tensor(d["inputs"]).float(), yi, xi)
+    assert _gate(rel_err(y.cpu(), d["y"]), rel_err(d["y32"], d["y"]))
+    assert _gate(rel_err(J.cpu(), d["jac"]), rel_err(J32, d["jac"]), floor=2e-5)
+
+
+@pytest.mark.parametrize("variant,si,so,n,l,K,B,dirs", [("siren", 1, 1, 64, 4, 32, 300, [0, 1]),   # C4: d/dt, d/dx
+                                                         ("siren", 3, 3, 128, 1, 4, 100, [0, 1, 2, 3]),
+                                                         ("siren_res", 2, 1, 64, 1, 3, 70, [2]),
+                                                         ("nif", 2, 2, 30, 2, 2, 150, [1, 0, 2])])
+def test_tangents_random(variant, si, so, n, l, K, B, dirs):
+    spec, prm, inputs, _, _ = _random_problem(variant, si, so, n, l, K, B, seed=K + n)
+    dev = torch.device("cuda:0")
+    wn, bn = O.last_layer_names(spec)
+    yi = list(range(so))
+    y64, J64 = O.jacobian(spec, prm, inputs, yi, dirs)
+    y32, J32 = O.jacobian(spec, {k: v.float() for k, v in prm.items()}, inputs.float(), yi, dirs)
+    # latent tangents from the oracle trunk (forward-mode through the trunk is plain torch in the product)
+    p_in = inputs[:, :1].clone().requires_grad_(True)
+    z = O.latent(spec, prm, p_in)
+    zdot = torch.zeros(len(dirs), B, K, dtype=torch.float64)
+    xdot = torch.zeros(len(dirs), B, si, dtype=torch.float64)
+    for d, c in enumerate(dirs):
+        if c == 0:
+            for k in range(K):
+                (g,) = torch.autograd.grad(z[:, k].sum(), p_in, retain_graph=True)
+                zdot[d, :, k] = g[:, 0]
+        else:
+            xdot[d, :, c - 1] = 1.0
+    eng = _engine(spec)
+    packed = eng.pack(prm[wn].float().to(dev), prm[bn].float().to(dev))
+    u, udot = eng.forward_tangent(z.detach().float().to(dev), inputs[:, 1:].float().contiguous().to(dev), packed,
+                                  zdot.float().to(dev), xdot.float().to(dev))
+    J = udot.permute(1, 2, 0)
+    assert _gate(rel_err(u.cpu(), y64.detach()), rel_err(y32.detach(), y64.detach()))
+    assert _gate(rel_err(J.cpu(), J64), rel_err(J32, J64), floor=2e-5)
