@@ -65,6 +65,7 @@ extern "C" int nif_pack(const nif_desc_t* d, int64_t G, const float* w_h, const 
   if (pl.K > 0 && G != 1) { nif_set_error("nif_pack: G>1 requires K==0 (explicit weight vectors in b_h)"); return NIF_E_BAD_ARG; }
   NIF_REQUIRE_PTR(b_h);
   NIF_REQUIRE_PTR(packed);
+  if (pl.tc && G != 1) { nif_set_error("nif_pack: the tensor-core image (dtype_compute=2) is built for G==1"); return NIF_E_BAD_ARG; }
   return nif_pack_impl(pl, G, w_h, b_h, packed, static_cast<cudaStream_t>(stream));
 }
 

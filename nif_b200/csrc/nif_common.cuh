@@ -28,7 +28,17 @@ struct Plan {
   int P;    // po_dim
   float omega0;
   long long off_MH, off_MHT, off_M0, off_ML, off_C, packed_floats;
+  // tensor-core operand images (dtype_compute == 2, NP == 64).  fp32-grade accuracy on the fp16 tensor-core
+  // path: every value is scaled by a power of two and split  x * 2^e = hi + lo  (two fp16), products use the
+  // three terms hi*hi + lo*hi + hi*lo accumulated in fp32.  Per hidden matrix h and per chunk c of 2 latent
+  // coordinates the image holds a [hi | lo] pair of 128x64 fp16 tiles (16 KB each) in the UMMA K-major
+  // core-matrix layout (nif_tc.cuh):
+  //   TCF: rows (kappa_l, j), K = i  (forward)        TCB: rows (kappa_l, i), K = j  (reverse data pass)
+  //   TCS: [H][KP] fp32 inverse scales 2^-e of slab (h, kappa)   (KP = K+1 rounded up to even, NCH = KP/2)
+  int tc, KP, NCH;
+  long long off_TCF, off_TCB, off_TCS;
 };
+#define NIF_TC_CHUNK_FLOATS 8192   // [hi | lo] x 128 x 64 fp16 = 32 KB, counted in floats
 
 __host__ __device__ inline int plan_w_off(const Plan& p, int m) {  // reference column offset of matrix m
   if (m == 0) return 0;

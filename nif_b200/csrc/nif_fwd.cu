@@ -322,8 +322,15 @@ static int dispatch_fwd(const Plan& pl, const FwdArgs& a, cudaStream_t st) {
   return save ? launch_fwd<C, false, true>(pl, a, st) : launch_fwd<C, false, false>(pl, a, st);
 }
 
+int nif_tc_forward_impl(const Plan& pl, long long B, const float* z, const float* x, const float* packed, float* u,
+                        float* save, cudaStream_t st);
+
 int nif_forward_impl(const Plan& pl, long long G, long long B, const float* z, const float* x, int x_shared,
                      const float* packed, float* u, float* save, cudaStream_t st) {
+  if (pl.tc && G == 1) {  // tensor-core path; shapes it does not cover fall through to the CUDA-core kernel
+    const int rc = nif_tc_forward_impl(pl, B, z, x, packed, u, save, st);
+    if (rc != NIF_E_UNSUPPORTED) return rc;
+  }
   FwdArgs a;
   a.G = G;
   a.B = B;

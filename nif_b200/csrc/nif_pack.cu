@@ -5,6 +5,7 @@
 // 769-846, 883-933).  Here the same offsets are applied ONCE to the shared [K,P] / [P] parameters.
 #include <cstdarg>
 #include <cstdio>
+#include <cuda_fp16.h>
 #include "nif_common.cuh"
 
 static thread_local char g_err[512] = "";
@@ -28,7 +29,14 @@ int nif_make_plan(const nif_desc_t* d, Plan* out) {
   if (d->l < 0 || d->l > 64) { nif_set_error("nlayers=%d outside [0,64]", d->l); return NIF_E_BAD_DESC; }
   if (d->K < 0 || d->K > 256) { nif_set_error("latent_dim=%d outside [0,256]", d->K); return NIF_E_BAD_DESC; }
   if (d->act < 0 || d->act > NIF_ACT_SIGMOID) { nif_set_error("activation id %d unknown", d->act); return NIF_E_BAD_DESC; }
-  if (d->dtype_compute != 0) { nif_set_error("dtype_compute=%d: only the fp32 path is built", d->dtype_compute); return NIF_E_UNSUPPORTED; }
+  if (d->dtype_compute != 0 && d->dtype_compute != 2) {
+    nif_set_error("dtype_compute=%d: built paths are 0 (fp32 CUDA cores) and 2 (3xTF32 tensor cores)", d->dtype_compute);
+    return NIF_E_UNSUPPORTED;
+  }
+  if (d->dtype_compute == 2 && (d->n <= 32 || d->n > 64)) {
+    nif_set_error("dtype_compute=2 (tensor cores) is built for 32 < units <= 64 only (got %d)", d->n);
+    return NIF_E_UNSUPPORTED;
+  }
   Plan p;
   p.variant = d->variant;
   p.act = d->variant == NIF_VARIANT_NIF ? d->act : NIF_ACT_SINE;
@@ -45,6 +53,16 @@ int nif_make_plan(const nif_desc_t* d, Plan* out) {
   p.off_M0 = off;  off += up4(K1 * p.si * NP);
   p.off_ML = off;  off += up4(K1 * NP * p.so);
   p.off_C = off;   off += up4((long long)p.Lm * K1 * NP);
+  p.tc = d->dtype_compute == 2 ? 1 : 0;
+  p.KP = (p.K + 2) / 2 * 2;
+  p.NCH = p.KP / 2;
+  p.off_TCF = p.off_TCB = p.off_TCS = 0;
+  if (p.tc) {
+    off = (off + 31) / 32 * 32;
+    p.off_TCF = off; off += (long long)p.H * p.NCH * NIF_TC_CHUNK_FLOATS;
+    p.off_TCB = off; off += (long long)p.H * p.NCH * NIF_TC_CHUNK_FLOATS;
+    p.off_TCS = off; off += up4((long long)p.H * p.KP);
+  }
   p.packed_floats = (off + 31) / 32 * 32;  // keep every image 128-byte aligned
   *out = p;
   return NIF_OK;
@@ -93,7 +111,7 @@ __global__ void __launch_bounds__(256) nif_pack_kernel(const Plan pl, long long 
         const int i = r % NP; const int kk = (int)(r / NP);
         if (i < n) v = src_at(pl, w_h, b_h, g, kk, plan_w_off(pl, H + 1) + i * pl.so + c);
       }
-    } else {  // C [Lm][K1][NP]
+    } else if (!pl.tc || r < pl.off_TCF) {  // C [Lm][K1][NP]
       r -= pl.off_C;
       if (r < (long long)pl.Lm * K1 * NP) {
         const int j = r % NP; r /= NP;
@@ -101,12 +119,75 @@ __global__ void __launch_bounds__(256) nif_pack_kernel(const Plan pl, long long 
         const int width = (m == pl.Lm - 1) ? pl.so : n;
         if (j < width) v = src_at(pl, w_h, b_h, g, kk, plan_b_off(pl, m) + j);
       }
+    } else if (r < pl.off_TCS) {
+      // tensor-core operand tiles (fp16 pairs stored in one float slot).  Within a 128x64 fp16 tile, element
+      // (row nrow, col kcol) lives at byte offset (nrow/8)*1024 + (kcol/8)*128 + (nrow%8)*16 + (kcol%8)*2.
+      const bool fwd = r < pl.off_TCB;
+      r -= fwd ? pl.off_TCF : pl.off_TCB;
+      int t = (int)(r % 4096); r /= 4096;           // float slot inside a 16 KB tile
+      const int lo = (int)(r % 2); r /= 2;
+      const int c = (int)(r % pl.NCH); const int h = (int)(r / pl.NCH);
+      const int kq2 = t % 4; t /= 4;
+      const int rq = t % 8; t /= 8;
+      const int kc = t % 8; const int rg = t / 8;
+      const int nrow = rg * 8 + rq, kcol = kc * 8 + kq2 * 2;
+      const int kk = 2 * c + nrow / 64, a = nrow % 64;
+      float w[2] = {0.f, 0.f};
+      if (kk < K1) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int i = fwd ? kcol + q : a, j = fwd ? a : kcol + q;  // fwd rows are j (K = i); reverse rows are i (K = j)
+          if (i < n && j < n) w[q] = src_at(pl, w_h, b_h, g, kk, plan_w_off(pl, h + 1) + i * n + j);
+        }
+      }
+      const float sc = 1.0f / packed[g * pl.packed_floats + pl.off_TCS + h * pl.KP + kk];  // exact power of two
+      __half2 out;
+      if (!lo) {
+        out = __floats2half2_rn(w[0] * sc, w[1] * sc);
+      } else {
+        const float a0 = w[0] * sc, a1 = w[1] * sc;
+        out = __floats2half2_rn(a0 - __half2float(__float2half_rn(a0)), a1 - __half2float(__float2half_rn(a1)));
+      }
+      v = __uint_as_float(*reinterpret_cast<uint32_t*>(&out));
+    } else {
+      continue;  // TCS is written by nif_pack_scales_kernel before this kernel runs
     }
     packed[e] = v;
   }
 }
 
+// one block per (hidden matrix, kappa): inverse power-of-two scale of the slab so that max|M| * 2^e is in [2^13, 2^14)
+__global__ void __launch_bounds__(256) nif_pack_scales_kernel(const Plan pl, const float* __restrict__ w_h,
+                                                              const float* __restrict__ b_h, float* __restrict__ packed) {
+  const int h = blockIdx.x / pl.KP, kk = blockIdx.x % pl.KP;
+  const int n = pl.n;
+  float m = 0.f;
+  if (kk <= pl.K)
+    for (int e = threadIdx.x; e < n * n; e += 256) m = fmaxf(m, fabsf(src_at(pl, w_h, b_h, 0, kk, plan_w_off(pl, h + 1) + e)));
+  __shared__ float red[256];
+  red[threadIdx.x] = m;
+  __syncthreads();
+  for (int o = 128; o >= 1; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] = fmaxf(red[threadIdx.x], red[threadIdx.x + o]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    float inv = 1.0f;
+    const float mx = red[0];
+    if (mx > 0.f && mx < 3.0e38f) {
+      int ex = (int)((__float_as_uint(mx) >> 23) & 0xFF) - 127;  // floor(log2(max)) for normal numbers
+      ex = max(-100, min(100, ex));
+      inv = __uint_as_float((uint32_t)(127 + ex - 13) << 23);    // 2^(ex-13): scaled max lands in [2^13, 2^14)
+    }
+    packed[pl.off_TCS + h * pl.KP + kk] = inv;
+  }
+}
+
 int nif_pack_impl(const Plan& pl, long long G, const float* w_h, const float* b_h, float* packed, cudaStream_t st) {
+  if (pl.tc && pl.H > 0) {
+    nif_pack_scales_kernel<<<(unsigned)(pl.H * pl.KP), 256, 0, st>>>(pl, w_h, b_h, packed);
+    NIF_CUDA_CHECK(cudaGetLastError());
+  }
   const long long total = G * pl.packed_floats;
   long long nblk = (total + 255) / 256;
   if (nblk > 148 * 16) nblk = 148 * 16;

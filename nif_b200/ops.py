@@ -42,16 +42,21 @@ class FusedShapeNet:
     linear layer (w_h, b_h) instead.
     """
 
+    COMPUTE = {"fp32": 0, "tf32x3": 2}
+
     def __init__(self, variant: str, si: int, so: int, n: int, l: int, K: int,
-                 activation: Optional[str] = "swish", omega0: float = 1.0):
+                 activation: Optional[str] = "swish", omega0: float = 1.0, compute: str = "fp32"):
         if variant not in VARIANT:
             raise ValueError(f"variant must be one of {list(VARIANT)}")
         if variant == "nif" and activation not in ACT:
             raise ValueError(f"activation {activation!r} is not supported by the fused kernels {list(ACT)}")
         self.variant, self.si, self.so, self.n, self.l, self.K = variant, si, so, n, l, K
         self.activation, self.omega0 = activation, float(omega0)
+        if compute not in self.COMPUTE:
+            raise ValueError(f"compute must be one of {list(self.COMPUTE)}")
+        self.compute = compute
         self.desc = Desc(VARIANT[variant], ACT[activation] if variant == "nif" else ACT["sine"], si, so, n, l, K,
-                         float(omega0) if variant != "nif" else 1.0, 0, 0)
+                         float(omega0) if variant != "nif" else 1.0, self.COMPUTE[compute], 0)
         s = Sizes()
         check(_lib.lib().nif_query_sizes(C.byref(self.desc), 0, C.byref(s)), "nif_query_sizes")
         self.po_dim, self.np, self.packed_floats = int(s.po_dim), int(s.np), int(s.packed_floats)
@@ -59,7 +64,8 @@ class FusedShapeNet:
         self._ws = None
 
     def with_latent(self, K: int) -> "FusedShapeNet":
-        return FusedShapeNet(self.variant, self.si, self.so, self.n, self.l, K, self.activation, self.omega0)
+        return FusedShapeNet(self.variant, self.si, self.so, self.n, self.l, K, self.activation, self.omega0,
+                             self.compute)
 
     # ------------------------------------------------------------------------------------------
     def grad_ws_floats(self, B: int) -> int:

@@ -295,3 +295,50 @@ def test_tangents_random(variant, si, so, n, l, K, B, dirs):
     J = udot.permute(1, 2, 0)
     assert _gate(rel_err(u.cpu(), y64.detach()), rel_err(y32.detach(), y64.detach()))
     assert _gate(rel_err(J.cpu(), J64), rel_err(J32, J64), floor=2e-5)
+
+
+# --------------------------------------------------------------------------------------------------
+# tensor-core path (tcgen05, 3xTF32): same gates as the fp32 CUDA-core path
+# --------------------------------------------------------------------------------------------------
+def _engine_tc(spec):
+    from nif_b200.ops import FusedShapeNet
+    return FusedShapeNet(spec.variant, spec.si, spec.so, spec.n, spec.l, spec.K, spec.s_act, spec.omega0,
+                         compute="tf32x3")
+
+
+@pytest.mark.parametrize(
+    "variant,si,so,n,l,K,B",
+    [
+        ("siren", 2, 1, 64, 4, 32, 300),     # C2 shape, ragged batch, odd number of latent rows (K+1 = 33)
+        ("siren", 1, 1, 64, 4, 32, 128),     # C4 shape, exactly one tile
+        ("siren", 2, 1, 64, 1, 3, 1000),     # even K+1, several tiles
+        ("siren", 3, 2, 48, 2, 5, 77),       # padded width
+        ("siren_res", 2, 2, 64, 2, 6, 150),  # res-blocks
+        ("nif", 2, 2, 48, 3, 7, 90),         # swish + residual
+        ("siren", 2, 1, 64, 2, 1, 20000),    # many tiles per CTA (persistent loop, barrier phases)
+    ],
+)
+def test_tc_forward_and_stash(variant, si, so, n, l, K, B):
+    spec, prm, inputs, target, sw = _random_problem(variant, si, so, n, l, K, B, seed=si * 100 + n + K)
+    dev = torch.device("cuda:0")
+    wn, bn = O.last_layer_names(spec)
+    loss64, g64, gz64, y64 = O.loss_and_grads(spec, prm, inputs, target, sw)
+    prm32 = {k: v.float() for k, v in prm.items()}
+    loss32, g32, gz32, y32 = O.loss_and_grads(spec, prm32, inputs.float(), target.float(), sw.float())
+    eng = _engine_tc(spec)
+    z = O.latent(spec, prm, inputs[:, :1]).float().to(dev)
+    x = inputs[:, 1:].float().contiguous().to(dev)
+    w_h, b_h = prm[wn].float().to(dev), prm[bn].float().to(dev)
+    packed = eng.pack(w_h, b_h)
+    u = eng.forward(z, x, packed)
+    u2, stash = eng.forward(z, x, packed, save=True)
+    torch.cuda.synchronize()
+    assert torch.equal(u, u2)
+    assert _gate(rel_err(u.cpu(), y64), rel_err(y32, y64)), (rel_err(u.cpu(), y64), rel_err(y32, y64))
+    # the stash written by the tensor-core forward drives the reverse pass
+    loss = torch.zeros(1, device=dev)
+    dw, db = torch.empty_like(w_h), torch.empty_like(b_h)
+    dz = eng.mse_backward(z, x, packed, u, stash, target.float().to(dev), sw.float().to(dev), 1.0 / B, loss, dw, db)
+    for name, got, r64, r32 in (("dz", dz, gz64, gz32), ("dw_h", dw, g64[wn], g32[wn]), ("db_h", db, g64[bn], g32[bn])):
+        e = rel_err(got.cpu(), r64)
+        assert _gate(e, rel_err(r32, r64)), f"{name} err {e:.3e} (cpu32 {rel_err(r32, r64):.3e})"
