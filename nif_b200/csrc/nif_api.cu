@@ -17,7 +17,7 @@ int nif_mse_backward_impl(const Plan& pl, long long B, const float* z, const flo
 int nif_adam_impl(long long n, float* p, const float* g, float* m, float* v, double lr, double b1, double b2,
                   double eps, long long t, float l1, float l2, float gs, cudaStream_t st);
 struct GradWs {
-  long long da, du, part_h, part_e, loss_part, total;
+  long long da, du, part_h, part_e, loss_part, maxes, total;
   int S_h, S_e, Q;
   long long rows_h, rows_e;
 };

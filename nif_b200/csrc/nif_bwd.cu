@@ -568,9 +568,12 @@ __global__ void nif_loss_final_kernel(int nparts, const float* __restrict__ part
 // ---------------------------------------------------------------------------------------------------
 int nif_unpack_grad_impl(const Plan& pl, int S_h, const float* part_h, int S_e, const float* part_e, int Q,
                          float* dw_h, float* db_h, float beta, cudaStream_t st);
+int nif_tc_bwd_data_impl(const Plan& pl, long long B, const float* z, const float* x, const float* packed,
+                         const float* save, const float* du, float* da, float* dz, unsigned* maxes,
+                         cudaStream_t st);
 
 struct GradWs {
-  long long da, du, part_h, part_e, loss_part, total;
+  long long da, du, part_h, part_e, loss_part, maxes, total;
   int S_h, S_e, Q;
   long long rows_h, rows_e;
 };
@@ -607,6 +610,7 @@ GradWs nif_grad_ws_layout(const Plan& pl, long long B) {
   w.part_h = off; off += round_up((long long)w.S_h * H * K1 * NP * NP, 4);
   w.part_e = off; off += round_up((long long)w.S_e * K1 * w.Q, 4);
   w.loss_part = off; off += 1024;
+  w.maxes = off; off += 256;  // device-side maxima used for tensor-core operand scales
   w.total = off;
   return w;
 }
@@ -621,7 +625,10 @@ int nif_backward_impl(const Plan& pl, long long B, const float* z, const float* 
   a.z = z; a.x = x; a.packed = packed; a.save = save; a.du = du;
   a.da = ws + w.da;
   a.dz = dz;
-  int rc;
+  int rc = NIF_E_UNSUPPORTED;
+  if (pl.tc)  // tensor-core data pass; shapes it does not cover use the CUDA-core kernel below
+    rc = nif_tc_bwd_data_impl(pl, B, z, x, packed, save, du, ws + w.da, dz, reinterpret_cast<unsigned*>(ws + w.maxes), st);
+  if (rc == NIF_E_UNSUPPORTED)
   switch (pl.NP) {
     case 32: a.total_tiles = (B + Cfg32::TB - 1) / Cfg32::TB; rc = launch_bwd_data<Cfg32>(pl, a, st); break;
     case 64: a.total_tiles = (B + Cfg64::TB - 1) / Cfg64::TB; rc = launch_bwd_data<Cfg64>(pl, a, st); break;

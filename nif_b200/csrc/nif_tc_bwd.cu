@@ -1,0 +1,361 @@
+// Reverse data pass on the tensor cores (tcgen05 + TMEM, FP16x3) -- the mirror image of nif_tc_fwd.cu.
+//
+// Per 128-row tile, hidden matrices m = H .. 1:
+//   T[b][kappa][i] = sum_j da_m[b][j] M_m[kappa][i][j]        tcgen05 GEMM: A = da_m tile (row-scaled, hi/lo split),
+//                                                             B = TCB chunk [128 (kappa_l, i) x 64 (j)]
+//   dh_m[b][i]   = omega * sum_kappa zt[b][kappa] T[b][kappa][i]            epilogue, thread = row
+//   dz[b][kappa] += omega * sum_i T[b][kappa][i] h_m[b][i]                  epilogue, thread = row (no shuffles)
+//   da_{m-1}     = dh_m * act'(pre_{m-1})                                   -> global stash + next operand tile
+// The thin dz terms (bias rows of every layer, first and last matrix) are added by nif_dz_edge_kernel, which
+// only needs the stashed da_m / h / x rows.
+// Also records max|da_m| per layer and max|zt|, max|h_m| (atomicMax on the float bits) for the operand scales
+// of the weight-gradient GEMM.
+#include "nif_tc.cuh"
+
+struct TcBwdArgs {
+  long long B, total_pairs;
+  const float *z, *x, *packed, *save, *du;
+  float* da;        // [(H+1)][B][64]
+  float* dz;        // [B][K]
+  unsigned* maxes;  // [0..H] max|da_m| bits, [H+1] max|zt| bits, [H+2 .. 2H+2] max|h_m| bits (m = 1..H+1)
+};
+
+#define TCB_THREADS 320
+#define TCB_STAGES 2
+#define TCB_STAGE_BYTES 32768u
+
+__host__ __device__ inline size_t tcb_smem_bytes(int KP) {
+  return 4 * (size_t)TC_TILE_BYTES + TCB_STAGES * (size_t)TCB_STAGE_BYTES + 4 * (size_t)KP * 128 * 4 + 256;
+}
+
+__device__ __forceinline__ void warp_atomic_max(unsigned* dst, float v) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(dst, __float_as_uint(v));  // v >= 0: uint order == float order
+}
+
+__global__ void __launch_bounds__(TCB_THREADS, 1) nif_tc_bwd_data_kernel(const Plan pl, const TcBwdArgs a) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char* A_all = smem;
+  unsigned char* Bst = smem + 4 * TC_TILE_BYTES;
+  float* zs_all = reinterpret_cast<float*>(Bst + TCB_STAGES * TCB_STAGE_BYTES);  // [2][KP][128]
+  float* dzs_all = zs_all + 2 * pl.KP * 128;                                     // [2][KP][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(dzs_all + 2 * pl.KP * 128);
+  uint64_t* b_full = bars;
+  uint64_t* b_empty = bars + TCB_STAGES;
+  uint64_t* t_full = bars + 2 * TCB_STAGES;
+  uint64_t* t_empty = t_full + 2;
+  uint64_t* a_ready = t_empty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_ready + 2);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int K = pl.K, K1 = pl.K + 1, KP = pl.KP, NCH = pl.NCH, H = pl.H, n = pl.n, so = pl.so;
+
+  if (tid == 0) {
+    for (int i = 0; i < TCB_STAGES; ++i) {
+      mbar_init(&b_full[i], 1);
+      mbar_init(&b_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&t_full[i], 1);
+      mbar_init(&t_empty[i], 128);
+      mbar_init(&a_ready[i], 128);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 8) tc_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  long long my_pairs = 0;
+  if ((long long)blockIdx.x < a.total_pairs) my_pairs = (a.total_pairs - blockIdx.x + gridDim.x - 1) / gridDim.x;
+
+  if (warp == 9) {
+    if (lane == 0) {  // weight-stream producer: hidden matrices in reverse order
+      long long g = 0;
+      const float* src0 = a.packed + pl.off_TCB;
+      for (long long t = 0; t < my_pairs; ++t)
+        for (int h = H - 1; h >= 0; --h)
+          for (int c = 0; c < NCH; ++c, ++g) {
+            const int s = (int)(g % TCB_STAGES);
+            mbar_wait(&b_empty[s], (uint32_t)(((g / TCB_STAGES) & 1) ^ 1));
+            mbar_expect_tx(&b_full[s], TCB_STAGE_BYTES);
+            bulk_g2s(Bst + s * TCB_STAGE_BYTES, src0 + ((long long)h * NCH + c) * NIF_TC_CHUNK_FLOATS,
+                     TCB_STAGE_BYTES, &b_full[s]);
+          }
+    }
+  } else if (warp == 8) {
+    if (lane == 0) {  // MMA issuer
+      const uint32_t idesc = tc_idesc_f16(128);
+      uint64_t da_hi[2], da_lo[2];
+      for (int t = 0; t < 2; ++t) {
+        da_hi[t] = tc_make_desc(smem_u32(A_all + t * 2 * TC_TILE_BYTES));
+        da_lo[t] = tc_make_desc(smem_u32(A_all + t * 2 * TC_TILE_BYTES + TC_TILE_BYTES));
+      }
+      long long g = 0, L = 0;
+      for (long long p = 0; p < my_pairs; ++p)
+        for (int h = 0; h < H; ++h, ++L)
+          for (int c = 0; c < NCH; ++c, ++g) {
+            const int s = (int)(g % TCB_STAGES);
+            mbar_wait(&b_full[s], (uint32_t)((g / TCB_STAGES) & 1));
+            const uint64_t db_hi = tc_make_desc(smem_u32(Bst + s * TCB_STAGE_BYTES));
+            const uint64_t db_lo = tc_make_desc(smem_u32(Bst + s * TCB_STAGE_BYTES + TC_TILE_BYTES));
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+              if (c == 0) mbar_wait(&a_ready[t], (uint32_t)(L & 1));
+              mbar_wait(&t_empty[t], (uint32_t)((g & 1) ^ 1));
+              tc_fence_after();
+              const uint32_t d1 = tmem + (uint32_t)t * 256u;
+              tc_mma_split_k64(d1, d1 + 128u, da_hi[t], da_lo[t], db_hi, db_lo, idesc);
+              tc_commit(&t_full[t]);
+            }
+            tc_commit(&b_empty[s]);
+          }
+    }
+  } else {
+    // ---------------- epilogue warps: thread r <-> row r of tile wg <-> TMEM lane r ----------------
+    const int wg = warp >> 2;
+    const int r = tid & 127;
+    const uint32_t tm = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)wg * 256u;
+    unsigned char* A_hi = A_all + wg * 2 * TC_TILE_BYTES;
+    unsigned char* A_lo = A_hi + TC_TILE_BYTES;
+    float* zs = zs_all + wg * KP * 128;
+    float* dzs = dzs_all + wg * KP * 128;
+    const float* invB = a.packed + pl.off_TCS;
+    long long g = 0;
+    for (long long p = 0; p < my_pairs; ++p) {
+      const long long row0 = ((blockIdx.x + p * gridDim.x) * 2 + wg) * 128;
+      const long long b = row0 + r;
+      const bool live = b < a.B;
+      named_bar_sync(1 + wg, 128);
+      for (int idx = r; idx < 128 * K; idx += 128) {
+        const int q = idx / K, kk = idx - q * K;
+        zs[kk * 128 + q] = (row0 + q < a.B) ? __ldg(&a.z[(row0 + q) * K + kk]) : 0.f;
+      }
+      zs[K * 128 + r] = 1.f;
+      for (int kk = K1; kk < KP; ++kk) zs[kk * 128 + r] = 0.f;
+      for (int kk = 0; kk < KP; ++kk) dzs[kk * 128 + r] = 0.f;
+      named_bar_sync(1 + wg, 128);
+      {
+        float zmax = 0.f;
+        for (int kk = 0; kk < K1; ++kk) zmax = fmaxf(zmax, fabsf(zs[kk * 128 + r]));
+        warp_atomic_max(&a.maxes[H + 1], live ? zmax : 0.f);
+      }
+
+      float acc[64];
+      // ---- last matrix (n -> so): dh_{H+1}[i] = sum_kappa zt[kappa] sum_c ML[kappa][i][c] du[c]  (CUDA cores) ----
+      {
+        float dy[NIF_MAX_SO];
+#pragma unroll
+        for (int c = 0; c < NIF_MAX_SO; ++c) dy[c] = (c < so && live) ? __ldg(&a.du[b * so + c]) : 0.f;
+#pragma unroll
+        for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+        const float* ML = a.packed + pl.off_ML;
+        for (int kk = 0; kk < K1; ++kk) {
+          const float zk = zs[kk * 128 + r];
+          const float* Mk = ML + (long long)kk * 64 * so;
+          if (so == 1) {
+            const float w = zk * dy[0];
+#pragma unroll
+            for (int c4 = 0; c4 < 16; ++c4) {
+              const float4 q = ldg4(Mk + 4 * c4);
+              acc[4 * c4] = fmaf(w, q.x, acc[4 * c4]); acc[4 * c4 + 1] = fmaf(w, q.y, acc[4 * c4 + 1]);
+              acc[4 * c4 + 2] = fmaf(w, q.z, acc[4 * c4 + 2]); acc[4 * c4 + 3] = fmaf(w, q.w, acc[4 * c4 + 3]);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 64; ++i) {
+              float s = 0.f;
+#pragma unroll
+              for (int c = 0; c < NIF_MAX_SO; ++c)
+                if (c < so) s = fmaf(dy[c], __ldg(&Mk[i * so + c]), s);
+              acc[i] = fmaf(zk, s, acc[i]);
+            }
+          }
+        }
+      }
+
+      // ---- layers H .. 0: da_m = dh_{m+1} * d_m; hidden matrices on the tensor cores ----
+      for (int m = H; m >= 0; --m) {
+        const float* dsv = a.save + (long long)(H + 1 + m) * a.B * 64 + b * 64;  // d_m row
+        float* dag = a.da + (long long)m * a.B * 64 + b * 64;
+        float dav[64];
+        float amax = 0.f;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          float4 dv = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (live) dv = ldg4(dsv + 4 * c);
+          dav[4 * c] = acc[4 * c] * dv.x; dav[4 * c + 1] = acc[4 * c + 1] * dv.y;
+          dav[4 * c + 2] = acc[4 * c + 2] * dv.z; dav[4 * c + 3] = acc[4 * c + 3] * dv.w;
+          if (live) *reinterpret_cast<float4*>(dag + 4 * c) = make_float4(dav[4 * c], dav[4 * c + 1], dav[4 * c + 2], dav[4 * c + 3]);
+          amax = fmaxf(fmaxf(amax, fabsf(dav[4 * c])), fmaxf(fabsf(dav[4 * c + 1]), fmaxf(fabsf(dav[4 * c + 2]), fabsf(dav[4 * c + 3]))));
+        }
+        warp_atomic_max(&a.maxes[m], amax);
+        if (m == 0) break;
+
+        float sc_a, inv_a;
+        tc_row_scale(amax, sc_a, inv_a);
+        tc_store_row_split(A_hi, A_lo, r, dav, sc_a);
+        fence_async_smem();
+        mbar_arrive(&a_ready[wg]);
+
+        // this layer's input row h_m (for the dz dot products)
+        float hm[64];
+        {
+          const float* hsrc = a.save + (long long)(m - 1) * a.B * 64 + b * 64;
+          float hmax = 0.f;
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (live) q = ldg4(hsrc + 4 * c);
+            hm[4 * c] = q.x; hm[4 * c + 1] = q.y; hm[4 * c + 2] = q.z; hm[4 * c + 3] = q.w;
+            hmax = fmaxf(fmaxf(hmax, fabsf(q.x)), fmaxf(fabsf(q.y), fmaxf(fabsf(q.z), fabsf(q.w))));
+          }
+          warp_atomic_max(&a.maxes[H + 2 + (m - 1)], hmax);
+        }
+        const int res = plan_res(pl, m);
+        if (res != 1) {  // res == 1 (NIF hidden layer): dh_m = T + dh_{m+1}, keep acc
+#pragma unroll
+          for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+        }
+        const float om_inv = plan_omega(pl, m) * inv_a;
+        const float* invBm = invB + (m - 1) * KP;
+        for (int c = 0; c < NCH; ++c, ++g) {
+          mbar_wait(&t_full[wg], (uint32_t)(g & 1));
+          tc_fence_after();
+#pragma unroll
+          for (int kl = 0; kl < 2; ++kl) {
+            const int kk = 2 * c + kl;
+            const float zk = zs[kk * 128 + r];
+            const float sB = om_inv * __ldg(&invBm[kk]);
+            const float zo = zk * sB;
+            float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {  // 16 columns (values of i) at a time keeps the register budget
+              float v1[16], v2[16];
+              const uint32_t col = (uint32_t)(kl * 64 + q * 16);
+              tc_ld16(tm + col, v1);
+              tc_ld16(tm + col + 128u, v2);
+              tc_wait_ld();
+#pragma unroll
+              for (int e = 0; e < 16; e += 2) {
+                const float t0 = v1[e] + v2[e], t1 = v1[e + 1] + v2[e + 1];
+                acc[q * 16 + e] = fmaf(zo, t0, acc[q * 16 + e]);
+                acc[q * 16 + e + 1] = fmaf(zo, t1, acc[q * 16 + e + 1]);
+                s0 = fmaf(t0, hm[q * 16 + e], s0);
+                s1 = fmaf(t1, hm[q * 16 + e + 1], s1);
+              }
+            }
+            dzs[kk * 128 + r] += sB * (s0 + s1);
+          }
+          tc_fence_before();
+          mbar_arrive(&t_empty[wg]);
+        }
+      }
+
+      if (live) {
+        for (int kk = 0; kk < K; ++kk) a.dz[b * K + kk] = dzs[kk * 128 + r];
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tc_dealloc(tmem, 512);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// thin dz terms, thread = row (CUDA cores; ~1 % of the reverse-pass FLOPs):
+//   dz[b][kappa] += sum_m sum_j C_m[kappa][j] da_m[b][j]                                  (bias rows, m = 0..H)
+//                 + sum_j da_0[b][j] * omega * sum_i x[b][i] M0[kappa][i][j]              (first matrix)
+//                 + sum_c du[b][c] * ( CL[kappa][c] + sum_i h_{H+1}[b][i] ML[kappa][i][c] ) (last matrix)
+// ---------------------------------------------------------------------------------------------------
+struct DzEdgeArgs {
+  long long B;
+  const float *x, *packed, *save, *da, *du;
+  float* dz;
+};
+
+__global__ void __launch_bounds__(128) nif_dz_edge_kernel(const Plan pl, const DzEdgeArgs a) {
+  const int K = pl.K, K1 = pl.K + 1, H = pl.H, si = pl.si, so = pl.so;
+  const long long b = blockIdx.x * 128LL + threadIdx.x;
+  const bool live = b < a.B;
+  const long long bb = live ? b : 0;
+  const float* C_all = a.packed + pl.off_C;
+  const float* M0 = a.packed + pl.off_M0;
+  const float* ML = a.packed + pl.off_ML;
+  // dz is accumulated per kappa in a register-free way: one pass per operand row, kappa in the inner loop would
+  // need K registers; instead loop kappa outside and re-read the (L1-resident) rows.
+  float xv[NIF_MAX_SI], dy[NIF_MAX_SO];
+#pragma unroll
+  for (int i = 0; i < NIF_MAX_SI; ++i) xv[i] = (i < si) ? a.x[bb * si + i] : 0.f;
+#pragma unroll
+  for (int c = 0; c < NIF_MAX_SO; ++c) dy[c] = (c < so) ? a.du[bb * so + c] : 0.f;
+  const float om0 = plan_omega(pl, 0);
+  for (int kk = 0; kk < K; ++kk) {
+    float s = 0.f;
+    for (int m = 0; m <= H; ++m) {
+      const float* dar = a.da + (long long)m * a.B * 64 + bb * 64;
+      const float* cb = C_all + ((long long)m * K1 + kk) * 64;
+#pragma unroll
+      for (int c4 = 0; c4 < 16; ++c4) {
+        const float4 d4 = *reinterpret_cast<const float4*>(dar + 4 * c4);
+        const float4 q = ldg4(cb + 4 * c4);
+        s = fmaf(d4.x, q.x, s); s = fmaf(d4.y, q.y, s); s = fmaf(d4.z, q.z, s); s = fmaf(d4.w, q.w, s);
+      }
+    }
+    {  // first matrix
+      const float* dar = a.da + bb * 64;
+      for (int i = 0; i < si; ++i) {
+        const float* mw = M0 + ((long long)kk * si + i) * 64;
+        float t = 0.f;
+#pragma unroll
+        for (int c4 = 0; c4 < 16; ++c4) {
+          const float4 d4 = *reinterpret_cast<const float4*>(dar + 4 * c4);
+          const float4 q = ldg4(mw + 4 * c4);
+          t = fmaf(d4.x, q.x, t); t = fmaf(d4.y, q.y, t); t = fmaf(d4.z, q.z, t); t = fmaf(d4.w, q.w, t);
+        }
+        s = fmaf(om0 * xv[i], t, s);
+      }
+    }
+    {  // last matrix
+      const float* hl = a.save + (long long)H * a.B * 64 + bb * 64;
+      const float* Mk = ML + (long long)kk * 64 * so;
+      const float* CL = C_all + ((long long)(H + 1) * K1 + kk) * 64;
+      for (int c = 0; c < so; ++c) {
+        float t = __ldg(&CL[c]);
+        for (int i = 0; i < pl.n; ++i) t = fmaf(hl[i], __ldg(&Mk[i * so + c]), t);
+        s = fmaf(dy[c], t, s);
+      }
+    }
+    if (live) a.dz[b * K + kk] += s;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+int nif_tc_bwd_data_impl(const Plan& pl, long long B, const float* z, const float* x, const float* packed,
+                         const float* save, const float* du, float* da, float* dz, unsigned* maxes,
+                         cudaStream_t st) {
+  if (!pl.tc || pl.NP != 64 || pl.H < 1 || pl.variant == NIF_VARIANT_SIREN_RES || pl.K < 1) return NIF_E_UNSUPPORTED;
+  const size_t smem = tcb_smem_bytes(pl.KP);
+  if (smem > 227 * 1024) return NIF_E_UNSUPPORTED;
+  TcBwdArgs a;
+  a.B = B;
+  a.total_pairs = (B + 255) / 256;
+  a.z = z; a.x = x; a.packed = packed; a.save = save; a.du = du; a.da = da; a.dz = dz; a.maxes = maxes;
+  NIF_CUDA_CHECK(cudaMemsetAsync(maxes, 0, sizeof(unsigned) * (2 * pl.H + 4), st));
+  NIF_CUDA_CHECK(cudaFuncSetAttribute(nif_tc_bwd_data_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int dev = 0, sms = 0;
+  NIF_CUDA_CHECK(cudaGetDevice(&dev));
+  NIF_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  long long grid = sms;
+  if (grid > a.total_pairs) grid = a.total_pairs;
+  nif_tc_bwd_data_kernel<<<(unsigned)grid, TCB_THREADS, smem, st>>>(pl, a);
+  NIF_CUDA_CHECK(cudaGetLastError());
+  DzEdgeArgs e;
+  e.B = B; e.x = x; e.packed = packed; e.save = save; e.da = da; e.du = du; e.dz = dz;
+  nif_dz_edge_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(pl, e);
+  NIF_CUDA_CHECK(cudaGetLastError());
+  return NIF_OK;
+}
