@@ -45,7 +45,8 @@ typedef struct nif_desc {
   int32_t act;
   int32_t si, so, n, l, K;
   float omega0;
-  int32_t dtype_compute; /* 0 = fp32 CUDA-core path (parity path) */
+  int32_t dtype_compute; /* 0 = fp32 on CUDA cores; 2 = tcgen05 tensor cores with the 3-product fp16 split
+                            (fp32-grade, same parity gates; 32 < n <= 64, falls through to 0 for shapes it lacks) */
   int32_t reserved;
 } nif_desc_t;
 

@@ -571,6 +571,8 @@ int nif_unpack_grad_impl(const Plan& pl, int S_h, const float* part_h, int S_e, 
 int nif_tc_bwd_data_impl(const Plan& pl, long long B, const float* z, const float* x, const float* packed,
                          const float* save, const float* du, float* da, float* dz, unsigned* maxes,
                          cudaStream_t st);
+int nif_tc_bwd_weight_impl(const Plan& pl, long long B, const float* z, const float* save, const float* da,
+                           const unsigned* maxes, int S, long long rows_per_split, float* part, cudaStream_t st);
 
 struct GradWs {
   long long da, du, part_h, part_e, loss_part, maxes, total;
@@ -628,6 +630,7 @@ int nif_backward_impl(const Plan& pl, long long B, const float* z, const float* 
   int rc = NIF_E_UNSUPPORTED;
   if (pl.tc)  // tensor-core data pass; shapes it does not cover use the CUDA-core kernel below
     rc = nif_tc_bwd_data_impl(pl, B, z, x, packed, save, du, ws + w.da, dz, reinterpret_cast<unsigned*>(ws + w.maxes), st);
+  const bool tc_data = (rc == NIF_OK);
   if (rc == NIF_E_UNSUPPORTED)
   switch (pl.NP) {
     case 32: a.total_tiles = (B + Cfg32::TB - 1) / Cfg32::TB; rc = launch_bwd_data<Cfg32>(pl, a, st); break;
@@ -637,7 +640,22 @@ int nif_backward_impl(const Plan& pl, long long B, const float* z, const float* 
   }
   if (rc != NIF_OK) return rc;
 
-  if (pl.H > 0) {
+  bool wgt_done = false;
+  int S_used = w.S_h;
+  if (tc_data && pl.H > 0) {  // tensor-core weight-gradient GEMM (needs the maxima recorded by the TC data pass)
+    // one CTA per SM: as many batch splits as fit one wave (never more than the workspace was sized for)
+    const int items = pl.H * ((pl.KP + 3) / 4);
+    int S = 148 / items;
+    if (S < 1) S = 1;
+    if (S > w.S_h) S = w.S_h;
+    long long rows = round_up((B + S - 1) / S, 64);
+    S = (int)((B + rows - 1) / rows);
+    const int rcw = nif_tc_bwd_weight_impl(pl, B, z, save, ws + w.da, reinterpret_cast<const unsigned*>(ws + w.maxes),
+                                           S, rows, ws + w.part_h, st);
+    if (rcw == NIF_OK) { wgt_done = true; S_used = S; }
+    else if (rcw != NIF_E_UNSUPPORTED) return rcw;
+  }
+  if (pl.H > 0 && !wgt_done) {
     WgtArgs g;
     g.B = B; g.rows_per_split = w.rows_h; g.S = w.S_h;
     g.z = z; g.save = save; g.da = ws + w.da; g.part = ws + w.part_h;
@@ -660,7 +678,7 @@ int nif_backward_impl(const Plan& pl, long long B, const float* z, const float* 
     nif_bwd_edge_kernel<<<grid, 256, 0, st>>>(pl, e);
     NIF_CUDA_CHECK(cudaGetLastError());
   }
-  return nif_unpack_grad_impl(pl, w.S_h, ws + w.part_h, w.S_e, ws + w.part_e, w.Q, dw_h, db_h, beta, st);
+  return nif_unpack_grad_impl(pl, S_used, ws + w.part_h, w.S_e, ws + w.part_e, w.Q, dw_h, db_h, beta, st);
 }
 
 int nif_mse_backward_impl(const Plan& pl, long long B, const float* z, const float* x, const float* packed,

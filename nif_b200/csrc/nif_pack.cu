@@ -30,7 +30,7 @@ int nif_make_plan(const nif_desc_t* d, Plan* out) {
   if (d->K < 0 || d->K > 256) { nif_set_error("latent_dim=%d outside [0,256]", d->K); return NIF_E_BAD_DESC; }
   if (d->act < 0 || d->act > NIF_ACT_SIGMOID) { nif_set_error("activation id %d unknown", d->act); return NIF_E_BAD_DESC; }
   if (d->dtype_compute != 0 && d->dtype_compute != 2) {
-    nif_set_error("dtype_compute=%d: built paths are 0 (fp32 CUDA cores) and 2 (3xTF32 tensor cores)", d->dtype_compute);
+    nif_set_error("dtype_compute=%d: built paths are 0 (fp32 CUDA cores) and 2 (tensor cores, FP16x3 split)", d->dtype_compute);
     return NIF_E_UNSUPPORTED;
   }
   if (d->dtype_compute == 2 && (d->n <= 32 || d->n > 64)) {

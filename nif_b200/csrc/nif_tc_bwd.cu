@@ -359,3 +359,226 @@ int nif_tc_bwd_data_impl(const Plan& pl, long long B, const float* z, const floa
   NIF_CUDA_CHECK(cudaGetLastError());
   return NIF_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------
+// Weight gradient of the hidden matrices on the tensor cores:
+//   dM_m[kappa][i][j] = omega * sum_b zt[b][kappa] h_m[b][i] da_m[b][j]
+// A batch-reduction GEMM: D[(kappa_l, i)][j] += A[(kappa_l, i)][b] * B[j][b] with the batch index b as the
+// MMA K dimension.  Both operands are generated on the fly by the row-owning threads (A = zt (x) h, B = da),
+// which is naturally "MN-major" (for a fixed row b the (kappa_l, i) / j index is contiguous).  Because b is the
+// reduction index the power-of-two scales must be constant over b: one global scale per layer from the maxima
+// the data pass recorded (max|zt| * max|h_m| and max|da_m|).
+// One CTA = (hidden matrix, group of 4 latent coordinates, batch split); 64-row sub-tiles, two operand slots
+// (generation of sub-tile t+1 overlaps the MMAs of sub-tile t); accumulators stay in TMEM for the whole batch
+// range; the result is written as a partial in the layout nif_unpack_grad_kernel sums.
+// ---------------------------------------------------------------------------------------------------
+struct TcWgtArgs {
+  long long B, rows_per_split;
+  int S;
+  const float *z, *save, *da;
+  const unsigned* maxes;
+  float* part;  // [S][H][K+1][64][64]
+};
+
+#define TCW_THREADS 288
+#define TCW_A_BYTES 16384u   // [128 (kappa_l, i) x 64 (b)] fp16, MN-major
+#define TCW_B_BYTES 8192u    // [64 (j) x 64 (b)] fp16, MN-major
+#define TCW_SLOT_BYTES (4 * TCW_A_BYTES + 2 * TCW_B_BYTES)  // A[q][hi|lo], B[hi|lo]
+
+// MN-major core-matrix layout of a [MN x 64] tile: 8 (k) x 16 B (8 consecutive mn) core matrices,
+// offset(mn, k) = (mn/8) * 1024 + (k/8) * 128 + (k%8) * 16 + (mn%8) * 2
+__device__ __forceinline__ uint64_t tcw_make_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((128u >> 4) & 0x3FFF) << 16;   // LBO: next group of 8 k
+  d |= (uint64_t)((1024u >> 4) & 0x3FFF) << 32;  // SBO: next group of 8 mn
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+
+// 8 values -> scaled hi / lo fp16 chunks (16 bytes each)
+__device__ __forceinline__ void tcw_split8(const float (&v)[8], float sc, uint4& hi, uint4& lo) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float a0 = v[2 * e] * sc, a1 = v[2 * e + 1] * sc;
+    const __half2 hh = __floats2half2_rn(a0, a1);
+    const float2 hf = __half22float2(hh);
+    const __half2 ll = __floats2half2_rn(a0 - hf.x, a1 - hf.y);
+    h[e] = *reinterpret_cast<const uint32_t*>(&hh);
+    l[e] = *reinterpret_cast<const uint32_t*>(&ll);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+__global__ void __launch_bounds__(TCW_THREADS, 1) nif_tc_bwd_weight_kernel(const Plan pl, const TcWgtArgs a) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ uint64_t slot_full[2], slot_empty[2], done_bar;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int K = pl.K, K1 = pl.K + 1, H = pl.H;
+  const int NPG = (pl.KP + 3) / 4;  // groups of 4 latent coordinates
+  const int h = blockIdx.x / NPG, pg = blockIdx.x % NPG;
+  const int s = blockIdx.y;
+  const long long r0 = (long long)s * a.rows_per_split;
+  long long r1 = r0 + a.rows_per_split;
+  if (r1 > a.B) r1 = a.B;
+  const long long nsub = r1 > r0 ? (r1 - r0 + 63) / 64 : 0;
+
+  if (tid == 0) {
+    mbar_init(&slot_full[0], 128); mbar_init(&slot_full[1], 128);
+    mbar_init(&slot_empty[0], 1); mbar_init(&slot_empty[1], 1);
+    mbar_init(&done_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 8) tc_alloc(&tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+
+  // global power-of-two operand scales of this layer (m = h + 1)
+  float scA, invA, scB, invB;
+  {
+    const float maxz = __uint_as_float(a.maxes[H + 1]);
+    const float maxh = __uint_as_float(a.maxes[H + 2 + h]);
+    const float maxd = __uint_as_float(a.maxes[h + 1]);
+    tc_row_scale(maxz * maxh, scA, invA);
+    tc_row_scale(maxd, scB, invB);
+  }
+
+  if (warp == 8) {
+    if (lane == 0) {  // MMA issuer
+      const uint32_t idesc = (1u << 4) | (1u << 15) | (1u << 16) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+      for (long long t = 0; t < nsub; ++t) {
+        const int sl = (int)(t & 1);
+        mbar_wait(&slot_full[sl], (uint32_t)((t >> 1) & 1));
+        tc_fence_after();
+        const uint32_t base = smem_u32(smem + sl * TCW_SLOT_BYTES);
+        const uint64_t b_hi = tcw_make_desc(base + 4 * TCW_A_BYTES), b_lo = tcw_make_desc(base + 4 * TCW_A_BYTES + TCW_B_BYTES);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const uint64_t a_hi = tcw_make_desc(base + (2 * q) * TCW_A_BYTES), a_lo = tcw_make_desc(base + (2 * q + 1) * TCW_A_BYTES);
+          const uint32_t d1 = tmem + (uint32_t)q * 128u, d2 = d1 + 64u;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {  // 16 rows (k) per instruction = 2 k-groups = 256 B
+            const uint64_t adv = (uint64_t)(ks * 16);
+            const uint32_t accf = (t > 0 || ks > 0) ? 1u : 0u;
+            tc_mma_f16(d2, a_lo + adv, b_hi + adv, idesc, accf);
+            tc_mma_f16(d2, a_hi + adv, b_lo + adv, idesc, 1u);
+            tc_mma_f16(d1, a_hi + adv, b_hi + adv, idesc, accf);
+          }
+        }
+        tc_commit(&slot_empty[sl]);
+      }
+      tc_commit(&done_bar);
+    }
+  } else {
+    // ---------------- operand generators: slot sl = warp / 4, thread (q, r) = pair q, row r of the sub-tile ----------------
+    const int sl = warp >> 2;
+    const int q = (tid >> 6) & 1, r = tid & 63;
+    unsigned char* slot = smem + sl * TCW_SLOT_BYTES;
+    unsigned char* Aq_hi = slot + (2 * q) * TCW_A_BYTES;
+    unsigned char* Aq_lo = Aq_hi + TCW_A_BYTES;
+    unsigned char* B_hi = slot + 4 * TCW_A_BYTES;
+    unsigned char* B_lo = B_hi + TCW_B_BYTES;
+    const uint32_t koff = (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 16u;  // this row's position along k
+    const float* hsrc = a.save + (long long)h * a.B * 64;        // h_m, m = h + 1 -> stash slot h
+    const float* dsrc = a.da + (long long)(h + 1) * a.B * 64;    // da_m
+    const int kk0 = 4 * pg + 2 * q;
+    long long n_mine = 0;
+    for (long long t = sl; t < nsub; t += 2, ++n_mine) {
+      const long long b = r0 + t * 64 + r;
+      const bool live = b < r1;
+      float zt[2];
+#pragma unroll
+      for (int kl = 0; kl < 2; ++kl) {
+        const int kk = kk0 + kl;
+        zt[kl] = 0.f;
+        if (live) zt[kl] = (kk < K) ? __ldg(&a.z[b * K + kk]) : (kk == K ? 1.f : 0.f);
+      }
+      // wait until the MMAs that read this slot two sub-tiles ago have completed
+      mbar_wait(&slot_empty[sl], (uint32_t)((n_mine & 1) ^ 1));
+#pragma unroll
+      for (int ig = 0; ig < 8; ++ig) {
+        float hv[8];
+        float4 p0 = make_float4(0.f, 0.f, 0.f, 0.f), p1 = p0;
+        if (live) { p0 = ldg4(hsrc + b * 64 + 8 * ig); p1 = ldg4(hsrc + b * 64 + 8 * ig + 4); }
+        hv[0] = p0.x; hv[1] = p0.y; hv[2] = p0.z; hv[3] = p0.w; hv[4] = p1.x; hv[5] = p1.y; hv[6] = p1.z; hv[7] = p1.w;
+#pragma unroll
+        for (int kl = 0; kl < 2; ++kl) {
+          float pv[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) pv[e] = zt[kl] * hv[e];
+          uint4 hi, lo;
+          tcw_split8(pv, scA, hi, lo);
+          const uint32_t off = (uint32_t)(kl * 8 + ig) * 1024u + koff;
+          *reinterpret_cast<uint4*>(Aq_hi + off) = hi;
+          *reinterpret_cast<uint4*>(Aq_lo + off) = lo;
+        }
+      }
+#pragma unroll
+      for (int jg = 0; jg < 4; ++jg) {  // pair q writes columns j = 32 q .. 32 q + 31 of the B operand
+        const int j0 = 32 * q + 8 * jg;
+        float dv[8];
+        float4 p0 = make_float4(0.f, 0.f, 0.f, 0.f), p1 = p0;
+        if (live) { p0 = ldg4(dsrc + b * 64 + j0); p1 = ldg4(dsrc + b * 64 + j0 + 4); }
+        dv[0] = p0.x; dv[1] = p0.y; dv[2] = p0.z; dv[3] = p0.w; dv[4] = p1.x; dv[5] = p1.y; dv[6] = p1.z; dv[7] = p1.w;
+        uint4 hi, lo;
+        tcw_split8(dv, scB, hi, lo);
+        const uint32_t off = (uint32_t)(j0 >> 3) * 1024u + koff;
+        *reinterpret_cast<uint4*>(B_hi + off) = hi;
+        *reinterpret_cast<uint4*>(B_lo + off) = lo;
+      }
+      fence_async_smem();
+      mbar_arrive(&slot_full[sl]);
+    }
+    // ---------------- final epilogue (warps 0-3): TMEM lane = (kappa_l, i) row of the gradient ----------------
+    if (warp < 4) {
+      mbar_wait(&done_bar, 0);
+      tc_fence_after();
+      const int row = tid;  // 0..127
+      const int kl = row >> 6, i = row & 63;
+      const float scale = plan_omega(pl, h + 1) * invA * invB;
+      const uint32_t tm = tmem + ((uint32_t)(warp * 32) << 16);
+#pragma unroll
+      for (int qq = 0; qq < 2; ++qq) {
+        const int kk = 4 * pg + 2 * qq + kl;
+        float* dst = a.part + ((((long long)s * H + h) * K1 + kk) * 64 + i) * 64;
+#pragma unroll
+        for (int c0 = 0; c0 < 64; c0 += 16) {
+          float v1[16], v2[16];
+          tc_ld16(tm + (uint32_t)(qq * 128 + c0), v1);
+          tc_ld16(tm + (uint32_t)(qq * 128 + 64 + c0), v2);
+          tc_wait_ld();
+          if (kk < K1) {
+#pragma unroll
+            for (int e = 0; e < 16; e += 4)
+              *reinterpret_cast<float4*>(dst + c0 + e) =
+                  make_float4(nsub ? scale * (v1[e] + v2[e]) : 0.f, nsub ? scale * (v1[e + 1] + v2[e + 1]) : 0.f,
+                              nsub ? scale * (v1[e + 2] + v2[e + 2]) : 0.f, nsub ? scale * (v1[e + 3] + v2[e + 3]) : 0.f);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tc_dealloc(tmem, 256);
+}
+
+int nif_tc_bwd_weight_impl(const Plan& pl, long long B, const float* z, const float* save, const float* da,
+                           const unsigned* maxes, int S, long long rows_per_split, float* part, cudaStream_t st) {
+  if (!pl.tc || pl.NP != 64 || pl.H < 1) return NIF_E_UNSUPPORTED;
+  TcWgtArgs a;
+  a.B = B; a.rows_per_split = rows_per_split; a.S = S;
+  a.z = z; a.save = save; a.da = da; a.maxes = maxes; a.part = part;
+  const size_t smem = 2 * (size_t)TCW_SLOT_BYTES;
+  NIF_CUDA_CHECK(cudaFuncSetAttribute(nif_tc_bwd_weight_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int NPG = (pl.KP + 3) / 4;
+  dim3 grid((unsigned)(pl.H * NPG), (unsigned)S);
+  nif_tc_bwd_weight_kernel<<<grid, TCW_THREADS, smem, st>>>(pl, a);
+  NIF_CUDA_CHECK(cudaGetLastError());
+  return NIF_OK;
+}

@@ -53,7 +53,7 @@ __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 
-// mode 0: tf32 (4-byte elements), mode 1: fp16 (2-byte elements)
+// mode 0: tf32 (4-byte elements), mode 1: fp16 (2-byte elements), mode 2: fp16 with MN-major operands
 // A [128 x KD], B [N x KD] row-major in global (as floats); D [128 x N] out.  KD = 64.
 template <int MODE, int N>
 __global__ void __launch_bounds__(128) probe_kernel(const float* A, const float* B, float* D, int reps, long long* cyc,
@@ -82,7 +82,9 @@ __global__ void __launch_bounds__(128) probe_kernel(const float* A, const float*
   }
   // operands -> shared, core-matrix layout: addr(r, k) = (r/8)*SBO + (k/EPC)*LBO + (r%8)*16 + (k%EPC)*ES
   auto put = [&](unsigned char* base, int r, int k, float v) {
-    const int off = (r / 8) * SBO + (k / EPC) * LBO + (r % 8) * 16 + (k % EPC) * ES;
+    // K-major: 8 rows x 16 B core matrices; MN-major (mode 2): 8 k x 16 B (8 consecutive rows) core matrices
+    const int off = MODE == 2 ? (r / 8) * SBO + (k / 8) * LBO + (k % 8) * 16 + (r % 8) * 2
+                              : (r / 8) * SBO + (k / EPC) * LBO + (r % 8) * 16 + (k % EPC) * ES;
     if (MODE == 0) *reinterpret_cast<float*>(base + off) = v;
     else *reinterpret_cast<__half*>(base + off) = __float2half_rn(v);
   };
@@ -96,7 +98,8 @@ __global__ void __launch_bounds__(128) probe_kernel(const float* A, const float*
 
   // instruction descriptor: D fp32, A/B format, K-major both, N>>3 at bit 17, M>>4 at bit 24
   const uint32_t fmt = MODE == 0 ? 2u : 0u;  // TF32 = 2, F16 = 0
-  const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+  const uint32_t mn = MODE == 2 ? 1u : 0u;   // a_major (bit 15) / b_major (bit 16): 1 = MN-major
+  const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (mn << 15) | (mn << 16) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
 
   long long t0 = 0, t1 = 0;
   if (tid == 0) {
@@ -205,6 +208,8 @@ int main() {
   bad += run<0, 256>("tf32");
   bad += run<1, 64>("fp16");
   bad += run<1, 256>("fp16");
+  bad += run<2, 64>("fp16-MNmajor");
+  bad += run<2, 128>("fp16-MNmajor");
   printf(bad ? "PROBE FAILED\n" : "PROBE OK\n");
   return bad;
 }

@@ -48,7 +48,7 @@ class NIF(object):
     _variant = "nif"
 
     def __init__(self, cfg_shape_net, cfg_parameter_net, mixed_policy="float32", *, seed: Optional[int] = None,
-                 device=None):
+                 device=None, compute: str = "auto"):
         self.cfg_shape_net = cfg_shape_net
         self.cfg_parameter_net = cfg_parameter_net
         self._validate_cfg(cfg_shape_net, cfg_parameter_net)
@@ -71,6 +71,9 @@ class NIF(object):
             raise NotImplementedError("jac_reg / act_l1_reg / act_l2_reg are outside the B200 hot-path scope")
         if mixed_policy not in _POLICIES:
             raise ValueError(f"mixed_policy must be one of {_POLICIES} (float64 has no GPU path)")
+        if compute not in ("auto", "fp32", "fp16x3"):
+            raise ValueError("compute must be 'auto', 'fp32' (CUDA cores) or 'fp16x3' (tensor cores, fp32-grade)")
+        self._compute_request = compute
         self.mixed_policy_name = mixed_policy
         self.variable_Dtype = "float32"
         self.compute_Dtype = "float32"  # the fp32 kernels serve every policy in this build
@@ -103,8 +106,13 @@ class NIF(object):
     @property
     def engine(self) -> FusedShapeNet:
         if self._engine is None:
+            # 'auto': the tensor-core path (same parity gates) where the library builds it, else the CUDA-core path;
+            # inside the library, shapes the tensor-core kernels do not cover fall through to the CUDA-core kernels.
+            comp = self._compute_request
+            if comp == "auto":
+                comp = "fp16x3" if (32 < self.n_sx <= 64 and self.pi_hidden >= 1) else "fp32"
             self._engine = FusedShapeNet(self._variant, self.si_dim, self.so_dim, self.n_sx, self.l_sx, self.pi_hidden,
-                                         self.cfg_shape_net.get("activation"), self._omega0)
+                                         self.cfg_shape_net.get("activation"), self._omega0, compute=comp)
             if self._engine.po_dim != self.po_dim:
                 raise NifError("po_dim mismatch between host and library")
         return self._engine

@@ -42,7 +42,7 @@ class FusedShapeNet:
     linear layer (w_h, b_h) instead.
     """
 
-    COMPUTE = {"fp32": 0, "tf32x3": 2}
+    COMPUTE = {"fp32": 0, "fp16x3": 2}  # fp32 CUDA cores | tensor cores, 3-product fp16 split (fp32-grade)
 
     def __init__(self, variant: str, si: int, so: int, n: int, l: int, K: int,
                  activation: Optional[str] = "swish", omega0: float = 1.0, compute: str = "fp32"):

@@ -298,12 +298,12 @@ def test_tangents_random(variant, si, so, n, l, K, B, dirs):
 
 
 # --------------------------------------------------------------------------------------------------
-# tensor-core path (tcgen05, 3xTF32): same gates as the fp32 CUDA-core path
+# tensor-core path (tcgen05, FP16x3): same gates as the fp32 CUDA-core path
 # --------------------------------------------------------------------------------------------------
 def _engine_tc(spec):
     from nif_b200.ops import FusedShapeNet
     return FusedShapeNet(spec.variant, spec.si, spec.so, spec.n, spec.l, spec.K, spec.s_act, spec.omega0,
-                         compute="tf32x3")
+                         compute="fp16x3")
 
 
 @pytest.mark.parametrize(

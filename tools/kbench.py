@@ -23,7 +23,7 @@ def ev(fn, reps=10):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / reps
 
-for comp in ("fp32", "tf32x3"):
+for comp in ("fp32", "fp16x3"):
     eng = FusedShapeNet("siren", 2, 1, 64, 4, 32, omega0=30.0, compute=comp)
     packed = eng.pack(w_h, b_h)
     t_pack = ev(lambda: eng.pack(w_h, b_h, out=packed))

@@ -14,7 +14,7 @@ for (variant, si, so, n, l, K, B, seed) in [("siren",2,1,64,4,32,2048,1), ("sire
     z = O.latent(spec, prm, inputs[:, :1]).float().to(dev); x = inputs[:, 1:].float().contiguous().to(dev)
     w_h, b_h = prm[wn].float().to(dev), prm[bn].float().to(dev)
     out = {"cpu32": (rel_err(y32, y64), rel_err(gz32, gz64), rel_err(g32[wn], g64[wn]))}
-    for comp in ("fp32", "tf32x3"):
+    for comp in ("fp32", "fp16x3"):
         eng = FusedShapeNet(spec.variant, spec.si, spec.so, spec.n, spec.l, spec.K, spec.s_act, spec.omega0, compute=comp)
         packed = eng.pack(w_h, b_h)
         u, stash = eng.forward(z, x, packed, save=True)
