@@ -277,7 +277,16 @@ struct DzEdgeArgs {
   float* dz;
 };
 
-__global__ void __launch_bounds__(128) nif_dz_edge_kernel(const Plan pl, const DzEdgeArgs a) {
+// dz_edge[b][:] = F[b][:] @ G  with per-row features F (Q of them) and a shared coefficient matrix G [Q][K]:
+//   q in [0,(H+1)*64)            F = da_m[b][j]                 G = C_m[kappa][j]
+//   next si*64                   F = omega * x[b][i] da_0[b][j] G = M0[kappa][i][j]
+//   next 64*so                   F = h_{H+1}[b][i] du[b][c]     G = ML[kappa][i][c]
+//   next so                      F = du[b][c]                   G = CL[kappa][c]
+// G is staged through shared memory in slabs of 64 features; every thread keeps its K outputs in registers
+// (KT of them per pass over the features).
+template <int KT>
+__global__ void __launch_bounds__(128) nif_dz_edge_kernel(const Plan pl, const DzEdgeArgs a, int k0) {
+  __shared__ __align__(16) float Gs[64][KT];
   const int K = pl.K, K1 = pl.K + 1, H = pl.H, si = pl.si, so = pl.so;
   const long long b = blockIdx.x * 128LL + threadIdx.x;
   const bool live = b < a.B;
@@ -285,51 +294,61 @@ __global__ void __launch_bounds__(128) nif_dz_edge_kernel(const Plan pl, const D
   const float* C_all = a.packed + pl.off_C;
   const float* M0 = a.packed + pl.off_M0;
   const float* ML = a.packed + pl.off_ML;
-  // dz is accumulated per kappa in a register-free way: one pass per operand row, kappa in the inner loop would
-  // need K registers; instead loop kappa outside and re-read the (L1-resident) rows.
-  float xv[NIF_MAX_SI], dy[NIF_MAX_SO];
-#pragma unroll
-  for (int i = 0; i < NIF_MAX_SI; ++i) xv[i] = (i < si) ? a.x[bb * si + i] : 0.f;
-#pragma unroll
-  for (int c = 0; c < NIF_MAX_SO; ++c) dy[c] = (c < so) ? a.du[bb * so + c] : 0.f;
   const float om0 = plan_omega(pl, 0);
-  for (int kk = 0; kk < K; ++kk) {
-    float s = 0.f;
-    for (int m = 0; m <= H; ++m) {
-      const float* dar = a.da + (long long)m * a.B * 64 + bb * 64;
-      const float* cb = C_all + ((long long)m * K1 + kk) * 64;
+  float acc[KT];
 #pragma unroll
-      for (int c4 = 0; c4 < 16; ++c4) {
-        const float4 d4 = *reinterpret_cast<const float4*>(dar + 4 * c4);
-        const float4 q = ldg4(cb + 4 * c4);
-        s = fmaf(d4.x, q.x, s); s = fmaf(d4.y, q.y, s); s = fmaf(d4.z, q.z, s); s = fmaf(d4.w, q.w, s);
+  for (int k = 0; k < KT; ++k) acc[k] = 0.f;
+
+  const int nslab = (H + 1) + si + so + 1;  // slabs of (up to) 64 features
+  for (int sb = 0; sb < nslab; ++sb) {
+    // ---- stage G slab: Gs[f][k] for 64 features f and KT latent coordinates ----
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < 64 * KT; idx += 128) {
+      const int f = idx / KT, k = idx - f * KT, kk = k0 + k;
+      float g = 0.f;
+      if (kk < K) {
+        if (sb <= H) g = __ldg(&C_all[((long long)sb * K1 + kk) * 64 + f]);
+        else if (sb < H + 1 + si) g = __ldg(&M0[((long long)kk * si + (sb - H - 1)) * 64 + f]);
+        else if (sb < H + 1 + si + so) g = __ldg(&ML[((long long)kk * 64 + f) * so + (sb - H - 1 - si)]);
+        else if (f < so) g = __ldg(&C_all[((long long)(H + 1) * K1 + kk) * 64 + f]);
       }
+      Gs[f][k] = g;
     }
-    {  // first matrix
-      const float* dar = a.da + bb * 64;
-      for (int i = 0; i < si; ++i) {
-        const float* mw = M0 + ((long long)kk * si + i) * 64;
-        float t = 0.f;
+    __syncthreads();
+    // ---- this row's 64 features of the slab ----
+    const float* src;
+    float mul = 1.f;
+    int nf = 64;
+    if (sb <= H) src = a.da + (long long)sb * a.B * 64 + bb * 64;
+    else if (sb < H + 1 + si) { src = a.da + bb * 64; mul = om0 * a.x[bb * si + (sb - H - 1)]; }
+    else if (sb < H + 1 + si + so) { src = a.save + (long long)H * a.B * 64 + bb * 64; mul = a.du[bb * so + (sb - H - 1 - si)]; }
+    else { src = a.du + bb * so; nf = so; }
+    if (nf == 64) {
+#pragma unroll 4
+      for (int f4 = 0; f4 < 16; ++f4) {
+        const float4 v = *reinterpret_cast<const float4*>(src + 4 * f4);
+        const float fv[4] = {v.x * mul, v.y * mul, v.z * mul, v.w * mul};
 #pragma unroll
-        for (int c4 = 0; c4 < 16; ++c4) {
-          const float4 d4 = *reinterpret_cast<const float4*>(dar + 4 * c4);
-          const float4 q = ldg4(mw + 4 * c4);
-          t = fmaf(d4.x, q.x, t); t = fmaf(d4.y, q.y, t); t = fmaf(d4.z, q.z, t); t = fmaf(d4.w, q.w, t);
-        }
-        s = fmaf(om0 * xv[i], t, s);
+        for (int e = 0; e < 4; ++e)
+#pragma unroll
+          for (int k = 0; k < KT; k += 4) {
+            const float4 g = *reinterpret_cast<const float4*>(&Gs[4 * f4 + e][k]);
+            acc[k] = fmaf(fv[e], g.x, acc[k]); acc[k + 1] = fmaf(fv[e], g.y, acc[k + 1]);
+            acc[k + 2] = fmaf(fv[e], g.z, acc[k + 2]); acc[k + 3] = fmaf(fv[e], g.w, acc[k + 3]);
+          }
+      }
+    } else {
+      for (int f = 0; f < nf; ++f) {
+        const float fv = src[f];
+#pragma unroll
+        for (int k = 0; k < KT; ++k) acc[k] = fmaf(fv, Gs[f][k], acc[k]);
       }
     }
-    {  // last matrix
-      const float* hl = a.save + (long long)H * a.B * 64 + bb * 64;
-      const float* Mk = ML + (long long)kk * 64 * so;
-      const float* CL = C_all + ((long long)(H + 1) * K1 + kk) * 64;
-      for (int c = 0; c < so; ++c) {
-        float t = __ldg(&CL[c]);
-        for (int i = 0; i < pl.n; ++i) t = fmaf(hl[i], __ldg(&Mk[i * so + c]), t);
-        s = fmaf(dy[c], t, s);
-      }
-    }
-    if (live) a.dz[b * K + kk] += s;
+  }
+  if (live) {
+#pragma unroll
+    for (int k = 0; k < KT; ++k)
+      if (k0 + k < K) a.dz[b * K + k0 + k] += acc[k];
   }
 }
 
@@ -355,8 +374,10 @@ int nif_tc_bwd_data_impl(const Plan& pl, long long B, const float* z, const floa
   NIF_CUDA_CHECK(cudaGetLastError());
   DzEdgeArgs e;
   e.B = B; e.x = x; e.packed = packed; e.save = save; e.da = da; e.du = du; e.dz = dz;
-  nif_dz_edge_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(pl, e);
-  NIF_CUDA_CHECK(cudaGetLastError());
+  for (int k0 = 0; k0 < pl.K; k0 += 32) {  // 32 latent coordinates per pass
+    nif_dz_edge_kernel<32><<<(unsigned)((B + 127) / 128), 128, 0, st>>>(pl, e, k0);
+    NIF_CUDA_CHECK(cudaGetLastError());
+  }
   return NIF_OK;
 }
 
