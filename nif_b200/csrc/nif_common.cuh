@@ -37,7 +37,17 @@ struct Plan {
   //   TCS: [H][KP] fp32 inverse scales 2^-e of slab (h, kappa)   (KP = K+1 rounded up to even, NCH = KP/2)
   int tc, KP, NCH;
   long long off_TCF, off_TCB, off_TCS;
+  // small forward operand tiles (same split / layout, one inverse scale per tile in TCS2):
+  //   X0[i'] (i' = 0..si)  [64 (j) x KZ (kappa)]   M0[kappa][i'][j], or C_0[kappa][j] for i' = si
+  //   XC[m]  (m = 1..H)    [64 (j) x KZ (kappa)]   C_m[kappa][j]
+  //   XL[q]  (q < NLC)     [LPC*KZ rows x 64 (i)]  row (c_l * KZ + kappa) = ML[kappa][i][LPC*q + c_l]
+  // KZ = K+1 rounded up to 16; LPC = outputs per XL tile (2 if 2*KZ <= 128 else 1); NLC = ceil(so / LPC).
+  int KZ, LPC, NLC;
+  long long off_TCX, off_TCS2;
 };
+__host__ __device__ inline long long plan_x0_floats(const Plan& p) { return 64LL * p.KZ; }            // one X0 / XC chunk [hi|lo]
+__host__ __device__ inline long long plan_xl_floats(const Plan& p) { return (long long)p.LPC * p.KZ * 64; }       // one XL chunk [hi|lo]
+__host__ __device__ inline int plan_n_small(const Plan& p) { return p.si + 1 + p.H + p.NLC; }        // number of small tiles
 #define NIF_TC_CHUNK_FLOATS 8192   // [hi | lo] x 128 x 64 fp16 = 32 KB, counted in floats
 
 __host__ __device__ inline int plan_w_off(const Plan& p, int m) {  // reference column offset of matrix m

@@ -56,12 +56,17 @@ int nif_make_plan(const nif_desc_t* d, Plan* out) {
   p.tc = d->dtype_compute == 2 ? 1 : 0;
   p.KP = (p.K + 2) / 2 * 2;
   p.NCH = p.KP / 2;
-  p.off_TCF = p.off_TCB = p.off_TCS = 0;
+  p.KZ = (p.K + 1 + 15) / 16 * 16;
+  p.LPC = (2 * p.KZ <= 128) ? 2 : 1;
+  p.NLC = (p.so + p.LPC - 1) / p.LPC;
+  p.off_TCF = p.off_TCB = p.off_TCS = p.off_TCX = p.off_TCS2 = 0;
   if (p.tc) {
     off = (off + 31) / 32 * 32;
     p.off_TCF = off; off += (long long)p.H * p.NCH * NIF_TC_CHUNK_FLOATS;
     p.off_TCB = off; off += (long long)p.H * p.NCH * NIF_TC_CHUNK_FLOATS;
     p.off_TCS = off; off += up4((long long)p.H * p.KP);
+    p.off_TCX = off; off += (p.si + 1 + p.H) * plan_x0_floats(p) + p.NLC * plan_xl_floats(p);
+    p.off_TCS2 = off; off += up4(plan_n_small(p));
   }
   p.packed_floats = (off + 31) / 32 * 32;  // keep every image 128-byte aligned
   *out = p;
@@ -72,6 +77,22 @@ int nif_make_plan(const nif_desc_t* d, Plan* out) {
 __device__ __forceinline__ float src_at(const Plan& pl, const float* __restrict__ w_h, const float* __restrict__ b_h,
                                         long long g, int kappa, int col) {
   return (kappa < pl.K) ? w_h[(long long)kappa * pl.P + col] : b_h[g * pl.P + col];
+}
+
+// logical value of small tile T at (row, col); see Plan for the tile list
+__device__ __forceinline__ float tcx_value(const Plan& pl, const float* __restrict__ w_h, const float* __restrict__ b_h,
+                                           int T, int row, int col) {
+  const int K1 = pl.K + 1, n = pl.n;
+  if (T <= pl.si + pl.H) {  // X0[i'] / XC[m]: row = j, col = kappa
+    if (col >= K1 || row >= n) return 0.f;
+    if (T < pl.si) return src_at(pl, w_h, b_h, 0, col, T * n + row);
+    const int m = T - pl.si;  // 0 (bias of the first layer) .. H
+    return src_at(pl, w_h, b_h, 0, col, plan_b_off(pl, m) + row);
+  }
+  const int q = T - (pl.si + 1 + pl.H);  // XL[q]: row = c_l * KZ + kappa, col = i
+  const int cl = row / pl.KZ, kk = row % pl.KZ, c = pl.LPC * q + cl;
+  if (kk >= K1 || c >= pl.so || col >= n) return 0.f;
+  return src_at(pl, w_h, b_h, 0, kk, plan_w_off(pl, pl.H + 1) + col * pl.so + c);
 }
 
 __global__ void __launch_bounds__(256) nif_pack_kernel(const Plan pl, long long G, const float* __restrict__ w_h,
@@ -149,8 +170,35 @@ __global__ void __launch_bounds__(256) nif_pack_kernel(const Plan pl, long long 
         out = __floats2half2_rn(a0 - __half2float(__float2half_rn(a0)), a1 - __half2float(__float2half_rn(a1)));
       }
       v = __uint_as_float(*reinterpret_cast<uint32_t*>(&out));
+    } else if (r >= pl.off_TCX && r < pl.off_TCS2) {
+      // small forward operand tiles; float slot -> (tile, hi/lo, row, col pair)
+      r -= pl.off_TCX;
+      const long long nz = (long long)(pl.si + 1 + pl.H) * plan_x0_floats(pl);
+      int T, lo, row, col;
+      if (r < nz) {
+        T = (int)(r / plan_x0_floats(pl));
+        int t = (int)(r % plan_x0_floats(pl));
+        lo = t / (32 * pl.KZ); t %= 32 * pl.KZ;
+        const int rg = t / (4 * pl.KZ); t %= 4 * pl.KZ;   // 8-row group: KZ/8 chunks x 32 float slots
+        const int kc = t / 32; t %= 32;
+        row = rg * 8 + t / 4; col = kc * 8 + (t % 4) * 2;
+      } else {
+        r -= nz;
+        T = pl.si + 1 + pl.H + (int)(r / plan_xl_floats(pl));
+        int t = (int)(r % plan_xl_floats(pl));
+        lo = t / (pl.LPC * pl.KZ * 32); t %= pl.LPC * pl.KZ * 32;  // hi tile: LPC*KZ rows x 64 fp16
+        const int rg = t / 256; t %= 256;
+        const int kc = t / 32; t %= 32;
+        row = rg * 8 + t / 4; col = kc * 8 + (t % 4) * 2;
+      }
+      const float sc = 1.0f / packed[pl.off_TCS2 + T];
+      const float a0 = tcx_value(pl, w_h, b_h, T, row, col) * sc, a1 = tcx_value(pl, w_h, b_h, T, row, col + 1) * sc;
+      __half2 out;
+      if (!lo) out = __floats2half2_rn(a0, a1);
+      else out = __floats2half2_rn(a0 - __half2float(__float2half_rn(a0)), a1 - __half2float(__float2half_rn(a1)));
+      v = __uint_as_float(*reinterpret_cast<uint32_t*>(&out));
     } else {
-      continue;  // TCS is written by nif_pack_scales_kernel before this kernel runs
+      continue;  // scale tables are written by nif_pack_scales_kernel before this kernel runs
     }
     packed[e] = v;
   }
@@ -159,10 +207,16 @@ __global__ void __launch_bounds__(256) nif_pack_kernel(const Plan pl, long long 
 // one block per (hidden matrix, kappa): inverse power-of-two scale of the slab so that max|M| * 2^e is in [2^13, 2^14)
 __global__ void __launch_bounds__(256) nif_pack_scales_kernel(const Plan pl, const float* __restrict__ w_h,
                                                               const float* __restrict__ b_h, float* __restrict__ packed) {
+  const int nmain = pl.H * pl.KP;
+  const bool small = (int)blockIdx.x >= nmain;
   const int h = blockIdx.x / pl.KP, kk = blockIdx.x % pl.KP;
+  const int T = blockIdx.x - nmain;
   const int n = pl.n;
   float m = 0.f;
-  if (kk <= pl.K)
+  if (small) {
+    const int rows = (T <= pl.si + pl.H) ? 64 : pl.LPC * pl.KZ, cols = (T <= pl.si + pl.H) ? pl.KZ : 64;
+    for (int e = threadIdx.x; e < rows * cols; e += 256) m = fmaxf(m, fabsf(tcx_value(pl, w_h, b_h, T, e / cols, e % cols)));
+  } else if (kk <= pl.K)
     for (int e = threadIdx.x; e < n * n; e += 256) m = fmaxf(m, fabsf(src_at(pl, w_h, b_h, 0, kk, plan_w_off(pl, h + 1) + e)));
   __shared__ float red[256];
   red[threadIdx.x] = m;
@@ -179,13 +233,14 @@ __global__ void __launch_bounds__(256) nif_pack_scales_kernel(const Plan pl, con
       ex = max(-100, min(100, ex));
       inv = __uint_as_float((uint32_t)(127 + ex - 13) << 23);    // 2^(ex-13): scaled max lands in [2^13, 2^14)
     }
-    packed[pl.off_TCS + h * pl.KP + kk] = inv;
+    if (small) packed[pl.off_TCS2 + T] = inv;
+    else packed[pl.off_TCS + h * pl.KP + kk] = inv;
   }
 }
 
 int nif_pack_impl(const Plan& pl, long long G, const float* w_h, const float* b_h, float* packed, cudaStream_t st) {
-  if (pl.tc && pl.H > 0) {
-    nif_pack_scales_kernel<<<(unsigned)(pl.H * pl.KP), 256, 0, st>>>(pl, w_h, b_h, packed);
+  if (pl.tc) {
+    nif_pack_scales_kernel<<<(unsigned)(pl.H * pl.KP + plan_n_small(pl)), 256, 0, st>>>(pl, w_h, b_h, packed);
     NIF_CUDA_CHECK(cudaGetLastError());
   }
   const long long total = G * pl.packed_floats;

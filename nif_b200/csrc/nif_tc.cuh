@@ -21,11 +21,11 @@
 #define TC_SBO 1024u
 #define TC_TILE_BYTES 16384u  // 128 rows x 64 fp16
 
-__device__ __forceinline__ uint64_t tc_make_desc(uint32_t saddr) {
+__device__ __forceinline__ uint64_t tc_make_desc(uint32_t saddr, uint32_t sbo = TC_SBO) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3FFF);
   d |= (uint64_t)((TC_LBO >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((TC_SBO >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;  // descriptor version (sm_100)
   return d;                // layout type 0 (no swizzle), base offset 0
 }
@@ -45,6 +45,16 @@ __device__ __forceinline__ void tc_mma_split_k64(uint32_t d1, uint32_t d2, uint6
                                                  uint64_t b_lo, uint32_t idesc) {
 #pragma unroll
   for (int ks = 0; ks < 4; ++ks) {  // 16 elements of K = 2 core matrices = 256 B = 16 descriptor units
+    const uint64_t adv = (uint64_t)(ks * 16);
+    tc_mma_f16(d2, a_lo + adv, b_hi + adv, idesc, ks > 0 ? 1u : 0u);
+    tc_mma_f16(d2, a_hi + adv, b_lo + adv, idesc, 1u);
+    tc_mma_f16(d1, a_hi + adv, b_hi + adv, idesc, ks > 0 ? 1u : 0u);
+  }
+}
+// same with a run-time K extent (ksteps instructions of K = 16 per term)
+__device__ __forceinline__ void tc_mma_split(uint32_t d1, uint32_t d2, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi,
+                                             uint64_t b_lo, uint32_t idesc, int ksteps) {
+  for (int ks = 0; ks < ksteps; ++ks) {
     const uint64_t adv = (uint64_t)(ks * 16);
     tc_mma_f16(d2, a_lo + adv, b_hi + adv, idesc, ks > 0 ? 1u : 0u);
     tc_mma_f16(d2, a_hi + adv, b_lo + adv, idesc, 1u);
@@ -92,6 +102,9 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16]) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+// warp-group register re-allocation (all 4 warps of an aligned warp group must execute it)
+template <int N> __device__ __forceinline__ void tc_reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void tc_reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -124,6 +137,27 @@ __device__ __forceinline__ void tc_store_row_split(unsigned char* tile_hi, unsig
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const float a0 = h[8 * c + 2 * e] * sc, a1 = h[8 * c + 2 * e + 1] * sc;
+      const __half2 hh = __floats2half2_rn(a0, a1);
+      const float2 hf = __half22float2(hh);
+      const __half2 ll = __floats2half2_rn(a0 - hf.x, a1 - hf.y);
+      hi[e] = *reinterpret_cast<const uint32_t*>(&hh);
+      lo[e] = *reinterpret_cast<const uint32_t*>(&ll);
+    }
+    *reinterpret_cast<uint4*>(tile_hi + row_off + c * TC_LBO) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(tile_lo + row_off + c * TC_LBO) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
+// same for a row of `w8 * 8` values held in shared memory style access v(k) (used for the zt operand tile)
+template <class F>
+__device__ __forceinline__ void tc_store_row_split_fn(unsigned char* tile_hi, unsigned char* tile_lo, int r, uint32_t sbo,
+                                                      int w8, float sc, F value) {
+  const uint32_t row_off = (uint32_t)(r >> 3) * sbo + (uint32_t)(r & 7) * 16u;
+  for (int c = 0; c < w8; ++c) {
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float a0 = value(8 * c + 2 * e) * sc, a1 = value(8 * c + 2 * e + 1) * sc;
       const __half2 hh = __floats2half2_rn(a0, a1);
       const float2 hf = __half22float2(hh);
       const __half2 ll = __floats2half2_rn(a0 - hf.x, a1 - hf.y);

@@ -20,7 +20,7 @@ struct TcBwdArgs {
   unsigned* maxes;  // [0..H] max|da_m| bits, [H+1] max|zt| bits, [H+2 .. 2H+2] max|h_m| bits (m = 1..H+1)
 };
 
-#define TCB_THREADS 320
+#define TCB_THREADS 384  // 8 epilogue warps + MMA warp + producer warp + 2 idle warps (register donors)
 #define TCB_STAGES 2
 #define TCB_STAGE_BYTES 32768u
 
@@ -72,6 +72,8 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) nif_tc_bwd_data_kernel(const P
   long long my_pairs = 0;
   if ((long long)blockIdx.x < a.total_pairs) my_pairs = (a.total_pairs - blockIdx.x + gridDim.x - 1) / gridDim.x;
 
+  if (warp >= 8) {
+  tc_reg_dec<56>();  // MMA / producer / idle warps donate registers to the epilogue warp groups
   if (warp == 9) {
     if (lane == 0) {  // weight-stream producer: hidden matrices in reverse order
       long long g = 0;
@@ -114,7 +116,9 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) nif_tc_bwd_data_kernel(const P
             tc_commit(&b_empty[s]);
           }
     }
+  }
   } else {
+    tc_reg_inc<224>();
     // ---------------- epilogue warps: thread r <-> row r of tile wg <-> TMEM lane r ----------------
     const int wg = warp >> 2;
     const int r = tid & 127;

@@ -5,7 +5,10 @@
 // with the shared-operand product V on the tensor cores:
 //   A = h tile [128 rows x 64], per-row power-of-two scale, hi/lo fp16 split, written by the epilogue threads;
 //   B = chunk of 2 latent coordinates [128 (kappa_l, j) x 64 (i)], per-slab scale, hi/lo split, streamed from the
-//       packed image by cp.async.bulk (32 KB per chunk, 3 stages);
+//       packed image by cp.async.bulk (32 KB per chunk, 2 stages);
+// Layer 0, the bias sums sum_kappa zt[kappa] C_m[kappa][:] and the last layer are tensor-core chunks too (A = the
+// zt tile resp. the h tile, small B tiles from the packed image), so the CUDA cores only run the per-row
+// latent contraction, the activations and the operand split.
 //   D = D1 [128 x 128] (hi*hi) and D2 [128 x 128] (cross terms), fp32 in TMEM.
 // The per-row contraction over kappa (and the un-scaling) runs on the CUDA cores straight out of TMEM: thread r
 // owns row r = TMEM lane r.
@@ -24,20 +27,28 @@ struct TcFwdArgs {
   float *u, *save;
 };
 
-#define TCF_THREADS 320
-#define TCF_STAGES 3
-#define TCF_STAGE_BYTES 32768u  // [hi | lo] x 16 KB
+#define TCF_THREADS 384  // 8 epilogue warps + MMA warp + producer warp + 2 idle warps (register donors)
+#define TCF_STAGES 2
+#define TCF_STAGE_BYTES 32768u  // [hi | lo] x 16 KB (small chunks use a prefix)
 
-__host__ __device__ inline size_t tcf_smem_bytes(int KP, int si) {
-  return 4 * (size_t)TC_TILE_BYTES + TCF_STAGES * (size_t)TCF_STAGE_BYTES + 2 * (size_t)KP * 128 * 4 +
-         2 * (size_t)si * 128 * 4 + 256;
+// Chunk schedule of one tile pair (identical for producer, MMA issuer and epilogue):
+//   Z0(i'), i' = 0..si      A = zt tile, B = X0[i']     N = 64      layer 0:  pre0 += xt[i'] * D
+//   for m = 1..H:  ZC(m)    A = zt tile, B = XC[m]      N = 64      bias sum of layer m (initialises acc)
+//                  M(m,c)   A = h_m tile, B = TCF[m-1][c] N = 128   c = 0..NCH-1
+//   L(q), q < NLC           A = h_{H+1} tile, B = XL[q] N = LPC*KZ  last layer
+__host__ __device__ inline size_t tcf_smem_bytes(int KP, int KZ, int si) {
+  return 4 * (size_t)TC_TILE_BYTES + 2 * 2 * 128 * (size_t)KZ * 2 + TCF_STAGES * (size_t)TCF_STAGE_BYTES +
+         2 * (size_t)KP * 128 * 4 + 2 * (size_t)si * 128 * 4 + 256;
 }
 
 template <bool SAVE>
 __global__ void __launch_bounds__(TCF_THREADS, 1) nif_tc_fwd_kernel(const Plan pl, const TcFwdArgs a) {
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char* A_all = smem;                                  // tile t: hi at t*32K, lo at t*32K + 16K
-  unsigned char* Bst = smem + 4 * TC_TILE_BYTES;                // [TCF_STAGES][hi | lo]
+  unsigned char* Z_all = smem + 4 * TC_TILE_BYTES;              // zt operand, tile t: hi at t*2*zbytes, lo at + zbytes
+  const uint32_t zbytes = 128u * (uint32_t)pl.KZ * 2u;          // one of hi / lo
+  const uint32_t sbo_z = (uint32_t)(pl.KZ / 8) * 128u;          // 8-row group stride of a KZ-wide K-major tile
+  unsigned char* Bst = Z_all + 4 * zbytes;                      // [TCF_STAGES][hi | lo]
   float* zs_all = reinterpret_cast<float*>(Bst + TCF_STAGES * TCF_STAGE_BYTES);  // [2][KP][128]
   float* xs_all = zs_all + 2 * pl.KP * 128;                     // [2][si][128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(xs_all + 2 * pl.si * 128);
@@ -50,6 +61,9 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) nif_tc_fwd_kernel(const Plan p
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int K = pl.K, K1 = pl.K + 1, KP = pl.KP, NCH = pl.NCH, H = pl.H, n = pl.n, si = pl.si, so = pl.so;
+  const int KZ = pl.KZ, NLC = pl.NLC, LPC = pl.LPC;
+  const uint32_t small_bytes = 2u * 64u * (uint32_t)KZ * 2u;        // X0 / XC chunk [hi | lo]
+  const uint32_t last_bytes = 2u * (uint32_t)(LPC * KZ) * 64u * 2u;  // XL chunk [hi | lo]
 
   if (tid == 0) {
     for (int i = 0; i < TCF_STAGES; ++i) {
@@ -72,63 +86,89 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) nif_tc_fwd_kernel(const Plan p
   long long my_pairs = 0;
   if ((long long)blockIdx.x < a.total_pairs) my_pairs = (a.total_pairs - blockIdx.x + gridDim.x - 1) / gridDim.x;
 
+  if (warp >= 8) {
+  tc_reg_dec<56>();  // MMA / producer / idle warps donate registers to the epilogue warp groups
   if (warp == 9) {
     // ---------------- weight-stream producer ----------------
     if (lane == 0) {
       long long g = 0;
-      const float* src0 = a.packed + pl.off_TCF;
-      for (long long t = 0; t < my_pairs; ++t)
-        for (int h = 0; h < H; ++h)
-          for (int c = 0; c < NCH; ++c, ++g) {
-            const int s = (int)(g % TCF_STAGES);
-            mbar_wait(&b_empty[s], (uint32_t)(((g / TCF_STAGES) & 1) ^ 1));
-            mbar_expect_tx(&b_full[s], TCF_STAGE_BYTES);
-            bulk_g2s(Bst + s * TCF_STAGE_BYTES, src0 + ((long long)h * NCH + c) * NIF_TC_CHUNK_FLOATS,
-                     TCF_STAGE_BYTES, &b_full[s]);
-          }
+      const float* tcf = a.packed + pl.off_TCF;
+      const float* tcx = a.packed + pl.off_TCX;
+      auto put = [&](const float* src, uint32_t bytes) {
+        const int s = (int)(g % TCF_STAGES);
+        mbar_wait(&b_empty[s], (uint32_t)(((g / TCF_STAGES) & 1) ^ 1));
+        mbar_expect_tx(&b_full[s], bytes);
+        bulk_g2s(Bst + s * TCF_STAGE_BYTES, src, bytes, &b_full[s]);
+        ++g;
+      };
+      for (long long t = 0; t < my_pairs; ++t) {
+        for (int i = 0; i <= si; ++i) put(tcx + (long long)i * plan_x0_floats(pl), small_bytes);
+        for (int h = 0; h < H; ++h) {
+          put(tcx + (long long)(si + 1 + h) * plan_x0_floats(pl), small_bytes);
+          for (int c = 0; c < NCH; ++c) put(tcf + ((long long)h * NCH + c) * NIF_TC_CHUNK_FLOATS, TCF_STAGE_BYTES);
+        }
+        for (int q = 0; q < NLC; ++q)
+          put(tcx + (long long)(si + 1 + H) * plan_x0_floats(pl) + (long long)q * plan_xl_floats(pl), last_bytes);
+      }
     }
   } else if (warp == 8) {
     // ---------------- MMA issuer ----------------
     if (lane == 0) {
-      const uint32_t idesc = tc_idesc_f16(128);
-      uint64_t da_hi[2], da_lo[2];
+      uint64_t da_hi[2], da_lo[2], dz_hi[2], dz_lo[2];
       for (int t = 0; t < 2; ++t) {
-        da_hi[t] = tc_make_desc(smem_u32(A_all + t * 2 * TC_TILE_BYTES));
-        da_lo[t] = tc_make_desc(smem_u32(A_all + t * 2 * TC_TILE_BYTES + TC_TILE_BYTES));
+        da_hi[t] = tc_make_desc(smem_u32(A_all + t * 2 * TC_TILE_BYTES), TC_SBO);
+        da_lo[t] = tc_make_desc(smem_u32(A_all + t * 2 * TC_TILE_BYTES + TC_TILE_BYTES), TC_SBO);
+        dz_hi[t] = tc_make_desc(smem_u32(Z_all + t * 2 * zbytes), sbo_z);
+        dz_lo[t] = tc_make_desc(smem_u32(Z_all + t * 2 * zbytes + zbytes), sbo_z);
       }
-      long long g = 0, L = 0;
-      for (long long p = 0; p < my_pairs; ++p)
-        for (int h = 0; h < H; ++h, ++L)
-          for (int c = 0; c < NCH; ++c, ++g) {
-            const int s = (int)(g % TCF_STAGES);
-            mbar_wait(&b_full[s], (uint32_t)((g / TCF_STAGES) & 1));
-            const uint64_t db_hi = tc_make_desc(smem_u32(Bst + s * TCF_STAGE_BYTES));
-            const uint64_t db_lo = tc_make_desc(smem_u32(Bst + s * TCF_STAGE_BYTES + TC_TILE_BYTES));
+      long long g = 0;        // chunk counter (stage / accumulator phases)
+      long long ar[2] = {0, 0};  // a_ready phases consumed per tile
+      // one chunk for both tiles: A operand kind (0 = zt tile, 1 = h tile), K extent, B geometry, N
+      auto chunk = [&](int a_kind, bool wait_a, int ksteps, uint32_t b_half_bytes, uint32_t b_sbo, int N) {
+        const int s = (int)(g % TCF_STAGES);
+        mbar_wait(&b_full[s], (uint32_t)((g / TCF_STAGES) & 1));
+        const uint64_t db_hi = tc_make_desc(smem_u32(Bst + s * TCF_STAGE_BYTES), b_sbo);
+        const uint64_t db_lo = tc_make_desc(smem_u32(Bst + s * TCF_STAGE_BYTES + b_half_bytes), b_sbo);
+        const uint32_t idesc = tc_idesc_f16(N);
 #pragma unroll
-            for (int t = 0; t < 2; ++t) {
-              if (c == 0) mbar_wait(&a_ready[t], (uint32_t)(L & 1));
-              mbar_wait(&t_empty[t], (uint32_t)((g & 1) ^ 1));
-              tc_fence_after();
-              const uint32_t d1 = tmem + (uint32_t)t * 256u;
-              tc_mma_split_k64(d1, d1 + 128u, da_hi[t], da_lo[t], db_hi, db_lo, idesc);
-              tc_commit(&t_full[t]);
-            }
-            tc_commit(&b_empty[s]);
-          }
+        for (int t = 0; t < 2; ++t) {
+          if (wait_a) { mbar_wait(&a_ready[t], (uint32_t)(ar[t] & 1)); ++ar[t]; }
+          mbar_wait(&t_empty[t], (uint32_t)((g & 1) ^ 1));
+          tc_fence_after();
+          const uint32_t d1 = tmem + (uint32_t)t * 256u;
+          tc_mma_split(d1, d1 + 128u, a_kind ? da_hi[t] : dz_hi[t], a_kind ? da_lo[t] : dz_lo[t], db_hi, db_lo, idesc, ksteps);
+          tc_commit(&t_full[t]);
+        }
+        tc_commit(&b_empty[s]);
+        ++g;
+      };
+      for (long long p = 0; p < my_pairs; ++p) {
+        for (int i = 0; i <= si; ++i) chunk(0, i == 0, KZ / 16, small_bytes / 2, sbo_z, 64);
+        for (int h = 0; h < H; ++h) {
+          chunk(0, false, KZ / 16, small_bytes / 2, sbo_z, 64);
+          for (int c = 0; c < NCH; ++c) chunk(1, c == 0, 4, TC_TILE_BYTES, TC_SBO, 128);
+        }
+        for (int q = 0; q < NLC; ++q) chunk(1, q == 0, 4, last_bytes / 2, TC_SBO, LPC * KZ);
+      }
     }
+  }
   } else {
+    tc_reg_inc<224>();
     // ---------------- epilogue warps: thread r <-> row r of tile wg <-> TMEM lane r ----------------
     const int wg = warp >> 2;  // tile of the pair
     const int r = tid & 127;
     const uint32_t tm = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)wg * 256u;
     unsigned char* A_hi = A_all + wg * 2 * TC_TILE_BYTES;
     unsigned char* A_lo = A_hi + TC_TILE_BYTES;
+    unsigned char* Z_hi = Z_all + wg * 2 * zbytes;
+    unsigned char* Z_lo = Z_hi + zbytes;
     float* zs = zs_all + wg * KP * 128;
     float* xs = xs_all + wg * si * 128;
     const float* C_all = a.packed + pl.off_C;
     const float* invB = a.packed + pl.off_TCS;
+    const float* invX = a.packed + pl.off_TCS2;
     const uint32_t row_off = (uint32_t)(r >> 3) * TC_SBO + (uint32_t)(r & 7) * 16u;
-    long long g = 0;
+    long long g = 0;  // chunk counter (accumulator phases), advances exactly like the MMA issuer's
     for (long long p = 0; p < my_pairs; ++p) {
       const long long row0 = ((blockIdx.x + p * gridDim.x) * 2 + wg) * 128;
       const long long b = row0 + r;
@@ -146,8 +186,46 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) nif_tc_fwd_kernel(const Plan p
       }
       named_bar_sync(1 + wg, 128);
 
+      // ---- zt operand tile (used by layer 0 and by every bias-sum chunk) ----
+      float inv_z;
+      {
+        float zmax = 0.f;
+        for (int kk = 0; kk < K1; ++kk) zmax = fmaxf(zmax, fabsf(zs[kk * 128 + r]));
+        float sc_z;
+        tc_row_scale(zmax, sc_z, inv_z);
+        // the MMAs that read the previous pair's zt tile completed before this thread finished that pair
+        tc_store_row_split_fn(Z_hi, Z_lo, r, sbo_z, KZ / 8, sc_z, [&](int kk) { return kk < K1 ? zs[kk * 128 + r] : 0.f; });
+        fence_async_smem();
+        mbar_arrive(&a_ready[wg]);
+      }
+
       float hcur[64];     // output of the layer being finished (input of the next one)
-      float inv_a = 1.f;  // inverse of the power-of-two scale of this row's operand tile
+      float inv_a = 1.f;  // inverse of the power-of-two scale of this row's h operand tile
+
+      // acc[j] (+)= coef * (D1 + D2)[j] for the 64 columns of a small chunk
+      auto drain64 = [&](float (&acc)[64], float coef, bool init) {
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          float v1[32], v2[32];
+          tc_ld32(tm + (uint32_t)(hf * 32), v1);
+          tc_ld32(tm + (uint32_t)(hf * 32) + 128u, v2);
+          tc_wait_ld();
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const float t = v1[e] + v2[e];
+            acc[hf * 32 + e] = init ? coef * t : fmaf(coef, t, acc[hf * 32 + e]);
+          }
+        }
+      };
+      auto chunk_begin = [&]() {
+        mbar_wait(&t_full[wg], (uint32_t)(g & 1));
+        tc_fence_after();
+      };
+      auto chunk_end = [&]() {
+        tc_fence_before();
+        mbar_arrive(&t_empty[wg]);
+        ++g;
+      };
 
       // activation / residual / stash for layer m given pre-activations in `pre`; result in hcur.
       auto finish_layer = [&](int m, float (&pre)[64]) {
@@ -189,41 +267,9 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) nif_tc_fwd_kernel(const Plan p
           }
         }
       };
-
-      // ---- layer 0 (si -> n) on the CUDA cores; weights are warp-uniform loads ----
-      {
-        float pre[64];
-#pragma unroll
-        for (int j = 0; j < 64; ++j) pre[j] = 0.f;
-        const float om = plan_omega(pl, 0);
-        const float* M0 = a.packed + pl.off_M0;
-        for (int kk = 0; kk < K1; ++kk) {
-          const float zk = zs[kk * 128 + r];
-          const float* cb = C_all + (long long)kk * 64;  // layer 0 bias rows
-#pragma unroll
-          for (int c = 0; c < 16; ++c) {
-            const float4 q = ldg4(cb + 4 * c);
-            pre[4 * c] = fmaf(zk, q.x, pre[4 * c]); pre[4 * c + 1] = fmaf(zk, q.y, pre[4 * c + 1]);
-            pre[4 * c + 2] = fmaf(zk, q.z, pre[4 * c + 2]); pre[4 * c + 3] = fmaf(zk, q.w, pre[4 * c + 3]);
-          }
-          for (int i = 0; i < si; ++i) {
-            const float ai = zk * om * xs[i * 128 + r];
-            const float* mw = M0 + ((long long)kk * si + i) * 64;
-#pragma unroll
-            for (int c = 0; c < 16; ++c) {
-              const float4 q = ldg4(mw + 4 * c);
-              pre[4 * c] = fmaf(ai, q.x, pre[4 * c]); pre[4 * c + 1] = fmaf(ai, q.y, pre[4 * c + 1]);
-              pre[4 * c + 2] = fmaf(ai, q.z, pre[4 * c + 2]); pre[4 * c + 3] = fmaf(ai, q.w, pre[4 * c + 3]);
-            }
-          }
-        }
-        finish_layer(0, pre);
-      }
-
-      // ---- hidden layers on the tensor cores ----
-      for (int m = 1; m <= H; ++m) {
-        // operand tile for this layer.  Every MMA that read the previous contents has completed: this thread
-        // observed the last t_full of the previous layer.
+      // h operand tile for the next tensor-core layer.  Every MMA that read the previous contents has
+      // completed: this thread observed the t_full of the last chunk that used it.
+      auto publish_h = [&]() {
         float amax = 0.f;
 #pragma unroll
         for (int j = 0; j < 64; ++j) amax = fmaxf(amax, fabsf(hcur[j]));
@@ -232,20 +278,36 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) nif_tc_fwd_kernel(const Plan p
         tc_store_row_split(A_hi, A_lo, r, hcur, sc_a);
         fence_async_smem();
         mbar_arrive(&a_ready[wg]);
+      };
+
+      // ---- layer 0:  pre0[j] = sum_i' xt[i'] * (zt @ X0[i'])[j],  xt = [omega x, 1] ----
+      {
+        float pre[64];
+        const float om = plan_omega(pl, 0);
+        for (int i = 0; i <= si; ++i) {
+          chunk_begin();
+          const float coef = inv_z * __ldg(&invX[i]) * (i < si ? om * xs[i * 128 + r] : 1.f);
+          drain64(pre, coef, i == 0);
+          chunk_end();
+        }
+        finish_layer(0, pre);
+      }
+
+      // ---- hidden layers ----
+      for (int m = 1; m <= H; ++m) {
+        publish_h();
+        float acc[64];
+        chunk_begin();  // bias sum: acc[j] = sum_kappa zt[kappa] C_m[kappa][j]
+        drain64(acc, inv_z * __ldg(&invX[si + m]), true);
+        chunk_end();
         const float om_inv = plan_omega(pl, m) * inv_a;
         const float* invBm = invB + (m - 1) * KP;
-        float acc[64];
-#pragma unroll
-        for (int j = 0; j < 64; ++j) acc[j] = 0.f;
-        for (int c = 0; c < NCH; ++c, ++g) {
-          mbar_wait(&t_full[wg], (uint32_t)(g & 1));
-          tc_fence_after();
+        for (int c = 0; c < NCH; ++c) {
+          chunk_begin();
 #pragma unroll
           for (int kl = 0; kl < 2; ++kl) {
             const int kk = 2 * c + kl;
-            const float zk = zs[kk * 128 + r];
-            const float zo = zk * om_inv * __ldg(&invBm[kk]);
-            const float* cb = C_all + ((long long)m * K1 + (kk < K1 ? kk : 0)) * 64;
+            const float zo = zs[kk * 128 + r] * om_inv * __ldg(&invBm[kk]);
 #pragma unroll
             for (int hf = 0; hf < 2; ++hf) {  // 32 columns at a time: D1 + D2, then the latent contraction
               float v1[32], v2[32];
@@ -253,53 +315,40 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) nif_tc_fwd_kernel(const Plan p
               tc_ld32(tm + col, v1);
               tc_ld32(tm + col + 128u, v2);
               tc_wait_ld();
-              if (kk < K1) {
 #pragma unroll
-                for (int q4 = 0; q4 < 8; ++q4) {
-                  const float4 cq = ldg4(cb + hf * 32 + 4 * q4);
-                  const int j = hf * 32 + 4 * q4;
-                  acc[j] = fmaf(zk, cq.x, fmaf(zo, v1[4 * q4] + v2[4 * q4], acc[j]));
-                  acc[j + 1] = fmaf(zk, cq.y, fmaf(zo, v1[4 * q4 + 1] + v2[4 * q4 + 1], acc[j + 1]));
-                  acc[j + 2] = fmaf(zk, cq.z, fmaf(zo, v1[4 * q4 + 2] + v2[4 * q4 + 2], acc[j + 2]));
-                  acc[j + 3] = fmaf(zk, cq.w, fmaf(zo, v1[4 * q4 + 3] + v2[4 * q4 + 3], acc[j + 3]));
-                }
-              }
+              for (int e = 0; e < 32; ++e) acc[hf * 32 + e] = fmaf(zo, v1[e] + v2[e], acc[hf * 32 + e]);
             }
           }
-          tc_fence_before();
-          mbar_arrive(&t_empty[wg]);
+          chunk_end();
         }
         finish_layer(m, acc);
       }
 
-      // ---- last layer (n -> so) on the CUDA cores ----
+      // ---- last layer:  y[c] = sum_kappa zt[kappa] * ( (h @ ML[kappa])[c] + CL[kappa][c] ) ----
+      publish_h();
       {
-        const float* ML = a.packed + pl.off_ML;
         const float* CL = C_all + (long long)(H + 1) * K1 * 64;
-        float y[NIF_MAX_SO];
+        for (int q = 0; q < NLC; ++q) {
+          chunk_begin();
+          const float sL = inv_a * __ldg(&invX[si + 1 + H + q]);
+          for (int cl = 0; cl < LPC; ++cl) {
+            const int c = LPC * q + cl;
+            float y = 0.f;
+            for (int k0 = 0; k0 < KZ; k0 += 16) {
+              float v1[16], v2[16];
+              tc_ld16(tm + (uint32_t)(cl * KZ + k0), v1);
+              tc_ld16(tm + (uint32_t)(cl * KZ + k0) + 128u, v2);
+              tc_wait_ld();
 #pragma unroll
-        for (int c = 0; c < NIF_MAX_SO; ++c) y[c] = 0.f;
-        for (int kk = 0; kk < K1; ++kk) {
-          float sacc[NIF_MAX_SO];
-#pragma unroll
-          for (int c = 0; c < NIF_MAX_SO; ++c) sacc[c] = (c < so) ? __ldg(&CL[(long long)kk * 64 + c]) : 0.f;
-          const float* Mk = ML + (long long)kk * 64 * so;
-#pragma unroll
-          for (int i = 0; i < 64; ++i) {
-            if (i < n) {
-#pragma unroll
-              for (int c = 0; c < NIF_MAX_SO; ++c)
-                if (c < so) sacc[c] = fmaf(hcur[i], __ldg(&Mk[i * so + c]), sacc[c]);
+              for (int e = 0; e < 16; ++e) {
+                const int kk = k0 + e;
+                if (kk < K1 && c < so)
+                  y = fmaf(zs[kk * 128 + r], fmaf(sL, v1[e] + v2[e], __ldg(&CL[(long long)kk * 64 + c])), y);
+              }
             }
+            if (live && c < so) a.u[b * so + c] = y;
           }
-          const float zk = zs[kk * 128 + r];
-#pragma unroll
-          for (int c = 0; c < NIF_MAX_SO; ++c) y[c] = fmaf(zk, sacc[c], y[c]);
-        }
-        if (live) {
-#pragma unroll
-          for (int c = 0; c < NIF_MAX_SO; ++c)
-            if (c < so) a.u[b * so + c] = y[c];
+          chunk_end();
         }
       }
     }
@@ -311,7 +360,7 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) nif_tc_fwd_kernel(const Plan p
 
 template <bool SAVE>
 static int launch_tcf(const Plan& pl, const TcFwdArgs& a, cudaStream_t st) {
-  const size_t smem = tcf_smem_bytes(pl.KP, pl.si);
+  const size_t smem = tcf_smem_bytes(pl.KP, pl.KZ, pl.si);
   auto kern = nif_tc_fwd_kernel<SAVE>;
   NIF_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int dev = 0, sms = 0;
@@ -330,7 +379,7 @@ static int launch_tcf(const Plan& pl, const TcFwdArgs& a, cudaStream_t st) {
 int nif_tc_forward_impl(const Plan& pl, long long B, const float* z, const float* x, const float* packed, float* u,
                         float* save, cudaStream_t st) {
   if (!pl.tc || pl.NP != 64 || pl.H < 1 || pl.variant == NIF_VARIANT_SIREN_RES) return NIF_E_UNSUPPORTED;
-  if (tcf_smem_bytes(pl.KP, pl.si) > 227 * 1024) return NIF_E_UNSUPPORTED;
+  if (tcf_smem_bytes(pl.KP, pl.KZ, pl.si) > 227 * 1024 || pl.LPC * pl.KZ > 128) return NIF_E_UNSUPPORTED;
   TcFwdArgs a;
   a.B = B;
   a.total_pairs = (B + 255) / 256;
