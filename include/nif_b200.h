@@ -127,6 +127,26 @@ int nif_adam_step(int64_t n, float* p, const float* g, float* m, float* v, doubl
                   double b1, double b2, double eps, int64_t t, float l1, float l2, float g_scale,
                   void* stream);
 
+/* ParameterNet trunk (everything before the last linear layer): Dense(act) -> nlayers x MLP_SimpleShortCut ->
+ * Dense(latent), i.e. _call_parameter_net up to the bottleneck (nif/model.py:326-343, 176-216, 668-720;
+ * nif/layers/mlp.py:148-160).  theta is the trunk's weight vector in the column order
+ *   [ W_first (pi x units) | W_hidden[i] (units x units) ... | W_bottleneck (units x latent)
+ *     | b_first | b_hidden[i] ... | b_bottleneck ],  every matrix row-major [in, out].
+ * act: NIF_ACT_* except SINE (SIREN trunks are outside these kernels); units <= 64. */
+typedef struct nif_trunk_desc {
+  int32_t pi, latent, units, nlayers, act;
+} nif_trunk_desc_t;
+
+/* n_theta: floats of theta; save_floats_per_row: stash per row for the reverse pass; ws_floats: scratch for batch B. */
+int nif_trunk_query(const nif_trunk_desc_t* d, int64_t B, int64_t* n_theta, int64_t* save_floats_per_row,
+                    int64_t* ws_floats);
+/* z [B,latent] = trunk(p_in [B,pi]); save may be NULL for inference. */
+int nif_trunk_forward(const nif_trunk_desc_t* d, int64_t B, const float* p_in, const float* theta, float* z,
+                      float* save, void* stream);
+/* g_theta (same layout as theta) = d loss / d theta given dz [B,latent]; written if beta == 0, accumulated if 1. */
+int nif_trunk_backward(const nif_trunk_desc_t* d, int64_t B, const float* p_in, const float* theta,
+                       const float* save, const float* dz, float* g_theta, float beta, float* ws, void* stream);
+
 /* Utility used by the benchmark: sustained FP32 FMA rate of this GPU (TFLOP/s),
  * measured with CUDA events; blocks until done. */
 int nif_measure_fp32_peak(double* tflops);

@@ -16,6 +16,7 @@ CSRC = os.path.join(_HERE, "csrc")
 SYMBOLS = (
     "nif_last_error", "nif_version", "nif_query_sizes", "nif_pack", "nif_forward", "nif_forward_tangent",
     "nif_forward_given_w", "nif_mse_backward", "nif_backward", "nif_adam_step", "nif_measure_fp32_peak",
+    "nif_trunk_query", "nif_trunk_forward", "nif_trunk_backward",
 )
 
 VARIANT = {"nif": 0, "siren": 1, "siren_res": 2}
@@ -32,6 +33,11 @@ class Desc(C.Structure):
         ("l", C.c_int32), ("K", C.c_int32), ("omega0", C.c_float), ("dtype_compute", C.c_int32),
         ("reserved", C.c_int32),
     ]
+
+
+class TrunkDesc(C.Structure):
+    _fields_ = [("pi", C.c_int32), ("latent", C.c_int32), ("units", C.c_int32), ("nlayers", C.c_int32),
+                ("act", C.c_int32)]
 
 
 class Sizes(C.Structure):
@@ -80,6 +86,10 @@ def lib() -> C.CDLL:
     L.nif_backward.argtypes = [DP, I64, VP, VP, VP, VP, VP, VP, VP, F, VP, VP, VP]
     L.nif_adam_step.argtypes = [I64, VP, VP, VP, VP, C.c_double, C.c_double, C.c_double, C.c_double, I64, F, F, F, VP]
     L.nif_measure_fp32_peak.argtypes = [C.POINTER(C.c_double)]
+    TP, I64P = C.POINTER(TrunkDesc), C.POINTER(C.c_int64)
+    L.nif_trunk_query.argtypes = [TP, I64, I64P, I64P, I64P]
+    L.nif_trunk_forward.argtypes = [TP, I64, VP, VP, VP, VP, VP]
+    L.nif_trunk_backward.argtypes = [TP, I64, VP, VP, VP, VP, VP, F, VP, VP]
     for name in SYMBOLS:
         getattr(L, name)  # raises AttributeError if the build is stale
         if name not in ("nif_last_error",):

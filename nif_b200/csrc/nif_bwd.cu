@@ -457,10 +457,11 @@ struct EdgeArgs {
   float* part;  // [S][K+1][Q]
 };
 
-#define NIF_EDGE_KE 17  // latent coordinates per thread; 4 * 17 = 68 per pass over the batch
+// KE latent coordinates per thread (4 * KE per pass over the batch): 1 for K+1 <= 4, 9 for K+1 <= 36, else 17
 
+template <int KE>
 __global__ void __launch_bounds__(256) nif_bwd_edge_kernel(const Plan pl, const EdgeArgs a) {
-  constexpr int RC = 64, KC = 4 * NIF_EDGE_KE;
+  constexpr int RC = 64, KC = 4 * KE;
   __shared__ float zsm[RC][KC + 1];
   const int NP = pl.NP, K = pl.K, K1 = pl.K + 1, H = pl.H, si = pl.si, so = pl.so;
   const int tid = threadIdx.x, ql = tid % 64, ks = tid / 64;
@@ -492,9 +493,9 @@ __global__ void __launch_bounds__(256) nif_bwd_edge_kernel(const Plan pl, const 
       Ap = a.save + (long long)H * a.B * NP + i; sA = NP; Bp = a.du + c; sB = so;
     }
   }
-  float acc[NIF_EDGE_KE];
+  float acc[KE];
 #pragma unroll
-  for (int e = 0; e < NIF_EDGE_KE; ++e) acc[e] = 0.f;
+  for (int e = 0; e < KE; ++e) acc[e] = 0.f;
 
   for (long long rb = r0; rb < r1; rb += RC) {
     __syncthreads();
@@ -514,13 +515,13 @@ __global__ void __launch_bounds__(256) nif_bwd_edge_kernel(const Plan pl, const 
         float f = scale * __ldg(&Ap[b * sA]);
         if (Bp) f *= __ldg(&Bp[b * sB]);
 #pragma unroll
-        for (int e = 0; e < NIF_EDGE_KE; ++e) acc[e] = fmaf(zsm[rr][ks + 4 * e], f, acc[e]);
+        for (int e = 0; e < KE; ++e) acc[e] = fmaf(zsm[rr][ks + 4 * e], f, acc[e]);
       }
     }
   }
   if (q < a.Q) {
 #pragma unroll
-    for (int e = 0; e < NIF_EDGE_KE; ++e) {
+    for (int e = 0; e < KE; ++e) {
       const int kk = k0 + ks + 4 * e;
       if (kk < K1) a.part[((long long)s * K1 + kk) * a.Q + q] = acc[e];
     }
@@ -574,11 +575,6 @@ int nif_tc_bwd_data_impl(const Plan& pl, long long B, const float* z, const floa
 int nif_tc_bwd_weight_impl(const Plan& pl, long long B, const float* z, const float* save, const float* da,
                            const unsigned* maxes, int S, long long rows_per_split, float* part, cudaStream_t st);
 
-struct GradWs {
-  long long da, du, part_h, part_e, loss_part, maxes, total;
-  int S_h, S_e, Q;
-  long long rows_h, rows_e;
-};
 
 static long long round_up(long long v, long long m) { return (v + m - 1) / m * m; }
 
@@ -598,7 +594,8 @@ GradWs nif_grad_ws_layout(const Plan& pl, long long B) {
   if (w.rows_h < 32) w.rows_h = 32;
   w.S_h = (int)((B + w.rows_h - 1) / w.rows_h);
   if (w.S_h < 1) w.S_h = 1;
-  const long long base_e = (w.Q + 63) / 64 * ((K1 + 67) / 68);
+  const long long ke = K1 <= 4 ? 1 : (K1 <= 36 ? 9 : 17);
+  const long long base_e = (w.Q + 63) / 64 * ((K1 + 4 * ke - 1) / (4 * ke));
   long long S_e = (4 * 148 + base_e - 1) / base_e;
   if (S_e > maxs) S_e = maxs;
   if (S_e < 1) S_e = 1;
@@ -615,6 +612,43 @@ GradWs nif_grad_ws_layout(const Plan& pl, long long B) {
   w.maxes = off; off += 256;  // device-side maxima used for tensor-core operand scales
   w.total = off;
   return w;
+}
+
+static cudaError_t launch_edge(const Plan& pl, const EdgeArgs& e, const GradWs& w, cudaStream_t st) {
+  const int K1 = pl.K + 1;
+  const int KE = K1 <= 4 ? 1 : (K1 <= 36 ? 9 : 17);
+  dim3 grid((unsigned)((w.Q + 63) / 64), (unsigned)w.S_e, (unsigned)((K1 + 4 * KE - 1) / (4 * KE)));
+  if (KE == 1) nif_bwd_edge_kernel<1><<<grid, 256, 0, st>>>(pl, e);
+  else if (KE == 9) nif_bwd_edge_kernel<9><<<grid, 256, 0, st>>>(pl, e);
+  else nif_bwd_edge_kernel<17><<<grid, 256, 0, st>>>(pl, e);
+  return cudaGetLastError();
+}
+
+// hidden-matrix GEMM (CUDA cores) + thin terms + un-packing, for stashes whose da_m already sit in ws.
+// Used by the trunk, whose parameter gradients are the same batch reductions with zt = [1].
+int nif_weight_grads_impl(const Plan& pl, long long B, const float* z, const float* x, const float* save, const float* du,
+                          float* dw_h, float* db_h, float beta, float* ws, cudaStream_t st) {
+  const GradWs w = nif_grad_ws_layout(pl, B);
+  if (pl.H > 0) {
+    WgtArgs g;
+    g.B = B; g.rows_per_split = w.rows_h; g.S = w.S_h;
+    g.z = z; g.save = save; g.da = ws + w.da; g.part = ws + w.part_h;
+    const int K1 = pl.K + 1;
+    if (pl.NP >= 64) {
+      const int nb = pl.NP / 64;
+      dim3 grid((unsigned)(pl.H * ((K1 + 3) / 4) * nb * nb), (unsigned)w.S_h);
+      nif_bwd_weight_kernel<64><<<grid, 256, 0, st>>>(pl, g);
+    } else {
+      dim3 grid((unsigned)(pl.H * ((K1 + 3) / 4)), (unsigned)w.S_h);
+      nif_bwd_weight_kernel<32><<<grid, 64, 0, st>>>(pl, g);
+    }
+    NIF_CUDA_CHECK(cudaGetLastError());
+  }
+  EdgeArgs e;
+  e.B = B; e.rows_per_split = w.rows_e; e.S = w.S_e; e.Q = w.Q;
+  e.z = z; e.x = x; e.save = save; e.da = ws + w.da; e.du = du; e.part = ws + w.part_e;
+  NIF_CUDA_CHECK(launch_edge(pl, e, w, st));
+  return nif_unpack_grad_impl(pl, w.S_h, ws + w.part_h, w.S_e, ws + w.part_e, w.Q, dw_h, db_h, beta, st);
 }
 
 int nif_backward_impl(const Plan& pl, long long B, const float* z, const float* x, const float* packed,
@@ -674,9 +708,7 @@ int nif_backward_impl(const Plan& pl, long long B, const float* z, const float* 
     EdgeArgs e;
     e.B = B; e.rows_per_split = w.rows_e; e.S = w.S_e; e.Q = w.Q;
     e.z = z; e.x = x; e.save = save; e.da = ws + w.da; e.du = du; e.part = ws + w.part_e;
-    dim3 grid((unsigned)((w.Q + 63) / 64), (unsigned)w.S_e, (unsigned)((pl.K + 1 + 67) / 68));
-    nif_bwd_edge_kernel<<<grid, 256, 0, st>>>(pl, e);
-    NIF_CUDA_CHECK(cudaGetLastError());
+    NIF_CUDA_CHECK(launch_edge(pl, e, w, st));
   }
   return nif_unpack_grad_impl(pl, S_used, ws + w.part_h, w.S_e, ws + w.part_e, w.Q, dw_h, db_h, beta, st);
 }

@@ -142,6 +142,13 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
+// reverse-pass workspace layout (offsets in floats), shared by nif_bwd.cu / nif_api.cu / nif_trunk.cu
+struct GradWs {
+  long long da, du, part_h, part_e, loss_part, maxes, total;
+  int S_h, S_e, Q;
+  long long rows_h, rows_e;
+};
+
 // host-side error plumbing ------------------------------------------------------------------------
 void nif_set_error(const char* fmt, ...);
 int nif_make_plan(const nif_desc_t* d, Plan* out);

@@ -224,18 +224,24 @@ class Model:
         return self._packed
 
     # ---- forward ------------------------------------------------------------------------------------
+    def _latent_nograd(self, p_in: torch.Tensor) -> torch.Tensor:
+        n = self.net
+        if n._trunk is not None:
+            return n._trunk.forward(p_in.contiguous(), n.theta_trunk)
+        return n._latent(p_in)
+
     @torch.no_grad()
     def _forward_batch(self, x):
         n = self.net
         if self.kind == "full":
             inp = self._dev(x)
-            z = n._latent(inp[:, : n.pi_dim])
+            z = self._latent_nograd(inp[:, : n.pi_dim])
             xs = inp[:, n.pi_dim: n.pi_dim + n.si_dim].contiguous()
             return n.engine.forward(z.contiguous(), xs, self._packed_weights())
         if self.kind == "p_to_lr":
-            return n._latent(self._dev(x))
+            return self._latent_nograd(self._dev(x))
         if self.kind == "p_to_w":
-            z = n._latent(self._dev(x))
+            z = self._latent_nograd(self._dev(x))
             return torch.addmm(n.b_h.detach(), z, n.w_h.detach())
         if self.kind == "lr_to_w":
             return torch.addmm(n.b_h.detach(), self._dev(x), n.w_h.detach())
@@ -303,12 +309,27 @@ class Model:
         eng = n.engine
         B = inp.shape[0]
         gb = int(global_batch) if global_batch else B
-        n.grad.zero_()
         if self._loss_buf is None:
             self._loss_buf = torch.zeros(1, dtype=torch.float32, device=n.device)
         self._loss_buf.zero_()
-        z = n._latent(inp[:, : n.pi_dim])
         xs = inp[:, n.pi_dim: n.pi_dim + n.si_dim].contiguous()
+        if not callable(self.loss) and n._trunk is not None:
+            # fully fused step: trunk, hyper-network head + ShapeNet, loss and both reverse passes are library kernels;
+            # every gradient is written (beta = 0) straight into the flat gradient buffer.
+            p_in = inp[:, : n.pi_dim].contiguous()
+            z, tstash = n._trunk.forward(p_in, n.theta_trunk, save=True)
+            packed = self._packed_weights()
+            u, stash = eng.forward(z, xs, packed, save=True)
+            dz = eng.mse_backward(z, xs, packed, u, stash, tgt, sw, 1.0 / gb, self._loss_buf,
+                                  n._gviews[n._last_names[0]], n._gviews[n._last_names[1]], 0.0)
+            n._trunk.backward(p_in, n.theta_trunk, tstash, dz, n.grad_trunk, 0.0)
+            if self.dist is not None:
+                self.dist.allreduce_(n.grad)
+            l1, l2 = n._kernel_regulariser()
+            self.optimizer.apply(n.theta, n.grad, l1, l2)
+            return self._loss_buf
+        n.grad.zero_()
+        z = n._latent(inp[:, : n.pi_dim])
         if not callable(self.loss):
             packed = self._packed_weights()
             zc = z.detach().contiguous()

@@ -133,22 +133,39 @@ class NIF(object):
         # every Dense of class NIF: TruncatedNormal(stddev=0.1) kernel and bias (nif/model.py:181-182, 222-223)
         return _trunc_normal(shape, 0.1, self._gen)
 
-    def _init_parameters(self):
-        layout = self._trunk_layout() + [(self._last_names[0], (self.pi_hidden, self.po_dim)),
-                                         (self._last_names[1], (self.po_dim,))]
-        self._layout: Dict[str, Tuple[int, Tuple[int, ...]]] = {}
-        off = 0
-        for name, shape in layout:
-            n = int(np.prod(shape))
-            self._layout[name] = (off, shape)
-            off += (n + 3) // 4 * 4  # keep every variable 16-byte aligned inside the flat buffer
-        self.n_flat = off
-        host = torch.zeros(off, dtype=torch.float32)
-        for name, shape in layout:
-            o, _ = self._layout[name]
-            host[o:o + int(np.prod(shape))] = self._draw(name, shape).reshape(-1)
-        self.theta = host.to(self.device)
-        self.grad = torch.zeros_like(self.theta)
+    def _fused_trunk_supported(self) -> bool:
+        """Dense(act) -> l_st x MLP_SimpleShortCut -> Dense(latent) with a non-sine activation and <= 64 units is
+        what libnif_b200's trunk kernels implement; other trunks run as torch ops."""
+        p = self.cfg_parameter_net
+        return (p.get("activation") in ("swish", "tanh", "relu", "sigmoid", "linear", None) and self.n_st <= 64
+                and not bool(p.get("use_resblock", False)) and self.pi_dim <= 8)
+
+    def _place(self, layout):
+        """Offsets of every variable in the flat buffer.  With the fused trunk, the trunk variables are laid out
+        kernels-first, unpadded, in the column order the trunk kernels read (include/nif_b200.h), so that the trunk
+        weight vector and its gradient are plain views of the flat buffers."""
+        names = [n for n, _ in layout]
+        shapes = dict(layout)
+        place, off = {}, 0
+        trunk = names[:-2]
+        if self._fused_trunk_supported():
+            order = [n for n in trunk if n.endswith("/kernel")] + [n for n in trunk if n.endswith("/bias")]
+            for n in order:
+                place[n] = off
+                off += int(np.prod(shapes[n]))
+            self._n_trunk = off
+            off = (off + 3) // 4 * 4
+        else:
+            self._n_trunk = 0
+            for n in trunk:
+                place[n] = off
+                off += (int(np.prod(shapes[n])) + 3) // 4 * 4
+        for n in names[-2:]:  # the last linear layer: 16-byte aligned for the kernels
+            place[n] = off
+            off += (int(np.prod(shapes[n])) + 3) // 4 * 4
+        return place, off
+
+    def _bind_views(self):
         self._views: Dict[str, torch.Tensor] = {}
         self._gviews: Dict[str, torch.Tensor] = {}
         for name, (o, shape) in self._layout.items():
@@ -158,6 +175,35 @@ class NIF(object):
             g = self.grad[o:o + n].view(shape)
             v.grad = g
             self._views[name], self._gviews[name] = v, g
+        self._trunk = None
+        if self._n_trunk and self.device.type == "cuda":
+            from .ops import FusedTrunk
+            self._trunk = FusedTrunk(self.pi_dim, self.pi_hidden, self.n_st, self.l_st,
+                                     self.cfg_parameter_net.get("activation") or "linear")
+            if self._trunk.n_theta != self._n_trunk:
+                raise NifError("trunk layout mismatch between host and library")
+
+    @property
+    def theta_trunk(self) -> torch.Tensor:
+        return self.theta[: self._n_trunk]
+
+    @property
+    def grad_trunk(self) -> torch.Tensor:
+        return self.grad[: self._n_trunk]
+
+    def _init_parameters(self):
+        layout = self._trunk_layout() + [(self._last_names[0], (self.pi_hidden, self.po_dim)),
+                                         (self._last_names[1], (self.po_dim,))]
+        place, total = self._place(layout)
+        self._layout: Dict[str, Tuple[int, Tuple[int, ...]]] = {name: (place[name], shape) for name, shape in layout}
+        self.n_flat = total
+        host = torch.zeros(total, dtype=torch.float32)
+        for name, shape in layout:  # draws happen in creation order, independent of the placement
+            o, _ = self._layout[name]
+            host[o:o + int(np.prod(shape))] = self._draw(name, shape).reshape(-1)
+        self.theta = host.to(self.device)
+        self.grad = torch.zeros_like(self.theta)
+        self._bind_views()
 
     @property
     def variables(self) -> Dict[str, torch.Tensor]:
@@ -180,15 +226,9 @@ class NIF(object):
         self.device = device
         self.theta = torch.zeros(self.n_flat, dtype=torch.float32, device=device)
         self.grad = torch.zeros_like(self.theta)
-        self._views, self._gviews = {}, {}
         for name, (o, shape) in self._layout.items():
-            n = int(np.prod(shape))
-            self.theta[o:o + n] = data[name].reshape(-1).to(device)
-            v = self.theta[o:o + n].view(shape)
-            v.requires_grad_(True)
-            g = self.grad[o:o + n].view(shape)
-            v.grad = g
-            self._views[name], self._gviews[name] = v, g
+            self.theta[o:o + int(np.prod(shape))] = data[name].reshape(-1).to(device)
+        self._bind_views()
         self._engine = None
         return self
 

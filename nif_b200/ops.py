@@ -11,7 +11,7 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import ACT, VARIANT, Desc, NifError, Sizes, check
+from ._lib import ACT, VARIANT, Desc, NifError, Sizes, TrunkDesc, check
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -165,6 +165,42 @@ class FusedShapeNet:
                                           _ptr(db_h), float(beta), _ptr(dz), _ptr(ws), _stream()),
               "nif_mse_backward")
         return dz
+
+
+class FusedTrunk:
+    """ParameterNet trunk up to the bottleneck (nif/model.py:326-343) as fused kernels: Dense(act) ->
+    nlayers x MLP_SimpleShortCut -> Dense(latent).  `theta` is the flat trunk weight vector in the column
+    order documented in include/nif_b200.h."""
+
+    def __init__(self, pi: int, latent: int, units: int, nlayers: int, activation: str):
+        if activation not in ACT or activation == "sine":
+            raise NifError(f"trunk activation {activation!r} is outside the fused trunk kernels")
+        self.pi, self.latent, self.units, self.nlayers = pi, latent, units, nlayers
+        self.desc = TrunkDesc(pi, latent, units, nlayers, ACT[activation])
+        nt, sv = C.c_int64(0), C.c_int64(0)
+        check(_lib.lib().nif_trunk_query(C.byref(self.desc), 0, C.byref(nt), C.byref(sv), None), "nif_trunk_query")
+        self.n_theta, self.save_floats_per_row = int(nt.value), int(sv.value)
+        self._ws = None
+
+    def forward(self, p_in: torch.Tensor, theta: torch.Tensor, save: bool = False):
+        p_in = _f32c(p_in, "p_in")
+        B = p_in.shape[0]
+        z = torch.empty(B, self.latent, dtype=torch.float32, device=p_in.device)
+        stash = torch.empty(self.save_floats_per_row * B, dtype=torch.float32, device=p_in.device) if save else None
+        check(_lib.lib().nif_trunk_forward(C.byref(self.desc), B, _ptr(p_in), _ptr(theta), _ptr(z), _ptr(stash),
+                                           _stream()), "nif_trunk_forward")
+        return (z, stash) if save else z
+
+    def backward(self, p_in, theta, stash, dz, g_theta, beta: float = 0.0):
+        p_in = _f32c(p_in, "p_in")
+        B = p_in.shape[0]
+        wsn = C.c_int64(0)
+        check(_lib.lib().nif_trunk_query(C.byref(self.desc), B, None, None, C.byref(wsn)), "nif_trunk_query")
+        if self._ws is None or self._ws.numel() < wsn.value or self._ws.device != p_in.device:
+            self._ws = torch.empty(int(wsn.value), dtype=torch.float32, device=p_in.device)
+        check(_lib.lib().nif_trunk_backward(C.byref(self.desc), B, _ptr(p_in), _ptr(theta), _ptr(stash),
+                                            _ptr(_f32c(dz, "dz")), _ptr(g_theta), float(beta), _ptr(self._ws),
+                                            _stream()), "nif_trunk_backward")
 
 
 class _FusedFn(torch.autograd.Function):

@@ -342,3 +342,79 @@ def test_tc_forward_and_stash(variant, si, so, n, l, K, B):
     for name, got, r64, r32 in (("dz", dz, gz64, gz32), ("dw_h", dw, g64[wn], g32[wn]), ("db_h", db, g64[bn], g32[bn])):
         e = rel_err(got.cpu(), r64)
         assert _gate(e, rel_err(r32, r64)), f"{name} err {e:.3e} (cpu32 {rel_err(r32, r64):.3e})"
+
+
+# --------------------------------------------------------------------------------------------------
+# fused ParameterNet trunk and the whole optimisation step
+# --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("pi,K,n_st,l_st,act,B", [(1, 32, 64, 4, "swish", 700), (1, 1, 30, 2, "swish", 300),
+                                                  (2, 5, 17, 1, "tanh", 129), (3, 64, 64, 0, "relu", 50)])
+def test_fused_trunk_matches_oracle(pi, K, n_st, l_st, act, B):
+    from nif_b200.ops import FusedTrunk
+    dev = torch.device("cuda:0")
+    spec = O.Spec(variant="siren", pi=pi, si=1, so=1, n=8, l=1, K=K, n_st=n_st, l_st=l_st, p_act=act, omega0=30.0,
+                  weight_init_factor=0.1)
+    prm = {k: v.double() for k, v in O.init_params(spec, 7).items()}
+    rng = np.random.default_rng(3)
+    p_in = torch.as_tensor(rng.uniform(-1, 1, (B, pi)))
+    dz = torch.as_tensor(rng.normal(size=(B, K)))
+    names = [k for k in O.trunk_param_names(spec)[:-2]]
+    order = [k for k in names if k.endswith("/kernel")] + [k for k in names if k.endswith("/bias")]
+    leaves = {k: prm[k].clone().requires_grad_(True) for k in names}
+    z64 = O.latent(spec, {**prm, **leaves}, p_in)
+    (z64 * dz).sum().backward()
+    z32 = O.latent(spec, {k: v.float() for k, v in prm.items()}, p_in.float())
+    g64 = torch.cat([leaves[k].grad.reshape(-1) for k in order])
+    theta = torch.cat([prm[k].reshape(-1) for k in order]).float().to(dev)
+    tr = FusedTrunk(pi, K, n_st, l_st, act)
+    assert tr.n_theta == theta.numel()
+    z, stash = tr.forward(p_in.float().to(dev), theta, save=True)
+    assert torch.equal(z, tr.forward(p_in.float().to(dev), theta))
+    assert _gate(rel_err(z.cpu(), z64.detach()), rel_err(z32, z64.detach()))
+    g = torch.full_like(theta, float("nan"))
+    tr.backward(p_in.float().to(dev), theta, stash, dz.float().to(dev), g, 0.0)
+    assert rel_err(g.cpu(), g64) < 2e-5
+    tr.backward(p_in.float().to(dev), theta, stash, dz.float().to(dev), g, 1.0)
+    assert rel_err(g.cpu(), 2 * g64) < 2e-5
+
+
+@pytest.mark.parametrize("cls,cfg_s,cfg_p", [
+    ("NIFMultiScale",
+     {"use_resblock": False, "connectivity": "full", "input_dim": 2, "output_dim": 1, "units": 64, "nlayers": 4,
+      "weight_init_factor": 0.01, "omega_0": 30.0},
+     {"use_resblock": False, "input_dim": 1, "latent_dim": 32, "units": 64, "nlayers": 4, "activation": "swish"}),
+    ("NIF",
+     {"connectivity": "full", "input_dim": 1, "output_dim": 1, "units": 30, "nlayers": 2, "activation": "swish"},
+     {"input_dim": 1, "latent_dim": 1, "units": 30, "nlayers": 2, "activation": "swish"}),
+    ("NIFMultiScale",
+     {"use_resblock": True, "connectivity": "full", "input_dim": 2, "output_dim": 2, "units": 24, "nlayers": 1,
+      "weight_init_factor": 0.1, "omega_0": 10.0},
+     {"use_resblock": True, "input_dim": 1, "latent_dim": 3, "units": 10, "nlayers": 2, "activation": "swish"}),
+])
+def test_training_steps_match_oracle_trainer(cls, cfg_s, cfg_p):
+    """Model.fit-style steps (trunk + head + ShapeNet + 'mse' + reverse pass + Adam) against the materialised
+    fp64 restatement of the reference's dataflow with TF-semantics Adam."""
+    import nif_b200
+    spec = O.spec_from_cfg(cls, cfg_s, cfg_p)
+    prm = O.init_params(spec, 11)
+    net = getattr(nif_b200, cls)(cfg_s, cfg_p, seed=0, device="cuda:0")
+    net.set_weights({k: v.numpy() for k, v in prm.items()})
+    model = net.build()
+    model.compile(nif_b200.Adam(1e-3), loss="mse")
+    ref = O.MaterialisedTrainer(spec, {k: v.double() for k, v in prm.items()}, lr=1e-3)
+    rng = np.random.default_rng(5)
+    B = 400
+    for step in range(4):
+        X = rng.uniform(-1, 1, (B, spec.pi + spec.si)).astype(np.float32)
+        Y = rng.uniform(-1, 1, (B, spec.so)).astype(np.float32)
+        sw = rng.uniform(0.5, 1.5, (B,)).astype(np.float32) if step % 2 else None
+        l_gpu = model.train_on_batch(X, Y, sample_weight=sw)
+        l_ref = ref.step(torch.as_tensor(X).double(), torch.as_tensor(Y).double(),
+                         None if sw is None else torch.as_tensor(sw).double())
+        assert abs(l_gpu - l_ref) <= 1e-4 * max(1.0, abs(l_ref)), (step, l_gpu, l_ref)
+    got = net.get_weights()
+    # Adam's first steps move every weight by ~lr whatever the gradient scale, and a weight whose gradient is at the
+    # rounding level may step the other way: compare absolutely, and allow a vanishing fraction of such weights.
+    diffs = np.concatenate([np.abs(got[k] - v.detach().numpy()).ravel() for k, v in ref.prm.items()])
+    assert float(np.quantile(diffs, 0.999)) < 1e-4, float(np.quantile(diffs, 0.999))
+    assert float(diffs.max()) < 4 * 2e-3
