@@ -338,7 +338,7 @@ __global__ void __launch_bounds__((TS / 4) * (TS / 4)) nif_bwd_weight_kernel(con
   __shared__ __align__(16) float hs[RC][TS];
   __shared__ __align__(16) float ds[RC][TS];
   __shared__ __align__(16) float zq[RC][4];
-  const int NP = pl.NP, K = pl.K, K1 = pl.K + 1, H = pl.H;
+  const int NP = pl.NP, K = pl.K, K1 = pl.K + 1, H = pl.H + pl.wide_last;
   const int nb = NP / TS;
   const int KGN = (K1 + 3) / 4;
   int bx = blockIdx.x;
@@ -432,7 +432,7 @@ __global__ void __launch_bounds__((TS / 4) * (TS / 4)) nif_bwd_weight_kernel(con
           for (int f = 0; f < 4; ++f) acc[q][e][f] = fmaf(zv[q], o[e][f], acc[q][e][f]);
     }
   }
-  const float om = plan_omega(pl, h + 1);
+  const float om = plan_omega(pl, h + 1);  // 1 for the last matrix (h == pl.H, wide_last)
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     const int kk = kg * 4 + q;
@@ -510,12 +510,21 @@ __global__ void __launch_bounds__(256) nif_bwd_edge_kernel(const Plan pl, const 
     __syncthreads();
     if (Ap) {
       const int nr = (int)((r1 - rb) < RC ? (r1 - rb) : RC);
-      for (int rr = 0; rr < nr; ++rr) {
-        const long long b = rb + rr;
-        float f = scale * __ldg(&Ap[b * sA]);
-        if (Bp) f *= __ldg(&Bp[b * sB]);
+      // 8 rows per trip: all loads are issued before the first use (the kernel is otherwise latency bound)
+      for (int rr0 = 0; rr0 < nr; rr0 += 8) {
+        float fa[8], fb[8];
 #pragma unroll
-        for (int e = 0; e < KE; ++e) acc[e] = fmaf(zsm[rr][ks + 4 * e], f, acc[e]);
+        for (int u = 0; u < 8; ++u) {
+          const long long b = rb + (rr0 + u < nr ? rr0 + u : nr - 1);
+          fa[u] = __ldg(&Ap[b * sA]);
+          fb[u] = Bp ? __ldg(&Bp[b * sB]) : 1.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const float f = (rr0 + u < nr) ? scale * fa[u] * fb[u] : 0.f;
+#pragma unroll
+          for (int e = 0; e < KE; ++e) acc[e] = fmaf(zsm[rr0 + u < RC ? rr0 + u : RC - 1][ks + 4 * e], f, acc[e]);
+        }
       }
     }
   }
@@ -581,10 +590,11 @@ static long long round_up(long long v, long long m) { return (v + m - 1) / m * m
 GradWs nif_grad_ws_layout(const Plan& pl, long long B) {
   GradWs w;
   const long long NP = pl.NP, K1 = pl.K + 1, H = pl.H;
-  w.Q = (int)((H + 1) * NP + pl.so + pl.si * NP + NP * pl.so);
+  w.Q = (int)((H + 1) * NP + pl.so + pl.si * NP + (pl.wide_last ? 0 : NP * pl.so));
   // batch splits: enough CTAs to fill the chip, but at least 256 rows per split
   const long long TS = NP >= 64 ? 64 : 32;
-  const long long base_h = H * ((K1 + 3) / 4) * (NP / TS) * (NP / TS);
+  const long long Hm = H + pl.wide_last;  // matrices handled by the hidden-matrix GEMM
+  const long long base_h = Hm * ((K1 + 3) / 4) * (NP / TS) * (NP / TS);
   long long S_h = base_h > 0 ? (2 * 148 + base_h - 1) / base_h : 1;
   long long maxs = (B + 255) / 256;
   if (maxs < 1) maxs = 1;
@@ -604,9 +614,9 @@ GradWs nif_grad_ws_layout(const Plan& pl, long long B) {
   w.S_e = (int)((B + w.rows_e - 1) / w.rows_e);
   if (w.S_e < 1) w.S_e = 1;
   long long off = 0;
-  w.da = off; off += round_up((H + 1) * B * NP, 4);
+  w.da = off; off += round_up((H + 1 + pl.wide_last) * B * NP, 4);
   w.du = off; off += round_up(B * pl.so, 4);
-  w.part_h = off; off += round_up((long long)w.S_h * H * K1 * NP * NP, 4);
+  w.part_h = off; off += round_up((long long)w.S_h * Hm * K1 * NP * NP, 4);
   w.part_e = off; off += round_up((long long)w.S_e * K1 * w.Q, 4);
   w.loss_part = off; off += 1024;
   w.maxes = off; off += 256;  // device-side maxima used for tensor-core operand scales
@@ -629,17 +639,18 @@ static cudaError_t launch_edge(const Plan& pl, const EdgeArgs& e, const GradWs& 
 int nif_weight_grads_impl(const Plan& pl, long long B, const float* z, const float* x, const float* save, const float* du,
                           float* dw_h, float* db_h, float beta, float* ws, cudaStream_t st) {
   const GradWs w = nif_grad_ws_layout(pl, B);
-  if (pl.H > 0) {
+  const int Hm = pl.H + pl.wide_last;
+  if (Hm > 0) {
     WgtArgs g;
     g.B = B; g.rows_per_split = w.rows_h; g.S = w.S_h;
     g.z = z; g.save = save; g.da = ws + w.da; g.part = ws + w.part_h;
     const int K1 = pl.K + 1;
     if (pl.NP >= 64) {
       const int nb = pl.NP / 64;
-      dim3 grid((unsigned)(pl.H * ((K1 + 3) / 4) * nb * nb), (unsigned)w.S_h);
+      dim3 grid((unsigned)(Hm * ((K1 + 3) / 4) * nb * nb), (unsigned)w.S_h);
       nif_bwd_weight_kernel<64><<<grid, 256, 0, st>>>(pl, g);
     } else {
-      dim3 grid((unsigned)(pl.H * ((K1 + 3) / 4)), (unsigned)w.S_h);
+      dim3 grid((unsigned)(Hm * ((K1 + 3) / 4)), (unsigned)w.S_h);
       nif_bwd_weight_kernel<32><<<grid, 64, 0, st>>>(pl, g);
     }
     NIF_CUDA_CHECK(cudaGetLastError());

@@ -44,6 +44,10 @@ struct Plan {
   // KZ = K+1 rounded up to 16; LPC = outputs per XL tile (2 if 2*KZ <= 128 else 1); NLC = ceil(so / LPC).
   int KZ, LPC, NLC;
   long long off_TCX, off_TCS2;
+  // wide_last (trunk plans): the last matrix [n x so] is wide (so up to 256); its gradient runs through the
+  // hidden-matrix batch-reduction GEMM as matrix index H (rows h_{H+1}, columns = the seed du padded to NP)
+  // instead of the column-per-thread edge kernel.
+  int wide_last;
 };
 __host__ __device__ inline long long plan_x0_floats(const Plan& p) { return 64LL * p.KZ; }            // one X0 / XC chunk [hi|lo]
 __host__ __device__ inline long long plan_xl_floats(const Plan& p) { return (long long)p.LPC * p.KZ * 64; }       // one XL chunk [hi|lo]

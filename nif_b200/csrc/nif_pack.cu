@@ -53,6 +53,7 @@ int nif_make_plan(const nif_desc_t* d, Plan* out) {
   p.off_M0 = off;  off += up4(K1 * p.si * NP);
   p.off_ML = off;  off += up4(K1 * NP * p.so);
   p.off_C = off;   off += up4((long long)p.Lm * K1 * NP);
+  p.wide_last = 0;
   p.tc = d->dtype_compute == 2 ? 1 : 0;
   p.KP = (p.K + 2) / 2 * 2;
   p.NCH = p.KP / 2;
@@ -266,7 +267,7 @@ __global__ void __launch_bounds__(256) nif_unpack_grad_kernel(const Plan pl, int
     if (col >= w_hid0 && col < w_last0) {
       const int r = col - w_hid0;
       const int h = r / (n * n), ij = r % (n * n), i = ij / n, j = ij % n;
-      const long long stride = (long long)H * K1 * NP * NP;
+      const long long stride = (long long)(H + pl.wide_last) * K1 * NP * NP;
       const float* src = part_h + (((long long)h * K1 + kk) * NP + i) * NP + j;
       for (int s = 0; s < S_h; ++s) v += src[s * stride];
     } else {
@@ -276,6 +277,15 @@ __global__ void __launch_bounds__(256) nif_unpack_grad_kernel(const Plan pl, int
         q = (H + 1) * NP + pl.so + i * NP + j;
       } else if (col < b0) {  // last matrix
         const int r = col - w_last0;
+        if (pl.wide_last) {  // produced by the hidden-matrix GEMM as matrix index H: [i][c] inside an NP x NP tile
+          const int i = r / pl.so, c = r % pl.so;
+          const long long stride = (long long)(H + 1) * K1 * NP * NP;
+          const float* src = part_h + (((long long)H * K1 + kk) * NP + i) * NP + c;
+          for (int s = 0; s < S_h; ++s) v += src[s * stride];
+          float* dst = (kk < pl.K) ? &dw_h[(long long)kk * P + col] : &db_h[col];
+          *dst = (beta != 0.f) ? (*dst * beta + v) : v;
+          continue;
+        }
         q = (H + 1) * NP + pl.so + pl.si * NP + r;  // r = i * so + c
       } else {
         const int r = col - b0;

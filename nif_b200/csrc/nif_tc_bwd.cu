@@ -409,6 +409,8 @@ struct TcWgtArgs {
 #define TCW_A_BYTES 16384u   // [128 (kappa_l, i) x 64 (b)] fp16, MN-major
 #define TCW_B_BYTES 8192u    // [64 (j) x 64 (b)] fp16, MN-major
 #define TCW_SLOT_BYTES (4 * TCW_A_BYTES + 2 * TCW_B_BYTES)  // A[q][hi|lo], B[hi|lo]
+#define TCW_ROW_STRIDE 272u                      // staged fp32 row (256 B) padded by 16 B: conflict-free per-row reads
+#define TCW_STAGE_BYTES (64 * TCW_ROW_STRIDE)      // the h rows of one 64-row sub-tile
 
 // MN-major core-matrix layout of a [MN x 64] tile: 8 (k) x 16 B (8 consecutive mn) core matrices,
 // offset(mn, k) = (mn/8) * 1024 + (k/8) * 128 + (k%8) * 16 + (mn%8) * 2
@@ -439,7 +441,7 @@ __device__ __forceinline__ void tcw_split8(const float (&v)[8], float sc, uint4&
 
 __global__ void __launch_bounds__(TCW_THREADS, 1) nif_tc_bwd_weight_kernel(const Plan pl, const TcWgtArgs a) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  __shared__ uint64_t slot_full[2], slot_empty[2], done_bar;
+  __shared__ uint64_t slot_full[2], slot_empty[2], st_full[2], done_bar;
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int K = pl.K, K1 = pl.K + 1, H = pl.H;
@@ -454,6 +456,7 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) nif_tc_bwd_weight_kernel(const
   if (tid == 0) {
     mbar_init(&slot_full[0], 128); mbar_init(&slot_full[1], 128);
     mbar_init(&slot_empty[0], 1); mbar_init(&slot_empty[1], 1);
+    mbar_init(&st_full[0], 1); mbar_init(&st_full[1], 1);
     mbar_init(&done_bar, 1);
     mbar_fence_init();
   }
@@ -512,6 +515,17 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) nif_tc_bwd_weight_kernel(const
     const float* hsrc = a.save + (long long)h * a.B * 64;        // h_m, m = h + 1 -> stash slot h
     const float* dsrc = a.da + (long long)(h + 1) * a.B * 64;    // da_m
     const int kk0 = 4 * pg + 2 * q;
+    // fp32 row staging: every row of the sub-tile is fetched by one cp.async.bulk (issued by the thread that
+    // owns it) into a padded shared-memory row; the copies of sub-tile t+2 fly while sub-tile t is converted.
+    unsigned char* stg = smem + 2 * TCW_SLOT_BYTES + sl * TCW_STAGE_BYTES;
+    auto stage_rows = [&](long long t) {
+      const long long bs = r0 + t * 64;
+      long long nvalid = a.B - bs;
+      nvalid = nvalid < 0 ? 0 : (nvalid > 64 ? 64 : nvalid);
+      if (q == 0 && r == 0) mbar_expect_tx(&st_full[sl], (uint32_t)(nvalid * 256));
+      if (q == 0 && r < nvalid) bulk_g2s(stg + r * TCW_ROW_STRIDE, hsrc + (bs + r) * 64, 256, &st_full[sl]);
+    };
+    if (sl < nsub) stage_rows(sl);
     long long n_mine = 0;
     for (long long t = sl; t < nsub; t += 2, ++n_mine) {
       const long long b = r0 + t * 64 + r;
@@ -523,14 +537,23 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) nif_tc_bwd_weight_kernel(const
         zt[kl] = 0.f;
         if (live) zt[kl] = (kk < K) ? __ldg(&a.z[b * K + kk]) : (kk == K ? 1.f : 0.f);
       }
+      // this thread's half of da_m (32 values, plain loads issued before the waits) and this row's h_m (64 values
+      // from the staged rows)
+      float4 hq[16], dq[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) dq[c] = live ? ldg4(dsrc + b * 64 + 32 * q + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      mbar_wait(&st_full[sl], (uint32_t)(n_mine & 1));
+#pragma unroll
+      for (int c = 0; c < 16; ++c)
+        hq[c] = live ? *reinterpret_cast<const float4*>(stg + r * TCW_ROW_STRIDE + c * 16) : make_float4(0.f, 0.f, 0.f, 0.f);
+      named_bar_sync(1 + sl, 128);  // every thread of the slot has its row in registers
+      if (t + 2 < nsub) stage_rows(t + 2);
       // wait until the MMAs that read this slot two sub-tiles ago have completed
       mbar_wait(&slot_empty[sl], (uint32_t)((n_mine & 1) ^ 1));
 #pragma unroll
       for (int ig = 0; ig < 8; ++ig) {
-        float hv[8];
-        float4 p0 = make_float4(0.f, 0.f, 0.f, 0.f), p1 = p0;
-        if (live) { p0 = ldg4(hsrc + b * 64 + 8 * ig); p1 = ldg4(hsrc + b * 64 + 8 * ig + 4); }
-        hv[0] = p0.x; hv[1] = p0.y; hv[2] = p0.z; hv[3] = p0.w; hv[4] = p1.x; hv[5] = p1.y; hv[6] = p1.z; hv[7] = p1.w;
+        const float4 p0 = hq[2 * ig], p1 = hq[2 * ig + 1];
+        const float hv[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
 #pragma unroll
         for (int kl = 0; kl < 2; ++kl) {
           float pv[8];
@@ -546,10 +569,8 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) nif_tc_bwd_weight_kernel(const
 #pragma unroll
       for (int jg = 0; jg < 4; ++jg) {  // pair q writes columns j = 32 q .. 32 q + 31 of the B operand
         const int j0 = 32 * q + 8 * jg;
-        float dv[8];
-        float4 p0 = make_float4(0.f, 0.f, 0.f, 0.f), p1 = p0;
-        if (live) { p0 = ldg4(dsrc + b * 64 + j0); p1 = ldg4(dsrc + b * 64 + j0 + 4); }
-        dv[0] = p0.x; dv[1] = p0.y; dv[2] = p0.z; dv[3] = p0.w; dv[4] = p1.x; dv[5] = p1.y; dv[6] = p1.z; dv[7] = p1.w;
+        const float4 p0 = dq[2 * jg], p1 = dq[2 * jg + 1];
+        const float dv[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
         uint4 hi, lo;
         tcw_split8(dv, scB, hi, lo);
         const uint32_t off = (uint32_t)(j0 >> 3) * 1024u + koff;
@@ -599,7 +620,7 @@ int nif_tc_bwd_weight_impl(const Plan& pl, long long B, const float* z, const fl
   TcWgtArgs a;
   a.B = B; a.rows_per_split = rows_per_split; a.S = S;
   a.z = z; a.save = save; a.da = da; a.maxes = maxes; a.part = part;
-  const size_t smem = 2 * (size_t)TCW_SLOT_BYTES;
+  const size_t smem = 2 * (size_t)TCW_SLOT_BYTES + 2 * (size_t)TCW_STAGE_BYTES;
   NIF_CUDA_CHECK(cudaFuncSetAttribute(nif_tc_bwd_weight_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int NPG = (pl.KP + 3) / 4;
   dim3 grid((unsigned)(pl.H * NPG), (unsigned)S);
