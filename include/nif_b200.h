@@ -137,15 +137,17 @@ typedef struct nif_trunk_desc {
   int32_t pi, latent, units, nlayers, act;
 } nif_trunk_desc_t;
 
-/* n_theta: floats of theta; save_floats_per_row: stash per row for the reverse pass; ws_floats: scratch for batch B. */
+/* n_theta: floats of theta; save_floats_per_row: stash per row for the reverse pass; packed_floats: scratch for the
+ * re-laid weights (written by forward, read by backward of the same step); ws_floats: reverse scratch for batch B. */
 int nif_trunk_query(const nif_trunk_desc_t* d, int64_t B, int64_t* n_theta, int64_t* save_floats_per_row,
-                    int64_t* ws_floats);
+                    int64_t* packed_floats, int64_t* ws_floats);
 /* z [B,latent] = trunk(p_in [B,pi]); save may be NULL for inference. */
 int nif_trunk_forward(const nif_trunk_desc_t* d, int64_t B, const float* p_in, const float* theta, float* z,
-                      float* save, void* stream);
+                      float* save, float* packed, void* stream);
 /* g_theta (same layout as theta) = d loss / d theta given dz [B,latent]; written if beta == 0, accumulated if 1. */
 int nif_trunk_backward(const nif_trunk_desc_t* d, int64_t B, const float* p_in, const float* theta,
-                       const float* save, const float* dz, float* g_theta, float beta, float* ws, void* stream);
+                       const float* save, const float* dz, float* g_theta, float beta, const float* packed,
+                       float* ws, void* stream);
 
 /* Utility used by the benchmark: sustained FP32 FMA rate of this GPU (TFLOP/s),
  * measured with CUDA events; blocks until done. */

@@ -87,9 +87,9 @@ def lib() -> C.CDLL:
     L.nif_adam_step.argtypes = [I64, VP, VP, VP, VP, C.c_double, C.c_double, C.c_double, C.c_double, I64, F, F, F, VP]
     L.nif_measure_fp32_peak.argtypes = [C.POINTER(C.c_double)]
     TP, I64P = C.POINTER(TrunkDesc), C.POINTER(C.c_int64)
-    L.nif_trunk_query.argtypes = [TP, I64, I64P, I64P, I64P]
-    L.nif_trunk_forward.argtypes = [TP, I64, VP, VP, VP, VP, VP]
-    L.nif_trunk_backward.argtypes = [TP, I64, VP, VP, VP, VP, VP, F, VP, VP]
+    L.nif_trunk_query.argtypes = [TP, I64, I64P, I64P, I64P, I64P]
+    L.nif_trunk_forward.argtypes = [TP, I64, VP, VP, VP, VP, VP, VP]
+    L.nif_trunk_backward.argtypes = [TP, I64, VP, VP, VP, VP, VP, F, VP, VP, VP]
     for name in SYMBOLS:
         getattr(L, name)  # raises AttributeError if the build is stale
         if name not in ("nif_last_error",):

@@ -158,9 +158,10 @@ extern "C" int nif_adam_step(int64_t n, float* p, const float* g, float* m, floa
 // ---- ParameterNet trunk --------------------------------------------------------------------------------
 int nif_make_trunk_plan(int pi, int K, int n_st, int l_st, int act, Plan* out);
 int nif_trunk_forward_impl(const Plan& pl, long long B, const float* p_in, const float* theta, float* z, float* save,
-                           cudaStream_t st);
+                           float* packed, cudaStream_t st);
 int nif_trunk_backward_impl(const Plan& pl, long long B, const float* p_in, const float* theta, const float* save,
-                            const float* dz, float* g_theta, float beta, float* ws, cudaStream_t st);
+                            const float* dz, float* g_theta, float beta, const float* packed, float* ws,
+                            cudaStream_t st);
 
 static int trunk_plan(const nif_trunk_desc_t* d, Plan* pl) {
   if (!d) { nif_set_error("null trunk descriptor"); return NIF_E_BAD_DESC; }
@@ -168,37 +169,39 @@ static int trunk_plan(const nif_trunk_desc_t* d, Plan* pl) {
 }
 
 extern "C" int nif_trunk_query(const nif_trunk_desc_t* d, int64_t B, int64_t* n_theta, int64_t* save_floats_per_row,
-                               int64_t* ws_floats) {
+                               int64_t* packed_floats, int64_t* ws_floats) {
   Plan pl;
   int rc = trunk_plan(d, &pl);
   if (rc) return rc;
   if (B < 0) { nif_set_error("nif_trunk_query: B=%lld", (long long)B); return NIF_E_BAD_ARG; }
   if (n_theta) *n_theta = pl.P;
   if (save_floats_per_row) *save_floats_per_row = 2LL * (pl.H + 1) * pl.NP;
+  if (packed_floats) *packed_floats = pl.packed_floats;
   if (ws_floats) *ws_floats = nif_grad_ws_layout(pl, B).total;
   return NIF_OK;
 }
 
 extern "C" int nif_trunk_forward(const nif_trunk_desc_t* d, int64_t B, const float* p_in, const float* theta, float* z,
-                                 float* save, void* stream) {
+                                 float* save, float* packed, void* stream) {
   Plan pl;
   int rc = trunk_plan(d, &pl);
   if (rc) return rc;
   if (B < 0) { nif_set_error("nif_trunk_forward: B=%lld", (long long)B); return NIF_E_BAD_ARG; }
   if (B == 0) return NIF_OK;
-  NIF_REQUIRE_PTR(p_in); NIF_REQUIRE_PTR(theta); NIF_REQUIRE_PTR(z); NIF_OPTIONAL_PTR(save);
-  return nif_trunk_forward_impl(pl, B, p_in, theta, z, save, static_cast<cudaStream_t>(stream));
+  NIF_REQUIRE_PTR(p_in); NIF_REQUIRE_PTR(theta); NIF_REQUIRE_PTR(z); NIF_OPTIONAL_PTR(save); NIF_REQUIRE_PTR(packed);
+  return nif_trunk_forward_impl(pl, B, p_in, theta, z, save, packed, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int nif_trunk_backward(const nif_trunk_desc_t* d, int64_t B, const float* p_in, const float* theta,
-                                  const float* save, const float* dz, float* g_theta, float beta, float* ws,
-                                  void* stream) {
+                                  const float* save, const float* dz, float* g_theta, float beta, const float* packed,
+                                  float* ws, void* stream) {
   Plan pl;
   int rc = trunk_plan(d, &pl);
   if (rc) return rc;
   if (B < 0) { nif_set_error("nif_trunk_backward: B=%lld", (long long)B); return NIF_E_BAD_ARG; }
   if (B == 0) return NIF_OK;
   NIF_REQUIRE_PTR(p_in); NIF_REQUIRE_PTR(theta); NIF_REQUIRE_PTR(save); NIF_REQUIRE_PTR(dz);
-  NIF_REQUIRE_PTR(g_theta); NIF_REQUIRE_PTR(ws);
-  return nif_trunk_backward_impl(pl, B, p_in, theta, save, dz, g_theta, beta, ws, static_cast<cudaStream_t>(stream));
+  NIF_REQUIRE_PTR(g_theta); NIF_REQUIRE_PTR(packed); NIF_REQUIRE_PTR(ws);
+  return nif_trunk_backward_impl(pl, B, p_in, theta, save, dz, g_theta, beta, packed, ws,
+                                 static_cast<cudaStream_t>(stream));
 }

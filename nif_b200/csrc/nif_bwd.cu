@@ -60,11 +60,12 @@ __global__ void __launch_bounds__(C::NT, 1) nif_bwd_data_kernel(const Plan pl, c
   WeightStream<C> ws;
   ws.stage = stage;
   ws.bar = bar;
-  ws.chunks_per_tile = H * K1 * C::NH;
+  const int HT = H + pl.wide_last;  // matrices streamed through the GEMM path (wide_last: the last matrix too)
+  ws.chunks_per_tile = HT * K1 * C::NH;
   ws.total = my_tiles * ws.chunks_per_tile;
   ws.issued = 0;
   ws.consumed = 0;
-  ws.H = H;
+  ws.H = HT;
   ws.K1 = K1;
   ws.packed = a.packed;
   ws.packed_floats = pl.packed_floats;
@@ -120,7 +121,56 @@ __global__ void __launch_bounds__(C::NT, 1) nif_bwd_data_kernel(const Plan pl, c
     float carry[RES ? MP : 1][RES ? MJ : 1];
 
     // ---- last layer (matrix H+1): n -> so --------------------------------------------------------------
-    {
+    if (pl.wide_last) {
+      // wide output (trunk plans): dh_{H+1} = sum_kappa zt[kappa] (du @ ML[kappa]^T) through the tile GEMM, with the
+      // seed du (zero padded to NP columns) as the A operand and the transposed last matrix streamed as matrix H
+      for (int idx = tid; idx < TB * NP; idx += NT) {
+        const int p = idx / NP, c = idx - p * NP;
+        const long long b = row0 + p;
+        const float v = (b < a.B && c < so) ? __ldg(&a.du[b * so + c]) : 0.f;
+        dact[act_idx<C>(c, p)] = v;
+        if (b < a.B) a.da[(long long)(H + 1) * a.B * NP + b * NP + c] = v;  // operand of the last matrix's gradient
+      }
+      __syncthreads();
+      const float* hL = a.save + (long long)H * a.B * NP;
+#pragma unroll
+      for (int r = 0; r < MP; ++r)
+#pragma unroll
+        for (int c = 0; c < MJ; ++c) acc[r][c] = 0.f;
+      for (int kk = 0; kk < K1; ++kk) {
+        float tmp[MP][MJ];
+#pragma unroll
+        for (int r = 0; r < MP; ++r)
+#pragma unroll
+          for (int c = 0; c < MJ; ++c) tmp[r][c] = 0.f;
+#pragma unroll 1
+        for (int hf = 0; hf < C::NH; ++hf) {
+          const float* st = ws.acquire();
+          mk_gemm<C>(dact, st, hf * C::NIS, tmp, tp, tj);
+          if (!(kk == K1 - 1 && hf == C::NH - 1)) ws.release();
+        }
+        float s[MP];
+#pragma unroll
+        for (int r = 0; r < MP; ++r) {
+          const float zk = zs[kk * TB + row_of<C>(tp, r)];
+          float sr = 0.f;
+#pragma unroll
+          for (int gj = 0; gj < C::GJ; ++gj) {
+            float4 hv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (brow[r] < a.B) hv = ldg4(&hL[brow[r] * NP + gj * C::JSTR + tj * 4]);
+            const float hvv[4] = {hv.x, hv.y, hv.z, hv.w};
+#pragma unroll
+            for (int f = 0; f < 4; ++f) {
+              acc[r][gj * 4 + f] = fmaf(zk, tmp[r][gj * 4 + f], acc[r][gj * 4 + f]);
+              sr = fmaf(tmp[r][gj * 4 + f], hvv[f], sr);
+            }
+          }
+          s[r] = sr;
+        }
+        dz_commit(s, kk);  // (bias-row part of dz is irrelevant for the K = 0 trunk plans that use this path)
+        if (kk == K1 - 1) ws.release();
+      }
+    } else {
       const float* ML = a.packed + pl.off_ML;
       const float* CL = C_all + (long long)(H + 1) * K1 * NP;
       const float* hL = a.save + (long long)H * a.B * NP;  // h_{H+1}
@@ -700,21 +750,8 @@ int nif_backward_impl(const Plan& pl, long long B, const float* z, const float* 
     if (rcw == NIF_OK) { wgt_done = true; S_used = S; }
     else if (rcw != NIF_E_UNSUPPORTED) return rcw;
   }
-  if (pl.H > 0 && !wgt_done) {
-    WgtArgs g;
-    g.B = B; g.rows_per_split = w.rows_h; g.S = w.S_h;
-    g.z = z; g.save = save; g.da = ws + w.da; g.part = ws + w.part_h;
-    const int K1 = pl.K + 1;
-    if (pl.NP >= 64) {
-      const int nb = pl.NP / 64;
-      dim3 grid((unsigned)(pl.H * ((K1 + 3) / 4) * nb * nb), (unsigned)w.S_h);
-      nif_bwd_weight_kernel<64><<<grid, 256, 0, st>>>(pl, g);
-    } else {
-      dim3 grid((unsigned)(pl.H * ((K1 + 3) / 4)), (unsigned)w.S_h);
-      nif_bwd_weight_kernel<32><<<grid, 64, 0, st>>>(pl, g);
-    }
-    NIF_CUDA_CHECK(cudaGetLastError());
-  }
+  if (!wgt_done)  // CUDA-core hidden-matrix GEMM + thin terms + un-packing
+    return nif_weight_grads_impl(pl, B, z, x, save, du, dw_h, db_h, beta, ws, st);
   {
     EdgeArgs e;
     e.B = B; e.rows_per_split = w.rows_e; e.S = w.S_e; e.Q = w.Q;

@@ -59,11 +59,12 @@ __global__ void __launch_bounds__(C::NT, (RES || C::NP == 32) ? 1 : 2) nif_fwd_k
   WeightStream<C> ws;
   ws.stage = stage;
   ws.bar = bar;
-  ws.chunks_per_tile = H * K1 * C::NH;
+  const int HT = H + pl.wide_last;  // matrices streamed through the GEMM path (wide_last: the last matrix too)
+  ws.chunks_per_tile = HT * K1 * C::NH;
   ws.total = my_tiles * ws.chunks_per_tile;
   ws.issued = 0;
   ws.consumed = 0;
-  ws.H = H;
+  ws.H = HT;
   ws.K1 = K1;
   ws.packed = a.packed;
   ws.packed_floats = pl.packed_floats;
@@ -101,6 +102,21 @@ __global__ void __launch_bounds__(C::NT, (RES || C::NP == 32) ? 1 : 2) nif_fwd_k
 
     // epilogue of layer m (0..H): activation, residual, stash for the reverse pass, write-back
     auto epilogue = [&](int m) {
+      if (m == H + 1) {  // wide last matrix (trunk plans): linear, straight to the output rows
+#pragma unroll
+        for (int r = 0; r < MP; ++r) {
+          const long long b = row0 + row_of<C>(tp, r);
+          if (b < a.B) {
+#pragma unroll
+            for (int c = 0; c < MJ; ++c) {
+              const int j = col_of<C>(tj, c);
+              if (j < so) a.u[(g * a.B + b) * so + j] = acc[r][c];
+            }
+          }
+        }
+        __syncthreads();
+        return;
+      }
       const float alpha = plan_alpha(pl, m);
       const int res = plan_res(pl, m);
       float outv[MP][MJ], dv[MP][MJ];
@@ -206,7 +222,7 @@ __global__ void __launch_bounds__(C::NT, (RES || C::NP == 32) ? 1 : 2) nif_fwd_k
     }
 
     // ---- hidden layers: n -> n ------------------------------------------------------------------------
-    for (int m = 1; m <= H; ++m) {
+    for (int m = 1; m <= HT; ++m) {
       const float om = plan_omega(pl, m);
 #pragma unroll
       for (int r = 0; r < MP; ++r)
@@ -245,7 +261,7 @@ __global__ void __launch_bounds__(C::NT, (RES || C::NP == 32) ? 1 : 2) nif_fwd_k
     }
 
     // ---- last layer: n -> so (thin).  Two threads per row split the kappa range -------------------------
-    {
+    if (!pl.wide_last) {
       const float* ML = pk + pl.off_ML;
       const float* CL = C_all + (long long)(H + 1) * K1 * NP;
       const int nsl = NT / TB;  // kappa slices

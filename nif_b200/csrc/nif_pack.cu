@@ -20,6 +20,34 @@ extern "C" int nif_version(void) { return 100; }
 
 static long long up4(long long v) { return (v + 3) / 4 * 4; }
 
+// offsets of the packed-image sections for a plan whose shape fields (variant .. NP, P, wide_last, tc) are set
+void nif_plan_layout(Plan* pp) {
+  Plan& p = *pp;
+  const long long K1 = p.K + 1, NP = p.NP;
+  const long long HT = p.H + p.wide_last;
+  long long off = 0;
+  p.off_MH = off;  off += up4(HT * K1 * NP * NP);
+  p.off_MHT = off; off += up4(HT * K1 * NP * NP);
+  p.off_M0 = off;  off += up4(K1 * p.si * NP);
+  p.off_ML = off;  off += up4(K1 * NP * p.so);
+  p.off_C = off;   off += up4((long long)p.Lm * K1 * NP);
+  p.KP = (p.K + 2) / 2 * 2;
+  p.NCH = p.KP / 2;
+  p.KZ = (p.K + 1 + 15) / 16 * 16;
+  p.LPC = (2 * p.KZ <= 128) ? 2 : 1;
+  p.NLC = (p.so + p.LPC - 1) / p.LPC;
+  p.off_TCF = p.off_TCB = p.off_TCS = p.off_TCX = p.off_TCS2 = 0;
+  if (p.tc) {
+    off = (off + 31) / 32 * 32;
+    p.off_TCF = off; off += (long long)p.H * p.NCH * NIF_TC_CHUNK_FLOATS;
+    p.off_TCB = off; off += (long long)p.H * p.NCH * NIF_TC_CHUNK_FLOATS;
+    p.off_TCS = off; off += up4((long long)p.H * p.KP);
+    p.off_TCX = off; off += (p.si + 1 + p.H) * plan_x0_floats(p) + p.NLC * plan_xl_floats(p);
+    p.off_TCS2 = off; off += up4(plan_n_small(p));
+  }
+  p.packed_floats = (off + 31) / 32 * 32;  // keep every image 128-byte aligned
+}
+
 int nif_make_plan(const nif_desc_t* d, Plan* out) {
   if (!d) { nif_set_error("null descriptor"); return NIF_E_BAD_DESC; }
   if (d->variant < 0 || d->variant > 2) { nif_set_error("variant %d not in {0,1,2}", d->variant); return NIF_E_BAD_DESC; }
@@ -46,30 +74,9 @@ int nif_make_plan(const nif_desc_t* d, Plan* out) {
   p.Lm = p.H + 2;
   p.NP = d->n <= 32 ? 32 : (d->n <= 64 ? 64 : 128);
   p.P = p.H * p.n * p.n + (p.si + p.so + 1 + p.H) * p.n + p.so;
-  const long long K1 = p.K + 1, NP = p.NP;
-  long long off = 0;
-  p.off_MH = off;  off += up4((long long)p.H * K1 * NP * NP);
-  p.off_MHT = off; off += up4((long long)p.H * K1 * NP * NP);
-  p.off_M0 = off;  off += up4(K1 * p.si * NP);
-  p.off_ML = off;  off += up4(K1 * NP * p.so);
-  p.off_C = off;   off += up4((long long)p.Lm * K1 * NP);
   p.wide_last = 0;
   p.tc = d->dtype_compute == 2 ? 1 : 0;
-  p.KP = (p.K + 2) / 2 * 2;
-  p.NCH = p.KP / 2;
-  p.KZ = (p.K + 1 + 15) / 16 * 16;
-  p.LPC = (2 * p.KZ <= 128) ? 2 : 1;
-  p.NLC = (p.so + p.LPC - 1) / p.LPC;
-  p.off_TCF = p.off_TCB = p.off_TCS = p.off_TCX = p.off_TCS2 = 0;
-  if (p.tc) {
-    off = (off + 31) / 32 * 32;
-    p.off_TCF = off; off += (long long)p.H * p.NCH * NIF_TC_CHUNK_FLOATS;
-    p.off_TCB = off; off += (long long)p.H * p.NCH * NIF_TC_CHUNK_FLOATS;
-    p.off_TCS = off; off += up4((long long)p.H * p.KP);
-    p.off_TCX = off; off += (p.si + 1 + p.H) * plan_x0_floats(p) + p.NLC * plan_xl_floats(p);
-    p.off_TCS2 = off; off += up4(plan_n_small(p));
-  }
-  p.packed_floats = (off + 31) / 32 * 32;  // keep every image 128-byte aligned
+  nif_plan_layout(&p);
   *out = p;
   return NIF_OK;
 }
@@ -104,20 +111,22 @@ __global__ void __launch_bounds__(256) nif_pack_kernel(const Plan pl, long long 
     const long long g = e / pl.packed_floats;
     long long r = e - g * pl.packed_floats;
     float v = 0.f;
-    if (r < pl.off_MHT) {  // MH [H][K1][NP][NP]
-      if (r < (long long)H * K1 * NP * NP) {
+    if (r < pl.off_MHT) {  // MH [H (+1 if wide_last)][K1][NP][NP]
+      if (r < (long long)(H + pl.wide_last) * K1 * NP * NP) {
         const int j = r % NP; r /= NP;
         const int i = r % NP; r /= NP;
         const int kk = r % K1; const int h = (int)(r / K1);
-        if (i < n && j < n) v = src_at(pl, w_h, b_h, g, kk, plan_w_off(pl, h + 1) + i * n + j);
+        if (h < H) { if (i < n && j < n) v = src_at(pl, w_h, b_h, g, kk, plan_w_off(pl, h + 1) + i * n + j); }
+        else if (i < n && j < pl.so) v = src_at(pl, w_h, b_h, g, kk, plan_w_off(pl, H + 1) + i * pl.so + j);  // last matrix [n][so]
       }
-    } else if (r < pl.off_M0) {  // MHT [H][K1][NP(j)][NP(i)]
+    } else if (r < pl.off_M0) {  // MHT: the same, transposed per matrix
       r -= pl.off_MHT;
-      if (r < (long long)H * K1 * NP * NP) {
+      if (r < (long long)(H + pl.wide_last) * K1 * NP * NP) {
         const int i = r % NP; r /= NP;
         const int j = r % NP; r /= NP;
         const int kk = r % K1; const int h = (int)(r / K1);
-        if (i < n && j < n) v = src_at(pl, w_h, b_h, g, kk, plan_w_off(pl, h + 1) + i * n + j);
+        if (h < H) { if (i < n && j < n) v = src_at(pl, w_h, b_h, g, kk, plan_w_off(pl, h + 1) + i * n + j); }
+        else if (i < n && j < pl.so) v = src_at(pl, w_h, b_h, g, kk, plan_w_off(pl, H + 1) + i * pl.so + j);
       }
     } else if (r < pl.off_ML) {  // M0 [K1][si][NP]
       r -= pl.off_M0;

@@ -177,10 +177,17 @@ class FusedTrunk:
             raise NifError(f"trunk activation {activation!r} is outside the fused trunk kernels")
         self.pi, self.latent, self.units, self.nlayers = pi, latent, units, nlayers
         self.desc = TrunkDesc(pi, latent, units, nlayers, ACT[activation])
-        nt, sv = C.c_int64(0), C.c_int64(0)
-        check(_lib.lib().nif_trunk_query(C.byref(self.desc), 0, C.byref(nt), C.byref(sv), None), "nif_trunk_query")
-        self.n_theta, self.save_floats_per_row = int(nt.value), int(sv.value)
+        nt, sv, pk = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+        check(_lib.lib().nif_trunk_query(C.byref(self.desc), 0, C.byref(nt), C.byref(sv), C.byref(pk), None),
+              "nif_trunk_query")
+        self.n_theta, self.save_floats_per_row, self.packed_floats = int(nt.value), int(sv.value), int(pk.value)
         self._ws = None
+        self._packed = None
+
+    def _packed_buf(self, device) -> torch.Tensor:
+        if self._packed is None or self._packed.device != device:
+            self._packed = torch.empty(self.packed_floats, dtype=torch.float32, device=device)
+        return self._packed
 
     def forward(self, p_in: torch.Tensor, theta: torch.Tensor, save: bool = False):
         p_in = _f32c(p_in, "p_in")
@@ -188,19 +195,21 @@ class FusedTrunk:
         z = torch.empty(B, self.latent, dtype=torch.float32, device=p_in.device)
         stash = torch.empty(self.save_floats_per_row * B, dtype=torch.float32, device=p_in.device) if save else None
         check(_lib.lib().nif_trunk_forward(C.byref(self.desc), B, _ptr(p_in), _ptr(theta), _ptr(z), _ptr(stash),
-                                           _stream()), "nif_trunk_forward")
+                                           _ptr(self._packed_buf(p_in.device)), _stream()), "nif_trunk_forward")
         return (z, stash) if save else z
 
     def backward(self, p_in, theta, stash, dz, g_theta, beta: float = 0.0):
+        """Reverse pass of the forward(save=True) call that preceded it (it reuses that call's re-laid weights)."""
         p_in = _f32c(p_in, "p_in")
         B = p_in.shape[0]
         wsn = C.c_int64(0)
-        check(_lib.lib().nif_trunk_query(C.byref(self.desc), B, None, None, C.byref(wsn)), "nif_trunk_query")
+        check(_lib.lib().nif_trunk_query(C.byref(self.desc), B, None, None, None, C.byref(wsn)), "nif_trunk_query")
         if self._ws is None or self._ws.numel() < wsn.value or self._ws.device != p_in.device:
             self._ws = torch.empty(int(wsn.value), dtype=torch.float32, device=p_in.device)
         check(_lib.lib().nif_trunk_backward(C.byref(self.desc), B, _ptr(p_in), _ptr(theta), _ptr(stash),
-                                            _ptr(_f32c(dz, "dz")), _ptr(g_theta), float(beta), _ptr(self._ws),
-                                            _stream()), "nif_trunk_backward")
+                                            _ptr(_f32c(dz, "dz")), _ptr(g_theta), float(beta),
+                                            _ptr(self._packed_buf(p_in.device)), _ptr(self._ws), _stream()),
+              "nif_trunk_backward")
 
 
 class _FusedFn(torch.autograd.Function):
