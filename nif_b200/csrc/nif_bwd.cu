@@ -381,7 +381,8 @@ struct WgtArgs {
   float* part;  // [S][H][K+1][NP][NP]
 };
 
-template <int TS>
+// KQ latent coordinates per thread: 4, or 1 for plans whose latent vector is just [1] (K = 0: the trunk)
+template <int TS, int KQ>
 __global__ void __launch_bounds__((TS / 4) * (TS / 4)) nif_bwd_weight_kernel(const Plan pl, const WgtArgs a) {
   constexpr int TT = TS / 4, NTW = TT * TT, RC = 32;  // RC rows per chunk
   constexpr int LD4 = (RC * TS / 4) / NTW;            // float4 loads per thread per operand per chunk
@@ -390,7 +391,7 @@ __global__ void __launch_bounds__((TS / 4) * (TS / 4)) nif_bwd_weight_kernel(con
   __shared__ __align__(16) float zq[RC][4];
   const int NP = pl.NP, K = pl.K, K1 = pl.K + 1, H = pl.H + pl.wide_last;
   const int nb = NP / TS;
-  const int KGN = (K1 + 3) / 4;
+  const int KGN = (K1 + KQ - 1) / KQ;
   int bx = blockIdx.x;
   const int jb = bx % nb; bx /= nb;
   const int ib = bx % nb; bx /= nb;
@@ -404,9 +405,9 @@ __global__ void __launch_bounds__((TS / 4) * (TS / 4)) nif_bwd_weight_kernel(con
   long long r1 = r0 + a.rows_per_split;
   if (r1 > a.B) r1 = a.B;
 
-  float acc[4][4][4];
+  float acc[KQ][4][4];
 #pragma unroll
-  for (int q = 0; q < 4; ++q)
+  for (int q = 0; q < KQ; ++q)
 #pragma unroll
     for (int e = 0; e < 4; ++e)
 #pragma unroll
@@ -435,8 +436,8 @@ __global__ void __launch_bounds__((TS / 4) * (TS / 4)) nif_bwd_weight_kernel(con
       if (e < RC * 4) {
         const int rr = e / 4, q = e % 4;
         const long long b = rb + rr;
-        const int kk = kg * 4 + q;
-        if (b < r1) pz[u] = (kk < K) ? __ldg(&a.z[b * K + kk]) : (kk == K ? 1.f : 0.f);
+        const int kk = kg * KQ + q;
+        if (b < r1 && q < KQ) pz[u] = (kk < K) ? __ldg(&a.z[b * K + kk]) : (kk == K ? 1.f : 0.f);
       }
     }
   };
@@ -469,23 +470,31 @@ __global__ void __launch_bounds__((TS / 4) * (TS / 4)) nif_bwd_weight_kernel(con
       const float hv[4] = {h4.x, h4.y, h4.z, h4.w};
       const float dv[4] = {d4.x, d4.y, d4.z, d4.w};
       const float zv[4] = {z4.x, z4.y, z4.z, z4.w};
-      float o[4][4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e)
-#pragma unroll
-        for (int f = 0; f < 4; ++f) o[e][f] = hv[e] * dv[f];
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
+      if (KQ == 1) {
+        const float zd[4] = {zv[0] * dv[0], zv[0] * dv[1], zv[0] * dv[2], zv[0] * dv[3]};
 #pragma unroll
         for (int e = 0; e < 4; ++e)
 #pragma unroll
-          for (int f = 0; f < 4; ++f) acc[q][e][f] = fmaf(zv[q], o[e][f], acc[q][e][f]);
+          for (int f = 0; f < 4; ++f) acc[0][e][f] = fmaf(hv[e], zd[f], acc[0][e][f]);
+      } else {
+        float o[4][4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+#pragma unroll
+          for (int f = 0; f < 4; ++f) o[e][f] = hv[e] * dv[f];
+#pragma unroll
+        for (int q = 0; q < KQ; ++q)
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+#pragma unroll
+            for (int f = 0; f < 4; ++f) acc[q][e][f] = fmaf(zv[q], o[e][f], acc[q][e][f]);
+      }
     }
   }
   const float om = plan_omega(pl, h + 1);  // 1 for the last matrix (h == pl.H, wide_last)
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const int kk = kg * 4 + q;
+  for (int q = 0; q < KQ; ++q) {
+    const int kk = kg * KQ + q;
     if (kk < K1) {
       float* dst = a.part + ((((long long)s * H + h) * K1 + kk) * NP + ib * TS + ti * 4) * NP + jb * TS + tj * 4;
 #pragma unroll
@@ -507,82 +516,147 @@ struct EdgeArgs {
   float* part;  // [S][K+1][Q]
 };
 
-// KE latent coordinates per thread (4 * KE per pass over the batch): 1 for K+1 <= 4, 9 for K+1 <= 36, else 17
-
-template <int KE>
-__global__ void __launch_bounds__(256) nif_bwd_edge_kernel(const Plan pl, const EdgeArgs a) {
-  constexpr int RC = 64, KC = 4 * KE;
-  __shared__ float zsm[RC][KC + 1];
+// Register-tiled batch reduction: a thread owns 4 columns x 4 latent coordinates; a CTA owns 64 columns x KG groups
+// of 4 latent coordinates x RS row slices (16 * KG * RS threads).  Per chunk of 32 rows the features F[32][64]
+// (generated on the fly from the stashed rows, coalesced along the columns) and the latent coordinates
+// zt[32][4 KG] are staged in shared memory; the next chunk's global loads fly while the current one is consumed.
+// Row slices (KG < 16) share the columns and split the rows of a chunk; they are summed through shared memory at
+// the end, so the kernel always writes one partial per (batch split, kappa, column).
+template <int KG, int RS>
+__global__ void __launch_bounds__(16 * KG * RS) nif_bwd_edge_kernel(const Plan pl, const EdgeArgs a) {
+  constexpr int NTH = 16 * KG * RS, RC = 32, KC = 4 * KG;
+  constexpr int FL = NTH / 64;                        // fetch lanes: thread (lane fl, column c) fetches rows fl, fl+FL, ..
+  constexpr int EPT = (RC + FL - 1) / FL;             // feature elements per fetch thread per chunk
+  constexpr int ZPT = (RC * KC + NTH - 1) / NTH;      // latent coordinates per thread per chunk
+  static_assert(NTH >= 64, "block too small");
+  __shared__ __align__(16) float Fs[RC][64];
+  __shared__ __align__(16) float Zs[RC][KC];
+  __shared__ __align__(16) float red[RS > 1 ? (RS - 1) * KG * 16 * 16 : 1];
   const int NP = pl.NP, K = pl.K, K1 = pl.K + 1, H = pl.H, si = pl.si, so = pl.so;
-  const int tid = threadIdx.x, ql = tid % 64, ks = tid / 64;
-  const int q = blockIdx.x * 64 + ql;
+  const int tid = threadIdx.x;
+  const int qg = tid % 16, kg = (tid / 16) % KG, rs = tid / (16 * KG);
   const int s = blockIdx.y;
   const int k0 = blockIdx.z * KC;  // first latent coordinate of this pass
   const long long r0 = (long long)s * a.rows_per_split;
   long long r1 = r0 + a.rows_per_split;
   if (r1 > a.B) r1 = a.B;
 
-  // decode the feature this thread owns:  F[b] = scale * A[b*sA] * (Bp ? Bp[b*sB] : 1)
+  // the feature column this thread fetches:  F[b] = scale * A[b*sA] * (Bp ? Bp[b*sB] : 1)
+  const int fc = tid % 64, fl = tid / 64;
   const float* Ap = nullptr;
   const float* Bp = nullptr;
   long long sA = 0, sB = 0;
   float scale = 1.f;
-  if (q < a.Q) {
-    int r = q;
-    if (r < (H + 1) * NP) {
-      const int m = r / NP, j = r % NP;
-      Ap = a.da + (long long)m * a.B * NP + j; sA = NP;
-    } else if ((r -= (H + 1) * NP) < so) {
-      Ap = a.du + r; sA = so;
-    } else if ((r -= so) < si * NP) {
-      const int i = r / NP, j = r % NP;
-      Ap = a.da + j; sA = NP; Bp = a.x + i; sB = si; scale = plan_omega(pl, 0);
-    } else {
-      r -= si * NP;
-      const int i = r / so, c = r % so;
-      Ap = a.save + (long long)H * a.B * NP + i; sA = NP; Bp = a.du + c; sB = so;
-    }
-  }
-  float acc[KE];
-#pragma unroll
-  for (int e = 0; e < KE; ++e) acc[e] = 0.f;
-
-  for (long long rb = r0; rb < r1; rb += RC) {
-    __syncthreads();
-    for (int idx = tid; idx < RC * KC; idx += 256) {
-      const int rr = idx / KC, kc = idx % KC;
-      const long long b = rb + rr;
-      const int kk = k0 + kc;
-      float v = 0.f;
-      if (b < r1) v = (kk < K) ? __ldg(&a.z[b * K + kk]) : (kk == K ? 1.f : 0.f);
-      zsm[rr][kc] = v;
-    }
-    __syncthreads();
-    if (Ap) {
-      const int nr = (int)((r1 - rb) < RC ? (r1 - rb) : RC);
-      // 8 rows per trip: all loads are issued before the first use (the kernel is otherwise latency bound)
-      for (int rr0 = 0; rr0 < nr; rr0 += 8) {
-        float fa[8], fb[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const long long b = rb + (rr0 + u < nr ? rr0 + u : nr - 1);
-          fa[u] = __ldg(&Ap[b * sA]);
-          fb[u] = Bp ? __ldg(&Bp[b * sB]) : 1.f;
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const float f = (rr0 + u < nr) ? scale * fa[u] * fb[u] : 0.f;
-#pragma unroll
-          for (int e = 0; e < KE; ++e) acc[e] = fmaf(zsm[rr0 + u < RC ? rr0 + u : RC - 1][ks + 4 * e], f, acc[e]);
-        }
+  {
+    int r = blockIdx.x * 64 + fc;
+    if (fl < FL && r < a.Q) {
+      if (r < (H + 1) * NP) {
+        const int m = r / NP, j = r % NP;
+        Ap = a.da + (long long)m * a.B * NP + j; sA = NP;
+      } else if ((r -= (H + 1) * NP) < so) {
+        Ap = a.du + r; sA = so;
+      } else if ((r -= so) < si * NP) {
+        const int i = r / NP, j = r % NP;
+        Ap = a.da + j; sA = NP; Bp = a.x + i; sB = si; scale = plan_omega(pl, 0);
+      } else {
+        r -= si * NP;
+        const int i = r / so, c = r % so;
+        Ap = a.save + (long long)H * a.B * NP + i; sA = NP; Bp = a.du + c; sB = so;
       }
     }
   }
-  if (q < a.Q) {
+  float acc[4][4];
 #pragma unroll
-    for (int e = 0; e < KE; ++e) {
-      const int kk = k0 + ks + 4 * e;
-      if (kk < K1) a.part[((long long)s * K1 + kk) * a.Q + q] = acc[e];
+  for (int e = 0; e < 4; ++e)
+#pragma unroll
+    for (int f = 0; f < 4; ++f) acc[e][f] = 0.f;
+
+  // Loads are branch-free (clamped row, dummy-but-valid pointers) and their results are first touched when the
+  // chunk is staged, so all of a chunk's loads are in flight while the previous chunk is consumed.
+  const bool has_col = Ap != nullptr;
+  const bool has_b = Bp != nullptr;
+  if (!has_col) { Ap = a.da; sA = 0; }
+  if (!has_b) { Bp = Ap; sB = 0; }
+  const float* zsrc = K > 0 ? a.z : a.da;  // K == 0 (trunk plans): zt = [1], nothing is read from z
+  float pa[EPT], pb[EPT], pz[ZPT];
+  auto fetch = [&](long long rb) {
+#pragma unroll
+    for (int u = 0; u < EPT; ++u) {
+      long long b = rb + fl + u * FL;
+      if (b >= r1) b = r0;
+      pa[u] = __ldg(&Ap[b * sA]);
+      pb[u] = __ldg(&Bp[b * sB]);
+    }
+#pragma unroll
+    for (int u = 0; u < ZPT; ++u) {
+      const int e = tid + u * NTH;
+      const int kk = k0 + e % KC;
+      long long b = rb + e / KC;
+      if (b >= r1) b = r0;
+      pz[u] = __ldg(&zsrc[K > 0 ? b * K + (kk < K ? kk : 0) : 0]);
+    }
+  };
+  if (r0 < r1) fetch(r0);
+  for (long long rb = r0; rb < r1; rb += RC) {
+    __syncthreads();  // previous chunk fully consumed
+    if (fl < FL) {
+#pragma unroll
+      for (int u = 0; u < EPT; ++u) {
+        const int rr = fl + u * FL;
+        float v = scale * pa[u];
+        if (has_b) v *= pb[u];
+        if (rr < RC) Fs[rr][fc] = (has_col && rb + rr < r1) ? v : 0.f;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < ZPT; ++u) {
+      const int e = tid + u * NTH;
+      const int kk = k0 + e % KC;
+      float v = (kk < K) ? pz[u] : (kk == K ? 1.f : 0.f);
+      if (rb + e / KC >= r1) v = 0.f;
+      if (e < RC * KC) Zs[e / KC][e % KC] = v;
+    }
+    __syncthreads();
+    if (rb + RC < r1) fetch(rb + RC);
+#pragma unroll 8
+    for (int rr = rs; rr < RC; rr += RS) {
+      const float4 f4 = *reinterpret_cast<const float4*>(&Fs[rr][4 * qg]);
+      const float4 z4 = *reinterpret_cast<const float4*>(&Zs[rr][4 * kg]);
+      const float fv[4] = {f4.x, f4.y, f4.z, f4.w};
+      const float zv[4] = {z4.x, z4.y, z4.z, z4.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+#pragma unroll
+        for (int f = 0; f < 4; ++f) acc[e][f] = fmaf(zv[e], fv[f], acc[e][f]);
+    }
+  }
+  if (RS > 1) {  // sum the row slices
+    __syncthreads();
+    if (rs > 0) {
+      float* dst = red + (((rs - 1) * KG + kg) * 16 + qg) * 16;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) *reinterpret_cast<float4*>(dst + 4 * e) = make_float4(acc[e][0], acc[e][1], acc[e][2], acc[e][3]);
+    }
+    __syncthreads();
+    if (rs > 0) return;
+    for (int o = 1; o < RS; ++o) {
+      const float* src = red + (((o - 1) * KG + kg) * 16 + qg) * 16;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float4 v = *reinterpret_cast<const float4*>(src + 4 * e);
+        acc[e][0] += v.x; acc[e][1] += v.y; acc[e][2] += v.z; acc[e][3] += v.w;
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int kk = k0 + 4 * kg + e;
+    if (kk < K1) {
+#pragma unroll
+      for (int f = 0; f < 4; ++f) {
+        const int q = blockIdx.x * 64 + 4 * qg + f;
+        if (q < a.Q) a.part[((long long)s * K1 + kk) * a.Q + q] = acc[e][f];
+      }
     }
   }
 }
@@ -637,6 +711,9 @@ int nif_tc_bwd_weight_impl(const Plan& pl, long long B, const float* z, const fl
 
 static long long round_up(long long v, long long m) { return (v + m - 1) / m * m; }
 
+// latent coordinates per pass of nif_bwd_edge_kernel (4 * KG of its instantiations)
+static int nif_edge_kc(int K1) { return K1 <= 4 ? 4 : K1 <= 8 ? 8 : K1 <= 16 ? 16 : K1 <= 32 ? 32 : K1 <= 36 ? 36 : 68; }
+
 GradWs nif_grad_ws_layout(const Plan& pl, long long B) {
   GradWs w;
   const long long NP = pl.NP, K1 = pl.K + 1, H = pl.H;
@@ -644,7 +721,8 @@ GradWs nif_grad_ws_layout(const Plan& pl, long long B) {
   // batch splits: enough CTAs to fill the chip, but at least 256 rows per split
   const long long TS = NP >= 64 ? 64 : 32;
   const long long Hm = H + pl.wide_last;  // matrices handled by the hidden-matrix GEMM
-  const long long base_h = Hm * ((K1 + 3) / 4) * (NP / TS) * (NP / TS);
+  const long long kq = K1 == 1 ? 1 : 4;  // latent coordinates per thread of nif_bwd_weight_kernel
+  const long long base_h = Hm * ((K1 + kq - 1) / kq) * (NP / TS) * (NP / TS);
   long long S_h = base_h > 0 ? (2 * 148 + base_h - 1) / base_h : 1;
   long long maxs = (B + 255) / 256;
   if (maxs < 1) maxs = 1;
@@ -654,8 +732,8 @@ GradWs nif_grad_ws_layout(const Plan& pl, long long B) {
   if (w.rows_h < 32) w.rows_h = 32;
   w.S_h = (int)((B + w.rows_h - 1) / w.rows_h);
   if (w.S_h < 1) w.S_h = 1;
-  const long long ke = K1 <= 4 ? 1 : (K1 <= 36 ? 9 : 17);
-  const long long base_e = (w.Q + 63) / 64 * ((K1 + 4 * ke - 1) / (4 * ke));
+  const long long kc = nif_edge_kc((int)K1);  // latent coordinates per pass of the thin-term kernel
+  const long long base_e = (w.Q + 63) / 64 * ((K1 + kc - 1) / kc);
   long long S_e = (4 * 148 + base_e - 1) / base_e;
   if (S_e > maxs) S_e = maxs;
   if (S_e < 1) S_e = 1;
@@ -676,11 +754,16 @@ GradWs nif_grad_ws_layout(const Plan& pl, long long B) {
 
 static cudaError_t launch_edge(const Plan& pl, const EdgeArgs& e, const GradWs& w, cudaStream_t st) {
   const int K1 = pl.K + 1;
-  const int KE = K1 <= 4 ? 1 : (K1 <= 36 ? 9 : 17);
-  dim3 grid((unsigned)((w.Q + 63) / 64), (unsigned)w.S_e, (unsigned)((K1 + 4 * KE - 1) / (4 * KE)));
-  if (KE == 1) nif_bwd_edge_kernel<1><<<grid, 256, 0, st>>>(pl, e);
-  else if (KE == 9) nif_bwd_edge_kernel<9><<<grid, 256, 0, st>>>(pl, e);
-  else nif_bwd_edge_kernel<17><<<grid, 256, 0, st>>>(pl, e);
+  const int KC = nif_edge_kc(K1);
+  dim3 grid((unsigned)((w.Q + 63) / 64), (unsigned)w.S_e, (unsigned)((K1 + KC - 1) / KC));
+  switch (KC) {
+    case 4: nif_bwd_edge_kernel<1, 16><<<grid, 256, 0, st>>>(pl, e); break;
+    case 8: nif_bwd_edge_kernel<2, 8><<<grid, 256, 0, st>>>(pl, e); break;
+    case 16: nif_bwd_edge_kernel<4, 4><<<grid, 256, 0, st>>>(pl, e); break;
+    case 32: nif_bwd_edge_kernel<8, 2><<<grid, 256, 0, st>>>(pl, e); break;
+    case 36: nif_bwd_edge_kernel<9, 1><<<grid, 144, 0, st>>>(pl, e); break;
+    default: nif_bwd_edge_kernel<17, 1><<<grid, 272, 0, st>>>(pl, e); break;
+  }
   return cudaGetLastError();
 }
 
@@ -695,13 +778,17 @@ int nif_weight_grads_impl(const Plan& pl, long long B, const float* z, const flo
     g.B = B; g.rows_per_split = w.rows_h; g.S = w.S_h;
     g.z = z; g.save = save; g.da = ws + w.da; g.part = ws + w.part_h;
     const int K1 = pl.K + 1;
+    const int kq = K1 == 1 ? 1 : 4;
+    const int kgn = (K1 + kq - 1) / kq;
     if (pl.NP >= 64) {
       const int nb = pl.NP / 64;
-      dim3 grid((unsigned)(Hm * ((K1 + 3) / 4) * nb * nb), (unsigned)w.S_h);
-      nif_bwd_weight_kernel<64><<<grid, 256, 0, st>>>(pl, g);
+      dim3 grid((unsigned)(Hm * kgn * nb * nb), (unsigned)w.S_h);
+      if (kq == 1) nif_bwd_weight_kernel<64, 1><<<grid, 256, 0, st>>>(pl, g);
+      else nif_bwd_weight_kernel<64, 4><<<grid, 256, 0, st>>>(pl, g);
     } else {
-      dim3 grid((unsigned)(Hm * ((K1 + 3) / 4)), (unsigned)w.S_h);
-      nif_bwd_weight_kernel<32><<<grid, 64, 0, st>>>(pl, g);
+      dim3 grid((unsigned)(Hm * kgn), (unsigned)w.S_h);
+      if (kq == 1) nif_bwd_weight_kernel<32, 1><<<grid, 64, 0, st>>>(pl, g);
+      else nif_bwd_weight_kernel<32, 4><<<grid, 64, 0, st>>>(pl, g);
     }
     NIF_CUDA_CHECK(cudaGetLastError());
   }

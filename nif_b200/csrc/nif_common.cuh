@@ -85,10 +85,34 @@ __host__ __device__ inline int plan_res(const Plan& p, int m) {
 // activations -----------------------------------------------------------------------------------
 __device__ __forceinline__ float sigmoidf_(float v) { return 1.0f / (1.0f + expf(-v)); }
 
+// sin and cos together, fp32-accurate (~1 ulp), compact: three-constant Cody-Waite reduction by pi/2 (good to
+// |v| < 1e5, far beyond omega_0-scaled SIREN pre-activations) and the Cephes minimax polynomials on [-pi/4, pi/4].
+// Larger / non-finite arguments take the library path out of line, so the inlined code stays ~25 instructions
+// (the library's inlined slow path bloats a 64-wide unrolled epilogue past the instruction cache).
+static __device__ __noinline__ void nif_sincos_slow(float v, float* s, float* c) { sincosf(v, s, c); }
+__device__ __forceinline__ void nif_sincosf(float v, float& s, float& c) {
+  if (!(fabsf(v) < 1.0e5f)) { nif_sincos_slow(v, &s, &c); return; }
+  const float kf = rintf(v * 0.636619747f);
+  const int k = __float2int_rn(kf);
+  float r = fmaf(kf, -1.57079601e+00f, v);
+  r = fmaf(kf, -3.13916473e-07f, r);
+  r = fmaf(kf, -5.39030253e-15f, r);
+  const float r2 = r * r;
+  float sp = fmaf(r2, -1.9515295891e-4f, 8.3321608736e-3f);
+  sp = fmaf(sp, r2, -1.6666654611e-1f);
+  sp = fmaf(sp * r2, r, r);
+  float cp = fmaf(r2, 2.443315711809948e-5f, -1.388731625493765e-3f);
+  cp = fmaf(cp, r2, 4.166664568298827e-2f);
+  cp = fmaf(cp * r2, r2, fmaf(r2, -0.5f, 1.0f));
+  const float a = (k & 1) ? cp : sp, b = (k & 1) ? sp : cp;
+  s = (k & 2) ? -a : a;
+  c = ((k + 1) & 2) ? -b : b;
+}
+
 // value and first derivative
 __device__ __forceinline__ void act_fd(int act, float v, float& f, float& d) {
   switch (act) {
-    case NIF_ACT_SINE: { float s, c; sincosf(v, &s, &c); f = s; d = c; } break;
+    case NIF_ACT_SINE: nif_sincosf(v, f, d); break;
     case NIF_ACT_SWISH: { float sg = sigmoidf_(v); f = v * sg; d = sg * (1.0f + v * (1.0f - sg)); } break;
     case NIF_ACT_TANH: { float t = tanhf(v); f = t; d = 1.0f - t * t; } break;
     case NIF_ACT_RELU: f = v > 0.f ? v : 0.f; d = v > 0.f ? 1.f : 0.f; break;
@@ -96,9 +120,14 @@ __device__ __forceinline__ void act_fd(int act, float v, float& f, float& d) {
     default: f = v; d = 1.0f; break;
   }
 }
+// four at a time, out of line: ONE copy of the activation switch per kernel instead of one per unrolled element
+static __device__ __noinline__ void act_fd4(int act, const float (&v)[4], float (&f)[4], float (&d)[4]) {
+#pragma unroll
+  for (int e = 0; e < 4; ++e) act_fd(act, v[e], f[e], d[e]);
+}
 __device__ __forceinline__ float act_f(int act, float v) {
   switch (act) {
-    case NIF_ACT_SINE: return sinf(v);
+    case NIF_ACT_SINE: { float s, c; nif_sincosf(v, s, c); return s; }
     case NIF_ACT_SWISH: return v * sigmoidf_(v);
     case NIF_ACT_TANH: return tanhf(v);
     case NIF_ACT_RELU: return v > 0.f ? v : 0.f;

@@ -119,15 +119,23 @@ __global__ void __launch_bounds__(C::NT, (RES || C::NP == 32) ? 1 : 2) nif_fwd_k
       }
       const float alpha = plan_alpha(pl, m);
       const int res = plan_res(pl, m);
-      float outv[MP][MJ], dv[MP][MJ];
+      float outv[MP][MJ], dv[MP][MJ], fv[MP][MJ];
+#pragma unroll
+      for (int r = 0; r < MP; ++r)
+#pragma unroll
+        for (int c4 = 0; c4 < MJ; c4 += 4) {
+          const float v4[4] = {acc[r][c4], acc[r][c4 + 1], acc[r][c4 + 2], acc[r][c4 + 3]};
+          float f4[4], d4[4];
+          act_fd4(pl.act, v4, f4, d4);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) { fv[r][c4 + e] = f4[e]; dv[r][c4 + e] = d4[e]; }
+        }
 #pragma unroll
       for (int r = 0; r < MP; ++r)
 #pragma unroll
         for (int c = 0; c < MJ; ++c) {
-          float f, d;
-          act_fd(pl.act, acc[r][c], f, d);
+          float f = fv[r][c], d = alpha * dv[r][c];
           float o = alpha * f;
-          d *= alpha;
           const int j = col_of<C>(tj, c);
           if (res == 1) o += act[act_idx<C>(j, row_of<C>(tp, r))];
           if (RES) {

@@ -148,9 +148,18 @@ __global__ void __launch_bounds__(C::NT, 1) nif_tangent_kernel(const Plan pl, co
 #pragma unroll
       for (int r = 0; r < MP; ++r)
 #pragma unroll
+        for (int c4 = 0; c4 < MJ; c4 += 4) {  // outv[0] / outv[1] hold f / act' until the loop below consumes them
+          const float v4[4] = {acc[0][r][c4], acc[0][r][c4 + 1], acc[0][r][c4 + 2], acc[0][r][c4 + 3]};
+          float f4[4], d4[4];
+          act_fd4(pl.act, v4, f4, d4);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) { outv[0][r][c4 + e] = f4[e]; outv[1][r][c4 + e] = d4[e]; }
+        }
+#pragma unroll
+      for (int r = 0; r < MP; ++r)
+#pragma unroll
         for (int c = 0; c < MJ; ++c) {
-          float f, d;
-          act_fd(pl.act, acc[0][r][c], f, d);
+          const float f = outv[0][r][c], d = outv[1][r][c];
           const int j = col_of<C>(tj, c);
           const int ai = act_idx<C>(j, row_of<C>(tp, r));
 #pragma unroll

@@ -288,20 +288,28 @@ struct DzEdgeArgs {
 //   next so                      F = du[b][c]                   G = CL[kappa][c]
 // G is staged through shared memory in slabs of 64 features; every thread keeps its K outputs in registers
 // (KT of them per pass over the features).
+// Every thread owns TWO rows (b and b + 128), so each shared-memory read of G feeds two FMAs.
 template <int KT>
 __global__ void __launch_bounds__(128) nif_dz_edge_kernel(const Plan pl, const DzEdgeArgs a, int k0) {
   __shared__ __align__(16) float Gs[64][KT];
   const int K = pl.K, K1 = pl.K + 1, H = pl.H, si = pl.si, so = pl.so;
-  const long long b = blockIdx.x * 128LL + threadIdx.x;
-  const bool live = b < a.B;
-  const long long bb = live ? b : 0;
+  const long long b0 = blockIdx.x * 256LL + threadIdx.x;
+  long long bb[2];
+  bool live[2];
+#pragma unroll
+  for (int w = 0; w < 2; ++w) {
+    live[w] = b0 + 128 * w < a.B;
+    bb[w] = live[w] ? b0 + 128 * w : 0;
+  }
   const float* C_all = a.packed + pl.off_C;
   const float* M0 = a.packed + pl.off_M0;
   const float* ML = a.packed + pl.off_ML;
   const float om0 = plan_omega(pl, 0);
-  float acc[KT];
+  float acc[2][KT];
 #pragma unroll
-  for (int k = 0; k < KT; ++k) acc[k] = 0.f;
+  for (int w = 0; w < 2; ++w)
+#pragma unroll
+    for (int k = 0; k < KT; ++k) acc[w][k] = 0.f;
 
   const int nslab = (H + 1) + si + so + 1;  // slabs of (up to) 64 features
   for (int sb = 0; sb < nslab; ++sb) {
@@ -319,41 +327,70 @@ __global__ void __launch_bounds__(128) nif_dz_edge_kernel(const Plan pl, const D
       Gs[f][k] = g;
     }
     __syncthreads();
-    // ---- this row's 64 features of the slab ----
-    const float* src;
-    float mul = 1.f;
+    // ---- the 64 features of the slab for both rows ----
+    const float* src[2];
+    float mul[2] = {1.f, 1.f};
     int nf = 64;
-    if (sb <= H) src = a.da + (long long)sb * a.B * 64 + bb * 64;
-    else if (sb < H + 1 + si) { src = a.da + bb * 64; mul = om0 * a.x[bb * si + (sb - H - 1)]; }
-    else if (sb < H + 1 + si + so) { src = a.save + (long long)H * a.B * 64 + bb * 64; mul = a.du[bb * so + (sb - H - 1 - si)]; }
-    else { src = a.du + bb * so; nf = so; }
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+      if (sb <= H) src[w] = a.da + (long long)sb * a.B * 64 + bb[w] * 64;
+      else if (sb < H + 1 + si) { src[w] = a.da + bb[w] * 64; mul[w] = om0 * a.x[bb[w] * si + (sb - H - 1)]; }
+      else if (sb < H + 1 + si + so) { src[w] = a.save + (long long)H * a.B * 64 + bb[w] * 64; mul[w] = a.du[bb[w] * so + (sb - H - 1 - si)]; }
+      else { src[w] = a.du + bb[w] * so; nf = so; }
+    }
     if (nf == 64) {
-#pragma unroll 4
-      for (int f4 = 0; f4 < 16; ++f4) {
-        const float4 v = *reinterpret_cast<const float4*>(src + 4 * f4);
-        const float fv[4] = {v.x * mul, v.y * mul, v.z * mul, v.w * mul};
+      // groups of 4 float4 per row; the next group's loads are issued before the current group is consumed
+      float4 cur[2][4], nxt[2][4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e)
+      for (int w = 0; w < 2; ++w)
 #pragma unroll
-          for (int k = 0; k < KT; k += 4) {
-            const float4 g = *reinterpret_cast<const float4*>(&Gs[4 * f4 + e][k]);
-            acc[k] = fmaf(fv[e], g.x, acc[k]); acc[k + 1] = fmaf(fv[e], g.y, acc[k + 1]);
-            acc[k + 2] = fmaf(fv[e], g.z, acc[k + 2]); acc[k + 3] = fmaf(fv[e], g.w, acc[k + 3]);
-          }
+        for (int q = 0; q < 4; ++q) cur[w][q] = ldg4(src[w] + 4 * q);
+#pragma unroll 1
+      for (int g4 = 0; g4 < 4; ++g4) {
+        if (g4 < 3) {
+#pragma unroll
+          for (int w = 0; w < 2; ++w)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) nxt[w][q] = ldg4(src[w] + 16 * (g4 + 1) + 4 * q);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float fv0[4] = {cur[0][q].x * mul[0], cur[0][q].y * mul[0], cur[0][q].z * mul[0], cur[0][q].w * mul[0]};
+          const float fv1[4] = {cur[1][q].x * mul[1], cur[1][q].y * mul[1], cur[1][q].z * mul[1], cur[1][q].w * mul[1]};
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+#pragma unroll
+            for (int k = 0; k < KT; k += 4) {
+              const float4 g = *reinterpret_cast<const float4*>(&Gs[16 * g4 + 4 * q + e][k]);
+              acc[0][k] = fmaf(fv0[e], g.x, acc[0][k]); acc[0][k + 1] = fmaf(fv0[e], g.y, acc[0][k + 1]);
+              acc[0][k + 2] = fmaf(fv0[e], g.z, acc[0][k + 2]); acc[0][k + 3] = fmaf(fv0[e], g.w, acc[0][k + 3]);
+              acc[1][k] = fmaf(fv1[e], g.x, acc[1][k]); acc[1][k + 1] = fmaf(fv1[e], g.y, acc[1][k + 1]);
+              acc[1][k + 2] = fmaf(fv1[e], g.z, acc[1][k + 2]); acc[1][k + 3] = fmaf(fv1[e], g.w, acc[1][k + 3]);
+            }
+        }
+#pragma unroll
+        for (int w = 0; w < 2; ++w)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) cur[w][q] = nxt[w][q];
       }
     } else {
       for (int f = 0; f < nf; ++f) {
-        const float fv = src[f];
+        const float f0 = src[0][f], f1 = src[1][f];
 #pragma unroll
-        for (int k = 0; k < KT; ++k) acc[k] = fmaf(fv, Gs[f][k], acc[k]);
+        for (int k = 0; k < KT; ++k) {
+          acc[0][k] = fmaf(f0, Gs[f][k], acc[0][k]);
+          acc[1][k] = fmaf(f1, Gs[f][k], acc[1][k]);
+        }
       }
     }
   }
-  if (live) {
 #pragma unroll
-    for (int k = 0; k < KT; ++k)
-      if (k0 + k < K) a.dz[b * K + k0 + k] += acc[k];
-  }
+  for (int w = 0; w < 2; ++w)
+    if (live[w]) {
+#pragma unroll
+      for (int k = 0; k < KT; ++k)
+        if (k0 + k < K) a.dz[bb[w] * K + k0 + k] += acc[w][k];
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -379,7 +416,7 @@ int nif_tc_bwd_data_impl(const Plan& pl, long long B, const float* z, const floa
   DzEdgeArgs e;
   e.B = B; e.x = x; e.packed = packed; e.save = save; e.da = da; e.du = du; e.dz = dz;
   for (int k0 = 0; k0 < pl.K; k0 += 32) {  // 32 latent coordinates per pass
-    nif_dz_edge_kernel<32><<<(unsigned)((B + 127) / 128), 128, 0, st>>>(pl, e, k0);
+    nif_dz_edge_kernel<32><<<(unsigned)((B + 255) / 256), 128, 0, st>>>(pl, e, k0);
     NIF_CUDA_CHECK(cudaGetLastError());
   }
   return NIF_OK;

@@ -247,12 +247,24 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) nif_tc_fwd_kernel(const Plan p
               hold[2 * e + 1] = (fh.y + fl.y) * inv_a;
             }
           }
-          float dch[8];
+          float dch[8], f8[8], d8[8];
+          if (pl.act == NIF_ACT_SINE) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) nif_sincosf(pre[8 * c + e], f8[e], d8[e]);
+          } else {
+#pragma unroll
+            for (int e4 = 0; e4 < 8; e4 += 4) {
+              const float v4[4] = {pre[8 * c + e4], pre[8 * c + e4 + 1], pre[8 * c + e4 + 2], pre[8 * c + e4 + 3]};
+              float f4[4], d4[4];
+              act_fd4(pl.act, v4, f4, d4);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) { f8[e4 + e] = f4[e]; d8[e4 + e] = d4[e]; }
+            }
+          }
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             const int j = 8 * c + e;
-            float f, d;
-            act_fd(pl.act, pre[j], f, d);
+            float f = f8[e], d = d8[e];
             float o = f;
             if (res == 1) o += hold[e];
             if (j >= n) { o = 0.f; d = 0.f; }
@@ -280,46 +292,46 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) nif_tc_fwd_kernel(const Plan p
         mbar_arrive(&a_ready[wg]);
       };
 
-      // ---- layer 0:  pre0[j] = sum_i' xt[i'] * (zt @ X0[i'])[j],  xt = [omega x, 1] ----
-      {
-        float pre[64];
-        const float om = plan_omega(pl, 0);
-        for (int i = 0; i <= si; ++i) {
-          chunk_begin();
-          const float coef = inv_z * __ldg(&invX[i]) * (i < si ? om * xs[i * 128 + r] : 1.f);
-          drain64(pre, coef, i == 0);
-          chunk_end();
-        }
-        finish_layer(0, pre);
-      }
-
-      // ---- hidden layers ----
-      for (int m = 1; m <= H; ++m) {
-        publish_h();
+      // ---- layers 0 .. H (one loop, so the activation epilogue exists once in the instruction stream) ----
+#pragma unroll 1
+      for (int m = 0; m <= H; ++m) {
         float acc[64];
-        chunk_begin();  // bias sum: acc[j] = sum_kappa zt[kappa] C_m[kappa][j]
-        drain64(acc, inv_z * __ldg(&invX[si + m]), true);
-        chunk_end();
-        const float om_inv = plan_omega(pl, m) * inv_a;
-        const float* invBm = invB + (m - 1) * KP;
-        for (int c = 0; c < NCH; ++c) {
-          chunk_begin();
-#pragma unroll
-          for (int kl = 0; kl < 2; ++kl) {
-            const int kk = 2 * c + kl;
-            const float zo = zs[kk * 128 + r] * om_inv * __ldg(&invBm[kk]);
-#pragma unroll
-            for (int hf = 0; hf < 2; ++hf) {  // 32 columns at a time: D1 + D2, then the latent contraction
-              float v1[32], v2[32];
-              const uint32_t col = (uint32_t)(kl * 64 + hf * 32);
-              tc_ld32(tm + col, v1);
-              tc_ld32(tm + col + 128u, v2);
-              tc_wait_ld();
-#pragma unroll
-              for (int e = 0; e < 32; ++e) acc[hf * 32 + e] = fmaf(zo, v1[e] + v2[e], acc[hf * 32 + e]);
-            }
+        if (m == 0) {
+          // layer 0:  pre0[j] = sum_i' xt[i'] * (zt @ X0[i'])[j],  xt = [omega x, 1]
+          const float om = plan_omega(pl, 0);
+          for (int i = 0; i <= si; ++i) {
+            chunk_begin();
+            const float coef = inv_z * __ldg(&invX[i]) * (i < si ? om * xs[i * 128 + r] : 1.f);
+            drain64(acc, coef, i == 0);
+            chunk_end();
           }
+        } else {
+          publish_h();
+          chunk_begin();  // bias sum: acc[j] = sum_kappa zt[kappa] C_m[kappa][j]
+          drain64(acc, inv_z * __ldg(&invX[si + m]), true);
           chunk_end();
+          const float om_inv = plan_omega(pl, m) * inv_a;
+          const float* invBm = invB + (m - 1) * KP;
+#pragma unroll 1
+          for (int c = 0; c < NCH; ++c) {
+            chunk_begin();
+#pragma unroll
+            for (int kl = 0; kl < 2; ++kl) {
+              const int kk = 2 * c + kl;
+              const float zo = zs[kk * 128 + r] * om_inv * __ldg(&invBm[kk]);
+#pragma unroll
+              for (int hf = 0; hf < 2; ++hf) {  // 32 columns at a time: D1 + D2, then the latent contraction
+                float v1[32], v2[32];
+                const uint32_t col = (uint32_t)(kl * 64 + hf * 32);
+                tc_ld32(tm + col, v1);
+                tc_ld32(tm + col + 128u, v2);
+                tc_wait_ld();
+#pragma unroll
+                for (int e = 0; e < 32; ++e) acc[hf * 32 + e] = fmaf(zo, v1[e] + v2[e], acc[hf * 32 + e]);
+              }
+            }
+            chunk_end();
+          }
         }
         finish_layer(m, acc);
       }
