@@ -87,11 +87,15 @@ __device__ __forceinline__ float sigmoidf_(float v) { return 1.0f / (1.0f + expf
 
 // sin and cos together, fp32-accurate (~1 ulp), compact: three-constant Cody-Waite reduction by pi/2 (good to
 // |v| < 1e5, far beyond omega_0-scaled SIREN pre-activations) and the Cephes minimax polynomials on [-pi/4, pi/4].
-// Larger / non-finite arguments take the library path out of line, so the inlined code stays ~25 instructions
-// (the library's inlined slow path bloats a 64-wide unrolled epilogue past the instruction cache).
-static __device__ __noinline__ void nif_sincos_slow(float v, float* s, float* c) { sincosf(v, s, c); }
+// ~25 instructions inline (the library's inlined Payne-Hanek slow path bloats a 64-wide unrolled epilogue past the
+// instruction cache).
 __device__ __forceinline__ void nif_sincosf(float v, float& s, float& c) {
-  if (!(fabsf(v) < 1.0e5f)) { nif_sincos_slow(v, &s, &c); return; }
+  // never taken for sane SIREN pre-activations; call-free so that unrolled epilogues keep their registers:
+  // fold the argument into [-pi, pi] in double precision (exact quadrant up to ~1e15; NaN / inf stay NaN)
+  if (!(fabsf(v) < 1.0e5f)) {
+    const double q = rint((double)v * 0.15915494309189535);
+    v = (float)fma(-q, 6.283185307179586, (double)v);
+  }
   const float kf = rintf(v * 0.636619747f);
   const int k = __float2int_rn(kf);
   float r = fmaf(kf, -1.57079601e+00f, v);
@@ -121,9 +125,19 @@ __device__ __forceinline__ void act_fd(int act, float v, float& f, float& d) {
   }
 }
 // four at a time, out of line: ONE copy of the activation switch per kernel instead of one per unrolled element
-static __device__ __noinline__ void act_fd4(int act, const float (&v)[4], float (&f)[4], float (&d)[4]) {
-#pragma unroll
-  for (int e = 0; e < 4; ++e) act_fd(act, v[e], f[e], d[e]);
+struct ActFd4 { float4 f, d; };
+static __device__ __noinline__ ActFd4 act_fd4v(int act, float4 v) {
+  ActFd4 r;
+  act_fd(act, v.x, r.f.x, r.d.x);
+  act_fd(act, v.y, r.f.y, r.d.y);
+  act_fd(act, v.z, r.f.z, r.d.z);
+  act_fd(act, v.w, r.f.w, r.d.w);
+  return r;
+}
+__device__ __forceinline__ void act_fd4(int act, const float (&v)[4], float (&f)[4], float (&d)[4]) {
+  const ActFd4 r = act_fd4v(act, make_float4(v[0], v[1], v[2], v[3]));
+  f[0] = r.f.x; f[1] = r.f.y; f[2] = r.f.z; f[3] = r.f.w;
+  d[0] = r.d.x; d[1] = r.d.y; d[2] = r.d.z; d[3] = r.d.w;
 }
 __device__ __forceinline__ float act_f(int act, float v) {
   switch (act) {

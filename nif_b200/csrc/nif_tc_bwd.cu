@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) nif_tc_bwd_data_kernel(const P
   if ((long long)blockIdx.x < a.total_pairs) my_pairs = (a.total_pairs - blockIdx.x + gridDim.x - 1) / gridDim.x;
 
   if (warp >= 8) {
-  tc_reg_dec<56>();  // MMA / producer / idle warps donate registers to the epilogue warp groups
+  tc_reg_dec<56>();  // MMA / producer / idle warps donate registers: 128 x (168 - 56) freed = 256 x (224 - 168) claimed below
   if (warp == 9) {
     if (lane == 0) {  // weight-stream producer: hidden matrices in reverse order
       long long g = 0;
@@ -226,15 +226,23 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) nif_tc_bwd_data_kernel(const P
         }
         const float om_inv = plan_omega(pl, m) * inv_a;
         const float* invBm = invB + (m - 1) * KP;
+        // per-chunk row coefficients, fetched one chunk ahead (their latency hides behind the accumulator wait)
+        float sBn[2] = {om_inv * __ldg(&invBm[0]), om_inv * __ldg(&invBm[1])};
+        float zkn[2] = {zs[r], zs[128 + r]};
+#pragma unroll 1
         for (int c = 0; c < NCH; ++c, ++g) {
+          const float sBc[2] = {sBn[0], sBn[1]}, zkc[2] = {zkn[0], zkn[1]};
+          if (c + 1 < NCH) {
+            sBn[0] = om_inv * __ldg(&invBm[2 * c + 2]); sBn[1] = om_inv * __ldg(&invBm[2 * c + 3]);
+            zkn[0] = zs[(2 * c + 2) * 128 + r]; zkn[1] = zs[(2 * c + 3) * 128 + r];
+          }
           mbar_wait(&t_full[wg], (uint32_t)(g & 1));
           tc_fence_after();
 #pragma unroll
           for (int kl = 0; kl < 2; ++kl) {
             const int kk = 2 * c + kl;
-            const float zk = zs[kk * 128 + r];
-            const float sB = om_inv * __ldg(&invBm[kk]);
-            const float zo = zk * sB;
+            const float sB = sBc[kl];
+            const float zo = zkc[kl] * sB;
             float s0 = 0.f, s1 = 0.f;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {  // 16 columns (values of i) at a time keeps the register budget

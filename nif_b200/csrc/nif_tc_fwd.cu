@@ -41,7 +41,8 @@ __host__ __device__ inline size_t tcf_smem_bytes(int KP, int KZ, int si) {
          2 * (size_t)KP * 128 * 4 + 2 * (size_t)si * 128 * 4 + 256;
 }
 
-template <bool SAVE>
+// SINE: the activation is sine (SIREN variants), inlined; otherwise the out-of-line activation switch is called
+template <bool SAVE, bool SINE>
 __global__ void __launch_bounds__(TCF_THREADS, 1) nif_tc_fwd_kernel(const Plan pl, const TcFwdArgs a) {
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char* A_all = smem;                                  // tile t: hi at t*32K, lo at t*32K + 16K
@@ -87,7 +88,7 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) nif_tc_fwd_kernel(const Plan p
   if ((long long)blockIdx.x < a.total_pairs) my_pairs = (a.total_pairs - blockIdx.x + gridDim.x - 1) / gridDim.x;
 
   if (warp >= 8) {
-  tc_reg_dec<56>();  // MMA / producer / idle warps donate registers to the epilogue warp groups
+  tc_reg_dec<56>();  // MMA / producer / idle warps donate registers: 128 x (168 - 56) freed = 256 x (224 - 168) claimed below
   if (warp == 9) {
     // ---------------- weight-stream producer ----------------
     if (lane == 0) {
@@ -248,7 +249,7 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) nif_tc_fwd_kernel(const Plan p
             }
           }
           float dch[8], f8[8], d8[8];
-          if (pl.act == NIF_ACT_SINE) {
+          if (SINE) {
 #pragma unroll
             for (int e = 0; e < 8; ++e) nif_sincosf(pre[8 * c + e], f8[e], d8[e]);
           } else {
@@ -312,13 +313,19 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) nif_tc_fwd_kernel(const Plan p
           chunk_end();
           const float om_inv = plan_omega(pl, m) * inv_a;
           const float* invBm = invB + (m - 1) * KP;
+          // per-chunk row coefficients, fetched one chunk ahead (their latency hides behind the accumulator wait)
+          float zo2[2] = {zs[r] * om_inv * __ldg(&invBm[0]), zs[128 + r] * om_inv * __ldg(&invBm[1])};
 #pragma unroll 1
           for (int c = 0; c < NCH; ++c) {
+            const float zc2[2] = {zo2[0], zo2[1]};
+            if (c + 1 < NCH) {
+              zo2[0] = zs[(2 * c + 2) * 128 + r] * om_inv * __ldg(&invBm[2 * c + 2]);
+              zo2[1] = zs[(2 * c + 3) * 128 + r] * om_inv * __ldg(&invBm[2 * c + 3]);
+            }
             chunk_begin();
 #pragma unroll
             for (int kl = 0; kl < 2; ++kl) {
-              const int kk = 2 * c + kl;
-              const float zo = zs[kk * 128 + r] * om_inv * __ldg(&invBm[kk]);
+              const float zo = zc2[kl];
 #pragma unroll
               for (int hf = 0; hf < 2; ++hf) {  // 32 columns at a time: D1 + D2, then the latent contraction
                 float v1[32], v2[32];
@@ -370,10 +377,10 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) nif_tc_fwd_kernel(const Plan p
   if (warp == 8) tc_dealloc(tmem, 512);
 }
 
-template <bool SAVE>
+template <bool SAVE, bool SINE>
 static int launch_tcf(const Plan& pl, const TcFwdArgs& a, cudaStream_t st) {
   const size_t smem = tcf_smem_bytes(pl.KP, pl.KZ, pl.si);
-  auto kern = nif_tc_fwd_kernel<SAVE>;
+  auto kern = nif_tc_fwd_kernel<SAVE, SINE>;
   NIF_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int dev = 0, sms = 0;
   NIF_CUDA_CHECK(cudaGetDevice(&dev));
@@ -396,5 +403,6 @@ int nif_tc_forward_impl(const Plan& pl, long long B, const float* z, const float
   a.B = B;
   a.total_pairs = (B + 255) / 256;
   a.z = z; a.x = x; a.packed = packed; a.u = u; a.save = save;
-  return save ? launch_tcf<true>(pl, a, st) : launch_tcf<false>(pl, a, st);
+  if (pl.act == NIF_ACT_SINE) return save ? launch_tcf<true, true>(pl, a, st) : launch_tcf<false, true>(pl, a, st);
+  return save ? launch_tcf<true, false>(pl, a, st) : launch_tcf<false, false>(pl, a, st);
 }
