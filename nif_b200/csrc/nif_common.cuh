@@ -89,13 +89,15 @@ __device__ __forceinline__ float sigmoidf_(float v) { return 1.0f / (1.0f + expf
 // |v| < 1e5, far beyond omega_0-scaled SIREN pre-activations) and the Cephes minimax polynomials on [-pi/4, pi/4].
 // ~25 instructions inline (the library's inlined Payne-Hanek slow path bloats a 64-wide unrolled epilogue past the
 // instruction cache).
+// huge / non-finite arguments (never seen for sane SIREN pre-activations): fold into [-pi, pi] in double precision
+// (exact quadrant up to ~1e15; NaN / inf stay NaN).  Out of line and by value, so the hot path carries neither the
+// fp64 instructions (the compiler would predicate them into every element) nor address-taken outputs.
+static __device__ __noinline__ float nif_fold_2pi(float v) {
+  const double q = rint((double)v * 0.15915494309189535);
+  return (float)fma(-q, 6.283185307179586, (double)v);
+}
 __device__ __forceinline__ void nif_sincosf(float v, float& s, float& c) {
-  // never taken for sane SIREN pre-activations; call-free so that unrolled epilogues keep their registers:
-  // fold the argument into [-pi, pi] in double precision (exact quadrant up to ~1e15; NaN / inf stay NaN)
-  if (!(fabsf(v) < 1.0e5f)) {
-    const double q = rint((double)v * 0.15915494309189535);
-    v = (float)fma(-q, 6.283185307179586, (double)v);
-  }
+  if (!(fabsf(v) < 1.0e5f)) v = nif_fold_2pi(v);
   const float kf = rintf(v * 0.636619747f);
   const int k = __float2int_rn(kf);
   float r = fmaf(kf, -1.57079601e+00f, v);

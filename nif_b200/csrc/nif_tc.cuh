@@ -9,9 +9,7 @@
 // fp32-grade accuracy on the fp16 pipe ("FP16x3"): every operand row is scaled by a power of two so that its
 // largest magnitude lies in [2^13, 2^14), then split  x * 2^e = hi + lo  with hi = fp16(x 2^e), lo = fp16(x 2^e - hi)
 // (22 significant bits for the large entries, absolute error 2^-25 relative to the row maximum for the rest).
-// Products use  hi*hi + lo*hi + hi*lo  with fp32 accumulation in TMEM; hi*hi goes to its own accumulator D1 and
-// the two small cross terms to D2, because the tensor core rounds its accumulator toward zero on every
-// instruction and the small terms would otherwise add 2/3 of those roundings to the dominant sum.
+// Products use  hi*hi + lo*hi + hi*lo  with fp32 accumulation in TMEM (cross terms first, see tc_mma_split).
 // The scales are powers of two, so un-scaling in the epilogue is exact.
 #pragma once
 #include <cuda_fp16.h>
@@ -40,26 +38,32 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t da, uint64_
       "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// D1 += Ahi*Bhi, D2 += Alo*Bhi + Ahi*Blo over a 64-deep K (4 instructions of K = 16 each per term)
-__device__ __forceinline__ void tc_mma_split_k64(uint32_t d1, uint32_t d2, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi,
-                                                 uint64_t b_lo, uint32_t idesc) {
-#pragma unroll
-  for (int ks = 0; ks < 4; ++ks) {  // 16 elements of K = 2 core matrices = 256 B = 16 descriptor units
+// D = Alo*Bhi + Ahi*Blo + Ahi*Bhi over a K extent of 16 * ksteps, ONE accumulator: the small cross terms of all k-steps
+// are accumulated first and the dominant hi*hi terms last, so only `ksteps` instructions truncate (the tensor core rounds
+// its accumulator toward zero on every instruction) at the magnitude of the result -- the same count a dedicated hi*hi
+// accumulator would see -- while the cross terms' truncations are 2^-11 smaller.
+__device__ __forceinline__ void tc_mma_split(uint32_t d, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo,
+                                             uint32_t idesc, int ksteps) {
+  for (int ks = 0; ks < ksteps; ++ks) {  // 16 elements of K = 2 core matrices = 256 B = 16 descriptor units
     const uint64_t adv = (uint64_t)(ks * 16);
-    tc_mma_f16(d2, a_lo + adv, b_hi + adv, idesc, ks > 0 ? 1u : 0u);
-    tc_mma_f16(d2, a_hi + adv, b_lo + adv, idesc, 1u);
-    tc_mma_f16(d1, a_hi + adv, b_hi + adv, idesc, ks > 0 ? 1u : 0u);
+    tc_mma_f16(d, a_lo + adv, b_hi + adv, idesc, ks > 0 ? 1u : 0u);
+    tc_mma_f16(d, a_hi + adv, b_lo + adv, idesc, 1u);
   }
-}
-// same with a run-time K extent (ksteps instructions of K = 16 per term)
-__device__ __forceinline__ void tc_mma_split(uint32_t d1, uint32_t d2, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi,
-                                             uint64_t b_lo, uint32_t idesc, int ksteps) {
   for (int ks = 0; ks < ksteps; ++ks) {
     const uint64_t adv = (uint64_t)(ks * 16);
-    tc_mma_f16(d2, a_lo + adv, b_hi + adv, idesc, ks > 0 ? 1u : 0u);
-    tc_mma_f16(d2, a_hi + adv, b_lo + adv, idesc, 1u);
-    tc_mma_f16(d1, a_hi + adv, b_hi + adv, idesc, ks > 0 ? 1u : 0u);
+    tc_mma_f16(d, a_hi + adv, b_hi + adv, idesc, 1u);
   }
+}
+__device__ __forceinline__ void tc_mma_split_k64(uint32_t d, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo,
+                                                 uint32_t idesc) {
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    const uint64_t adv = (uint64_t)(ks * 16);
+    tc_mma_f16(d, a_lo + adv, b_hi + adv, idesc, ks > 0 ? 1u : 0u);
+    tc_mma_f16(d, a_hi + adv, b_lo + adv, idesc, 1u);
+  }
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) tc_mma_f16(d, a_hi + (uint64_t)(ks * 16), b_hi + (uint64_t)(ks * 16), idesc, 1u);
 }
 // arrive on an mbarrier when every tcgen05 op issued so far by this thread has completed
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {

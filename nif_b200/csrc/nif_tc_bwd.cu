@@ -43,9 +43,9 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) nif_tc_bwd_data_kernel(const P
   uint64_t* bars = reinterpret_cast<uint64_t*>(dzs_all + 2 * pl.KP * 128);
   uint64_t* b_full = bars;
   uint64_t* b_empty = bars + TCB_STAGES;
-  uint64_t* t_full = bars + 2 * TCB_STAGES;
-  uint64_t* t_empty = t_full + 2;
-  uint64_t* a_ready = t_empty + 2;
+  uint64_t* t_full = bars + 2 * TCB_STAGES;  // [2][2]  accumulator stage s of tile t ready
+  uint64_t* t_empty = t_full + 4;            // [2][2]  accumulator stage s of tile t drained
+  uint64_t* a_ready = t_empty + 4;           // [2]     operand tile of tile t written
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_ready + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -54,13 +54,13 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) nif_tc_bwd_data_kernel(const P
   if (tid == 0) {
     for (int i = 0; i < TCB_STAGES; ++i) {
       mbar_init(&b_full[i], 1);
-      mbar_init(&b_empty[i], 1);
+      mbar_init(&b_empty[i], 2);  // both MMA issuers
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 4; ++i) {
       mbar_init(&t_full[i], 1);
       mbar_init(&t_empty[i], 128);
-      mbar_init(&a_ready[i], 128);
     }
+    for (int i = 0; i < 2; ++i) mbar_init(&a_ready[i], 128);
     mbar_fence_init();
   }
   if (warp == 8) tc_alloc(tmem_slot, 512);
@@ -88,31 +88,27 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) nif_tc_bwd_data_kernel(const P
                      TCB_STAGE_BYTES, &b_full[s]);
           }
     }
-  } else if (warp == 8) {
-    if (lane == 0) {  // MMA issuer
+  } else if (warp == 8 || warp == 10) {
+    if (lane == 0) {  // MMA issuers: warp 8 feeds tile 0, warp 10 feeds tile 1 (see nif_tc_fwd.cu)
+      const int t = warp == 8 ? 0 : 1;
       const uint32_t idesc = tc_idesc_f16(128);
-      uint64_t da_hi[2], da_lo[2];
-      for (int t = 0; t < 2; ++t) {
-        da_hi[t] = tc_make_desc(smem_u32(A_all + t * 2 * TC_TILE_BYTES));
-        da_lo[t] = tc_make_desc(smem_u32(A_all + t * 2 * TC_TILE_BYTES + TC_TILE_BYTES));
-      }
+      const uint64_t da_hi = tc_make_desc(smem_u32(A_all + t * 2 * TC_TILE_BYTES));
+      const uint64_t da_lo = tc_make_desc(smem_u32(A_all + t * 2 * TC_TILE_BYTES + TC_TILE_BYTES));
       long long g = 0, L = 0;
       for (long long p = 0; p < my_pairs; ++p)
         for (int h = 0; h < H; ++h, ++L)
           for (int c = 0; c < NCH; ++c, ++g) {
             const int s = (int)(g % TCB_STAGES);
+            const int as = (int)(g & 1);  // accumulator stage: the MMAs of chunk g+1 run while chunk g is drained
+            if (c == 0) mbar_wait(&a_ready[t], (uint32_t)(L & 1));
+            mbar_wait(&t_empty[2 * t + as], (uint32_t)(((g >> 1) & 1) ^ 1));
             mbar_wait(&b_full[s], (uint32_t)((g / TCB_STAGES) & 1));
+            tc_fence_after();
             const uint64_t db_hi = tc_make_desc(smem_u32(Bst + s * TCB_STAGE_BYTES));
             const uint64_t db_lo = tc_make_desc(smem_u32(Bst + s * TCB_STAGE_BYTES + TC_TILE_BYTES));
-#pragma unroll
-            for (int t = 0; t < 2; ++t) {
-              if (c == 0) mbar_wait(&a_ready[t], (uint32_t)(L & 1));
-              mbar_wait(&t_empty[t], (uint32_t)((g & 1) ^ 1));
-              tc_fence_after();
-              const uint32_t d1 = tmem + (uint32_t)t * 256u;
-              tc_mma_split_k64(d1, d1 + 128u, da_hi[t], da_lo[t], db_hi, db_lo, idesc);
-              tc_commit(&t_full[t]);
-            }
+            const uint32_t d = tmem + (uint32_t)t * 256u + (uint32_t)as * 128u;
+            tc_mma_split_k64(d, da_hi, da_lo, db_hi, db_lo, idesc);
+            tc_commit(&t_full[2 * t + as]);
             tc_commit(&b_empty[s]);
           }
     }
@@ -134,9 +130,14 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) nif_tc_bwd_data_kernel(const P
       const long long b = row0 + r;
       const bool live = b < a.B;
       named_bar_sync(1 + wg, 128);
-      for (int idx = r; idx < 128 * K; idx += 128) {
-        const int q = idx / K, kk = idx - q * K;
-        zs[kk * 128 + q] = (row0 + q < a.B) ? __ldg(&a.z[(row0 + q) * K + kk]) : 0.f;
+      // every thread stages its own row of z (independent vector loads, conflict-free transposed stores)
+      if ((K & 3) == 0) {
+        for (int k4 = 0; k4 < K; k4 += 4) {
+          const float4 q4 = live ? ldg4(a.z + b * K + k4) : make_float4(0.f, 0.f, 0.f, 0.f);
+          zs[k4 * 128 + r] = q4.x; zs[(k4 + 1) * 128 + r] = q4.y; zs[(k4 + 2) * 128 + r] = q4.z; zs[(k4 + 3) * 128 + r] = q4.w;
+        }
+      } else {
+        for (int kk = 0; kk < K; ++kk) zs[kk * 128 + r] = live ? __ldg(&a.z[b * K + kk]) : 0.f;
       }
       zs[K * 128 + r] = 1.f;
       for (int kk = K1; kk < KP; ++kk) zs[kk * 128 + r] = 0.f;
@@ -236,8 +237,9 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) nif_tc_bwd_data_kernel(const P
             sBn[0] = om_inv * __ldg(&invBm[2 * c + 2]); sBn[1] = om_inv * __ldg(&invBm[2 * c + 3]);
             zkn[0] = zs[(2 * c + 2) * 128 + r]; zkn[1] = zs[(2 * c + 3) * 128 + r];
           }
-          mbar_wait(&t_full[wg], (uint32_t)(g & 1));
+          mbar_wait(&t_full[2 * wg + (int)(g & 1)], (uint32_t)((g >> 1) & 1));
           tc_fence_after();
+          const uint32_t td = tm + (uint32_t)(g & 1) * 128u;
 #pragma unroll
           for (int kl = 0; kl < 2; ++kl) {
             const int kk = 2 * c + kl;
@@ -245,25 +247,24 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) nif_tc_bwd_data_kernel(const P
             const float zo = zkc[kl] * sB;
             float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {  // 16 columns (values of i) at a time keeps the register budget
+            for (int q = 0; q < 2; ++q) {  // 32 columns (values of i) at a time
               float v1[16], v2[16];
-              const uint32_t col = (uint32_t)(kl * 64 + q * 16);
-              tc_ld16(tm + col, v1);
-              tc_ld16(tm + col + 128u, v2);
+              const uint32_t col = (uint32_t)(kl * 64 + q * 32);
+              tc_ld16(td + col, v1);
+              tc_ld16(td + col + 16u, v2);
               tc_wait_ld();
 #pragma unroll
-              for (int e = 0; e < 16; e += 2) {
-                const float t0 = v1[e] + v2[e], t1 = v1[e + 1] + v2[e + 1];
-                acc[q * 16 + e] = fmaf(zo, t0, acc[q * 16 + e]);
-                acc[q * 16 + e + 1] = fmaf(zo, t1, acc[q * 16 + e + 1]);
-                s0 = fmaf(t0, hm[q * 16 + e], s0);
-                s1 = fmaf(t1, hm[q * 16 + e + 1], s1);
+              for (int e = 0; e < 16; ++e) {
+                acc[q * 32 + e] = fmaf(zo, v1[e], acc[q * 32 + e]);
+                acc[q * 32 + 16 + e] = fmaf(zo, v2[e], acc[q * 32 + 16 + e]);
+                s0 = fmaf(v1[e], hm[q * 32 + e], s0);
+                s1 = fmaf(v2[e], hm[q * 32 + 16 + e], s1);
               }
             }
             dzs[kk * 128 + r] += sB * (s0 + s1);
           }
           tc_fence_before();
-          mbar_arrive(&t_empty[wg]);
+          mbar_arrive(&t_empty[2 * wg + (int)(g & 1)]);
         }
       }
 

@@ -9,7 +9,7 @@
 // Layer 0, the bias sums sum_kappa zt[kappa] C_m[kappa][:] and the last layer are tensor-core chunks too (A = the
 // zt tile resp. the h tile, small B tiles from the packed image), so the CUDA cores only run the per-row
 // latent contraction, the activations and the operand split.
-//   D = D1 [128 x 128] (hi*hi) and D2 [128 x 128] (cross terms), fp32 in TMEM.
+//   D = [128 x 128] fp32 in TMEM, two accumulator stages per tile (the MMAs of chunk c+1 run while chunk c is drained).
 // The per-row contraction over kappa (and the un-scaling) runs on the CUDA cores straight out of TMEM: thread r
 // owns row r = TMEM lane r.
 //
@@ -17,9 +17,33 @@
 // chunk (halves the L2 traffic per row) and ping-pong on the tensor pipe: while the MMAs of one tile run, the
 // other tile's epilogue warps drain its accumulators.
 //   warps 0-3  epilogue of tile 0        warps 4-7  epilogue of tile 1
-//   warp 8     MMA issuer (one elected lane) and TMEM owner (512 columns: 2 tiles x (D1 | D2))
+//   warp 8     MMA issuer of tile 0 (one elected lane) and TMEM owner (512 columns: 2 tiles x 2 accumulator stages x 128)
 //   warp 9     weight-stream producer
+//   warp 10    MMA issuer of tile 1;  warp 11 idle (register donor)
 #include "nif_tc.cuh"
+
+// Optional timeline trace (make -C nif_b200/csrc EXTRA=-DNIF_TRACE): CTA 0 records clock64() at the hand-offs of its first
+// tile pair; read back with nif_debug_read_trace().  Compiled out of the product build.
+#ifdef NIF_TRACE
+__device__ long long g_trace[4][2048];
+__device__ int g_trace_n[4];
+#define TRACE(role, tag)                                                                  \
+  do {                                                                                    \
+    if (blockIdx.x == 0 && trace_n < 1023) {                                              \
+      g_trace[role][2 * trace_n] = (long long)(tag);                                      \
+      g_trace[role][2 * trace_n + 1] = clock64();                                         \
+      ++trace_n;                                                                          \
+      g_trace_n[role] = 2 * trace_n;                                                      \
+    }                                                                                     \
+  } while (0)
+extern "C" int nif_debug_read_trace(long long* host, int* counts) {
+  cudaMemcpyFromSymbol(host, g_trace, sizeof(g_trace));
+  cudaMemcpyFromSymbol(counts, g_trace_n, sizeof(g_trace_n));
+  return 0;
+}
+#else
+#define TRACE(role, tag) do {} while (0)
+#endif
 
 struct TcFwdArgs {
   long long B, total_pairs;
@@ -55,27 +79,30 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) nif_tc_fwd_kernel(const Plan p
   uint64_t* bars = reinterpret_cast<uint64_t*>(xs_all + 2 * pl.si * 128);
   uint64_t* b_full = bars;                    // [TCF_STAGES]
   uint64_t* b_empty = bars + TCF_STAGES;      // [TCF_STAGES]
-  uint64_t* t_full = bars + 2 * TCF_STAGES;   // [2]  accumulators of tile t ready
-  uint64_t* t_empty = t_full + 2;             // [2]  accumulators of tile t drained
-  uint64_t* a_ready = t_empty + 2;            // [2]  operand tile of tile t written
+  uint64_t* t_full = bars + 2 * TCF_STAGES;   // [2][2]  accumulator stage s of tile t ready
+  uint64_t* t_empty = t_full + 4;             // [2][2]  accumulator stage s of tile t drained
+  uint64_t* a_ready = t_empty + 4;            // [2]  operand tile of tile t written
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_ready + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int K = pl.K, K1 = pl.K + 1, KP = pl.KP, NCH = pl.NCH, H = pl.H, n = pl.n, si = pl.si, so = pl.so;
   const int KZ = pl.KZ, NLC = pl.NLC, LPC = pl.LPC;
+#ifdef NIF_TRACE
+  int trace_n = 0;
+#endif
   const uint32_t small_bytes = 2u * 64u * (uint32_t)KZ * 2u;        // X0 / XC chunk [hi | lo]
   const uint32_t last_bytes = 2u * (uint32_t)(LPC * KZ) * 64u * 2u;  // XL chunk [hi | lo]
 
   if (tid == 0) {
     for (int i = 0; i < TCF_STAGES; ++i) {
       mbar_init(&b_full[i], 1);
-      mbar_init(&b_empty[i], 1);
+      mbar_init(&b_empty[i], 2);  // both MMA issuers
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 4; ++i) {
       mbar_init(&t_full[i], 1);
       mbar_init(&t_empty[i], 128);
-      mbar_init(&a_ready[i], 128);
     }
+    for (int i = 0; i < 2; ++i) mbar_init(&a_ready[i], 128);
     mbar_fence_init();
   }
   if (warp == 8) tc_alloc(tmem_slot, 512);
@@ -98,6 +125,7 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) nif_tc_fwd_kernel(const Plan p
       auto put = [&](const float* src, uint32_t bytes) {
         const int s = (int)(g % TCF_STAGES);
         mbar_wait(&b_empty[s], (uint32_t)(((g / TCF_STAGES) & 1) ^ 1));
+        TRACE(3, g);
         mbar_expect_tx(&b_full[s], bytes);
         bulk_g2s(Bst + s * TCF_STAGE_BYTES, src, bytes, &b_full[s]);
         ++g;
@@ -112,35 +140,34 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) nif_tc_fwd_kernel(const Plan p
           put(tcx + (long long)(si + 1 + H) * plan_x0_floats(pl) + (long long)q * plan_xl_floats(pl), last_bytes);
       }
     }
-  } else if (warp == 8) {
-    // ---------------- MMA issuer ----------------
+  } else if (warp == 8 || warp == 10) {
+    // ---------------- MMA issuers: warp 8 feeds tile 0, warp 10 feeds tile 1 ----------------
+    // (one issuer per tile: while one is between chunks -- barrier waits, descriptors, commits -- the other keeps
+    // the tensor pipe fed; both read the same staged weight chunk and each commits to its b_empty, count 2)
     if (lane == 0) {
-      uint64_t da_hi[2], da_lo[2], dz_hi[2], dz_lo[2];
-      for (int t = 0; t < 2; ++t) {
-        da_hi[t] = tc_make_desc(smem_u32(A_all + t * 2 * TC_TILE_BYTES), TC_SBO);
-        da_lo[t] = tc_make_desc(smem_u32(A_all + t * 2 * TC_TILE_BYTES + TC_TILE_BYTES), TC_SBO);
-        dz_hi[t] = tc_make_desc(smem_u32(Z_all + t * 2 * zbytes), sbo_z);
-        dz_lo[t] = tc_make_desc(smem_u32(Z_all + t * 2 * zbytes + zbytes), sbo_z);
-      }
-      long long g = 0;        // chunk counter (stage / accumulator phases)
-      long long ar[2] = {0, 0};  // a_ready phases consumed per tile
-      // one chunk for both tiles: A operand kind (0 = zt tile, 1 = h tile), K extent, B geometry, N
+      const int t = warp == 8 ? 0 : 1;
+      const uint64_t da_hi = tc_make_desc(smem_u32(A_all + t * 2 * TC_TILE_BYTES), TC_SBO);
+      const uint64_t da_lo = tc_make_desc(smem_u32(A_all + t * 2 * TC_TILE_BYTES + TC_TILE_BYTES), TC_SBO);
+      const uint64_t dz_hi = tc_make_desc(smem_u32(Z_all + t * 2 * zbytes), sbo_z);
+      const uint64_t dz_lo = tc_make_desc(smem_u32(Z_all + t * 2 * zbytes + zbytes), sbo_z);
+      long long g = 0;   // chunk counter (stage / accumulator phases)
+      long long ar = 0;  // a_ready phases consumed
+      // one chunk: A operand kind (0 = zt tile, 1 = h tile), K extent, B geometry, N
       auto chunk = [&](int a_kind, bool wait_a, int ksteps, uint32_t b_half_bytes, uint32_t b_sbo, int N) {
         const int s = (int)(g % TCF_STAGES);
+        const int as = (int)(g & 1);  // accumulator stage
+        if (wait_a) { mbar_wait(&a_ready[t], (uint32_t)(ar & 1)); ++ar; }
+        mbar_wait(&t_empty[2 * t + as], (uint32_t)(((g >> 1) & 1) ^ 1));
         mbar_wait(&b_full[s], (uint32_t)((g / TCF_STAGES) & 1));
+        if (t == 0) TRACE(2, g * 8 + 1 + t);
+        tc_fence_after();
         const uint64_t db_hi = tc_make_desc(smem_u32(Bst + s * TCF_STAGE_BYTES), b_sbo);
         const uint64_t db_lo = tc_make_desc(smem_u32(Bst + s * TCF_STAGE_BYTES + b_half_bytes), b_sbo);
-        const uint32_t idesc = tc_idesc_f16(N);
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          if (wait_a) { mbar_wait(&a_ready[t], (uint32_t)(ar[t] & 1)); ++ar[t]; }
-          mbar_wait(&t_empty[t], (uint32_t)((g & 1) ^ 1));
-          tc_fence_after();
-          const uint32_t d1 = tmem + (uint32_t)t * 256u;
-          tc_mma_split(d1, d1 + 128u, a_kind ? da_hi[t] : dz_hi[t], a_kind ? da_lo[t] : dz_lo[t], db_hi, db_lo, idesc, ksteps);
-          tc_commit(&t_full[t]);
-        }
+        const uint32_t d = tmem + (uint32_t)t * 256u + (uint32_t)as * 128u;
+        tc_mma_split(d, a_kind ? da_hi : dz_hi, a_kind ? da_lo : dz_lo, db_hi, db_lo, tc_idesc_f16(N), ksteps);
+        tc_commit(&t_full[2 * t + as]);
         tc_commit(&b_empty[s]);
+        if (t == 0) TRACE(2, g * 8 + 3 + t);
         ++g;
       };
       for (long long p = 0; p < my_pairs; ++p) {
@@ -175,16 +202,18 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) nif_tc_fwd_kernel(const Plan p
       const long long b = row0 + r;
       const bool live = b < a.B;
       named_bar_sync(1 + wg, 128);  // this tile's threads are done with the previous zs / xs
-      for (int idx = r; idx < 128 * K; idx += 128) {
-        const int q = idx / K, kk = idx - q * K;
-        zs[kk * 128 + q] = (row0 + q < a.B) ? __ldg(&a.z[(row0 + q) * K + kk]) : 0.f;
+      // every thread stages its own row of z (independent vector loads, conflict-free transposed stores)
+      if ((K & 3) == 0) {
+        for (int k4 = 0; k4 < K; k4 += 4) {
+          const float4 q4 = live ? ldg4(a.z + b * K + k4) : make_float4(0.f, 0.f, 0.f, 0.f);
+          zs[k4 * 128 + r] = q4.x; zs[(k4 + 1) * 128 + r] = q4.y; zs[(k4 + 2) * 128 + r] = q4.z; zs[(k4 + 3) * 128 + r] = q4.w;
+        }
+      } else {
+        for (int kk = 0; kk < K; ++kk) zs[kk * 128 + r] = live ? __ldg(&a.z[b * K + kk]) : 0.f;
       }
       zs[K * 128 + r] = 1.f;
       for (int kk = K1; kk < KP; ++kk) zs[kk * 128 + r] = 0.f;
-      for (int idx = r; idx < 128 * si; idx += 128) {
-        const int q = idx / si, i = idx - q * si;
-        xs[i * 128 + q] = (row0 + q < a.B) ? __ldg(&a.x[(row0 + q) * si + i]) : 0.f;
-      }
+      for (int i = 0; i < si; ++i) xs[i * 128 + r] = live ? __ldg(&a.x[b * si + i]) : 0.f;
       named_bar_sync(1 + wg, 128);
 
       // ---- zt operand tile (used by layer 0 and by every bias-sum chunk) ----
@@ -204,27 +233,29 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) nif_tc_fwd_kernel(const Plan p
       float inv_a = 1.f;  // inverse of the power-of-two scale of this row's h operand tile
 
       // acc[j] (+)= coef * (D1 + D2)[j] for the 64 columns of a small chunk
-      auto drain64 = [&](float (&acc)[64], float coef, bool init) {
+      auto drain64 = [&](uint32_t td, float (&acc)[64], float coef, bool init) {
+        float v1[32], v2[32];
+        tc_ld32(td, v1);
+        tc_ld32(td + 32u, v2);
+        tc_wait_ld();
 #pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-          float v1[32], v2[32];
-          tc_ld32(tm + (uint32_t)(hf * 32), v1);
-          tc_ld32(tm + (uint32_t)(hf * 32) + 128u, v2);
-          tc_wait_ld();
-#pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            const float t = v1[e] + v2[e];
-            acc[hf * 32 + e] = init ? coef * t : fmaf(coef, t, acc[hf * 32 + e]);
-          }
+        for (int e = 0; e < 32; ++e) {
+          acc[e] = init ? coef * v1[e] : fmaf(coef, v1[e], acc[e]);
+          acc[32 + e] = init ? coef * v2[e] : fmaf(coef, v2[e], acc[32 + e]);
         }
       };
-      auto chunk_begin = [&]() {
-        mbar_wait(&t_full[wg], (uint32_t)(g & 1));
+      // accumulator stage g & 1 of this tile: wait until its MMAs have completed; returns its TMEM address
+      auto chunk_begin = [&]() -> uint32_t {
+        if (r == 0) TRACE(wg, g * 4 + 0);
+        mbar_wait(&t_full[2 * wg + (int)(g & 1)], (uint32_t)((g >> 1) & 1));
+        if (r == 0) TRACE(wg, g * 4 + 1);
         tc_fence_after();
+        return tm + (uint32_t)(g & 1) * 128u;
       };
       auto chunk_end = [&]() {
         tc_fence_before();
-        mbar_arrive(&t_empty[wg]);
+        mbar_arrive(&t_empty[2 * wg + (int)(g & 1)]);
+        if (r == 0) TRACE(wg, g * 4 + 2);
         ++g;
       };
 
@@ -301,16 +332,19 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) nif_tc_fwd_kernel(const Plan p
           // layer 0:  pre0[j] = sum_i' xt[i'] * (zt @ X0[i'])[j],  xt = [omega x, 1]
           const float om = plan_omega(pl, 0);
           for (int i = 0; i <= si; ++i) {
-            chunk_begin();
             const float coef = inv_z * __ldg(&invX[i]) * (i < si ? om * xs[i * 128 + r] : 1.f);
-            drain64(acc, coef, i == 0);
+            const uint32_t td = chunk_begin();
+            drain64(td, acc, coef, i == 0);
             chunk_end();
           }
         } else {
           publish_h();
-          chunk_begin();  // bias sum: acc[j] = sum_kappa zt[kappa] C_m[kappa][j]
-          drain64(acc, inv_z * __ldg(&invX[si + m]), true);
-          chunk_end();
+          {
+            const float coef = inv_z * __ldg(&invX[si + m]);
+            const uint32_t td = chunk_begin();  // bias sum: acc[j] = sum_kappa zt[kappa] C_m[kappa][j]
+            drain64(td, acc, coef, true);
+            chunk_end();
+          }
           const float om_inv = plan_omega(pl, m) * inv_a;
           const float* invBm = invB + (m - 1) * KP;
           // per-chunk row coefficients, fetched one chunk ahead (their latency hides behind the accumulator wait)
@@ -322,19 +356,18 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) nif_tc_fwd_kernel(const Plan p
               zo2[0] = zs[(2 * c + 2) * 128 + r] * om_inv * __ldg(&invBm[2 * c + 2]);
               zo2[1] = zs[(2 * c + 3) * 128 + r] * om_inv * __ldg(&invBm[2 * c + 3]);
             }
-            chunk_begin();
+            const uint32_t td = chunk_begin();
 #pragma unroll
-            for (int kl = 0; kl < 2; ++kl) {
+            for (int kl = 0; kl < 2; ++kl) {  // the 64 columns of one latent coordinate, then its contraction
               const float zo = zc2[kl];
+              float v1[32], v2[32];
+              tc_ld32(td + (uint32_t)(kl * 64), v1);
+              tc_ld32(td + (uint32_t)(kl * 64 + 32), v2);
+              tc_wait_ld();
 #pragma unroll
-              for (int hf = 0; hf < 2; ++hf) {  // 32 columns at a time: D1 + D2, then the latent contraction
-                float v1[32], v2[32];
-                const uint32_t col = (uint32_t)(kl * 64 + hf * 32);
-                tc_ld32(tm + col, v1);
-                tc_ld32(tm + col + 128u, v2);
-                tc_wait_ld();
-#pragma unroll
-                for (int e = 0; e < 32; ++e) acc[hf * 32 + e] = fmaf(zo, v1[e] + v2[e], acc[hf * 32 + e]);
+              for (int e = 0; e < 32; ++e) {
+                acc[e] = fmaf(zo, v1[e], acc[e]);
+                acc[32 + e] = fmaf(zo, v2[e], acc[32 + e]);
               }
             }
             chunk_end();
@@ -348,21 +381,20 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) nif_tc_fwd_kernel(const Plan p
       {
         const float* CL = C_all + (long long)(H + 1) * K1 * 64;
         for (int q = 0; q < NLC; ++q) {
-          chunk_begin();
           const float sL = inv_a * __ldg(&invX[si + 1 + H + q]);
+          const uint32_t td = chunk_begin();
           for (int cl = 0; cl < LPC; ++cl) {
             const int c = LPC * q + cl;
             float y = 0.f;
             for (int k0 = 0; k0 < KZ; k0 += 16) {
-              float v1[16], v2[16];
-              tc_ld16(tm + (uint32_t)(cl * KZ + k0), v1);
-              tc_ld16(tm + (uint32_t)(cl * KZ + k0) + 128u, v2);
+              float v1[16];
+              tc_ld16(td + (uint32_t)(cl * KZ + k0), v1);
               tc_wait_ld();
 #pragma unroll
               for (int e = 0; e < 16; ++e) {
                 const int kk = k0 + e;
                 if (kk < K1 && c < so)
-                  y = fmaf(zs[kk * 128 + r], fmaf(sL, v1[e] + v2[e], __ldg(&CL[(long long)kk * 64 + c])), y);
+                  y = fmaf(zs[kk * 128 + r], fmaf(sL, v1[e], __ldg(&CL[(long long)kk * 64 + c])), y);
               }
             }
             if (live && c < so) a.u[b * so + c] = y;

@@ -1,0 +1,45 @@
+"""Timeline of the first tile pair of nif_tc_fwd_kernel on CTA 0 (needs a -DNIF_TRACE build of the library):
+    make -C nif_b200/csrc clean && make -C nif_b200/csrc -j8 EXTRA=-DNIF_TRACE && python tools/tc_trace.py
+"""
+import ctypes as C
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, '.')
+from oracle import nif_oracle as O
+from nif_b200 import _lib
+from nif_b200.ops import FusedShapeNet
+
+dev = torch.device('cuda:0')
+B = 65536
+spec = O.Spec(variant="siren", pi=1, si=2, so=1, n=64, l=4, K=32, n_st=64, l_st=4, p_act="swish", omega0=30.0, weight_init_factor=0.01)
+prm = O.init_params(spec, 0)
+g = torch.Generator().manual_seed(0)
+z = (torch.rand(B, 32, generator=g) - 0.5).to(dev)
+x = (torch.rand(B, 2, generator=g) * 2 - 1).to(dev)
+eng = FusedShapeNet("siren", 2, 1, 64, 4, 32, omega0=30.0, compute="fp16x3")
+packed = eng.pack(prm["HyperLinearForSIREN_w"].to(dev), prm["HyperLinearForSIREN_b"].to(dev))
+L = _lib.lib()
+host = np.zeros((4, 2048), dtype=np.int64)
+cnt = np.zeros(4, dtype=np.int32)
+for it in range(2):
+    eng.forward(z, x, packed, save=True)
+    torch.cuda.synchronize()
+    L.nif_debug_read_trace(host.ctypes.data_as(C.c_void_p), cnt.ctypes.data_as(C.c_void_p))
+ev = []
+names = {0: "epi0", 1: "epi1", 2: "mma", 3: "prod"}
+for role in range(4):
+    for i in range(0, cnt[role], 2):
+        ev.append((int(host[role, i + 1]), names[role], int(host[role, i])))
+ev.sort()
+t0 = ev[0][0]
+sub = {"epi": {0: "wait_full", 1: "got_full", 2: "arrived_empty"}, "mma": {0: "got_b_full", 1: "got_empty0", 2: "got_empty1", 3: "committed0", 4: "committed1"}}
+for t, who, tag in ev[:int(sys.argv[1]) if len(sys.argv) > 1 else 400]:
+    if who.startswith("epi"):
+        print(f"{t - t0:8d} {who} chunk {tag // 4:3d} {sub['epi'][tag % 4]}")
+    elif who == "mma":
+        print(f"{t - t0:8d} {who}  chunk {tag // 8:3d} {sub['mma'][tag % 8]}")
+    else:
+        print(f"{t - t0:8d} {who} chunk {tag:3d} stage free, load issued")
