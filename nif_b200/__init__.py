@@ -11,9 +11,10 @@ from .ops import FusedShapeNet, adam_step, fused_shapenet  # noqa: F401
 __all__ = ["FusedShapeNet", "fused_shapenet", "adam_step"]
 
 from .model import NIF, NIFMultiScale  # noqa: E402,F401
-from .keras_like import Adam, Callback, Dataset, LearningRateScheduler, Model  # noqa: E402,F401
+from .keras_like import Adam, Callback, Dataset, LearningRateScheduler, Model, SobolevMSE  # noqa: E402,F401
+from .layers import JacobianLayer  # noqa: E402,F401
 from .distributed import DataParallel  # noqa: E402,F401
 from . import data, demo  # noqa: E402,F401
 
 __all__ += ["NIF", "NIFMultiScale", "Adam", "Callback", "Dataset", "LearningRateScheduler", "Model",
-            "DataParallel", "data", "demo"]
+            "DataParallel", "data", "demo", "SobolevMSE", "JacobianLayer"]

@@ -6,7 +6,10 @@ int nif_pack_impl(const Plan& pl, long long G, const float* w_h, const float* b_
 int nif_forward_impl(const Plan& pl, long long G, long long B, const float* z, const float* x, int x_shared,
                      const float* packed, float* u, float* save, cudaStream_t st);
 int nif_tangent_impl(const Plan& pl, long long B, const float* z, const float* x, const float* packed, int n_dir,
-                     const float* zdot, const float* xdot, float* u, float* udot, cudaStream_t st);
+                     const float* zdot, const float* xdot, float* u, float* udot, float* save, cudaStream_t st);
+int nif_sobolev_backward_impl(const Plan& pl, long long B, const float* z, const float* x, const float* xdot,
+                              const float* packed, const float* save, const float* du, const float* dud, float* dw_h,
+                              float* db_h, float beta, float* dz, float* ws, cudaStream_t st);
 int nif_given_w_impl(const Plan& pl, long long B, const float* x, const float* w, float* u, cudaStream_t st);
 int nif_backward_impl(const Plan& pl, long long B, const float* z, const float* x, const float* packed,
                       const float* save, const float* du, float* dw_h, float* db_h, float beta, float* dz,
@@ -98,7 +101,49 @@ extern "C" int nif_forward_tangent(const nif_desc_t* d, int64_t B, const float* 
   NIF_REQUIRE_PTR(udot);
   NIF_OPTIONAL_PTR(zdot);
   NIF_OPTIONAL_PTR(xdot);
-  return nif_tangent_impl(pl, B, z, x, packed, n_dir, zdot, xdot, u, udot, static_cast<cudaStream_t>(stream));
+  return nif_tangent_impl(pl, B, z, x, packed, n_dir, zdot, xdot, u, udot, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int nif_sobolev_query(const nif_desc_t* d, int64_t B, int64_t* save_floats_per_row, int64_t* ws_floats) {
+  Plan pl;
+  int rc = nif_make_plan(d, &pl);
+  if (rc) return rc;
+  if (B < 0) { nif_set_error("nif_sobolev_query: B=%lld", (long long)B); return NIF_E_BAD_ARG; }
+  if (save_floats_per_row) *save_floats_per_row = 4LL * (pl.H + 1) * pl.NP;
+  if (ws_floats) *ws_floats = nif_grad_ws_layout(pl, B).total + (long long)(pl.H + 1) * B * pl.NP;
+  return NIF_OK;
+}
+
+extern "C" int nif_forward_tangent_save(const nif_desc_t* d, int64_t B, const float* z, const float* x,
+                                        const float* packed, int32_t n_dir, const float* zdot, const float* xdot,
+                                        float* u, float* udot, float* save, void* stream) {
+  Plan pl;
+  int rc = nif_make_plan(d, &pl);
+  if (rc) return rc;
+  if (B < 0 || n_dir < 1 || n_dir > NIF_MAX_DIR) {
+    nif_set_error("nif_forward_tangent_save: B=%lld n_dir=%d (max %d)", (long long)B, n_dir, NIF_MAX_DIR);
+    return NIF_E_BAD_ARG;
+  }
+  if (B == 0) return NIF_OK;
+  if (pl.K > 0) NIF_REQUIRE_PTR(z);
+  NIF_REQUIRE_PTR(x); NIF_REQUIRE_PTR(packed); NIF_REQUIRE_PTR(u); NIF_REQUIRE_PTR(udot); NIF_REQUIRE_PTR(xdot);
+  NIF_REQUIRE_PTR(save); NIF_OPTIONAL_PTR(zdot);
+  return nif_tangent_impl(pl, B, z, x, packed, n_dir, zdot, xdot, u, udot, save, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int nif_sobolev_backward(const nif_desc_t* d, int64_t B, const float* z, const float* x, const float* xdot,
+                                    const float* packed, const float* save, const float* du, const float* dudot,
+                                    float* dw_h, float* db_h, float beta, float* dz, float* ws, void* stream) {
+  Plan pl;
+  int rc = nif_make_plan(d, &pl);
+  if (rc) return rc;
+  if (B < 0) { nif_set_error("nif_sobolev_backward: B=%lld", (long long)B); return NIF_E_BAD_ARG; }
+  if (B == 0) return NIF_OK;
+  if (pl.K > 0) { NIF_REQUIRE_PTR(z); NIF_REQUIRE_PTR(dw_h); NIF_REQUIRE_PTR(dz); }
+  NIF_REQUIRE_PTR(x); NIF_REQUIRE_PTR(xdot); NIF_REQUIRE_PTR(packed); NIF_REQUIRE_PTR(save); NIF_REQUIRE_PTR(du);
+  NIF_REQUIRE_PTR(dudot); NIF_REQUIRE_PTR(db_h); NIF_REQUIRE_PTR(ws);
+  return nif_sobolev_backward_impl(pl, B, z, x, xdot, packed, save, du, dudot, dw_h, db_h, beta, dz, ws,
+                                   static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int nif_forward_given_w(const nif_desc_t* d, int64_t B, const float* x, const float* w, float* u,

@@ -21,6 +21,13 @@ struct BwdArgs {
   const float *z, *x, *packed, *save, *du;
   float* da;  // [(H+1)][B][NP]
   float* dz;  // [B][K]
+  // reverse-over-forward (Sobolev training); all null / 0 for the plain reverse pass:
+  const float* h_stash;  // the h_m slots this pass pairs with its da_m (save, or the tangent activations h'_m)
+  const float* e_stash;  // [H+1] slots e_m; with ext_out: ext_out[m] = dh_{m+1} * e_m (tangent-adjoint pass)
+  float* ext_out;
+  const float* ext_add;  // [H+1] slots added to da_m (primal-adjoint pass consumes what the tangent pass wrote)
+  int no_bias;           // tangent-adjoint pass: bias rows do not enter pre_m', drop their dz terms
+  int dz_accumulate;     // dz += instead of =
 };
 
 template <class C>
@@ -132,7 +139,7 @@ __global__ void __launch_bounds__(C::NT, 1) nif_bwd_data_kernel(const Plan pl, c
         if (b < a.B) a.da[(long long)(H + 1) * a.B * NP + b * NP + c] = v;  // operand of the last matrix's gradient
       }
       __syncthreads();
-      const float* hL = a.save + (long long)H * a.B * NP;
+      const float* hL = a.h_stash + (long long)H * a.B * NP;
 #pragma unroll
       for (int r = 0; r < MP; ++r)
 #pragma unroll
@@ -173,7 +180,7 @@ __global__ void __launch_bounds__(C::NT, 1) nif_bwd_data_kernel(const Plan pl, c
     } else {
       const float* ML = a.packed + pl.off_ML;
       const float* CL = C_all + (long long)(H + 1) * K1 * NP;
-      const float* hL = a.save + (long long)H * a.B * NP;  // h_{H+1}
+      const float* hL = a.h_stash + (long long)H * a.B * NP;  // h_{H+1}
 #pragma unroll
       for (int r = 0; r < MP; ++r)
 #pragma unroll
@@ -197,7 +204,7 @@ __global__ void __launch_bounds__(C::NT, 1) nif_bwd_data_kernel(const Plan pl, c
 #pragma unroll
             for (int r = 0; r < MP; ++r) tmp[r][c] = fmaf(dyv[r], w, tmp[r][c]);
           }
-          if (tj == 0) {
+          if (tj == 0 && !a.no_bias) {
             const float cb = __ldg(&CL[(long long)kk * NP + cc]);
 #pragma unroll
             for (int r = 0; r < MP; ++r) s[r] = fmaf(cb, dyv[r], s[r]);
@@ -239,6 +246,15 @@ __global__ void __launch_bounds__(C::NT, 1) nif_bwd_data_kernel(const Plan pl, c
           daf[r][gj * 4 + 1] = acc[r][gj * 4 + 1] * dv.y;
           daf[r][gj * 4 + 2] = acc[r][gj * 4 + 2] * dv.z;
           daf[r][gj * 4 + 3] = acc[r][gj * 4 + 3] * dv.w;
+          if (a.ext_add && brow[r] < a.B) {  // + dh'_{m+1} * e_m, written by the tangent-adjoint pass
+            const float4 xv = ldg4(&a.ext_add[(long long)m * a.B * NP + brow[r] * NP + gj * C::JSTR + tj * 4]);
+            daf[r][gj * 4 + 0] += xv.x; daf[r][gj * 4 + 1] += xv.y; daf[r][gj * 4 + 2] += xv.z; daf[r][gj * 4 + 3] += xv.w;
+          }
+          if (a.ext_out && brow[r] < a.B) {
+            const float4 ev = ldg4(&a.e_stash[(long long)m * a.B * NP + brow[r] * NP + gj * C::JSTR + tj * 4]);
+            *reinterpret_cast<float4*>(&a.ext_out[(long long)m * a.B * NP + brow[r] * NP + gj * C::JSTR + tj * 4]) =
+                make_float4(acc[r][gj * 4 + 0] * ev.x, acc[r][gj * 4 + 1] * ev.y, acc[r][gj * 4 + 2] * ev.z, acc[r][gj * 4 + 3] * ev.w);
+          }
           if (brow[r] < a.B)
             *reinterpret_cast<float4*>(&dag[brow[r] * NP + gj * C::JSTR + tj * 4]) =
                 make_float4(daf[r][gj * 4], daf[r][gj * 4 + 1], daf[r][gj * 4 + 2], daf[r][gj * 4 + 3]);
@@ -271,7 +287,7 @@ __global__ void __launch_bounds__(C::NT, 1) nif_bwd_data_kernel(const Plan pl, c
           }
         }
         __syncthreads();
-        const float* hm = a.save + (long long)(m - 1) * a.B * NP;  // h_m
+        const float* hm = a.h_stash + (long long)(m - 1) * a.B * NP;  // h_m
         for (int kk = 0; kk < K1; ++kk) {
           float tmp[MP][MJ];
 #pragma unroll
@@ -303,7 +319,7 @@ __global__ void __launch_bounds__(C::NT, 1) nif_bwd_data_kernel(const Plan pl, c
                 const float tv = om * tmp[r][c];
                 acc[r][c] = fmaf(zk, tv, acc[r][c]);
                 sr = fmaf(tv, hvv[f], sr);
-                sr = fmaf(cvv[f], dact[act_idx<C>(col_of<C>(tj, c), row_of<C>(tp, r))], sr);
+                if (!a.no_bias) sr = fmaf(cvv[f], dact[act_idx<C>(col_of<C>(tj, c), row_of<C>(tp, r))], sr);
               }
             }
             s[r] = sr;
@@ -321,7 +337,7 @@ __global__ void __launch_bounds__(C::NT, 1) nif_bwd_data_kernel(const Plan pl, c
 #pragma unroll
           for (int c = 0; c < MJ; ++c) {
             const int j = col_of<C>(tj, c);
-            const float cb = __ldg(&C_all[((long long)0 * K1 + kk) * NP + j]);
+            const float cb = a.no_bias ? 0.f : __ldg(&C_all[((long long)0 * K1 + kk) * NP + j]);
             float wv[NIF_MAX_SI];
 #pragma unroll
             for (int i = 0; i < NIF_MAX_SI; ++i) wv[i] = (i < si) ? __ldg(&M0[((long long)kk * si + i) * NP + j]) : 0.f;
@@ -342,7 +358,7 @@ __global__ void __launch_bounds__(C::NT, 1) nif_bwd_data_kernel(const Plan pl, c
     for (int idx = tid; idx < TB * K; idx += NT) {
       const int p = idx / K, kk = idx - p * K;
       const long long b = row0 + p;
-      if (b < a.B) a.dz[b * K + kk] = dzs[kk * TB + p];
+      if (b < a.B) a.dz[b * K + kk] = a.dz_accumulate ? a.dz[b * K + kk] + dzs[kk * TB + p] : dzs[kk * TB + p];
     }
     __syncthreads();
   }
@@ -514,6 +530,7 @@ struct EdgeArgs {
   int S, Q;
   const float *z, *x, *save, *da, *du;
   float* part;  // [S][K+1][Q]
+  int no_bias;  // tangent-adjoint pass: the bias-row columns are zero
 };
 
 // Register-tiled batch reduction: a thread owns 4 columns x 4 latent coordinates; a CTA owns 64 columns x KG groups
@@ -552,9 +569,9 @@ __global__ void __launch_bounds__(16 * KG * RS) nif_bwd_edge_kernel(const Plan p
     if (fl < FL && r < a.Q) {
       if (r < (H + 1) * NP) {
         const int m = r / NP, j = r % NP;
-        Ap = a.da + (long long)m * a.B * NP + j; sA = NP;
+        if (!a.no_bias) { Ap = a.da + (long long)m * a.B * NP + j; sA = NP; }
       } else if ((r -= (H + 1) * NP) < so) {
-        Ap = a.du + r; sA = so;
+        if (!a.no_bias) { Ap = a.du + r; sA = so; }
       } else if ((r -= so) < si * NP) {
         const int i = r / NP, j = r % NP;
         Ap = a.da + j; sA = NP; Bp = a.x + i; sB = si; scale = plan_omega(pl, 0);
@@ -770,7 +787,7 @@ static cudaError_t launch_edge(const Plan& pl, const EdgeArgs& e, const GradWs& 
 // hidden-matrix GEMM (CUDA cores) + thin terms + un-packing, for stashes whose da_m already sit in ws.
 // Used by the trunk, whose parameter gradients are the same batch reductions with zt = [1].
 int nif_weight_grads_impl(const Plan& pl, long long B, const float* z, const float* x, const float* save, const float* du,
-                          float* dw_h, float* db_h, float beta, float* ws, cudaStream_t st) {
+                          float* dw_h, float* db_h, float beta, float* ws, cudaStream_t st, int no_bias = 0) {
   const GradWs w = nif_grad_ws_layout(pl, B);
   const int Hm = pl.H + pl.wide_last;
   if (Hm > 0) {
@@ -794,7 +811,7 @@ int nif_weight_grads_impl(const Plan& pl, long long B, const float* z, const flo
   }
   EdgeArgs e;
   e.B = B; e.rows_per_split = w.rows_e; e.S = w.S_e; e.Q = w.Q;
-  e.z = z; e.x = x; e.save = save; e.da = ws + w.da; e.du = du; e.part = ws + w.part_e;
+  e.z = z; e.x = x; e.save = save; e.da = ws + w.da; e.du = du; e.part = ws + w.part_e; e.no_bias = no_bias;
   NIF_CUDA_CHECK(launch_edge(pl, e, w, st));
   return nif_unpack_grad_impl(pl, w.S_h, ws + w.part_h, w.S_e, ws + w.part_e, w.Q, dw_h, db_h, beta, st);
 }
@@ -809,6 +826,7 @@ int nif_backward_impl(const Plan& pl, long long B, const float* z, const float* 
   a.z = z; a.x = x; a.packed = packed; a.save = save; a.du = du;
   a.da = ws + w.da;
   a.dz = dz;
+  a.h_stash = save; a.e_stash = nullptr; a.ext_out = nullptr; a.ext_add = nullptr; a.no_bias = 0; a.dz_accumulate = 0;
   int rc = NIF_E_UNSUPPORTED;
   if (pl.tc)  // tensor-core data pass; shapes it does not cover use the CUDA-core kernel below
     rc = nif_tc_bwd_data_impl(pl, B, z, x, packed, save, du, ws + w.da, dz, reinterpret_cast<unsigned*>(ws + w.maxes), st);
@@ -842,10 +860,58 @@ int nif_backward_impl(const Plan& pl, long long B, const float* z, const float* 
   {
     EdgeArgs e;
     e.B = B; e.rows_per_split = w.rows_e; e.S = w.S_e; e.Q = w.Q;
-    e.z = z; e.x = x; e.save = save; e.da = ws + w.da; e.du = du; e.part = ws + w.part_e;
+    e.z = z; e.x = x; e.save = save; e.da = ws + w.da; e.du = du; e.part = ws + w.part_e; e.no_bias = 0;
     NIF_CUDA_CHECK(launch_edge(pl, e, w, st));
   }
   return nif_unpack_grad_impl(pl, S_used, ws + w.part_h, w.S_e, ws + w.part_e, w.Q, dw_h, db_h, beta, st);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Reverse-over-forward pass for Sobolev training (JacobianLayer inside the loss, tutorial/8 cell 20;
+// nif/layers/gradient.py:207-231 differentiated once more by Keras' tape).  One tangent direction xdot on the ShapeNet
+// inputs (z' = 0).  With a_m the pre-activations, a_m' their tangents, and seeds du = dL/du, dud = dL/du':
+//   tangent adjoint:  da_m' = dh'_{m+1} * d_m                                   (same weights, same d_m)
+//   primal adjoint :  da_m  = dh_{m+1}  * d_m + dh'_{m+1} * e_m,   e_m = alpha act''(a_m) a_m'
+//   dW_m = omega (h_m (x) da_m + h_m' (x) da_m'),  dC_m = da_m,  dz = dz(primal pass) + dz(tangent pass, no bias rows)
+// i.e. two passes of the plain reverse machinery: first the tangent adjoint (stash slots h', inputs xdot, bias rows
+// dropped; it leaves X_m = dh'_{m+1} * e_m in the workspace), then the primal adjoint (adds X_m), each followed by the
+// batch-reduction kernels; the second pass accumulates.  Runs on the fp32 CUDA-core kernels.
+// ws: nif_grad_ws_layout(pl, B).total + (H+1) * B * NP floats.
+// ---------------------------------------------------------------------------------------------------
+int nif_sobolev_backward_impl(const Plan& pl, long long B, const float* z, const float* x, const float* xdot,
+                              const float* packed, const float* save, const float* du, const float* dud, float* dw_h,
+                              float* db_h, float beta, float* dz, float* ws, cudaStream_t st) {
+  if (B <= 0) return NIF_OK;
+  const GradWs w = nif_grad_ws_layout(pl, B);
+  float* X = ws + w.total;
+  const long long slot = B * (long long)pl.NP;
+  const float* h_dot = save + 2LL * (pl.H + 1) * slot;
+  const float* e_st = save + 3LL * (pl.H + 1) * slot;
+  for (int pass = 0; pass < 2; ++pass) {
+    BwdArgs a;
+    a.B = B;
+    a.z = z; a.packed = packed; a.save = save;
+    a.da = ws + w.da;
+    a.dz = dz;
+    if (pass == 0) {  // tangent adjoint
+      a.x = xdot; a.du = dud; a.h_stash = h_dot; a.e_stash = e_st; a.ext_out = X; a.ext_add = nullptr;
+      a.no_bias = 1; a.dz_accumulate = 0;
+    } else {          // primal adjoint
+      a.x = x; a.du = du; a.h_stash = save; a.e_stash = nullptr; a.ext_out = nullptr; a.ext_add = X;
+      a.no_bias = 0; a.dz_accumulate = 1;
+    }
+    int rc;
+    switch (pl.NP) {
+      case 32: a.total_tiles = (B + Cfg32::TB - 1) / Cfg32::TB; rc = launch_bwd_data<Cfg32>(pl, a, st); break;
+      case 64: a.total_tiles = (B + Cfg64::TB - 1) / Cfg64::TB; rc = launch_bwd_data<Cfg64>(pl, a, st); break;
+      case 128: a.total_tiles = (B + Cfg128::TB - 1) / Cfg128::TB; rc = launch_bwd_data<Cfg128>(pl, a, st); break;
+      default: nif_set_error("unsupported padded width %d", pl.NP); return NIF_E_UNSUPPORTED;
+    }
+    if (rc != NIF_OK) return rc;
+    rc = nif_weight_grads_impl(pl, B, z, a.x, a.h_stash, a.du, dw_h, db_h, pass == 0 ? beta : 1.0f, ws, st, a.no_bias);
+    if (rc != NIF_OK) return rc;
+  }
+  return NIF_OK;
 }
 
 int nif_mse_backward_impl(const Plan& pl, long long B, const float* z, const float* x, const float* packed,

@@ -126,6 +126,16 @@ __device__ __forceinline__ void act_fd(int act, float v, float& f, float& d) {
     default: f = v; d = 1.0f; break;
   }
 }
+// second derivative, given v and the already computed f = act(v), d = act'(v)  (reverse-over-forward pass)
+__device__ __forceinline__ float act_dd(int act, float v, float f, float d) {
+  switch (act) {
+    case NIF_ACT_SINE: return -f;
+    case NIF_ACT_SWISH: { const float sg = sigmoidf_(v); return sg * (1.0f - sg) * (2.0f + v * (1.0f - 2.0f * sg)); }
+    case NIF_ACT_TANH: return -2.0f * f * d;
+    case NIF_ACT_SIGMOID: return d * (1.0f - 2.0f * f);
+    default: return 0.0f;  // relu, linear
+  }
+}
 // four at a time, out of line: ONE copy of the activation switch per kernel instead of one per unrolled element
 struct ActFd4 { float4 f, d; };
 static __device__ __noinline__ ActFd4 act_fd4v(int act, float4 v) {

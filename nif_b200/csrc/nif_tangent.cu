@@ -14,6 +14,10 @@ struct TanArgs {
   long long B, total_tiles;
   const float *z, *x, *packed, *zdot, *xdot;  // zdot [ND][B][K], xdot [ND][B][si] (either may be null)
   float *u, *udot;                            // udot [ND][B][so]
+  // optional stash for the reverse-over-forward pass (Sobolev training), slots of [B][NP]:
+  //   [0, H]            h_{m+1}                       [H+1, 2H+1]     d_m = alpha act'(pre_m)
+  //   [2H+2, 3H+2]      h'_{m+1} of direction 0       [3H+3, 4H+3]    e_m = alpha act''(pre_m) pre_m' of direction 0
+  float* save;
 };
 
 using TCfg32 = TileCfg<32, 128, 1, 1>;
@@ -155,6 +159,30 @@ __global__ void __launch_bounds__(C::NT, 1) nif_tangent_kernel(const Plan pl, co
 #pragma unroll
           for (int e = 0; e < 4; ++e) { outv[0][r][c4 + e] = f4[e]; outv[1][r][c4 + e] = d4[e]; }
         }
+      if (a.save) {  // d_m and e_m (before the residual bookkeeping below overwrites outv)
+        float* sd = a.save + (long long)(H + 1 + m) * a.B * NP;
+        float* se = a.save + (long long)(3 * (H + 1) + m) * a.B * NP;
+#pragma unroll
+        for (int r = 0; r < MP; ++r) {
+          const long long b = row0 + row_of<C>(tp, r);
+          if (b < a.B) {
+#pragma unroll
+            for (int gj = 0; gj < C::GJ; ++gj) {
+              float dq[4], eq[4];
+#pragma unroll
+              for (int f = 0; f < 4; ++f) {
+                const int c = gj * 4 + f;
+                const bool livec = col_of<C>(tj, c) < n;
+                dq[f] = livec ? alpha * outv[1][r][c] : 0.f;
+                eq[f] = livec ? alpha * act_dd(pl.act, acc[0][r][c], outv[0][r][c], outv[1][r][c]) * acc[1][r][c] : 0.f;
+              }
+              const int j0 = gj * C::JSTR + tj * 4;
+              *reinterpret_cast<float4*>(&sd[b * NP + j0]) = make_float4(dq[0], dq[1], dq[2], dq[3]);
+              *reinterpret_cast<float4*>(&se[b * NP + j0]) = make_float4(eq[0], eq[1], eq[2], eq[3]);
+            }
+          }
+        }
+      }
 #pragma unroll
       for (int r = 0; r < MP; ++r)
 #pragma unroll
@@ -174,6 +202,22 @@ __global__ void __launch_bounds__(C::NT, 1) nif_tangent_kernel(const Plan pl, co
             outv[s][r][c] = o;
           }
         }
+      if (a.save) {  // h_{m+1} and h'_{m+1}
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          float* sh = a.save + (long long)(s * 2 * (H + 1) + m) * a.B * NP;
+#pragma unroll
+          for (int r = 0; r < MP; ++r) {
+            const long long b = row0 + row_of<C>(tp, r);
+            if (b < a.B) {
+#pragma unroll
+              for (int gj = 0; gj < C::GJ; ++gj)
+                *reinterpret_cast<float4*>(&sh[b * NP + gj * C::JSTR + tj * 4]) =
+                    make_float4(outv[s][r][gj * 4], outv[s][r][gj * 4 + 1], outv[s][r][gj * 4 + 2], outv[s][r][gj * 4 + 3]);
+            }
+          }
+        }
+      }
 #pragma unroll
       for (int s = 0; s < NS; ++s)
 #pragma unroll
@@ -353,7 +397,7 @@ static int dispatch_tan(const Plan& pl, const TanArgs& a, cudaStream_t st) {
 }
 
 int nif_tangent_impl(const Plan& pl, long long B, const float* z, const float* x, const float* packed, int n_dir,
-                     const float* zdot, const float* xdot, float* u, float* udot, cudaStream_t st) {
+                     const float* zdot, const float* xdot, float* u, float* udot, float* save, cudaStream_t st) {
   // directions are processed two at a time (the primal is recomputed per pair)
   for (int d0 = 0; d0 < n_dir; d0 += 2) {
     TanArgs a;
@@ -364,6 +408,7 @@ int nif_tangent_impl(const Plan& pl, long long B, const float* z, const float* x
     a.xdot = xdot ? xdot + (long long)d0 * B * pl.si : nullptr;
     a.u = u;
     a.udot = udot + (long long)d0 * B * pl.so;
+    a.save = d0 == 0 ? save : nullptr;  // the stash describes direction 0
     const int nd = (n_dir - d0) >= 2 ? 2 : 1;
     const int rc = nd == 2 ? dispatch_tan<2>(pl, a, st) : dispatch_tan<1>(pl, a, st);
     if (rc != NIF_OK) return rc;

@@ -52,6 +52,24 @@ class Adam:
                       self.epsilon, l1, l2, g_scale)
 
 
+class SobolevMSE:
+    """The `Sobolov_MSE` loss of tutorial 8 (tutorial/8_NIF_with_Sobolov_training.ipynb:815-820) for a model built
+    with JacobianLayer.as_model(): per row  sum_{c in value_cols} (t_c - p_c)^2 + coef_grad * sum_{c in grad_cols}
+    (t_c - p_c)^2, averaged over the batch.  Columns index the concatenated output [y | dy/dx flattened]; the
+    tutorial uses value_cols=[0], grad_cols=[2] (u and du/dx; du/dt is only monitored).  Every grad column must be a
+    derivative with respect to the SAME ShapeNet input (that is what the reverse-over-forward kernels differentiate)."""
+
+    def __init__(self, coef_grad=1e-3, value_cols=(0,), grad_cols=(2,)):
+        self.coef_grad = float(coef_grad)
+        self.value_cols = [int(c) for c in value_cols]
+        self.grad_cols = [int(c) for c in grad_cols]
+
+    def __call__(self, y_true, y_pred):
+        sd = ((y_true[:, self.value_cols] - y_pred[:, self.value_cols]) ** 2).sum(-1)
+        sg = ((y_true[:, self.grad_cols] - y_pred[:, self.grad_cols]) ** 2).sum(-1)
+        return (sd + self.coef_grad * sg).mean()
+
+
 class Callback:
     model = None
 
@@ -190,14 +208,16 @@ class Model:
     @property
     def inputs(self):
         n = self.net
-        return {"full": [("input_tot", n.pi_dim + n.si_dim)], "p_to_w": [("input_p_to_w", n.pi_dim)],
+        return {"full": [("input_tot", n.pi_dim + n.si_dim)], "jacobian": [("input_tot", n.pi_dim + n.si_dim)],
+                "p_to_w": [("input_p_to_w", n.pi_dim)],
                 "p_to_lr": [("input_p_to_lr", n.pi_dim)], "lr_to_w": [("input_lr_to_w", n.pi_hidden)],
                 "x_to_u_given_w": [("input_x_to_u_given_w", n.si_dim), ("input_w_and_b_from_pnet", n.po_dim)]}[self.kind]
 
     def count_params(self) -> int:
         n = self.net
         last = n.pi_hidden * n.po_dim + n.po_dim
-        return {"full": n.count_params(), "p_to_w": n.count_params(), "p_to_lr": n.count_params() - last,
+        return {"full": n.count_params(), "jacobian": n.count_params(), "p_to_w": n.count_params(),
+                "p_to_lr": n.count_params() - last,
                 "lr_to_w": last, "x_to_u_given_w": 0}[self.kind]
 
     def summary(self, print_fn=print):
@@ -238,6 +258,9 @@ class Model:
             z = self._latent_nograd(inp[:, : n.pi_dim])
             xs = inp[:, n.pi_dim: n.pi_dim + n.si_dim].contiguous()
             return n.engine.forward(z.contiguous(), xs, self._packed_weights())
+        if self.kind == "jacobian":
+            u, J = self._jacobian_forward(self._dev(x))
+            return torch.cat([u, J.reshape(u.shape[0], -1)], -1)
         if self.kind == "p_to_lr":
             return self._latent_nograd(self._dev(x))
         if self.kind == "p_to_w":
@@ -252,6 +275,37 @@ class Model:
 
     def __call__(self, x, training=False):
         return self._forward_batch(x)
+
+    @torch.no_grad()
+    def _jacobian_forward(self, inp: torch.Tensor, y_index=None, x_index=None):
+        """(y, J[b,a,c] = dy[b, y_index[a]] / d input[b, x_index[c]]) with forward-mode tangents: one direction per
+        requested input column; directions on ParameterNet inputs carry the trunk tangent of the latent code
+        (JacobianLayer, nif/layers/gradient.py:36-49, 207-231)."""
+        n = self.net
+        y_index = self.jac_y if y_index is None else y_index
+        x_index = self.jac_x if x_index is None else x_index
+        B = inp.shape[0]
+        p_in = inp[:, : n.pi_dim].contiguous()
+        xs = inp[:, n.pi_dim: n.pi_dim + n.si_dim].contiguous()
+        nd = len(x_index)
+        zdot = torch.zeros(nd, B, n.pi_hidden, device=inp.device)
+        xdot = torch.zeros(nd, B, n.si_dim, device=inp.device)
+        z = None
+        for d, c in enumerate(x_index):
+            if c < n.pi_dim:
+                e = torch.zeros_like(p_in)
+                e[:, c] = 1.0
+                z, zd = torch.func.jvp(n._latent, (p_in,), (e,))
+                zdot[d] = zd
+            elif c < n.pi_dim + n.si_dim:
+                xdot[d, :, c - n.pi_dim] = 1.0
+            else:
+                raise IndexError(f"x_index {c} outside the {n.pi_dim + n.si_dim} model inputs")
+        if z is None:
+            z = self._latent_nograd(p_in)
+        u, udot = n.engine.forward_tangent(z.contiguous(), xs, self._packed_weights(), zdot, xdot)  # udot [nd, B, so]
+        J = udot.permute(1, 2, 0)[:, y_index, :]  # [B, |y|, |x|]
+        return u, J.contiguous()
 
     def predict(self, x, batch_size=None, verbose=0, **_kw) -> np.ndarray:
         """Keras predict: batched forward, numpy out.  (Keras' default batch of 32 only affects speed;
@@ -285,13 +339,17 @@ class Model:
 
     # ---- training -----------------------------------------------------------------------------------
     def compile(self, optimizer=None, loss="mse", metrics=None, **_kw):
-        if self.kind != "full":
+        if self.kind == "jacobian":
+            if not isinstance(loss, SobolevMSE):
+                raise NifError("a JacobianLayer model trains with nif_b200.SobolevMSE (tutorial 8's Sobolov_MSE)")
+            self._sobolev_plan = self._plan_sobolev(loss)
+        elif self.kind != "full":
             raise NifError("only the full model is trainable")
         if optimizer is None:
             optimizer = Adam()
         if not isinstance(optimizer, Adam):
             raise NifError("nif_b200 ships Adam (tf.keras semantics); other optimisers are outside the hot path")
-        if not (loss in ("mse", "mean_squared_error") or callable(loss)):
+        if not (isinstance(loss, str) and loss in ("mse", "mean_squared_error") or callable(loss)):
             raise NifError("loss must be 'mse' or a callable(y_true, y_pred) -> scalar tensor")
         self.optimizer, self.loss = optimizer, loss
         self.metrics_fns = list(metrics or [])
@@ -305,6 +363,8 @@ class Model:
 
     def _train_step(self, inp: torch.Tensor, tgt: torch.Tensor, sw: Optional[torch.Tensor],
                     global_batch: Optional[int]) -> torch.Tensor:
+        if self.kind == "jacobian":
+            return self._train_step_sobolev(inp, tgt, global_batch)
         n = self.net
         eng = n.engine
         B = inp.shape[0]
@@ -348,6 +408,68 @@ class Model:
         l1, l2 = n._kernel_regulariser()
         self.optimizer.apply(n.theta, n.grad, l1, l2)
         return loss
+
+    # ---- Sobolev training (JacobianLayer inside the loss) ---------------------------------------------------
+    def _plan_sobolev(self, loss: "SobolevMSE"):
+        """Map the loss columns onto (ShapeNet outputs, one ShapeNet-input direction)."""
+        n = self.net
+        ny, nx = len(self.jac_y), len(self.jac_x)
+        for c in loss.value_cols:
+            if not 0 <= c < n.so_dim:
+                raise NifError(f"value column {c} is not one of the {n.so_dim} model outputs")
+        xcol, gy = None, []
+        for c in loss.grad_cols:
+            k = c - n.so_dim
+            if not 0 <= k < ny * nx:
+                raise NifError(f"grad column {c} is outside the Jacobian block of the model output")
+            a, cc = divmod(k, nx)
+            if xcol is not None and self.jac_x[cc] != xcol:
+                raise NifError("SobolevMSE: all grad columns must differentiate w.r.t. the same input")
+            xcol = self.jac_x[cc]
+            gy.append(self.jac_y[a])
+        if xcol is None or xcol < n.pi_dim:
+            raise NifError("SobolevMSE needs grad columns w.r.t. a ShapeNet input (x), as in tutorial 8; derivatives "
+                           "w.r.t. ParameterNet inputs are forward-only (monitoring) in this build")
+        return {"x": xcol - n.pi_dim, "gy": gy}
+
+    def _train_step_sobolev(self, inp: torch.Tensor, tgt: torch.Tensor, global_batch: Optional[int]) -> torch.Tensor:
+        n, loss, plan = self.net, self.loss, self._sobolev_plan
+        eng = n.engine
+        B = inp.shape[0]
+        gb = int(global_batch) if global_batch else B
+        xs = inp[:, n.pi_dim: n.pi_dim + n.si_dim].contiguous()
+        p_in = inp[:, : n.pi_dim].contiguous()
+        fused_trunk = n._trunk is not None
+        if fused_trunk:
+            z, tstash = n._trunk.forward(p_in, n.theta_trunk, save=True)
+        else:
+            n.grad.zero_()
+            z = n._latent(p_in)
+        zc = z.detach().contiguous()
+        packed = self._packed_weights()
+        xdot = torch.zeros(1, B, n.si_dim, device=inp.device)
+        xdot[0, :, plan["x"]] = 1.0
+        u, udot, stash = eng.forward_tangent(zc, xs, packed, None, xdot, save=True)
+        # seeds of the batch-mean loss (O(B) elementwise; everything heavier is in the library)
+        du = torch.zeros_like(u)
+        dud = torch.zeros_like(u)
+        vc, gc, gy = loss.value_cols, loss.grad_cols, plan["gy"]
+        ev = u[:, vc] - tgt[:, vc]
+        eg = udot[0][:, gy] - tgt[:, gc]
+        du[:, vc] = (2.0 / gb) * ev
+        dud[:, gy] = (2.0 * loss.coef_grad / gb) * eg
+        lv = ((ev * ev).sum() + loss.coef_grad * (eg * eg).sum()) / gb
+        dz = eng.sobolev_backward(zc, xs, xdot[0], packed, stash, du, dud, n._gviews[n._last_names[0]],
+                                  n._gviews[n._last_names[1]], 0.0)
+        if fused_trunk:
+            n._trunk.backward(p_in, n.theta_trunk, tstash, dz, n.grad_trunk, 0.0)
+        else:
+            z.backward(dz)
+        if self.dist is not None:
+            self.dist.allreduce_(n.grad)
+        l1, l2 = n._kernel_regulariser()
+        self.optimizer.apply(n.theta, n.grad, l1, l2)
+        return lv.reshape(1)
 
     def fit(self, x=None, y=None, batch_size=None, epochs=1, verbose=0, callbacks=None, shuffle=True,
             sample_weight=None, initial_epoch=0, **_kw):

@@ -21,32 +21,18 @@ class JacobianLayer:
         self.y_index = list(y_index)
         self.x_index = list(x_index)
 
+    def as_model(self):
+        """The Keras model tutorial 8 builds around this layer (tutorial/8_...ipynb:809-813):
+        output = concat([y, reshape(dy/dx, (-1, |y|*|x|))], -1).  It shares the wrapped model's variables, predicts
+        with the forward-mode kernel and trains with `SobolevMSE` through the reverse-over-forward kernels."""
+        from .keras_like import Model
+        m = Model(self.model.net, "jacobian")
+        m.jac_y, m.jac_x = self.y_index, self.x_index
+        return m
+
     @torch.no_grad()
     def __call__(self, x):
-        m, n = self.model, self.model.net
-        inp = m._dev(x)
-        B = inp.shape[0]
-        p_in = inp[:, : n.pi_dim].contiguous()
-        xs = inp[:, n.pi_dim: n.pi_dim + n.si_dim].contiguous()
-        nd = len(self.x_index)
-        zdot = torch.zeros(nd, B, n.pi_hidden, device=inp.device)
-        xdot = torch.zeros(nd, B, n.si_dim, device=inp.device)
-        z = None
-        for d, c in enumerate(self.x_index):
-            if c < n.pi_dim:
-                e = torch.zeros_like(p_in)
-                e[:, c] = 1.0
-                z, zd = torch.func.jvp(n._latent, (p_in,), (e,))
-                zdot[d] = zd
-            elif c < n.pi_dim + n.si_dim:
-                xdot[d, :, c - n.pi_dim] = 1.0
-            else:
-                raise IndexError(f"x_index {c} outside the {n.pi_dim + n.si_dim} model inputs")
-        if z is None:
-            z = n._latent(p_in)
-        packed = m._packed_weights()
-        u, udot = n.engine.forward_tangent(z.contiguous(), xs, packed, zdot, xdot)  # udot [nd, B, so]
-        J = udot.permute(1, 2, 0)[:, self.y_index, :]  # [B, |y|, |x|]
-        return u, J.contiguous()
+        m = self.model
+        return m._jacobian_forward(m._dev(x), self.y_index, self.x_index)
 
     call = __call__

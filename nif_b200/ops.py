@@ -116,8 +116,11 @@ class FusedShapeNet:
               "nif_forward")
         return (u, stash) if save else u
 
-    def forward_tangent(self, z, x, packed, zdot: Optional[torch.Tensor], xdot: Optional[torch.Tensor]):
-        """(u, udot[n_dir,B,so]) for tangent directions zdot [n_dir,B,K] / xdot [n_dir,B,si]."""
+    def forward_tangent(self, z, x, packed, zdot: Optional[torch.Tensor], xdot: Optional[torch.Tensor],
+                        save: bool = False):
+        """(u, udot[n_dir,B,so]) for tangent directions zdot [n_dir,B,K] / xdot [n_dir,B,si].
+        save=True also returns the stash for sobolev_backward (direction 0 must then be a ShapeNet-input
+        direction, i.e. given through xdot)."""
         x = _f32c(x, "x")
         B = x.shape[0]
         z = _f32c(z, "z") if self.K > 0 else None
@@ -126,10 +129,36 @@ class FusedShapeNet:
         xdot = _f32c(xdot, "xdot") if xdot is not None else None
         u = torch.empty(B, self.so, dtype=torch.float32, device=x.device)
         udot = torch.empty(n_dir, B, self.so, dtype=torch.float32, device=x.device)
-        check(_lib.lib().nif_forward_tangent(C.byref(self.desc), B, _ptr(z), _ptr(x), _ptr(packed), n_dir,
-                                             _ptr(zdot), _ptr(xdot), _ptr(u), _ptr(udot), _stream()),
-              "nif_forward_tangent")
-        return u, udot
+        if not save:
+            check(_lib.lib().nif_forward_tangent(C.byref(self.desc), B, _ptr(z), _ptr(x), _ptr(packed), n_dir,
+                                                 _ptr(zdot), _ptr(xdot), _ptr(u), _ptr(udot), _stream()),
+                  "nif_forward_tangent")
+            return u, udot
+        if xdot is None:
+            raise NifError("forward_tangent(save=True) needs xdot: direction 0 must act on the ShapeNet inputs")
+        per_row = C.c_int64(0)
+        check(_lib.lib().nif_sobolev_query(C.byref(self.desc), B, C.byref(per_row), None), "nif_sobolev_query")
+        stash = torch.empty(int(per_row.value) * B, dtype=torch.float32, device=x.device)
+        check(_lib.lib().nif_forward_tangent_save(C.byref(self.desc), B, _ptr(z), _ptr(x), _ptr(packed), n_dir,
+                                                  _ptr(zdot), _ptr(xdot), _ptr(u), _ptr(udot), _ptr(stash), _stream()),
+              "nif_forward_tangent_save")
+        return u, udot, stash
+
+    def sobolev_backward(self, z, x, xdot0, packed, stash, du, dudot0, dw_h, db_h, beta: float = 0.0):
+        """Reverse-over-forward pass: seeds du = dL/du [B,so] and dudot0 = dL/d(udot of direction 0) [B,so];
+        xdot0 [B,si] is direction 0 of the forward_tangent(save=True) call.  Fills dw_h / db_h, returns dz."""
+        x, xdot0 = _f32c(x, "x"), _f32c(xdot0, "xdot0")
+        B = x.shape[0]
+        du, dudot0 = _f32c(du, "du"), _f32c(dudot0, "dudot0")
+        dz = torch.empty(B, self.K, dtype=torch.float32, device=x.device) if self.K > 0 else None
+        wsn = C.c_int64(0)
+        check(_lib.lib().nif_sobolev_query(C.byref(self.desc), B, None, C.byref(wsn)), "nif_sobolev_query")
+        if self._ws is None or self._ws.numel() < wsn.value or self._ws.device != x.device:
+            self._ws = torch.empty(int(wsn.value), dtype=torch.float32, device=x.device)
+        check(_lib.lib().nif_sobolev_backward(C.byref(self.desc), B, _ptr(z), _ptr(x), _ptr(xdot0), _ptr(packed),
+                                              _ptr(stash), _ptr(du), _ptr(dudot0), _ptr(dw_h), _ptr(db_h), float(beta),
+                                              _ptr(dz), _ptr(self._ws), _stream()), "nif_sobolev_backward")
+        return dz
 
     def given_w(self, x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
         """model_x_to_u_given_w: every row of `w` is a full weight vector (nif/model.py:435-464, 956-986)."""

@@ -470,6 +470,32 @@ def sobolev_loss(y3: Tensor, t3: Tensor, coef_grad: float) -> Tensor:
     return sd.mean() + coef_grad * sg.mean()
 
 
+def sobolev_loss_and_grads(spec: Spec, prm: Dict[str, Tensor], inputs: Tensor, target_u: Tensor, target_g: Tensor,
+                           x_col: int, coef_grad: float):
+    """Gradient of  mean_b mean_c (u - t_u)^2 + coef_grad * mean_b mean_c (du/dinputs[:, x_col] - t_g)^2  w.r.t. every
+    parameter: what Keras' tape computes for the tutorial-8 model (JacobianLayer output concatenated into the model
+    output, Sobolov_MSE on it, tutorial/8_...ipynb:809-820), i.e. reverse mode through compute_output_and_grad
+    (nif/layers/gradient.py:207-231).  Returns (loss, {name: grad}, dL/dz, u, du/dx_col)."""
+    leaves = {k: v.detach().clone().requires_grad_(True) for k, v in prm.items()}
+    inp = inputs.detach().clone().requires_grad_(True)
+    p_in = inp[:, : spec.pi]
+    x = inp[:, spec.pi : spec.pi + spec.si]
+    wn, bn = last_layer_names(spec)
+    z = latent(spec, leaves, p_in)
+    y = shape_net(spec, x, hyper_linear(z, leaves[wn], leaves[bn]))
+    cols = []
+    for c in range(y.shape[1]):  # one reverse pass per output index, like the reference
+        (g,) = torch.autograd.grad(y[:, c].sum(), inp, create_graph=True, retain_graph=True)
+        cols.append(g[:, x_col])
+    dy = torch.stack(cols, 1)
+    loss = ((y - target_u) ** 2).mean(-1).mean() + coef_grad * ((dy - target_g) ** 2).mean(-1).mean()
+    # (torch.autograd.grad, not .backward(): a retain_grad() hook on z would also collect the inner reverse passes)
+    names = list(leaves)
+    got = torch.autograd.grad(loss, [z] + [leaves[k] for k in names], allow_unused=True)
+    grads = {k: (g if g is not None else torch.zeros_like(leaves[k])) for k, g in zip(names, got[1:])}
+    return loss.detach(), grads, got[0].detach(), y.detach(), dy.detach()
+
+
 # ----------------------------------------------------------------------------
 # a whole training step in the reference's materialised dataflow (CPU baseline)
 # ----------------------------------------------------------------------------

@@ -297,6 +297,53 @@ def test_tangents_random(variant, si, so, n, l, K, B, dirs):
     assert _gate(rel_err(J.cpu(), J64), rel_err(J32, J64), floor=2e-5)
 
 
+@pytest.mark.parametrize("variant,si,so,n,l,K,B,xc,act", [
+    ("siren", 1, 1, 64, 4, 32, 300, 0, None),      # C4 shape: d/dx of the 1-D travelling wave
+    ("siren", 2, 2, 30, 2, 3, 257, 1, None),       # padded width, two outputs, second coordinate
+    ("siren_res", 2, 1, 64, 1, 3, 70, 0, None),    # res-blocks
+    ("nif", 2, 2, 30, 2, 2, 150, 1, "swish"),      # swish + residual
+    ("nif", 3, 1, 20, 1, 4, 65, 2, "tanh"),
+    ("siren", 3, 3, 128, 1, 4, 100, 1, None),      # width 128
+])
+def test_sobolev_reverse_over_forward(variant, si, so, n, l, K, B, xc, act):
+    """JacobianLayer inside the loss (tutorial 8): gradients of  mse(u) + coef * mse(du/dx_c)  from the
+    reverse-over-forward kernels vs autograd-of-autograd over the oracle."""
+    spec, prm, inputs, target, _ = _random_problem(variant, si, so, n, l, K, B, seed=7 * K + n, act=act or "swish")
+    dev = torch.device("cuda:0")
+    wn, bn = O.last_layer_names(spec)
+    g = torch.Generator().manual_seed(5)
+    tgt_g = torch.randn(B, so, generator=g, dtype=torch.float64)
+    coef = 0.37
+    l64, g64, gz64, y64, dy64 = O.sobolev_loss_and_grads(spec, prm, inputs, target, tgt_g, spec.pi + xc, coef)
+    prm32 = {k: v.float() for k, v in prm.items()}
+    l32, g32, gz32, y32, dy32 = O.sobolev_loss_and_grads(spec, prm32, inputs.float(), target.float(), tgt_g.float(),
+                                                         spec.pi + xc, coef)
+    eng = _engine(spec)
+    z = O.latent(spec, prm, inputs[:, : spec.pi]).float().to(dev)
+    x = inputs[:, spec.pi:].float().contiguous().to(dev)
+    w_h, b_h = prm[wn].float().to(dev), prm[bn].float().to(dev)
+    packed = eng.pack(w_h, b_h)
+    xdot = torch.zeros(1, B, si, device=dev)
+    xdot[0, :, xc] = 1.0
+    u, udot, stash = eng.forward_tangent(z, x, packed, None, xdot, save=True)
+    u_ref, udot_ref = eng.forward_tangent(z, x, packed, None, xdot)
+    assert torch.equal(u, u_ref) and torch.equal(udot, udot_ref), "stash on/off must not change the outputs"
+    assert _gate(rel_err(u.cpu(), y64), rel_err(y32, y64))
+    assert _gate(rel_err(udot[0].cpu(), dy64), rel_err(dy32, dy64), floor=2e-5)
+    du = (2.0 / (B * so)) * (u - target.float().to(dev))
+    dud = (2.0 * coef / (B * so)) * (udot[0] - tgt_g.float().to(dev))
+    dw = torch.full_like(w_h, float("nan"))
+    db = torch.full_like(b_h, float("nan"))
+    dz = eng.sobolev_backward(z, x, xdot[0], packed, stash, du, dud, dw, db, 0.0)
+    torch.cuda.synchronize()
+    for name, got, r64, r32 in (("dz", dz, gz64, gz32), ("dw_h", dw, g64[wn], g32[wn]), ("db_h", db, g64[bn], g32[bn])):
+        e = rel_err(got.cpu(), r64)
+        assert _gate(e, rel_err(r32, r64), floor=2e-5), f"{name} err {e:.3e} (cpu32 {rel_err(r32, r64):.3e})"
+    # accumulate semantics
+    eng.sobolev_backward(z, x, xdot[0], packed, stash, du, dud, dw, db, 1.0)
+    assert rel_err(dw.cpu(), 2 * g64[wn]) < 1e-4 and rel_err(db.cpu(), 2 * g64[bn]) < 1e-4
+
+
 # --------------------------------------------------------------------------------------------------
 # tensor-core path (tcgen05, FP16x3): same gates as the fp32 CUDA-core path
 # --------------------------------------------------------------------------------------------------
@@ -416,5 +463,48 @@ def test_training_steps_match_oracle_trainer(cls, cfg_s, cfg_p):
     # Adam's first steps move every weight by ~lr whatever the gradient scale, and a weight whose gradient is at the
     # rounding level may step the other way: compare absolutely, and allow a vanishing fraction of such weights.
     diffs = np.concatenate([np.abs(got[k] - v.detach().numpy()).ravel() for k, v in ref.prm.items()])
+    assert float(np.quantile(diffs, 0.999)) < 1e-4, float(np.quantile(diffs, 0.999))
+    assert float(diffs.max()) < 4 * 2e-3
+
+
+def test_sobolev_training_matches_oracle_tutorial8():
+    """Tutorial 8 end to end: JacobianLayer(model, [0], [0, 1]) -> concat [u, du/dt, du/dx] -> Sobolov_MSE (u and du/dx)
+    -> Adam, against autograd-of-autograd over the oracle with TF-semantics Adam."""
+    import nif_b200
+    cfg_s = {"use_resblock": False, "connectivity": "full", "input_dim": 1, "output_dim": 1, "units": 30, "nlayers": 2,
+             "weight_init_factor": 0.01, "omega_0": 30.0}
+    cfg_p = {"use_resblock": False, "input_dim": 1, "latent_dim": 1, "units": 30, "nlayers": 2, "activation": "swish"}
+    spec = O.spec_from_cfg("NIFMultiScale", cfg_s, cfg_p)
+    prm0 = O.init_params(spec, 3)
+    net = nif_b200.NIFMultiScale(cfg_s, cfg_p, seed=0, device="cuda:0")
+    net.set_weights({k: v.numpy() for k, v in prm0.items()})
+    coef = 1e-3
+    model = nif_b200.JacobianLayer(net.build(), y_index=[0], x_index=[0, 1]).as_model()
+    model.compile(nif_b200.Adam(1e-3), loss=nif_b200.SobolevMSE(coef, value_cols=[0], grad_cols=[2]))
+    prm = {k: v.double().clone() for k, v in prm0.items()}
+    m_ = {k: torch.zeros_like(v) for k, v in prm.items()}
+    v_ = {k: torch.zeros_like(v) for k, v in prm.items()}
+    rng = np.random.default_rng(9)
+    B = 300
+    for step in range(1, 4):
+        X = rng.uniform(-1, 1, (B, 2)).astype(np.float32)
+        Y3 = rng.uniform(-1, 1, (B, 3)).astype(np.float32)
+        Y3[:, 2] *= 20.0
+        if step == 1:  # predict() of the wrapped model = [u, du/dt, du/dx] of the oracle
+            y64, J64 = O.jacobian(spec, prm, torch.as_tensor(X).double(), [0], [0, 1])
+            y32, J32 = O.jacobian(spec, {k: v.float() for k, v in prm.items()}, torch.as_tensor(X), [0], [0, 1])
+            ref3 = torch.cat([y64.detach(), J64.reshape(B, 2)], -1)
+            ref3_32 = torch.cat([y32.detach(), J32.reshape(B, 2)], -1).double()
+            got3 = model.predict(X)
+            assert got3.shape == (B, 3)
+            assert _gate(rel_err(torch.as_tensor(got3), ref3), rel_err(ref3_32, ref3), floor=2e-5)
+        l_gpu = model.train_on_batch(X, Y3)
+        Xd, Yd = torch.as_tensor(X).double(), torch.as_tensor(Y3).double()
+        l_ref, g, _, _, _ = O.sobolev_loss_and_grads(spec, prm, Xd, Yd[:, :1], Yd[:, 2:3], 1, coef)
+        for k in prm:
+            O.adam_tf(prm[k], g[k], m_[k], v_[k], step, 1e-3)
+        assert abs(l_gpu - float(l_ref)) <= 1e-4 * max(1.0, abs(float(l_ref))), (step, l_gpu, float(l_ref))
+    got = net.get_weights()
+    diffs = np.concatenate([np.abs(got[k] - v.numpy()).ravel() for k, v in prm.items()])
     assert float(np.quantile(diffs, 0.999)) < 1e-4, float(np.quantile(diffs, 0.999))
     assert float(diffs.max()) < 4 * 2e-3
