@@ -251,6 +251,12 @@ def run_ours(args):
     kernel_name = ("nif_tc_fwd_kernel (tcgen05 fp16 MMA, 3-product split, fp32 accumulate in TMEM)" if tc
                    else "nif_fwd_kernel (fp32 CUDA cores)")
 
+    traffic = None
+    try:  # DRAM bytes per launch of the dominant kernel from the committed ncu capture
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_tc_fwd.json")))["dram_bytes_per_launch"] if tc else None
+    except (OSError, KeyError, ValueError):
+        pass
+
     cores = os.cpu_count() or 1
     cpu_rate, cpu_sec = cpu_reference_rate(2048, 6, 1, cores) if world == 1 else (None, None)
 
@@ -266,9 +272,13 @@ def run_ours(args):
         "clocks": clocks,
         "e2e": {"value": pts_e2e, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": BATCH * 4 * 4,
                 "d2h_bytes_per_step": 4},
-        "gpu_launches": (16 if model.net._trunk is not None else 11) * args.steps,
+        # nif_* kernels per optimisation step (profiles/r01_launches_step.csv): trunk pack + forward, pack scales + pack,
+        # forward, seed + loss, data pass + dz edge, weight GEMM + edge + unpack, trunk data + weight + edge + unpack, Adam
+        "gpu_launches": (17 if model.net._trunk is not None else 11) * args.steps,
         "roofline": {"bound": "tensor", "kernel": kernel_name, "achieved": ach_fwd,
-                     "peak": tensor_peak, "unit": "TFLOP/s", "frac": ach_fwd / tensor_peak, "traffic": None,
+                     "peak": tensor_peak, "unit": "TFLOP/s", "frac": ach_fwd / tensor_peak, "traffic": traffic,
+                     "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full "
+                                     "(profiles/r01_ncu_tc_kernels.txt): the activation stash written for the reverse pass",
                      "peak_source": f"bf16_tflops_sustained (dense 16-bit MMA), {peak_src}",
                      "note": "achieved = ALGORITHMIC FLOPs (2KP+2Ws per row) / launch time; the fp32-grade split "
                              "issues 3 tensor-core MACs per algorithmic MAC, so 1/3 of peak is this path's ceiling",
