@@ -40,6 +40,20 @@ class DataParallel:
             dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return t
 
+    def allreduce_start(self, t: torch.Tensor):
+        """Begin an in-place sum over ranks on NCCL's own stream (ordered after the work already enqueued on the
+        current stream); returns a handle for allreduce_finish, or None for a single process.  Kernels enqueued on
+        the current stream afterwards run concurrently with the transfer."""
+        if self.world > 1:
+            return dist.all_reduce(t, op=dist.ReduceOp.SUM, async_op=True)
+        return None
+
+    @staticmethod
+    def allreduce_finish(handle) -> None:
+        """Make the current stream wait for an allreduce_start."""
+        if handle is not None:
+            handle.wait()
+
     def max_(self, t: torch.Tensor) -> torch.Tensor:
         if self.world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)

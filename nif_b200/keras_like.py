@@ -382,9 +382,14 @@ class Model:
             u, stash = eng.forward(z, xs, packed, save=True)
             dz = eng.mse_backward(z, xs, packed, u, stash, tgt, sw, 1.0 / gb, self._loss_buf,
                                   n._gviews[n._last_names[0]], n._gviews[n._last_names[1]], 0.0)
+            # data parallel: the last linear layer's gradient (almost all of the buffer) is summed across ranks
+            # while the trunk's reverse pass runs; the small trunk gradient follows
+            h_head = self.dist.allreduce_start(n.grad[n._n_trunk:]) if self.dist is not None else None
             n._trunk.backward(p_in, n.theta_trunk, tstash, dz, n.grad_trunk, 0.0)
             if self.dist is not None:
-                self.dist.allreduce_(n.grad)
+                h_trunk = self.dist.allreduce_start(n.grad_trunk)
+                self.dist.allreduce_finish(h_head)
+                self.dist.allreduce_finish(h_trunk)
             l1, l2 = n._kernel_regulariser()
             self.optimizer.apply(n.theta, n.grad, l1, l2)
             return self._loss_buf

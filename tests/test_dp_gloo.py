@@ -55,6 +55,13 @@ def _worker(rank, world, port, out):
         lt = torch.tensor([float(loss) * scale], dtype=torch.float64)
         dp.allreduce_(lt)
         assert abs(float(lt) - float(l1)) < 1e-12
+    # the split, overlapped reduction the training step uses (head gradient first, trunk gradient second)
+    buf = torch.arange(6, dtype=torch.float32) + rank
+    h_head = dp.allreduce_start(buf[2:])
+    h_trunk = dp.allreduce_start(buf[:2])
+    dp.allreduce_finish(h_head)
+    dp.allreduce_finish(h_trunk)
+    assert torch.equal(buf, world * torch.arange(6, dtype=torch.float32) + sum(range(world)))
     m = torch.tensor([float(rank)])
     dp.max_(m)
     assert float(m) == world - 1
