@@ -37,8 +37,11 @@ __host__ __device__ inline size_t bwd_smem_bytes(int K, int si, int so) {
   return f * 4 + 64;
 }
 
-template <class C, bool RES>
-__global__ void __launch_bounds__(C::NT, 1) nif_bwd_data_kernel(const Plan pl, const BwdArgs a) {
+// EXT: the reverse-over-forward hooks of BwdArgs are live (Sobolev training); the plain pass compiles them away
+template <class C, bool RES, bool EXT>
+__global__ void __launch_bounds__(C::NT, 1) nif_bwd_data_kernel(const Plan pl, const BwdArgs a_in) {
+  BwdArgs a = a_in;
+  if (!EXT) { a.h_stash = a.save; a.e_stash = nullptr; a.ext_out = nullptr; a.ext_add = nullptr; a.no_bias = 0; a.dz_accumulate = 0; }
   constexpr int NP = C::NP, TB = C::TB, MP = C::MP, MJ = C::MJ, NT = C::NT;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* stage = reinterpret_cast<float*>(smem_raw);
@@ -204,7 +207,7 @@ __global__ void __launch_bounds__(C::NT, 1) nif_bwd_data_kernel(const Plan pl, c
 #pragma unroll
             for (int r = 0; r < MP; ++r) tmp[r][c] = fmaf(dyv[r], w, tmp[r][c]);
           }
-          if (tj == 0 && !a.no_bias) {
+          if (tj == 0 && !(EXT && a.no_bias)) {
             const float cb = __ldg(&CL[(long long)kk * NP + cc]);
 #pragma unroll
             for (int r = 0; r < MP; ++r) s[r] = fmaf(cb, dyv[r], s[r]);
@@ -246,11 +249,11 @@ __global__ void __launch_bounds__(C::NT, 1) nif_bwd_data_kernel(const Plan pl, c
           daf[r][gj * 4 + 1] = acc[r][gj * 4 + 1] * dv.y;
           daf[r][gj * 4 + 2] = acc[r][gj * 4 + 2] * dv.z;
           daf[r][gj * 4 + 3] = acc[r][gj * 4 + 3] * dv.w;
-          if (a.ext_add && brow[r] < a.B) {  // + dh'_{m+1} * e_m, written by the tangent-adjoint pass
+          if (EXT && a.ext_add && brow[r] < a.B) {  // + dh'_{m+1} * e_m, written by the tangent-adjoint pass
             const float4 xv = ldg4(&a.ext_add[(long long)m * a.B * NP + brow[r] * NP + gj * C::JSTR + tj * 4]);
             daf[r][gj * 4 + 0] += xv.x; daf[r][gj * 4 + 1] += xv.y; daf[r][gj * 4 + 2] += xv.z; daf[r][gj * 4 + 3] += xv.w;
           }
-          if (a.ext_out && brow[r] < a.B) {
+          if (EXT && a.ext_out && brow[r] < a.B) {
             const float4 ev = ldg4(&a.e_stash[(long long)m * a.B * NP + brow[r] * NP + gj * C::JSTR + tj * 4]);
             *reinterpret_cast<float4*>(&a.ext_out[(long long)m * a.B * NP + brow[r] * NP + gj * C::JSTR + tj * 4]) =
                 make_float4(acc[r][gj * 4 + 0] * ev.x, acc[r][gj * 4 + 1] * ev.y, acc[r][gj * 4 + 2] * ev.z, acc[r][gj * 4 + 3] * ev.w);
@@ -319,7 +322,7 @@ __global__ void __launch_bounds__(C::NT, 1) nif_bwd_data_kernel(const Plan pl, c
                 const float tv = om * tmp[r][c];
                 acc[r][c] = fmaf(zk, tv, acc[r][c]);
                 sr = fmaf(tv, hvv[f], sr);
-                if (!a.no_bias) sr = fmaf(cvv[f], dact[act_idx<C>(col_of<C>(tj, c), row_of<C>(tp, r))], sr);
+                if (!(EXT && a.no_bias)) sr = fmaf(cvv[f], dact[act_idx<C>(col_of<C>(tj, c), row_of<C>(tp, r))], sr);
               }
             }
             s[r] = sr;
@@ -337,7 +340,7 @@ __global__ void __launch_bounds__(C::NT, 1) nif_bwd_data_kernel(const Plan pl, c
 #pragma unroll
           for (int c = 0; c < MJ; ++c) {
             const int j = col_of<C>(tj, c);
-            const float cb = a.no_bias ? 0.f : __ldg(&C_all[((long long)0 * K1 + kk) * NP + j]);
+            const float cb = (EXT && a.no_bias) ? 0.f : __ldg(&C_all[((long long)0 * K1 + kk) * NP + j]);
             float wv[NIF_MAX_SI];
 #pragma unroll
             for (int i = 0; i < NIF_MAX_SI; ++i) wv[i] = (i < si) ? __ldg(&M0[((long long)kk * si + i) * NP + j]) : 0.f;
@@ -358,7 +361,7 @@ __global__ void __launch_bounds__(C::NT, 1) nif_bwd_data_kernel(const Plan pl, c
     for (int idx = tid; idx < TB * K; idx += NT) {
       const int p = idx / K, kk = idx - p * K;
       const long long b = row0 + p;
-      if (b < a.B) a.dz[b * K + kk] = a.dz_accumulate ? a.dz[b * K + kk] + dzs[kk * TB + p] : dzs[kk * TB + p];
+      if (b < a.B) a.dz[b * K + kk] = (EXT && a.dz_accumulate) ? a.dz[b * K + kk] + dzs[kk * TB + p] : dzs[kk * TB + p];
     }
     __syncthreads();
   }
@@ -372,7 +375,9 @@ static int launch_bwd_data(const Plan& pl, const BwdArgs& a, cudaStream_t st) {
     return NIF_E_UNSUPPORTED;
   }
   const bool res = pl.variant == NIF_VARIANT_SIREN_RES;
-  auto kern = res ? nif_bwd_data_kernel<C, true> : nif_bwd_data_kernel<C, false>;
+  const bool ext = a.h_stash != a.save || a.ext_add || a.ext_out || a.no_bias || a.dz_accumulate;
+  auto kern = ext ? (res ? nif_bwd_data_kernel<C, true, true> : nif_bwd_data_kernel<C, false, true>)
+                  : (res ? nif_bwd_data_kernel<C, true, false> : nif_bwd_data_kernel<C, false, false>);
   NIF_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int dev = 0, sms = 0, occ = 0;
   NIF_CUDA_CHECK(cudaGetDevice(&dev));
@@ -546,8 +551,8 @@ __global__ void __launch_bounds__(16 * KG * RS) nif_bwd_edge_kernel(const Plan p
   constexpr int EPT = (RC + FL - 1) / FL;             // feature elements per fetch thread per chunk
   constexpr int ZPT = (RC * KC + NTH - 1) / NTH;      // latent coordinates per thread per chunk
   static_assert(NTH >= 64, "block too small");
-  __shared__ __align__(16) float Fs[RC][64];
-  __shared__ __align__(16) float Zs[RC][KC];
+  __shared__ __align__(16) float Fs[2][RC][64];  // double buffered: one barrier per chunk
+  __shared__ __align__(16) float Zs[2][RC][KC];
   __shared__ __align__(16) float red[RS > 1 ? (RS - 1) * KG * 16 * 16 : 1];
   const int NP = pl.NP, K = pl.K, K1 = pl.K + 1, H = pl.H, si = pl.si, so = pl.so;
   const int tid = threadIdx.x;
@@ -614,15 +619,16 @@ __global__ void __launch_bounds__(16 * KG * RS) nif_bwd_edge_kernel(const Plan p
     }
   };
   if (r0 < r1) fetch(r0);
-  for (long long rb = r0; rb < r1; rb += RC) {
-    __syncthreads();  // previous chunk fully consumed
+  int buf = 0;
+  for (long long rb = r0; rb < r1; rb += RC, buf ^= 1) {
+    // buffer `buf` was last read two chunks ago; every thread has passed the barrier of the chunk in between
     if (fl < FL) {
 #pragma unroll
       for (int u = 0; u < EPT; ++u) {
         const int rr = fl + u * FL;
         float v = scale * pa[u];
         if (has_b) v *= pb[u];
-        if (rr < RC) Fs[rr][fc] = (has_col && rb + rr < r1) ? v : 0.f;
+        if (rr < RC) Fs[buf][rr][fc] = (has_col && rb + rr < r1) ? v : 0.f;
       }
     }
 #pragma unroll
@@ -631,14 +637,14 @@ __global__ void __launch_bounds__(16 * KG * RS) nif_bwd_edge_kernel(const Plan p
       const int kk = k0 + e % KC;
       float v = (kk < K) ? pz[u] : (kk == K ? 1.f : 0.f);
       if (rb + e / KC >= r1) v = 0.f;
-      if (e < RC * KC) Zs[e / KC][e % KC] = v;
+      if (e < RC * KC) Zs[buf][e / KC][e % KC] = v;
     }
     __syncthreads();
     if (rb + RC < r1) fetch(rb + RC);
 #pragma unroll 8
     for (int rr = rs; rr < RC; rr += RS) {
-      const float4 f4 = *reinterpret_cast<const float4*>(&Fs[rr][4 * qg]);
-      const float4 z4 = *reinterpret_cast<const float4*>(&Zs[rr][4 * kg]);
+      const float4 f4 = *reinterpret_cast<const float4*>(&Fs[buf][rr][4 * qg]);
+      const float4 z4 = *reinterpret_cast<const float4*>(&Zs[buf][rr][4 * kg]);
       const float fv[4] = {f4.x, f4.y, f4.z, f4.w};
       const float zv[4] = {z4.x, z4.y, z4.z, z4.w};
 #pragma unroll

@@ -44,6 +44,11 @@ struct Plan {
   // KZ = K+1 rounded up to 16; LPC = outputs per XL tile (2 if 2*KZ <= 128 else 1); NLC = ceil(so / LPC).
   int KZ, LPC, NLC;
   long long off_TCX, off_TCS2;
+  // coefficient table of the thin dz terms (nif_dz_edge_kernel):  GE[slab][f][kappa], kappa < KG = K rounded up to 4,
+  // slabs = (H+1) bias-row slabs C_m[kappa][f] | si first-matrix slabs M0[kappa][i][f] | so last-matrix slabs
+  // ML[kappa][f][c] | one slab CL[kappa][f < so]
+  int KG;
+  long long off_GE;
   // wide_last (trunk plans): the last matrix [n x so] is wide (so up to 256); its gradient runs through the
   // hidden-matrix batch-reduction GEMM as matrix index H (rows h_{H+1}, columns = the seed du padded to NP)
   // instead of the column-per-thread edge kernel.
@@ -200,6 +205,18 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 }
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+// 256-bit global accesses (sm_100: LDG.256 / STG.256): a thread that owns a row moves whole 32-byte sectors, half the
+// instructions of float4 accesses.  p must be 32-byte aligned.
+__device__ __forceinline__ void ldg8(const float* p, float (&v)[8]) {
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void stg8(float* p, float a0, float a1, float a2, float a3, float a4, float a5, float a6, float a7) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(a0), "f"(a1), "f"(a2), "f"(a3), "f"(a4),
+               "f"(a5), "f"(a6), "f"(a7)
+               : "memory");
+}
 
 // reverse-pass workspace layout (offsets in floats), shared by nif_bwd.cu / nif_api.cu / nif_trunk.cu
 struct GradWs {

@@ -36,7 +36,8 @@ void nif_plan_layout(Plan* pp) {
   p.KZ = (p.K + 1 + 15) / 16 * 16;
   p.LPC = (2 * p.KZ <= 128) ? 2 : 1;
   p.NLC = (p.so + p.LPC - 1) / p.LPC;
-  p.off_TCF = p.off_TCB = p.off_TCS = p.off_TCX = p.off_TCS2 = 0;
+  p.off_TCF = p.off_TCB = p.off_TCS = p.off_TCX = p.off_TCS2 = p.off_GE = 0;
+  p.KG = 0;
   if (p.tc) {
     off = (off + 31) / 32 * 32;
     p.off_TCF = off; off += (long long)p.H * p.NCH * NIF_TC_CHUNK_FLOATS;
@@ -44,6 +45,8 @@ void nif_plan_layout(Plan* pp) {
     p.off_TCS = off; off += up4((long long)p.H * p.KP);
     p.off_TCX = off; off += (p.si + 1 + p.H) * plan_x0_floats(p) + p.NLC * plan_xl_floats(p);
     p.off_TCS2 = off; off += up4(plan_n_small(p));
+    p.KG = (p.K + 3) / 4 * 4;
+    p.off_GE = off; off += (long long)(p.H + 1 + p.si + p.so + 1) * 64 * p.KG;
   }
   p.packed_floats = (off + 31) / 32 * 32;  // keep every image 128-byte aligned
 }
@@ -207,6 +210,16 @@ __global__ void __launch_bounds__(256) nif_pack_kernel(const Plan pl, long long 
       if (!lo) out = __floats2half2_rn(a0, a1);
       else out = __floats2half2_rn(a0 - __half2float(__float2half_rn(a0)), a1 - __half2float(__float2half_rn(a1)));
       v = __uint_as_float(*reinterpret_cast<uint32_t*>(&out));
+    } else if (r >= pl.off_GE && r < pl.off_GE + (long long)(H + 1 + pl.si + pl.so + 1) * 64 * pl.KG) {
+      r -= pl.off_GE;
+      const int k = (int)(r % pl.KG); r /= pl.KG;
+      const int f = (int)(r % 64); const int sb = (int)(r / 64);
+      if (k < pl.K) {
+        if (sb <= H) { if (f < n) v = src_at(pl, w_h, b_h, g, k, plan_b_off(pl, sb) + f); }
+        else if (sb < H + 1 + pl.si) { if (f < n) v = src_at(pl, w_h, b_h, g, k, (sb - H - 1) * n + f); }
+        else if (sb < H + 1 + pl.si + pl.so) { if (f < n) v = src_at(pl, w_h, b_h, g, k, plan_w_off(pl, H + 1) + f * pl.so + (sb - H - 1 - pl.si)); }
+        else if (f < pl.so) v = src_at(pl, w_h, b_h, g, k, plan_b_off(pl, H + 1) + f);
+      }
     } else {
       continue;  // scale tables are written by nif_pack_scales_kernel before this kernel runs
     }

@@ -189,13 +189,17 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) nif_tc_bwd_data_kernel(const P
         float dav[64];
         float amax = 0.f;
 #pragma unroll
-        for (int c = 0; c < 16; ++c) {
-          float4 dv = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (live) dv = ldg4(dsv + 4 * c);
-          dav[4 * c] = acc[4 * c] * dv.x; dav[4 * c + 1] = acc[4 * c + 1] * dv.y;
-          dav[4 * c + 2] = acc[4 * c + 2] * dv.z; dav[4 * c + 3] = acc[4 * c + 3] * dv.w;
-          if (live) *reinterpret_cast<float4*>(dag + 4 * c) = make_float4(dav[4 * c], dav[4 * c + 1], dav[4 * c + 2], dav[4 * c + 3]);
-          amax = fmaxf(fmaxf(amax, fabsf(dav[4 * c])), fmaxf(fabsf(dav[4 * c + 1]), fmaxf(fabsf(dav[4 * c + 2]), fabsf(dav[4 * c + 3]))));
+        for (int c = 0; c < 8; ++c) {
+          float dv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          if (live) ldg8(dsv + 8 * c, dv);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            dav[8 * c + e] = acc[8 * c + e] * dv[e];
+            amax = fmaxf(amax, fabsf(dav[8 * c + e]));
+          }
+          if (live)
+            stg8(dag + 8 * c, dav[8 * c], dav[8 * c + 1], dav[8 * c + 2], dav[8 * c + 3], dav[8 * c + 4], dav[8 * c + 5],
+                 dav[8 * c + 6], dav[8 * c + 7]);
         }
         warp_atomic_max(&a.maxes[m], amax);
         if (m == 0) break;
@@ -212,11 +216,14 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) nif_tc_bwd_data_kernel(const P
           const float* hsrc = a.save + (long long)(m - 1) * a.B * 64 + b * 64;
           float hmax = 0.f;
 #pragma unroll
-          for (int c = 0; c < 16; ++c) {
-            float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (live) q = ldg4(hsrc + 4 * c);
-            hm[4 * c] = q.x; hm[4 * c + 1] = q.y; hm[4 * c + 2] = q.z; hm[4 * c + 3] = q.w;
-            hmax = fmaxf(fmaxf(hmax, fabsf(q.x)), fmaxf(fabsf(q.y), fmaxf(fabsf(q.z), fabsf(q.w))));
+          for (int c = 0; c < 8; ++c) {
+            float q[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (live) ldg8(hsrc + 8 * c, q);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              hm[8 * c + e] = q[e];
+              hmax = fmaxf(hmax, fabsf(q[e]));
+            }
           }
           warp_atomic_max(&a.maxes[H + 2 + (m - 1)], hmax);
         }
@@ -297,11 +304,12 @@ struct DzEdgeArgs {
 //   next so                      F = du[b][c]                   G = CL[kappa][c]
 // G is staged through shared memory in slabs of 64 features; every thread keeps its K outputs in registers
 // (KT of them per pass over the features).
-// Every thread owns TWO rows (b and b + 128), so each shared-memory read of G feeds two FMAs.
+// Every thread owns TWO rows (b and b + blockDim.x), so each coefficient read feeds two FMAs; the coefficient table
+// GE[slab][f][kappa] is re-laid by nif_pack so that a slab is staged into shared memory with coalesced vector loads.
 template <int KT>
 __global__ void __launch_bounds__(128) nif_dz_edge_kernel(const Plan pl, const DzEdgeArgs a, int k0) {
-  __shared__ __align__(16) float Gs[64][KT];
-  const int K = pl.K, K1 = pl.K + 1, H = pl.H, si = pl.si, so = pl.so;
+  __shared__ __align__(16) float Gs[64 * KT];
+  const int K = pl.K, H = pl.H, si = pl.si, so = pl.so, KG = pl.KG;
   const long long b0 = blockIdx.x * 256LL + threadIdx.x;
   long long bb[2];
   bool live[2];
@@ -310,9 +318,7 @@ __global__ void __launch_bounds__(128) nif_dz_edge_kernel(const Plan pl, const D
     live[w] = b0 + 128 * w < a.B;
     bb[w] = live[w] ? b0 + 128 * w : 0;
   }
-  const float* C_all = a.packed + pl.off_C;
-  const float* M0 = a.packed + pl.off_M0;
-  const float* ML = a.packed + pl.off_ML;
+  const float* GE = a.packed + pl.off_GE + k0;
   const float om0 = plan_omega(pl, 0);
   float acc[2][KT];
 #pragma unroll
@@ -322,21 +328,12 @@ __global__ void __launch_bounds__(128) nif_dz_edge_kernel(const Plan pl, const D
 
   const int nslab = (H + 1) + si + so + 1;  // slabs of (up to) 64 features
   for (int sb = 0; sb < nslab; ++sb) {
-    // ---- stage G slab: Gs[f][k] for 64 features f and KT latent coordinates ----
-    __syncthreads();
-    for (int idx = threadIdx.x; idx < 64 * KT; idx += 128) {
-      const int f = idx / KT, k = idx - f * KT, kk = k0 + k;
-      float g = 0.f;
-      if (kk < K) {
-        if (sb <= H) g = __ldg(&C_all[((long long)sb * K1 + kk) * 64 + f]);
-        else if (sb < H + 1 + si) g = __ldg(&M0[((long long)kk * si + (sb - H - 1)) * 64 + f]);
-        else if (sb < H + 1 + si + so) g = __ldg(&ML[((long long)kk * 64 + f) * so + (sb - H - 1 - si)]);
-        else if (f < so) g = __ldg(&C_all[((long long)(H + 1) * K1 + kk) * 64 + f]);
-      }
-      Gs[f][k] = g;
+    __syncthreads();  // the previous slab has been consumed
+    for (int idx = threadIdx.x; idx < 64 * KT / 4; idx += 128) {
+      const int f = idx / (KT / 4), k4 = idx - f * (KT / 4);
+      *reinterpret_cast<float4*>(&Gs[f * KT + 4 * k4]) = ldg4(GE + ((long long)sb * 64 + f) * KG + 4 * k4);
     }
     __syncthreads();
-    // ---- the 64 features of the slab for both rows ----
     const float* src[2];
     float mul[2] = {1.f, 1.f};
     int nf = 64;
@@ -348,47 +345,53 @@ __global__ void __launch_bounds__(128) nif_dz_edge_kernel(const Plan pl, const D
       else { src[w] = a.du + bb[w] * so; nf = so; }
     }
     if (nf == 64) {
-      // groups of 4 float4 per row; the next group's loads are issued before the current group is consumed
-      float4 cur[2][4], nxt[2][4];
+      // groups of 16 features per row (two 256-bit loads); the next group's loads are issued before the current
+      // group is consumed
+      float cur[2][16], nxt[2][16];
 #pragma unroll
-      for (int w = 0; w < 2; ++w)
-#pragma unroll
-        for (int q = 0; q < 4; ++q) cur[w][q] = ldg4(src[w] + 4 * q);
+      for (int w = 0; w < 2; ++w) {
+        ldg8(src[w], *reinterpret_cast<float(*)[8]>(&cur[w][0]));
+        ldg8(src[w] + 8, *reinterpret_cast<float(*)[8]>(&cur[w][8]));
+      }
 #pragma unroll 1
       for (int g4 = 0; g4 < 4; ++g4) {
         if (g4 < 3) {
 #pragma unroll
+          for (int w = 0; w < 2; ++w) {
+            ldg8(src[w] + 16 * (g4 + 1), *reinterpret_cast<float(*)[8]>(&nxt[w][0]));
+            ldg8(src[w] + 16 * (g4 + 1) + 8, *reinterpret_cast<float(*)[8]>(&nxt[w][8]));
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const float f0 = cur[0][e] * mul[0], f1 = cur[1][e] * mul[1];
+          const float* Gf = Gs + (16 * g4 + e) * KT;
+#pragma unroll
+          for (int k = 0; k < KT; k += 4) {
+            const float4 g = *reinterpret_cast<const float4*>(Gf + k);
+            acc[0][k] = fmaf(f0, g.x, acc[0][k]); acc[0][k + 1] = fmaf(f0, g.y, acc[0][k + 1]);
+            acc[0][k + 2] = fmaf(f0, g.z, acc[0][k + 2]); acc[0][k + 3] = fmaf(f0, g.w, acc[0][k + 3]);
+            acc[1][k] = fmaf(f1, g.x, acc[1][k]); acc[1][k + 1] = fmaf(f1, g.y, acc[1][k + 1]);
+            acc[1][k + 2] = fmaf(f1, g.z, acc[1][k + 2]); acc[1][k + 3] = fmaf(f1, g.w, acc[1][k + 3]);
+          }
+        }
+        if (g4 < 3) {
+#pragma unroll
           for (int w = 0; w < 2; ++w)
 #pragma unroll
-            for (int q = 0; q < 4; ++q) nxt[w][q] = ldg4(src[w] + 16 * (g4 + 1) + 4 * q);
+            for (int e = 0; e < 16; ++e) cur[w][e] = nxt[w][e];
         }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float fv0[4] = {cur[0][q].x * mul[0], cur[0][q].y * mul[0], cur[0][q].z * mul[0], cur[0][q].w * mul[0]};
-          const float fv1[4] = {cur[1][q].x * mul[1], cur[1][q].y * mul[1], cur[1][q].z * mul[1], cur[1][q].w * mul[1]};
-#pragma unroll
-          for (int e = 0; e < 4; ++e)
-#pragma unroll
-            for (int k = 0; k < KT; k += 4) {
-              const float4 g = *reinterpret_cast<const float4*>(&Gs[16 * g4 + 4 * q + e][k]);
-              acc[0][k] = fmaf(fv0[e], g.x, acc[0][k]); acc[0][k + 1] = fmaf(fv0[e], g.y, acc[0][k + 1]);
-              acc[0][k + 2] = fmaf(fv0[e], g.z, acc[0][k + 2]); acc[0][k + 3] = fmaf(fv0[e], g.w, acc[0][k + 3]);
-              acc[1][k] = fmaf(fv1[e], g.x, acc[1][k]); acc[1][k + 1] = fmaf(fv1[e], g.y, acc[1][k + 1]);
-              acc[1][k + 2] = fmaf(fv1[e], g.z, acc[1][k + 2]); acc[1][k + 3] = fmaf(fv1[e], g.w, acc[1][k + 3]);
-            }
-        }
-#pragma unroll
-        for (int w = 0; w < 2; ++w)
-#pragma unroll
-          for (int q = 0; q < 4; ++q) cur[w][q] = nxt[w][q];
       }
     } else {
       for (int f = 0; f < nf; ++f) {
         const float f0 = src[0][f], f1 = src[1][f];
 #pragma unroll
-        for (int k = 0; k < KT; ++k) {
-          acc[0][k] = fmaf(f0, Gs[f][k], acc[0][k]);
-          acc[1][k] = fmaf(f1, Gs[f][k], acc[1][k]);
+        for (int k = 0; k < KT; k += 4) {
+          const float4 g = *reinterpret_cast<const float4*>(&Gs[f * KT + k]);
+          acc[0][k] = fmaf(f0, g.x, acc[0][k]); acc[0][k + 1] = fmaf(f0, g.y, acc[0][k + 1]);
+          acc[0][k + 2] = fmaf(f0, g.z, acc[0][k + 2]); acc[0][k + 3] = fmaf(f0, g.w, acc[0][k + 3]);
+          acc[1][k] = fmaf(f1, g.x, acc[1][k]); acc[1][k + 1] = fmaf(f1, g.y, acc[1][k + 1]);
+          acc[1][k + 2] = fmaf(f1, g.z, acc[1][k + 2]); acc[1][k + 3] = fmaf(f1, g.w, acc[1][k + 3]);
         }
       }
     }
@@ -409,6 +412,8 @@ int nif_tc_bwd_data_impl(const Plan& pl, long long B, const float* z, const floa
   if (!pl.tc || pl.NP != 64 || pl.H < 1 || pl.variant == NIF_VARIANT_SIREN_RES || pl.K < 1) return NIF_E_UNSUPPORTED;
   const size_t smem = tcb_smem_bytes(pl.KP);
   if (smem > 227 * 1024) return NIF_E_UNSUPPORTED;
+  // the row-owning threads move 32-byte sectors (256-bit loads / stores)
+  if ((reinterpret_cast<uintptr_t>(save) | reinterpret_cast<uintptr_t>(da)) & 31) return NIF_E_UNSUPPORTED;
   TcBwdArgs a;
   a.B = B;
   a.total_pairs = (B + 255) / 256;
@@ -424,9 +429,16 @@ int nif_tc_bwd_data_impl(const Plan& pl, long long B, const float* z, const floa
   NIF_CUDA_CHECK(cudaGetLastError());
   DzEdgeArgs e;
   e.B = B; e.x = x; e.packed = packed; e.save = save; e.da = da; e.du = du; e.dz = dz;
-  for (int k0 = 0; k0 < pl.K; k0 += 32) {  // 32 latent coordinates per pass
-    nif_dz_edge_kernel<32><<<(unsigned)((B + 255) / 256), 128, 0, st>>>(pl, e, k0);
+  for (int k0 = 0; k0 < pl.K;) {  // up to 32 latent coordinates per pass (the table is KG = ceil4(K) wide)
+    const int left = pl.KG - k0;
+    const unsigned grid = (unsigned)((B + 255) / 256);
+    int kt;
+    if (left >= 32) { kt = 32; nif_dz_edge_kernel<32><<<grid, 128, 0, st>>>(pl, e, k0); }
+    else if (left >= 16) { kt = 16; nif_dz_edge_kernel<16><<<grid, 128, 0, st>>>(pl, e, k0); }
+    else if (left >= 8) { kt = 8; nif_dz_edge_kernel<8><<<grid, 128, 0, st>>>(pl, e, k0); }
+    else { kt = 4; nif_dz_edge_kernel<4><<<grid, 128, 0, st>>>(pl, e, k0); }
     NIF_CUDA_CHECK(cudaGetLastError());
+    k0 += kt;
   }
   return NIF_OK;
 }

@@ -304,10 +304,9 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) nif_tc_fwd_kernel(const Plan p
             dch[e] = d;
           }
           if (SAVE && live) {
-            *reinterpret_cast<float4*>(sh + 8 * c) = make_float4(hcur[8 * c], hcur[8 * c + 1], hcur[8 * c + 2], hcur[8 * c + 3]);
-            *reinterpret_cast<float4*>(sh + 8 * c + 4) = make_float4(hcur[8 * c + 4], hcur[8 * c + 5], hcur[8 * c + 6], hcur[8 * c + 7]);
-            *reinterpret_cast<float4*>(sd + 8 * c) = make_float4(dch[0], dch[1], dch[2], dch[3]);
-            *reinterpret_cast<float4*>(sd + 8 * c + 4) = make_float4(dch[4], dch[5], dch[6], dch[7]);
+            stg8(sh + 8 * c, hcur[8 * c], hcur[8 * c + 1], hcur[8 * c + 2], hcur[8 * c + 3], hcur[8 * c + 4], hcur[8 * c + 5],
+                 hcur[8 * c + 6], hcur[8 * c + 7]);
+            stg8(sd + 8 * c, dch[0], dch[1], dch[2], dch[3], dch[4], dch[5], dch[6], dch[7]);
           }
         }
       };
@@ -431,6 +430,7 @@ int nif_tc_forward_impl(const Plan& pl, long long B, const float* z, const float
                         float* save, cudaStream_t st) {
   if (!pl.tc || pl.NP != 64 || pl.H < 1 || pl.variant == NIF_VARIANT_SIREN_RES) return NIF_E_UNSUPPORTED;
   if (tcf_smem_bytes(pl.KP, pl.KZ, pl.si) > 227 * 1024 || pl.LPC * pl.KZ > 128) return NIF_E_UNSUPPORTED;
+  if (reinterpret_cast<uintptr_t>(save) & 31) return NIF_E_UNSUPPORTED;  // stash rows are written as 32-byte sectors
   TcFwdArgs a;
   a.B = B;
   a.total_pairs = (B + 255) / 256;
