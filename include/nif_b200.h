@@ -56,7 +56,9 @@ typedef struct nif_sizes {
   int64_t n_layers;      /* ShapeNet matrices: l+2, or 2l+2 with res-blocks */
   int64_t np;            /* padded width used on chip (32/64/128) */
   int64_t packed_floats; /* floats of one packed weight image (nif_pack output) */
-  int64_t save_floats_per_row;  /* floats/row of the activation stash written by forward for backward */
+  int64_t save_floats_per_row;  /* floats/row of the activation stash written by forward for backward; the buffer
+                                   holds save_floats_per_row * B64 floats, B64 = B rounded up to a multiple of 64
+                                   (the tensor-core path tiles rows in groups) */
   int64_t grad_ws_floats;       /* floats of the partial-gradient workspace for batch size B (see nif_sizes B) */
   int64_t tile_rows;     /* rows per CTA tile */
 } nif_sizes_t;
@@ -82,7 +84,8 @@ int nif_pack(const nif_desc_t* d, int64_t G, const float* w_h, const float* b_h,
  * (nif/model.py:233-324, 738-954) + EinsumLayer (nif/layers/mlp.py:209-219).
  * z [G*B,K] (ignored when K==0), x [G*B,si] or, if x_shared!=0, [B,si] shared by
  * all groups; packed [G*packed_floats]; u [G*B,so].
- * save: NULL for inference, else [save_floats_per_row * B] (G must be 1). */
+ * save: NULL for inference, else [save_floats_per_row * B64], B64 = B rounded up to 64 (G must be 1); its layout is
+ * private to the library (row-major or tiled, depending on the kernels that serve the descriptor). */
 int nif_forward(const nif_desc_t* d, int64_t G, int64_t B, const float* z, const float* x,
                 int32_t x_shared, const float* packed, float* u, float* save, void* stream);
 

@@ -536,6 +536,7 @@ struct EdgeArgs {
   const float *z, *x, *save, *da, *du;
   float* part;  // [S][K+1][Q]
   int no_bias;  // tangent-adjoint pass: the bias-row columns are zero
+  int tiled;    // da / save are in the tiled layout of the tensor-core path (nif_common.cuh), NP = 64
 };
 
 // Register-tiled batch reduction: a thread owns 4 columns x 4 latent coordinates; a CTA owns 64 columns x KG groups
@@ -563,27 +564,32 @@ __global__ void __launch_bounds__(16 * KG * RS) nif_bwd_edge_kernel(const Plan p
   long long r1 = r0 + a.rows_per_split;
   if (r1 > a.B) r1 = a.B;
 
-  // the feature column this thread fetches:  F[b] = scale * A[b*sA] * (Bp ? Bp[b*sB] : 1)
+  // the feature column this thread fetches:  F[b] = scale * A[row(b)] * (Bp ? Bp[b*sB] : 1), row(b) = b * sA, or the
+  // tiled row offset when the source is a tiled stash / da slot
   const int fc = tid % 64, fl = tid / 64;
   const float* Ap = nullptr;
   const float* Bp = nullptr;
   long long sA = 0, sB = 0;
+  bool a_tiled = false;
   float scale = 1.f;
   {
+    const long long slot = a.tiled ? nif_tiled_rows(a.B) * 64 : a.B * NP;  // floats per da / stash slot
     int r = blockIdx.x * 64 + fc;
     if (fl < FL && r < a.Q) {
       if (r < (H + 1) * NP) {
         const int m = r / NP, j = r % NP;
-        if (!a.no_bias) { Ap = a.da + (long long)m * a.B * NP + j; sA = NP; }
+        if (!a.no_bias) { Ap = a.da + (long long)m * slot + (a.tiled ? nif_tiled_col(j) : j); sA = NP; a_tiled = a.tiled; }
       } else if ((r -= (H + 1) * NP) < so) {
         if (!a.no_bias) { Ap = a.du + r; sA = so; }
       } else if ((r -= so) < si * NP) {
         const int i = r / NP, j = r % NP;
-        Ap = a.da + j; sA = NP; Bp = a.x + i; sB = si; scale = plan_omega(pl, 0);
+        Ap = a.da + (a.tiled ? nif_tiled_col(j) : j); sA = NP; a_tiled = a.tiled;
+        Bp = a.x + i; sB = si; scale = plan_omega(pl, 0);
       } else {
         r -= si * NP;
         const int i = r / so, c = r % so;
-        Ap = a.save + (long long)H * a.B * NP + i; sA = NP; Bp = a.du + c; sB = so;
+        Ap = a.save + (long long)H * slot + (a.tiled ? nif_tiled_col(i) : i); sA = NP; a_tiled = a.tiled;
+        Bp = a.du + c; sB = so;
       }
     }
   }
@@ -606,7 +612,7 @@ __global__ void __launch_bounds__(16 * KG * RS) nif_bwd_edge_kernel(const Plan p
     for (int u = 0; u < EPT; ++u) {
       long long b = rb + fl + u * FL;
       if (b >= r1) b = r0;
-      pa[u] = __ldg(&Ap[b * sA]);
+      pa[u] = __ldg(&Ap[a_tiled ? nif_tiled_row(b) : b * sA]);
       pb[u] = __ldg(&Bp[b * sB]);
     }
 #pragma unroll
@@ -765,7 +771,7 @@ GradWs nif_grad_ws_layout(const Plan& pl, long long B) {
   w.S_e = (int)((B + w.rows_e - 1) / w.rows_e);
   if (w.S_e < 1) w.S_e = 1;
   long long off = 0;
-  w.da = off; off += round_up((H + 1 + pl.wide_last) * B * NP, 4);
+  w.da = off; off += round_up((H + 1 + pl.wide_last) * nif_tiled_rows(B) * NP, 4);  // (tiled slots hold B rounded up to 64 rows)
   w.du = off; off += round_up(B * pl.so, 4);
   w.part_h = off; off += round_up((long long)w.S_h * Hm * K1 * NP * NP, 4);
   w.part_e = off; off += round_up((long long)w.S_e * K1 * w.Q, 4);
@@ -817,7 +823,7 @@ int nif_weight_grads_impl(const Plan& pl, long long B, const float* z, const flo
   }
   EdgeArgs e;
   e.B = B; e.rows_per_split = w.rows_e; e.S = w.S_e; e.Q = w.Q;
-  e.z = z; e.x = x; e.save = save; e.da = ws + w.da; e.du = du; e.part = ws + w.part_e; e.no_bias = no_bias;
+  e.z = z; e.x = x; e.save = save; e.da = ws + w.da; e.du = du; e.part = ws + w.part_e; e.no_bias = no_bias; e.tiled = 0;
   NIF_CUDA_CHECK(launch_edge(pl, e, w, st));
   return nif_unpack_grad_impl(pl, w.S_h, ws + w.part_h, w.S_e, ws + w.part_e, w.Q, dw_h, db_h, beta, st);
 }
@@ -866,7 +872,7 @@ int nif_backward_impl(const Plan& pl, long long B, const float* z, const float* 
   {
     EdgeArgs e;
     e.B = B; e.rows_per_split = w.rows_e; e.S = w.S_e; e.Q = w.Q;
-    e.z = z; e.x = x; e.save = save; e.da = ws + w.da; e.du = du; e.part = ws + w.part_e; e.no_bias = 0;
+    e.z = z; e.x = x; e.save = save; e.da = ws + w.da; e.du = du; e.part = ws + w.part_e; e.no_bias = 0; e.tiled = 1;
     NIF_CUDA_CHECK(launch_edge(pl, e, w, st));
   }
   return nif_unpack_grad_impl(pl, S_used, ws + w.part_h, w.S_e, ws + w.part_e, w.Q, dw_h, db_h, beta, st);

@@ -218,6 +218,19 @@ __device__ __forceinline__ void stg8(float* p, float a0, float a1, float a2, flo
                : "memory");
 }
 
+// Tiled activation layout of the tensor-core path (NP = 64; stash slots h_m, d_m and the reverse pass's da_m): the
+// kernels that own a row per thread would otherwise touch one 32-byte sector per lane and instruction.  Rows are
+// grouped by 32; inside a group the 16 column quads follow each other, and inside a quad the 32 rows' float4:
+//   offset(b, j) = (b >> 5) * 2048 + (j >> 2) * 128 + (b & 31) * 4 + (j & 3)
+// so a warp that reads one quad of 32 consecutive rows moves 512 contiguous bytes, and a 64-row sub-tile is one
+// contiguous 16 KB block (a single bulk copy) whose rows are conflict-free in shared memory.  Slots hold
+// nif_tiled_rows(B) rows (B rounded up to 64).
+__host__ __device__ inline long long nif_tiled_rows(long long B) { return (B + 63) / 64 * 64; }
+__host__ __device__ inline long long nif_tiled_row(long long b) { return (b >> 5) * 2048 + (b & 31) * 4; }
+__host__ __device__ inline int nif_tiled_col(int j) { return (j >> 2) * 128 + (j & 3); }
+// static shape test shared by forward and reverse: does this plan run on the tensor-core kernels (tiled stash)?
+bool nif_plan_uses_tc(const Plan& pl);
+
 // reverse-pass workspace layout (offsets in floats), shared by nif_bwd.cu / nif_api.cu / nif_trunk.cu
 struct GradWs {
   long long da, du, part_h, part_e, loss_part, maxes, total;

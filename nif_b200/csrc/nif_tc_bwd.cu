@@ -24,9 +24,12 @@ struct TcBwdArgs {
 #define TCB_STAGES 2
 #define TCB_STAGE_BYTES 32768u
 
+size_t nif_tcb_smem_bytes(int KP);
 __host__ __device__ inline size_t tcb_smem_bytes(int KP) {
   return 4 * (size_t)TC_TILE_BYTES + TCB_STAGES * (size_t)TCB_STAGE_BYTES + 4 * (size_t)KP * 128 * 4 + 256;
 }
+
+size_t nif_tcb_smem_bytes(int KP) { return tcb_smem_bytes(KP); }
 
 __device__ __forceinline__ void warp_atomic_max(unsigned* dst, float v) {
 #pragma unroll
@@ -124,6 +127,7 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) nif_tc_bwd_data_kernel(const P
     float* zs = zs_all + wg * KP * 128;
     float* dzs = dzs_all + wg * KP * 128;
     const float* invB = a.packed + pl.off_TCS;
+    const long long slot_floats = nif_tiled_rows(a.B) * 64;  // one slot of the (tiled) stash / da buffer
     long long g = 0;
     for (long long p = 0; p < my_pairs; ++p) {
       const long long row0 = ((blockIdx.x + p * gridDim.x) * 2 + wg) * 128;
@@ -184,22 +188,18 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) nif_tc_bwd_data_kernel(const P
 
       // ---- layers H .. 0: da_m = dh_{m+1} * d_m; hidden matrices on the tensor cores ----
       for (int m = H; m >= 0; --m) {
-        const float* dsv = a.save + (long long)(H + 1 + m) * a.B * 64 + b * 64;  // d_m row
-        float* dag = a.da + (long long)m * a.B * 64 + b * 64;
+        const float* dsv = a.save + (long long)(H + 1 + m) * slot_floats + nif_tiled_row(b);  // d_m row (tiled)
+        float* dag = a.da + (long long)m * slot_floats + nif_tiled_row(b);
         float dav[64];
         float amax = 0.f;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          float dv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-          if (live) ldg8(dsv + 8 * c, dv);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            dav[8 * c + e] = acc[8 * c + e] * dv[e];
-            amax = fmaxf(amax, fabsf(dav[8 * c + e]));
-          }
-          if (live)
-            stg8(dag + 8 * c, dav[8 * c], dav[8 * c + 1], dav[8 * c + 2], dav[8 * c + 3], dav[8 * c + 4], dav[8 * c + 5],
-                 dav[8 * c + 6], dav[8 * c + 7]);
+        for (int c = 0; c < 16; ++c) {  // column quad c: a warp moves 512 contiguous bytes per access
+          float4 dv = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (live) dv = ldg4(dsv + c * 128);
+          dav[4 * c] = acc[4 * c] * dv.x; dav[4 * c + 1] = acc[4 * c + 1] * dv.y;
+          dav[4 * c + 2] = acc[4 * c + 2] * dv.z; dav[4 * c + 3] = acc[4 * c + 3] * dv.w;
+          if (live) *reinterpret_cast<float4*>(dag + c * 128) = make_float4(dav[4 * c], dav[4 * c + 1], dav[4 * c + 2], dav[4 * c + 3]);
+          amax = fmaxf(fmaxf(amax, fabsf(dav[4 * c])), fmaxf(fabsf(dav[4 * c + 1]), fmaxf(fabsf(dav[4 * c + 2]), fabsf(dav[4 * c + 3]))));
         }
         warp_atomic_max(&a.maxes[m], amax);
         if (m == 0) break;
@@ -213,17 +213,14 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) nif_tc_bwd_data_kernel(const P
         // this layer's input row h_m (for the dz dot products)
         float hm[64];
         {
-          const float* hsrc = a.save + (long long)(m - 1) * a.B * 64 + b * 64;
+          const float* hsrc = a.save + (long long)(m - 1) * slot_floats + nif_tiled_row(b);
           float hmax = 0.f;
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            float q[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            if (live) ldg8(hsrc + 8 * c, q);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              hm[8 * c + e] = q[e];
-              hmax = fmaxf(hmax, fabsf(q[e]));
-            }
+          for (int c = 0; c < 16; ++c) {
+            float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (live) q = ldg4(hsrc + c * 128);
+            hm[4 * c] = q.x; hm[4 * c + 1] = q.y; hm[4 * c + 2] = q.z; hm[4 * c + 3] = q.w;
+            hmax = fmaxf(fmaxf(hmax, fabsf(q.x)), fmaxf(fabsf(q.y), fmaxf(fabsf(q.z), fabsf(q.w))));
           }
           warp_atomic_max(&a.maxes[H + 2 + (m - 1)], hmax);
         }
@@ -320,6 +317,7 @@ __global__ void __launch_bounds__(128) nif_dz_edge_kernel(const Plan pl, const D
   }
   const float* GE = a.packed + pl.off_GE + k0;
   const float om0 = plan_omega(pl, 0);
+  const long long slot_floats = nif_tiled_rows(a.B) * 64;  // da and the stash are in the tiled layout
   float acc[2][KT];
 #pragma unroll
   for (int w = 0; w < 2; ++w)
@@ -339,29 +337,28 @@ __global__ void __launch_bounds__(128) nif_dz_edge_kernel(const Plan pl, const D
     int nf = 64;
 #pragma unroll
     for (int w = 0; w < 2; ++w) {
-      if (sb <= H) src[w] = a.da + (long long)sb * a.B * 64 + bb[w] * 64;
-      else if (sb < H + 1 + si) { src[w] = a.da + bb[w] * 64; mul[w] = om0 * a.x[bb[w] * si + (sb - H - 1)]; }
-      else if (sb < H + 1 + si + so) { src[w] = a.save + (long long)H * a.B * 64 + bb[w] * 64; mul[w] = a.du[bb[w] * so + (sb - H - 1 - si)]; }
+      if (sb <= H) src[w] = a.da + (long long)sb * slot_floats + nif_tiled_row(bb[w]);
+      else if (sb < H + 1 + si) { src[w] = a.da + nif_tiled_row(bb[w]); mul[w] = om0 * a.x[bb[w] * si + (sb - H - 1)]; }
+      else if (sb < H + 1 + si + so) { src[w] = a.save + (long long)H * slot_floats + nif_tiled_row(bb[w]); mul[w] = a.du[bb[w] * so + (sb - H - 1 - si)]; }
       else { src[w] = a.du + bb[w] * so; nf = so; }
     }
     if (nf == 64) {
       // groups of 16 features per row (two 256-bit loads); the next group's loads are issued before the current
       // group is consumed
       float cur[2][16], nxt[2][16];
+      auto load16 = [&](int g4, float (&dst)[2][16]) {  // features 16 g4 .. 16 g4 + 15 = column quads 4 g4 .. 4 g4 + 3
 #pragma unroll
-      for (int w = 0; w < 2; ++w) {
-        ldg8(src[w], *reinterpret_cast<float(*)[8]>(&cur[w][0]));
-        ldg8(src[w] + 8, *reinterpret_cast<float(*)[8]>(&cur[w][8]));
-      }
+        for (int w = 0; w < 2; ++w)
+#pragma unroll
+          for (int qd = 0; qd < 4; ++qd) {
+            const float4 v = ldg4(src[w] + (4 * g4 + qd) * 128);
+            dst[w][4 * qd] = v.x; dst[w][4 * qd + 1] = v.y; dst[w][4 * qd + 2] = v.z; dst[w][4 * qd + 3] = v.w;
+          }
+      };
+      load16(0, cur);
 #pragma unroll 1
       for (int g4 = 0; g4 < 4; ++g4) {
-        if (g4 < 3) {
-#pragma unroll
-          for (int w = 0; w < 2; ++w) {
-            ldg8(src[w] + 16 * (g4 + 1), *reinterpret_cast<float(*)[8]>(&nxt[w][0]));
-            ldg8(src[w] + 16 * (g4 + 1) + 8, *reinterpret_cast<float(*)[8]>(&nxt[w][8]));
-          }
-        }
+        if (g4 < 3) load16(g4 + 1, nxt);
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
           const float f0 = cur[0][e] * mul[0], f1 = cur[1][e] * mul[1];
@@ -409,11 +406,8 @@ __global__ void __launch_bounds__(128) nif_dz_edge_kernel(const Plan pl, const D
 int nif_tc_bwd_data_impl(const Plan& pl, long long B, const float* z, const float* x, const float* packed,
                          const float* save, const float* du, float* da, float* dz, unsigned* maxes,
                          cudaStream_t st) {
-  if (!pl.tc || pl.NP != 64 || pl.H < 1 || pl.variant == NIF_VARIANT_SIREN_RES || pl.K < 1) return NIF_E_UNSUPPORTED;
+  if (!nif_plan_uses_tc(pl)) return NIF_E_UNSUPPORTED;
   const size_t smem = tcb_smem_bytes(pl.KP);
-  if (smem > 227 * 1024) return NIF_E_UNSUPPORTED;
-  // the row-owning threads move 32-byte sectors (256-bit loads / stores)
-  if ((reinterpret_cast<uintptr_t>(save) | reinterpret_cast<uintptr_t>(da)) & 31) return NIF_E_UNSUPPORTED;
   TcBwdArgs a;
   a.B = B;
   a.total_pairs = (B + 255) / 256;
@@ -467,8 +461,7 @@ struct TcWgtArgs {
 #define TCW_A_BYTES 16384u   // [128 (kappa_l, i) x 64 (b)] fp16, MN-major
 #define TCW_B_BYTES 8192u    // [64 (j) x 64 (b)] fp16, MN-major
 #define TCW_SLOT_BYTES (4 * TCW_A_BYTES + 2 * TCW_B_BYTES)  // A[q][hi|lo], B[hi|lo]
-#define TCW_ROW_STRIDE 272u                      // staged fp32 row (256 B) padded by 16 B: conflict-free per-row reads
-#define TCW_STAGE_BYTES (64 * TCW_ROW_STRIDE)      // the h rows of one 64-row sub-tile
+#define TCW_STAGE_BYTES 16384u                     // the h rows of one 64-row sub-tile: two 32-row groups of the tiled stash
 
 // MN-major core-matrix layout of a [MN x 64] tile: 8 (k) x 16 B (8 consecutive mn) core matrices,
 // offset(mn, k) = (mn/8) * 1024 + (k/8) * 128 + (k%8) * 16 + (mn%8) * 2
@@ -499,7 +492,7 @@ __device__ __forceinline__ void tcw_split8(const float (&v)[8], float sc, uint4&
 
 __global__ void __launch_bounds__(TCW_THREADS, 1) nif_tc_bwd_weight_kernel(const Plan pl, const TcWgtArgs a) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  __shared__ uint64_t slot_full[2], slot_empty[2], st_full[2], done_bar;
+  __shared__ uint64_t slot_full[2], slot_empty[2], done_bar;
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int K = pl.K, K1 = pl.K + 1, H = pl.H;
@@ -514,7 +507,6 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) nif_tc_bwd_weight_kernel(const
   if (tid == 0) {
     mbar_init(&slot_full[0], 128); mbar_init(&slot_full[1], 128);
     mbar_init(&slot_empty[0], 1); mbar_init(&slot_empty[1], 1);
-    mbar_init(&st_full[0], 1); mbar_init(&st_full[1], 1);
     mbar_init(&done_bar, 1);
     mbar_fence_init();
   }
@@ -570,18 +562,24 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) nif_tc_bwd_weight_kernel(const
     unsigned char* B_hi = slot + 4 * TCW_A_BYTES;
     unsigned char* B_lo = B_hi + TCW_B_BYTES;
     const uint32_t koff = (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 16u;  // this row's position along k
-    const float* hsrc = a.save + (long long)h * a.B * 64;        // h_m, m = h + 1 -> stash slot h
-    const float* dsrc = a.da + (long long)(h + 1) * a.B * 64;    // da_m
+    const long long slot_floats = nif_tiled_rows(a.B) * 64;
+    const float* hsrc = a.save + (long long)h * slot_floats;        // h_m, m = h + 1 -> stash slot h (tiled layout)
+    const float* dsrc = a.da + (long long)(h + 1) * slot_floats;    // da_m (tiled layout)
     const int kk0 = 4 * pg + 2 * q;
-    // fp32 row staging: every row of the sub-tile is fetched by one cp.async.bulk (issued by the thread that
-    // owns it) into a padded shared-memory row; the copies of sub-tile t+2 fly while sub-tile t is converted.
+    // fp32 row staging: in the tiled stash a 64-row sub-tile is one contiguous 16 KB block; the slot's 128 threads
+    // fetch it with cp.async (8 x 16 B each, fully coalesced), and the copy of sub-tile t+2 flies while sub-tile t is
+    // converted.  Row r of the block reads its column quads at (r >> 5) * 8 KB + quad * 512 + (r & 31) * 16:
+    // consecutive rows hit consecutive banks.
     unsigned char* stg = smem + 2 * TCW_SLOT_BYTES + sl * TCW_STAGE_BYTES;
+    const int ts = tid & 127;  // thread index inside the slot
     auto stage_rows = [&](long long t) {
-      const long long bs = r0 + t * 64;
-      long long nvalid = a.B - bs;
-      nvalid = nvalid < 0 ? 0 : (nvalid > 64 ? 64 : nvalid);
-      if (q == 0 && r == 0) mbar_expect_tx(&st_full[sl], (uint32_t)(nvalid * 256));
-      if (q == 0 && r < nvalid) bulk_g2s(stg + r * TCW_ROW_STRIDE, hsrc + (bs + r) * 64, 256, &st_full[sl]);
+      const unsigned char* src = reinterpret_cast<const unsigned char*>(hsrc + nif_tiled_row(r0 + t * 64));
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint32_t off = (uint32_t)(ts + i * 128) * 16u;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(stg + off)), "l"(src + off) : "memory");
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
     };
     if (sl < nsub) stage_rows(sl);
     long long n_mine = 0;
@@ -599,11 +597,12 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) nif_tc_bwd_weight_kernel(const
       // from the staged rows)
       float4 hq[16], dq[8];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) dq[c] = live ? ldg4(dsrc + b * 64 + 32 * q + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
-      mbar_wait(&st_full[sl], (uint32_t)(n_mine & 1));
+      for (int c = 0; c < 8; ++c) dq[c] = live ? ldg4(dsrc + nif_tiled_row(b) + (8 * q + c) * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      named_bar_sync(1 + sl, 128);  // every thread's part of the block has landed
 #pragma unroll
       for (int c = 0; c < 16; ++c)
-        hq[c] = live ? *reinterpret_cast<const float4*>(stg + r * TCW_ROW_STRIDE + c * 16) : make_float4(0.f, 0.f, 0.f, 0.f);
+        hq[c] = live ? *reinterpret_cast<const float4*>(stg + (r >> 5) * 8192 + c * 512 + (r & 31) * 16) : make_float4(0.f, 0.f, 0.f, 0.f);
       named_bar_sync(1 + sl, 128);  // every thread of the slot has its row in registers
       if (t + 2 < nsub) stage_rows(t + 2);
       // wait until the MMAs that read this slot two sub-tiles ago have completed
@@ -674,7 +673,7 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) nif_tc_bwd_weight_kernel(const
 
 int nif_tc_bwd_weight_impl(const Plan& pl, long long B, const float* z, const float* save, const float* da,
                            const unsigned* maxes, int S, long long rows_per_split, float* part, cudaStream_t st) {
-  if (!pl.tc || pl.NP != 64 || pl.H < 1) return NIF_E_UNSUPPORTED;
+  if (!nif_plan_uses_tc(pl)) return NIF_E_UNSUPPORTED;
   TcWgtArgs a;
   a.B = B; a.rows_per_split = rows_per_split; a.S = S;
   a.z = z; a.save = save; a.da = da; a.maxes = maxes; a.part = part;

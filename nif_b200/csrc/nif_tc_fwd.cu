@@ -195,6 +195,7 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) nif_tc_fwd_kernel(const Plan p
     const float* C_all = a.packed + pl.off_C;
     const float* invB = a.packed + pl.off_TCS;
     const float* invX = a.packed + pl.off_TCS2;
+    const long long slot_floats = nif_tiled_rows(a.B) * 64;  // one stash slot
     const uint32_t row_off = (uint32_t)(r >> 3) * TC_SBO + (uint32_t)(r & 7) * 16u;
     long long g = 0;  // chunk counter (accumulator phases), advances exactly like the MMA issuer's
     for (long long p = 0; p < my_pairs; ++p) {
@@ -262,8 +263,8 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) nif_tc_fwd_kernel(const Plan p
       // activation / residual / stash for layer m given pre-activations in `pre`; result in hcur.
       auto finish_layer = [&](int m, float (&pre)[64]) {
         const int res = plan_res(pl, m);  // 0 or 1 on this path (res-blocks use the CUDA-core kernel)
-        float* sh = a.save + (long long)m * a.B * 64 + b * 64;            // h_{m+1}
-        float* sd = a.save + (long long)(H + 1 + m) * a.B * 64 + b * 64;  // d_m
+        float* sh = a.save + (long long)m * slot_floats + nif_tiled_row(b);            // h_{m+1}, tiled layout
+        float* sd = a.save + (long long)(H + 1 + m) * slot_floats + nif_tiled_row(b);  // d_m
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           float hold[8];
@@ -303,10 +304,11 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) nif_tc_fwd_kernel(const Plan p
             hcur[j] = o;
             dch[e] = d;
           }
-          if (SAVE && live) {
-            stg8(sh + 8 * c, hcur[8 * c], hcur[8 * c + 1], hcur[8 * c + 2], hcur[8 * c + 3], hcur[8 * c + 4], hcur[8 * c + 5],
-                 hcur[8 * c + 6], hcur[8 * c + 7]);
-            stg8(sd + 8 * c, dch[0], dch[1], dch[2], dch[3], dch[4], dch[5], dch[6], dch[7]);
+          if (SAVE && live) {  // column quads 2c, 2c+1: a warp writes 512 contiguous bytes per store
+            *reinterpret_cast<float4*>(sh + (2 * c) * 128) = make_float4(hcur[8 * c], hcur[8 * c + 1], hcur[8 * c + 2], hcur[8 * c + 3]);
+            *reinterpret_cast<float4*>(sh + (2 * c + 1) * 128) = make_float4(hcur[8 * c + 4], hcur[8 * c + 5], hcur[8 * c + 6], hcur[8 * c + 7]);
+            *reinterpret_cast<float4*>(sd + (2 * c) * 128) = make_float4(dch[0], dch[1], dch[2], dch[3]);
+            *reinterpret_cast<float4*>(sd + (2 * c + 1) * 128) = make_float4(dch[4], dch[5], dch[6], dch[7]);
           }
         }
       };
@@ -424,13 +426,19 @@ static int launch_tcf(const Plan& pl, const TcFwdArgs& a, cudaStream_t st) {
   return NIF_OK;
 }
 
+size_t nif_tcb_smem_bytes(int KP);
+// One static predicate for forward and reverse (the stash layout depends on it): shapes the tensor-core kernels cover.
+bool nif_plan_uses_tc(const Plan& pl) {
+  if (!pl.tc || pl.NP != 64 || pl.H < 1 || pl.variant == NIF_VARIANT_SIREN_RES || pl.K < 1) return false;
+  if (tcf_smem_bytes(pl.KP, pl.KZ, pl.si) > 227 * 1024 || pl.LPC * pl.KZ > 128) return false;
+  return nif_tcb_smem_bytes(pl.KP) <= 227 * 1024;
+}
+
 // returns NIF_E_UNSUPPORTED (without setting an error) when the shape does not fit this kernel, so that the
 // dispatcher can use the CUDA-core kernel instead
 int nif_tc_forward_impl(const Plan& pl, long long B, const float* z, const float* x, const float* packed, float* u,
                         float* save, cudaStream_t st) {
-  if (!pl.tc || pl.NP != 64 || pl.H < 1 || pl.variant == NIF_VARIANT_SIREN_RES) return NIF_E_UNSUPPORTED;
-  if (tcf_smem_bytes(pl.KP, pl.KZ, pl.si) > 227 * 1024 || pl.LPC * pl.KZ > 128) return NIF_E_UNSUPPORTED;
-  if (reinterpret_cast<uintptr_t>(save) & 31) return NIF_E_UNSUPPORTED;  // stash rows are written as 32-byte sectors
+  if (!nif_plan_uses_tc(pl)) return NIF_E_UNSUPPORTED;
   TcFwdArgs a;
   a.B = B;
   a.total_pairs = (B + 255) / 256;

@@ -110,7 +110,9 @@ class FusedShapeNet:
         if x.shape[-1] != self.si:
             raise NifError(f"x must have {self.si} columns")
         u = torch.empty(groups * B, self.so, dtype=torch.float32, device=x.device)
-        stash = torch.empty(self.save_floats_per_row * B, dtype=torch.float32, device=x.device) if save else None
+        # (rows rounded up to 64: the tensor-core path tiles the stash in row groups)
+        stash = (torch.empty(self.save_floats_per_row * ((B + 63) // 64 * 64), dtype=torch.float32, device=x.device)
+                 if save else None)
         check(_lib.lib().nif_forward(C.byref(self.desc), groups, B, _ptr(z) if self.K > 0 else None, _ptr(x),
                                      1 if x_shared else 0, _ptr(packed), _ptr(u), _ptr(stash), _stream()),
               "nif_forward")
