@@ -537,6 +537,7 @@ struct EdgeArgs {
   float* part;  // [S][K+1][Q]
   int no_bias;  // tangent-adjoint pass: the bias-row columns are zero
   int tiled;    // da / save are in the tiled layout of the tensor-core path (nif_common.cuh), NP = 64
+  int q_begin, q_end;  // columns handled by this launch (the tensor-core thin-term kernel takes the rest)
 };
 
 // Register-tiled batch reduction: a thread owns 4 columns x 4 latent coordinates; a CTA owns 64 columns x KG groups
@@ -574,8 +575,8 @@ __global__ void __launch_bounds__(16 * KG * RS) nif_bwd_edge_kernel(const Plan p
   float scale = 1.f;
   {
     const long long slot = a.tiled ? nif_tiled_rows(a.B) * 64 : a.B * NP;  // floats per da / stash slot
-    int r = blockIdx.x * 64 + fc;
-    if (fl < FL && r < a.Q) {
+    int r = a.q_begin + blockIdx.x * 64 + fc;
+    if (fl < FL && r < a.q_end) {
       if (r < (H + 1) * NP) {
         const int m = r / NP, j = r % NP;
         if (!a.no_bias) { Ap = a.da + (long long)m * slot + (a.tiled ? nif_tiled_col(j) : j); sA = NP; a_tiled = a.tiled; }
@@ -683,8 +684,8 @@ __global__ void __launch_bounds__(16 * KG * RS) nif_bwd_edge_kernel(const Plan p
     if (kk < K1) {
 #pragma unroll
       for (int f = 0; f < 4; ++f) {
-        const int q = blockIdx.x * 64 + 4 * qg + f;
-        if (q < a.Q) a.part[((long long)s * K1 + kk) * a.Q + q] = acc[e][f];
+        const int q = a.q_begin + blockIdx.x * 64 + 4 * qg + f;
+        if (q < a.q_end) a.part[((long long)s * K1 + kk) * a.Q + q] = acc[e][f];
       }
     }
   }
@@ -736,6 +737,9 @@ int nif_tc_bwd_data_impl(const Plan& pl, long long B, const float* z, const floa
                          cudaStream_t st);
 int nif_tc_bwd_weight_impl(const Plan& pl, long long B, const float* z, const float* save, const float* da,
                            const unsigned* maxes, int S, long long rows_per_split, float* part, cudaStream_t st);
+int nif_tc_bwd_edge_impl(const Plan& pl, long long B, const float* z, const float* x, const float* save, const float* da,
+                         const float* du, const unsigned* maxes, int S, long long rows_per_split, int Q, float* part,
+                         cudaStream_t st);
 
 
 static long long round_up(long long v, long long m) { return (v + m - 1) / m * m; }
@@ -784,7 +788,7 @@ GradWs nif_grad_ws_layout(const Plan& pl, long long B) {
 static cudaError_t launch_edge(const Plan& pl, const EdgeArgs& e, const GradWs& w, cudaStream_t st) {
   const int K1 = pl.K + 1;
   const int KC = nif_edge_kc(K1);
-  dim3 grid((unsigned)((w.Q + 63) / 64), (unsigned)w.S_e, (unsigned)((K1 + KC - 1) / KC));
+  dim3 grid((unsigned)((e.q_end - e.q_begin + 63) / 64), (unsigned)w.S_e, (unsigned)((K1 + KC - 1) / KC));
   switch (KC) {
     case 4: nif_bwd_edge_kernel<1, 16><<<grid, 256, 0, st>>>(pl, e); break;
     case 8: nif_bwd_edge_kernel<2, 8><<<grid, 256, 0, st>>>(pl, e); break;
@@ -824,6 +828,7 @@ int nif_weight_grads_impl(const Plan& pl, long long B, const float* z, const flo
   EdgeArgs e;
   e.B = B; e.rows_per_split = w.rows_e; e.S = w.S_e; e.Q = w.Q;
   e.z = z; e.x = x; e.save = save; e.da = ws + w.da; e.du = du; e.part = ws + w.part_e; e.no_bias = no_bias; e.tiled = 0;
+  e.q_begin = 0; e.q_end = w.Q;
   NIF_CUDA_CHECK(launch_edge(pl, e, w, st));
   return nif_unpack_grad_impl(pl, w.S_h, ws + w.part_h, w.S_e, ws + w.part_e, w.Q, dw_h, db_h, beta, st);
 }
@@ -853,7 +858,7 @@ int nif_backward_impl(const Plan& pl, long long B, const float* z, const float* 
   if (rc != NIF_OK) return rc;
 
   bool wgt_done = false;
-  int S_used = w.S_h;
+  int S_used = w.S_h, S_e_used = w.S_e;
   if (tc_data && pl.H > 0) {  // tensor-core weight-gradient GEMM (needs the maxima recorded by the TC data pass)
     // one CTA per SM: as many batch splits as fit one wave (never more than the workspace was sized for)
     const int items = pl.H * ((pl.KP + 3) / 4);
@@ -873,9 +878,21 @@ int nif_backward_impl(const Plan& pl, long long B, const float* z, const float* 
     EdgeArgs e;
     e.B = B; e.rows_per_split = w.rows_e; e.S = w.S_e; e.Q = w.Q;
     e.z = z; e.x = x; e.save = save; e.da = ws + w.da; e.du = du; e.part = ws + w.part_e; e.no_bias = 0; e.tiled = 1;
-    NIF_CUDA_CHECK(launch_edge(pl, e, w, st));
+    e.q_begin = 0; e.q_end = w.Q;
+    // thin terms on the tensor cores: one wave of CTAs (column-block pairs x batch splits)
+    const int ncta_x = (pl.H + 1 + pl.si + pl.so + 1 + 1) / 2;
+    int S_tc = 148 / ncta_x;
+    if (S_tc < 1) S_tc = 1;
+    if (S_tc > w.S_e) S_tc = w.S_e;
+    const long long rows_tc = round_up((B + S_tc - 1) / S_tc, 64);
+    S_tc = (int)((B + rows_tc - 1) / rows_tc);
+    const int rce = nif_tc_bwd_edge_impl(pl, B, z, x, save, ws + w.da, du, reinterpret_cast<const unsigned*>(ws + w.maxes),
+                                         S_tc, rows_tc, w.Q, ws + w.part_e, st);
+    if (rce == NIF_OK) S_e_used = S_tc;
+    else if (rce != NIF_E_UNSUPPORTED) return rce;
+    else NIF_CUDA_CHECK(launch_edge(pl, e, w, st));
   }
-  return nif_unpack_grad_impl(pl, S_used, ws + w.part_h, w.S_e, ws + w.part_e, w.Q, dw_h, db_h, beta, st);
+  return nif_unpack_grad_impl(pl, S_used, ws + w.part_h, S_e_used, ws + w.part_e, w.Q, dw_h, db_h, beta, st);
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -292,7 +292,12 @@ struct DzEdgeArgs {
   long long B;
   const float *x, *packed, *save, *da, *du;
   float* dz;
+  unsigned* maxes;  // + NIF_MAX_X / NIF_MAX_DU / NIF_MAX_HL: operand-scale bounds for nif_tc_bwd_edge_kernel
 };
+// slots of the maxima buffer written here (the data pass owns [0, 2H + 2))
+#define NIF_MAX_X 192    // + i : max |x[:, i]|
+#define NIF_MAX_DU 200   // + c : max |du[:, c]|
+#define NIF_MAX_HL 208   //       max |h_{H+1}|
 
 // dz_edge[b][:] = F[b][:] @ G  with per-row features F (Q of them) and a shared coefficient matrix G [Q][K]:
 //   q in [0,(H+1)*64)            F = da_m[b][j]                 G = C_m[kappa][j]
@@ -324,6 +329,13 @@ __global__ void __launch_bounds__(128) nif_dz_edge_kernel(const Plan pl, const D
 #pragma unroll
     for (int k = 0; k < KT; ++k) acc[w][k] = 0.f;
 
+  if (k0 == 0) {  // bounds of the thin-term operands (rows this thread owns; dead rows repeat row 0)
+    for (int i = 0; i < si; ++i)
+      warp_atomic_max(&a.maxes[NIF_MAX_X + i], fmaxf(fabsf(__ldg(&a.x[bb[0] * si + i])), fabsf(__ldg(&a.x[bb[1] * si + i]))));
+    for (int c = 0; c < so; ++c)
+      warp_atomic_max(&a.maxes[NIF_MAX_DU + c], fmaxf(fabsf(__ldg(&a.du[bb[0] * so + c])), fabsf(__ldg(&a.du[bb[1] * so + c]))));
+  }
+  float hl_max = 0.f;
   const int nslab = (H + 1) + si + so + 1;  // slabs of (up to) 64 features
   for (int sb = 0; sb < nslab; ++sb) {
     __syncthreads();  // the previous slab has been consumed
@@ -359,6 +371,10 @@ __global__ void __launch_bounds__(128) nif_dz_edge_kernel(const Plan pl, const D
 #pragma unroll 1
       for (int g4 = 0; g4 < 4; ++g4) {
         if (g4 < 3) load16(g4 + 1, nxt);
+        if (k0 == 0 && sb == H + 1 + si) {  // the h_{H+1} rows pass through here: record their magnitude
+#pragma unroll
+          for (int e = 0; e < 16; ++e) hl_max = fmaxf(hl_max, fmaxf(fabsf(cur[0][e]), fabsf(cur[1][e])));
+        }
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
           const float f0 = cur[0][e] * mul[0], f1 = cur[1][e] * mul[1];
@@ -393,6 +409,7 @@ __global__ void __launch_bounds__(128) nif_dz_edge_kernel(const Plan pl, const D
       }
     }
   }
+  if (k0 == 0) warp_atomic_max(&a.maxes[NIF_MAX_HL], hl_max);
 #pragma unroll
   for (int w = 0; w < 2; ++w)
     if (live[w]) {
@@ -412,7 +429,7 @@ int nif_tc_bwd_data_impl(const Plan& pl, long long B, const float* z, const floa
   a.B = B;
   a.total_pairs = (B + 255) / 256;
   a.z = z; a.x = x; a.packed = packed; a.save = save; a.du = du; a.da = da; a.dz = dz; a.maxes = maxes;
-  NIF_CUDA_CHECK(cudaMemsetAsync(maxes, 0, sizeof(unsigned) * (2 * pl.H + 4), st));
+  NIF_CUDA_CHECK(cudaMemsetAsync(maxes, 0, sizeof(unsigned) * 256, st));
   NIF_CUDA_CHECK(cudaFuncSetAttribute(nif_tc_bwd_data_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int dev = 0, sms = 0;
   NIF_CUDA_CHECK(cudaGetDevice(&dev));
@@ -422,7 +439,7 @@ int nif_tc_bwd_data_impl(const Plan& pl, long long B, const float* z, const floa
   nif_tc_bwd_data_kernel<<<(unsigned)grid, TCB_THREADS, smem, st>>>(pl, a);
   NIF_CUDA_CHECK(cudaGetLastError());
   DzEdgeArgs e;
-  e.B = B; e.x = x; e.packed = packed; e.save = save; e.da = da; e.du = du; e.dz = dz;
+  e.B = B; e.x = x; e.packed = packed; e.save = save; e.da = da; e.du = du; e.dz = dz; e.maxes = maxes;
   for (int k0 = 0; k0 < pl.K;) {  // up to 32 latent coordinates per pass (the table is KG = ceil4(K) wide)
     const int left = pl.KG - k0;
     const unsigned grid = (unsigned)((B + 255) / 256);
