@@ -278,7 +278,7 @@ def run_ours(args):
         "roofline": {"bound": "tensor", "kernel": kernel_name, "achieved": ach_fwd,
                      "peak": tensor_peak, "unit": "TFLOP/s", "frac": ach_fwd / tensor_peak, "traffic": traffic,
                      "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full "
-                                     "(profiles/r01_ncu_tc_kernels.txt): the activation stash written for the reverse pass",
+                                     "(profiles/r01_ncu_step_final.txt): the activation stash written for the reverse pass",
                      "peak_source": f"bf16_tflops_sustained (dense 16-bit MMA), {peak_src}",
                      "note": "achieved = ALGORITHMIC FLOPs (2KP+2Ws per row) / launch time; the fp32-grade split "
                              "issues 3 tensor-core MACs per algorithmic MAC, so 1/3 of peak is this path's ceiling",
