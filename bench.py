@@ -109,7 +109,7 @@ class ClockSampler:
         self.p = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms",
-                                       "100", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "20", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
 
@@ -172,9 +172,8 @@ def run_ours(args):
         return model._train_step(inp_d[i % nb], tgt_d[i % nb], None, gb)
 
     def step_e2e(i):
-        a = inp_pin[i % nb].to(dev, non_blocking=True)
-        b = tgt_pin[i % nb].to(dev, non_blocking=True)
-        return float(model._train_step(a, b, None, gb))  # device -> host read of the step's loss
+        # the public call: pinned HOST batch in (copied to the device inside), the step's loss read back as a float
+        return model.train_on_batch(inp_pin[i % nb], tgt_pin[i % nb], global_batch=gb)
 
     def timed(fn, steps, warmup):
         for i in range(warmup):
@@ -195,8 +194,8 @@ def run_ours(args):
 
     sampler = ClockSampler(dev.index if dev.index is not None else 0) if rank == 0 else None
     ms_step = timed(step_resident, args.steps, args.warmup)
-    clocks = sampler.stop() if sampler else None
     ms_e2e = timed(step_e2e, args.steps, max(3, args.warmup // 2))
+    clocks = sampler.stop() if sampler else None  # sampled under load across both timed regions
 
     if rank != 0:
         dp.shutdown()
@@ -302,7 +301,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     args = ap.parse_args()

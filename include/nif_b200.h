@@ -147,6 +147,13 @@ int nif_adam_step(int64_t n, float* p, const float* g, float* m, float* v, doubl
                   double b1, double b2, double eps, int64_t t, float l1, float l2, float g_scale,
                   void* stream);
 
+/* The same update with the bias-corrected step size  alpha = lr*sqrt(1-b2^t)/(1-b1^t)  read from DEVICE memory
+ * (one float, formed by the caller in double like nif_adam_step does).  Nothing that changes from step to step is a
+ * launch argument, so a whole optimisation step (trunk, forward, loss, reverse passes, this update) can be captured
+ * once in a CUDA graph and replayed: the caller rewrites *alpha_dev (stream-ordered) before every replay. */
+int nif_adam_step_dev(int64_t n, float* p, const float* g, float* m, float* v, const float* alpha_dev,
+                      double b1, double b2, double eps, float l1, float l2, float g_scale, void* stream);
+
 /* ParameterNet trunk (everything before the last linear layer): Dense(act) -> nlayers x MLP_SimpleShortCut ->
  * Dense(latent), i.e. _call_parameter_net up to the bottleneck (nif/model.py:326-343, 176-216, 668-720;
  * nif/layers/mlp.py:148-160).  theta is the trunk's weight vector in the column order

@@ -200,6 +200,17 @@ extern "C" int nif_adam_step(int64_t n, float* p, const float* g, float* m, floa
   return nif_adam_impl(n, p, g, m, v, lr, b1, b2, eps, t, l1, l2, g_scale, static_cast<cudaStream_t>(stream));
 }
 
+int nif_adam_dev_impl(long long n, float* p, const float* g, float* m, float* v, const float* alpha_dev, double b1,
+                      double b2, double eps, float l1, float l2, float gs, cudaStream_t st);
+extern "C" int nif_adam_step_dev(int64_t n, float* p, const float* g, float* m, float* v, const float* alpha_dev,
+                                 double b1, double b2, double eps, float l1, float l2, float g_scale, void* stream) {
+  if (n < 0) { nif_set_error("nif_adam_step_dev: n=%lld", (long long)n); return NIF_E_BAD_ARG; }
+  if (n == 0) return NIF_OK;
+  NIF_REQUIRE_PTR(p); NIF_REQUIRE_PTR(g); NIF_REQUIRE_PTR(m); NIF_REQUIRE_PTR(v);
+  if (!alpha_dev) { nif_set_error("nif_adam_step_dev: alpha_dev is null"); return NIF_E_BAD_ARG; }
+  return nif_adam_dev_impl(n, p, g, m, v, alpha_dev, b1, b2, eps, l1, l2, g_scale, static_cast<cudaStream_t>(stream));
+}
+
 // ---- ParameterNet trunk --------------------------------------------------------------------------------
 int nif_make_trunk_plan(int pi, int K, int n_st, int l_st, int act, Plan* out);
 int nif_trunk_forward_impl(const Plan& pl, long long B, const float* p_in, const float* theta, float* z, float* save,

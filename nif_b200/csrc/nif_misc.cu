@@ -135,9 +135,12 @@ __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, 
   p -= alpha * m / (sqrtf(v) + eps);
 }
 
+// alpha_dev != nullptr: the step size comes from device memory (graph-replayed steps, nif_adam_step_dev)
 __global__ void __launch_bounds__(256) nif_adam_kernel(long long n, float* __restrict__ p, const float* __restrict__ g,
                                                        float* __restrict__ m, float* __restrict__ v, float alpha,
+                                                       const float* __restrict__ alpha_dev,
                                                        float b1, float b2, float eps, float l1, float l2, float gs) {
+  if (alpha_dev) alpha = __ldg(alpha_dev);
   const long long n4 = n / 4;
   const long long stride = 256LL * gridDim.x;
   for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n4; i += stride) {
@@ -164,8 +167,20 @@ int nif_adam_impl(long long n, float* p, const float* g, float* m, float* v, dou
   long long nblk = (n / 4 + 255) / 256;
   if (nblk < 1) nblk = 1;
   if (nblk > 148 * 8) nblk = 148 * 8;
-  nif_adam_kernel<<<(unsigned)nblk, 256, 0, st>>>(n, p, g, m, v, (float)alpha, (float)(1.0 - b1),
+  nif_adam_kernel<<<(unsigned)nblk, 256, 0, st>>>(n, p, g, m, v, (float)alpha, nullptr, (float)(1.0 - b1),
                                                   (float)(1.0 - b2), (float)eps, l1, l2, gs);
+  NIF_CUDA_CHECK(cudaGetLastError());
+  return NIF_OK;
+}
+
+int nif_adam_dev_impl(long long n, float* p, const float* g, float* m, float* v, const float* alpha_dev, double b1,
+                      double b2, double eps, float l1, float l2, float gs, cudaStream_t st) {
+  if (n <= 0) return NIF_OK;
+  long long nblk = (n / 4 + 255) / 256;
+  if (nblk < 1) nblk = 1;
+  if (nblk > 148 * 8) nblk = 148 * 8;
+  nif_adam_kernel<<<(unsigned)nblk, 256, 0, st>>>(n, p, g, m, v, 0.f, alpha_dev, (float)(1.0 - b1), (float)(1.0 - b2),
+                                                  (float)eps, l1, l2, gs);
   NIF_CUDA_CHECK(cudaGetLastError());
   return NIF_OK;
 }

@@ -8,6 +8,7 @@ called at the start of every epoch, short last batch kept, predict() batched.
 """
 from __future__ import annotations
 
+import math
 import os
 import time
 from typing import Callable, Dict, Iterable, List, Optional, Sequence
@@ -50,6 +51,23 @@ class Adam:
         self.iterations += 1
         ops.adam_step(theta, grad, self._m, self._v, self.learning_rate, self.iterations, self.beta_1, self.beta_2,
                       self.epsilon, l1, l2, g_scale)
+
+    # graph-replayed steps: the update is recorded once with its step size in device memory (record_apply, inside the
+    # capture); before every replay the host forms this step's alpha exactly like nif_adam_step does and stores it.
+    def record_apply(self, theta: torch.Tensor, grad: torch.Tensor, l1=0.0, l2=0.0, g_scale=1.0):
+        ops.adam_step_dev(theta, grad, self._m, self._v, self._alpha_dev, self.beta_1, self.beta_2, self.epsilon, l1, l2,
+                          g_scale)
+
+    def prepare_replay(self, theta: torch.Tensor):
+        self._ensure(theta)
+        if getattr(self, "_alpha_dev", None) is None or self._alpha_dev.device != theta.device:
+            self._alpha_dev = torch.zeros(4, dtype=torch.float32, device=theta.device)  # 16 bytes: aligned like the rest
+
+    def advance_replay(self):
+        self.iterations += 1
+        t = float(self.iterations)
+        alpha = self.learning_rate * math.sqrt(1.0 - self.beta_2 ** t) / (1.0 - self.beta_1 ** t)
+        self._alpha_dev.fill_(alpha)  # by-value launch argument of a fill kernel: stream-ordered, no host buffer to race on
 
 
 class SobolevMSE:
@@ -188,6 +206,8 @@ class Model:
         self._loss_buf = None
         self._packed = None
         self.dist = None  # set by nif_b200.distributed.DataParallel
+        self.use_graph: Optional[bool] = None  # None: NIF_B200_GRAPH env (default on); see _train_step_graph
+        self._graphs: Dict[tuple, dict] = {}
 
     # ---- plumbing -----------------------------------------------------------------------------------
     def _dev(self, a, pinned_ok=True) -> torch.Tensor:
@@ -338,7 +358,9 @@ class Model:
         return u.view(zg.shape[0], xs.shape[0], n.so_dim)
 
     # ---- training -----------------------------------------------------------------------------------
-    def compile(self, optimizer=None, loss="mse", metrics=None, **_kw):
+    def compile(self, optimizer=None, loss="mse", metrics=None, graph: Optional[bool] = None, **_kw):
+        self.use_graph = graph
+        self._graphs = {}
         if self.kind == "jacobian":
             if not isinstance(loss, SobolevMSE):
                 raise NifError("a JacobianLayer model trains with nif_b200.SobolevMSE (tutorial 8's Sobolov_MSE)")
@@ -371,28 +393,14 @@ class Model:
         gb = int(global_batch) if global_batch else B
         if self._loss_buf is None:
             self._loss_buf = torch.zeros(1, dtype=torch.float32, device=n.device)
+        if not callable(self.loss) and n._trunk is not None:
+            if B > 0 and self._graph_enabled():
+                return self._train_step_graph(inp, tgt, sw, gb)
+            self._loss_buf.zero_()
+            self._fused_step(inp, tgt, sw, gb, self.optimizer.apply)
+            return self._loss_buf
         self._loss_buf.zero_()
         xs = inp[:, n.pi_dim: n.pi_dim + n.si_dim].contiguous()
-        if not callable(self.loss) and n._trunk is not None:
-            # fully fused step: trunk, hyper-network head + ShapeNet, loss and both reverse passes are library kernels;
-            # every gradient is written (beta = 0) straight into the flat gradient buffer.
-            p_in = inp[:, : n.pi_dim].contiguous()
-            z, tstash = n._trunk.forward(p_in, n.theta_trunk, save=True)
-            packed = self._packed_weights()
-            u, stash = eng.forward(z, xs, packed, save=True)
-            dz = eng.mse_backward(z, xs, packed, u, stash, tgt, sw, 1.0 / gb, self._loss_buf,
-                                  n._gviews[n._last_names[0]], n._gviews[n._last_names[1]], 0.0)
-            # data parallel: the last linear layer's gradient (almost all of the buffer) is summed across ranks
-            # while the trunk's reverse pass runs; the small trunk gradient follows
-            h_head = self.dist.allreduce_start(n.grad[n._n_trunk:]) if self.dist is not None else None
-            n._trunk.backward(p_in, n.theta_trunk, tstash, dz, n.grad_trunk, 0.0)
-            if self.dist is not None:
-                h_trunk = self.dist.allreduce_start(n.grad_trunk)
-                self.dist.allreduce_finish(h_head)
-                self.dist.allreduce_finish(h_trunk)
-            l1, l2 = n._kernel_regulariser()
-            self.optimizer.apply(n.theta, n.grad, l1, l2)
-            return self._loss_buf
         n.grad.zero_()
         z = n._latent(inp[:, : n.pi_dim])
         if not callable(self.loss):
@@ -413,6 +421,84 @@ class Model:
         l1, l2 = n._kernel_regulariser()
         self.optimizer.apply(n.theta, n.grad, l1, l2)
         return loss
+
+    def _fused_step(self, inp, tgt, sw, gb, apply_update):
+        """Fully fused step: trunk, hyper-network head + ShapeNet, loss and both reverse passes are library kernels;
+        every gradient is written (beta = 0) straight into the flat gradient buffer.  Only stream-ordered work (no
+        host read, no allocation outside torch's caching allocator), so the same body is what a CUDA graph records."""
+        n = self.net
+        eng = n.engine
+        xs = inp[:, n.pi_dim: n.pi_dim + n.si_dim].contiguous()
+        p_in = inp[:, : n.pi_dim].contiguous()
+        z, tstash = n._trunk.forward(p_in, n.theta_trunk, save=True)
+        packed = self._packed_weights()
+        u, stash = eng.forward(z, xs, packed, save=True)
+        dz = eng.mse_backward(z, xs, packed, u, stash, tgt, sw, 1.0 / gb, self._loss_buf,
+                              n._gviews[n._last_names[0]], n._gviews[n._last_names[1]], 0.0)
+        # data parallel: the last linear layer's gradient (almost all of the buffer) is summed across ranks
+        # while the trunk's reverse pass runs; the small trunk gradient follows
+        h_head = self.dist.allreduce_start(n.grad[n._n_trunk:]) if self.dist is not None else None
+        n._trunk.backward(p_in, n.theta_trunk, tstash, dz, n.grad_trunk, 0.0)
+        if self.dist is not None:
+            h_trunk = self.dist.allreduce_start(n.grad_trunk)
+            self.dist.allreduce_finish(h_head)
+            self.dist.allreduce_finish(h_trunk)
+        l1, l2 = n._kernel_regulariser()
+        apply_update(n.theta, n.grad, l1, l2)
+
+    # ---- CUDA-graph replay of the fused step ------------------------------------------------------------------
+    # One optimisation step is 17 kernel launches from Python; at tutorial-1 sizes (512 rows) the launches, not the
+    # kernels, set the step time.  The step body is stream-ordered and allocation-free apart from torch's caching
+    # allocator, so it is recorded once per (rows, global batch, sample-weighted?) and replayed; per step the host
+    # only copies the batch into the graph's input buffers and stores Adam's bias-corrected step size.
+    GRAPH_CACHE = 4
+
+    def _graph_enabled(self) -> bool:
+        g = self.use_graph
+        if g is None:
+            g = os.environ.get("NIF_B200_GRAPH", "1") != "0"
+        return bool(g) and self.dist is None
+
+    def _graph_signature(self):
+        n, opt = self.net, self.optimizer
+        return (n.theta.data_ptr(), n.grad.data_ptr(), opt._m.data_ptr(), opt._v.data_ptr(), opt._alpha_dev.data_ptr(),
+                self._loss_buf.data_ptr(), id(opt), opt.beta_1, opt.beta_2, opt.epsilon, n._kernel_regulariser())
+
+    def _train_step_graph(self, inp, tgt, sw, gb) -> torch.Tensor:
+        n, opt = self.net, self.optimizer
+        opt.prepare_replay(n.theta)
+        key = (inp.shape[0], gb, sw is not None)
+        ent = self._graphs.get(key)
+        if ent is not None and ent.get("sig") not in (None, self._graph_signature()):
+            ent = None  # parameters / optimiser state were re-created: the recorded pointers are stale
+        if ent is None:
+            # first visit of this shape: run it eagerly (this also sizes the persistent workspaces the graph will use)
+            while len(self._graphs) >= self.GRAPH_CACHE:
+                self._graphs.pop(next(iter(self._graphs)))
+            self._graphs[key] = {"sig": None}
+            self._loss_buf.zero_()
+            self._fused_step(inp, tgt, sw, gb, opt.apply)
+            return self._loss_buf
+        if ent["sig"] is None:
+            # second visit: record.  (Capture launches nothing; the replay below performs this step.)
+            ent["inp"], ent["tgt"] = torch.empty_like(inp), torch.empty_like(tgt)
+            ent["sw"] = torch.empty_like(sw) if sw is not None else None
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._loss_buf.zero_()
+                self._fused_step(ent["inp"], ent["tgt"], ent["sw"], gb, opt.record_apply)
+            ent["graph"] = g
+            # buffers whose addresses are baked into the graph stay alive as long as it does
+            ent["keep"] = (n.engine._ws, n._trunk._ws, n._trunk._packed, self._packed, self._loss_buf, n.theta, n.grad,
+                           opt._m, opt._v, opt._alpha_dev)
+            ent["sig"] = self._graph_signature()
+        ent["inp"].copy_(inp, non_blocking=True)
+        ent["tgt"].copy_(tgt, non_blocking=True)
+        if sw is not None:
+            ent["sw"].copy_(sw, non_blocking=True)
+        opt.advance_replay()
+        ent["graph"].replay()
+        return self._loss_buf
 
     # ---- Sobolev training (JacobianLayer inside the loss) ---------------------------------------------------
     def _plan_sobolev(self, loss: "SobolevMSE"):

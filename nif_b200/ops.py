@@ -280,6 +280,14 @@ def adam_step(p, g, m, v, lr, t, b1=0.9, b2=0.999, eps=1e-7, l1=0.0, l2=0.0, g_s
           "nif_adam_step")
 
 
+def adam_step_dev(p, g, m, v, alpha_dev, b1=0.9, b2=0.999, eps=1e-7, l1=0.0, l2=0.0, g_scale=1.0):
+    """The same update with the bias-corrected step size read from the 1-element device tensor `alpha_dev`
+    (graph-replayed steps: no launch argument changes from one step to the next)."""
+    check(_lib.lib().nif_adam_step_dev(p.numel(), _ptr(p), _ptr(g), _ptr(m), _ptr(v), _ptr(alpha_dev), float(b1),
+                                       float(b2), float(eps), float(l1), float(l2), float(g_scale), _stream()),
+          "nif_adam_step_dev")
+
+
 def measure_fp32_peak() -> float:
     v = C.c_double(0.0)
     check(_lib.lib().nif_measure_fp32_peak(C.byref(v)), "nif_measure_fp32_peak")

@@ -508,3 +508,39 @@ def test_sobolev_training_matches_oracle_tutorial8():
     diffs = np.concatenate([np.abs(got[k] - v.numpy()).ravel() for k, v in prm.items()])
     assert float(np.quantile(diffs, 0.999)) < 1e-4, float(np.quantile(diffs, 0.999))
     assert float(diffs.max()) < 4 * 2e-3
+
+
+def test_graph_replayed_steps_equal_eager_steps_bitwise():
+    """The CUDA-graph replay of the fused step (Model._train_step_graph) launches the same kernels on the same
+    buffers as the eager step: after a run that mixes two batch sizes, sample weights and a learning-rate change the
+    parameters, the Adam moments and every reported loss are bit-identical."""
+    import nif_b200
+    cfg_s = {"use_resblock": False, "connectivity": "full", "input_dim": 2, "output_dim": 1, "units": 64, "nlayers": 4,
+             "weight_init_factor": 0.01, "omega_0": 30.0}
+    cfg_p = {"use_resblock": False, "input_dim": 1, "latent_dim": 32, "units": 64, "nlayers": 4, "activation": "swish"}
+    rng = np.random.default_rng(21)
+    batches = []
+    for step in range(9):
+        B = 700 if step % 3 != 2 else 333
+        X = rng.uniform(-1, 1, (B, 3)).astype(np.float32)
+        Y = rng.uniform(-1, 1, (B, 1)).astype(np.float32)
+        sw = rng.uniform(0.5, 1.5, (B,)).astype(np.float32) if step >= 6 and B == 700 else None
+        batches.append((X, Y, sw))
+    runs = {}
+    for graph in (False, True):
+        net = nif_b200.NIFMultiScale(cfg_s, cfg_p, seed=4, device="cuda:0")
+        model = net.build()
+        opt = nif_b200.Adam(1e-3)
+        model.compile(opt, loss="mse", graph=graph)
+        losses = []
+        for step, (X, Y, sw) in enumerate(batches):
+            if step == 5:
+                opt.learning_rate = 2.5e-4  # what LearningRateScheduler does at an epoch boundary
+            losses.append(model.train_on_batch(X, Y, sample_weight=sw))
+        runs[graph] = (net.theta.cpu().clone(), opt._m.cpu().clone(), opt._v.cpu().clone(), losses, opt.iterations)
+        if graph:
+            assert sum(1 for e in model._graphs.values() if e.get("graph") is not None) >= 2  # both sizes were recorded
+    (t0, m0, v0, l0, i0), (t1, m1, v1, l1, i1) = runs[False], runs[True]
+    assert i0 == i1 == len(batches)
+    assert l0 == l1
+    assert torch.equal(t0, t1) and torch.equal(m0, m1) and torch.equal(v0, v1)
