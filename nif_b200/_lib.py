@@ -9,7 +9,8 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnif_b200.so")
+# NIF_B200_LIB: an instrumented build of the same library (tools/tc_trace.py); never a different implementation
+LIB_PATH = os.path.abspath(os.environ["NIF_B200_LIB"]) if os.environ.get("NIF_B200_LIB") else os.path.join(_HERE, "libnif_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 # every symbol include/nif_b200.h declares

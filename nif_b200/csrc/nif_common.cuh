@@ -101,8 +101,27 @@ static __device__ __noinline__ float nif_fold_2pi(float v) {
   const double q = rint((double)v * 0.15915494309189535);
   return (float)fma(-q, 6.283185307179586, (double)v);
 }
+// branch-free core, valid for |v| < 1e5 (NaN propagates).  Callers that evaluate many elements test the whole group
+// once (nif_sincos_fold8) and then run the cores back to back: without a branch per element the compiler interleaves
+// the independent polynomial chains instead of executing them one after the other.
+__device__ __forceinline__ void nif_sincosf_core(float v, float& s, float& c);
 __device__ __forceinline__ void nif_sincosf(float v, float& s, float& c) {
   if (!(fabsf(v) < 1.0e5f)) v = nif_fold_2pi(v);
+  nif_sincosf_core(v, s, c);
+}
+// folds the huge / non-finite members of a group of 8 arguments (one test for the group)
+__device__ __forceinline__ void nif_sincos_fold8(float* v) {
+  float mx = 0.f;
+  bool bad = false;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { mx = fmaxf(mx, fabsf(v[e])); bad |= (v[e] != v[e]); }
+  if (bad || !(mx < 1.0e5f)) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+      if (!(fabsf(v[e]) < 1.0e5f)) v[e] = nif_fold_2pi(v[e]);
+  }
+}
+__device__ __forceinline__ void nif_sincosf_core(float v, float& s, float& c) {
   const float kf = rintf(v * 0.636619747f);
   const int k = __float2int_rn(kf);
   float r = fmaf(kf, -1.57079601e+00f, v);

@@ -65,6 +65,15 @@ __device__ __forceinline__ void tc_mma_split_k64(uint32_t d, uint64_t a_hi, uint
 #pragma unroll
   for (int ks = 0; ks < 4; ++ks) tc_mma_f16(d, a_hi + (uint64_t)(ks * 16), b_hi + (uint64_t)(ks * 16), idesc, 1u);
 }
+// One lane of a converged warp.  The MMA-issuer warps run their whole loop warp-uniformly and put only the tcgen05.mma /
+// commit instructions under this predicate: descriptors and addresses then live in uniform registers.  (Inside an
+// `if (lane == 0)` region the compiler cannot use the uniform datapath and wraps EVERY tcgen05.mma in an
+// elect / 5 x R2UR.BROADCAST / branch loop, ~90 cycles of issue per 64-cycle instruction.)
+__device__ __forceinline__ bool tc_elect_one() {
+  uint32_t p;
+  asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\tselp.b32 %0, 1, 0, q;\n\t}\n" : "=r"(p));
+  return p != 0;
+}
 // arrive on an mbarrier when every tcgen05 op issued so far by this thread has completed
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -172,3 +181,29 @@ __device__ __forceinline__ void tc_store_row_split_fn(unsigned char* tile_hi, un
     *reinterpret_cast<uint4*>(tile_lo + row_off + c * TC_LBO) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
   }
 }
+
+// Optional timeline trace (make -C nif_b200/csrc trace): CTA 0 records clock64() at the hand-offs of its first tile
+// pairs (per translation unit); read back with the reader each kernel file instantiates.  Compiled out of the product
+// build.  Roles: 0 / 1 = epilogue of tile 0 / 1, 2 = MMA issuer of tile 0, 3 = weight-stream producer.
+#ifdef NIF_TRACE
+static __device__ long long g_trace[4][2048];
+static __device__ int g_trace_n[4];
+#define TRACE(role, tag)                                                                  \
+  do {                                                                                    \
+    if (blockIdx.x == 0 && trace_n < 1023) {                                              \
+      g_trace[role][2 * trace_n] = (long long)(tag);                                      \
+      g_trace[role][2 * trace_n + 1] = clock64();                                         \
+      ++trace_n;                                                                          \
+      g_trace_n[role] = 2 * trace_n;                                                      \
+    }                                                                                     \
+  } while (0)
+#define NIF_TRACE_READER(name)                                                            \
+  extern "C" int name(long long* host, int* counts) {                                     \
+    cudaMemcpyFromSymbol(host, g_trace, sizeof(g_trace));                                 \
+    cudaMemcpyFromSymbol(counts, g_trace_n, sizeof(g_trace_n));                           \
+    return 0;                                                                             \
+  }
+#else
+#define TRACE(role, tag) do {} while (0)
+#define NIF_TRACE_READER(name)
+#endif

@@ -12,24 +12,30 @@
 // of the weight-gradient GEMM.
 #include "nif_tc.cuh"
 
+NIF_TRACE_READER(nif_debug_read_trace_bwd)
+
 struct TcBwdArgs {
   long long B, total_pairs;
   const float *z, *x, *packed, *save, *du;
   float* da;        // [(H+1)][B][64]
   float* dz;        // [B][K]
   unsigned* maxes;  // [0..H] max|da_m| bits, [H+1] max|zt| bits, [H+2 .. 2H+2] max|h_m| bits (m = 1..H+1)
+  int nst;          // weight-stream stages (3 where shared memory allows, else 2)
 };
 
 #define TCB_THREADS 384  // 8 epilogue warps + MMA warp + producer warp + 2 idle warps (register donors)
-#define TCB_STAGES 2
+#define TCB_MAX_STAGES 3
 #define TCB_STAGE_BYTES 32768u
 
-size_t nif_tcb_smem_bytes(int KP);
-__host__ __device__ inline size_t tcb_smem_bytes(int KP) {
-  return 4 * (size_t)TC_TILE_BYTES + TCB_STAGES * (size_t)TCB_STAGE_BYTES + 4 * (size_t)KP * 128 * 4 + 256;
+// operand tiles of both row tiles | weight-stream stages | zt and dz rows of both tiles ([K+1][128] each) | barriers.
+// A third stage decouples the two tiles of a pair: with two, the tile that runs ahead holds a stage until the other has
+// used it and then waits a full L2 round trip for the chunk after next (traced: 2350 cycles per chunk against 1536 of MMA).
+size_t nif_tcb_smem_bytes(int K);
+__host__ __device__ inline size_t tcb_smem_bytes(int K, int nst) {
+  return 4 * (size_t)TC_TILE_BYTES + (size_t)nst * TCB_STAGE_BYTES + 4 * (size_t)(K + 1) * 128 * 4 + 256;
 }
 
-size_t nif_tcb_smem_bytes(int KP) { return tcb_smem_bytes(KP); }
+size_t nif_tcb_smem_bytes(int K) { return tcb_smem_bytes(K, 2); }
 
 __device__ __forceinline__ void warp_atomic_max(unsigned* dst, float v) {
 #pragma unroll
@@ -41,21 +47,25 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) nif_tc_bwd_data_kernel(const P
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char* A_all = smem;
   unsigned char* Bst = smem + 4 * TC_TILE_BYTES;
-  float* zs_all = reinterpret_cast<float*>(Bst + TCB_STAGES * TCB_STAGE_BYTES);  // [2][KP][128]
-  float* dzs_all = zs_all + 2 * pl.KP * 128;                                     // [2][KP][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(dzs_all + 2 * pl.KP * 128);
+  const int nst = a.nst;
+  float* zs_all = reinterpret_cast<float*>(Bst + nst * TCB_STAGE_BYTES);  // [2][K+1][128]
+  float* dzs_all = zs_all + 2 * (pl.K + 1) * 128;                         // [2][K+1][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(dzs_all + 2 * (pl.K + 1) * 128);
   uint64_t* b_full = bars;
-  uint64_t* b_empty = bars + TCB_STAGES;
-  uint64_t* t_full = bars + 2 * TCB_STAGES;  // [2][2]  accumulator stage s of tile t ready
+  uint64_t* b_empty = bars + TCB_MAX_STAGES;
+  uint64_t* t_full = bars + 2 * TCB_MAX_STAGES;  // [2][2]  accumulator stage s of tile t ready
   uint64_t* t_empty = t_full + 4;            // [2][2]  accumulator stage s of tile t drained
   uint64_t* a_ready = t_empty + 4;           // [2]     operand tile of tile t written
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_ready + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int K = pl.K, K1 = pl.K + 1, KP = pl.KP, NCH = pl.NCH, H = pl.H, n = pl.n, so = pl.so;
+#ifdef NIF_TRACE
+  int trace_n = 0;
+#endif
 
   if (tid == 0) {
-    for (int i = 0; i < TCB_STAGES; ++i) {
+    for (int i = 0; i < nst; ++i) {
       mbar_init(&b_full[i], 1);
       mbar_init(&b_empty[i], 2);  // both MMA issuers
     }
@@ -84,37 +94,45 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) nif_tc_bwd_data_kernel(const P
       for (long long t = 0; t < my_pairs; ++t)
         for (int h = H - 1; h >= 0; --h)
           for (int c = 0; c < NCH; ++c, ++g) {
-            const int s = (int)(g % TCB_STAGES);
-            mbar_wait(&b_empty[s], (uint32_t)(((g / TCB_STAGES) & 1) ^ 1));
+            const int s = (int)(g % nst);
+            mbar_wait(&b_empty[s], (uint32_t)(((g / nst) & 1) ^ 1));
+            TRACE(3, g);
             mbar_expect_tx(&b_full[s], TCB_STAGE_BYTES);
             bulk_g2s(Bst + s * TCB_STAGE_BYTES, src0 + ((long long)h * NCH + c) * NIF_TC_CHUNK_FLOATS,
                      TCB_STAGE_BYTES, &b_full[s]);
           }
     }
   } else if (warp == 8 || warp == 10) {
-    if (lane == 0) {  // MMA issuers: warp 8 feeds tile 0, warp 10 feeds tile 1 (see nif_tc_fwd.cu)
-      const int t = warp == 8 ? 0 : 1;
-      const uint32_t idesc = tc_idesc_f16(128);
-      const uint64_t da_hi = tc_make_desc(smem_u32(A_all + t * 2 * TC_TILE_BYTES));
-      const uint64_t da_lo = tc_make_desc(smem_u32(A_all + t * 2 * TC_TILE_BYTES + TC_TILE_BYTES));
-      long long g = 0, L = 0;
-      for (long long p = 0; p < my_pairs; ++p)
-        for (int h = 0; h < H; ++h, ++L)
-          for (int c = 0; c < NCH; ++c, ++g) {
-            const int s = (int)(g % TCB_STAGES);
-            const int as = (int)(g & 1);  // accumulator stage: the MMAs of chunk g+1 run while chunk g is drained
-            if (c == 0) mbar_wait(&a_ready[t], (uint32_t)(L & 1));
-            mbar_wait(&t_empty[2 * t + as], (uint32_t)(((g >> 1) & 1) ^ 1));
-            mbar_wait(&b_full[s], (uint32_t)((g / TCB_STAGES) & 1));
-            tc_fence_after();
-            const uint64_t db_hi = tc_make_desc(smem_u32(Bst + s * TCB_STAGE_BYTES));
-            const uint64_t db_lo = tc_make_desc(smem_u32(Bst + s * TCB_STAGE_BYTES + TC_TILE_BYTES));
-            const uint32_t d = tmem + (uint32_t)t * 256u + (uint32_t)as * 128u;
+    // MMA issuers: warp 8 feeds tile 0, warp 10 feeds tile 1 (see nif_tc_fwd.cu).  The whole warp runs the loop
+    // (uniform control flow and operands); one elected lane issues.
+    const int t = __shfl_sync(0xffffffffu, warp == 8 ? 0 : 1, 0);
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+    const uint32_t idesc = tc_idesc_f16(128);
+    const uint64_t da_hi = tc_make_desc(smem_u32(A_all + t * 2 * TC_TILE_BYTES));
+    const uint64_t da_lo = tc_make_desc(smem_u32(A_all + t * 2 * TC_TILE_BYTES + TC_TILE_BYTES));
+    long long g = 0, L = 0;
+    for (long long p = 0; p < my_pairs; ++p)
+      for (int h = 0; h < H; ++h, ++L)
+        for (int c = 0; c < NCH; ++c, ++g) {
+          const int s = (int)(g % nst);
+          const int as = (int)(g & 1);  // accumulator stage: the MMAs of chunk g+1 run while chunk g is drained
+          if (c == 0) mbar_wait(&a_ready[t], (uint32_t)(L & 1));
+          mbar_wait(&t_empty[2 * t + as], (uint32_t)(((g >> 1) & 1) ^ 1));
+          if (t == 0 && lane == 0) TRACE(2, g * 8 + 2);
+          mbar_wait(&b_full[s], (uint32_t)((g / nst) & 1));
+          if (t == 0 && lane == 0) TRACE(2, g * 8 + 1);
+          tc_fence_after();
+          const uint64_t db_hi = tc_make_desc(smem_u32(Bst + s * TCB_STAGE_BYTES));
+          const uint64_t db_lo = tc_make_desc(smem_u32(Bst + s * TCB_STAGE_BYTES + TC_TILE_BYTES));
+          const uint32_t d = tmem_u + (uint32_t)t * 256u + (uint32_t)as * 128u;
+          if (tc_elect_one()) {
             tc_mma_split_k64(d, da_hi, da_lo, db_hi, db_lo, idesc);
             tc_commit(&t_full[2 * t + as]);
             tc_commit(&b_empty[s]);
           }
-    }
+          __syncwarp();
+          if (t == 0 && lane == 0) TRACE(2, g * 8 + 3);
+        }
   }
   } else {
     tc_reg_inc<224>();
@@ -124,8 +142,8 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) nif_tc_bwd_data_kernel(const P
     const uint32_t tm = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)wg * 256u;
     unsigned char* A_hi = A_all + wg * 2 * TC_TILE_BYTES;
     unsigned char* A_lo = A_hi + TC_TILE_BYTES;
-    float* zs = zs_all + wg * KP * 128;
-    float* dzs = dzs_all + wg * KP * 128;
+    float* zs = zs_all + wg * K1 * 128;
+    float* dzs = dzs_all + wg * K1 * 128;
     const float* invB = a.packed + pl.off_TCS;
     const long long slot_floats = nif_tiled_rows(a.B) * 64;  // one slot of the (tiled) stash / da buffer
     long long g = 0;
@@ -144,8 +162,7 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) nif_tc_bwd_data_kernel(const P
         for (int kk = 0; kk < K; ++kk) zs[kk * 128 + r] = live ? __ldg(&a.z[b * K + kk]) : 0.f;
       }
       zs[K * 128 + r] = 1.f;
-      for (int kk = K1; kk < KP; ++kk) zs[kk * 128 + r] = 0.f;
-      for (int kk = 0; kk < KP; ++kk) dzs[kk * 128 + r] = 0.f;
+      for (int kk = 0; kk < K1; ++kk) dzs[kk * 128 + r] = 0.f;
       named_bar_sync(1 + wg, 128);
       {
         float zmax = 0.f;
@@ -202,6 +219,7 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) nif_tc_bwd_data_kernel(const P
           amax = fmaxf(fmaxf(amax, fabsf(dav[4 * c])), fmaxf(fabsf(dav[4 * c + 1]), fmaxf(fabsf(dav[4 * c + 2]), fabsf(dav[4 * c + 3]))));
         }
         warp_atomic_max(&a.maxes[m], amax);
+        if (r == 0) TRACE(wg, g * 4 + 3);  // da_m formed and stored
         if (m == 0) break;
 
         float sc_a, inv_a;
@@ -239,9 +257,12 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) nif_tc_bwd_data_kernel(const P
           const float sBc[2] = {sBn[0], sBn[1]}, zkc[2] = {zkn[0], zkn[1]};
           if (c + 1 < NCH) {
             sBn[0] = om_inv * __ldg(&invBm[2 * c + 2]); sBn[1] = om_inv * __ldg(&invBm[2 * c + 3]);
-            zkn[0] = zs[(2 * c + 2) * 128 + r]; zkn[1] = zs[(2 * c + 3) * 128 + r];
+            zkn[0] = zs[(2 * c + 2) * 128 + r];
+            zkn[1] = 2 * c + 3 < K1 ? zs[(2 * c + 3) * 128 + r] : 0.f;  // the padding coordinate of an odd K + 1
           }
+          if (r == 0) TRACE(wg, g * 4 + 0);
           mbar_wait(&t_full[2 * wg + (int)(g & 1)], (uint32_t)((g >> 1) & 1));
+          if (r == 0) TRACE(wg, g * 4 + 1);
           tc_fence_after();
           const uint32_t td = tm + (uint32_t)(g & 1) * 128u;
 #pragma unroll
@@ -254,21 +275,32 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) nif_tc_bwd_data_kernel(const P
             for (int q = 0; q < 2; ++q) {  // 32 columns (values of i) at a time
               float v1[16], v2[16];
               const uint32_t col = (uint32_t)(kl * 64 + q * 32);
+#ifndef NIF_EXP_NOLD
               tc_ld16(td + col, v1);
               tc_ld16(td + col + 16u, v2);
               tc_wait_ld();
+#else
+              for (int e = 0; e < 16; ++e) { v1[e] = hm[e]; v2[e] = hm[16 + e]; }
+#endif
 #pragma unroll
               for (int e = 0; e < 16; ++e) {
+#ifndef NIF_EXP_NOACC
                 acc[q * 32 + e] = fmaf(zo, v1[e], acc[q * 32 + e]);
                 acc[q * 32 + 16 + e] = fmaf(zo, v2[e], acc[q * 32 + 16 + e]);
+#else
+                if (e == 0) acc[q * 32] += v1[0] + v2[0];
+#endif
+#ifndef NIF_EXP_NODZ
                 s0 = fmaf(v1[e], hm[q * 32 + e], s0);
                 s1 = fmaf(v2[e], hm[q * 32 + 16 + e], s1);
+#endif
               }
             }
-            dzs[kk * 128 + r] += sB * (s0 + s1);
+            if (kk < K1) dzs[kk * 128 + r] += sB * (s0 + s1);
           }
           tc_fence_before();
           mbar_arrive(&t_empty[2 * wg + (int)(g & 1)]);
+          if (r == 0) TRACE(wg, g * 4 + 2);
         }
       }
 
@@ -424,8 +456,9 @@ int nif_tc_bwd_data_impl(const Plan& pl, long long B, const float* z, const floa
                          const float* save, const float* du, float* da, float* dz, unsigned* maxes,
                          cudaStream_t st) {
   if (!nif_plan_uses_tc(pl)) return NIF_E_UNSUPPORTED;
-  const size_t smem = tcb_smem_bytes(pl.KP);
   TcBwdArgs a;
+  a.nst = tcb_smem_bytes(pl.K, 3) <= 227 * 1024 ? 3 : 2;
+  const size_t smem = tcb_smem_bytes(pl.K, a.nst);
   a.B = B;
   a.total_pairs = (B + 255) / 256;
   a.z = z; a.x = x; a.packed = packed; a.save = save; a.du = du; a.da = da; a.dz = dz; a.maxes = maxes;
@@ -544,18 +577,20 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) nif_tc_bwd_weight_kernel(const
   }
 
   if (warp == 8) {
-    if (lane == 0) {  // MMA issuer
+    {  // MMA issuer: the whole warp runs the loop (uniform operands), one elected lane issues -- see tc_elect_one
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
       const uint32_t idesc = (1u << 4) | (1u << 15) | (1u << 16) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
       for (long long t = 0; t < nsub; ++t) {
         const int sl = (int)(t & 1);
         mbar_wait(&slot_full[sl], (uint32_t)((t >> 1) & 1));
         tc_fence_after();
+        if (tc_elect_one()) {
         const uint32_t base = smem_u32(smem + sl * TCW_SLOT_BYTES);
         const uint64_t b_hi = tcw_make_desc(base + 4 * TCW_A_BYTES), b_lo = tcw_make_desc(base + 4 * TCW_A_BYTES + TCW_B_BYTES);
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
           const uint64_t a_hi = tcw_make_desc(base + (2 * q) * TCW_A_BYTES), a_lo = tcw_make_desc(base + (2 * q + 1) * TCW_A_BYTES);
-          const uint32_t d1 = tmem + (uint32_t)q * 128u, d2 = d1 + 64u;
+          const uint32_t d1 = tmem_u + (uint32_t)q * 128u, d2 = d1 + 64u;
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {  // 16 rows (k) per instruction = 2 k-groups = 256 B
             const uint64_t adv = (uint64_t)(ks * 16);
@@ -566,8 +601,11 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) nif_tc_bwd_weight_kernel(const
           }
         }
         tc_commit(&slot_empty[sl]);
+        }
+        __syncwarp();
       }
-      tc_commit(&done_bar);
+      if (tc_elect_one()) tc_commit(&done_bar);
+      __syncwarp();
     }
   } else {
     // ---------------- operand generators: slot sl = warp / 4, thread (q, r) = pair q, row r of the sub-tile ----------------

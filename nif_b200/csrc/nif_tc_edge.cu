@@ -113,16 +113,18 @@ __global__ void __launch_bounds__(TCE_THREADS, 1) nif_tc_bwd_edge_kernel(const P
   tc_row_scale(__uint_as_float(a.maxes[H + 1]), scB, invB);
 
   if (warp == 8) {
-    if (lane == 0) {  // MMA issuer
+    {  // MMA issuer: the whole warp runs the loop (uniform operands), one elected lane issues -- see tc_elect_one
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
       const uint32_t idesc = (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(KZ >> 3) << 17) | ((128u >> 4) << 24);
       for (long long t = 0; t < nsub; ++t) {
         const int sl = (int)(t & 1);
         mbar_wait(&slot_full[sl], (uint32_t)((t >> 1) & 1));
         tc_fence_after();
+        if (tc_elect_one()) {
         const uint32_t base = smem_u32(smem + sl * TCE_SLOT_BYTES);
         const uint64_t a_hi = tce_make_desc(base), a_lo = tce_make_desc(base + TCE_A_BYTES);
         const uint64_t b_hi = tce_make_desc(base + 2 * TCE_A_BYTES), b_lo = tce_make_desc(base + 2 * TCE_A_BYTES + TCE_B_BYTES);
-        const uint32_t d1 = tmem, d2 = tmem + 64u;
+        const uint32_t d1 = tmem_u, d2 = tmem_u + 64u;
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {  // 16 rows (k) per instruction
           const uint64_t adv = (uint64_t)(ks * 16);
@@ -132,8 +134,11 @@ __global__ void __launch_bounds__(TCE_THREADS, 1) nif_tc_bwd_edge_kernel(const P
           tc_mma_f16(d1, a_hi + adv, b_hi + adv, idesc, accf);
         }
         tc_commit(&slot_empty[sl]);
+        }
+        __syncwarp();
       }
-      tc_commit(&done_bar);
+      if (tc_elect_one()) tc_commit(&done_bar);
+      __syncwarp();
     }
   } else {
     // ---------------- operand generators: slot sl = warp / 4, thread (q, r) = block q of the pair, row r ----------------

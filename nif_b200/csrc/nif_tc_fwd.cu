@@ -22,28 +22,7 @@
 //   warp 10    MMA issuer of tile 1;  warp 11 idle (register donor)
 #include "nif_tc.cuh"
 
-// Optional timeline trace (make -C nif_b200/csrc EXTRA=-DNIF_TRACE): CTA 0 records clock64() at the hand-offs of its first
-// tile pair; read back with nif_debug_read_trace().  Compiled out of the product build.
-#ifdef NIF_TRACE
-__device__ long long g_trace[4][2048];
-__device__ int g_trace_n[4];
-#define TRACE(role, tag)                                                                  \
-  do {                                                                                    \
-    if (blockIdx.x == 0 && trace_n < 1023) {                                              \
-      g_trace[role][2 * trace_n] = (long long)(tag);                                      \
-      g_trace[role][2 * trace_n + 1] = clock64();                                         \
-      ++trace_n;                                                                          \
-      g_trace_n[role] = 2 * trace_n;                                                      \
-    }                                                                                     \
-  } while (0)
-extern "C" int nif_debug_read_trace(long long* host, int* counts) {
-  cudaMemcpyFromSymbol(host, g_trace, sizeof(g_trace));
-  cudaMemcpyFromSymbol(counts, g_trace_n, sizeof(g_trace_n));
-  return 0;
-}
-#else
-#define TRACE(role, tag) do {} while (0)
-#endif
+NIF_TRACE_READER(nif_debug_read_trace)
 
 struct TcFwdArgs {
   long long B, total_pairs;
@@ -144,8 +123,9 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) nif_tc_fwd_kernel(const Plan p
     // ---------------- MMA issuers: warp 8 feeds tile 0, warp 10 feeds tile 1 ----------------
     // (one issuer per tile: while one is between chunks -- barrier waits, descriptors, commits -- the other keeps
     // the tensor pipe fed; both read the same staged weight chunk and each commits to its b_empty, count 2)
-    if (lane == 0) {
-      const int t = warp == 8 ? 0 : 1;
+    {  // the whole warp runs the loop (uniform control flow and operands); one elected lane issues -- see tc_elect_one
+      const int t = __shfl_sync(0xffffffffu, warp == 8 ? 0 : 1, 0);
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
       const uint64_t da_hi = tc_make_desc(smem_u32(A_all + t * 2 * TC_TILE_BYTES), TC_SBO);
       const uint64_t da_lo = tc_make_desc(smem_u32(A_all + t * 2 * TC_TILE_BYTES + TC_TILE_BYTES), TC_SBO);
       const uint64_t dz_hi = tc_make_desc(smem_u32(Z_all + t * 2 * zbytes), sbo_z);
@@ -159,15 +139,18 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) nif_tc_fwd_kernel(const Plan p
         if (wait_a) { mbar_wait(&a_ready[t], (uint32_t)(ar & 1)); ++ar; }
         mbar_wait(&t_empty[2 * t + as], (uint32_t)(((g >> 1) & 1) ^ 1));
         mbar_wait(&b_full[s], (uint32_t)((g / TCF_STAGES) & 1));
-        if (t == 0) TRACE(2, g * 8 + 1 + t);
+        if (t == 0 && lane == 0) TRACE(2, g * 8 + 1 + t);
         tc_fence_after();
         const uint64_t db_hi = tc_make_desc(smem_u32(Bst + s * TCF_STAGE_BYTES), b_sbo);
         const uint64_t db_lo = tc_make_desc(smem_u32(Bst + s * TCF_STAGE_BYTES + b_half_bytes), b_sbo);
-        const uint32_t d = tmem + (uint32_t)t * 256u + (uint32_t)as * 128u;
-        tc_mma_split(d, a_kind ? da_hi : dz_hi, a_kind ? da_lo : dz_lo, db_hi, db_lo, tc_idesc_f16(N), ksteps);
-        tc_commit(&t_full[2 * t + as]);
-        tc_commit(&b_empty[s]);
-        if (t == 0) TRACE(2, g * 8 + 3 + t);
+        const uint32_t d = tmem_u + (uint32_t)t * 256u + (uint32_t)as * 128u;
+        if (tc_elect_one()) {
+          tc_mma_split(d, a_kind ? da_hi : dz_hi, a_kind ? da_lo : dz_lo, db_hi, db_lo, tc_idesc_f16(N), ksteps);
+          tc_commit(&t_full[2 * t + as]);
+          tc_commit(&b_empty[s]);
+        }
+        __syncwarp();
+        if (t == 0 && lane == 0) TRACE(2, g * 8 + 3 + t);
         ++g;
       };
       for (long long p = 0; p < my_pairs; ++p) {
@@ -282,8 +265,9 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) nif_tc_fwd_kernel(const Plan p
           }
           float dch[8], f8[8], d8[8];
           if (SINE) {
+            nif_sincos_fold8(&pre[8 * c]);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) nif_sincosf(pre[8 * c + e], f8[e], d8[e]);
+            for (int e = 0; e < 8; ++e) nif_sincosf_core(pre[8 * c + e], f8[e], d8[e]);
           } else {
 #pragma unroll
             for (int e4 = 0; e4 < 8; e4 += 4) {
@@ -375,6 +359,7 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) nif_tc_fwd_kernel(const Plan p
           }
         }
         finish_layer(m, acc);
+        if (r == 0) TRACE(wg, g * 4 + 3);
       }
 
       // ---- last layer:  y[c] = sum_kappa zt[kappa] * ( (h @ ML[kappa])[c] + CL[kappa][c] ) ----
@@ -426,12 +411,12 @@ static int launch_tcf(const Plan& pl, const TcFwdArgs& a, cudaStream_t st) {
   return NIF_OK;
 }
 
-size_t nif_tcb_smem_bytes(int KP);
+size_t nif_tcb_smem_bytes(int K);
 // One static predicate for forward and reverse (the stash layout depends on it): shapes the tensor-core kernels cover.
 bool nif_plan_uses_tc(const Plan& pl) {
   if (!pl.tc || pl.NP != 64 || pl.H < 1 || pl.variant == NIF_VARIANT_SIREN_RES || pl.K < 1) return false;
   if (tcf_smem_bytes(pl.KP, pl.KZ, pl.si) > 227 * 1024 || pl.LPC * pl.KZ > 128) return false;
-  return nif_tcb_smem_bytes(pl.KP) <= 227 * 1024;
+  return nif_tcb_smem_bytes(pl.K) <= 227 * 1024;
 }
 
 // returns NIF_E_UNSUPPORTED (without setting an error) when the shape does not fit this kernel, so that the
