@@ -43,6 +43,59 @@ __device__ __forceinline__ void warp_atomic_max(unsigned* dst, float v) {
   if ((threadIdx.x & 31) == 0) atomicMax(dst, __float_as_uint(v));  // v >= 0: uint order == float order
 }
 
+// MMA issuer of tile T (warp 8: tile 0, warp 10: tile 1; see nif_tc_fwd.cu).  The whole warp runs the loop and one
+// elected lane issues.  T is a template constant and every counter is a 32-bit value derived from kernel parameters, so
+// descriptors, barrier addresses and phases all live in uniform registers: the per-chunk instruction stream of this
+// warp is a few dozen instructions.  It has to be: the warp shares its scheduler with two epilogue warps whose dense
+// FMA streams keep the issue slot, and every extra instruction here delays the next chunk's MMAs (traced: the issuer
+// used to reach the top of its loop only when the epilogue of the previous chunk went to sleep).
+template <int T>
+__device__ __forceinline__ void tcb_issue(const Plan& pl, const TcBwdArgs& a, unsigned char* smem, uint64_t* bars,
+                                          uint32_t tmem, long long my_pairs) {
+  const uint32_t nst = (uint32_t)a.nst;
+  unsigned char* A_all = smem;
+  unsigned char* Bst = smem + 4 * TC_TILE_BYTES;
+  uint64_t* b_full = bars;
+  uint64_t* b_empty = bars + TCB_MAX_STAGES;
+  uint64_t* t_full = bars + 2 * TCB_MAX_STAGES;
+  uint64_t* t_empty = t_full + 4;
+  uint64_t* a_ready = t_empty + 4;
+  const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0) + (uint32_t)T * 256u;
+  const uint32_t idesc = tc_idesc_f16(128);
+  const uint64_t da_hi = tc_make_desc(smem_u32(A_all + T * 2 * TC_TILE_BYTES));
+  const uint64_t da_lo = tc_make_desc(smem_u32(A_all + T * 2 * TC_TILE_BYTES + TC_TILE_BYTES));
+  const uint64_t db0_hi = tc_make_desc(smem_u32(Bst));
+  const uint64_t db0_lo = tc_make_desc(smem_u32(Bst + TC_TILE_BYTES));
+  const uint32_t H = (uint32_t)pl.H, NCH = (uint32_t)pl.NCH;
+  uint32_t g = 0, L = 0;     // chunk and layer counters
+  uint32_t s = 0, sph = 0;   // weight-stream stage and its phase
+  const int lane = threadIdx.x & 31;
+  (void)lane;
+#ifdef NIF_TRACE
+  int trace_n = 0;
+#endif
+  for (long long p = 0; p < my_pairs; ++p)
+    for (uint32_t h = 0; h < H; ++h, ++L)
+      for (uint32_t c = 0; c < NCH; ++c, ++g) {
+        const uint32_t as = g & 1u;  // accumulator stage: the MMAs of chunk g+1 run while chunk g is drained
+        if (c == 0) mbar_wait(&a_ready[T], L & 1u);
+        mbar_wait(&t_empty[2 * T + as], ((g >> 1) & 1u) ^ 1u);
+        if (T == 0 && lane == 0) TRACE(2, g * 8 + 2);
+        mbar_wait(&b_full[s], sph);
+        if (T == 0 && lane == 0) TRACE(2, g * 8 + 1);
+        tc_fence_after();
+        const uint64_t boff = (uint64_t)(s * (TCB_STAGE_BYTES >> 4));
+        if (tc_elect_one()) {
+          tc_mma_split_k64(tmem_u + as * 128u, da_hi, da_lo, db0_hi + boff, db0_lo + boff, idesc);
+          tc_commit(&t_full[2 * T + as]);
+          tc_commit(&b_empty[s]);
+        }
+        __syncwarp();
+        if (T == 0 && lane == 0) TRACE(2, g * 8 + 3);
+        if (++s == nst) { s = 0; sph ^= 1u; }
+      }
+}
+
 __global__ void __launch_bounds__(TCB_THREADS, 1) nif_tc_bwd_data_kernel(const Plan pl, const TcBwdArgs a) {
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char* A_all = smem;
@@ -102,37 +155,10 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) nif_tc_bwd_data_kernel(const P
                      TCB_STAGE_BYTES, &b_full[s]);
           }
     }
-  } else if (warp == 8 || warp == 10) {
-    // MMA issuers: warp 8 feeds tile 0, warp 10 feeds tile 1 (see nif_tc_fwd.cu).  The whole warp runs the loop
-    // (uniform control flow and operands); one elected lane issues.
-    const int t = __shfl_sync(0xffffffffu, warp == 8 ? 0 : 1, 0);
-    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
-    const uint32_t idesc = tc_idesc_f16(128);
-    const uint64_t da_hi = tc_make_desc(smem_u32(A_all + t * 2 * TC_TILE_BYTES));
-    const uint64_t da_lo = tc_make_desc(smem_u32(A_all + t * 2 * TC_TILE_BYTES + TC_TILE_BYTES));
-    long long g = 0, L = 0;
-    for (long long p = 0; p < my_pairs; ++p)
-      for (int h = 0; h < H; ++h, ++L)
-        for (int c = 0; c < NCH; ++c, ++g) {
-          const int s = (int)(g % nst);
-          const int as = (int)(g & 1);  // accumulator stage: the MMAs of chunk g+1 run while chunk g is drained
-          if (c == 0) mbar_wait(&a_ready[t], (uint32_t)(L & 1));
-          mbar_wait(&t_empty[2 * t + as], (uint32_t)(((g >> 1) & 1) ^ 1));
-          if (t == 0 && lane == 0) TRACE(2, g * 8 + 2);
-          mbar_wait(&b_full[s], (uint32_t)((g / nst) & 1));
-          if (t == 0 && lane == 0) TRACE(2, g * 8 + 1);
-          tc_fence_after();
-          const uint64_t db_hi = tc_make_desc(smem_u32(Bst + s * TCB_STAGE_BYTES));
-          const uint64_t db_lo = tc_make_desc(smem_u32(Bst + s * TCB_STAGE_BYTES + TC_TILE_BYTES));
-          const uint32_t d = tmem_u + (uint32_t)t * 256u + (uint32_t)as * 128u;
-          if (tc_elect_one()) {
-            tc_mma_split_k64(d, da_hi, da_lo, db_hi, db_lo, idesc);
-            tc_commit(&t_full[2 * t + as]);
-            tc_commit(&b_empty[s]);
-          }
-          __syncwarp();
-          if (t == 0 && lane == 0) TRACE(2, g * 8 + 3);
-        }
+  } else if (warp == 8) {
+    tcb_issue<0>(pl, a, smem, bars, tmem, my_pairs);
+  } else if (warp == 10) {
+    tcb_issue<1>(pl, a, smem, bars, tmem, my_pairs);
   }
   } else {
     tc_reg_inc<224>();

@@ -47,7 +47,7 @@ for role in range(4):
         ev.append((int(host[role, i + 1]), names[role], int(host[role, i])))
 ev.sort()
 t0 = ev[0][0]
-sub = {"epi": {0: "wait_full", 1: "got_full", 2: "arrived_empty", 3: "layer_finished (fwd: before publish_h; bwd: da_m stored)"}, "mma": {0: "got_b_full", 1: "waits done", 2: "accumulator free (bwd)", 3: "committed0", 4: "committed1"}}
+sub = {"epi": {0: "wait_full", 1: "got_full", 2: "arrived_empty", 3: "layer_finished (fwd: before publish_h; bwd: da_m stored)"}, "mma": {0: "got_b_full", 1: "waits done", 2: "accumulator free (bwd)", 3: "committed0", 4: "loop top (bwd)", 5: "mmas issued (bwd)"}}
 for t, who, tag in ev[:int(sys.argv[1]) if len(sys.argv) > 1 else 400]:
     if who.startswith("epi"):
         print(f"{t - t0:8d} {who} chunk {tag // 4:3d} {sub['epi'][tag % 4]}")
