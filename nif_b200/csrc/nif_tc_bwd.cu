@@ -663,22 +663,32 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) nif_tc_bwd_weight_kernel(const
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
     if (sl < nsub) stage_rows(sl);
+    // this thread's row data that comes straight from global memory -- its latent coordinates (pre-multiplied by the
+    // operand scale) and its half of da_m (32 values) -- is fetched one sub-tile ahead, so that its latency hides
+    // behind the conversion of the current sub-tile
+    float ztn[2];
+    float4 dqn[8];
+    auto fetch_row = [&](long long t) {
+      const long long b = r0 + t * 64 + r;
+      const bool live = t < nsub && b < r1;
+#pragma unroll
+      for (int kl = 0; kl < 2; ++kl) {
+        const int kk = kk0 + kl;
+        ztn[kl] = 0.f;
+        if (live) ztn[kl] = (kk < K) ? __ldg(&a.z[b * K + kk]) : (kk == K ? 1.f : 0.f);
+      }
+#pragma unroll
+      for (int c = 0; c < 8; ++c) dqn[c] = live ? ldg4(dsrc + nif_tiled_row(b) + (8 * q + c) * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    fetch_row(sl);
     long long n_mine = 0;
     for (long long t = sl; t < nsub; t += 2, ++n_mine) {
       const long long b = r0 + t * 64 + r;
       const bool live = b < r1;
-      float zt[2];
-#pragma unroll
-      for (int kl = 0; kl < 2; ++kl) {
-        const int kk = kk0 + kl;
-        zt[kl] = 0.f;
-        if (live) zt[kl] = (kk < K) ? __ldg(&a.z[b * K + kk]) : (kk == K ? 1.f : 0.f);
-      }
-      // this thread's half of da_m (32 values, plain loads issued before the waits) and this row's h_m (64 values
-      // from the staged rows)
+      const float zt[2] = {ztn[0] * scA, ztn[1] * scA};
       float4 hq[16], dq[8];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) dq[c] = live ? ldg4(dsrc + nif_tiled_row(b) + (8 * q + c) * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int c = 0; c < 8; ++c) dq[c] = dqn[c];
       asm volatile("cp.async.wait_group 0;" ::: "memory");
       named_bar_sync(1 + sl, 128);  // every thread's part of the block has landed
 #pragma unroll
@@ -686,6 +696,7 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) nif_tc_bwd_weight_kernel(const
         hq[c] = live ? *reinterpret_cast<const float4*>(stg + (r >> 5) * 8192 + c * 512 + (r & 31) * 16) : make_float4(0.f, 0.f, 0.f, 0.f);
       named_bar_sync(1 + sl, 128);  // every thread of the slot has its row in registers
       if (t + 2 < nsub) stage_rows(t + 2);
+      fetch_row(t + 2);
       // wait until the MMAs that read this slot two sub-tiles ago have completed
       mbar_wait(&slot_empty[sl], (uint32_t)((n_mine & 1) ^ 1));
 #pragma unroll
@@ -696,9 +707,9 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) nif_tc_bwd_weight_kernel(const
         for (int kl = 0; kl < 2; ++kl) {
           float pv[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) pv[e] = zt[kl] * hv[e];
+          for (int e = 0; e < 8; ++e) pv[e] = zt[kl] * hv[e];  // zt carries the operand scale (a power of two: exact)
           uint4 hi, lo;
-          tcw_split8(pv, scA, hi, lo);
+          tcw_split8(pv, 1.f, hi, lo);
           const uint32_t off = (uint32_t)(kl * 8 + ig) * 1024u + koff;
           *reinterpret_cast<uint4*>(Aq_hi + off) = hi;
           *reinterpret_cast<uint4*>(Aq_lo + off) = lo;
