@@ -719,12 +719,14 @@ __global__ void __launch_bounds__(256) nif_mse_seed_kernel(long long B, int so, 
   }
   if (threadIdx.x == 0) part[blockIdx.x] = red[0];
 }
+// one warp, fixed summation order (lane-strided partial sums, then a shuffle tree): deterministic, and the loads of a
+// lane are independent instead of one serial chain over every partial
 __global__ void nif_loss_final_kernel(int nparts, const float* __restrict__ part, float* __restrict__ loss) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    float sacc = 0.f;
-    for (int i = 0; i < nparts; ++i) sacc += part[i];
-    *loss += sacc;
-  }
+  float sacc = 0.f;
+  for (int i = threadIdx.x; i < nparts; i += 32) sacc += part[i];
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
+  if (threadIdx.x == 0) *loss += sacc;
 }
 
 // ---------------------------------------------------------------------------------------------------
