@@ -180,6 +180,11 @@ int nif_trunk_backward(const nif_trunk_desc_t* d, int64_t B, const float* p_in, 
  * measured with CUDA events; blocks until done. */
 int nif_measure_fp32_peak(double* tflops);
 
+/* CRC-32C (Castagnoli) of a HOST buffer, continuing from `crc` (0 for a fresh checksum): the checksum of the TFRecord
+ * framing (nif/data/tfr_dataset.py:84-88, 159 use tf.io.TFRecordWriter / tf.data.TFRecordDataset, third-party).  Host
+ * code only; the one entry point that takes host pointers. */
+uint32_t nif_crc32c(const void* data, uint64_t n, uint32_t crc);
+
 #ifdef __cplusplus
 }
 #endif

@@ -18,7 +18,7 @@ SYMBOLS = (
     "nif_last_error", "nif_version", "nif_query_sizes", "nif_pack", "nif_forward", "nif_forward_tangent",
     "nif_forward_given_w", "nif_mse_backward", "nif_backward", "nif_adam_step", "nif_adam_step_dev", "nif_measure_fp32_peak",
     "nif_trunk_query", "nif_trunk_forward", "nif_trunk_backward",
-    "nif_sobolev_query", "nif_forward_tangent_save", "nif_sobolev_backward",
+    "nif_sobolev_query", "nif_forward_tangent_save", "nif_sobolev_backward", "nif_crc32c",
 )
 
 VARIANT = {"nif": 0, "siren": 1, "siren_res": 2}
@@ -98,8 +98,10 @@ def lib() -> C.CDLL:
     L.nif_trunk_backward.argtypes = [TP, I64, VP, VP, VP, VP, VP, F, VP, VP, VP]
     for name in SYMBOLS:
         getattr(L, name)  # raises AttributeError if the build is stale
-        if name not in ("nif_last_error",):
+        if name not in ("nif_last_error", "nif_crc32c"):
             getattr(L, name).restype = C.c_int
+    L.nif_crc32c.restype = C.c_uint32
+    L.nif_crc32c.argtypes = [C.c_char_p, C.c_uint64, C.c_uint32]
     _lib = L
     return L
 

@@ -261,3 +261,31 @@ extern "C" int nif_trunk_backward(const nif_trunk_desc_t* d, int64_t B, const fl
   return nif_trunk_backward_impl(pl, B, p_in, theta, save, dz, g_theta, beta, packed, ws,
                                  static_cast<cudaStream_t>(stream));
 }
+
+// ---- CRC-32C for the TFRecord framing (host code, slicing-by-8) ----------------------------------------------------
+static uint32_t g_crc_tab[8][256];
+static bool g_crc_ready = false;
+static void crc32c_init() {
+  for (uint32_t i = 0; i < 256; ++i) {
+    uint32_t c = i;
+    for (int k = 0; k < 8; ++k) c = (c & 1u) ? (c >> 1) ^ 0x82F63B78u : (c >> 1);  // reflected Castagnoli polynomial
+    g_crc_tab[0][i] = c;
+  }
+  for (uint32_t i = 0; i < 256; ++i)
+    for (int t = 1; t < 8; ++t) g_crc_tab[t][i] = (g_crc_tab[t - 1][i] >> 8) ^ g_crc_tab[0][g_crc_tab[t - 1][i] & 0xFFu];
+  g_crc_ready = true;
+}
+extern "C" uint32_t nif_crc32c(const void* data, uint64_t n, uint32_t crc) {
+  if (!g_crc_ready) crc32c_init();  // idempotent: a racing second initialisation writes the same values
+  const unsigned char* p = static_cast<const unsigned char*>(data);
+  uint32_t c = ~crc;
+  while (n >= 8) {
+    const uint32_t lo = c ^ ((uint32_t)p[0] | (uint32_t)p[1] << 8 | (uint32_t)p[2] << 16 | (uint32_t)p[3] << 24);
+    c = g_crc_tab[7][lo & 0xFFu] ^ g_crc_tab[6][(lo >> 8) & 0xFFu] ^ g_crc_tab[5][(lo >> 16) & 0xFFu] ^ g_crc_tab[4][lo >> 24] ^
+        g_crc_tab[3][p[4]] ^ g_crc_tab[2][p[5]] ^ g_crc_tab[1][p[6]] ^ g_crc_tab[0][p[7]];
+    p += 8;
+    n -= 8;
+  }
+  while (n--) c = (c >> 8) ^ g_crc_tab[0][(c ^ *p++) & 0xFFu];
+  return ~c;
+}

@@ -301,25 +301,15 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) nif_tc_bwd_data_kernel(const P
             for (int q = 0; q < 2; ++q) {  // 32 columns (values of i) at a time
               float v1[16], v2[16];
               const uint32_t col = (uint32_t)(kl * 64 + q * 32);
-#ifndef NIF_EXP_NOLD
               tc_ld16(td + col, v1);
               tc_ld16(td + col + 16u, v2);
               tc_wait_ld();
-#else
-              for (int e = 0; e < 16; ++e) { v1[e] = hm[e]; v2[e] = hm[16 + e]; }
-#endif
 #pragma unroll
               for (int e = 0; e < 16; ++e) {
-#ifndef NIF_EXP_NOACC
                 acc[q * 32 + e] = fmaf(zo, v1[e], acc[q * 32 + e]);
                 acc[q * 32 + 16 + e] = fmaf(zo, v2[e], acc[q * 32 + 16 + e]);
-#else
-                if (e == 0) acc[q * 32] += v1[0] + v2[0];
-#endif
-#ifndef NIF_EXP_NODZ
                 s0 = fmaf(v1[e], hm[q * 32 + e], s0);
                 s1 = fmaf(v2[e], hm[q * 32 + 16 + e], s1);
-#endif
               }
             }
             if (kk < K1) dzs[kk * 128 + r] += sB * (s0 + s1);
@@ -364,34 +354,47 @@ struct DzEdgeArgs {
 //   next so                      F = du[b][c]                   G = CL[kappa][c]
 // G is staged through shared memory in slabs of 64 features; every thread keeps its K outputs in registers
 // (KT of them per pass over the features).
-// Every thread owns TWO rows (b and b + blockDim.x), so each coefficient read feeds two FMAs; the coefficient table
-// GE[slab][f][kappa] is re-laid by nif_pack so that a slab is staged into shared memory with coalesced vector loads.
+// Every thread owns DZE_R = 2 rows (b and b + blockDim.x), so each coefficient read feeds two FMAs.  (One row per
+// thread -- twice the warps at 105 instead of 167 registers -- measured the same 112 us: the kernel is bound by its
+// instruction count, not by latency.)  The coefficient table GE[slab][f][kappa] is re-laid by nif_pack so that a slab
+// is staged into shared memory with coalesced vector loads.
+#define DZE_R 2
 template <int KT>
 __global__ void __launch_bounds__(128) nif_dz_edge_kernel(const Plan pl, const DzEdgeArgs a, int k0) {
   __shared__ __align__(16) float Gs[64 * KT];
   const int K = pl.K, H = pl.H, si = pl.si, so = pl.so, KG = pl.KG;
-  const long long b0 = blockIdx.x * 256LL + threadIdx.x;
-  long long bb[2];
-  bool live[2];
+  const long long b0 = blockIdx.x * (128LL * DZE_R) + threadIdx.x;
+  long long bb[DZE_R];
+  bool live[DZE_R];
 #pragma unroll
-  for (int w = 0; w < 2; ++w) {
+  for (int w = 0; w < DZE_R; ++w) {
     live[w] = b0 + 128 * w < a.B;
     bb[w] = live[w] ? b0 + 128 * w : 0;
   }
   const float* GE = a.packed + pl.off_GE + k0;
   const float om0 = plan_omega(pl, 0);
   const long long slot_floats = nif_tiled_rows(a.B) * 64;  // da and the stash are in the tiled layout
-  float acc[2][KT];
+  float acc[DZE_R][KT];
 #pragma unroll
-  for (int w = 0; w < 2; ++w)
+  for (int w = 0; w < DZE_R; ++w)
 #pragma unroll
     for (int k = 0; k < KT; ++k) acc[w][k] = 0.f;
 
   if (k0 == 0) {  // bounds of the thin-term operands (rows this thread owns; dead rows repeat row 0)
     for (int i = 0; i < si; ++i)
-      warp_atomic_max(&a.maxes[NIF_MAX_X + i], fmaxf(fabsf(__ldg(&a.x[bb[0] * si + i])), fabsf(__ldg(&a.x[bb[1] * si + i]))));
+    {
+      float mx = 0.f;
+#pragma unroll
+      for (int w = 0; w < DZE_R; ++w) mx = fmaxf(mx, fabsf(__ldg(&a.x[bb[w] * si + i])));
+      warp_atomic_max(&a.maxes[NIF_MAX_X + i], mx);
+    }
     for (int c = 0; c < so; ++c)
-      warp_atomic_max(&a.maxes[NIF_MAX_DU + c], fmaxf(fabsf(__ldg(&a.du[bb[0] * so + c])), fabsf(__ldg(&a.du[bb[1] * so + c]))));
+    {
+      float mx = 0.f;
+#pragma unroll
+      for (int w = 0; w < DZE_R; ++w) mx = fmaxf(mx, fabsf(__ldg(&a.du[bb[w] * so + c])));
+      warp_atomic_max(&a.maxes[NIF_MAX_DU + c], mx);
+    }
   }
   float hl_max = 0.f;
   const int nslab = (H + 1) + si + so + 1;  // slabs of (up to) 64 features
@@ -402,11 +405,13 @@ __global__ void __launch_bounds__(128) nif_dz_edge_kernel(const Plan pl, const D
       *reinterpret_cast<float4*>(&Gs[f * KT + 4 * k4]) = ldg4(GE + ((long long)sb * 64 + f) * KG + 4 * k4);
     }
     __syncthreads();
-    const float* src[2];
-    float mul[2] = {1.f, 1.f};
+    const float* src[DZE_R];
+    float mul[DZE_R];
+#pragma unroll
+    for (int w = 0; w < DZE_R; ++w) mul[w] = 1.f;
     int nf = 64;
 #pragma unroll
-    for (int w = 0; w < 2; ++w) {
+    for (int w = 0; w < DZE_R; ++w) {
       if (sb <= H) src[w] = a.da + (long long)sb * slot_floats + nif_tiled_row(bb[w]);
       else if (sb < H + 1 + si) { src[w] = a.da + nif_tiled_row(bb[w]); mul[w] = om0 * a.x[bb[w] * si + (sb - H - 1)]; }
       else if (sb < H + 1 + si + so) { src[w] = a.save + (long long)H * slot_floats + nif_tiled_row(bb[w]); mul[w] = a.du[bb[w] * so + (sb - H - 1 - si)]; }
@@ -415,10 +420,10 @@ __global__ void __launch_bounds__(128) nif_dz_edge_kernel(const Plan pl, const D
     if (nf == 64) {
       // groups of 16 features per row (two 256-bit loads); the next group's loads are issued before the current
       // group is consumed
-      float cur[2][16], nxt[2][16];
-      auto load16 = [&](int g4, float (&dst)[2][16]) {  // features 16 g4 .. 16 g4 + 15 = column quads 4 g4 .. 4 g4 + 3
+      float cur[DZE_R][16], nxt[DZE_R][16];
+      auto load16 = [&](int g4, float (&dst)[DZE_R][16]) {  // features 16 g4 .. 16 g4 + 15 = column quads 4 g4 .. 4 g4 + 3
 #pragma unroll
-        for (int w = 0; w < 2; ++w)
+        for (int w = 0; w < DZE_R; ++w)
 #pragma unroll
           for (int qd = 0; qd < 4; ++qd) {
             const float4 v = ldg4(src[w] + (4 * g4 + qd) * 128);
@@ -431,45 +436,53 @@ __global__ void __launch_bounds__(128) nif_dz_edge_kernel(const Plan pl, const D
         if (g4 < 3) load16(g4 + 1, nxt);
         if (k0 == 0 && sb == H + 1 + si) {  // the h_{H+1} rows pass through here: record their magnitude
 #pragma unroll
-          for (int e = 0; e < 16; ++e) hl_max = fmaxf(hl_max, fmaxf(fabsf(cur[0][e]), fabsf(cur[1][e])));
+          for (int e = 0; e < 16; ++e)
+#pragma unroll
+            for (int w = 0; w < DZE_R; ++w) hl_max = fmaxf(hl_max, fabsf(cur[w][e]));
         }
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
-          const float f0 = cur[0][e] * mul[0], f1 = cur[1][e] * mul[1];
+          float fw[DZE_R];
+#pragma unroll
+          for (int w = 0; w < DZE_R; ++w) fw[w] = cur[w][e] * mul[w];
           const float* Gf = Gs + (16 * g4 + e) * KT;
 #pragma unroll
           for (int k = 0; k < KT; k += 4) {
             const float4 g = *reinterpret_cast<const float4*>(Gf + k);
-            acc[0][k] = fmaf(f0, g.x, acc[0][k]); acc[0][k + 1] = fmaf(f0, g.y, acc[0][k + 1]);
-            acc[0][k + 2] = fmaf(f0, g.z, acc[0][k + 2]); acc[0][k + 3] = fmaf(f0, g.w, acc[0][k + 3]);
-            acc[1][k] = fmaf(f1, g.x, acc[1][k]); acc[1][k + 1] = fmaf(f1, g.y, acc[1][k + 1]);
-            acc[1][k + 2] = fmaf(f1, g.z, acc[1][k + 2]); acc[1][k + 3] = fmaf(f1, g.w, acc[1][k + 3]);
+#pragma unroll
+            for (int w = 0; w < DZE_R; ++w) {
+              acc[w][k] = fmaf(fw[w], g.x, acc[w][k]); acc[w][k + 1] = fmaf(fw[w], g.y, acc[w][k + 1]);
+              acc[w][k + 2] = fmaf(fw[w], g.z, acc[w][k + 2]); acc[w][k + 3] = fmaf(fw[w], g.w, acc[w][k + 3]);
+            }
           }
         }
         if (g4 < 3) {
 #pragma unroll
-          for (int w = 0; w < 2; ++w)
+          for (int w = 0; w < DZE_R; ++w)
 #pragma unroll
             for (int e = 0; e < 16; ++e) cur[w][e] = nxt[w][e];
         }
       }
     } else {
       for (int f = 0; f < nf; ++f) {
-        const float f0 = src[0][f], f1 = src[1][f];
+        float fw[DZE_R];
+#pragma unroll
+        for (int w = 0; w < DZE_R; ++w) fw[w] = src[w][f];
 #pragma unroll
         for (int k = 0; k < KT; k += 4) {
           const float4 g = *reinterpret_cast<const float4*>(&Gs[f * KT + k]);
-          acc[0][k] = fmaf(f0, g.x, acc[0][k]); acc[0][k + 1] = fmaf(f0, g.y, acc[0][k + 1]);
-          acc[0][k + 2] = fmaf(f0, g.z, acc[0][k + 2]); acc[0][k + 3] = fmaf(f0, g.w, acc[0][k + 3]);
-          acc[1][k] = fmaf(f1, g.x, acc[1][k]); acc[1][k + 1] = fmaf(f1, g.y, acc[1][k + 1]);
-          acc[1][k + 2] = fmaf(f1, g.z, acc[1][k + 2]); acc[1][k + 3] = fmaf(f1, g.w, acc[1][k + 3]);
+#pragma unroll
+          for (int w = 0; w < DZE_R; ++w) {
+            acc[w][k] = fmaf(fw[w], g.x, acc[w][k]); acc[w][k + 1] = fmaf(fw[w], g.y, acc[w][k + 1]);
+            acc[w][k + 2] = fmaf(fw[w], g.z, acc[w][k + 2]); acc[w][k + 3] = fmaf(fw[w], g.w, acc[w][k + 3]);
+          }
         }
       }
     }
   }
   if (k0 == 0) warp_atomic_max(&a.maxes[NIF_MAX_HL], hl_max);
 #pragma unroll
-  for (int w = 0; w < 2; ++w)
+  for (int w = 0; w < DZE_R; ++w)
     if (live[w]) {
 #pragma unroll
       for (int k = 0; k < KT; ++k)
@@ -501,7 +514,7 @@ int nif_tc_bwd_data_impl(const Plan& pl, long long B, const float* z, const floa
   e.B = B; e.x = x; e.packed = packed; e.save = save; e.da = da; e.du = du; e.dz = dz; e.maxes = maxes;
   for (int k0 = 0; k0 < pl.K;) {  // up to 32 latent coordinates per pass (the table is KG = ceil4(K) wide)
     const int left = pl.KG - k0;
-    const unsigned grid = (unsigned)((B + 255) / 256);
+    const unsigned grid = (unsigned)((B + 128 * DZE_R - 1) / (128 * DZE_R));
     int kt;
     if (left >= 32) { kt = 32; nif_dz_edge_kernel<32><<<grid, 128, 0, st>>>(pl, e, k0); }
     else if (left >= 16) { kt = 16; nif_dz_edge_kernel<16><<<grid, 128, 0, st>>>(pl, e, k0); }

@@ -1,4 +1,5 @@
-"""Host-side data helpers (mirror of nif/data/__init__.py; the TFRecord reader is out of scope)."""
+"""Host-side data helpers (mirror of nif/data/__init__.py)."""
 from .point_wise_data import PointWiseData
+from .tfr_dataset import TFRDataset
 
-__all__ = ["PointWiseData"]
+__all__ = ["PointWiseData", "TFRDataset"]
