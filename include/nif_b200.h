@@ -97,6 +97,15 @@ int nif_forward_tangent(const nif_desc_t* d, int64_t B, const float* z, const fl
                         const float* packed, int32_t n_dir, const float* zdot, const float* xdot,
                         float* u, float* udot, void* stream);
 
+/* Second-order forward mode for one pair of directions (a, b): HessianLayer (nif/layers/gradient.py:130-180, 234-261,
+ * compute_output_and_grad_and_hessian) without the two nested tapes.  zdot [2][B][K] / xdot [2][B][si] hold the two
+ * directions (either may be null), zddot [B][K] the second derivative of the latent code along (a, b) (null = 0;
+ * coordinates have none).  Outputs: u [B][so], udot [2][B][so] = (du/da, du/db), uddot [B][so] = d2u / da db.
+ * a == b (the same direction twice) gives a diagonal entry. */
+int nif_forward_tangent2(const nif_desc_t* d, int64_t B, const float* z, const float* x, const float* packed,
+                         const float* zdot, const float* xdot, const float* zddot, float* u, float* udot,
+                         float* uddot, void* stream);
+
 /* Sobolev training: JacobianLayer INSIDE the loss (tutorial/8_NIF_with_Sobolov_training.ipynb cell 20:
  * JacobianLayer(model, y_index, x_index) -> concat [u, du/dt, du/dx] -> Sobolov_MSE on u and du/dx), where Keras
  * differentiates the tape of nif/layers/gradient.py:207-231 a second time.  Here: forward-mode tangents with a stash,

@@ -15,7 +15,7 @@ CSRC = os.path.join(_HERE, "csrc")
 
 # every symbol include/nif_b200.h declares
 SYMBOLS = (
-    "nif_last_error", "nif_version", "nif_query_sizes", "nif_pack", "nif_forward", "nif_forward_tangent",
+    "nif_last_error", "nif_version", "nif_query_sizes", "nif_pack", "nif_forward", "nif_forward_tangent", "nif_forward_tangent2",
     "nif_forward_given_w", "nif_mse_backward", "nif_backward", "nif_adam_step", "nif_adam_step_dev", "nif_measure_fp32_peak",
     "nif_trunk_query", "nif_trunk_forward", "nif_trunk_backward",
     "nif_sobolev_query", "nif_forward_tangent_save", "nif_sobolev_backward", "nif_crc32c",
@@ -83,6 +83,7 @@ def lib() -> C.CDLL:
     L.nif_pack.argtypes = [DP, I64, VP, VP, VP, VP]
     L.nif_forward.argtypes = [DP, I64, I64, VP, VP, I32, VP, VP, VP, VP]
     L.nif_forward_tangent.argtypes = [DP, I64, VP, VP, VP, I32, VP, VP, VP, VP, VP]
+    L.nif_forward_tangent2.argtypes = [DP, I64, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP]
     L.nif_forward_given_w.argtypes = [DP, I64, VP, VP, VP, VP]
     L.nif_mse_backward.argtypes = [DP, I64, VP, VP, VP, VP, VP, VP, VP, F, VP, VP, VP, F, VP, VP, VP]
     L.nif_backward.argtypes = [DP, I64, VP, VP, VP, VP, VP, VP, VP, F, VP, VP, VP]

@@ -104,6 +104,23 @@ extern "C" int nif_forward_tangent(const nif_desc_t* d, int64_t B, const float* 
   return nif_tangent_impl(pl, B, z, x, packed, n_dir, zdot, xdot, u, udot, nullptr, static_cast<cudaStream_t>(stream));
 }
 
+int nif_tangent2_impl(const Plan& pl, long long B, const float* z, const float* x, const float* packed,
+                      const float* zdot, const float* xdot, const float* zddot, float* u, float* udot, float* uddot,
+                      cudaStream_t st);
+extern "C" int nif_forward_tangent2(const nif_desc_t* d, int64_t B, const float* z, const float* x,
+                                    const float* packed, const float* zdot, const float* xdot, const float* zddot,
+                                    float* u, float* udot, float* uddot, void* stream) {
+  Plan pl;
+  int rc = nif_make_plan(d, &pl);
+  if (rc) return rc;
+  if (B < 0) { nif_set_error("nif_forward_tangent2: B=%lld", (long long)B); return NIF_E_BAD_ARG; }
+  if (B == 0) return NIF_OK;
+  if (pl.K > 0) NIF_REQUIRE_PTR(z);
+  NIF_REQUIRE_PTR(x); NIF_REQUIRE_PTR(packed); NIF_REQUIRE_PTR(u); NIF_REQUIRE_PTR(udot); NIF_REQUIRE_PTR(uddot);
+  NIF_OPTIONAL_PTR(zdot); NIF_OPTIONAL_PTR(xdot); NIF_OPTIONAL_PTR(zddot);
+  return nif_tangent2_impl(pl, B, z, x, packed, zdot, xdot, zddot, u, udot, uddot, static_cast<cudaStream_t>(stream));
+}
+
 extern "C" int nif_sobolev_query(const nif_desc_t* d, int64_t B, int64_t* save_floats_per_row, int64_t* ws_floats) {
   Plan pl;
   int rc = nif_make_plan(d, &pl);

@@ -8,12 +8,24 @@
 //   h_{m+1}  = alpha act(pre_m) (+ residual),   h_{m+1}' = alpha act'(pre_m) pre_m' (+ residual')
 // The weight stream is shared: every staged chunk M_m[k] is used by the primal GEMM and by one GEMM
 // per direction, and the primal product is reused for the zd term.
+//
+// Second order (HessianLayer, nif/layers/gradient.py:130-180, 234-261), template flag SEC: four streams
+// h, h_a', h_b', h_ab'' through the same weight stream,
+//   pre_m'' = sum_k zt[k] omega (h_ab'' M_m[k]) + zd_a[k] omega (h_b' M_m[k]) + zd_b[k] omega (h_a' M_m[k])
+//             + zdd_ab[k] (omega h M_m[k] + C_m[k])
+//   h_{m+1}'' = alpha ( act''(pre_m) pre_a' pre_b' + act'(pre_m) pre_m'' ) (+ residual'')
+// one launch per pair of directions (a, b); a == b gives the diagonal.
 #include "nif_tile.cuh"
 
 struct TanArgs {
   long long B, total_tiles;
   const float *z, *x, *packed, *zdot, *xdot;  // zdot [ND][B][K], xdot [ND][B][si] (either may be null)
   float *u, *udot;                            // udot [ND][B][so]
+  // second-order mode (SEC, HessianLayer): streams 1, 2 are the directions a, b given by zdot / xdot [2][..], stream 3
+  // carries the mixed second derivative; zddot [B][K] is the second derivative of the latent code along (a, b)
+  // (null = 0; coordinates have none), uddot [B][so] receives d2u / da db
+  const float* zddot;
+  float* uddot;
   // optional stash for the reverse-over-forward pass (Sobolev training), slots of [B][NP]:
   //   [0, H]            h_{m+1}                       [H+1, 2H+1]     d_m = alpha act'(pre_m)
   //   [2H+2, 3H+2]      h'_{m+1} of direction 0       [3H+3, 4H+3]    e_m = alpha act''(pre_m) pre_m' of direction 0
@@ -31,9 +43,10 @@ __host__ __device__ inline size_t tan_smem_bytes(int K, int si, int so) {
   return f * 4 + 64;
 }
 
-template <class C, int ND, bool RES>
+template <class C, int ND, bool RES, bool SEC>
 __global__ void __launch_bounds__(C::NT, 1) nif_tangent_kernel(const Plan pl, const TanArgs a) {
   constexpr int NP = C::NP, TB = C::TB, MP = C::MP, MJ = C::MJ, NT = C::NT, NS = 1 + ND;
+  static_assert(!SEC || ND == 3, "second-order mode carries the streams h, h_a', h_b', h_ab''");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* stage = reinterpret_cast<float*>(smem_raw);
   float* act = stage + 2 * C::STAGE_FLOATS;          // [NS][NP][TB]  stream 0 = primal
@@ -89,6 +102,7 @@ __global__ void __launch_bounds__(C::NT, 1) nif_tangent_kernel(const Plan pl, co
     // ---- stage z, zdot, x, xdot --------------------------------------------------------------------
     for (int s = 0; s < NS; ++s) {
       const float* zsrc = (s == 0) ? a.z : (a.zdot ? a.zdot + (long long)(s - 1) * a.B * K : nullptr);
+      if (SEC && s == 3) zsrc = a.zddot;
       for (int idx = tid; idx < TB * K; idx += NT) {
         const int p = idx / K, kk = idx - p * K;
         const long long b = row0 + p;
@@ -96,6 +110,7 @@ __global__ void __launch_bounds__(C::NT, 1) nif_tangent_kernel(const Plan pl, co
       }
       for (int p = tid; p < TB; p += NT) zs[(s * K1 + K) * TB + p] = (s == 0) ? 1.f : 0.f;
       const float* xsrc = (s == 0) ? a.x : (a.xdot ? a.xdot + (long long)(s - 1) * a.B * si : nullptr);
+      if (SEC && s == 3) xsrc = nullptr;  // coordinates have no second derivative
       for (int idx = tid; idx < TB * si; idx += NT) {
         const int p = idx / si, i = idx - p * si;
         const long long b = row0 + p;
@@ -141,6 +156,16 @@ __global__ void __launch_bounds__(C::NT, 1) nif_tangent_kernel(const Plan pl, co
           for (int r = 0; r < MP; ++r)
 #pragma unroll
             for (int c = 0; c < MJ; ++c) acc[d][r][c] = fmaf(zd[r], fmaf(om, tmp[r][c], cv[c]), acc[d][r][c]);
+        }
+      }
+      if (SEC && (s == 1 || s == 2)) {  // cross terms: the product of h_a' meets zd_b and vice versa
+        float zo[MP];
+        load_rows4(&zs[((3 - s) * K1 + kk) * TB], zo);
+#pragma unroll
+        for (int r = 0; r < MP; ++r) {
+          const float w = zo[r] * om;
+#pragma unroll
+          for (int c = 0; c < MJ; ++c) acc[SEC ? 3 : 0][r][c] = fmaf(w, tmp[r][c], acc[SEC ? 3 : 0][r][c]);
         }
       }
     };
@@ -193,6 +218,8 @@ __global__ void __launch_bounds__(C::NT, 1) nif_tangent_kernel(const Plan pl, co
 #pragma unroll
           for (int s = 0; s < NS; ++s) {
             float o = (s == 0) ? alpha * f : alpha * d * acc[s][r][c];
+            if (SEC && s == 3)
+              o = alpha * fmaf(act_dd(pl.act, acc[0][r][c], f, d), acc[1][r][c] * acc[SEC ? 2 : 0][r][c], d * acc[s][r][c]);
             if (res == 1) o += act[s * NP * TB + ai];
             if (RES) {
               if (res == 2) carry[RES ? s : 0][RES ? r : 0][RES ? c : 0] = act[s * NP * TB + ai];
@@ -262,6 +289,7 @@ __global__ void __launch_bounds__(C::NT, 1) nif_tangent_kernel(const Plan pl, co
           if (s == 0) fold(0, tmp, 0, kk, om, true);
           else if (s == 1) fold(1, tmp, 0, kk, om, false);
           else if (ND >= 2 && s == 2) fold(ND >= 2 ? 2 : 0, tmp, 0, kk, om, false);
+          else if (ND >= 3 && s == 3) fold(ND >= 3 ? 3 : 0, tmp, 0, kk, om, false);
         }
       }
       epilogue(0);
@@ -286,6 +314,7 @@ __global__ void __launch_bounds__(C::NT, 1) nif_tangent_kernel(const Plan pl, co
             if (s == 0) fold(0, tmp, m, kk, om, hf == 0);
             else if (s == 1) fold(1, tmp, m, kk, om, false);
             else if (ND >= 2 && s == 2) fold(ND >= 2 ? 2 : 0, tmp, m, kk, om, false);
+            else if (ND >= 3 && s == 3) fold(ND >= 3 ? 3 : 0, tmp, m, kk, om, false);
           }
           ws.release();
         }
@@ -332,6 +361,10 @@ __global__ void __launch_bounds__(C::NT, 1) nif_tangent_kernel(const Plan pl, co
             y[d][c] = fmaf(zk, sacc[d][c], y[d][c]);
             y[d][c] = fmaf(zs[(d * K1 + kk) * TB + p], sacc[0][c], y[d][c]);
           }
+          if (SEC) {
+            y[SEC ? 3 : 0][c] = fmaf(zs[(1 * K1 + kk) * TB + p], sacc[SEC ? 2 : 0][c], y[SEC ? 3 : 0][c]);
+            y[SEC ? 3 : 0][c] = fmaf(zs[((SEC ? 2 : 0) * K1 + kk) * TB + p], sacc[1][c], y[SEC ? 3 : 0][c]);
+          }
         }
       }
       // combine the kappa slices through shared memory (slot q of thread p)
@@ -352,6 +385,7 @@ __global__ void __launch_bounds__(C::NT, 1) nif_tangent_kernel(const Plan pl, co
                 float v = 0.f;
                 for (int qq = 0; qq < nsl; ++qq) v += ys[(s * so + c) * NT + qq * TB + p];
                 if (s == 0) a.u[b * so + c] = v;
+                else if (SEC && s == 3) a.uddot[b * so + c] = v;
                 else a.udot[((long long)(s - 1) * a.B + b) * so + c] = v;
               }
         }
@@ -361,7 +395,7 @@ __global__ void __launch_bounds__(C::NT, 1) nif_tangent_kernel(const Plan pl, co
   }
 }
 
-template <class C, int ND>
+template <class C, int ND, bool SEC = false>
 static int launch_tan(const Plan& pl, TanArgs a, cudaStream_t st) {
   const size_t smem = tan_smem_bytes<C, ND>(pl.K, pl.si, pl.so);
   if (smem > 227 * 1024) {
@@ -369,7 +403,7 @@ static int launch_tan(const Plan& pl, TanArgs a, cudaStream_t st) {
     return NIF_E_UNSUPPORTED;
   }
   const bool res = pl.variant == NIF_VARIANT_SIREN_RES;
-  auto kern = res ? nif_tangent_kernel<C, ND, true> : nif_tangent_kernel<C, ND, false>;
+  auto kern = res ? nif_tangent_kernel<C, ND, true, SEC> : nif_tangent_kernel<C, ND, false, SEC>;
   NIF_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int dev = 0, sms = 0, occ = 0;
   NIF_CUDA_CHECK(cudaGetDevice(&dev));
@@ -409,9 +443,28 @@ int nif_tangent_impl(const Plan& pl, long long B, const float* z, const float* x
     a.u = u;
     a.udot = udot + (long long)d0 * B * pl.so;
     a.save = d0 == 0 ? save : nullptr;  // the stash describes direction 0
+    a.zddot = nullptr; a.uddot = nullptr;
     const int nd = (n_dir - d0) >= 2 ? 2 : 1;
     const int rc = nd == 2 ? dispatch_tan<2>(pl, a, st) : dispatch_tan<1>(pl, a, st);
     if (rc != NIF_OK) return rc;
   }
   return NIF_OK;
+}
+
+// second order: one pair of directions (a, b) per call; udot [2][B][so] = (du/da, du/db), uddot [B][so] = d2u / da db
+int nif_tangent2_impl(const Plan& pl, long long B, const float* z, const float* x, const float* packed,
+                      const float* zdot, const float* xdot, const float* zddot, float* u, float* udot, float* uddot,
+                      cudaStream_t st) {
+  TanArgs a;
+  a.B = B;
+  a.total_tiles = 0;
+  a.z = z; a.x = x; a.packed = packed; a.zdot = zdot; a.xdot = xdot; a.zddot = zddot;
+  a.u = u; a.udot = udot; a.uddot = uddot; a.save = nullptr;
+  switch (pl.NP) {
+    case 32: return launch_tan<TCfg32, 3, true>(pl, a, st);
+    case 64: return launch_tan<TCfg64, 3, true>(pl, a, st);
+    case 128: return launch_tan<TCfg128, 3, true>(pl, a, st);
+  }
+  nif_set_error("unsupported padded width %d", pl.NP);
+  return NIF_E_UNSUPPORTED;
 }

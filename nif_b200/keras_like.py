@@ -327,6 +327,58 @@ class Model:
         J = udot.permute(1, 2, 0)[:, y_index, :]  # [B, |y|, |x|]
         return u, J.contiguous()
 
+    @torch.no_grad()
+    def _hessian_forward(self, inp: torch.Tensor, y_index, x_index):
+        """(y, J[b,a,c], H[b,a,c,e] = d2 y[b, y_index[a]] / d input[b, x_index[c]] d input[b, x_index[e]]) with
+        second-order forward mode: one launch per unordered pair of requested input columns carries h, the two first
+        tangents and the mixed second tangent through the fused kernel (HessianLayer, nif/layers/gradient.py:130-180,
+        234-261).  Directions on ParameterNet inputs take the first and second directional derivatives of the latent
+        code from the trunk (torch forward-mode AD)."""
+        n = self.net
+        B = inp.shape[0]
+        dev = inp.device
+        p_in = inp[:, : n.pi_dim].contiguous()
+        xs = inp[:, n.pi_dim: n.pi_dim + n.si_dim].contiguous()
+        nx, ny = len(x_index), len(y_index)
+        for c in x_index:
+            if not 0 <= c < n.pi_dim + n.si_dim:
+                raise IndexError(f"x_index {c} outside the {n.pi_dim + n.si_dim} model inputs")
+        jvp = torch.func.jvp
+
+        def unit(c):
+            e = torch.zeros_like(p_in)
+            e[:, c] = 1.0
+            return e
+
+        z = self._latent_nograd(p_in).contiguous()
+        zd = {c: jvp(n._latent, (p_in,), (unit(c),))[1] for c in set(x_index) if c < n.pi_dim}
+        packed = self._packed_weights()
+        u = None
+        J = torch.zeros(B, ny, nx, device=dev)
+        Hs = torch.zeros(B, ny, nx, nx, device=dev)
+        for ia in range(nx):
+            for ib in range(ia, nx):
+                ca, cb = x_index[ia], x_index[ib]
+                zdot = torch.zeros(2, B, n.pi_hidden, device=dev)
+                xdot = torch.zeros(2, B, n.si_dim, device=dev)
+                for k, c in enumerate((ca, cb)):
+                    if c < n.pi_dim:
+                        zdot[k] = zd[c]
+                    else:
+                        xdot[k, :, c - n.pi_dim] = 1.0
+                zddot = None
+                if ca < n.pi_dim and cb < n.pi_dim:  # both directions act on the trunk: its second directional derivative
+                    ea, eb = unit(ca), unit(cb)
+                    zddot = jvp(lambda q: jvp(n._latent, (q,), (ea,))[1], (p_in,), (eb,))[1].contiguous()
+                u, ud, udd = n.engine.forward_tangent2(z, xs, packed, zdot, xdot, zddot)
+                J[:, :, ia] = ud[0][:, y_index]
+                J[:, :, ib] = ud[1][:, y_index]
+                Hs[:, :, ia, ib] = udd[:, y_index]
+                Hs[:, :, ib, ia] = udd[:, y_index]
+        if u is None:
+            u = n.engine.forward(z, xs, packed)
+        return u, J, Hs
+
     def predict(self, x, batch_size=None, verbose=0, **_kw) -> np.ndarray:
         """Keras predict: batched forward, numpy out.  (Keras' default batch of 32 only affects speed;
         rows are independent, so a larger internal batch returns the same values.)"""

@@ -146,6 +146,28 @@ class FusedShapeNet:
               "nif_forward_tangent_save")
         return u, udot, stash
 
+    def forward_tangent2(self, z, x, packed, zdot: Optional[torch.Tensor], xdot: Optional[torch.Tensor],
+                         zddot: Optional[torch.Tensor]):
+        """Second-order forward mode for one pair of directions (a, b): zdot [2,B,K] / xdot [2,B,si] (either may be
+        None), zddot [B,K] = second derivative of the latent code along (a, b) (None = 0).  Returns
+        (u [B,so], udot [2,B,so] = (du/da, du/db), uddot [B,so] = d2u/da db)."""
+        x = _f32c(x, "x")
+        B = x.shape[0]
+        z = _f32c(z, "z") if self.K > 0 else None
+        zdot = _f32c(zdot, "zdot") if zdot is not None else None
+        xdot = _f32c(xdot, "xdot") if xdot is not None else None
+        zddot = _f32c(zddot, "zddot") if zddot is not None else None
+        for name, t, shape in (("zdot", zdot, (2, B, self.K)), ("xdot", xdot, (2, B, self.si)), ("zddot", zddot, (B, self.K))):
+            if t is not None and tuple(t.shape) != shape:
+                raise NifError(f"{name} must be {list(shape)}, got {list(t.shape)}")
+        u = torch.empty(B, self.so, dtype=torch.float32, device=x.device)
+        udot = torch.empty(2, B, self.so, dtype=torch.float32, device=x.device)
+        uddot = torch.empty(B, self.so, dtype=torch.float32, device=x.device)
+        check(_lib.lib().nif_forward_tangent2(C.byref(self.desc), B, _ptr(z), _ptr(x), _ptr(packed), _ptr(zdot), _ptr(xdot),
+                                              _ptr(zddot), _ptr(u), _ptr(udot), _ptr(uddot), _stream()),
+              "nif_forward_tangent2")
+        return u, udot, uddot
+
     def sobolev_backward(self, z, x, xdot0, packed, stash, du, dudot0, dw_h, db_h, beta: float = 0.0):
         """Reverse-over-forward pass: seeds du = dL/du [B,so] and dudot0 = dL/d(udot of direction 0) [B,so];
         xdot0 [B,si] is direction 0 of the forward_tangent(save=True) call.  Fills dw_h / db_h, returns dz."""

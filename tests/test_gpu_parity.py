@@ -544,3 +544,54 @@ def test_graph_replayed_steps_equal_eager_steps_bitwise():
     assert i0 == i1 == len(batches)
     assert l0 == l1
     assert torch.equal(t0, t1) and torch.equal(m0, m1) and torch.equal(v0, v1)
+
+
+@pytest.mark.parametrize("case", ["siren_2x30", "nif_tanh_si3_so2", "siren_res_so3_n12_K3_sine"])
+def test_hessian_layer_matches_reference_golden(case):
+    """HessianLayer via second-order forward tangents (nif_forward_tangent2) vs the reference's
+    compute_output_and_grad_and_hessian (golden `jac`, `hess`, made by running the reference source)."""
+    import nif_b200
+    d, cls, cfg_s, cfg_p, spec, prm, _ = load_golden(case)
+    net = getattr(nif_b200, cls)(cfg_s, cfg_p, seed=0, device="cuda:0")
+    net.set_weights({k: v.float().numpy() for k, v in prm.items()})
+    yi, xi = list(d["jac_y_index"]), list(d["jac_x_index"])
+    y, J, H = nif_b200.HessianLayer(net.build(), yi, xi)(d["inputs"].astype(np.float32))
+    assert tuple(J.shape) == d["jac"].shape and tuple(H.shape) == d["hess"].shape
+    prm32 = {k: v.float() for k, v in prm.items()}
+    _, J32, H32 = O.hessian(spec, prm32, torch.as_tensor(d["inputs"]).float(), yi, xi)
+    assert _gate(rel_err(y.cpu(), d["y"]), rel_err(d["y32"], d["y"]))
+    assert _gate(rel_err(J.cpu(), d["jac"]), rel_err(J32, d["jac"]), floor=2e-5)
+    assert _gate(rel_err(H.cpu(), d["hess"]), rel_err(H32, d["hess"]), floor=5e-5)
+
+
+@pytest.mark.parametrize("cls,cfg_s,cfg_p,B,xi", [
+    ("NIFMultiScale",  # C4 shape: derivatives w.r.t. t (through the trunk, second order) and x
+     {"use_resblock": False, "connectivity": "full", "input_dim": 1, "output_dim": 1, "units": 64, "nlayers": 4,
+      "weight_init_factor": 0.01, "omega_0": 30.0},
+     {"use_resblock": False, "input_dim": 1, "latent_dim": 32, "units": 64, "nlayers": 4, "activation": "swish"}, 200, [0, 1]),
+    ("NIFMultiScale",  # spatial Hessian of a 3-D field, width 128
+     {"use_resblock": False, "connectivity": "full", "input_dim": 3, "output_dim": 2, "units": 128, "nlayers": 1,
+      "weight_init_factor": 0.05, "omega_0": 10.0},
+     {"use_resblock": False, "input_dim": 1, "latent_dim": 4, "units": 16, "nlayers": 1, "activation": "swish"}, 90, [1, 2, 3]),
+    ("NIF",
+     {"connectivity": "full", "input_dim": 2, "output_dim": 2, "units": 30, "nlayers": 2, "activation": "swish"},
+     {"input_dim": 1, "latent_dim": 2, "units": 30, "nlayers": 2, "activation": "tanh"}, 150, [2, 0]),
+])
+def test_hessian_layer_random(cls, cfg_s, cfg_p, B, xi):
+    import nif_b200
+    spec = O.spec_from_cfg(cls, cfg_s, cfg_p)
+    prm = O.init_params(spec, 17)
+    net = getattr(nif_b200, cls)(cfg_s, cfg_p, seed=0, device="cuda:0")
+    net.set_weights({k: v.numpy() for k, v in prm.items()})
+    rng = np.random.default_rng(B)
+    X = rng.uniform(-1, 1, (B, spec.pi + spec.si)).astype(np.float32)
+    yi = list(range(spec.so))
+    y, J, H = nif_b200.HessianLayer(net.build(), yi, xi)(X)
+    prm64 = {k: v.double() for k, v in prm.items()}
+    y64, J64, H64 = O.hessian(spec, prm64, torch.as_tensor(X).double(), yi, xi)
+    y32, J32, H32 = O.hessian(spec, prm, torch.as_tensor(X), yi, xi)
+    assert tuple(H.shape) == (B, len(yi), len(xi), len(xi))
+    assert torch.equal(H, H.transpose(2, 3))
+    assert _gate(rel_err(y.cpu(), y64), rel_err(y32, y64))
+    assert _gate(rel_err(J.cpu(), J64), rel_err(J32, J64), floor=2e-5)
+    assert _gate(rel_err(H.cpu(), H64), rel_err(H32, H64), floor=5e-5)
