@@ -474,10 +474,11 @@ class Model:
         self.optimizer.apply(n.theta, n.grad, l1, l2)
         return loss
 
-    def _fused_step(self, inp, tgt, sw, gb, apply_update):
-        """Fully fused step: trunk, hyper-network head + ShapeNet, loss and both reverse passes are library kernels;
-        every gradient is written (beta = 0) straight into the flat gradient buffer.  Only stream-ordered work (no
-        host read, no allocation outside torch's caching allocator), so the same body is what a CUDA graph records."""
+    def _fused_part1(self, inp, tgt, sw, gb):
+        """Trunk forward, hyper-network head + ShapeNet, loss, reverse pass of the head: every gradient of the last
+        linear layer is written (beta = 0) straight into the flat gradient buffer.  Returns what the trunk's reverse
+        pass needs.  Only stream-ordered work (no host read, no allocation outside torch's caching allocator), so the
+        same body is what a CUDA graph records."""
         n = self.net
         eng = n.engine
         xs = inp[:, n.pi_dim: n.pi_dim + n.si_dim].contiguous()
@@ -487,10 +488,24 @@ class Model:
         u, stash = eng.forward(z, xs, packed, save=True)
         dz = eng.mse_backward(z, xs, packed, u, stash, tgt, sw, 1.0 / gb, self._loss_buf,
                               n._gviews[n._last_names[0]], n._gviews[n._last_names[1]], 0.0)
-        # data parallel: the last linear layer's gradient (almost all of the buffer) is summed across ranks
-        # while the trunk's reverse pass runs; the small trunk gradient follows
-        h_head = self.dist.allreduce_start(n.grad[n._n_trunk:]) if self.dist is not None else None
+        return p_in, tstash, dz
+
+    def _fused_part2(self, ctx):
+        n = self.net
+        p_in, tstash, dz = ctx
         n._trunk.backward(p_in, n.theta_trunk, tstash, dz, n.grad_trunk, 0.0)
+
+    def _fused_step(self, inp, tgt, sw, gb, apply_update, part1=None, part2=None):
+        """One fully fused optimisation step; `part1` / `part2` replace the two kernel sequences by graph replays.
+        Data parallel: the last linear layer's gradient (almost all of the buffer) is summed across ranks while the
+        trunk's reverse pass runs; the small trunk gradient follows."""
+        n = self.net
+        ctx = part1() if part1 is not None else self._fused_part1(inp, tgt, sw, gb)
+        h_head = self.dist.allreduce_start(n.grad[n._n_trunk:]) if self.dist is not None else None
+        if part2 is not None:
+            part2()
+        else:
+            self._fused_part2(ctx)
         if self.dist is not None:
             h_trunk = self.dist.allreduce_start(n.grad_trunk)
             self.dist.allreduce_finish(h_head)
@@ -503,18 +518,21 @@ class Model:
     # kernels, set the step time.  The step body is stream-ordered and allocation-free apart from torch's caching
     # allocator, so it is recorded once per (rows, global batch, sample-weighted?) and replayed; per step the host
     # only copies the batch into the graph's input buffers and stores Adam's bias-corrected step size.
+    # Data parallel: the two kernel sequences either side of the first all-reduce are recorded as two graphs sharing
+    # one memory pool; the NCCL calls and the Adam launch between / after them stay eager.
     GRAPH_CACHE = 4
 
     def _graph_enabled(self) -> bool:
         g = self.use_graph
         if g is None:
             g = os.environ.get("NIF_B200_GRAPH", "1") != "0"
-        return bool(g) and self.dist is None
+        return bool(g)
 
     def _graph_signature(self):
         n, opt = self.net, self.optimizer
         return (n.theta.data_ptr(), n.grad.data_ptr(), opt._m.data_ptr(), opt._v.data_ptr(), opt._alpha_dev.data_ptr(),
-                self._loss_buf.data_ptr(), id(opt), opt.beta_1, opt.beta_2, opt.epsilon, n._kernel_regulariser())
+                self._loss_buf.data_ptr(), id(opt), opt.beta_1, opt.beta_2, opt.epsilon, n._kernel_regulariser(),
+                self.dist is not None)
 
     def _train_step_graph(self, inp, tgt, sw, gb) -> torch.Tensor:
         n, opt = self.net, self.optimizer
@@ -536,10 +554,19 @@ class Model:
             ent["inp"], ent["tgt"] = torch.empty_like(inp), torch.empty_like(tgt)
             ent["sw"] = torch.empty_like(sw) if sw is not None else None
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                self._loss_buf.zero_()
-                self._fused_step(ent["inp"], ent["tgt"], ent["sw"], gb, opt.record_apply)
-            ent["graph"] = g
+            if self.dist is None:
+                with torch.cuda.graph(g):
+                    self._loss_buf.zero_()
+                    self._fused_step(ent["inp"], ent["tgt"], ent["sw"], gb, opt.record_apply)
+                ent["graph"] = g
+            else:
+                g2 = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._loss_buf.zero_()
+                    ctx = self._fused_part1(ent["inp"], ent["tgt"], ent["sw"], gb)
+                with torch.cuda.graph(g2, pool=g.pool()):
+                    self._fused_part2(ctx)
+                ent["graph"], ent["graph2"], ent["ctx"] = g, g2, ctx  # ctx: buffers the second graph reads stay alive
             # buffers whose addresses are baked into the graph stay alive as long as it does
             ent["keep"] = (n.engine._ws, n._trunk._ws, n._trunk._packed, self._packed, self._loss_buf, n.theta, n.grad,
                            opt._m, opt._v, opt._alpha_dev)
@@ -548,8 +575,11 @@ class Model:
         ent["tgt"].copy_(tgt, non_blocking=True)
         if sw is not None:
             ent["sw"].copy_(sw, non_blocking=True)
-        opt.advance_replay()
-        ent["graph"].replay()
+        if self.dist is None:
+            opt.advance_replay()
+            ent["graph"].replay()
+        else:
+            self._fused_step(None, None, None, gb, opt.apply, part1=ent["graph"].replay, part2=ent["graph2"].replay)
         return self._loss_buf
 
     # ---- Sobolev training (JacobianLayer inside the loss) ---------------------------------------------------

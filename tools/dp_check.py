@@ -14,16 +14,16 @@ rng = np.random.default_rng(0)
 GB = 4096
 X = rng.uniform(-1, 1, (GB, 3)).astype(np.float32); Y = rng.uniform(-1, 1, (GB, 1)).astype(np.float32)
 
-def run(parallel):
+def run(parallel, graph=None, steps=3):
     net = nif_b200.NIFMultiScale(cfg_s, cfg_p, seed=0, device=dev)
-    m = net.build(); m.compile(nif_b200.Adam(1e-3), loss="mse")
+    m = net.build(); m.compile(nif_b200.Adam(1e-3), loss="mse", graph=graph)
     if parallel:
         dp.attach(m)
         xs, ys = X[dp.rank::dp.world], Y[dp.rank::dp.world]
     else:
         xs, ys = X, Y
     losses = []
-    for _ in range(3):
+    for _ in range(steps):
         l = m._train_step(torch.as_tensor(xs).to(dev), torch.as_tensor(ys).to(dev), None, GB).clone()
         if parallel: dp.allreduce_(l)
         losses.append(float(l))
@@ -35,4 +35,10 @@ err = float((th_dp - th_1).abs().max() / th_1.abs().max())
 if dp.rank == 0:
     print("DP check: world", dp.world, "losses dp", l_dp, "single", l_1, "max rel param diff after 3 steps", err)
 assert err < 1e-5 and all(abs(a - b) < 1e-5 * max(1, abs(b)) for a, b in zip(l_dp, l_1)), (err, l_dp, l_1)
+# the graph-replayed data-parallel step (two graphs around the first all-reduce) == the eager one, bit for bit
+th_g, l_g = run(True, graph=True, steps=5)
+th_e, l_e = run(True, graph=False, steps=5)
+if dp.rank == 0:
+    print("DP graph vs eager: params equal", bool(torch.equal(th_g, th_e)), "losses equal", l_g == l_e)
+assert torch.equal(th_g, th_e) and l_g == l_e
 dp.shutdown()
