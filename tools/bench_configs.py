@@ -53,7 +53,7 @@ Y = torch.as_tensor(rng.uniform(-1, 1, (512, 1)).astype(np.float32)).to(dev)
 ms = ev_time(lambda: m._train_step(X, Y, None, 512), 50)
 F, P = flops_step(1, 1, 1, 30, 2, 1, 30, 2)
 out.append({"config": "C1 tutorial-1 NIF swish 2x30, latent 1, batch 512", "po_dim": P, "ms_per_step": ms,
-            "points_per_s": 512 / ms * 1e3, "note": "launch-latency bound (17 launches per step)"})
+            "points_per_s": 512 / ms * 1e3, "note": "graph-replayed step (17 kernels per step; 0.178 ms with eager launches)"})
 
 # ---- C3: turbulence, ShapeNet 3->6x128->3 SIREN, ParameterNet 1->4x128->latent 64 ----
 cfg_s = {"use_resblock": False, "connectivity": "full", "input_dim": 3, "output_dim": 3, "units": 128, "nlayers": 6,
