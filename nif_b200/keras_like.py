@@ -454,18 +454,27 @@ class Model:
         self._loss_buf.zero_()
         xs = inp[:, n.pi_dim: n.pi_dim + n.si_dim].contiguous()
         n.grad.zero_()
-        z = n._latent(inp[:, : n.pi_dim])
+        p_in = inp[:, : n.pi_dim]
+        z = n._latent(p_in)
+        # JacRegLatentLayer's add_loss term (this process's share of the global-batch mean)
+        reg = n._jac_reg_loss(p_in) * (B / gb) if isinstance(n.p_jac_reg, (float, int)) else None
         if not callable(self.loss):
             packed = self._packed_weights()
             zc = z.detach().contiguous()
             u, stash = eng.forward(zc, xs, packed, save=True)
             dz = eng.mse_backward(zc, xs, packed, u, stash, tgt, sw, 1.0 / gb, self._loss_buf,
                                   n._gviews[n._last_names[0]], n._gviews[n._last_names[1]], 0.0)
-            z.backward(dz)
+            if reg is None:
+                z.backward(dz)
+            else:
+                torch.autograd.backward([z, reg], [dz, torch.ones_like(reg)])
+                self._loss_buf += reg.detach()
             loss = self._loss_buf
         else:
             u = ops.fused_shapenet(z, xs, n.w_h, n.b_h, eng)
             lv = self.loss(tgt, u) * (B / gb)
+            if reg is not None:
+                lv = lv + reg
             lv.backward()
             loss = lv.detach().reshape(1)
         if self.dist is not None:

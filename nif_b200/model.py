@@ -66,9 +66,8 @@ class NIF(object):
         self.p_l2_reg = cfg_parameter_net.get("l2_reg", None)
         self.p_act_l1_reg = cfg_parameter_net.get("act_l1_reg", None)
         self.p_act_l2_reg = cfg_parameter_net.get("act_l2_reg", None)
-        if isinstance(self.p_jac_reg, (float, int)) or isinstance(self.p_act_l1_reg, (float, int)) or isinstance(
-                self.p_act_l2_reg, (float, int)):
-            raise NotImplementedError("jac_reg / act_l1_reg / act_l2_reg are outside the B200 hot-path scope")
+        if isinstance(self.p_act_l1_reg, (float, int)) or isinstance(self.p_act_l2_reg, (float, int)):
+            raise NotImplementedError("act_l1_reg / act_l2_reg are outside the B200 hot-path scope")
         if mixed_policy not in _POLICIES:
             raise ValueError(f"mixed_policy must be one of {_POLICIES} (float64 has no GPU path)")
         if compute not in ("auto", "fp32", "fp16x3"):
@@ -138,7 +137,8 @@ class NIF(object):
         what libnif_b200's trunk kernels implement; other trunks run as torch ops."""
         p = self.cfg_parameter_net
         return (p.get("activation") in ("swish", "tanh", "relu", "sigmoid", "linear", None) and self.n_st <= 64
-                and not bool(p.get("use_resblock", False)) and self.pi_dim <= 8)
+                and not bool(p.get("use_resblock", False)) and self.pi_dim <= 8
+                and not isinstance(self.p_jac_reg, (float, int)))  # the Jacobian regulariser differentiates the trunk twice
 
     def _place(self, layout):
         """Offsets of every variable in the flat buffer.  With the fused trunk, the trunk variables are laid out
@@ -277,6 +277,19 @@ class NIF(object):
     def b_h(self) -> torch.Tensor:
         return self._views[self._last_names[1]]
 
+    def _jac_reg_loss(self, input_p: torch.Tensor) -> torch.Tensor:
+        """JacRegLatentLayer (nif/layers/gradient.py:52-113) as build() wires it (nif/model.py:353-375, y_index = every
+        latent unit, x_index = every ParameterNet input):  jac_reg * mean_{b,k,c} (d latent[b,k] / d input_p[b,c])^2.
+        One forward-mode tangent per ParameterNet input; the result is differentiable w.r.t. the trunk variables
+        (reverse over forward), which is how its gradient reaches the flat gradient buffer."""
+        sq = input_p.new_zeros(())
+        for c in range(self.pi_dim):
+            e = torch.zeros_like(input_p)
+            e[:, c] = 1.0
+            _, zd = torch.func.jvp(self._latent, (input_p,), (e,))
+            sq = sq + (zd * zd).sum()
+        return float(self.p_jac_reg) * sq / (input_p.shape[0] * self.pi_hidden * self.pi_dim)
+
     def _kernel_regulariser(self) -> Tuple[float, float]:
         """(l1, l2) applied to every ParameterNet kernel and bias (nif/model.py:107-117); l2 wins."""
         if isinstance(self.p_l2_reg, (float, int)):
@@ -291,7 +304,8 @@ class NIF(object):
         return self.model()(inputs, training=bool(training))
 
     def build(self) -> Model:
-        """nif/model.py:345-377 (jac_reg is rejected in __init__, so this is `.model()`)."""
+        """nif/model.py:345-377: with `jac_reg` the reference wraps the model in JacRegLatentLayer, which only adds a loss
+        term; here that term is added by the training step (Model._train_step), so this is `.model()`."""
         return self.model()
 
     def model(self) -> Model:

@@ -499,12 +499,29 @@ def sobolev_loss_and_grads(spec: Spec, prm: Dict[str, Tensor], inputs: Tensor, t
 # ----------------------------------------------------------------------------
 # a whole training step in the reference's materialised dataflow (CPU baseline)
 # ----------------------------------------------------------------------------
+def jac_reg_loss(spec: Spec, prm: Dict[str, Tensor], inputs: Tensor, l1: float) -> Tensor:
+    """The add_loss term of JacRegLatentLayer (nif/layers/gradient.py:52-113) as NIF.build() wires it
+    (nif/model.py:353-375): y_index = range(latent_dim), x_index = range(pi_dim) on the augmented model whose second
+    output is the latent code, so  l1 * reduce_mean(square(d latent / d input_p))  over (batch, latent, pi).
+    compute_output_and_augment_grad (gradient.py:183-204) takes the batch Jacobian w.r.t. the whole input and gathers
+    the ParameterNet columns; the latent code does not depend on the other columns."""
+    p_in = inputs[:, : spec.pi].detach().clone().requires_grad_(True)
+    z = latent(spec, prm, p_in)
+    rows = []
+    for k in range(z.shape[1]):
+        (g,) = torch.autograd.grad(z[:, k].sum(), p_in, create_graph=True, retain_graph=True)
+        rows.append(g)
+    J = torch.stack(rows, 1)  # [B, K, pi]
+    return l1 * (J * J).mean()
+
+
 class MaterialisedTrainer:
     """fit()-equivalent inner loop on CPU: forward with the (B, po_dim) tensor
     materialised, reverse-mode gradient, TF-semantics Adam.  Used as the
     'TF2-CPU proxy' baseline."""
 
-    def __init__(self, spec: Spec, prm: Dict[str, Tensor], lr: float = 1e-3):
+    def __init__(self, spec: Spec, prm: Dict[str, Tensor], lr: float = 1e-3, jac_reg: Optional[float] = None):
+        self.jac_reg = jac_reg
         self.spec = spec
         self.prm = {k: v.detach().clone().requires_grad_(True) for k, v in prm.items()}
         self.m = {k: torch.zeros_like(v) for k, v in self.prm.items()}
@@ -517,6 +534,8 @@ class MaterialisedTrainer:
             p.grad = None
         y = forward(self.spec, self.prm, inputs)
         loss = mse(y, target, sample_weight)
+        if self.jac_reg is not None:
+            loss = loss + jac_reg_loss(self.spec, self.prm, inputs, self.jac_reg)
         loss.backward()
         self.t += 1
         with torch.no_grad():

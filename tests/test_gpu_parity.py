@@ -595,3 +595,34 @@ def test_hessian_layer_random(cls, cfg_s, cfg_p, B, xi):
     assert _gate(rel_err(y.cpu(), y64), rel_err(y32, y64))
     assert _gate(rel_err(J.cpu(), J64), rel_err(J32, J64), floor=2e-5)
     assert _gate(rel_err(H.cpu(), H64), rel_err(H32, H64), floor=5e-5)
+
+
+def test_training_with_jac_reg_matches_oracle_trainer():
+    """cfg_parameter_net['jac_reg'] (JacRegLatentLayer, nif/model.py:353-375): the training step adds
+    jac_reg * mean((d latent / d input_p)^2) to the loss; steps against the oracle trainer with the same term."""
+    import nif_b200
+    cfg_s = {"connectivity": "full", "input_dim": 1, "output_dim": 1, "units": 30, "nlayers": 2, "activation": "swish"}
+    cfg_p = {"input_dim": 1, "latent_dim": 2, "units": 30, "nlayers": 2, "activation": "swish", "jac_reg": 30.0}
+    spec = O.spec_from_cfg("NIF", cfg_s, cfg_p)
+    prm = O.init_params(spec, 23)
+    net = nif_b200.NIF(cfg_s, cfg_p, seed=0, device="cuda:0")
+    net.set_weights({k: v.numpy() for k, v in prm.items()})
+    model = net.build()
+    model.compile(nif_b200.Adam(1e-3), loss="mse")
+    ref = O.MaterialisedTrainer(spec, {k: v.double() for k, v in prm.items()}, lr=1e-3, jac_reg=30.0)
+    ref0 = O.MaterialisedTrainer(spec, {k: v.double() for k, v in prm.items()}, lr=1e-3)
+    rng = np.random.default_rng(6)
+    B = 256
+    for step in range(3):
+        X = rng.uniform(-1, 1, (B, 2)).astype(np.float32)
+        Y = rng.uniform(-1, 1, (B, 1)).astype(np.float32)
+        l_gpu = model.train_on_batch(X, Y)
+        l_ref = ref.step(torch.as_tensor(X).double(), torch.as_tensor(Y).double())
+        if step == 0:
+            l_plain = ref0.step(torch.as_tensor(X).double(), torch.as_tensor(Y).double())
+            assert l_ref - l_plain > 1e-2 * l_plain  # the regulariser is a visible part of the loss in this set-up
+        assert abs(l_gpu - l_ref) <= 1e-4 * max(1.0, abs(l_ref)), (step, l_gpu, l_ref)
+    got = net.get_weights()
+    diffs = np.concatenate([np.abs(got[k] - v.detach().numpy()).ravel() for k, v in ref.prm.items()])
+    assert float(np.quantile(diffs, 0.999)) < 1e-4, float(np.quantile(diffs, 0.999))
+    assert float(diffs.max()) < 4 * 2e-3

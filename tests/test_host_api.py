@@ -184,3 +184,37 @@ def test_pointwise_normalisers_match_oracle():
     rawa = np.hstack([rng.normal(size=(50, 3)), rng.uniform(1, 2, (50, 1))])
     d, mean, std, w = PointWiseData.minmax_normalize(rawa.copy(), 1, 1, 1, area_weighted=True)
     assert d.shape == (50, 3) and abs(w.mean() - 1) < 1e-12 and mean[-1] == 0
+
+
+@pytest.mark.parametrize("cls,cfg_s,cfg_p", [
+    ("NIF", {"connectivity": "full", "input_dim": 1, "output_dim": 1, "units": 30, "nlayers": 2, "activation": "swish"},
+     {"input_dim": 2, "latent_dim": 3, "units": 30, "nlayers": 2, "activation": "swish", "jac_reg": 1e-2}),
+    ("NIFMultiScale", CFG_S, dict(CFG_P, jac_reg=0.5)),
+])
+def test_jac_reg_latent_loss_matches_oracle(cls, cfg_s, cfg_p):
+    """The add_loss term of JacRegLatentLayer (gradient.py:52-113, model.py:353-375): value and trunk gradient of the
+    product's forward-mode formulation against the oracle's batch-Jacobian restatement (trunk only: runs on CPU)."""
+    import torch
+    from oracle import nif_oracle as O
+    spec = O.spec_from_cfg(cls, cfg_s, cfg_p)
+    prm = {k: v.double() for k, v in O.init_params(spec, 5).items()}
+    net = getattr(nif_b200, cls)(cfg_s, cfg_p, seed=0, device="cpu")
+    assert net._trunk is None and not net._fused_trunk_supported()  # the regulariser needs the differentiable trunk
+    net.set_weights({k: v.float().numpy() for k, v in prm.items()})
+    rng = np.random.default_rng(0)
+    X = torch.as_tensor(rng.uniform(-1, 1, (64, spec.pi + spec.si)))
+    ref_prm = {k: v.clone().requires_grad_(True) for k, v in prm.items()}
+    ref = O.jac_reg_loss(spec, ref_prm, X, cfg_p["jac_reg"])
+    ref.backward()
+    got = net._jac_reg_loss(X[:, : spec.pi].float())
+    net.grad.zero_()
+    got.backward()
+    assert abs(float(got) - float(ref)) <= 1e-5 * abs(float(ref))
+    last = set(net._last_names)
+    for k, v in ref_prm.items():
+        g = net._gviews[k]
+        if k in last or v.grad is None:
+            # the last linear layer is not part of the latent code; the bottleneck bias does not enter its Jacobian
+            assert v.grad is None and float(g.abs().max()) == 0.0, k
+        else:
+            assert float((g.double() - v.grad).abs().max()) <= 2e-5 * float(v.grad.abs().max()) + 1e-12, k
