@@ -1,3 +1,5 @@
+"""Error report (not a pytest module): fp32 CUDA-core and FP16x3 tensor-core kernels against the fp64 oracle, next to what
+fp32 on the CPU gives.    python tests/report_tc_errors.py"""
 import sys, numpy as np, torch
 sys.path.insert(0, '.')
 from oracle import nif_oracle as O

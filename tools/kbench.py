@@ -1,18 +1,18 @@
 """Kernel micro-benchmark at the C2 shape: CUDA events around individual C-ABI calls."""
 import sys, torch
 sys.path.insert(0, '.')
-from oracle import nif_oracle as O
+import bench
+import nif_b200
 from nif_b200.ops import FusedShapeNet
 
 dev = torch.device('cuda:0')
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
-spec = O.Spec(variant="siren", pi=1, si=2, so=1, n=64, l=4, K=32, n_st=64, l_st=4, p_act="swish", omega0=30.0, weight_init_factor=0.01)
-prm = O.init_params(spec, 0)
+net = nif_b200.NIFMultiScale(bench.CFG_S, bench.CFG_P, "float32", seed=0, device=torch.device("cuda:0"))  # the product's own initialiser
 g = torch.Generator().manual_seed(0)
 z = (torch.rand(B, 32, generator=g) - 0.5).to(dev)
 x = (torch.rand(B, 2, generator=g) * 2 - 1).to(dev)
 tgt = torch.rand(B, 1, generator=g).to(dev)
-w_h, b_h = prm["HyperLinearForSIREN_w"].to(dev), prm["HyperLinearForSIREN_b"].to(dev)
+w_h, b_h = net.w_h.detach(), net.b_h.detach()
 flops = (2 * 32 * 16897 + 2 * (128 + 4 * 4096 + 64)) * B
 
 def ev(fn, reps=10):

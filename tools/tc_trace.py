@@ -8,19 +8,19 @@ import numpy as np
 import torch
 
 sys.path.insert(0, '.')
-from oracle import nif_oracle as O
+import bench
+import nif_b200
 from nif_b200 import _lib
 from nif_b200.ops import FusedShapeNet
 
 dev = torch.device('cuda:0')
 B = 65536
-spec = O.Spec(variant="siren", pi=1, si=2, so=1, n=64, l=4, K=32, n_st=64, l_st=4, p_act="swish", omega0=30.0, weight_init_factor=0.01)
-prm = O.init_params(spec, 0)
+net = nif_b200.NIFMultiScale(bench.CFG_S, bench.CFG_P, "float32", seed=0, device=torch.device("cuda:0"))  # the product's own initialiser
 g = torch.Generator().manual_seed(0)
 z = (torch.rand(B, 32, generator=g) - 0.5).to(dev)
 x = (torch.rand(B, 2, generator=g) * 2 - 1).to(dev)
 eng = FusedShapeNet("siren", 2, 1, 64, 4, 32, omega0=30.0, compute="fp16x3")
-packed = eng.pack(prm["HyperLinearForSIREN_w"].to(dev), prm["HyperLinearForSIREN_b"].to(dev))
+packed = eng.pack(net.w_h.detach(), net.b_h.detach())
 L = _lib.lib()
 which = sys.argv[2] if len(sys.argv) > 2 else "fwd"
 host = np.zeros((4, 2048), dtype=np.int64)
