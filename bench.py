@@ -33,6 +33,8 @@ CFG_P = {"use_resblock": False, "input_dim": 1, "latent_dim": 32, "units": 64, "
 N_POINTS = 1_000_000
 BATCH = 65_536
 METRIC = "point-evals/sec (fwd+bwd+Adam)"
+WORKLOAD = ("C2 tutorial-2 multi-scale NIF: ShapeNet 2->4x64->1 SIREN (omega0 30), ParameterNet 1->64x4 swish->latent 32, "
+            "po_dim 16897, 1M points/GPU, fp32")
 UNIT = "points/s"
 
 
@@ -88,9 +90,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "C2 tutorial-2 multi-scale NIF: ShapeNet 2->4x64->1 SIREN, latent 32, fp32",
-                   "rows_per_step": rows, "note": "TensorFlow 2.11 is not installable here; oracle port of the "
-                                                  "reference's materialised (B,po_dim) dataflow, torch CPU fp32"},
+        "config": {"workload": WORKLOAD, "rows_per_step": rows,
+                   "note": "TensorFlow 2.11 is not installable here; oracle port of the reference's materialised "
+                           "(B,po_dim) dataflow, torch CPU fp32, on a bounded sample of the workload per step"},
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{args.steps} steps x {rows} rows of the C2 workload (fwd+bwd+Adam)"},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -263,9 +265,7 @@ def run_ours(args):
         "metric": METRIC, "value": pts, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": "C2 tutorial-2 multi-scale NIF: ShapeNet 2->4x64->1 SIREN (omega0 30), ParameterNet "
-                               "1->64x4 swish->latent 32, po_dim 16897, 1M points/GPU, fp32",
-                   "batch_per_gpu": BATCH, "global_batch": gb, "parallelism": f"dp{world}",
+        "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "global_batch": gb, "parallelism": f"dp{world}",
                    "l2": "inputs rotate through the 1M-point set; per-step working set (activation stash 168 MB + "
                          "deltas 84 MB) exceeds the 126 MB L2, no explicit flush"},
         "clocks": clocks,
