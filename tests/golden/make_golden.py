@@ -9,7 +9,8 @@ Writes tests/golden/<case>.npz with: the two cfg dicts (JSON), every weight the
 reference layers created (named by the reference layer names), a seeded input
 batch, the reference output `y`, the pnet_output `(B, po_dim)` tensor, the
 latent, the gradients of Keras-'mse' w.r.t. every weight and the latent, and
-the JacobianLayer output for the cases that have one.  fp64 is stored; the
+the JacobianLayer / HessianLayer outputs for the cases that have one, and the latent-code Jacobian that
+JacRegLatentLayer regularises.  fp64 is stored; the
 fp32 run of the same weights is stored as `y32`.
 """
 import importlib
@@ -154,6 +155,15 @@ def main():
             out["jac"] = J.detach().numpy()
             _, J2, H = grad.compute_output_and_grad_and_hessian(M(), inputs.clone().requires_grad_(True), xi, yi)
             out["hess"] = H.detach().numpy()
+        # what JacRegLatentLayer differentiates (nif/model.py:353-375 wires y_index = every latent unit, x_index = every
+        # ParameterNet input on the model augmented with the latent code): d latent / d input_p, [B, K, pi]
+        class M2:
+            def __call__(self, x):
+                return net.call(x), net._call_parameter_net(x[:, :pi], net.pnet_list)[1]
+
+        _, dl = grad.compute_output_and_augment_grad(M2(), inputs.clone().requires_grad_(True), list(range(pi)),
+                                                     list(range(cfg_p["latent_dim"])))
+        out["latent_jac"] = dl.detach().numpy()
         path = os.path.join(HERE, case + ".npz")
         np.savez_compressed(path, **out)
         print(case, "po_dim", net.po_dim, "loss", float(loss), os.path.getsize(path), "bytes")

@@ -58,6 +58,24 @@ def test_jacobian_hessian_match_reference_source(case):
     assert rel_err(H, d["hess"]) < 1e-10
 
 
+@pytest.mark.parametrize("case", golden_cases())
+def test_jac_reg_loss_matches_reference_source(case):
+    """JacRegLatentLayer's add_loss term: the golden `latent_jac` is what the reference's
+    compute_output_and_augment_grad returns for the model augmented with the latent code (gradient.py:183-204 as wired
+    by model.py:353-375); the layer then adds l1 * reduce_mean(square(.)) (gradient.py:101-104).  The oracle, and the
+    product's forward-mode formulation of the same term (trunk only, runs on CPU), are pinned against it."""
+    import nif_b200
+    d, cls, cfg_s, cfg_p, spec, prm, _ = load_golden(case)
+    l1 = 0.37
+    want = l1 * float(np.mean(np.square(d["latent_jac"])))
+    got = float(O.jac_reg_loss(spec, prm, torch.as_tensor(d["inputs"]), l1))
+    assert abs(got - want) <= 1e-12 * max(1.0, abs(want))
+    net = getattr(nif_b200, cls)(cfg_s, dict(cfg_p, jac_reg=l1), seed=0, device="cpu")
+    net.set_weights({k: v.float().numpy() for k, v in prm.items()})
+    prod = float(net._jac_reg_loss(torch.as_tensor(d["inputs"][:, : spec.pi]).float()))
+    assert abs(prod - want) <= 2e-5 * abs(want) + 1e-12
+
+
 def test_notebook_known_answers():
     # tutorial/1_simple_1d_wave.ipynb cells 27/31/33: po_dim 1951; p->lr 1951 params; lr->w 3902 params
     cfg_s = {"connectivity": "full", "input_dim": 1, "output_dim": 1, "units": 30, "nlayers": 2, "activation": "swish"}
