@@ -626,3 +626,51 @@ def test_training_with_jac_reg_matches_oracle_trainer():
     diffs = np.concatenate([np.abs(got[k] - v.detach().numpy()).ravel() for k, v in ref.prm.items()])
     assert float(np.quantile(diffs, 0.999)) < 1e-4, float(np.quantile(diffs, 0.999))
     assert float(diffs.max()) < 4 * 2e-3
+
+
+def test_fit_matches_oracle_trainer_on_tutorial1_data():
+    """Model.fit (tutorial/1_simple_1d_wave.ipynb: NIF swish 2x30, batch 512 over the 2000-point travelling wave, so
+    a short last batch; LearningRateScheduler; shuffled tf.data-style Dataset) against the oracle trainer fed the same
+    batch sequence: per-epoch loss (Keras' sample-weighted running mean) and final parameters."""
+    import nif_b200
+    cfg_s = {"connectivity": "full", "input_dim": 1, "output_dim": 1, "units": 30, "nlayers": 2, "activation": "swish"}
+    cfg_p = {"input_dim": 1, "latent_dim": 1, "units": 30, "nlayers": 2, "activation": "swish"}
+    spec = O.spec_from_cfg("NIF", cfg_s, cfg_p)
+    prm = O.init_params(spec, 2)
+    raw = O.traveling_wave_raw(4.0)
+    data, _, _ = O.standard_normalize(raw)
+    data = data.astype(np.float32)
+    X, Y = data[:, :2], data[:, 2:3]
+    net = nif_b200.NIF(cfg_s, cfg_p, seed=0, device="cuda:0")
+    net.set_weights({k: v.numpy() for k, v in prm.items()})
+    model = net.build()
+    model.compile(nif_b200.Adam(1e-3), loss="mse")
+    sched = lambda epoch, lr: 1e-3 if epoch < 2 else 5e-4
+    ds = nif_b200.Dataset.from_tensor_slices((X, Y)).shuffle(2000, seed=5).batch(512).prefetch(1)
+    hist = model.fit(ds, epochs=3, callbacks=[nif_b200.LearningRateScheduler(sched)], verbose=0)
+    # the same batches through the oracle
+    ref = O.MaterialisedTrainer(spec, {k: v.double() for k, v in prm.items()}, lr=1e-3)
+    ds2 = nif_b200.Dataset.from_tensor_slices((X, Y)).shuffle(2000, seed=5).batch(512)
+    ref_hist = []
+    for epoch in range(3):
+        ref.lr = sched(epoch, ref.lr)
+        tot, rows = 0.0, 0
+        sizes = []
+        for gb, parts in ds2.batches(epoch):
+            l = ref.step(parts[0].double(), parts[1].double())
+            tot += l * gb
+            rows += gb
+            sizes.append(gb)
+        assert sizes == [512, 512, 512, 464]
+        ref_hist.append(tot / rows)
+    assert len(hist.history["loss"]) == 3 and hist.history["lr"] == [1e-3, 1e-3, 5e-4]
+    for a, b in zip(hist.history["loss"], ref_hist):
+        assert abs(a - b) <= 2e-4 * max(1.0, abs(b)), (hist.history["loss"], ref_hist)
+    got = net.get_weights()
+    diffs = np.concatenate([np.abs(got[k] - v.detach().numpy()).ravel() for k, v in ref.prm.items()])
+    # (Adam moves every weight by ~lr per step whatever the gradient scale; a weight whose gradient sits at the rounding
+    # level may step the other way, so compare a high quantile tightly and the maximum loosely)
+    assert float(np.quantile(diffs, 0.995)) < 3e-4, float(np.quantile(diffs, 0.995))
+    assert float(diffs.max()) < 12 * 2e-3
+    assert model.optimizer.iterations == 12
+    assert ds.arrays[0].is_cuda  # fit() keeps a data set of this size resident in HBM

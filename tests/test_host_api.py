@@ -153,6 +153,20 @@ def test_dataset_semantics():
         assert sorted(np.concatenate([a[0].numpy().ravel(), b[0].numpy().ravel()]).tolist()) == sorted(full.tolist())
 
 
+def test_dataset_cache_on_device_yields_the_same_batches():
+    """Dataset.cache_on(device) (what fit() does for data sets that fit in HBM): same batches in the same order; exercised
+    here with the CPU as the 'device' -- the code path is device-agnostic."""
+    import torch
+    x = np.arange(40, dtype=np.float32).reshape(20, 2)
+    y = x.sum(1, keepdims=True)
+    a = nif_b200.Dataset.from_tensor_slices((x, y)).shuffle(20, seed=3).batch(6)
+    b = nif_b200.Dataset.from_tensor_slices((x, y)).shuffle(20, seed=3).batch(6).cache_on(torch.device("cpu"))
+    assert b.nbytes() == x.nbytes + y.nbytes
+    for epoch in range(2):
+        for (ga, ra), (gb, rb) in zip(a.batches(epoch), b.batches(epoch)):
+            assert ga == gb and all(torch.equal(p, q) for p, q in zip(ra, rb))
+
+
 def test_lr_scheduler_and_adam_object():
     opt = nif_b200.Adam(1e-3)
     assert (opt.beta_1, opt.beta_2, opt.epsilon) == (0.9, 0.999, 1e-7)  # tf.keras defaults
