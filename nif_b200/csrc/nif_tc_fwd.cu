@@ -44,73 +44,6 @@ __host__ __device__ inline size_t tcf_smem_bytes(int KP, int KZ, int si) {
          2 * (size_t)KP * 128 * 4 + 2 * (size_t)si * 128 * 4 + 256;
 }
 
-// MMA issuer of tile T (warp 8: tile 0, warp 10: tile 1).  One issuer per tile: while one is between chunks (barrier
-// waits, commits) the other keeps the tensor pipe fed; both read the same staged weight chunk and each commits to its
-// b_empty (count 2).  The whole warp runs the loop and one elected lane issues; T is a template constant and every
-// counter a 32-bit value derived from kernel parameters, so descriptors, barrier addresses and phases live in uniform
-// registers and the per-chunk instruction stream is a few dozen instructions.  It has to be: this warp shares its
-// scheduler with two epilogue warps whose dense FMA streams keep the issue slot (see nif_tc_bwd.cu).
-template <int T>
-__device__ __forceinline__ void tcf_issue(const Plan& pl, unsigned char* smem, uint64_t* bars, uint32_t tmem,
-                                          long long my_pairs) {
-  unsigned char* A_all = smem;
-  unsigned char* Z_all = smem + 4 * TC_TILE_BYTES;
-  const uint32_t KZ = (uint32_t)pl.KZ;
-  const uint32_t zbytes = 128u * KZ * 2u;
-  const uint32_t sbo_z = (KZ / 8u) * 128u;
-  unsigned char* Bst = Z_all + 4 * zbytes;
-  uint64_t* b_full = bars;
-  uint64_t* b_empty = bars + TCF_STAGES;
-  uint64_t* t_full = bars + 2 * TCF_STAGES;
-  uint64_t* t_empty = t_full + 4;
-  uint64_t* a_ready = t_empty + 4;
-  const uint32_t H = (uint32_t)pl.H, NCH = (uint32_t)pl.NCH, si = (uint32_t)pl.si, NLC = (uint32_t)pl.NLC;
-  const uint32_t small_half = 64u * KZ * 2u;                         // one of hi / lo of an X0 / XC chunk
-  const uint32_t last_half = (uint32_t)(pl.LPC * pl.KZ) * 64u * 2u;  // one of hi / lo of an XL chunk
-  const uint32_t n_last = (uint32_t)(pl.LPC * pl.KZ);
-  const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0) + (uint32_t)T * 256u;
-  const uint64_t da_hi = tc_make_desc(smem_u32(A_all + T * 2 * TC_TILE_BYTES), TC_SBO);
-  const uint64_t da_lo = tc_make_desc(smem_u32(A_all + T * 2 * TC_TILE_BYTES + TC_TILE_BYTES), TC_SBO);
-  const uint64_t dz_hi = tc_make_desc(smem_u32(Z_all + T * 2 * zbytes), sbo_z);
-  const uint64_t dz_lo = tc_make_desc(smem_u32(Z_all + T * 2 * zbytes + zbytes), sbo_z);
-  const int lane = threadIdx.x & 31;
-  (void)lane;
-#ifdef NIF_TRACE
-  int trace_n = 0;
-#endif
-  uint32_t g = 0;   // chunk counter (stage / accumulator phases)
-  uint32_t ar = 0;  // a_ready phases consumed
-  // one chunk: A operand kind (0 = zt tile, 1 = h tile), K extent, B geometry, N
-  auto chunk = [&](int a_kind, bool wait_a, uint32_t ksteps, uint32_t b_half_bytes, uint32_t b_sbo, uint32_t N) {
-    const uint32_t s = g % TCF_STAGES;
-    const uint32_t as = g & 1u;  // accumulator stage
-    if (wait_a) { mbar_wait(&a_ready[T], ar & 1u); ++ar; }
-    mbar_wait(&t_empty[2 * T + as], ((g >> 1) & 1u) ^ 1u);
-    mbar_wait(&b_full[s], (g / TCF_STAGES) & 1u);
-    if (T == 0 && lane == 0) TRACE(2, g * 8 + 1 + T);
-    tc_fence_after();
-    const uint64_t db_hi = tc_make_desc(smem_u32(Bst + s * TCF_STAGE_BYTES), b_sbo);
-    const uint64_t db_lo = tc_make_desc(smem_u32(Bst + s * TCF_STAGE_BYTES + b_half_bytes), b_sbo);
-    if (tc_elect_one()) {
-      tc_mma_split(tmem_u + as * 128u, a_kind ? da_hi : dz_hi, a_kind ? da_lo : dz_lo, db_hi, db_lo, tc_idesc_f16((int)N),
-                   (int)ksteps);
-      tc_commit(&t_full[2 * T + as]);
-      tc_commit(&b_empty[s]);
-    }
-    __syncwarp();
-    if (T == 0 && lane == 0) TRACE(2, g * 8 + 3 + T);
-    ++g;
-  };
-  for (long long p = 0; p < my_pairs; ++p) {
-    for (uint32_t i = 0; i <= si; ++i) chunk(0, i == 0, KZ / 16u, small_half, sbo_z, 64u);
-    for (uint32_t h = 0; h < H; ++h) {
-      chunk(0, false, KZ / 16u, small_half, sbo_z, 64u);
-      for (uint32_t c = 0; c < NCH; ++c) chunk(1, c == 0, 4u, TC_TILE_BYTES, TC_SBO, 128u);
-    }
-    for (uint32_t q = 0; q < NLC; ++q) chunk(1, q == 0, 4u, last_half, TC_SBO, n_last);
-  }
-}
-
 // SINE: the activation is sine (SIREN variants), inlined; otherwise the out-of-line activation switch is called
 template <bool SAVE, bool SINE>
 __global__ void __launch_bounds__(TCF_THREADS, 1) nif_tc_fwd_kernel(const Plan pl, const TcFwdArgs a) {
@@ -186,10 +119,49 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) nif_tc_fwd_kernel(const Plan p
           put(tcx + (long long)(si + 1 + H) * plan_x0_floats(pl) + (long long)q * plan_xl_floats(pl), last_bytes);
       }
     }
-  } else if (warp == 8) {
-    tcf_issue<0>(pl, smem, bars, tmem, my_pairs);
-  } else if (warp == 10) {
-    tcf_issue<1>(pl, smem, bars, tmem, my_pairs);
+  } else if (warp == 8 || warp == 10) {
+    // ---------------- MMA issuers: warp 8 feeds tile 0, warp 10 feeds tile 1 ----------------
+    // (one issuer per tile: while one is between chunks -- barrier waits, descriptors, commits -- the other keeps
+    // the tensor pipe fed; both read the same staged weight chunk and each commits to its b_empty, count 2)
+    {  // the whole warp runs the loop (uniform control flow and operands); one elected lane issues -- see tc_elect_one
+      const int t = __shfl_sync(0xffffffffu, warp == 8 ? 0 : 1, 0);
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+      const uint64_t da_hi = tc_make_desc(smem_u32(A_all + t * 2 * TC_TILE_BYTES), TC_SBO);
+      const uint64_t da_lo = tc_make_desc(smem_u32(A_all + t * 2 * TC_TILE_BYTES + TC_TILE_BYTES), TC_SBO);
+      const uint64_t dz_hi = tc_make_desc(smem_u32(Z_all + t * 2 * zbytes), sbo_z);
+      const uint64_t dz_lo = tc_make_desc(smem_u32(Z_all + t * 2 * zbytes + zbytes), sbo_z);
+      long long g = 0;   // chunk counter (stage / accumulator phases)
+      long long ar = 0;  // a_ready phases consumed
+      // one chunk: A operand kind (0 = zt tile, 1 = h tile), K extent, B geometry, N
+      auto chunk = [&](int a_kind, bool wait_a, int ksteps, uint32_t b_half_bytes, uint32_t b_sbo, int N) {
+        const int s = (int)(g % TCF_STAGES);
+        const int as = (int)(g & 1);  // accumulator stage
+        if (wait_a) { mbar_wait(&a_ready[t], (uint32_t)(ar & 1)); ++ar; }
+        mbar_wait(&t_empty[2 * t + as], (uint32_t)(((g >> 1) & 1) ^ 1));
+        mbar_wait(&b_full[s], (uint32_t)((g / TCF_STAGES) & 1));
+        if (t == 0 && lane == 0) TRACE(2, g * 8 + 1 + t);
+        tc_fence_after();
+        const uint64_t db_hi = tc_make_desc(smem_u32(Bst + s * TCF_STAGE_BYTES), b_sbo);
+        const uint64_t db_lo = tc_make_desc(smem_u32(Bst + s * TCF_STAGE_BYTES + b_half_bytes), b_sbo);
+        const uint32_t d = tmem_u + (uint32_t)t * 256u + (uint32_t)as * 128u;
+        if (tc_elect_one()) {
+          tc_mma_split(d, a_kind ? da_hi : dz_hi, a_kind ? da_lo : dz_lo, db_hi, db_lo, tc_idesc_f16(N), ksteps);
+          tc_commit(&t_full[2 * t + as]);
+          tc_commit(&b_empty[s]);
+        }
+        __syncwarp();
+        if (t == 0 && lane == 0) TRACE(2, g * 8 + 3 + t);
+        ++g;
+      };
+      for (long long p = 0; p < my_pairs; ++p) {
+        for (int i = 0; i <= si; ++i) chunk(0, i == 0, KZ / 16, small_bytes / 2, sbo_z, 64);
+        for (int h = 0; h < H; ++h) {
+          chunk(0, false, KZ / 16, small_bytes / 2, sbo_z, 64);
+          for (int c = 0; c < NCH; ++c) chunk(1, c == 0, 4, TC_TILE_BYTES, TC_SBO, 128);
+        }
+        for (int q = 0; q < NLC; ++q) chunk(1, q == 0, 4, last_bytes / 2, TC_SBO, LPC * KZ);
+      }
+    }
   }
   } else {
     tc_reg_inc<224>();
