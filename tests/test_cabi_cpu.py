@@ -67,3 +67,31 @@ def test_null_arguments_fail_before_touching_the_device():
     assert L.nif_adam_step(16, None, None, None, None, 1e-3, 0.9, 0.999, 1e-7, 1, 0.0, 0.0, 1.0, None) == -2
     assert L.nif_adam_step(16, None, None, None, None, 1e-3, 0.9, 0.999, 1e-7, 0, 0.0, 0.0, 1.0, None) == -2  # t >= 1
     assert L.nif_forward(C.byref(d), 1, 0, None, None, 0, None, None, None, None) == 0  # empty batch is a no-op
+
+
+def test_null_arguments_of_the_later_entry_points():
+    """nif_forward_tangent2 (HessianLayer), nif_adam_step_dev (graph-replayed steps), the Sobolev pair and the trunk:
+    same conventions -- -2 with a message before anything is enqueued, 0 for an empty batch."""
+    from nif_b200 import _lib
+    L = _lib.lib()
+    d = _lib.Desc(1, 1, 2, 1, 64, 4, 32, 30.0, 0, 0)
+    assert L.nif_forward_tangent2(C.byref(d), 8, None, None, None, None, None, None, None, None, None, None) == -2
+    assert b"nif_forward_tangent2" in L.nif_last_error()
+    assert L.nif_forward_tangent2(C.byref(d), 0, None, None, None, None, None, None, None, None, None, None) == 0
+    assert L.nif_forward_tangent2(C.byref(d), -1, None, None, None, None, None, None, None, None, None, None) == -2
+    assert L.nif_adam_step_dev(16, None, None, None, None, None, 0.9, 0.999, 1e-7, 0.0, 0.0, 1.0, None) == -2
+    assert L.nif_adam_step_dev(0, None, None, None, None, None, 0.9, 0.999, 1e-7, 0.0, 0.0, 1.0, None) == 0
+    assert L.nif_forward_tangent(C.byref(d), 8, None, None, None, 5, None, None, None, None, None) == -2  # n_dir > 4
+    assert L.nif_sobolev_backward(C.byref(d), 8, None, None, None, None, None, None, None, None, None, 0.0, None, None,
+                                  None) == -2
+    t = _lib.TrunkDesc(1, 32, 64, 4, 2)
+    assert L.nif_trunk_forward(C.byref(t), 8, None, None, None, None, None, None) == -2
+    bad = _lib.TrunkDesc(1, 32, 65, 4, 2)  # wider than the fused trunk kernels
+    n = C.c_int64(0)
+    assert L.nif_trunk_query(C.byref(bad), 8, C.byref(n), None, None, None) == -3
+    # a misaligned pointer is refused too
+    buf = (C.c_float * 64)()
+    addr = C.addressof(buf)
+    mis = C.c_void_p(addr + 4 if addr % 16 == 0 else addr + (16 - addr % 16) + 4)
+    assert L.nif_adam_step(8, mis, mis, mis, mis, 1e-3, 0.9, 0.999, 1e-7, 1, 0.0, 0.0, 1.0, None) == -2
+    assert b"aligned" in L.nif_last_error()
