@@ -6,7 +6,7 @@ number on the hot path is produced by libnif_b200.so.
 from __future__ import annotations
 
 import ctypes as C
-from typing import Optional, Tuple
+from typing import Optional
 
 import torch
 

@@ -8,7 +8,6 @@ random-initialised weights of the named architecture.  bench.py stays the headli
 """
 import json
 import sys
-import time
 
 import numpy as np
 import torch

@@ -1,5 +1,5 @@
 """torchrun --nproc-per-node 2 tools/dp_check.py : data-parallel step == single-process step on the same global batch."""
-import os, sys, torch
+import sys, torch
 sys.path.insert(0, '.')
 import nif_b200
 from nif_b200.distributed import DataParallel
