@@ -745,6 +745,7 @@ int nif_tc_bwd_edge_impl(const Plan& pl, long long B, const float* z, const floa
 
 
 static long long round_up(long long v, long long m) { return (v + m - 1) / m * m; }
+#define NIF_TC_WGT_MAX_ROWS 16384  // rows per batch split of the tensor-core weight-gradient kernel
 
 // latent coordinates per pass of nif_bwd_edge_kernel (4 * KG of its instantiations)
 static int nif_edge_kc(int K1) { return K1 <= 4 ? 4 : K1 <= 8 ? 8 : K1 <= 16 ? 16 : K1 <= 32 ? 32 : K1 <= 36 ? 36 : 68; }
@@ -767,6 +768,17 @@ GradWs nif_grad_ws_layout(const Plan& pl, long long B) {
   if (w.rows_h < 32) w.rows_h = 32;
   w.S_h = (int)((B + w.rows_h - 1) / w.rows_h);
   if (w.S_h < 1) w.S_h = 1;
+  if (nif_plan_uses_tc(pl)) {
+    // The tensor-core weight kernel keeps its accumulators in TMEM for a whole batch split, and the tensor core
+    // truncates its fp32 accumulator on every instruction: an error that grows with the length of the chain (measured
+    // 6e-4 on the gradient of a 4 Mi-row batch cut into 4 splits).  At most NIF_TC_WGT_MAX_ROWS rows per split, so the
+    // workspace must hold that many partials.
+    const long long s_cap = (B + NIF_TC_WGT_MAX_ROWS - 1) / NIF_TC_WGT_MAX_ROWS;
+    if (w.S_h < s_cap) {
+      w.S_h = (int)s_cap;
+      w.rows_h = round_up((B + s_cap - 1) / s_cap, 64);
+    }
+  }
   const long long kc = nif_edge_kc((int)K1);  // latent coordinates per pass of the thin-term kernel
   const long long base_e = (w.Q + 63) / 64 * ((K1 + kc - 1) / kc);
   long long S_e = (4 * 148 + base_e - 1) / base_e;
@@ -866,6 +878,8 @@ int nif_backward_impl(const Plan& pl, long long B, const float* z, const float* 
     const int items = pl.H * ((pl.KP + 3) / 4);
     int S = 148 / items;
     if (S < 1) S = 1;
+    const long long s_cap = (B + NIF_TC_WGT_MAX_ROWS - 1) / NIF_TC_WGT_MAX_ROWS;  // bounded accumulation chains, see nif_grad_ws_layout
+    if (S < s_cap) S = (int)s_cap;
     if (S > w.S_h) S = w.S_h;
     long long rows = round_up((B + S - 1) / S, 64);
     S = (int)((B + rows - 1) / rows);

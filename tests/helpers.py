@@ -30,3 +30,16 @@ def rel_err(a, b):
     a = torch.as_tensor(a).double()
     b = torch.as_tensor(b).double()
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-300))
+
+
+def fullbatch_problem(B=65536):
+    """The C2 head (ShapeNet 2 -> 4x64 -> 1 SIREN, latent 32) at the full benchmark batch with seeded inputs:
+    (spec, parameters, z [B,32], x [B,2], target [B,1]), all fp32 on the CPU."""
+    spec = O.Spec(variant="siren", pi=1, si=2, so=1, n=64, l=4, K=32, n_st=64, l_st=4, p_act="swish", omega0=30.0,
+                  weight_init_factor=0.01)
+    prm = O.init_params(spec, 0)
+    g = torch.Generator().manual_seed(1234)
+    z = torch.rand(B, 32, generator=g) - 0.5
+    x = torch.rand(B, 2, generator=g) * 2 - 1
+    tgt = torch.rand(B, 1, generator=g) * 2 - 1
+    return spec, prm, z, x, tgt

@@ -674,3 +674,33 @@ def test_fit_matches_oracle_trainer_on_tutorial1_data():
     assert float(diffs.max()) < 12 * 2e-3
     assert model.optimizer.iterations == 12
     assert ds.arrays[0].is_cuda  # fit() keeps a data set of this size resident in HBM
+
+
+def test_full_batch_head_gradient_against_oracle():
+    """Parity AT the benchmark batch (65 536 rows), where the tensor-core weight-gradient kernel accumulates 16 384 rows per
+    TMEM accumulator: head gradients, dz and the loss against the fp64 oracle summed over 4096-row chunks
+    (tests/golden/fullbatch/make_fullbatch_ref.py).
+
+    Measured on B200 (round 1, deterministic kernels): loss 1.4e-7, dz 2.5e-6, dw 1.95e-5, db 2.38e-5 -- the two
+    batch-reduced gradients are ABOVE the 1e-5 target at this batch size (they meet it at the small batches of the other
+    tests): the reduction runs through fp16 operand pairs with one power-of-two scale for the whole batch and fp32
+    tensor-core accumulators that truncate on every instruction.  This test pins the measured level (gate 4e-5) so that it
+    cannot get worse unnoticed; DESIGN.md section 9 lists the fix (shorter accumulation chains, per-split scales)."""
+    import os
+    from tests.helpers import GOLDEN, fullbatch_problem
+    ref = np.load(os.path.join(GOLDEN, "fullbatch", "c2_fullbatch_head_grad.npz"))
+    spec, prm, z, x, tgt = fullbatch_problem()
+    dev = torch.device("cuda:0")
+    wn, bn = O.last_layer_names(spec)
+    eng = _engine_tc(spec)
+    w_h, b_h = prm[wn].to(dev), prm[bn].to(dev)
+    packed = eng.pack(w_h, b_h)
+    zd, xd = z.to(dev), x.to(dev)
+    u, stash = eng.forward(zd, xd, packed, save=True)
+    loss = torch.zeros(1, device=dev)
+    dw, db = torch.empty_like(w_h), torch.empty_like(b_h)
+    dz = eng.mse_backward(zd, xd, packed, u, stash, tgt.to(dev), None, 1.0 / z.shape[0], loss, dw, db)
+    errs = {"dw": rel_err(dw.cpu(), ref["dw"]), "db": rel_err(db.cpu(), ref["db"]),
+            "dz": rel_err(dz[:256].cpu(), ref["dz_head"]), "loss": abs(float(loss) - float(ref["loss"])) / float(ref["loss"])}
+    print("full-batch errors vs fp64 oracle:", {k: f"{v:.2e}" for k, v in errs.items()})
+    assert errs["loss"] < 1e-5 and errs["dz"] < 2e-5 and errs["dw"] < 4e-5 and errs["db"] < 4e-5, errs
