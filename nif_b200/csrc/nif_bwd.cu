@@ -745,7 +745,19 @@ int nif_tc_bwd_edge_impl(const Plan& pl, long long B, const float* z, const floa
 
 
 static long long round_up(long long v, long long m) { return (v + m - 1) / m * m; }
-#define NIF_TC_WGT_MAX_ROWS 16384  // rows per batch split of the tensor-core weight-gradient kernel
+// rows per batch split of the tensor-core weight-gradient kernel (bounds the truncating accumulation chains, see
+// nif_grad_ws_layout); NIF_B200_TC_WGT_MAX_ROWS overrides the default for measurements
+#include <cstdlib>
+static long long nif_tc_wgt_max_rows() {
+  static const long long v = [] {
+    const char* e = std::getenv("NIF_B200_TC_WGT_MAX_ROWS");
+    long long r = e ? std::atoll(e) : 4096;
+    if (r < 256) r = 256;
+    return round_up(r, 64);
+  }();
+  return v;
+}
+#define NIF_TC_WGT_MAX_ROWS nif_tc_wgt_max_rows()
 
 // latent coordinates per pass of nif_bwd_edge_kernel (4 * KG of its instantiations)
 static int nif_edge_kc(int K1) { return K1 <= 4 ? 4 : K1 <= 8 ? 8 : K1 <= 16 ? 16 : K1 <= 32 ? 32 : K1 <= 36 ? 36 : 68; }
@@ -770,9 +782,10 @@ GradWs nif_grad_ws_layout(const Plan& pl, long long B) {
   if (w.S_h < 1) w.S_h = 1;
   if (nif_plan_uses_tc(pl)) {
     // The tensor-core weight kernel keeps its accumulators in TMEM for a whole batch split, and the tensor core
-    // truncates its fp32 accumulator on every instruction: an error that grows with the length of the chain (measured
-    // 6e-4 on the gradient of a 4 Mi-row batch cut into 4 splits).  At most NIF_TC_WGT_MAX_ROWS rows per split, so the
-    // workspace must hold that many partials.
+    // truncates its fp32 accumulator on every instruction: an error that grows with the length of the chain.  Measured
+    // against the fp64 oracle at 65 536 rows: dw 1.95e-5 / db 2.38e-5 with 16 384 rows per split, 4.8e-6 / 5.9e-6 with
+    // 4096 (tools/emulate_batch_reduction.py reproduces both on the CPU).  At most NIF_TC_WGT_MAX_ROWS (4096) rows per
+    // split, so the workspace must hold that many partials; they are added in fp32 round-to-nearest by the unpack kernel.
     const long long s_cap = (B + NIF_TC_WGT_MAX_ROWS - 1) / NIF_TC_WGT_MAX_ROWS;
     if (w.S_h < s_cap) {
       w.S_h = (int)s_cap;

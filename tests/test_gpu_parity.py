@@ -677,15 +677,13 @@ def test_fit_matches_oracle_trainer_on_tutorial1_data():
 
 
 def test_full_batch_head_gradient_against_oracle():
-    """Parity AT the benchmark batch (65 536 rows), where the tensor-core weight-gradient kernel accumulates 16 384 rows per
-    TMEM accumulator: head gradients, dz and the loss against the fp64 oracle summed over 4096-row chunks
+    """Parity AT the benchmark batch (65 536 rows), where the tensor-core weight-gradient kernel runs its longest
+    accumulation chains: head gradients, dz and the loss against the fp64 oracle summed over 4096-row chunks
     (tests/golden/fullbatch/make_fullbatch_ref.py).
 
-    Measured on B200 (round 1, deterministic kernels): loss 1.4e-7, dz 2.5e-6, dw 1.95e-5, db 2.38e-5 -- the two
-    batch-reduced gradients are ABOVE the 1e-5 target at this batch size (they meet it at the small batches of the other
-    tests): the reduction runs through fp16 operand pairs with one power-of-two scale for the whole batch and fp32
-    tensor-core accumulators that truncate on every instruction.  This test pins the measured level (gate 4e-5) so that it
-    cannot get worse unnoticed; DESIGN.md section 9 lists the fix (shorter accumulation chains, per-split scales)."""
+    Measured on B200 (round 1, deterministic kernels): loss 1.4e-7, dz 2.5e-6, dw 4.8e-6, db 5.9e-6 with at most 4096 rows
+    per TMEM accumulation chain (the default).  With 16 384 rows per chain (one wave of CTAs, what the kernel did first)
+    dw / db were 1.95e-5 / 2.38e-5: the tensor core truncates its fp32 accumulator on every instruction."""
     import os
     from tests.helpers import GOLDEN, fullbatch_problem
     ref = np.load(os.path.join(GOLDEN, "fullbatch", "c2_fullbatch_head_grad.npz"))
@@ -703,4 +701,4 @@ def test_full_batch_head_gradient_against_oracle():
     errs = {"dw": rel_err(dw.cpu(), ref["dw"]), "db": rel_err(db.cpu(), ref["db"]),
             "dz": rel_err(dz[:256].cpu(), ref["dz_head"]), "loss": abs(float(loss) - float(ref["loss"])) / float(ref["loss"])}
     print("full-batch errors vs fp64 oracle:", {k: f"{v:.2e}" for k, v in errs.items()})
-    assert errs["loss"] < 1e-5 and errs["dz"] < 2e-5 and errs["dw"] < 4e-5 and errs["db"] < 4e-5, errs
+    assert errs["loss"] < 1e-5 and errs["dz"] < 1e-5 and errs["dw"] < 1e-5 and errs["db"] < 1e-5, errs

@@ -1,7 +1,7 @@
 """64-bit indexing at scale: one 4 Mi-row batch at the C2 shape (activation stash 2.7 G floats, past 2^31) against the same
 rows processed as two halves.  python tools/big_batch_check.py [log2_rows]
 Measured (round 1): forward and dz bit-identical; dw / db of whole vs halves 2.0e-5 / 2.7e-5 with at most 16 384 rows per
-TMEM accumulation chain (6.1e-4 / 8.0e-4 before that cap, with 1 Mi rows per chain)."""
+TMEM accumulation chain (6.1e-4 / 8.0e-4 with 1 Mi rows per chain; the default cap is now 4096 rows)."""
 import sys
 
 import torch
