@@ -95,3 +95,21 @@ def test_null_arguments_of_the_later_entry_points():
     mis = C.c_void_p(addr + 4 if addr % 16 == 0 else addr + (16 - addr % 16) + 4)
     assert L.nif_adam_step(8, mis, mis, mis, mis, 1e-3, 0.9, 0.999, 1e-7, 1, 0.0, 0.0, 1.0, None) == -2
     assert b"aligned" in L.nif_last_error()
+
+
+def test_gradient_workspace_holds_the_capped_batch_splits():
+    """The tensor-core weight-gradient kernel cuts the batch into splits of at most 4096 rows (bounded TMEM accumulation
+    chains); nif_query_sizes must size the workspace for that many partials [H][K+1][NP][NP] on top of the da slots."""
+    from nif_b200 import _lib
+    L = _lib.lib()
+    d = _lib.Desc(1, 1, 2, 1, 64, 4, 32, 30.0, 2, 0)  # the C2 head on the tensor-core path
+    prev = 0
+    for B in (512, 4096, 65536, 1 << 20):
+        s = _lib.Sizes()
+        assert L.nif_query_sizes(C.byref(d), B, C.byref(s)) == 0
+        H, K1, NP = 4, 33, 64
+        da = (H + 1) * ((B + 63) // 64 * 64) * NP
+        partials = max(1, -(-B // 4096)) * H * K1 * NP * NP
+        assert s.grad_ws_floats >= da + partials, (B, s.grad_ws_floats, da, partials)
+        assert s.grad_ws_floats > prev
+        prev = s.grad_ws_floats
