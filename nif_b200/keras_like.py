@@ -185,13 +185,13 @@ class Dataset:
         if self._shuffle:
             g = torch.Generator().manual_seed(self._seed * 1000003 + epoch)
             perm = torch.randperm(self.n, generator=g)
+            if self.arrays[0].device != perm.device:
+                perm = perm.to(self.arrays[0].device)  # device-resident arrays: one transfer per epoch, gathers on the device
         else:
             perm = None
         for s in range(0, self.n, bs):
             e = min(self.n, s + bs)
             idx = slice(s, e) if perm is None else perm[s:e]
-            if perm is not None and self.arrays[0].device != idx.device:
-                idx = idx.to(self.arrays[0].device)  # device-resident arrays: gather there (the permutation is drawn on the host either way)
             rows = [a[idx] for a in self.arrays]
             gb = e - s
             if self._world > 1:
