@@ -758,6 +758,17 @@ static long long nif_tc_wgt_max_rows() {
   return v;
 }
 #define NIF_TC_WGT_MAX_ROWS nif_tc_wgt_max_rows()
+// batch splits of the tensor-core weight-gradient kernel: one CTA per SM and every CTA costs the same, so whole waves of
+// CTAs -- a multiple of the splits that fill one wave -- and enough of them to respect the accumulation cap
+static int nif_tc_wgt_splits(const Plan& pl, long long B) {
+  const long long items = (long long)pl.H * ((pl.KP + 3) / 4);
+  long long per_wave = items > 0 ? 148 / items : 1;
+  if (per_wave < 1) per_wave = 1;
+  const long long s_cap = (B + NIF_TC_WGT_MAX_ROWS - 1) / NIF_TC_WGT_MAX_ROWS;
+  long long S = per_wave;
+  if (S < s_cap) S = round_up(s_cap, per_wave);
+  return (int)S;
+}
 
 // latent coordinates per pass of nif_bwd_edge_kernel (4 * KG of its instantiations)
 static int nif_edge_kc(int K1) { return K1 <= 4 ? 4 : K1 <= 8 ? 8 : K1 <= 16 ? 16 : K1 <= 32 ? 32 : K1 <= 36 ? 36 : 68; }
@@ -786,10 +797,10 @@ GradWs nif_grad_ws_layout(const Plan& pl, long long B) {
     // against the fp64 oracle at 65 536 rows: dw 1.95e-5 / db 2.38e-5 with 16 384 rows per split, 4.8e-6 / 5.9e-6 with
     // 4096 (tools/emulate_batch_reduction.py reproduces both on the CPU).  At most NIF_TC_WGT_MAX_ROWS (4096) rows per
     // split, so the workspace must hold that many partials; they are added in fp32 round-to-nearest by the unpack kernel.
-    const long long s_cap = (B + NIF_TC_WGT_MAX_ROWS - 1) / NIF_TC_WGT_MAX_ROWS;
-    if (w.S_h < s_cap) {
-      w.S_h = (int)s_cap;
-      w.rows_h = round_up((B + s_cap - 1) / s_cap, 64);
+    const long long s_need = nif_tc_wgt_splits(pl, B);
+    if (w.S_h < s_need && B > NIF_TC_WGT_MAX_ROWS) {
+      w.S_h = (int)s_need;
+      w.rows_h = round_up((B + s_need - 1) / s_need, 64);
     }
   }
   const long long kc = nif_edge_kc((int)K1);  // latent coordinates per pass of the thin-term kernel
@@ -888,11 +899,7 @@ int nif_backward_impl(const Plan& pl, long long B, const float* z, const float* 
   int S_used = w.S_h, S_e_used = w.S_e;
   if (tc_data && pl.H > 0) {  // tensor-core weight-gradient GEMM (needs the maxima recorded by the TC data pass)
     // one CTA per SM: as many batch splits as fit one wave (never more than the workspace was sized for)
-    const int items = pl.H * ((pl.KP + 3) / 4);
-    int S = 148 / items;
-    if (S < 1) S = 1;
-    const long long s_cap = (B + NIF_TC_WGT_MAX_ROWS - 1) / NIF_TC_WGT_MAX_ROWS;  // bounded accumulation chains, see nif_grad_ws_layout
-    if (S < s_cap) S = (int)s_cap;
+    int S = nif_tc_wgt_splits(pl, B);  // whole waves, bounded accumulation chains (see nif_grad_ws_layout)
     if (S > w.S_h) S = w.S_h;
     long long rows = round_up((B + S - 1) / S, 64);
     S = (int)((B + rows - 1) / rows);
