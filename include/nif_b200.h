@@ -47,7 +47,10 @@ typedef struct nif_desc {
   float omega0;
   int32_t dtype_compute; /* 0 = fp32 on CUDA cores; 2 = tcgen05 tensor cores with the 3-product fp16 split
                             (fp32-grade, same parity gates; 32 < n <= 64, falls through to 0 for shapes it lacks) */
-  int32_t reserved;
+  int32_t acc_rows;      /* tensor-core batch reductions (weight gradients): rows per accumulation chain.  The tensor
+                            core truncates its fp32 accumulator on every instruction, so the error of a batch-reduced
+                            gradient grows with the chain; 0 = default (4096 rows: dw within 1e-5 of fp64 at 65 536
+                            rows), larger = fewer partials, larger error (16 384: 2e-5).  Rounded up to 64, min 256. */
 } nif_desc_t;
 
 /* Sizes derived from a descriptor. */
@@ -61,6 +64,8 @@ typedef struct nif_sizes {
                                    (the tensor-core path tiles rows in groups) */
   int64_t grad_ws_floats;       /* floats of the partial-gradient workspace for batch size B (see nif_sizes B) */
   int64_t tile_rows;     /* rows per CTA tile */
+  int64_t kernel_path;   /* which kernels serve this descriptor: 0 = fp32 CUDA-core tile kernels, 2 = tcgen05 FP16x3
+                            (the value of dtype_compute that is actually honoured for this shape) */
 } nif_sizes_t;
 
 const char* nif_last_error(void);

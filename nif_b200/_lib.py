@@ -33,7 +33,7 @@ class Desc(C.Structure):
     _fields_ = [
         ("variant", C.c_int32), ("act", C.c_int32), ("si", C.c_int32), ("so", C.c_int32), ("n", C.c_int32),
         ("l", C.c_int32), ("K", C.c_int32), ("omega0", C.c_float), ("dtype_compute", C.c_int32),
-        ("reserved", C.c_int32),
+        ("acc_rows", C.c_int32),
     ]
 
 
@@ -45,7 +45,7 @@ class TrunkDesc(C.Structure):
 class Sizes(C.Structure):
     _fields_ = [
         ("po_dim", C.c_int64), ("n_layers", C.c_int64), ("np", C.c_int64), ("packed_floats", C.c_int64),
-        ("save_floats_per_row", C.c_int64), ("grad_ws_floats", C.c_int64), ("tile_rows", C.c_int64),
+        ("save_floats_per_row", C.c_int64), ("grad_ws_floats", C.c_int64), ("tile_rows", C.c_int64), ("kernel_path", C.c_int64),
     ]
 
 

@@ -50,6 +50,7 @@ extern "C" int nif_query_sizes(const nif_desc_t* d, int64_t B, nif_sizes_t* out)
   out->save_floats_per_row = 2LL * (pl.H + 1) * pl.NP;
   out->grad_ws_floats = nif_grad_ws_layout(pl, B).total;
   out->tile_rows = pl.NP == 128 ? 64 : 128;
+  out->kernel_path = nif_plan_uses_tc(pl) ? 2 : 0;
   return NIF_OK;
 }
 

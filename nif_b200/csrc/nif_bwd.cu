@@ -745,19 +745,14 @@ int nif_tc_bwd_edge_impl(const Plan& pl, long long B, const float* z, const floa
 
 
 static long long round_up(long long v, long long m) { return (v + m - 1) / m * m; }
-// rows per batch split of the tensor-core weight-gradient kernel (bounds the truncating accumulation chains, see
-// nif_grad_ws_layout); NIF_B200_TC_WGT_MAX_ROWS overrides the default for measurements
-#include <cstdlib>
-static long long nif_tc_wgt_max_rows() {
-  static const long long v = [] {
-    const char* e = std::getenv("NIF_B200_TC_WGT_MAX_ROWS");
-    long long r = e ? std::atoll(e) : 4096;
-    if (r < 256) r = 256;
-    return round_up(r, 64);
-  }();
-  return v;
+// rows per batch split of the tensor-core batch-reduction kernels (bounds the truncating accumulation chains, see
+// nif_grad_ws_layout): nif_desc_t.acc_rows, default 4096
+static long long nif_tc_wgt_max_rows(const Plan& pl) {
+  long long r = pl.acc_rows > 0 ? pl.acc_rows : 4096;
+  if (r < 256) r = 256;
+  return round_up(r, 64);
 }
-#define NIF_TC_WGT_MAX_ROWS nif_tc_wgt_max_rows()
+#define NIF_TC_WGT_MAX_ROWS nif_tc_wgt_max_rows(pl)
 // batch splits of the tensor-core weight-gradient kernel: one CTA per SM and every CTA costs the same, so whole waves of
 // CTAs -- a multiple of the splits that fill one wave -- and enough of them to respect the accumulation cap
 static int nif_tc_wgt_splits(const Plan& pl, long long B) {
@@ -767,6 +762,21 @@ static int nif_tc_wgt_splits(const Plan& pl, long long B) {
   const long long s_cap = (B + NIF_TC_WGT_MAX_ROWS - 1) / NIF_TC_WGT_MAX_ROWS;
   long long S = per_wave;
   if (S < s_cap) S = round_up(s_cap, per_wave);
+  return (int)S;
+}
+
+// batch splits of the tensor-core thin-term kernel: whole waves of CTAs (column-block pairs x splits), and enough of
+// them that no TMEM accumulation chain exceeds the cap (the same truncation mechanism as in the weight kernel)
+static int nif_tc_edge_splits(const Plan& pl, long long B) {
+  const int ncta_x = (pl.H + 1 + pl.si + pl.so + 1 + 1) / 2;
+  long long per_wave = 148 / ncta_x;
+  if (per_wave < 1) per_wave = 1;
+  const long long s_cap = (B + NIF_TC_WGT_MAX_ROWS - 1) / NIF_TC_WGT_MAX_ROWS;
+  long long S = per_wave;
+  if (S < s_cap) S = round_up(s_cap, per_wave);
+  const long long maxs = (B + 63) / 64;
+  if (S > maxs) S = maxs;
+  if (S < 1) S = 1;
   return (int)S;
 }
 
@@ -812,11 +822,16 @@ GradWs nif_grad_ws_layout(const Plan& pl, long long B) {
   if (w.rows_e < 64) w.rows_e = 64;
   w.S_e = (int)((B + w.rows_e - 1) / w.rows_e);
   if (w.S_e < 1) w.S_e = 1;
+  w.S_e_ws = w.S_e;  // partials the workspace holds (S_e stays the CUDA-core kernel's split count)
+  if (nif_plan_uses_tc(pl)) {  // room for the tensor-core thin-term kernel's splits (accumulation cap)
+    const int s_tc = nif_tc_edge_splits(pl, B);
+    if (s_tc > w.S_e_ws) w.S_e_ws = s_tc;
+  }
   long long off = 0;
   w.da = off; off += round_up((H + 1 + pl.wide_last) * nif_tiled_rows(B) * NP, 4);  // (tiled slots hold B rounded up to 64 rows)
   w.du = off; off += round_up(B * pl.so, 4);
   w.part_h = off; off += round_up((long long)w.S_h * Hm * K1 * NP * NP, 4);
-  w.part_e = off; off += round_up((long long)w.S_e * K1 * w.Q, 4);
+  w.part_e = off; off += round_up((long long)w.S_e_ws * K1 * w.Q, 4);
   w.loss_part = off; off += 1024;
   w.maxes = off; off += 256;  // device-side maxima used for tensor-core operand scales
   w.total = off;
@@ -916,10 +931,8 @@ int nif_backward_impl(const Plan& pl, long long B, const float* z, const float* 
     e.z = z; e.x = x; e.save = save; e.da = ws + w.da; e.du = du; e.part = ws + w.part_e; e.no_bias = 0; e.tiled = 1;
     e.q_begin = 0; e.q_end = w.Q;
     // thin terms on the tensor cores: one wave of CTAs (column-block pairs x batch splits)
-    const int ncta_x = (pl.H + 1 + pl.si + pl.so + 1 + 1) / 2;
-    int S_tc = 148 / ncta_x;
-    if (S_tc < 1) S_tc = 1;
-    if (S_tc > w.S_e) S_tc = w.S_e;
+    int S_tc = nif_tc_edge_splits(pl, B);
+    if (S_tc > w.S_e_ws) S_tc = w.S_e_ws;
     const long long rows_tc = round_up((B + S_tc - 1) / S_tc, 64);
     S_tc = (int)((B + rows_tc - 1) / rows_tc);
     const int rce = nif_tc_bwd_edge_impl(pl, B, z, x, save, ws + w.da, du, reinterpret_cast<const unsigned*>(ws + w.maxes),

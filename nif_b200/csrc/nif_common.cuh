@@ -53,6 +53,8 @@ struct Plan {
   // hidden-matrix batch-reduction GEMM as matrix index H (rows h_{H+1}, columns = the seed du padded to NP)
   // instead of the column-per-thread edge kernel.
   int wide_last;
+  // rows per accumulation chain of the tensor-core batch reductions (nif_desc_t.acc_rows; 0 = default 4096)
+  int acc_rows;
 };
 __host__ __device__ inline long long plan_x0_floats(const Plan& p) { return 64LL * p.KZ; }            // one X0 / XC chunk [hi|lo]
 __host__ __device__ inline long long plan_xl_floats(const Plan& p) { return (long long)p.LPC * p.KZ * 64; }       // one XL chunk [hi|lo]
@@ -253,7 +255,7 @@ bool nif_plan_uses_tc(const Plan& pl);
 // reverse-pass workspace layout (offsets in floats), shared by nif_bwd.cu / nif_api.cu / nif_trunk.cu
 struct GradWs {
   long long da, du, part_h, part_e, loss_part, maxes, total;
-  int S_h, S_e, Q;
+  int S_h, S_e, S_e_ws, Q;
   long long rows_h, rows_e;
 };
 

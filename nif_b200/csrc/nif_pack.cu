@@ -79,6 +79,8 @@ int nif_make_plan(const nif_desc_t* d, Plan* out) {
   p.P = p.H * p.n * p.n + (p.si + p.so + 1 + p.H) * p.n + p.so;
   p.wide_last = 0;
   p.tc = d->dtype_compute == 2 ? 1 : 0;
+  if (d->acc_rows < 0) { nif_set_error("acc_rows=%d is negative", d->acc_rows); return NIF_E_BAD_DESC; }
+  p.acc_rows = d->acc_rows;
   nif_plan_layout(&p);
   *out = p;
   return NIF_OK;

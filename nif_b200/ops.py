@@ -27,7 +27,10 @@ def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
         raise NifError(f"{name} must be a CUDA tensor (nif_b200 has no CPU path)")
     if t.dtype != torch.float32:
         t = t.float()
-    return t.contiguous()
+    t = t.contiguous()
+    if t.data_ptr() % 16 != 0:  # e.g. a row slice a[s:e] of a cached array: the C ABI wants 16-byte aligned pointers
+        t = t.clone()
+    return t
 
 
 class FusedShapeNet:
@@ -45,7 +48,7 @@ class FusedShapeNet:
     COMPUTE = {"fp32": 0, "fp16x3": 2}  # fp32 CUDA cores | tensor cores, 3-product fp16 split (fp32-grade)
 
     def __init__(self, variant: str, si: int, so: int, n: int, l: int, K: int,
-                 activation: Optional[str] = "swish", omega0: float = 1.0, compute: str = "fp32"):
+                 activation: Optional[str] = "swish", omega0: float = 1.0, compute: str = "fp32", acc_rows: int = 0):
         if variant not in VARIANT:
             raise ValueError(f"variant must be one of {list(VARIANT)}")
         if variant == "nif" and activation not in ACT:
@@ -56,16 +59,25 @@ class FusedShapeNet:
             raise ValueError(f"compute must be one of {list(self.COMPUTE)}")
         self.compute = compute
         self.desc = Desc(VARIANT[variant], ACT[activation] if variant == "nif" else ACT["sine"], si, so, n, l, K,
-                         float(omega0) if variant != "nif" else 1.0, self.COMPUTE[compute], 0)
+                         float(omega0) if variant != "nif" else 1.0, self.COMPUTE[compute], int(acc_rows))
+        self.acc_rows = int(acc_rows)
         s = Sizes()
         check(_lib.lib().nif_query_sizes(C.byref(self.desc), 0, C.byref(s)), "nif_query_sizes")
         self.po_dim, self.np, self.packed_floats = int(s.po_dim), int(s.np), int(s.packed_floats)
         self.save_floats_per_row, self.tile_rows = int(s.save_floats_per_row), int(s.tile_rows)
+        # which kernels the library will run for this descriptor (shapes a tensor-core path lacks fall through to
+        # the CUDA-core kernels): "fp32" | "fp16x3" | "bf16"
+        self.kernel_path = {v: k for k, v in self.COMPUTE.items()}[int(s.kernel_path)]
         self._ws = None
 
     def with_latent(self, K: int) -> "FusedShapeNet":
-        return FusedShapeNet(self.variant, self.si, self.so, self.n, self.l, K, self.activation, self.omega0,
-                             self.compute)
+        # the FP16x3 tensor-core kernels need a latent contraction (K >= 1) and a single group; a K == 0 engine
+        # (explicit per-group weight vectors) runs on the kernels that serve grouped launches
+        comp = self.compute
+        if K == 0 and comp == "fp16x3":
+            comp = "fp32"
+        return FusedShapeNet(self.variant, self.si, self.so, self.n, self.l, K, self.activation, self.omega0, comp,
+                             self.acc_rows)
 
     # ------------------------------------------------------------------------------------------
     def grad_ws_floats(self, B: int) -> int:
@@ -271,6 +283,9 @@ class _FusedFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, z, x, w_h, b_h, engine: FusedShapeNet):
         packed = engine.pack(w_h, b_h)
+        # the reverse pass hands these tensors' raw pointers to the library: normalise them once, here
+        x = _f32c(x, "x")
+        z = _f32c(z, "z") if engine.K > 0 else z
         need = any(ctx.needs_input_grad[:4])
         if need:
             u, stash = engine.forward(z, x, packed, save=True)

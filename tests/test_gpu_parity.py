@@ -360,7 +360,7 @@ def _engine_tc(spec):
         ("siren", 1, 1, 64, 4, 32, 128),     # C4 shape, exactly one tile
         ("siren", 2, 1, 64, 1, 3, 1000),     # even K+1, several tiles
         ("siren", 3, 2, 48, 2, 5, 77),       # padded width
-        ("siren_res", 2, 2, 64, 2, 6, 150),  # res-blocks
+        ("siren", 2, 2, 64, 2, 6, 150),      # two outputs share one last-layer chunk
         ("nif", 2, 2, 48, 3, 7, 90),         # swish + residual
         ("siren", 2, 1, 64, 2, 1, 20000),    # many tiles per CTA (persistent loop, barrier phases)
     ],
@@ -373,6 +373,7 @@ def test_tc_forward_and_stash(variant, si, so, n, l, K, B):
     prm32 = {k: v.float() for k, v in prm.items()}
     loss32, g32, gz32, y32 = O.loss_and_grads(spec, prm32, inputs.float(), target.float(), sw.float())
     eng = _engine_tc(spec)
+    assert eng.kernel_path == "fp16x3", "this descriptor must be served by the tcgen05 kernels, not a fall-through"
     z = O.latent(spec, prm, inputs[:, :1]).float().to(dev)
     x = inputs[:, 1:].float().contiguous().to(dev)
     w_h, b_h = prm[wn].float().to(dev), prm[bn].float().to(dev)

@@ -1,18 +1,15 @@
 #!/bin/bash
-# First GPU call of the next round: everything that was changed after the last benchmark of round 1 (the 4096-row
-# accumulation cap of the tensor-core weight-gradient kernel) re-measured, with the old cap beside it.
-#   gpurun --timeout 600 -- 'bash tools/remeasure.sh'
+# One GPU call that re-measures the HEAD build: GPU tests, bench line, eager launch list, one --set full step.
+#   gpurun --timeout 900 -- 'bash tools/remeasure.sh r02a'
+TAG=${1:-r02}
 set -x
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-python bench.py > gpurun_out/bench_cap4096.log 2>&1
-NIF_B200_TC_WGT_MAX_ROWS=16384 python bench.py > gpurun_out/bench_cap16384.log 2>&1
-python - <<'PY'
-import json
-for f in ("gpurun_out/bench_cap4096.log", "gpurun_out/bench_cap16384.log"):
-    d = json.loads(open(f).read().strip().splitlines()[-1])
-    print(f, d["ms_per_step"], d["e2e"]["ms_per_step"], d["roofline"]["ms_per_launch"], d["roofline"]["reverse_pass"]["ms"])
-PY
-NIF_B200_GRAPH=0 ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv \
-    --log-file gpurun_out/launches.csv python tools/step_prof.py 4 > gpurun_out/step_prof.log 2>&1
-python tools/big_batch_check.py 22 2>&1 | tail -2
+python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_pytest.log 2>&1; tail -3 gpurun_out/${TAG}_pytest.log
+python bench.py > gpurun_out/${TAG}_bench.log 2>&1; tail -1 gpurun_out/${TAG}_bench.log
+NIF_B200_GRAPH=0 ncu --metrics gpu__time_duration.sum --clock-control none -c 160 --csv \
+    --log-file gpurun_out/${TAG}_launches.csv python tools/step_prof.py 4 > gpurun_out/${TAG}_step_prof.log 2>&1
+NIF_B200_GRAPH=0 ncu --set full --clock-control none --import-source on -s 60 -c 40 -f -o gpurun_out/${TAG}_step_full \
+    python tools/step_prof.py 4 > gpurun_out/${TAG}_full.log 2>&1
+ncu -i gpurun_out/${TAG}_step_full.ncu-rep --page raw --csv > gpurun_out/${TAG}_raw.csv 2>/dev/null
+python tools/ncu_summary.py gpurun_out/${TAG}_raw.csv > gpurun_out/${TAG}_ncu_step.txt 2>&1; cat gpurun_out/${TAG}_ncu_step.txt
+nproc; nvidia-smi --query-gpu=name,clocks.max.sm --format=csv
