@@ -2,6 +2,7 @@
 // dispatch; nothing here allocates, synchronises or touches the host copy of any tensor.
 #include "nif_common.cuh"
 
+bool nif_plan_uses_bf(const Plan& pl);
 int nif_pack_impl(const Plan& pl, long long G, const float* w_h, const float* b_h, float* packed, cudaStream_t st);
 int nif_forward_impl(const Plan& pl, long long G, long long B, const float* z, const float* x, int x_shared,
                      const float* packed, float* u, float* save, cudaStream_t st);
@@ -50,7 +51,7 @@ extern "C" int nif_query_sizes(const nif_desc_t* d, int64_t B, nif_sizes_t* out)
   out->save_floats_per_row = 2LL * (pl.H + 1) * pl.NP;
   out->grad_ws_floats = nif_grad_ws_layout(pl, B).total;
   out->tile_rows = pl.NP == 128 ? 64 : 128;
-  out->kernel_path = nif_plan_uses_tc(pl) ? 2 : 0;
+  out->kernel_path = nif_plan_uses_tc(pl) ? 2 : (nif_plan_uses_bf(pl) ? 1 : 0);
   return NIF_OK;
 }
 

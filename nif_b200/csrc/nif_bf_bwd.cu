@@ -1,0 +1,562 @@
+// Reverse pass on the tensor cores with bf16 operands (dtype_compute = 1) -- the mirror image of nif_bf_fwd.cu.
+//
+// nif_bf_bwd_data_kernel, per 128-row tile, two threads per row (thread (r, half): row r, columns half*NP/2 ..):
+//   prologue   dh_{H+1}[i] = sum_c du[c] * (zt @ BLT[c])[i]                       LT(c):  A = zt tile,       N = NP
+//              dz[kappa]  += sum_c du[c] * ((h_{H+1} @ XL[c])[kappa] + CL[kappa][c])   LZ(c):  A = h_{H+1} tile,  N = KZ
+//   m = H..0   da_m = dh_{m+1} * d_m   -> global (tiled) and the A tile
+//              dz[kappa]  += (da_m @ BC[m])[kappa]                                 BC(m):  bias rows,         N = KZ
+//       m >= 1 T = da_m @ WB[m-1][chunk];  dh_m[i] += omega zt[kappa] T[kappa][i];  dz[kappa] += omega sum_i T[kappa][i] h_m[i]
+//       m == 0 dz[kappa]  += omega x[i] (da_0 @ B0[i])[kappa]                      B0(i):  first matrix,      N = KZ
+// so every dz term, thin or not, is a tensor-core chunk over operand tiles that are in shared memory anyway.
+// The halves of a row keep separate dz accumulators in shared memory ([2][K+1][128], thread-private entries: no atomics,
+// deterministic) and are added when the row is written.
+//
+// nif_bf_bwd_weight_kernel: the batch-reduction GEMM dM_m[kappa][i][j] = omega sum_b zt[b][kappa] h_m[b][i] da_m[b][j]
+// with both operands generated on the fly (MN-major bf16), accumulators resident in TMEM over the batch split.
+#include "nif_bf.cuh"
+
+struct BfBwdArgs {
+  long long B, total_tiles;
+  const float *z, *x, *packed, *save, *du;
+  float* da;  // [(H+1)] tiled slots
+  float* dz;  // [B][K]
+  int nst;
+};
+
+#define BFB_THREADS 384
+
+size_t nif_bfb_smem_fixed(const Plan& pl) {
+  return (size_t)128 * pl.NP * 2 + (size_t)128 * pl.KZ * 2 + (size_t)2 * (pl.K + 1) * 128 * 4 + 256;
+}
+
+template <int NP>
+__global__ void __launch_bounds__(BFB_THREADS, 1) nif_bf_bwd_data_kernel(const Plan pl, const BfBwdArgs a) {
+  constexpr int CH = NP / 2;
+  constexpr int CK = 128 / NP;
+  constexpr uint32_t SBO_A = (NP / 8) * 128u;
+  constexpr uint32_t MAIN_BYTES = 128u * NP * 2u;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char* A_tile = smem;
+  unsigned char* Z_tile = smem + 128 * NP * 2;
+  const uint32_t zbytes = 128u * (uint32_t)pl.KZ * 2u;
+  const uint32_t sbo_z = (uint32_t)(pl.KZ / 8) * 128u;
+  unsigned char* Bst = Z_tile + zbytes;
+  float* dzs_all = reinterpret_cast<float*>(Bst + a.nst * BF_STAGE_BYTES);  // [2][K+1][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(dzs_all + 2 * (pl.K + 1) * 128);
+  uint64_t* b_full = bars;
+  uint64_t* b_empty = bars + 8;
+  uint64_t* t_full = bars + 16;
+  uint64_t* t_empty = bars + 18;
+  uint64_t* a_ready = bars + 20;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int K = pl.K, K1 = pl.K + 1, H = pl.H, si = pl.si, so = pl.so, KZ = pl.KZ;
+  const int NCHW = bf_nchw(pl);
+  const uint32_t nst = (uint32_t)a.nst;
+  const uint32_t small_bytes = (uint32_t)NP * (uint32_t)KZ * 2u;
+
+  if (tid == 0) {
+    for (int i = 0; i < 8; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 256); }
+    mbar_init(&a_ready[0], 256);
+    mbar_fence_init();
+  }
+  if (warp == 8) tc_alloc(tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  long long my_tiles = 0;
+  if ((long long)blockIdx.x < a.total_tiles) my_tiles = (a.total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+
+  if (warp >= 8) {
+    tc_reg_dec<56>();
+    if (warp == 9) {
+      if (lane == 0) {  // weight-stream producer
+        uint32_t s = 0, ph = 0;
+        auto put = [&](const float* src, uint32_t bytes) {
+          mbar_wait(&b_empty[s], ph ^ 1u);
+          mbar_expect_tx(&b_full[s], bytes);
+          bulk_g2s(Bst + s * BF_STAGE_BYTES, src, bytes, &b_full[s]);
+          if (++s == nst) { s = 0; ph ^= 1u; }
+        };
+        const float* wb = a.packed + pl.off_WB;
+        const float* wx = a.packed + pl.off_WX;
+        auto small = [&](int T) { put(wx + (long long)T * bf_small_floats(pl), small_bytes); };
+        for (long long t = 0; t < my_tiles; ++t) {
+          for (int c = 0; c < so; ++c) small(bf_t_blt(pl, c));
+          for (int c = 0; c < so; ++c) small(bf_t_xl(pl, c));
+          for (int m = H; m >= 0; --m) {
+            small(bf_t_bc(pl, m));
+            if (m >= 1) {
+              for (int c = 0; c < NCHW; ++c) put(wb + ((long long)(m - 1) * NCHW + c) * bf_chunk_floats(pl), MAIN_BYTES);
+            } else {
+              for (int i = 0; i < si; ++i) small(bf_t_b0(pl, i));
+            }
+          }
+        }
+      }
+    } else if (warp == 8) {
+      // MMA issuer: warp-uniform loop, one elected lane issues
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+      const uint64_t da = bf_make_desc(smem_u32(A_tile), SBO_A);
+      const uint64_t dz = bf_make_desc(smem_u32(Z_tile), sbo_z);
+      uint32_t g = 0, s = 0, ph = 0, ar = 0;
+      auto chunk = [&](bool a_main, bool wait_a, int ksteps, uint32_t b_sbo, int N) {
+        const uint32_t as = g & 1u;
+        if (wait_a) { mbar_wait(&a_ready[0], ar & 1u); ++ar; }
+        mbar_wait(&t_empty[as], ((g >> 1) & 1u) ^ 1u);
+        mbar_wait(&b_full[s], ph);
+        tc_fence_after();
+        const uint64_t db = bf_make_desc(smem_u32(Bst + s * BF_STAGE_BYTES), b_sbo);
+        const uint64_t dA = a_main ? da : dz;
+        const uint32_t d = tmem_u + as * 128u;
+        const uint32_t idesc = bf_idesc(N);
+        if (tc_elect_one()) {
+          for (int ks = 0; ks < ksteps; ++ks)
+            tc_mma_f16(d, dA + (uint64_t)(ks * 16), db + (uint64_t)(ks * 16), idesc, ks > 0 ? 1u : 0u);
+          tc_commit(&t_full[as]);
+          tc_commit(&b_empty[s]);
+        }
+        __syncwarp();
+        ++g;
+        if (++s == nst) { s = 0; ph ^= 1u; }
+      };
+      for (long long t = 0; t < my_tiles; ++t) {
+        for (int c = 0; c < so; ++c) chunk(false, c == 0, KZ / 16, sbo_z, NP);   // LT(c): zt tile (+ h tile) published
+        for (int c = 0; c < so; ++c) chunk(true, false, NP / 16, SBO_A, KZ);    // LZ(c)
+        for (int m = H; m >= 0; --m) {
+          chunk(true, true, NP / 16, SBO_A, KZ);                                // BC(m): da_m published
+          if (m >= 1) {
+            for (int c = 0; c < NCHW; ++c) chunk(true, false, NP / 16, SBO_A, 128);
+          } else {
+            for (int i = 0; i < si; ++i) chunk(true, false, NP / 16, SBO_A, KZ);
+          }
+        }
+      }
+    }
+  } else {
+    tc_reg_inc<224>();
+    const int half = warp >> 2;
+    const int r = tid & 127;
+    const uint32_t tm = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    const uint32_t row_off = (uint32_t)(r >> 3) * SBO_A + (uint32_t)(r & 7) * 16u;
+    const uint32_t zrow_off = (uint32_t)(r >> 3) * sbo_z + (uint32_t)(r & 7) * 16u;
+    const long long slot_floats = bf_slot_floats(a.B, NP);
+    float* dzs = dzs_all + (long long)half * K1 * 128 + r;  // dzs[kk * 128]: this thread's private accumulators
+    const float* C_all = a.packed + pl.off_C;
+    const float* CL = C_all + (long long)(H + 1) * K1 * pl.NP;
+    const int kh = KZ / 2, k0 = half * kh;  // this thread's latent coordinates in the N = KZ chunks
+    uint32_t g = 0;
+    for (long long t = 0; t < my_tiles; ++t) {
+      const long long b = (blockIdx.x + t * gridDim.x) * 128 + r;
+      const bool live = b < a.B;
+      const float* zrow = a.z + (live ? b : 0) * K;
+      auto zt_at = [&](int kk) -> float { return kk < K ? (live ? __ldg(zrow + kk) : 0.f) : (kk == K ? 1.f : 0.f); };
+      const long long trow = bf_tiled_row(b, NP) + (long long)(half * (CH / 4)) * 128;  // this thread's quads of a slot
+
+      auto chunk_begin = [&]() -> uint32_t {
+        mbar_wait(&t_full[g & 1u], (g >> 1) & 1u);
+        tc_fence_after();
+        return tm + (g & 1u) * 128u;
+      };
+      auto chunk_end = [&]() {
+        tc_fence_before();
+        mbar_arrive(&t_empty[g & 1u]);
+        ++g;
+      };
+      // an N = KZ chunk: dzs[kappa] += coef * (D[kappa] + add[kappa]) for this thread's half of the latent coordinates
+      auto drain_kz = [&](float coef, const float* add, int add_stride) {
+        const uint32_t td = chunk_begin();
+        for (int q = 0; q < kh; q += 8) {
+          float v[8];
+          tc_ld8(td + (uint32_t)(k0 + q), v);
+          tc_wait_ld();
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int kk = k0 + q + e;
+            if (kk < K1) dzs[kk * 128] += coef * (v[e] + (add ? __ldg(add + (long long)kk * add_stride) : 0.f));
+          }
+        }
+        chunk_end();
+      };
+
+      // ---- prologue: operand tiles zt and h_{H+1}; private dz accumulators cleared ----
+      for (int kk = 0; kk < K1; ++kk) dzs[kk * 128] = 0.f;
+      {
+        const int ng = KZ / 8;
+        for (int c = half; c < ng; c += 2) {
+          uint32_t w[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) w[e] = bf_pack2(zt_at(8 * c + 2 * e), zt_at(8 * c + 2 * e + 1));
+          *reinterpret_cast<uint4*>(Z_tile + zrow_off + c * 128) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        const float* hsrc = a.save + (long long)H * slot_floats + trow;  // h_{H+1}
+#pragma unroll
+        for (int c = 0; c < CH / 8; ++c) {
+          float4 p0 = make_float4(0.f, 0.f, 0.f, 0.f), p1 = p0;
+          if (live) { p0 = ldg4(hsrc + (2 * c) * 128); p1 = ldg4(hsrc + (2 * c + 1) * 128); }
+          *reinterpret_cast<uint4*>(A_tile + row_off + (uint32_t)(half * (CH / 8) + c) * 128u) =
+              make_uint4(bf_pack2(p0.x, p0.y), bf_pack2(p0.z, p0.w), bf_pack2(p1.x, p1.y), bf_pack2(p1.z, p1.w));
+        }
+        fence_async_smem();
+        mbar_arrive(&a_ready[0]);
+      }
+      float dy[NIF_MAX_SO];
+#pragma unroll
+      for (int c = 0; c < NIF_MAX_SO; ++c) dy[c] = (c < so && live) ? __ldg(&a.du[b * so + c]) : 0.f;
+
+      float acc[CH];  // dh_{m+1}, this thread's columns
+      // ---- last matrix: dh_{H+1} ----
+      for (int c = 0; c < so; ++c) {
+        const uint32_t td = chunk_begin();
+        float dyc = 0.f;
+#pragma unroll
+        for (int cc = 0; cc < NIF_MAX_SO; ++cc) if (cc == c) dyc = dy[cc];
+#pragma unroll
+        for (int q = 0; q < CH / 32; ++q) {
+          float v[32];
+          tc_ld32(td + (uint32_t)(half * CH + q * 32), v);
+          tc_wait_ld();
+#pragma unroll
+          for (int e = 0; e < 32; ++e) acc[q * 32 + e] = c == 0 ? dyc * v[e] : fmaf(dyc, v[e], acc[q * 32 + e]);
+        }
+        chunk_end();
+      }
+      // ---- last matrix: its dz terms ----
+      for (int c = 0; c < so; ++c) {
+        float dyc = 0.f;
+#pragma unroll
+        for (int cc = 0; cc < NIF_MAX_SO; ++cc) if (cc == c) dyc = dy[cc];
+        drain_kz(dyc, CL + c, pl.NP);
+      }
+
+      // ---- layers H .. 0 ----
+#pragma unroll 1
+      for (int m = H; m >= 0; --m) {
+        {  // da_m = dh_{m+1} * d_m -> global (tiled) and the operand tile
+          const float* dsv = a.save + (long long)(H + 1 + m) * slot_floats + trow;
+          float* dag = a.da + (long long)m * slot_floats + trow;
+#pragma unroll
+          for (int c = 0; c < CH / 8; ++c) {
+            float4 d0 = make_float4(0.f, 0.f, 0.f, 0.f), d1 = d0;
+            if (live) { d0 = ldg4(dsv + (2 * c) * 128); d1 = ldg4(dsv + (2 * c + 1) * 128); }
+            const float v0 = acc[8 * c] * d0.x, v1 = acc[8 * c + 1] * d0.y, v2 = acc[8 * c + 2] * d0.z, v3 = acc[8 * c + 3] * d0.w;
+            const float v4 = acc[8 * c + 4] * d1.x, v5 = acc[8 * c + 5] * d1.y, v6 = acc[8 * c + 6] * d1.z, v7 = acc[8 * c + 7] * d1.w;
+            if (live) {
+              *reinterpret_cast<float4*>(dag + (2 * c) * 128) = make_float4(v0, v1, v2, v3);
+              *reinterpret_cast<float4*>(dag + (2 * c + 1) * 128) = make_float4(v4, v5, v6, v7);
+            }
+            *reinterpret_cast<uint4*>(A_tile + row_off + (uint32_t)(half * (CH / 8) + c) * 128u) =
+                make_uint4(bf_pack2(v0, v1), bf_pack2(v2, v3), bf_pack2(v4, v5), bf_pack2(v6, v7));
+          }
+          fence_async_smem();
+          mbar_arrive(&a_ready[0]);
+        }
+        // this layer's input h_m (this thread's columns) for the dz dot products: fetched before the bias-row chunk is
+        // drained, so that the loads fly behind its wait
+        float hm[CH];
+        if (m >= 1) {
+          const float* hsrc = a.save + (long long)(m - 1) * slot_floats + trow;
+#pragma unroll
+          for (int c = 0; c < CH / 4; ++c) {
+            float4 q4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (live) q4 = ldg4(hsrc + c * 128);
+            hm[4 * c] = q4.x; hm[4 * c + 1] = q4.y; hm[4 * c + 2] = q4.z; hm[4 * c + 3] = q4.w;
+          }
+        }
+        drain_kz(1.f, nullptr, 0);  // bias rows of layer m
+        if (m == 0) {
+          const float om = plan_omega(pl, 0);
+          for (int i = 0; i < si; ++i) drain_kz(om * (live ? __ldg(&a.x[b * si + i]) : 0.f), nullptr, 0);
+          break;
+        }
+        if (plan_res(pl, m) != 1) {  // res == 1 (NIF hidden layer): dh_m = T + dh_{m+1}, keep acc
+#pragma unroll
+          for (int e = 0; e < CH; ++e) acc[e] = 0.f;
+        }
+        const float om = plan_omega(pl, m);
+        float zn[CK];
+#pragma unroll
+        for (int kl = 0; kl < CK; ++kl) zn[kl] = om * zt_at(kl);
+#pragma unroll 1
+        for (int c = 0; c < NCHW; ++c) {
+          float zc[CK];
+#pragma unroll
+          for (int kl = 0; kl < CK; ++kl) zc[kl] = zn[kl];
+          if (c + 1 < NCHW) {
+#pragma unroll
+            for (int kl = 0; kl < CK; ++kl) zn[kl] = om * zt_at((c + 1) * CK + kl);
+          }
+          const uint32_t td = chunk_begin();
+#pragma unroll
+          for (int kl = 0; kl < CK; ++kl) {
+            float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+            for (int q = 0; q < CH / 32; ++q) {
+              float v[32];
+              tc_ld32(td + (uint32_t)(kl * NP + half * CH + q * 32), v);
+              tc_wait_ld();
+#pragma unroll
+              for (int e = 0; e < 32; e += 2) {
+                acc[q * 32 + e] = fmaf(zc[kl], v[e], acc[q * 32 + e]);
+                acc[q * 32 + e + 1] = fmaf(zc[kl], v[e + 1], acc[q * 32 + e + 1]);
+                s0 = fmaf(v[e], hm[q * 32 + e], s0);
+                s1 = fmaf(v[e + 1], hm[q * 32 + e + 1], s1);
+              }
+            }
+            const int kk = c * CK + kl;
+            if (kk < K1) dzs[kk * 128] += om * (s0 + s1);
+          }
+          chunk_end();
+        }
+      }
+
+      // ---- dz row: the two halves' accumulators added ----
+      named_bar_sync(1, 256);
+      if (live) {
+        const float* d0 = dzs_all + r;
+        const float* d1 = dzs_all + (long long)K1 * 128 + r;
+        for (int kk = half; kk < K; kk += 2) a.dz[b * K + kk] = d0[kk * 128] + d1[kk * 128];
+      }
+      named_bar_sync(1, 256);  // the accumulators are cleared by the next tile
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tc_dealloc(tmem, 256);
+}
+
+static int bfb_pick_stages(size_t fixed_bytes) {
+  for (int nst = 4; nst >= 2; --nst)
+    if (fixed_bytes + (size_t)nst * BF_STAGE_BYTES <= 227 * 1024) return nst;
+  return 0;
+}
+
+int nif_bf_bwd_data_impl(const Plan& pl, long long B, const float* z, const float* x, const float* packed,
+                         const float* save, const float* du, float* da, float* dz, cudaStream_t st) {
+  if (!nif_plan_uses_bf(pl) || pl.K < 1) return NIF_E_UNSUPPORTED;
+  BfBwdArgs a;
+  a.nst = bfb_pick_stages(nif_bfb_smem_fixed(pl));
+  if (!a.nst) return NIF_E_UNSUPPORTED;
+  const size_t smem = nif_bfb_smem_fixed(pl) + (size_t)a.nst * BF_STAGE_BYTES;
+  a.B = B;
+  a.total_tiles = (B + 127) / 128;
+  a.z = z; a.x = x; a.packed = packed; a.save = save; a.du = du; a.da = da; a.dz = dz;
+  auto kern = pl.NP == 128 ? nif_bf_bwd_data_kernel<128> : nif_bf_bwd_data_kernel<64>;
+  NIF_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int dev = 0, sms = 0;
+  NIF_CUDA_CHECK(cudaGetDevice(&dev));
+  NIF_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  long long grid = sms;
+  if (grid > a.total_tiles) grid = a.total_tiles;
+  if (grid < 1) return NIF_OK;
+  kern<<<(unsigned)grid, BFB_THREADS, smem, st>>>(pl, a);
+  NIF_CUDA_CHECK(cudaGetLastError());
+  return NIF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Weight gradient of the hidden matrices:  D[(kappa_l, i)][j] += A[(kappa_l, i)][b] * Bm[j][b],  A = zt (x) h_m, Bm = da_m,
+// the batch index b is the MMA K dimension; both operands are generated on the fly by row-owning threads, MN-major
+// (for a fixed row b the (kappa_l, i) / j index is contiguous):
+//   offset(mn, k) = (mn/8) * 1024 + (k/8) * 128 + (k%8) * 16 + (mn%8) * 2        [MN x 64 (b)] bf16 tiles
+// One CTA = (hidden matrix, group of 4 "slabs", batch split); a slab is one M = 128 operand: CK = 128/NP latent
+// coordinates x NP rows i, N = NP.  64-row sub-tiles, two operand slots (generation of sub-tile t+1 overlaps the MMAs of
+// sub-tile t); accumulators stay in TMEM (4 slabs x NP columns) for the whole batch range; the result is written as a
+// partial in the layout nif_unpack_grad_kernel sums.  Row data comes straight from the tiled stash / da slots: the 32
+// lanes of a warp read 512 contiguous bytes per access.
+// ---------------------------------------------------------------------------------------------------
+struct BfWgtArgs {
+  long long B, rows_per_split;
+  int S;
+  const float *z, *save, *da;
+  float* part;  // [S][H][K+1][NP][NP]
+};
+
+#define BFW_THREADS 288
+#define BFW_A_BYTES 16384u  // [128 (kappa_l, i) x 64 (b)] bf16, MN-major
+
+__device__ __forceinline__ uint64_t bfw_make_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((128u >> 4) & 0x3FFF) << 16;   // LBO: next group of 8 k
+  d |= (uint64_t)((1024u >> 4) & 0x3FFF) << 32;  // SBO: next group of 8 mn
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+
+template <int NP>
+__global__ void __launch_bounds__(BFW_THREADS, 1) nif_bf_bwd_weight_kernel(const Plan pl, const BfWgtArgs a) {
+  constexpr int CK = 128 / NP;              // latent coordinates per slab
+  constexpr int KQ = 4 * CK;                // latent coordinates per CTA
+  constexpr uint32_t B_BYTES = NP * 128u;   // [NP (j) x 64 (b)] bf16
+  constexpr uint32_t SLOT_BYTES = 4 * BFW_A_BYTES + B_BYTES;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ uint64_t slot_full[2], slot_empty[2], done_bar;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int K = pl.K, K1 = pl.K + 1, H = pl.H;
+  const int NG = (K1 + KQ - 1) / KQ;
+  const int h = blockIdx.x / NG, pg = blockIdx.x % NG;
+  const int s = blockIdx.y;
+  const long long r0 = (long long)s * a.rows_per_split;
+  long long r1 = r0 + a.rows_per_split;
+  if (r1 > a.B) r1 = a.B;
+  const long long nsub = r1 > r0 ? (r1 - r0 + 63) / 64 : 0;
+
+  if (tid == 0) {
+    mbar_init(&slot_full[0], 128); mbar_init(&slot_full[1], 128);
+    mbar_init(&slot_empty[0], 1); mbar_init(&slot_empty[1], 1);
+    mbar_init(&done_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 8) tc_alloc(&tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+
+  if (warp == 8) {
+    // MMA issuer: warp-uniform loop, one elected lane issues
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+    const uint32_t idesc = bf_idesc(NP, 1, 1);
+    for (long long t = 0; t < nsub; ++t) {
+      const int sl = (int)(t & 1);
+      mbar_wait(&slot_full[sl], (uint32_t)((t >> 1) & 1));
+      tc_fence_after();
+      if (tc_elect_one()) {
+        const uint32_t base = smem_u32(smem + sl * SLOT_BYTES);
+        const uint64_t db = bfw_make_desc(base + 4 * BFW_A_BYTES);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint64_t dA = bfw_make_desc(base + q * BFW_A_BYTES);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)  // 16 rows (k) per instruction = 2 k-groups = 256 B
+            tc_mma_f16(tmem_u + (uint32_t)(q * NP), dA + (uint64_t)(ks * 16), db + (uint64_t)(ks * 16), idesc,
+                       (t > 0 || ks > 0) ? 1u : 0u);
+        }
+        tc_commit(&slot_empty[sl]);
+      }
+      __syncwarp();
+    }
+    if (tc_elect_one()) tc_commit(&done_bar);
+    __syncwarp();
+  } else {
+    // ---------------- operand generators: slot sl = warp / 4; thread (q, r): slabs 2q, 2q+1 and half q of da; row r ----------------
+    const int sl = warp >> 2;
+    const int q = (tid >> 6) & 1, r = tid & 63;
+    unsigned char* slot = smem + sl * SLOT_BYTES;
+    unsigned char* Bt = slot + 4 * BFW_A_BYTES;
+    const uint32_t koff = (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 16u;  // this row's position along k
+    const long long slot_floats = bf_slot_floats(a.B, NP);
+    const float* hsrc = a.save + (long long)h * slot_floats;      // h_m, m = h + 1 -> stash slot h
+    const float* dsrc = a.da + (long long)(h + 1) * slot_floats;  // da_m
+    const int kk0 = KQ * pg + 2 * CK * q;                         // first latent coordinate of this thread
+    long long n_mine = 0;
+    for (long long t = sl; t < nsub; t += 2, ++n_mine) {
+      const long long b = r0 + t * 64 + r;
+      const bool live = b < r1;
+      float zt[2 * CK];
+#pragma unroll
+      for (int kl = 0; kl < 2 * CK; ++kl) {
+        const int kk = kk0 + kl;
+        zt[kl] = 0.f;
+        if (live) zt[kl] = (kk < K) ? __ldg(&a.z[b * K + kk]) : (kk == K ? 1.f : 0.f);
+      }
+      const float* hrow = hsrc + bf_tiled_row(b, NP);
+      const float* drow = dsrc + bf_tiled_row(b, NP) + (long long)(q * (NP / 8)) * 128;  // quads of columns q*NP/2 ..
+      // wait until the MMAs that read this slot two sub-tiles ago have completed
+      mbar_wait(&slot_empty[sl], (uint32_t)((n_mine & 1) ^ 1));
+      // A: groups of 8 consecutive i, all of this thread's latent coordinates; loads batched 4 groups at a time
+#pragma unroll 1
+      for (int ig0 = 0; ig0 < NP / 8; ig0 += 4) {
+        float4 p[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) p[u] = live ? ldg4(hrow + (2 * ig0 + u) * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int ig = ig0 + u;
+          const float4 p0 = p[2 * u], p1 = p[2 * u + 1];
+#pragma unroll
+          for (int kl = 0; kl < 2 * CK; ++kl) {
+            const float zk = zt[kl];
+            // slab 2q + kl / CK, rows (kl % CK) * NP + 8 ig ..
+            const uint32_t mg = (uint32_t)((kl % CK) * (NP / 8) + ig);
+            *reinterpret_cast<uint4*>(slot + (uint32_t)(2 * q + kl / CK) * BFW_A_BYTES + mg * 1024u + koff) =
+                make_uint4(bf_pack2(zk * p0.x, zk * p0.y), bf_pack2(zk * p0.z, zk * p0.w), bf_pack2(zk * p1.x, zk * p1.y),
+                           bf_pack2(zk * p1.z, zk * p1.w));
+          }
+        }
+      }
+      // B: this thread's half of the columns j
+#pragma unroll 1
+      for (int jg0 = 0; jg0 < NP / 16; jg0 += 4) {
+        float4 p[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) p[u] = live ? ldg4(drow + (2 * jg0 + u) * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float4 p0 = p[2 * u], p1 = p[2 * u + 1];
+          const uint32_t mg = (uint32_t)(q * (NP / 16) + jg0 + u);
+          *reinterpret_cast<uint4*>(Bt + mg * 1024u + koff) =
+              make_uint4(bf_pack2(p0.x, p0.y), bf_pack2(p0.z, p0.w), bf_pack2(p1.x, p1.y), bf_pack2(p1.z, p1.w));
+        }
+      }
+      fence_async_smem();
+      mbar_arrive(&slot_full[sl]);
+    }
+    // ---------------- final epilogue (warps 0-3): TMEM lane = (kappa_l, i) row of the gradient ----------------
+    if (warp < 4) {
+      mbar_wait(&done_bar, 0);
+      tc_fence_after();
+      const int row = tid;  // 0..127
+      const int kl = row / NP, i = row % NP;
+      const float scale = plan_omega(pl, h + 1);
+      const uint32_t tm = tmem + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+      for (int qq = 0; qq < 4; ++qq) {
+        const int kk = KQ * pg + qq * CK + kl;
+        float* dst = a.part + ((((long long)s * H + h) * K1 + kk) * NP + i) * NP;
+#pragma unroll 1
+        for (int c0 = 0; c0 < NP; c0 += 32) {
+          float v[32];
+          tc_ld32(tm + (uint32_t)(qq * NP + c0), v);
+          tc_wait_ld();
+          if (kk < K1) {
+#pragma unroll
+            for (int e = 0; e < 32; e += 4)
+              *reinterpret_cast<float4*>(dst + c0 + e) = make_float4(nsub ? scale * v[e] : 0.f, nsub ? scale * v[e + 1] : 0.f,
+                                                                      nsub ? scale * v[e + 2] : 0.f, nsub ? scale * v[e + 3] : 0.f);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tc_dealloc(tmem, 512);
+}
+
+int nif_bf_bwd_weight_impl(const Plan& pl, long long B, const float* z, const float* save, const float* da, int S,
+                           long long rows_per_split, float* part, cudaStream_t st) {
+  if (!nif_plan_uses_bf(pl) || pl.K < 1) return NIF_E_UNSUPPORTED;
+  BfWgtArgs a;
+  a.B = B; a.rows_per_split = rows_per_split; a.S = S;
+  a.z = z; a.save = save; a.da = da; a.part = part;
+  const int CK = 128 / pl.NP, KQ = 4 * CK;
+  const int NG = (pl.K + 1 + KQ - 1) / KQ;
+  const size_t smem = 2 * (size_t)(4 * BFW_A_BYTES + pl.NP * 128u);
+  dim3 grid((unsigned)(pl.H * NG), (unsigned)S);
+  if (pl.NP == 128) {
+    NIF_CUDA_CHECK(cudaFuncSetAttribute(nif_bf_bwd_weight_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    nif_bf_bwd_weight_kernel<128><<<grid, BFW_THREADS, smem, st>>>(pl, a);
+  } else {
+    NIF_CUDA_CHECK(cudaFuncSetAttribute(nif_bf_bwd_weight_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    nif_bf_bwd_weight_kernel<64><<<grid, BFW_THREADS, smem, st>>>(pl, a);
+  }
+  NIF_CUDA_CHECK(cudaGetLastError());
+  return NIF_OK;
+}

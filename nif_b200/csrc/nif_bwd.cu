@@ -536,7 +536,7 @@ struct EdgeArgs {
   const float *z, *x, *save, *da, *du;
   float* part;  // [S][K+1][Q]
   int no_bias;  // tangent-adjoint pass: the bias-row columns are zero
-  int tiled;    // da / save are in the tiled layout of the tensor-core path (nif_common.cuh), NP = 64
+  int tiled;    // da / save are in the tiled layout of the tensor-core paths (nif_common.cuh)
   int q_begin, q_end;  // columns handled by this launch (the tensor-core thin-term kernel takes the rest)
 };
 
@@ -574,7 +574,7 @@ __global__ void __launch_bounds__(16 * KG * RS) nif_bwd_edge_kernel(const Plan p
   bool a_tiled = false;
   float scale = 1.f;
   {
-    const long long slot = a.tiled ? nif_tiled_rows(a.B) * 64 : a.B * NP;  // floats per da / stash slot
+    const long long slot = a.tiled ? nif_tiled_rows(a.B) * NP : a.B * NP;  // floats per da / stash slot
     int r = a.q_begin + blockIdx.x * 64 + fc;
     if (fl < FL && r < a.q_end) {
       if (r < (H + 1) * NP) {
@@ -613,7 +613,7 @@ __global__ void __launch_bounds__(16 * KG * RS) nif_bwd_edge_kernel(const Plan p
     for (int u = 0; u < EPT; ++u) {
       long long b = rb + fl + u * FL;
       if (b >= r1) b = r0;
-      pa[u] = __ldg(&Ap[a_tiled ? nif_tiled_row(b) : b * sA]);
+      pa[u] = __ldg(&Ap[a_tiled ? nif_tiled_row_np(b, NP) : b * sA]);
       pb[u] = __ldg(&Bp[b * sB]);
     }
 #pragma unroll
@@ -744,7 +744,36 @@ int nif_tc_bwd_edge_impl(const Plan& pl, long long B, const float* z, const floa
                          cudaStream_t st);
 
 
+bool nif_plan_uses_bf(const Plan& pl);
+int nif_bf_bwd_data_impl(const Plan& pl, long long B, const float* z, const float* x, const float* packed,
+                         const float* save, const float* du, float* da, float* dz, cudaStream_t st);
+int nif_bf_bwd_weight_impl(const Plan& pl, long long B, const float* z, const float* save, const float* da, int S,
+                           long long rows_per_split, float* part, cudaStream_t st);
+
 static long long round_up(long long v, long long m) { return (v + m - 1) / m * m; }
+// batch splits of the bf16 weight-gradient kernel: one CTA per SM and every CTA costs the same, so the count that
+// wastes the least of the last wave (at least 512 rows per split; an explicit acc_rows caps the rows per split)
+static int nif_bf_wgt_splits(const Plan& pl, long long B) {
+  const int KQ = 4 * (128 / pl.NP);
+  const long long items = (long long)pl.H * ((pl.K + 1 + KQ - 1) / KQ);
+  long long s_max = (B + 511) / 512;
+  if (s_max < 1) s_max = 1;
+  if (s_max > 64) s_max = 64;
+  long long s_min = 1;
+  if (pl.acc_rows > 0) {
+    long long rows = pl.acc_rows < 256 ? 256 : pl.acc_rows;
+    s_min = (B + rows - 1) / rows;
+    if (s_max < s_min) s_max = s_min;
+  }
+  long long best = s_min;
+  double best_eff = 0.0;
+  for (long long S = s_min; S <= s_max; ++S) {
+    const long long ctas = items * S, waves = (ctas + 147) / 148;
+    const double eff = (double)ctas / (double)(waves * 148);
+    if (eff > best_eff + 1e-9) { best_eff = eff; best = S; }
+  }
+  return (int)best;
+}
 // rows per batch split of the tensor-core batch-reduction kernels (bounds the truncating accumulation chains, see
 // nif_grad_ws_layout): nif_desc_t.acc_rows, default 4096
 static long long nif_tc_wgt_max_rows(const Plan& pl) {
@@ -812,6 +841,13 @@ GradWs nif_grad_ws_layout(const Plan& pl, long long B) {
       w.S_h = (int)s_need;
       w.rows_h = round_up((B + s_need - 1) / s_need, 64);
     }
+  }
+  if (nif_plan_uses_bf(pl) && pl.K >= 1) {
+    const long long S = nif_bf_wgt_splits(pl, B);
+    w.rows_h = round_up((B + S - 1) / S, 64);
+    if (w.rows_h < 64) w.rows_h = 64;
+    w.S_h = (int)((B + w.rows_h - 1) / w.rows_h);
+    if (w.S_h < 1) w.S_h = 1;
   }
   const long long kc = nif_edge_kc((int)K1);  // latent coordinates per pass of the thin-term kernel
   const long long base_e = (w.Q + 63) / 64 * ((K1 + kc - 1) / kc);
@@ -897,6 +933,20 @@ int nif_backward_impl(const Plan& pl, long long B, const float* z, const float* 
   a.da = ws + w.da;
   a.dz = dz;
   a.h_stash = save; a.e_stash = nullptr; a.ext_out = nullptr; a.ext_add = nullptr; a.no_bias = 0; a.dz_accumulate = 0;
+  if (pl.bf) {  // bf16 tensor-core reverse pass: data kernel, weight-gradient GEMM, thin terms on the CUDA cores
+    int rcb = nif_bf_bwd_data_impl(pl, B, z, x, packed, save, du, ws + w.da, dz, st);
+    if (rcb == NIF_OK) {
+      rcb = nif_bf_bwd_weight_impl(pl, B, z, save, ws + w.da, w.S_h, w.rows_h, ws + w.part_h, st);
+      if (rcb != NIF_OK) return rcb;
+      EdgeArgs e;
+      e.B = B; e.rows_per_split = w.rows_e; e.S = w.S_e; e.Q = w.Q;
+      e.z = z; e.x = x; e.save = save; e.da = ws + w.da; e.du = du; e.part = ws + w.part_e; e.no_bias = 0; e.tiled = 1;
+      e.q_begin = 0; e.q_end = w.Q;
+      NIF_CUDA_CHECK(launch_edge(pl, e, w, st));
+      return nif_unpack_grad_impl(pl, w.S_h, ws + w.part_h, w.S_e, ws + w.part_e, w.Q, dw_h, db_h, beta, st);
+    }
+    if (rcb != NIF_E_UNSUPPORTED) return rcb;
+  }
   int rc = NIF_E_UNSUPPORTED;
   if (pl.tc)  // tensor-core data pass; shapes it does not cover use the CUDA-core kernel below
     rc = nif_tc_bwd_data_impl(pl, B, z, x, packed, save, du, ws + w.da, dz, reinterpret_cast<unsigned*>(ws + w.maxes), st);

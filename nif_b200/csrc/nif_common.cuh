@@ -55,6 +55,9 @@ struct Plan {
   int wide_last;
   // rows per accumulation chain of the tensor-core batch reductions (nif_desc_t.acc_rows; 0 = default 4096)
   int acc_rows;
+  // bf16 single-product tensor-core path (dtype_compute == 1, nif_bf.cuh): bf16 operand tiles appended to the image
+  int bf;
+  long long off_WF, off_WB, off_WX;
 };
 __host__ __device__ inline long long plan_x0_floats(const Plan& p) { return 64LL * p.KZ; }            // one X0 / XC chunk [hi|lo]
 __host__ __device__ inline long long plan_xl_floats(const Plan& p) { return (long long)p.LPC * p.KZ * 64; }       // one XL chunk [hi|lo]
@@ -249,6 +252,8 @@ __device__ __forceinline__ void stg8(float* p, float a0, float a1, float a2, flo
 __host__ __device__ inline long long nif_tiled_rows(long long B) { return (B + 63) / 64 * 64; }
 __host__ __device__ inline long long nif_tiled_row(long long b) { return (b >> 5) * 2048 + (b & 31) * 4; }
 __host__ __device__ inline int nif_tiled_col(int j) { return (j >> 2) * 128 + (j & 3); }
+// the same layout for a slot of NP columns (the bf16 tensor-core path, nif_bf.cuh): row groups are 32 NP floats apart
+__host__ __device__ inline long long nif_tiled_row_np(long long b, int NP) { return (b >> 5) * (32LL * NP) + (b & 31) * 4; }
 // static shape test shared by forward and reverse: does this plan run on the tensor-core kernels (tiled stash)?
 bool nif_plan_uses_tc(const Plan& pl);
 

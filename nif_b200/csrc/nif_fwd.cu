@@ -349,8 +349,15 @@ static int dispatch_fwd(const Plan& pl, const FwdArgs& a, cudaStream_t st) {
 int nif_tc_forward_impl(const Plan& pl, long long B, const float* z, const float* x, const float* packed, float* u,
                         float* save, cudaStream_t st);
 
+int nif_bf_forward_impl(const Plan& pl, long long G, long long B, const float* z, const float* x, int x_shared,
+                        const float* packed, float* u, float* save, cudaStream_t st);
+
 int nif_forward_impl(const Plan& pl, long long G, long long B, const float* z, const float* x, int x_shared,
                      const float* packed, float* u, float* save, cudaStream_t st) {
+  if (pl.bf) {  // bf16 tensor-core path (grouped launches included); other shapes fall through
+    const int rc = nif_bf_forward_impl(pl, G, B, z, x, x_shared, packed, u, save, st);
+    if (rc != NIF_E_UNSUPPORTED) return rc;
+  }
   if (pl.tc && G == 1) {  // tensor-core path; shapes it does not cover fall through to the CUDA-core kernel
     const int rc = nif_tc_forward_impl(pl, B, z, x, packed, u, save, st);
     if (rc != NIF_E_UNSUPPORTED) return rc;

@@ -48,7 +48,15 @@ void nif_plan_layout(Plan* pp) {
     p.KG = (p.K + 3) / 4 * 4;
     p.off_GE = off; off += (long long)(p.H + 1 + p.si + p.so + 1) * 64 * p.KG;
   }
-  p.packed_floats = (off + 31) / 32 * 32;  // keep every image 128-byte aligned
+  p.off_WF = p.off_WB = p.off_WX = 0;
+  if (p.bf) {
+    off = (off + 255) / 256 * 256;  // bulk-copy sources: 1 KB aligned
+    const long long nchw = (p.K + 1 + (128 / p.NP) - 1) / (128 / p.NP);
+    p.off_WF = off; off += (long long)p.H * nchw * 64 * p.NP;
+    p.off_WB = off; off += (long long)p.H * nchw * 64 * p.NP;
+    p.off_WX = off; off += (long long)(2 * (p.si + p.so + p.H + 1)) * p.NP * p.KZ / 2;
+  }
+  p.packed_floats = (off + 255) / 256 * 256;  // keep every image 1 KB aligned
 }
 
 int nif_make_plan(const nif_desc_t* d, Plan* out) {
@@ -60,8 +68,12 @@ int nif_make_plan(const nif_desc_t* d, Plan* out) {
   if (d->l < 0 || d->l > 64) { nif_set_error("nlayers=%d outside [0,64]", d->l); return NIF_E_BAD_DESC; }
   if (d->K < 0 || d->K > 256) { nif_set_error("latent_dim=%d outside [0,256]", d->K); return NIF_E_BAD_DESC; }
   if (d->act < 0 || d->act > NIF_ACT_SIGMOID) { nif_set_error("activation id %d unknown", d->act); return NIF_E_BAD_DESC; }
-  if (d->dtype_compute != 0 && d->dtype_compute != 2) {
-    nif_set_error("dtype_compute=%d: built paths are 0 (fp32 CUDA cores) and 2 (tensor cores, FP16x3 split)", d->dtype_compute);
+  if (d->dtype_compute < 0 || d->dtype_compute > 2) {
+    nif_set_error("dtype_compute=%d: built paths are 0 (fp32 CUDA cores), 1 (tensor cores, bf16 operands) and 2 (tensor cores, FP16x3 split)", d->dtype_compute);
+    return NIF_E_UNSUPPORTED;
+  }
+  if (d->dtype_compute == 1 && d->n <= 32) {
+    nif_set_error("dtype_compute=1 (bf16 tensor cores) is built for units > 32 (got %d)", d->n);
     return NIF_E_UNSUPPORTED;
   }
   if (d->dtype_compute == 2 && (d->n <= 32 || d->n > 64)) {
@@ -79,6 +91,7 @@ int nif_make_plan(const nif_desc_t* d, Plan* out) {
   p.P = p.H * p.n * p.n + (p.si + p.so + 1 + p.H) * p.n + p.so;
   p.wide_last = 0;
   p.tc = d->dtype_compute == 2 ? 1 : 0;
+  p.bf = d->dtype_compute == 1 ? 1 : 0;
   if (d->acc_rows < 0) { nif_set_error("acc_rows=%d is negative", d->acc_rows); return NIF_E_BAD_DESC; }
   p.acc_rows = d->acc_rows;
   nif_plan_layout(&p);
@@ -116,6 +129,7 @@ __global__ void __launch_bounds__(256) nif_pack_kernel(const Plan pl, long long 
     const long long g = e / pl.packed_floats;
     long long r = e - g * pl.packed_floats;
     float v = 0.f;
+    if (pl.bf && r >= pl.off_WF) continue;  // bf16 operand tiles: written by nif_pack_bf_kernel
     if (r < pl.off_MHT) {  // MH [H (+1 if wide_last)][K1][NP][NP]
       if (r < (long long)(H + pl.wide_last) * K1 * NP * NP) {
         const int j = r % NP; r /= NP;
@@ -263,7 +277,12 @@ __global__ void __launch_bounds__(256) nif_pack_scales_kernel(const Plan pl, con
   }
 }
 
+int nif_pack_bf_impl(const Plan& pl, long long G, const float* w_h, const float* b_h, float* packed, cudaStream_t st);
 int nif_pack_impl(const Plan& pl, long long G, const float* w_h, const float* b_h, float* packed, cudaStream_t st) {
+  if (pl.bf) {
+    const int rc = nif_pack_bf_impl(pl, G, w_h, b_h, packed, st);
+    if (rc) return rc;
+  }
   if (pl.tc) {
     nif_pack_scales_kernel<<<(unsigned)(pl.H * pl.KP + plan_n_small(pl)), 256, 0, st>>>(pl, w_h, b_h, packed);
     NIF_CUDA_CHECK(cudaGetLastError());

@@ -70,12 +70,15 @@ class NIF(object):
             raise NotImplementedError("act_l1_reg / act_l2_reg are outside the B200 hot-path scope")
         if mixed_policy not in _POLICIES:
             raise ValueError(f"mixed_policy must be one of {_POLICIES} (float64 has no GPU path)")
-        if compute not in ("auto", "fp32", "fp16x3"):
-            raise ValueError("compute must be 'auto', 'fp32' (CUDA cores) or 'fp16x3' (tensor cores, fp32-grade)")
+        if compute not in ("auto", "fp32", "fp16x3", "bf16"):
+            raise ValueError("compute must be 'auto', 'fp32' (CUDA cores), 'fp16x3' (tensor cores, fp32-grade) or "
+                             "'bf16' (tensor cores, bf16 operands)")
         self._compute_request = compute
         self.mixed_policy_name = mixed_policy
         self.variable_Dtype = "float32"
-        self.compute_Dtype = "float32"  # the fp32 kernels serve every policy in this build
+        # mixed_bfloat16 (nif/model.py:101-105): bf16 operands on the tensor cores, fp32 accumulation, fp32 variables.
+        # mixed_float16 is served at fp32 grade (the FP16x3 path already runs on the fp16 tensor-core pipe).
+        self.compute_Dtype = "bfloat16" if mixed_policy == "mixed_bfloat16" else "float32"
         if device is None:
             device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
         self.device = torch.device(device)
@@ -109,7 +112,10 @@ class NIF(object):
             # inside the library, shapes the tensor-core kernels do not cover fall through to the CUDA-core kernels.
             comp = self._compute_request
             if comp == "auto":
-                comp = "fp16x3" if (32 < self.n_sx <= 64 and self.pi_hidden >= 1) else "fp32"
+                if self.mixed_policy_name == "mixed_bfloat16" and self.n_sx > 32 and self._variant != "siren_res":
+                    comp = "bf16"
+                else:
+                    comp = "fp16x3" if (32 < self.n_sx <= 64 and self.pi_hidden >= 1) else "fp32"
             self._engine = FusedShapeNet(self._variant, self.si_dim, self.so_dim, self.n_sx, self.l_sx, self.pi_hidden,
                                          self.cfg_shape_net.get("activation"), self._omega0, compute=comp)
             if self._engine.po_dim != self.po_dim:

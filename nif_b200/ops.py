@@ -45,7 +45,8 @@ class FusedShapeNet:
     linear layer (w_h, b_h) instead.
     """
 
-    COMPUTE = {"fp32": 0, "fp16x3": 2}  # fp32 CUDA cores | tensor cores, 3-product fp16 split (fp32-grade)
+    # fp32 CUDA cores | tensor cores, bf16 operands (mixed_bfloat16) | tensor cores, 3-product fp16 split (fp32-grade)
+    COMPUTE = {"fp32": 0, "bf16": 1, "fp16x3": 2}
 
     def __init__(self, variant: str, si: int, so: int, n: int, l: int, K: int,
                  activation: Optional[str] = "swish", omega0: float = 1.0, compute: str = "fp32", acc_rows: int = 0):

@@ -204,6 +204,126 @@ def shape_net_mres(
     return _bvm(u, ws[-1]) + bs[-1]
 
 
+def _bf16(t: Tensor) -> Tensor:
+    """Round to bfloat16 (round-to-nearest-even) and come back in the working precision."""
+    return t.to(torch.float32).to(torch.bfloat16).to(t.dtype)
+
+
+def shape_net_factored(spec: Spec, x: Tensor, z: Tensor, w_h: Tensor, b_h: Tensor, quant: Optional[str] = None) -> Tensor:
+    """The same ShapeNet (nif/model.py:233-324, 738-954) in the re-associated form the kernels evaluate, with the
+    latent code kept separate from the last linear layer:
+        pre_m[b,j] = omega * sum_{kappa,i} zt[b,kappa] h[b,i] M_m[kappa,i,j] + sum_kappa zt[b,kappa] C_m[kappa,j],
+    zt = [z, 1], M_m / C_m = the column slices of [w_h; b_h].  quant=None is exact arithmetic in the working precision
+    (equal to shape_net(hyper_linear(z, w_h, b_h)) up to summation order).
+
+    quant='bf16' restates what the reference's `mixed_bfloat16` policy (nif/model.py:101-105, 146, 530-533, 954;
+    nif/layers/siren.py:519-521: variables cast to the compute dtype, einsum in bf16) permits, at the rounding points of
+    the bf16 tensor-core kernels: every matmul operand -- the entries of [w_h; b_h], the activations h, and the latent
+    code where it is a matmul operand (layer 0 and the bias sums) -- is rounded to bfloat16; products are accumulated
+    in the working precision; the latent contraction, omega_0, the activation and the last layer's bias stay fp32."""
+    q = _bf16 if quant == "bf16" else (lambda t: t)
+    L = layout(spec.si, spec.so, spec.n, spec.l, spec.variant == "siren_res")
+    K1 = z.shape[1] + 1
+    W = torch.cat([w_h, b_h[None, :]], 0)  # [K+1, P]
+    zt = torch.cat([z, torch.ones(z.shape[0], 1, dtype=z.dtype)], 1)
+    Wq, ztq = q(W), q(zt)
+    mats = [Wq[:, o:o + a * c].reshape(K1, a, c) for (o, a, c) in L.w]
+    bias = [Wq[:, o:o + c] for (o, c) in L.b]
+    sine = spec.variant != "nif"
+    f = torch.sin if sine else activation(spec.s_act)
+    om = spec.omega0 if sine else 1.0
+    H = len(mats) - 2
+    # layer 0: the coordinates stay fp32 and multiply the tensor-core result
+    d0 = torch.einsum("bk,kij->bij", ztq, mats[0])
+    u = f(om * torch.einsum("bi,bij->bj", x, d0) + ztq @ bias[0])
+    carry = None
+    for m in range(1, H + 1):
+        pre = om * torch.einsum("bk,bi,kij->bj", zt, q(u), mats[m]) + ztq @ bias[m]
+        if spec.variant == "nif":
+            u = f(pre) + u
+        elif spec.variant == "siren_res":
+            if m % 2 == 1:
+                carry, u = u, f(pre)
+            else:
+                u = 0.5 * (carry + f(pre))
+        else:
+            u = f(pre)
+    bL = W[:, L.b[-1][0]:L.b[-1][0] + L.b[-1][1]]  # the last bias is added on the CUDA cores: not rounded
+    return torch.einsum("bk,bkc->bc", zt, torch.einsum("bi,kic->bkc", q(u), mats[-1]) + bL[None])
+
+
+def shape_net_factored_backward_bf16(spec: Spec, x: Tensor, z: Tensor, w_h: Tensor, b_h: Tensor, du: Tensor):
+    """Reverse pass of shape_net_factored(quant='bf16') at the rounding points of the bf16 tensor-core kernels
+    (what GradientTape computes for nif/model.py:130-154 / 510-539 under `mixed_bfloat16`, with fp32
+    accumulation): the operands of every tensor-core product are rounded to bfloat16 -- da_m, the weight slices, zt
+    where it is a matmul operand, the generated operand zt (x) h_m of the weight-gradient GEMM (the PRODUCT is
+    rounded) -- while the stashed activations h_m / act'(pre_m), the latent contraction and the thin batch reductions
+    (bias rows, first and last matrix: fp32 CUDA-core kernel) are not.  Variants 'nif' and 'siren'.
+    Returns (u, dw_h [K,P], db_h [P], dz [B,K])."""
+    assert spec.variant in ("nif", "siren")
+    q = _bf16
+    L = layout(spec.si, spec.so, spec.n, spec.l, False)
+    K = z.shape[1]
+    W = torch.cat([w_h, b_h[None, :]], 0)
+    zt = torch.cat([z, torch.ones(z.shape[0], 1, dtype=z.dtype)], 1)
+    Wq, ztq = q(W), q(zt)
+    mats = [Wq[:, o:o + a * c].reshape(K + 1, a, c) for (o, a, c) in L.w]
+    bias = [Wq[:, o:o + c] for (o, c) in L.b]
+    sine = spec.variant != "nif"
+    om = spec.omega0 if sine else 1.0
+    H = len(mats) - 2
+
+    def act_fd(v):
+        if sine:
+            return torch.sin(v), torch.cos(v)
+        vv = v.detach().clone().requires_grad_(True)
+        f = activation(spec.s_act)(vv)
+        (d,) = torch.autograd.grad(f.sum(), vv)
+        return f.detach(), d
+
+    hs, ds = [], []  # hs[m] = input of matrix m (m = 1..H+1 -> index m-1), ds[m] = act'(pre_m)
+    d0 = torch.einsum("bk,kij->bij", ztq, mats[0])
+    f, d = act_fd(om * torch.einsum("bi,bij->bj", x, d0) + ztq @ bias[0])
+    u = f
+    ds.append(d)
+    hs.append(u)
+    for m in range(1, H + 1):
+        pre = om * torch.einsum("bk,bi,kij->bj", zt, q(u), mats[m]) + ztq @ bias[m]
+        f, d = act_fd(pre)
+        u = f + u if spec.variant == "nif" else f
+        ds.append(d)
+        hs.append(u)
+    bL = W[:, L.b[-1][0]:L.b[-1][0] + L.b[-1][1]]
+    y = torch.einsum("bk,bkc->bc", zt, torch.einsum("bi,kic->bkc", q(u), mats[-1]) + bL[None])
+
+    dW = torch.zeros_like(W)
+    dzt = torch.zeros_like(zt)
+    # last matrix
+    dh = torch.einsum("bc,bk,kic->bi", du, ztq, mats[-1])
+    dzt += torch.einsum("bc,bkc->bk", du, torch.einsum("bi,kic->bkc", q(hs[H]), mats[-1]) + bL[None])
+    o, a_, c_ = L.w[-1]
+    dW[:, o:o + a_ * c_] = torch.einsum("bk,bi,bc->kic", zt, hs[H], du).reshape(K + 1, -1)
+    o, c_ = L.b[-1]
+    dW[:, o:o + c_] = zt.T @ du
+    for m in range(H, -1, -1):
+        da = dh * ds[m]
+        daq = q(da)
+        dzt += daq @ bias[m].T
+        o, c_ = L.b[m]
+        dW[:, o:o + c_] = zt.T @ da
+        o, a_, c_ = L.w[m]
+        if m >= 1:
+            T = torch.einsum("bj,kij->bki", daq, mats[m])
+            dh = (dh if spec.variant == "nif" else 0) + om * torch.einsum("bk,bki->bi", zt, T)
+            dzt += om * torch.einsum("bki,bi->bk", T, hs[m - 1])
+            A = q(zt[:, :, None] * hs[m - 1][:, None, :])  # the generated operand: the product is rounded
+            dW[:, o:o + a_ * c_] = om * torch.einsum("bki,bj->kij", A, daq).reshape(K + 1, -1)
+        else:
+            dzt += om * torch.einsum("bi,bj,kij->bk", x, daq, mats[0])
+            dW[:, o:o + a_ * c_] = om * torch.einsum("bk,bi,bj->kij", zt, x, da).reshape(K + 1, -1)
+    return y, dW[:K], dW[K], dzt[:, :K]
+
+
 def shape_net(spec: Spec, x: Tensor, p: Tensor) -> Tensor:
     if spec.variant == "nif":
         return shape_net_nif(x, p, spec.si, spec.so, spec.n, spec.l, spec.s_act)
