@@ -199,64 +199,79 @@ def run_ours(args):
     ms_e2e = timed(step_e2e, args.steps, max(3, args.warmup // 2))
     clocks = sampler.stop() if sampler else None  # sampled under load across both timed regions
 
+    # ---- sustained rate: >= 3 s of back-to-back steps after the timed regions, with its own clock sample ----
+    sampler2 = ClockSampler(dev.index if dev.index is not None else 0) if rank == 0 else None
+    n_sus = max(args.steps, int(3000.0 / max(ms_step, 1e-3)) + 1)
+    ms_sus = timed(step_resident, n_sus, 3)
+    clocks_sus = sampler2.stop() if sampler2 else None
+
+    # ---- replicas agree: after all those steps every rank must hold bit-identical parameters ----
+    params_equal = None
+    if world > 1:
+        lo, hi = net.theta.clone(), net.theta.clone()
+        torch.distributed.all_reduce(lo, op=torch.distributed.ReduceOp.MIN)
+        torch.distributed.all_reduce(hi, op=torch.distributed.ReduceOp.MAX)
+        params_equal = bool(torch.equal(lo, hi))
+
     if rank != 0:
         dp.shutdown()
         return
 
-    # ---- per-kernel times for the roofline (outside the timed region; CUDA events on the launch stream) ----
+    # ---- per-kernel table (outside the timed regions): eager launches, every launch of the library bracketed by CUDA
+    # events on its own stream (nif_profile_begin / nif_profile_end); isolates which kernel dominates the step ----
+    from nif_b200.ops import kernel_profile
     eng = net.engine
     F_fwd, F_step, P = flops_per_point()
-    z = model._latent_nograd(inp_d[0][:, :1]).detach().contiguous()
-    xs = inp_d[0][:, 1:3].contiguous()
-    packed = eng.pack(net.w_h.detach(), net.b_h.detach())
-    u, stash = eng.forward(z, xs, packed, save=True)
-    dw, db = torch.empty_like(net.w_h), torch.empty_like(net.b_h)
-    loss = torch.zeros(1, device=dev)
-
-    def ev_time(fn, reps=10):
-        fn()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(reps):
-            fn()
-        e1.record()
-        torch.cuda.synchronize()
-        return e0.elapsed_time(e1) / reps
-
-    ms_fwd = ev_time(lambda: eng.forward(z, xs, packed, save=True))
-    ms_bwd = ev_time(lambda: eng.mse_backward(z, xs, packed, u, stash, tgt_d[0], None, 1.0 / gb, loss, dw, db))
-    fp32_peak = nif_b200.ops.measure_fp32_peak()
+    model.use_graph = False
+    model.dist = None  # the table is this rank's kernels; the collective is not a kernel of the library
+    for i in range(2):
+        step_resident(i)
+    torch.cuda.synchronize()
+    n_prof = 5
+    with kernel_profile() as prof:
+        for i in range(n_prof):
+            step_resident(i)
+    W_s = 2 * 64 + 4 * 64 * 64 + 64
+    K, H, n_s = 32, 4, 64
+    alg_flops = {  # ALGORITHMIC flops per launch: rows x per-row figure
+        "nif_tc_fwd_kernel": (2 * K * P + 2 * W_s) * BATCH,            # latent->weights projection + ShapeNet, forward
+        "nif_tc_bwd_data_kernel": (2 * K * P + 2 * W_s) * BATCH,       # the same products, transposed weights
+        "nif_tc_bwd_weight_kernel": 2 * (K + 1) * H * n_s * n_s * BATCH,  # batch reduction of zt (x) h (x) da, hidden matrices
+    }
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except OSError:
         pass
-    # fp16 tensor-core path at fp32-grade accuracy: every algorithmic MAC costs 3 tensor-core MACs (hi*hi, lo*hi,
-    # hi*lo), so the ceiling for ALGORITHMIC FLOP/s is a third of the measured dense 16-bit peak.
-    tensor_peak = float(peaks.get("bf16_tflops_sustained", 1590.0 * 0.88))
+    peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
+    peak_burst = float(peaks.get("bf16_tflops", 1590.0))
+    peak_sus = float(peaks.get("bf16_tflops_sustained", 1590.0 * 0.88))
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "measured" if peaks else "fallback"
-    # forward kernel: algorithmic FLOPs of the fused path (latent->weights projection + ShapeNet), no trunk
-    W_s = 2 * 64 + 4 * 64 * 64 + 64
-    flops_fwd_kernel = (2 * 32 * P + 2 * W_s) * BATCH
-    ach_fwd = flops_fwd_kernel / (ms_fwd * 1e-3) / 1e12
-    ach_bwd = 2 * flops_fwd_kernel / (ms_bwd * 1e-3) / 1e12
+    traffic_by_kernel = {}
+    try:  # DRAM bytes per launch from the committed `ncu --set full` capture of one step
+        traffic_by_kernel = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_kernels.json")))
+    except (OSError, ValueError):
+        pass
+    tot_ms = sum(ms for _, _, ms in prof.table) or 1.0
+    table = []
+    for name, cnt, ms in sorted(prof.table, key=lambda r: -r[2]):
+        us = ms * 1e3 / cnt
+        row = {"kernel": name, "launches_per_step": cnt / n_prof, "us_per_launch": us, "share_of_step": ms / tot_ms}
+        if name in alg_flops:
+            row["tflops"] = alg_flops[name] / (us * 1e-6) / 1e12
+            row["frac_of_burst_peak"] = row["tflops"] / peak_burst
+        if name in traffic_by_kernel:
+            row["dram_bytes_per_launch"] = traffic_by_kernel[name]
+        table.append(row)
+    dom = table[0]
+    launches_per_step = sum(cnt for _, cnt, _ in prof.table) / n_prof
+    fp32_peak = nif_b200.ops.measure_fp32_peak()
     step_tflops = F_step * BATCH / (ms_step * 1e-3) / 1e12
     # algorithmic HBM bytes per step: inputs + targets + Adam (28 B/param) + gradient write/read (8 B/param)
     n_par = net.count_params()
     hbm_bytes = BATCH * 4 * (1 + 2 + 1) + 36 * n_par
     pts = BATCH * world / (ms_step * 1e-3)
     pts_e2e = BATCH * world / (ms_e2e * 1e-3)
-    tc = eng.compute == "fp16x3"
-    kernel_name = ("nif_tc_fwd_kernel (tcgen05 fp16 MMA, 3-product split, fp32 accumulate in TMEM)" if tc
-                   else "nif_fwd_kernel (fp32 CUDA cores)")
-
-    traffic = None
-    try:  # DRAM bytes per launch of the dominant kernel from the committed ncu capture
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_tc_fwd.json")))["dram_bytes_per_launch"] if tc else None
-    except (OSError, KeyError, ValueError):
-        pass
 
     cores = os.cpu_count() or 1
     cpu_rate, cpu_sec = cpu_reference_rate(2048, 6, 1, cores) if world == 1 else (None, None)
@@ -266,27 +281,33 @@ def run_ours(args):
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "global_batch": gb, "parallelism": f"dp{world}",
-                   "l2": "inputs rotate through the 1M-point set; per-step working set (activation stash 168 MB + "
-                         "deltas 84 MB) exceeds the 126 MB L2, no explicit flush"},
+                   "kernels": eng.kernel_path,
+                   "l2": "inputs rotate through the 1M-point set; per-step working set (activation stash + deltas, "
+                         "> 200 MB) exceeds the 126 MB L2, no explicit flush"},
         "clocks": clocks,
         "e2e": {"value": pts_e2e, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": BATCH * 4 * 4,
                 "d2h_bytes_per_step": 4},
-        # nif_* kernels per optimisation step (profiles/r01_launches_step.csv): trunk pack + forward, pack scales + pack,
-        # forward, seed + loss, data pass + dz edge, weight GEMM + edge + unpack, trunk data + weight + edge + unpack, Adam
-        "gpu_launches": (17 if model.net._trunk is not None else 11) * args.steps,
-        "roofline": {"bound": "tensor", "kernel": kernel_name, "achieved": ach_fwd,
-                     "peak": tensor_peak, "unit": "TFLOP/s", "frac": ach_fwd / tensor_peak, "traffic": traffic,
+        "sustained": {"value": BATCH * world / (ms_sus * 1e-3), "unit": UNIT, "ms_per_step": ms_sus, "steps": n_sus,
+                      "seconds": ms_sus * n_sus / 1e3, "clocks": clocks_sus},
+        "params_equal_across_ranks": params_equal,
+        "gpu_launches": int(round(launches_per_step * args.steps)),
+        # the DOMINANT kernel of the step by time (kernel table below), timed by CUDA events around its launches inside
+        # eager steps, against the burst dense 16-bit peak
+        "roofline": {"bound": "tensor", "kernel": dom["kernel"], "achieved": dom.get("tflops"),
+                     "peak": peak_burst, "unit": "TFLOP/s",
+                     "frac": (dom["tflops"] / peak_burst) if "tflops" in dom else None,
+                     "traffic": dom.get("dram_bytes_per_launch"),
                      "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full "
-                                     "(profiles/r01_ncu_step_final.txt): the activation stash written for the reverse pass",
-                     "peak_source": f"bf16_tflops_sustained (dense 16-bit MMA), {peak_src}",
-                     "note": "achieved = ALGORITHMIC FLOPs (2KP+2Ws per row) / launch time; the fp32-grade split "
-                             "issues 3 tensor-core MACs per algorithmic MAC, so 1/3 of peak is this path's ceiling",
-                     "tensor_macs_per_algorithmic_mac": 3 if tc else 0,
-                     "frac_of_split_ceiling": (3 * ach_fwd / tensor_peak) if tc else None,
-                     "ms_per_launch": ms_fwd, "fp32_fma_peak_tflops": fp32_peak,
-                     "x_over_fp32_fma_peak": ach_fwd / fp32_peak,
-                     "reverse_pass": {"ms": ms_bwd, "achieved": ach_bwd, "x_over_fp32_fma_peak": ach_bwd / fp32_peak},
-                     "whole_step_tflops": step_tflops,
+                                     "(profiles/r02_ncu_kernels.json)",
+                     "peak_source": f"bf16_tflops (burst, dense 16-bit MMA), {peak_src}",
+                     "note": "achieved = ALGORITHMIC flops per launch / launch time; the fp32-grade FP16x3 split issues 3 "
+                             "tensor-core MACs per algorithmic MAC, so 1/3 of peak is this path's ceiling",
+                     "tensor_macs_per_algorithmic_mac": 3 if eng.kernel_path == "fp16x3" else 1,
+                     "us_per_launch": dom["us_per_launch"], "share_of_step": dom["share_of_step"],
+                     "kernel_table": table,
+                     "whole_step": {"tflops": step_tflops, "peak": peak_sus, "frac": step_tflops / peak_sus,
+                                    "peak_source": f"bf16_tflops_sustained, {peak_src}"},
+                     "fp32_fma_peak_tflops": fp32_peak,
                      "hbm": {"achieved_gbs": hbm_bytes / (ms_step * 1e-3) / 1e9, "peak_gbs": hbm_peak,
                              "frac": hbm_bytes / (ms_step * 1e-3) / 1e9 / hbm_peak,
                              "note": "compute-bound by design: 16 B/point + 36 B/param per step"}},

@@ -194,6 +194,13 @@ int nif_trunk_backward(const nif_trunk_desc_t* d, int64_t B, const float* p_in, 
  * measured with CUDA events; blocks until done. */
 int nif_measure_fp32_peak(double* tflops);
 
+/* Per-kernel timing for the benchmark's kernel table.  Between nif_profile_begin() and nif_profile_end() every kernel
+ * the library launches is bracketed by two CUDA events on its own stream (eager launches only: do not open a profile
+ * while capturing a CUDA graph).  nif_profile_end blocks until that work is done and writes one line per kernel name,
+ * "name launches total_ms\n" in order of first launch, into the HOST buffer `out` (NUL-terminated, cut at cap). */
+int nif_profile_begin(void);
+int nif_profile_end(char* out, int64_t cap);
+
 /* CRC-32C (Castagnoli) of a HOST buffer, continuing from `crc` (0 for a fresh checksum): the checksum of the TFRecord
  * framing (nif/data/tfr_dataset.py:84-88, 159 use tf.io.TFRecordWriter / tf.data.TFRecordDataset, third-party).  Host
  * code only; the one entry point that takes host pointers. */

@@ -19,6 +19,7 @@ SYMBOLS = (
     "nif_forward_given_w", "nif_mse_backward", "nif_backward", "nif_adam_step", "nif_adam_step_dev", "nif_measure_fp32_peak",
     "nif_trunk_query", "nif_trunk_forward", "nif_trunk_backward",
     "nif_sobolev_query", "nif_forward_tangent_save", "nif_sobolev_backward", "nif_crc32c",
+    "nif_profile_begin", "nif_profile_end",
 )
 
 VARIANT = {"nif": 0, "siren": 1, "siren_res": 2}
@@ -101,6 +102,8 @@ def lib() -> C.CDLL:
         getattr(L, name)  # raises AttributeError if the build is stale
         if name not in ("nif_last_error", "nif_crc32c"):
             getattr(L, name).restype = C.c_int
+    L.nif_profile_begin.argtypes = []
+    L.nif_profile_end.argtypes = [C.c_char_p, C.c_int64]
     L.nif_crc32c.restype = C.c_uint32
     L.nif_crc32c.argtypes = [C.c_char_p, C.c_uint64, C.c_uint32]
     _lib = L

@@ -281,6 +281,62 @@ extern "C" int nif_trunk_backward(const nif_trunk_desc_t* d, int64_t B, const fl
                                  static_cast<cudaStream_t>(stream));
 }
 
+// ---- per-kernel timing (bench.py's kernel table) -------------------------------------------------------------------
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+int g_nif_prof_on = 0;
+namespace {
+struct ProfRec { const char* name; cudaEvent_t e0, e1; };
+std::vector<ProfRec> g_prof;
+}
+void nif_prof_push(const char* name, cudaStream_t st, bool begin) {
+  if (begin) {
+    ProfRec r;
+    r.name = name;
+    if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return;
+    cudaEventRecord(r.e0, st);
+    g_prof.push_back(r);
+  } else if (!g_prof.empty()) {
+    cudaEventRecord(g_prof.back().e1, st);
+  }
+}
+extern "C" int nif_profile_begin(void) {
+  for (auto& r : g_prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  g_prof.clear();
+  g_nif_prof_on = 1;
+  return NIF_OK;
+}
+// Closes the profile (blocks until the recorded work is done) and writes one line per kernel name,
+// "name launches total_ms\n", in order of first launch, into `out` (NUL-terminated, truncated to cap).
+extern "C" int nif_profile_end(char* out, int64_t cap) {
+  g_nif_prof_on = 0;
+  if (!out || cap < 1) { nif_set_error("nif_profile_end: null buffer"); return NIF_E_BAD_ARG; }
+  std::vector<std::string> names;
+  std::vector<double> ms;
+  std::vector<long long> cnt;
+  for (auto& r : g_prof) {
+    float t = 0.f;
+    if (cudaEventSynchronize(r.e1) != cudaSuccess || cudaEventElapsedTime(&t, r.e0, r.e1) != cudaSuccess) t = 0.f;
+    size_t i = 0;
+    for (; i < names.size(); ++i) if (names[i] == r.name) break;
+    if (i == names.size()) { names.push_back(r.name); ms.push_back(0.0); cnt.push_back(0); }
+    ms[i] += t; cnt[i] += 1;
+    cudaEventDestroy(r.e0); cudaEventDestroy(r.e1);
+  }
+  g_prof.clear();
+  std::string s;
+  char line[256];
+  for (size_t i = 0; i < names.size(); ++i) {
+    snprintf(line, sizeof(line), "%s %lld %.6f\n", names[i].c_str(), cnt[i], ms[i]);
+    s += line;
+  }
+  strncpy(out, s.c_str(), (size_t)cap - 1);
+  out[cap - 1] = 0;
+  return NIF_OK;
+}
+
 // ---- CRC-32C for the TFRecord framing (host code, slicing-by-8) ----------------------------------------------------
 static uint32_t g_crc_tab[8][256];
 static bool g_crc_ready = false;

@@ -353,7 +353,7 @@ int nif_bf_bwd_data_impl(const Plan& pl, long long B, const float* z, const floa
   long long grid = sms;
   if (grid > a.total_tiles) grid = a.total_tiles;
   if (grid < 1) return NIF_OK;
-  kern<<<(unsigned)grid, BFB_THREADS, smem, st>>>(pl, a);
+  { NIF_PROF("nif_bf_bwd_data_kernel", st); kern<<<(unsigned)grid, BFB_THREADS, smem, st>>>(pl, a); }
   NIF_CUDA_CHECK(cudaGetLastError());
   return NIF_OK;
 }
@@ -552,10 +552,10 @@ int nif_bf_bwd_weight_impl(const Plan& pl, long long B, const float* z, const fl
   dim3 grid((unsigned)(pl.H * NG), (unsigned)S);
   if (pl.NP == 128) {
     NIF_CUDA_CHECK(cudaFuncSetAttribute(nif_bf_bwd_weight_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    nif_bf_bwd_weight_kernel<128><<<grid, BFW_THREADS, smem, st>>>(pl, a);
+    { NIF_PROF("nif_bf_bwd_weight_kernel", st); nif_bf_bwd_weight_kernel<128><<<grid, BFW_THREADS, smem, st>>>(pl, a); }
   } else {
     NIF_CUDA_CHECK(cudaFuncSetAttribute(nif_bf_bwd_weight_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    nif_bf_bwd_weight_kernel<64><<<grid, BFW_THREADS, smem, st>>>(pl, a);
+    { NIF_PROF("nif_bf_bwd_weight_kernel", st); nif_bf_bwd_weight_kernel<64><<<grid, BFW_THREADS, smem, st>>>(pl, a); }
   }
   NIF_CUDA_CHECK(cudaGetLastError());
   return NIF_OK;

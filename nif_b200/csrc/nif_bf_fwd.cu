@@ -353,7 +353,7 @@ static int launch_bff(const Plan& pl, BfFwdArgs& a, cudaStream_t st) {
   long long grid = sms;
   if (grid > a.total_tiles) grid = a.total_tiles;
   if (grid < 1) return NIF_OK;
-  kern<<<(unsigned)grid, BFF_THREADS, smem, st>>>(pl, a);
+  { NIF_PROF("nif_bf_fwd_kernel", st); kern<<<(unsigned)grid, BFF_THREADS, smem, st>>>(pl, a); }
   NIF_CUDA_CHECK(cudaGetLastError());
   return NIF_OK;
 }

@@ -81,7 +81,7 @@ int nif_pack_bf_impl(const Plan& pl, long long G, const float* w_h, const float*
   const long long total = G * (pl.packed_floats - pl.off_WF);
   long long nblk = (total + 255) / 256;
   if (nblk > 148 * 32) nblk = 148 * 32;
-  nif_pack_bf_kernel<<<(unsigned)nblk, 256, 0, st>>>(pl, G, w_h, b_h, packed);
+  { NIF_PROF("nif_pack_bf_kernel", st); nif_pack_bf_kernel<<<(unsigned)nblk, 256, 0, st>>>(pl, G, w_h, b_h, packed); }
   NIF_CUDA_CHECK(cudaGetLastError());
   return NIF_OK;
 }

@@ -387,7 +387,7 @@ static int launch_bwd_data(const Plan& pl, const BwdArgs& a, cudaStream_t st) {
   long long grid = (long long)sms * occ;
   if (grid > a.total_tiles) grid = a.total_tiles;
   if (grid < 1) return NIF_OK;
-  kern<<<(unsigned)grid, C::NT, smem, st>>>(pl, a);
+  { NIF_PROF("nif_bwd_data_kernel", st); kern<<<(unsigned)grid, C::NT, smem, st>>>(pl, a); }
   NIF_CUDA_CHECK(cudaGetLastError());
   return NIF_OK;
 }
@@ -879,12 +879,12 @@ static cudaError_t launch_edge(const Plan& pl, const EdgeArgs& e, const GradWs& 
   const int KC = nif_edge_kc(K1);
   dim3 grid((unsigned)((e.q_end - e.q_begin + 63) / 64), (unsigned)w.S_e, (unsigned)((K1 + KC - 1) / KC));
   switch (KC) {
-    case 4: nif_bwd_edge_kernel<1, 16><<<grid, 256, 0, st>>>(pl, e); break;
-    case 8: nif_bwd_edge_kernel<2, 8><<<grid, 256, 0, st>>>(pl, e); break;
-    case 16: nif_bwd_edge_kernel<4, 4><<<grid, 256, 0, st>>>(pl, e); break;
-    case 32: nif_bwd_edge_kernel<8, 2><<<grid, 256, 0, st>>>(pl, e); break;
-    case 36: nif_bwd_edge_kernel<9, 1><<<grid, 144, 0, st>>>(pl, e); break;
-    default: nif_bwd_edge_kernel<17, 1><<<grid, 272, 0, st>>>(pl, e); break;
+    case 4: { NIF_PROF("nif_bwd_edge_kernel", st); nif_bwd_edge_kernel<1, 16><<<grid, 256, 0, st>>>(pl, e); } break;
+    case 8: { NIF_PROF("nif_bwd_edge_kernel", st); nif_bwd_edge_kernel<2, 8><<<grid, 256, 0, st>>>(pl, e); } break;
+    case 16: { NIF_PROF("nif_bwd_edge_kernel", st); nif_bwd_edge_kernel<4, 4><<<grid, 256, 0, st>>>(pl, e); } break;
+    case 32: { NIF_PROF("nif_bwd_edge_kernel", st); nif_bwd_edge_kernel<8, 2><<<grid, 256, 0, st>>>(pl, e); } break;
+    case 36: { NIF_PROF("nif_bwd_edge_kernel", st); nif_bwd_edge_kernel<9, 1><<<grid, 144, 0, st>>>(pl, e); } break;
+    default: { NIF_PROF("nif_bwd_edge_kernel", st); nif_bwd_edge_kernel<17, 1><<<grid, 272, 0, st>>>(pl, e); } break;
   }
   return cudaGetLastError();
 }
@@ -905,12 +905,12 @@ int nif_weight_grads_impl(const Plan& pl, long long B, const float* z, const flo
     if (pl.NP >= 64) {
       const int nb = pl.NP / 64;
       dim3 grid((unsigned)(Hm * kgn * nb * nb), (unsigned)w.S_h);
-      if (kq == 1) nif_bwd_weight_kernel<64, 1><<<grid, 256, 0, st>>>(pl, g);
-      else nif_bwd_weight_kernel<64, 4><<<grid, 256, 0, st>>>(pl, g);
+      if (kq == 1) { NIF_PROF("nif_bwd_weight_kernel", st); nif_bwd_weight_kernel<64, 1><<<grid, 256, 0, st>>>(pl, g); }
+      else { NIF_PROF("nif_bwd_weight_kernel", st); nif_bwd_weight_kernel<64, 4><<<grid, 256, 0, st>>>(pl, g); }
     } else {
       dim3 grid((unsigned)(Hm * kgn), (unsigned)w.S_h);
-      if (kq == 1) nif_bwd_weight_kernel<32, 1><<<grid, 64, 0, st>>>(pl, g);
-      else nif_bwd_weight_kernel<32, 4><<<grid, 64, 0, st>>>(pl, g);
+      if (kq == 1) { NIF_PROF("nif_bwd_weight_kernel", st); nif_bwd_weight_kernel<32, 1><<<grid, 64, 0, st>>>(pl, g); }
+      else { NIF_PROF("nif_bwd_weight_kernel", st); nif_bwd_weight_kernel<32, 4><<<grid, 64, 0, st>>>(pl, g); }
     }
     NIF_CUDA_CHECK(cudaGetLastError());
   }
@@ -1050,9 +1050,9 @@ int nif_mse_backward_impl(const Plan& pl, long long B, const float* z, const flo
   if (B <= 0) return NIF_OK;
   int nblk = (int)((B + 255) / 256);
   if (nblk > 1024) nblk = 1024;
-  nif_mse_seed_kernel<<<nblk, 256, 0, st>>>(B, pl.so, u, target, sw, inv_gb, ws + w.du, ws + w.loss_part);
+  { NIF_PROF("nif_mse_seed_kernel", st); nif_mse_seed_kernel<<<nblk, 256, 0, st>>>(B, pl.so, u, target, sw, inv_gb, ws + w.du, ws + w.loss_part); }
   NIF_CUDA_CHECK(cudaGetLastError());
-  nif_loss_final_kernel<<<1, 32, 0, st>>>(nblk, ws + w.loss_part, loss);
+  { NIF_PROF("nif_loss_final_kernel", st); nif_loss_final_kernel<<<1, 32, 0, st>>>(nblk, ws + w.loss_part, loss); }
   NIF_CUDA_CHECK(cudaGetLastError());
   return nif_backward_impl(pl, B, z, x, packed, save, ws + w.du, dw_h, db_h, beta, dz, ws, st);
 }

@@ -268,6 +268,19 @@ struct GradWs {
 void nif_set_error(const char* fmt, ...);
 int nif_make_plan(const nif_desc_t* d, Plan* out);
 
+// per-kernel timing for the benchmark's kernel table (nif_profile_begin / nif_profile_end): while a profile is open,
+// every launch of the library is bracketed by two CUDA events on its own stream
+extern int g_nif_prof_on;
+void nif_prof_push(const char* name, cudaStream_t st, bool begin);
+struct NifProfScope {
+  const char* name;
+  cudaStream_t st;
+  bool on;
+  NifProfScope(const char* n, cudaStream_t s) : name(n), st(s), on(g_nif_prof_on != 0) { if (on) nif_prof_push(name, st, true); }
+  ~NifProfScope() { if (on) nif_prof_push(name, st, false); }
+};
+#define NIF_PROF(name, st) NifProfScope nif_prof_scope_(name, st)
+
 #define NIF_CUDA_CHECK(expr)                                                            \
   do {                                                                                  \
     cudaError_t _e = (expr);                                                            \

@@ -333,7 +333,7 @@ static int launch_fwd(const Plan& pl, const FwdArgs& a, cudaStream_t st) {
   long long grid = (long long)sms * occ;
   if (grid > a.total_tiles) grid = a.total_tiles;
   if (grid < 1) return NIF_OK;
-  kern<<<(unsigned)grid, C::NT, smem, st>>>(pl, a);
+  { NIF_PROF("nif_fwd_kernel", st); kern<<<(unsigned)grid, C::NT, smem, st>>>(pl, a); }
   NIF_CUDA_CHECK(cudaGetLastError());
   return NIF_OK;
 }

@@ -112,10 +112,10 @@ int nif_given_w_impl(const Plan& pl, long long B, const float* x, const float* w
   if (nblk > 148 * 8) nblk = 148 * 8;
   const int jpl = (pl.n + 31) / 32;
   switch (jpl) {
-    case 1: nif_given_w_kernel<1><<<(unsigned)nblk, 256, 0, st>>>(pl, B, x, w, u); break;
-    case 2: nif_given_w_kernel<2><<<(unsigned)nblk, 256, 0, st>>>(pl, B, x, w, u); break;
-    case 3: nif_given_w_kernel<3><<<(unsigned)nblk, 256, 0, st>>>(pl, B, x, w, u); break;
-    default: nif_given_w_kernel<4><<<(unsigned)nblk, 256, 0, st>>>(pl, B, x, w, u); break;
+    case 1: { NIF_PROF("nif_given_w_kernel", st); nif_given_w_kernel<1><<<(unsigned)nblk, 256, 0, st>>>(pl, B, x, w, u); } break;
+    case 2: { NIF_PROF("nif_given_w_kernel", st); nif_given_w_kernel<2><<<(unsigned)nblk, 256, 0, st>>>(pl, B, x, w, u); } break;
+    case 3: { NIF_PROF("nif_given_w_kernel", st); nif_given_w_kernel<3><<<(unsigned)nblk, 256, 0, st>>>(pl, B, x, w, u); } break;
+    default: { NIF_PROF("nif_given_w_kernel", st); nif_given_w_kernel<4><<<(unsigned)nblk, 256, 0, st>>>(pl, B, x, w, u); } break;
   }
   NIF_CUDA_CHECK(cudaGetLastError());
   return NIF_OK;
@@ -167,8 +167,8 @@ int nif_adam_impl(long long n, float* p, const float* g, float* m, float* v, dou
   long long nblk = (n / 4 + 255) / 256;
   if (nblk < 1) nblk = 1;
   if (nblk > 148 * 8) nblk = 148 * 8;
-  nif_adam_kernel<<<(unsigned)nblk, 256, 0, st>>>(n, p, g, m, v, (float)alpha, nullptr, (float)(1.0 - b1),
-                                                  (float)(1.0 - b2), (float)eps, l1, l2, gs);
+  { NIF_PROF("nif_adam_kernel", st); nif_adam_kernel<<<(unsigned)nblk, 256, 0, st>>>(n, p, g, m, v, (float)alpha, nullptr, (float)(1.0 - b1),
+                                                  (float)(1.0 - b2), (float)eps, l1, l2, gs); }
   NIF_CUDA_CHECK(cudaGetLastError());
   return NIF_OK;
 }
@@ -179,8 +179,8 @@ int nif_adam_dev_impl(long long n, float* p, const float* g, float* m, float* v,
   long long nblk = (n / 4 + 255) / 256;
   if (nblk < 1) nblk = 1;
   if (nblk > 148 * 8) nblk = 148 * 8;
-  nif_adam_kernel<<<(unsigned)nblk, 256, 0, st>>>(n, p, g, m, v, 0.f, alpha_dev, (float)(1.0 - b1), (float)(1.0 - b2),
-                                                  (float)eps, l1, l2, gs);
+  { NIF_PROF("nif_adam_kernel", st); nif_adam_kernel<<<(unsigned)nblk, 256, 0, st>>>(n, p, g, m, v, 0.f, alpha_dev, (float)(1.0 - b1), (float)(1.0 - b2),
+                                                  (float)eps, l1, l2, gs); }
   NIF_CUDA_CHECK(cudaGetLastError());
   return NIF_OK;
 }

@@ -284,13 +284,13 @@ int nif_pack_impl(const Plan& pl, long long G, const float* w_h, const float* b_
     if (rc) return rc;
   }
   if (pl.tc) {
-    nif_pack_scales_kernel<<<(unsigned)(pl.H * pl.KP + plan_n_small(pl)), 256, 0, st>>>(pl, w_h, b_h, packed);
+    { NIF_PROF("nif_pack_scales_kernel", st); nif_pack_scales_kernel<<<(unsigned)(pl.H * pl.KP + plan_n_small(pl)), 256, 0, st>>>(pl, w_h, b_h, packed); }
     NIF_CUDA_CHECK(cudaGetLastError());
   }
   const long long total = G * pl.packed_floats;
   long long nblk = (total + 255) / 256;
   if (nblk > 148 * 16) nblk = 148 * 16;
-  nif_pack_kernel<<<(unsigned)nblk, 256, 0, st>>>(pl, G, w_h, b_h, packed);
+  { NIF_PROF("nif_pack_kernel", st); nif_pack_kernel<<<(unsigned)nblk, 256, 0, st>>>(pl, G, w_h, b_h, packed); }
   NIF_CUDA_CHECK(cudaGetLastError());
   return NIF_OK;
 }
@@ -350,7 +350,7 @@ int nif_unpack_grad_impl(const Plan& pl, int S_h, const float* part_h, int S_e, 
   const long long total = (long long)(pl.K + 1) * pl.P;
   long long nblk = (total + 255) / 256;
   if (nblk > 148 * 16) nblk = 148 * 16;
-  nif_unpack_grad_kernel<<<(unsigned)nblk, 256, 0, st>>>(pl, S_h, part_h, S_e, part_e, Q, dw_h, db_h, beta);
+  { NIF_PROF("nif_unpack_grad_kernel", st); nif_unpack_grad_kernel<<<(unsigned)nblk, 256, 0, st>>>(pl, S_h, part_h, S_e, part_e, Q, dw_h, db_h, beta); }
   NIF_CUDA_CHECK(cudaGetLastError());
   return NIF_OK;
 }

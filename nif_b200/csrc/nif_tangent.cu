@@ -414,7 +414,7 @@ static int launch_tan(const Plan& pl, TanArgs a, cudaStream_t st) {
   long long grid = (long long)sms * occ;
   if (grid > a.total_tiles) grid = a.total_tiles;
   if (grid < 1) return NIF_OK;
-  kern<<<(unsigned)grid, C::NT, smem, st>>>(pl, a);
+  { NIF_PROF("nif_tangent_kernel", st); kern<<<(unsigned)grid, C::NT, smem, st>>>(pl, a); }
   NIF_CUDA_CHECK(cudaGetLastError());
   return NIF_OK;
 }

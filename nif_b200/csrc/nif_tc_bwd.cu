@@ -508,7 +508,7 @@ int nif_tc_bwd_data_impl(const Plan& pl, long long B, const float* z, const floa
   NIF_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   long long grid = sms;
   if (grid > a.total_pairs) grid = a.total_pairs;
-  nif_tc_bwd_data_kernel<<<(unsigned)grid, TCB_THREADS, smem, st>>>(pl, a);
+  { NIF_PROF("nif_tc_bwd_data_kernel", st); nif_tc_bwd_data_kernel<<<(unsigned)grid, TCB_THREADS, smem, st>>>(pl, a); }
   NIF_CUDA_CHECK(cudaGetLastError());
   DzEdgeArgs e;
   e.B = B; e.x = x; e.packed = packed; e.save = save; e.da = da; e.du = du; e.dz = dz; e.maxes = maxes;
@@ -516,10 +516,10 @@ int nif_tc_bwd_data_impl(const Plan& pl, long long B, const float* z, const floa
     const int left = pl.KG - k0;
     const unsigned grid = (unsigned)((B + 128 * DZE_R - 1) / (128 * DZE_R));
     int kt;
-    if (left >= 32) { kt = 32; nif_dz_edge_kernel<32><<<grid, 128, 0, st>>>(pl, e, k0); }
-    else if (left >= 16) { kt = 16; nif_dz_edge_kernel<16><<<grid, 128, 0, st>>>(pl, e, k0); }
-    else if (left >= 8) { kt = 8; nif_dz_edge_kernel<8><<<grid, 128, 0, st>>>(pl, e, k0); }
-    else { kt = 4; nif_dz_edge_kernel<4><<<grid, 128, 0, st>>>(pl, e, k0); }
+    if (left >= 32) { kt = 32; { NIF_PROF("nif_dz_edge_kernel", st); nif_dz_edge_kernel<32><<<grid, 128, 0, st>>>(pl, e, k0); } }
+    else if (left >= 16) { kt = 16; { NIF_PROF("nif_dz_edge_kernel", st); nif_dz_edge_kernel<16><<<grid, 128, 0, st>>>(pl, e, k0); } }
+    else if (left >= 8) { kt = 8; { NIF_PROF("nif_dz_edge_kernel", st); nif_dz_edge_kernel<8><<<grid, 128, 0, st>>>(pl, e, k0); } }
+    else { kt = 4; { NIF_PROF("nif_dz_edge_kernel", st); nif_dz_edge_kernel<4><<<grid, 128, 0, st>>>(pl, e, k0); } }
     NIF_CUDA_CHECK(cudaGetLastError());
     k0 += kt;
   }
@@ -786,7 +786,7 @@ int nif_tc_bwd_weight_impl(const Plan& pl, long long B, const float* z, const fl
   NIF_CUDA_CHECK(cudaFuncSetAttribute(nif_tc_bwd_weight_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int NPG = (pl.KP + 3) / 4;
   dim3 grid((unsigned)(pl.H * NPG), (unsigned)S);
-  nif_tc_bwd_weight_kernel<<<grid, TCW_THREADS, smem, st>>>(pl, a);
+  { NIF_PROF("nif_tc_bwd_weight_kernel", st); nif_tc_bwd_weight_kernel<<<grid, TCW_THREADS, smem, st>>>(pl, a); }
   NIF_CUDA_CHECK(cudaGetLastError());
   return NIF_OK;
 }

@@ -248,7 +248,7 @@ int nif_tc_bwd_edge_impl(const Plan& pl, long long B, const float* z, const floa
   NIF_CUDA_CHECK(cudaFuncSetAttribute(nif_tc_bwd_edge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int nblk = pl.H + 1 + pl.si + pl.so + 1;
   dim3 grid((unsigned)((nblk + 1) / 2), (unsigned)S);
-  nif_tc_bwd_edge_kernel<<<grid, TCE_THREADS, smem, st>>>(pl, a);
+  { NIF_PROF("nif_tc_bwd_edge_kernel", st); nif_tc_bwd_edge_kernel<<<grid, TCE_THREADS, smem, st>>>(pl, a); }
   NIF_CUDA_CHECK(cudaGetLastError());
   return NIF_OK;
 }

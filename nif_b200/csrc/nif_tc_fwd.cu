@@ -406,7 +406,7 @@ static int launch_tcf(const Plan& pl, const TcFwdArgs& a, cudaStream_t st) {
   long long grid = sms;
   if (grid > a.total_pairs) grid = a.total_pairs;
   if (grid < 1) return NIF_OK;
-  kern<<<(unsigned)grid, TCF_THREADS, smem, st>>>(pl, a);
+  { NIF_PROF("nif_tc_fwd_kernel", st); kern<<<(unsigned)grid, TCF_THREADS, smem, st>>>(pl, a); }
   NIF_CUDA_CHECK(cudaGetLastError());
   return NIF_OK;
 }

@@ -330,3 +330,21 @@ def measure_fp32_peak() -> float:
     v = C.c_double(0.0)
     check(_lib.lib().nif_measure_fp32_peak(C.byref(v)), "nif_measure_fp32_peak")
     return float(v.value)
+
+
+class kernel_profile:
+    """Context manager around nif_profile_begin / nif_profile_end: per-kernel CUDA-event times of the library's launches
+    (eager launches only).  After exit, `.table` is [(kernel name, launches, total ms)] in order of first launch."""
+
+    def __enter__(self):
+        check(_lib.lib().nif_profile_begin(), "nif_profile_begin")
+        self.table = []
+        return self
+
+    def __exit__(self, *exc):
+        buf = C.create_string_buffer(1 << 16)
+        check(_lib.lib().nif_profile_end(buf, len(buf)), "nif_profile_end")
+        for ln in buf.value.decode().splitlines():
+            name, cnt, ms = ln.rsplit(" ", 2)
+            self.table.append((name, int(cnt), float(ms)))
+        return False

@@ -43,3 +43,19 @@ def fullbatch_problem(B=65536):
     x = torch.rand(B, 2, generator=g) * 2 - 1
     tgt = torch.rand(B, 1, generator=g) * 2 - 1
     return spec, prm, z, x, tgt
+
+
+C2_CFG_S = {"use_resblock": False, "connectivity": "full", "input_dim": 2, "output_dim": 1, "units": 64, "nlayers": 4,
+            "weight_init_factor": 0.01, "omega_0": 30.0}
+C2_CFG_P = {"use_resblock": False, "input_dim": 1, "latent_dim": 32, "units": 64, "nlayers": 4, "activation": "swish"}
+
+
+def fullmodel_problem(B=65536):
+    """The whole C2 model (bench.py's configuration: trunk 1 -> 64 x 4 swish -> 32, head, ShapeNet 2 -> 4 x 64 -> 1) at the
+    full benchmark batch with seeded inputs: (spec, parameters, inputs [B,3], target [B,1]), fp32 on the CPU."""
+    spec = O.spec_from_cfg("NIFMultiScale", C2_CFG_S, C2_CFG_P)
+    prm = O.init_params(spec, 0)
+    g = torch.Generator().manual_seed(4321)
+    inputs = torch.rand(B, 3, generator=g) * 2 - 1
+    tgt = torch.rand(B, 1, generator=g) * 2 - 1
+    return spec, prm, inputs, tgt

@@ -703,3 +703,91 @@ def test_full_batch_head_gradient_against_oracle():
             "dz": rel_err(dz[:256].cpu(), ref["dz_head"]), "loss": abs(float(loss) - float(ref["loss"])) / float(ref["loss"])}
     print("full-batch errors vs fp64 oracle:", {k: f"{v:.2e}" for k, v in errs.items()})
     assert errs["loss"] < 1e-5 and errs["dz"] < 1e-5 and errs["dw"] < 1e-5 and errs["db"] < 1e-5, errs
+
+
+def test_full_batch_whole_model_step_against_oracle():
+    """Parity of the WHOLE model AT the benchmark batch: one train_on_batch at 65 536 rows on bench.py's configuration, then
+    every variable's gradient (trunk kernels and biases included) as it sits in the flat gradient buffer BEFORE Adam reads
+    it, against the fp64 oracle summed over 4096-row chunks (tests/golden/fullbatch/make_fullmodel_ref.py).  Gate 1e-5."""
+    import os
+    import nif_b200
+    from tests.helpers import GOLDEN, C2_CFG_S, C2_CFG_P, fullmodel_problem
+    ref = np.load(os.path.join(GOLDEN, "fullbatch", "c2_fullbatch_model_grad.npz"))
+    spec, prm, inputs, tgt = fullmodel_problem()
+    dev = torch.device("cuda:0")
+    net = nif_b200.NIFMultiScale(C2_CFG_S, C2_CFG_P, "float32", seed=0, device=dev)
+    net.set_weights({k: v.numpy() for k, v in prm.items()})
+    assert net.engine.kernel_path == "fp16x3"
+    model = net.build()
+    model.compile(nif_b200.Adam(1e-3), loss="mse", graph=False)
+    loss = model.train_on_batch(inputs, tgt)
+    errs = {"loss": abs(loss - float(ref["loss"])) / float(ref["loss"])}
+    for k in net.variables:
+        errs[k] = rel_err(net._gviews[k].cpu(), ref["g:" + k])
+    print("whole-model full-batch errors vs fp64 oracle:", {k: f"{v:.2e}" for k, v in errs.items()})
+    assert all(v < 1e-5 for v in errs.values()), errs
+
+
+def test_fit_without_shuffle_and_odd_batch_size():
+    """Device-resident data set + shuffle=False hands the step row-slice views at arbitrary byte offsets: the host
+    layer must re-align them for the C ABI.  Batch 50 with one output column puts the second target batch at offset 200 B."""
+    import nif_b200
+    dev = torch.device("cuda:0")
+    cfg_s = {"input_dim": 1, "output_dim": 1, "units": 30, "nlayers": 2, "activation": "swish"}
+    cfg_p = {"input_dim": 1, "latent_dim": 1, "units": 30, "nlayers": 2, "activation": "swish"}
+    rng = np.random.default_rng(0)
+    X = rng.uniform(-1, 1, (230, 2)).astype(np.float32)
+    Y = np.sin(3 * X[:, :1] + X[:, 1:]).astype(np.float32)
+    sw = rng.uniform(0.5, 1.5, (230,)).astype(np.float32)
+    losses = {}
+    for graph in (False, True):
+        net = nif_b200.NIF(cfg_s, cfg_p, seed=0, device=dev)
+        model = net.build()
+        model.compile(nif_b200.Adam(1e-3), loss="mse", graph=graph)
+        h = model.fit(X, Y, batch_size=50, epochs=3, shuffle=False, sample_weight=sw)
+        losses[graph] = h.history["loss"]
+        assert np.all(np.isfinite(losses[graph]))
+    assert losses[False] == losses[True]
+    # user-provided CUDA slices through train_on_batch
+    Xd, Yd = torch.as_tensor(X).to(dev), torch.as_tensor(Y).to(dev)
+    assert np.isfinite(model.train_on_batch(Xd[3:53], Yd[3:53]))
+
+
+def test_predict_latent_grid_on_a_tensor_core_model():
+    """Model.predict_latent_grid on a 64-unit model whose training engine is the FP16x3 tensor-core one (the K = 0
+    engine it derives must not inherit a compute mode that has no grouped kernels)."""
+    import nif_b200
+    dev = torch.device("cuda:0")
+    cfg_s = {"use_resblock": False, "connectivity": "full", "input_dim": 2, "output_dim": 1, "units": 64, "nlayers": 2,
+             "weight_init_factor": 0.01, "omega_0": 30.0}
+    cfg_p = {"use_resblock": False, "input_dim": 1, "latent_dim": 4, "units": 16, "nlayers": 1, "activation": "swish"}
+    net = nif_b200.NIFMultiScale(cfg_s, cfg_p, seed=0, device=dev)
+    assert net.engine.kernel_path == "fp16x3"
+    model = net.build()
+    rng = np.random.default_rng(1)
+    lat = rng.normal(size=(3, 4)).astype(np.float32)
+    grid = rng.uniform(-1, 1, (200, 2)).astype(np.float32)
+    u = model.predict_latent_grid(lat, grid).cpu()
+    spec = O.spec_from_cfg("NIFMultiScale", cfg_s, cfg_p)
+    prm = {k: torch.as_tensor(v).double() for k, v in net.get_weights().items()}
+    wn, bn = O.last_layer_names(spec)
+    wg = O.hyper_linear(torch.as_tensor(lat).double(), prm[wn], prm[bn])
+    for g in range(3):
+        ref = O.shape_net(spec, torch.as_tensor(grid).double(), wg[g:g + 1].expand(200, -1))
+        assert rel_err(u[g], ref) < 2e-5
+
+
+def test_two_rank_nccl_data_parallel_equals_single_process():
+    """N ranks produce the single-process parameters (tools/dp_check.py's body as a driver-run test): spawns 2 ranks over
+    NCCL when at least 2 GPUs are visible, skips otherwise."""
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29533", os.path.join(root, "tools", "dp_check.py")],
+                       capture_output=True, text=True, cwd=root, timeout=600)
+    print(r.stdout[-2000:], r.stderr[-2000:])
+    assert r.returncode == 0 and "DP check" in r.stdout and "params equal True" in r.stdout

@@ -60,13 +60,13 @@ cfg_s = {"use_resblock": False, "connectivity": "full", "input_dim": 3, "output_
 cfg_p = {"use_resblock": False, "input_dim": 1, "latent_dim": 64, "units": 128, "nlayers": 4, "activation": "swish"}
 net = nif_b200.NIFMultiScale(cfg_s, cfg_p, "mixed_bfloat16", seed=0, device=dev)
 m = net.build(); m.compile(nif_b200.Adam(1e-3), loss="mse")
-B = 16384
+B = 65536
 X = torch.as_tensor(rng.uniform(-1, 1, (B, 4)).astype(np.float32)).to(dev)
 Y = torch.as_tensor(rng.uniform(-1, 1, (B, 3)).astype(np.float32)).to(dev)
 ms = ev_time(lambda: m._train_step(X, Y, None, B), 5)
 F, P = flops_step(1, 3, 3, 128, 6, 64, 128, 4)
-out.append({"config": "C3 turbulence ShapeNet 6x128 SIREN, latent 64, batch 16384 (fp32 CUDA-core kernels; the tensor-core "
-                      "path covers widths <= 64)", "po_dim": P, "ms_per_step": ms, "points_per_s": B / ms * 1e3,
+out.append({"config": f"C3 turbulence ShapeNet 6x128 SIREN, latent 64, batch {B}, mixed_bfloat16 (kernels: "
+                      f"{net.engine.kernel_path})", "po_dim": P, "ms_per_step": ms, "points_per_s": B / ms * 1e3,
             "algorithmic_tflops": F * B / ms / 1e9})
 
 # ---- C4: Sobolev training, ShapeNet 1->4x64->1, JacobianLayer(y=[0], x=[0,1]) ----
@@ -88,7 +88,7 @@ out.append({"config": "C4 Sobolev training ShapeNet 4x64, latent 32, batch 65536
 cfg_s = {"use_resblock": False, "connectivity": "full", "input_dim": 3, "output_dim": 1, "units": 128, "nlayers": 6,
          "weight_init_factor": 0.01, "omega_0": 30.0}
 cfg_p = {"use_resblock": False, "input_dim": 1, "latent_dim": 64, "units": 128, "nlayers": 4, "activation": "swish"}
-net = nif_b200.NIFMultiScale(cfg_s, cfg_p, seed=0, device=dev)
+net = nif_b200.NIFMultiScale(cfg_s, cfg_p, "mixed_bfloat16", seed=0, device=dev)
 m = net.build()
 G, side = 64, 64
 lin = np.linspace(-1, 1, side, dtype=np.float32)
@@ -96,8 +96,9 @@ grid = torch.as_tensor(np.stack(np.meshgrid(lin, lin, lin, indexing="ij"), -1).r
 lat = torch.as_tensor(rng.normal(size=(G, 64)).astype(np.float32)).to(dev)
 ms = ev_time(lambda: m.predict_latent_grid(lat, grid), 3)
 W_s = 3 * 128 + 6 * 128 * 128 + 128
-out.append({"config": f"C5 latent sweep ShapeNet 6x128, {G} latents x {side}^3 grid per call (factored form: weights "
-                      "generated once per latent, grouped launches over the shared grid)", "ms_per_call": ms,
+out.append({"config": f"C5 latent sweep ShapeNet 6x128, {G} latents x {side}^3 grid per call, mixed_bfloat16 (factored form: "
+                      f"weights generated once per latent, grouped launches over the shared grid; kernels: {m._eng0.kernel_path})",
+            "ms_per_call": ms,
             "evals_per_s": G * grid.shape[0] / ms * 1e3, "algorithmic_tflops": 2 * W_s * G * grid.shape[0] / ms / 1e9})
 
 for o in out:
