@@ -182,6 +182,10 @@ typedef struct nif_trunk_desc {
  * re-laid weights (written by forward, read by backward of the same step); ws_floats: reverse scratch for batch B. */
 int nif_trunk_query(const nif_trunk_desc_t* d, int64_t B, int64_t* n_theta, int64_t* save_floats_per_row,
                     int64_t* packed_floats, int64_t* ws_floats);
+/* Which kernels serve this trunk: 3 = tcgen05 tensor cores, bf16x3 split (fp32-grade; units <= 64, latent <= 64, 1..5
+ * hidden layers), 0 = fp32 CUDA-core tile kernels.  The stash then holds save_floats_per_row * B64 floats, B64 = B rounded
+ * up to a multiple of 64. */
+int nif_trunk_kernel_path(const nif_trunk_desc_t* d);
 /* z [B,latent] = trunk(p_in [B,pi]); save may be NULL for inference. */
 int nif_trunk_forward(const nif_trunk_desc_t* d, int64_t B, const float* p_in, const float* theta, float* z,
                       float* save, float* packed, void* stream);

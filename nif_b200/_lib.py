@@ -17,7 +17,7 @@ CSRC = os.path.join(_HERE, "csrc")
 SYMBOLS = (
     "nif_last_error", "nif_version", "nif_query_sizes", "nif_pack", "nif_forward", "nif_forward_tangent", "nif_forward_tangent2",
     "nif_forward_given_w", "nif_mse_backward", "nif_backward", "nif_adam_step", "nif_adam_step_dev", "nif_measure_fp32_peak",
-    "nif_trunk_query", "nif_trunk_forward", "nif_trunk_backward",
+    "nif_trunk_query", "nif_trunk_forward", "nif_trunk_backward", "nif_trunk_kernel_path",
     "nif_sobolev_query", "nif_forward_tangent_save", "nif_sobolev_backward", "nif_crc32c",
     "nif_profile_begin", "nif_profile_end",
 )
@@ -96,6 +96,7 @@ def lib() -> C.CDLL:
     L.nif_sobolev_backward.argtypes = [DP, I64, VP, VP, VP, VP, VP, VP, VP, VP, VP, F, VP, VP, VP]
     TP, I64P = C.POINTER(TrunkDesc), C.POINTER(C.c_int64)
     L.nif_trunk_query.argtypes = [TP, I64, I64P, I64P, I64P, I64P]
+    L.nif_trunk_kernel_path.argtypes = [TP]
     L.nif_trunk_forward.argtypes = [TP, I64, VP, VP, VP, VP, VP, VP]
     L.nif_trunk_backward.argtypes = [TP, I64, VP, VP, VP, VP, VP, F, VP, VP, VP]
     for name in SYMBOLS:

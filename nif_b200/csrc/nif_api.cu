@@ -243,6 +243,16 @@ static int trunk_plan(const nif_trunk_desc_t* d, Plan* pl) {
   return nif_make_trunk_plan(d->pi, d->latent, d->units, d->nlayers, d->act, pl);
 }
 
+bool nif_trunk_uses_tc(int pi, int K, int n, int l, int act);
+long long nif_trunk_tc_packed_floats(int pi, int K, int n, int l, int act);
+long long nif_trunk_tc_ws_floats(int pi, int K, int n, int l, int act, long long B);
+int nif_trunk_tc_forward_impl(int pi, int K, int n, int l, int act, long long B, const float* p_in, const float* theta,
+                              float* z, float* save, float* packed, cudaStream_t st);
+int nif_trunk_tc_backward_impl(int pi, int K, int n, int l, int act, long long B, const float* p_in, const float* save,
+                               const float* dz, float* g_theta, float beta, const float* packed, float* ws,
+                               cudaStream_t st);
+static bool trunk_tc(const nif_trunk_desc_t* d) { return nif_trunk_uses_tc(d->pi, d->latent, d->units, d->nlayers, d->act); }
+
 extern "C" int nif_trunk_query(const nif_trunk_desc_t* d, int64_t B, int64_t* n_theta, int64_t* save_floats_per_row,
                                int64_t* packed_floats, int64_t* ws_floats) {
   Plan pl;
@@ -250,10 +260,23 @@ extern "C" int nif_trunk_query(const nif_trunk_desc_t* d, int64_t B, int64_t* n_
   if (rc) return rc;
   if (B < 0) { nif_set_error("nif_trunk_query: B=%lld", (long long)B); return NIF_E_BAD_ARG; }
   if (n_theta) *n_theta = pl.P;
+  if (trunk_tc(d)) {  // tensor-core trunk kernels: 64-wide tiled stash (rows rounded up to 64 by the caller)
+    if (save_floats_per_row) *save_floats_per_row = 2LL * (pl.H + 1) * 64;
+    if (packed_floats) *packed_floats = nif_trunk_tc_packed_floats(d->pi, d->latent, d->units, d->nlayers, d->act);
+    if (ws_floats) *ws_floats = nif_trunk_tc_ws_floats(d->pi, d->latent, d->units, d->nlayers, d->act, B);
+    return NIF_OK;
+  }
   if (save_floats_per_row) *save_floats_per_row = 2LL * (pl.H + 1) * pl.NP;
   if (packed_floats) *packed_floats = pl.packed_floats;
   if (ws_floats) *ws_floats = nif_grad_ws_layout(pl, B).total;
   return NIF_OK;
+}
+
+extern "C" int nif_trunk_kernel_path(const nif_trunk_desc_t* d) {
+  Plan pl;
+  int rc = trunk_plan(d, &pl);
+  if (rc) return rc;
+  return trunk_tc(d) ? 3 : 0;
 }
 
 extern "C" int nif_trunk_forward(const nif_trunk_desc_t* d, int64_t B, const float* p_in, const float* theta, float* z,
@@ -264,6 +287,9 @@ extern "C" int nif_trunk_forward(const nif_trunk_desc_t* d, int64_t B, const flo
   if (B < 0) { nif_set_error("nif_trunk_forward: B=%lld", (long long)B); return NIF_E_BAD_ARG; }
   if (B == 0) return NIF_OK;
   NIF_REQUIRE_PTR(p_in); NIF_REQUIRE_PTR(theta); NIF_REQUIRE_PTR(z); NIF_OPTIONAL_PTR(save); NIF_REQUIRE_PTR(packed);
+  if (trunk_tc(d))
+    return nif_trunk_tc_forward_impl(d->pi, d->latent, d->units, d->nlayers, d->act, B, p_in, theta, z, save, packed,
+                                     static_cast<cudaStream_t>(stream));
   return nif_trunk_forward_impl(pl, B, p_in, theta, z, save, packed, static_cast<cudaStream_t>(stream));
 }
 
@@ -277,6 +303,9 @@ extern "C" int nif_trunk_backward(const nif_trunk_desc_t* d, int64_t B, const fl
   if (B == 0) return NIF_OK;
   NIF_REQUIRE_PTR(p_in); NIF_REQUIRE_PTR(theta); NIF_REQUIRE_PTR(save); NIF_REQUIRE_PTR(dz);
   NIF_REQUIRE_PTR(g_theta); NIF_REQUIRE_PTR(packed); NIF_REQUIRE_PTR(ws);
+  if (trunk_tc(d))
+    return nif_trunk_tc_backward_impl(d->pi, d->latent, d->units, d->nlayers, d->act, B, p_in, save, dz, g_theta, beta,
+                                      packed, ws, static_cast<cudaStream_t>(stream));
   return nif_trunk_backward_impl(pl, B, p_in, theta, save, dz, g_theta, beta, packed, ws,
                                  static_cast<cudaStream_t>(stream));
 }

@@ -247,6 +247,8 @@ class FusedTrunk:
         check(_lib.lib().nif_trunk_query(C.byref(self.desc), 0, C.byref(nt), C.byref(sv), C.byref(pk), None),
               "nif_trunk_query")
         self.n_theta, self.save_floats_per_row, self.packed_floats = int(nt.value), int(sv.value), int(pk.value)
+        # "bf16x3": tcgen05 tensor cores, fp32-grade three-way bf16 split | "fp32": CUDA-core tile kernels
+        self.kernel_path = "bf16x3" if _lib.lib().nif_trunk_kernel_path(C.byref(self.desc)) == 3 else "fp32"
         self._ws = None
         self._packed = None
 
@@ -259,7 +261,8 @@ class FusedTrunk:
         p_in = _f32c(p_in, "p_in")
         B = p_in.shape[0]
         z = torch.empty(B, self.latent, dtype=torch.float32, device=p_in.device)
-        stash = torch.empty(self.save_floats_per_row * B, dtype=torch.float32, device=p_in.device) if save else None
+        stash = (torch.empty(self.save_floats_per_row * ((B + 63) // 64 * 64), dtype=torch.float32, device=p_in.device)
+                 if save else None)
         check(_lib.lib().nif_trunk_forward(C.byref(self.desc), B, _ptr(p_in), _ptr(theta), _ptr(z), _ptr(stash),
                                            _ptr(self._packed_buf(p_in.device)), _stream()), "nif_trunk_forward")
         return (z, stash) if save else z

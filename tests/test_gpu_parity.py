@@ -396,7 +396,10 @@ def test_tc_forward_and_stash(variant, si, so, n, l, K, B):
 # fused ParameterNet trunk and the whole optimisation step
 # --------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("pi,K,n_st,l_st,act,B", [(1, 32, 64, 4, "swish", 700), (1, 1, 30, 2, "swish", 300),
-                                                  (2, 5, 17, 1, "tanh", 129), (3, 64, 64, 0, "relu", 50)])
+                                                  (2, 5, 17, 1, "tanh", 129), (3, 64, 64, 0, "relu", 50),
+                                                  (8, 64, 64, 4, "sigmoid", 1000),      # widest shapes of the tensor-core trunk
+                                                  (1, 32, 64, 4, "swish", 65536),       # the benchmark batch
+                                                  (1, 16, 48, 2, "swish", 700000)])     # > 32 tiles per CTA: accumulators flushed
 def test_fused_trunk_matches_oracle(pi, K, n_st, l_st, act, B):
     from nif_b200.ops import FusedTrunk
     dev = torch.device("cuda:0")
@@ -416,6 +419,7 @@ def test_fused_trunk_matches_oracle(pi, K, n_st, l_st, act, B):
     theta = torch.cat([prm[k].reshape(-1) for k in order]).float().to(dev)
     tr = FusedTrunk(pi, K, n_st, l_st, act)
     assert tr.n_theta == theta.numel()
+    assert tr.kernel_path == ("bf16x3" if 1 <= l_st <= 4 else "fp32")  # tcgen05 trunk kernels wherever they are built
     z, stash = tr.forward(p_in.float().to(dev), theta, save=True)
     assert torch.equal(z, tr.forward(p_in.float().to(dev), theta))
     assert _gate(rel_err(z.cpu(), z64.detach()), rel_err(z32, z64.detach()))
