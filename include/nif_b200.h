@@ -168,6 +168,24 @@ int nif_adam_step(int64_t n, float* p, const float* g, float* m, float* v, doubl
 int nif_adam_step_dev(int64_t n, float* p, const float* g, float* m, float* v, const float* alpha_dev,
                       double b1, double b2, double eps, float l1, float l2, float g_scale, void* stream);
 
+/* AdaBeliefOptimizer (nif/optimizers/external_optimizers.py:321-628; dense update :458-528), the optimiser tutorials 1
+ * and 3 train with:  m = b1 m + (1-b1) g;  v = b2 v + (1-b2)(g-m)^2 + eps;  [amsgrad: vhat = max(vhat, v)];
+ * p -= lr_t * ( rectify ? (sma_t >= sma_threshold ? r_t m^/(sqrt(v^)+eps) : m^) : m^/(sqrt(v^)+eps)  + weight_decay * p ),
+ * m^ = m/(1-b1^t), v^ = v/(1-b2^t).  lr_t is the caller's (warm-up adjusted) learning rate of step t (t >= 1); vhat may be
+ * NULL (amsgrad off).  l1 / l2 / g_scale as in nif_adam_step.  Buffers need 4-byte alignment only. */
+int nif_adabelief_step(int64_t n, float* p, const float* g, float* m, float* v, float* vhat, double lr_t, double b1,
+                       double b2, double eps, int64_t t, int32_t rectify, double sma_threshold, double weight_decay,
+                       float l1, float l2, float g_scale, void* stream);
+
+/* Lion (nif/optimizers/external_optimizers.py:631-735; dense update :681-702):
+ * p -= lr * (sign(b1 m + (1-b1) g) + wd * p);  m = b2 m + (1-b2) g. */
+int nif_lion_step(int64_t n, float* p, const float* g, float* m, double lr, double b1, double b2, double wd, float l1,
+                  float l2, float g_scale, void* stream);
+
+/* Gradient centralisation (nif/optimizers/gtcf.py:27-32): for a gradient of rank >= 2 viewed as [rows, cols] (cols = its
+ * last axis), subtract from every column its mean over the rows, in place. */
+int nif_centralize_gradient(int64_t rows, int64_t cols, float* g, void* stream);
+
 /* ParameterNet trunk (everything before the last linear layer): Dense(act) -> nlayers x MLP_SimpleShortCut ->
  * Dense(latent), i.e. _call_parameter_net up to the bottleneck (nif/model.py:326-343, 176-216, 668-720;
  * nif/layers/mlp.py:148-160).  theta is the trunk's weight vector in the column order

@@ -10,11 +10,11 @@ from .ops import FusedShapeNet, adam_step, fused_shapenet  # noqa: F401
 
 __all__ = ["FusedShapeNet", "fused_shapenet", "adam_step"]
 
-from .model import NIF, NIFMultiScale  # noqa: E402,F401
+from .model import NIF, NIFMultiScale, NIFMultiScaleLastLayerParameterized  # noqa: E402,F401
 from .keras_like import Adam, Callback, Dataset, LearningRateScheduler, Model, SobolevMSE  # noqa: E402,F401
 from .layers import HessianLayer, JacobianLayer  # noqa: E402,F401
 from .distributed import DataParallel  # noqa: E402,F401
-from . import data, demo  # noqa: E402,F401
+from . import data, demo, optimizers  # noqa: E402,F401
 
-__all__ += ["NIF", "NIFMultiScale", "Adam", "Callback", "Dataset", "LearningRateScheduler", "Model",
+__all__ += ["NIF", "NIFMultiScale", "NIFMultiScaleLastLayerParameterized", "optimizers", "Adam", "Callback", "Dataset", "LearningRateScheduler", "Model",
             "DataParallel", "data", "demo", "SobolevMSE", "JacobianLayer", "HessianLayer"]

@@ -1,0 +1,119 @@
+// Optimisers of nif/optimizers beyond Adam, on the flat fp32 parameter / gradient / slot buffers (HBM-bound, one launch):
+//   AdaBeliefOptimizer  nif/optimizers/external_optimizers.py:321-628  (_resource_apply_dense :458-528)
+//   Lion                nif/optimizers/external_optimizers.py:631-735  (_resource_apply_dense :681-702)
+//   gradient centralisation  nif/optimizers/gtcf.py:7-67 (get_centralized_gradients :27-32)
+// Every step-dependent scalar (bias corrections, warm-up learning rate, the rectification term) is formed on the host in
+// double, as the reference forms them in the variable dtype once per step.
+#include <cmath>
+#include "nif_common.cuh"
+
+// g_scale multiplies the gradient first (data parallel: 1 / world_size); l1 / l2: Keras kernel regularisers folded in
+__global__ void __launch_bounds__(256) nif_adabelief_kernel(long long n, float* __restrict__ p, const float* __restrict__ g,
+                                                            float* __restrict__ m, float* __restrict__ v,
+                                                            float* __restrict__ vhat, float lr_t, float b1, float b2,
+                                                            float eps, float inv_bc1, float inv_bc2, float r_t, int mode,
+                                                            float wd, float l1, float l2, float gs) {
+  // mode: 0 = m_corr / (v_corr + eps)   1 = rectified, SMA above threshold: r_t * that   2 = rectified, below: m_corr
+  const long long stride = 256LL * gridDim.x;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += stride) {
+    float pp = p[i], gg = g[i] * gs;
+    if (l1 != 0.f) gg += l1 * (pp > 0.f ? 1.f : (pp < 0.f ? -1.f : 0.f));
+    if (l2 != 0.f) gg += 2.f * l2 * pp;
+    const float mt = b1 * m[i] + (1.f - b1) * gg;
+    const float d = gg - mt;
+    float vt = b2 * v[i] + (1.f - b2) * d * d + eps;
+    m[i] = mt;
+    v[i] = vt;
+    if (vhat) { vt = fmaxf(vhat[i], vt); vhat[i] = vt; }
+    const float m_corr = mt * inv_bc1;
+    const float v_corr = sqrtf(vt * inv_bc2);
+    float upd = mode == 2 ? m_corr : m_corr / (v_corr + eps);
+    if (mode == 1) upd *= r_t;
+    if (wd != 0.f) upd += wd * pp;
+    p[i] = pp - lr_t * upd;
+  }
+}
+
+__global__ void __launch_bounds__(256) nif_lion_kernel(long long n, float* __restrict__ p, const float* __restrict__ g,
+                                                       float* __restrict__ m, float lr, float b1, float b2, float wd,
+                                                       float l1, float l2, float gs) {
+  const long long stride = 256LL * gridDim.x;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += stride) {
+    float pp = p[i], gg = g[i] * gs;
+    if (l1 != 0.f) gg += l1 * (pp > 0.f ? 1.f : (pp < 0.f ? -1.f : 0.f));
+    if (l2 != 0.f) gg += 2.f * l2 * pp;
+    const float mm = m[i];
+    const float c = mm * b1 + gg * (1.f - b1);
+    const float sgn = c > 0.f ? 1.f : (c < 0.f ? -1.f : 0.f);
+    p[i] = pp - lr * (sgn + pp * wd);
+    m[i] = mm * b2 + gg * (1.f - b2);
+  }
+}
+
+// grad[rows][cols] -= mean over rows (every axis but the last of a rank >= 2 gradient); one thread per column
+__global__ void __launch_bounds__(256) nif_centralize_kernel(long long rows, long long cols, float* __restrict__ g) {
+  const long long c = blockIdx.x * 256LL + threadIdx.x;
+  if (c >= cols) return;
+  float s = 0.f;
+  for (long long r = 0; r < rows; ++r) s += g[r * cols + c];
+  const float mean = s / (float)rows;
+  for (long long r = 0; r < rows; ++r) g[r * cols + c] -= mean;
+}
+
+static unsigned blocks_for(long long n) {
+  long long nblk = (n + 255) / 256;
+  if (nblk < 1) nblk = 1;
+  if (nblk > 148 * 16) nblk = 148 * 16;
+  return (unsigned)nblk;
+}
+
+extern "C" int nif_adabelief_step(int64_t n, float* p, const float* g, float* m, float* v, float* vhat, double lr_t,
+                                  double b1, double b2, double eps, int64_t t, int32_t rectify, double sma_threshold,
+                                  double weight_decay, float l1, float l2, float g_scale, void* stream) {
+  if (n < 0 || t < 1) { nif_set_error("nif_adabelief_step: n=%lld t=%lld", (long long)n, (long long)t); return NIF_E_BAD_ARG; }
+  if (n == 0) return NIF_OK;
+  if (!p || !g || !m || !v) { nif_set_error("nif_adabelief_step: null buffer"); return NIF_E_BAD_ARG; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const double b1p = std::pow(b1, (double)t), b2p = std::pow(b2, (double)t);
+  const double sma_inf = 2.0 / (1.0 - b2) - 1.0;
+  const double sma_t = sma_inf - 2.0 * (double)t * b2p / (1.0 - b2p);
+  int mode = 0;
+  double r_t = 1.0;
+  if (rectify) {
+    if (sma_t >= sma_threshold) {
+      mode = 1;
+      r_t = std::sqrt((sma_t - 4.0) / (sma_inf - 4.0) * (sma_t - 2.0) / (sma_inf - 2.0) * sma_inf / sma_t);
+    } else {
+      mode = 2;
+    }
+  }
+  { NIF_PROF("nif_adabelief_kernel", st);
+    nif_adabelief_kernel<<<blocks_for(n), 256, 0, st>>>(n, p, g, m, v, vhat, (float)lr_t, (float)b1, (float)b2, (float)eps,
+                                                        (float)(1.0 / (1.0 - b1p)), (float)(1.0 / (1.0 - b2p)), (float)r_t, mode,
+                                                        (float)weight_decay, l1, l2, g_scale); }
+  NIF_CUDA_CHECK(cudaGetLastError());
+  return NIF_OK;
+}
+
+extern "C" int nif_lion_step(int64_t n, float* p, const float* g, float* m, double lr, double b1, double b2, double wd,
+                             float l1, float l2, float g_scale, void* stream) {
+  if (n < 0) { nif_set_error("nif_lion_step: n=%lld", (long long)n); return NIF_E_BAD_ARG; }
+  if (n == 0) return NIF_OK;
+  if (!p || !g || !m) { nif_set_error("nif_lion_step: null buffer"); return NIF_E_BAD_ARG; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  { NIF_PROF("nif_lion_kernel", st);
+    nif_lion_kernel<<<blocks_for(n), 256, 0, st>>>(n, p, g, m, (float)lr, (float)b1, (float)b2, (float)wd, l1, l2, g_scale); }
+  NIF_CUDA_CHECK(cudaGetLastError());
+  return NIF_OK;
+}
+
+extern "C" int nif_centralize_gradient(int64_t rows, int64_t cols, float* g, void* stream) {
+  if (rows < 0 || cols < 0) { nif_set_error("nif_centralize_gradient: rows=%lld cols=%lld", (long long)rows, (long long)cols); return NIF_E_BAD_ARG; }
+  if (rows == 0 || cols == 0) return NIF_OK;
+  if (!g) { nif_set_error("nif_centralize_gradient: null buffer"); return NIF_E_BAD_ARG; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  { NIF_PROF("nif_centralize_kernel", st);
+    nif_centralize_kernel<<<(unsigned)((cols + 255) / 256), 256, 0, st>>>(rows, cols, g); }
+  NIF_CUDA_CHECK(cudaGetLastError());
+  return NIF_OK;
+}

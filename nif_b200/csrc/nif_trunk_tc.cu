@@ -133,6 +133,37 @@ __global__ void __launch_bounds__(256) nif_trunk_tc_pack_kernel(const TrunkGeo g
   }
 }
 
+// value and first derivative of 8 activations at once, branch-free and inline: with two epilogue warps per scheduler the
+// kernel is bound by instruction latency, so the eight independent chains have to interleave (the out-of-line act_fd4 of
+// the CUDA-core kernels serialises four).  exp via ex2.approx (relative error 2^-22), 1/(1+e) via the approximate
+// reciprocal (2 ulp): far inside the 1e-5 parity gate.
+template <int ACT>
+__device__ __forceinline__ void trunk_act8(const float (&v)[8], float (&f)[8], float (&d)[8]) {
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const float x = v[e];
+    if (ACT == NIF_ACT_SWISH) {
+      const float sg = __fdividef(1.f, 1.f + __expf(-x));
+      f[e] = x * sg;
+      d[e] = sg * fmaf(x, 1.f - sg, 1.f);
+    } else if (ACT == NIF_ACT_SIGMOID) {
+      const float sg = __fdividef(1.f, 1.f + __expf(-x));
+      f[e] = sg;
+      d[e] = sg * (1.f - sg);
+    } else if (ACT == NIF_ACT_TANH) {
+      const float t = tanhf(x);
+      f[e] = t;
+      d[e] = fmaf(-t, t, 1.f);
+    } else if (ACT == NIF_ACT_RELU) {
+      f[e] = x > 0.f ? x : 0.f;
+      d[e] = x > 0.f ? 1.f : 0.f;
+    } else {
+      f[e] = x;
+      d[e] = 1.f;
+    }
+  }
+}
+
 // ---- forward -----------------------------------------------------------------------------------------------------------
 struct TrunkFwdArgs {
   long long B, total_pairs;
@@ -145,6 +176,7 @@ __host__ __device__ inline size_t tkf_smem_bytes(const TrunkGeo& g) {
   return (size_t)g.f_bytes + 2 * 3 * 16384 + (size_t)(g.pi * 64 + (g.l + 1) * 64 + g.KB) * 4 + 128;
 }
 
+template <int ACT>
 __global__ void __launch_bounds__(TKF_THREADS, 1) nif_trunk_tc_fwd_kernel(const TrunkGeo g, const TrunkFwdArgs a) {
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char* Wimg = smem;                       // forward image, resident
@@ -250,22 +282,21 @@ __global__ void __launch_bounds__(TKF_THREADS, 1) nif_trunk_tc_fwd_kernel(const 
         for (int i = 0; i < NIF_MAX_SI; ++i) pv[i] = (i < pi && live) ? __ldg(&a.p_in[b * pi + i]) : 0.f;
         float dv[64];
 #pragma unroll
-        for (int c = 0; c < 16; ++c) {
-          float pre[4];
+        for (int c = 0; c < 8; ++c) {
+          float pre[8], f8[8], d8[8];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            float s = bs[4 * c + e];
+          for (int e = 0; e < 8; ++e) {
+            float s = bs[8 * c + e];
 #pragma unroll
-            for (int i = 0; i < NIF_MAX_SI; ++i) if (i < pi) s = fmaf(pv[i], W0s[i * 64 + 4 * c + e], s);
+            for (int i = 0; i < NIF_MAX_SI; ++i) if (i < pi) s = fmaf(pv[i], W0s[i * 64 + 8 * c + e], s);
             pre[e] = s;
           }
-          float f4[4], d4[4];
-          act_fd4(g.act, pre, f4, d4);
+          trunk_act8<ACT>(pre, f8, d8);
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const bool pad = 4 * c + e >= n;
-            h[4 * c + e] = pad ? 0.f : f4[e];
-            dv[4 * c + e] = pad ? 0.f : d4[e];
+          for (int e = 0; e < 8; ++e) {
+            const bool pad = 8 * c + e >= n;
+            h[8 * c + e] = pad ? 0.f : f8[e];
+            dv[8 * c + e] = pad ? 0.f : d8[e];
           }
         }
         stash(0, dv);
@@ -283,17 +314,17 @@ __global__ void __launch_bounds__(TKF_THREADS, 1) nif_trunk_tc_fwd_kernel(const 
           tc_ld32(tm + (uint32_t)(q * 32), v);
           tc_wait_ld();
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            float pre[4], f4[4], d4[4];
+          for (int c = 0; c < 4; ++c) {
+            float pre[8], f8[8], d8[8];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) pre[e] = v[4 * c + e] + bs[k * 64 + q * 32 + 4 * c + e];
-            act_fd4(g.act, pre, f4, d4);
+            for (int e = 0; e < 8; ++e) pre[e] = v[8 * c + e] + bs[k * 64 + q * 32 + 8 * c + e];
+            trunk_act8<ACT>(pre, f8, d8);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int j = q * 32 + 4 * c + e;
+            for (int e = 0; e < 8; ++e) {
+              const int j = q * 32 + 8 * c + e;
               const bool pad = j >= n;
-              h[j] = pad ? 0.f : h[j] + f4[e];
-              dv[j] = pad ? 0.f : d4[e];
+              h[j] = pad ? 0.f : h[j] + f8[e];
+              dv[j] = pad ? 0.f : d8[e];
             }
           }
         }
@@ -331,38 +362,44 @@ struct TrunkBwdArgs {
   int nflush;      // partial sets per CTA
   int flush_tiles; // tiles per accumulation chain
 };
-#define TKB_THREADS 192
+#define TKB_THREADS 320
 #define TKB_DA_PART 16384u   // [64 mn (j) x 128 k (b)] bf16
-#define TKB_A_PART 32768u    // [128 mn x 128 k (b)] bf16
+#define TKB_A_PART 20480u    // [80 mn x 128 k (b)] bf16: the rows the batch reduction needs (see below)
 #define TKB_W_STAGE 24576u   // 3 parts x 8 KB
 
-__host__ __device__ inline size_t tkb_smem_bytes() { return 3 * TKB_DA_PART + 3 * TKB_A_PART + 2 * TKB_W_STAGE + 256; }
+__host__ __device__ inline size_t tkb_smem_bytes() { return 3 * TKB_DA_PART + 2 * 3 * TKB_A_PART + 2 * TKB_W_STAGE + 256; }
 
+// Two threads per row: thread (r, half) owns row r (TMEM lane r) and the columns [32 half, 32 half + 32) of everything it
+// drains or writes.  Warps 0-3: half 0, warps 4-7: half 1, warp 8: MMA issuer, warp 9: weight stream.
 __global__ void __launch_bounds__(TKB_THREADS, 1) nif_trunk_tc_bwd_kernel(const TrunkGeo g, const TrunkBwdArgs a) {
   extern __shared__ __align__(1024) unsigned char smem[];
   // da tile (3 parts):  offset(j, b) = (j/8) * 2048 + (b/8) * 128 + (b%8) * 16 + (j%8) * 2
   //   as B, MN-major (N = j, K = b):  LBO = 128, SBO = 2048;   as A, K-major (M = b, K = j):  LBO = 2048, SBO = 128
   unsigned char* DA = smem;
-  // A tile (3 parts), MN-major [128 mn x 128 k (b)], same strides: mn < 64: h_{m-1}[b][mn]; mn = 64: 1; mn = 65 + i: p_in[b][i]
+  // A tile, two buffers x 3 parts, MN-major [mn x 128 k (b)], same strides: mn < 64: h_{m-1}[b][mn]; mn = 64: 1;
+  // mn = 65 + i: p_in[b][i].  The M = 128 instruction also reads rows 80..127, i.e. the 12 KB behind each 20 KB part: whatever
+  // bytes lie there only reach accumulator rows 80..127, which nobody reads (TMEM lanes are independent).
   unsigned char* AT = smem + 3 * TKB_DA_PART;
-  unsigned char* Wst = AT + 3 * TKB_A_PART;  // [2] stages of natural-layout weights (3 parts)
+  unsigned char* Wst = AT + 2 * 3 * TKB_A_PART;  // [2] stages of natural-layout weights (3 parts)
   uint64_t* bars = reinterpret_cast<uint64_t*>(Wst + 2 * TKB_W_STAGE);
   uint64_t* w_full = bars;       // [2]
   uint64_t* w_empty = bars + 2;  // [2]
   uint64_t* a_ready = bars + 4;  // tiles written
   uint64_t* d_full = bars + 5;   // data-path accumulator ready
-  uint64_t* w_done = bars + 6;   // every MMA of the step has completed: tiles may be rewritten
+  uint64_t* w_done = bars + 6;   // every MMA of the step has completed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n = g.n, l = g.l, K = g.K, KB = g.KB, pi = g.pi;
 
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-    mbar_init(a_ready, 128); mbar_init(d_full, 1); mbar_init(w_done, 1);
+    mbar_init(a_ready, 256); mbar_init(d_full, 1); mbar_init(w_done, 1);
     mbar_fence_init();
   }
-  if (warp == 4) tc_alloc(tmem_slot, 512);
-  for (int e = tid; e < (int)(3 * TKB_A_PART / 16); e += TKB_THREADS) reinterpret_cast<uint4*>(AT)[e] = make_uint4(0, 0, 0, 0);
+  if (warp == 8) tc_alloc(tmem_slot, 512);
+  // everything the tensor core may read as operand rows must be finite: clear the A buffers and the weight stages once
+  for (int e = tid; e < (int)((2 * 3 * TKB_A_PART + 2 * TKB_W_STAGE) / 16); e += TKB_THREADS)
+    reinterpret_cast<uint4*>(AT)[e] = make_uint4(0, 0, 0, 0);
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -375,7 +412,7 @@ __global__ void __launch_bounds__(TKB_THREADS, 1) nif_trunk_tc_bwd_kernel(const 
   if ((long long)blockIdx.x < a.total_tiles) my_tiles = (a.total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
   const int steps = l + 2;  // per tile: bottleneck, layers l..1, layer 0
 
-  if (warp == 5) {
+  if (warp == 9) {
     if (lane == 0) {  // natural-layout weights, one stage per step that has a data product (bottleneck, layers l..1)
       const unsigned char* src = reinterpret_cast<const unsigned char*>(a.packed) + g.f_bytes;
       uint32_t s = 0, ph = 0;
@@ -389,20 +426,20 @@ __global__ void __launch_bounds__(TKB_THREADS, 1) nif_trunk_tc_bwd_kernel(const 
           if (++s == 2) { s = 0; ph ^= 1u; }
         }
     }
-  } else if (warp == 4) {
+  } else if (warp == 8) {
     // ---------------- MMA issuer ----------------
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
     const uint64_t dA_k = tk_desc(smem_u32(DA), 2048, 128);    // da tile as K-major A (M = b, K = j)
     const uint64_t dB_mn = tk_desc(smem_u32(DA), 128, 2048);   // da tile as MN-major B (N = j, K = b)
-    const uint64_t dAT = tk_desc(smem_u32(AT), 128, 2048);     // MN-major A (M = mn, K = b)
-    uint32_t s = 0, wph = 0, aph = 0;
+    uint32_t s = 0, wph = 0, aph = 0, gs = 0;
     for (long long t = 0; t < my_tiles; ++t) {
       const bool fresh = (t % a.flush_tiles) == 0;
-      for (int st = 0; st < steps; ++st, aph ^= 1u) {
+      for (int st = 0; st < steps; ++st, aph ^= 1u, ++gs) {
         mbar_wait(a_ready, aph);
         const bool has_data = st <= l;
         if (has_data) mbar_wait(&w_full[s], wph);
         tc_fence_after();
+        const uint64_t dAT = tk_desc(smem_u32(AT + (gs & 1u) * 3 * TKB_A_PART), 128, 2048);  // MN-major A (M = mn, K = b)
         if (tc_elect_one()) {
           if (has_data) {
             // dh (+)= da @ W^T : A = da tile (K-major view), B = natural weights [64 rows i x K extent]
@@ -424,130 +461,113 @@ __global__ void __launch_bounds__(TKB_THREADS, 1) nif_trunk_tc_bwd_kernel(const 
       }
     }
   } else {
-    // ---------------- epilogue warps: thread = row r of the tile = TMEM lane r ----------------
-    const int r = tid;
-    const uint32_t tm = tmem + ((uint32_t)(warp * 32) << 16);
+    // ---------------- epilogue warps ----------------
+    const int r = tid & 127, half = tid >> 7;
+    const uint32_t tm = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     const uint32_t koff = (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 16u;  // this row's position along k = b
     const long long slot_floats = nif_tiled_rows(a.B) * 64;
-    uint32_t dph = 0, wdph = 0;
-    bool first_step = true;  // no MMA has been issued yet: nothing to wait for before the first tile write
-    auto wait_tiles_free = [&]() {
+    uint32_t dph = 0, wdph = 0, gs = 0;  // gs: global step counter (selects the A buffer)
+    bool first_step = true;  // no MMA is in flight: nothing to wait for before writing
+    auto wait_mmas = [&]() {  // every MMA issued so far has completed
       if (!first_step) { mbar_wait(w_done, wdph); wdph ^= 1u; }
       first_step = false;
     };
-    // write 64 values v[j] of this row into the da tile (3 parts); ng groups of 8
-    auto put_da = [&](const float (&v)[64], int ng) {
+    // 8 values -> group `grp` (8 consecutive mn) of a 3-part tile at `base`, parts `pstride` bytes apart
+    auto put8 = [&](unsigned char* base, uint32_t pstride, int grp, const float (&w8)[8]) {
+      uint4 q0, q1, q2;
+      bf3_split8(w8, q0, q1, q2);
+      *reinterpret_cast<uint4*>(base + grp * 2048 + koff) = q0;
+      *reinterpret_cast<uint4*>(base + pstride + grp * 2048 + koff) = q1;
+      *reinterpret_cast<uint4*>(base + 2 * pstride + grp * 2048 + koff) = q2;
+    };
+    // this thread's half of the stashed row of slot `slot`: 8 quads -> 32 floats
+    auto load_half = [&](int slot, long long b, bool live, float (&v)[32]) {
+      const float* src = a.save + (long long)slot * slot_floats + nif_tiled_row(b) + (long long)(half * 8) * 128;
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
-        if (c >= ng) break;
-        const float w8[8] = {v[8 * c], v[8 * c + 1], v[8 * c + 2], v[8 * c + 3], v[8 * c + 4], v[8 * c + 5], v[8 * c + 6], v[8 * c + 7]};
-        uint4 q0, q1, q2;
-        bf3_split8(w8, q0, q1, q2);
-        *reinterpret_cast<uint4*>(DA + c * 2048 + koff) = q0;
-        *reinterpret_cast<uint4*>(DA + TKB_DA_PART + c * 2048 + koff) = q1;
-        *reinterpret_cast<uint4*>(DA + 2 * TKB_DA_PART + c * 2048 + koff) = q2;
+        float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (live) q = ldg4(src + c * 128);
+        v[4 * c] = q.x; v[4 * c + 1] = q.y; v[4 * c + 2] = q.z; v[4 * c + 3] = q.w;
       }
     };
-    // write the stashed row h_m (slot m) into rows mn < 64 of the A tile
-    auto put_h = [&](int m, long long b, bool live) {
-      const float* hs = a.save + (long long)m * slot_floats + nif_tiled_row(b);
+    // rows mn = 32 half .. of A buffer `buf` := v (this thread's 32 columns of h)
+    auto put_h = [&](uint32_t buf, const float (&v)[32]) {
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        float4 p0 = make_float4(0.f, 0.f, 0.f, 0.f), p1 = p0;
-        if (live) { p0 = ldg4(hs + (2 * c) * 128); p1 = ldg4(hs + (2 * c + 1) * 128); }
-        const float w8[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
-        uint4 q0, q1, q2;
-        bf3_split8(w8, q0, q1, q2);
-        *reinterpret_cast<uint4*>(AT + c * 2048 + koff) = q0;
-        *reinterpret_cast<uint4*>(AT + TKB_A_PART + c * 2048 + koff) = q1;
-        *reinterpret_cast<uint4*>(AT + 2 * TKB_A_PART + c * 2048 + koff) = q2;
+      for (int c = 0; c < 4; ++c) {
+        const float w8[8] = {v[8 * c], v[8 * c + 1], v[8 * c + 2], v[8 * c + 3], v[8 * c + 4], v[8 * c + 5], v[8 * c + 6], v[8 * c + 7]};
+        put8(AT + buf * 3 * TKB_A_PART, TKB_A_PART, half * 4 + c, w8);
       }
     };
     long long flush_idx = 0;
     for (long long t = 0; t < my_tiles; ++t) {
       const long long b = (blockIdx.x + t * gridDim.x) * 128 + r;
       const bool live = b < a.B;
-      // ---- step 0: da tile := dz (KB columns), A tile := [h_l | 1 | p_in] ----
-      float dzv[64];
+      // ---- step 0: da tile := dz (KB columns), A buffer := [h_l | 1 | p_in]; the [1 | p_in] rows go into both buffers ----
+      float hv[32];
+      load_half(l, b, live, hv);
+      float ev[8];  // half 0: rows 64..71 = [1, p_0 .. p_6];  half 1: rows 72..79 = [p_7, 0 ..]
 #pragma unroll
-      for (int e = 0; e < 64; ++e) dzv[e] = 0.f;
-      if (live) {
-        if ((K & 3) == 0) {
-#pragma unroll
-          for (int k4 = 0; k4 < 64; k4 += 4) {
-            if (k4 < K) {
-              const float4 q = ldg4(a.dz + b * K + k4);
-              dzv[k4] = q.x; dzv[k4 + 1] = q.y; dzv[k4 + 2] = q.z; dzv[k4 + 3] = q.w;
-            }
-          }
-        } else {
-#pragma unroll
-          for (int kk = 0; kk < 64; ++kk) if (kk < K) dzv[kk] = __ldg(&a.dz[b * K + kk]);
-        }
+      for (int e = 0; e < 8; ++e) {
+        const int i = half * 8 + e - 1;  // p_in column
+        ev[e] = !live ? 0.f : (half == 0 && e == 0 ? 1.f : ((i >= 0 && i < pi) ? __ldg(&a.p_in[b * pi + i]) : 0.f));
       }
-      wait_tiles_free();
-      put_da(dzv, KB / 8);
-      put_h(l, b, live);
-      {  // rows 64 .. 64 + pi of the A tile: [1, p_in]; two groups of 8 rows (64..71, 72..79)
-        float ev[16];
+      const int ngz = KB / 16;  // groups of 8 dz columns per half
+      float dzv[32];
 #pragma unroll
-        for (int e = 0; e < 16; ++e) ev[e] = 0.f;
-        if (live) {
-          ev[0] = 1.f;
-#pragma unroll
-          for (int i = 0; i < NIF_MAX_SI; ++i) if (i < pi) ev[1 + i] = __ldg(&a.p_in[b * pi + i]);
-        }
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          const float w8[8] = {ev[8 * c], ev[8 * c + 1], ev[8 * c + 2], ev[8 * c + 3], ev[8 * c + 4], ev[8 * c + 5], ev[8 * c + 6], ev[8 * c + 7]};
-          uint4 q0, q1, q2;
-          bf3_split8(w8, q0, q1, q2);
-          *reinterpret_cast<uint4*>(AT + (8 + c) * 2048 + koff) = q0;
-          *reinterpret_cast<uint4*>(AT + TKB_A_PART + (8 + c) * 2048 + koff) = q1;
-          *reinterpret_cast<uint4*>(AT + 2 * TKB_A_PART + (8 + c) * 2048 + koff) = q2;
-        }
+      for (int e = 0; e < 32; ++e) {
+        const int kk = half * 8 * ngz + e;
+        dzv[e] = (live && e < 8 * ngz && kk < K) ? __ldg(&a.dz[b * K + kk]) : 0.f;
       }
+      wait_mmas();
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (c >= ngz) break;
+        const float w8[8] = {dzv[8 * c], dzv[8 * c + 1], dzv[8 * c + 2], dzv[8 * c + 3], dzv[8 * c + 4], dzv[8 * c + 5], dzv[8 * c + 6], dzv[8 * c + 7]};
+        put8(DA, TKB_DA_PART, half * ngz + c, w8);
+      }
+      put_h(gs & 1u, hv);
+      put8(AT, TKB_A_PART, 8 + half, ev);
+      put8(AT + 3 * TKB_A_PART, TKB_A_PART, 8 + half, ev);
       fence_async_smem();
       mbar_arrive(a_ready);
+      ++gs;
 
-      float dh[64];
+      float dh[32];
       // ---- steps 1 .. l+1: layer m = l .. 0 ----
 #pragma unroll 1
-      for (int m = l; m >= 0; --m) {
-        // act'(pre_m) of this row, fetched before the accumulator wait
-        float dv[64];
-        {
-          const float* ds = a.save + (long long)(l + 1 + m) * slot_floats + nif_tiled_row(b);
-#pragma unroll
-          for (int c = 0; c < 16; ++c) {
-            float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (live) q = ldg4(ds + c * 128);
-            dv[4 * c] = q.x; dv[4 * c + 1] = q.y; dv[4 * c + 2] = q.z; dv[4 * c + 3] = q.w;
-          }
+      for (int m = l; m >= 0; --m, ++gs) {
+        // this step's stash rows, fetched before any wait: act'(pre_m) and (m >= 1) the layer input h_{m-1}
+        float dv[32];
+        load_half(l + 1 + m, b, live, dv);
+        if (m >= 1) {
+          load_half(m - 1, b, live, hv);
+          put_h(gs & 1u, hv);  // the other A buffer: its last reader (two steps back) finished before the previous da write
         }
-        // dh_m: the data-path accumulator of the previous step (shortcut: dh_{m} = dh_{m+1} + da_{m+1} W_{m+1}^T)
+        // dh_m: the data-path accumulator of the previous step (shortcut: dh_m = dh_{m+1} + da_{m+1} W_{m+1}^T)
         mbar_wait(d_full, dph);
         dph ^= 1u;
         tc_fence_after();
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
+        {
           float v[32];
-          tc_ld32(tm + (uint32_t)(q * 32), v);
+          tc_ld32(tm + (uint32_t)(half * 32), v);
           tc_wait_ld();
 #pragma unroll
-          for (int e = 0; e < 32; ++e) dh[q * 32 + e] = (m == l) ? v[e] : dh[q * 32 + e] + v[e];
+          for (int e = 0; e < 32; ++e) dh[e] = (m == l) ? v[e] : dh[e] + v[e];
         }
         tc_fence_before();
 #pragma unroll
-        for (int e = 0; e < 64; ++e) dv[e] *= dh[e];  // da_m
-        wait_tiles_free();
-        put_da(dv, 8);
-        if (m >= 1) put_h(m - 1, b, live);
+        for (int e = 0; e < 32; ++e) dv[e] *= dh[e];  // da_m
+        wait_mmas();  // the da tile is free
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float w8[8] = {dv[8 * c], dv[8 * c + 1], dv[8 * c + 2], dv[8 * c + 3], dv[8 * c + 4], dv[8 * c + 5], dv[8 * c + 6], dv[8 * c + 7]};
+          put8(DA, TKB_DA_PART, half * 4 + c, w8);
+        }
         fence_async_smem();
         mbar_arrive(a_ready);
       }
 
-      // ---- end of an accumulation chain: accumulators -> this CTA's partial ----
+      // ---- end of an accumulation chain: accumulators -> this CTA's partial (each half drains its columns) ----
       if ((t + 1) % a.flush_tiles == 0 || t + 1 == my_tiles) {
         mbar_wait(w_done, wdph);
         wdph ^= 1u;
@@ -556,12 +576,12 @@ __global__ void __launch_bounds__(TKB_THREADS, 1) nif_trunk_tc_bwd_kernel(const 
         float* part = a.part + ((long long)blockIdx.x * a.nflush + flush_idx) * g.P;
         ++flush_idx;
         // bottleneck: rows i < n -> W_b[i][kk], row 64 -> b_b[kk]
-        for (int c0 = 0; c0 < KB; c0 += 16) {
-          float v[16];
-          tc_ld16(tm + col_b + (uint32_t)c0, v);
+        for (int c0 = half * (KB / 2); c0 < (half + 1) * (KB / 2); c0 += 8) {
+          float v[8];
+          tc_ld8(tm + col_b + (uint32_t)c0, v);
           tc_wait_ld();
 #pragma unroll
-          for (int e = 0; e < 16; ++e) {
+          for (int e = 0; e < 8; ++e) {
             const int kk = c0 + e;
             if (kk < K) {
               if (r < n) part[g.off_Wb + (long long)r * K + kk] = v[e];
@@ -570,19 +590,17 @@ __global__ void __launch_bounds__(TKB_THREADS, 1) nif_trunk_tc_bwd_kernel(const 
           }
         }
         for (int m = l; m >= 0; --m) {
-          const uint32_t col = col_m0 + (uint32_t)(l - m) * 64u;
-          for (int c0 = 0; c0 < 64; c0 += 16) {
-            float v[16];
-            tc_ld16(tm + col + (uint32_t)c0, v);
-            tc_wait_ld();
+          const uint32_t col = col_m0 + (uint32_t)(l - m) * 64u + (uint32_t)(half * 32);
+          float v[32];
+          tc_ld32(tm + col, v);
+          tc_wait_ld();
 #pragma unroll
-            for (int e = 0; e < 16; ++e) {
-              const int j = c0 + e;
-              if (j < n) {
-                if (r < n && m >= 1) part[g.off_Wh + (long long)(m - 1) * n * n + (long long)r * n + j] = v[e];
-                else if (r == 64) part[(m == 0 ? g.off_b0 : g.off_bh + (long long)(m - 1) * n) + j] = v[e];
-                else if (m == 0 && r > 64 && r <= 64 + pi) part[(long long)(r - 65) * n + j] = v[e];
-              }
+          for (int e = 0; e < 32; ++e) {
+            const int j = half * 32 + e;
+            if (j < n) {
+              if (r < n && m >= 1) part[g.off_Wh + (long long)(m - 1) * n * n + (long long)r * n + j] = v[e];
+              else if (r == 64) part[(m == 0 ? g.off_b0 : g.off_bh + (long long)(m - 1) * n) + j] = v[e];
+              else if (m == 0 && r > 64 && r <= 64 + pi) part[(long long)(r - 65) * n + j] = v[e];
             }
           }
         }
@@ -592,7 +610,7 @@ __global__ void __launch_bounds__(TKB_THREADS, 1) nif_trunk_tc_bwd_kernel(const 
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tc_dealloc(tmem, 512);
+  if (warp == 8) tc_dealloc(tmem, 512);
 }
 
 // g_theta[e] = beta * g_theta[e] + sum over partials
@@ -648,11 +666,19 @@ int nif_trunk_tc_forward_impl(int pi, int K, int n, int l, int act, long long B,
   a.B = B; a.total_pairs = (B + 255) / 256;
   a.p_in = p_in; a.theta = theta; a.packed = packed; a.z = z; a.save = save;
   const size_t smem = tkf_smem_bytes(g);
-  NIF_CUDA_CHECK(cudaFuncSetAttribute(nif_trunk_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  void (*kern)(const TrunkGeo, const TrunkFwdArgs) = nullptr;
+  switch (act) {
+    case NIF_ACT_SWISH: kern = nif_trunk_tc_fwd_kernel<NIF_ACT_SWISH>; break;
+    case NIF_ACT_SIGMOID: kern = nif_trunk_tc_fwd_kernel<NIF_ACT_SIGMOID>; break;
+    case NIF_ACT_TANH: kern = nif_trunk_tc_fwd_kernel<NIF_ACT_TANH>; break;
+    case NIF_ACT_RELU: kern = nif_trunk_tc_fwd_kernel<NIF_ACT_RELU>; break;
+    default: kern = nif_trunk_tc_fwd_kernel<NIF_ACT_LINEAR>; break;
+  }
+  NIF_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   long long grid = trunk_sms();
   if (grid > a.total_pairs) grid = a.total_pairs;
   if (grid < 1) return NIF_OK;
-  { NIF_PROF("nif_trunk_tc_fwd_kernel", st); nif_trunk_tc_fwd_kernel<<<(unsigned)grid, TKF_THREADS, smem, st>>>(g, a); }
+  { NIF_PROF("nif_trunk_tc_fwd_kernel", st); kern<<<(unsigned)grid, TKF_THREADS, smem, st>>>(g, a); }
   NIF_CUDA_CHECK(cudaGetLastError());
   return NIF_OK;
 }

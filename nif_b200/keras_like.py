@@ -75,7 +75,8 @@ class SobolevMSE:
     with JacobianLayer.as_model(): per row  sum_{c in value_cols} (t_c - p_c)^2 + coef_grad * sum_{c in grad_cols}
     (t_c - p_c)^2, averaged over the batch.  Columns index the concatenated output [y | dy/dx flattened]; the
     tutorial uses value_cols=[0], grad_cols=[2] (u and du/dx; du/dt is only monitored).  Every grad column must be a
-    derivative with respect to the SAME ShapeNet input (that is what the reverse-over-forward kernels differentiate)."""
+    derivative with respect to the SAME ShapeNet input (that is what the reverse-over-forward kernels differentiate).
+    Like the tutorial's `Sobolov_MSE`, each group is a MEAN over its columns (tf.reduce_mean(..., axis=-1))."""
 
     def __init__(self, coef_grad=1e-3, value_cols=(0,), grad_cols=(2,)):
         self.coef_grad = float(coef_grad)
@@ -83,8 +84,8 @@ class SobolevMSE:
         self.grad_cols = [int(c) for c in grad_cols]
 
     def __call__(self, y_true, y_pred):
-        sd = ((y_true[:, self.value_cols] - y_pred[:, self.value_cols]) ** 2).sum(-1)
-        sg = ((y_true[:, self.grad_cols] - y_pred[:, self.grad_cols]) ** 2).sum(-1)
+        sd = ((y_true[:, self.value_cols] - y_pred[:, self.value_cols]) ** 2).mean(-1)
+        sg = ((y_true[:, self.grad_cols] - y_pred[:, self.grad_cols]) ** 2).mean(-1)
         return (sd + self.coef_grad * sg).mean()
 
 
@@ -243,11 +244,14 @@ class Model:
         return {"full": [("input_tot", n.pi_dim + n.si_dim)], "jacobian": [("input_tot", n.pi_dim + n.si_dim)],
                 "p_to_w": [("input_p_to_w", n.pi_dim)],
                 "p_to_lr": [("input_p_to_lr", n.pi_dim)], "lr_to_w": [("input_lr_to_w", n.pi_hidden)],
+                "x_to_phi": [("input_x_to_phi", n.si_dim)],
                 "x_to_u_given_w": [("input_x_to_u_given_w", n.si_dim), ("input_w_and_b_from_pnet", n.po_dim)]}[self.kind]
 
     def count_params(self) -> int:
         n = self.net
         last = n.pi_hidden * n.po_dim + n.po_dim
+        if getattr(n, "_last_layer_only", False):
+            return n._count_params_kind(self.kind)
         return {"full": n.count_params(), "jacobian": n.count_params(), "p_to_w": n.count_params(),
                 "p_to_lr": n.count_params() - last,
                 "lr_to_w": last, "x_to_u_given_w": 0}[self.kind]
@@ -285,6 +289,11 @@ class Model:
     @torch.no_grad()
     def _forward_batch(self, x):
         n = self.net
+        if getattr(n, "_last_layer_only", False):
+            if self.kind == "x_to_u_given_w":
+                xs, w = x
+                return n._forward_kind(self.kind, self._dev(xs), self._dev(w))
+            return n._forward_kind(self.kind, self._dev(x))
         if self.kind == "full":
             inp = self._dev(x)
             z = self._latent_nograd(inp[:, : n.pi_dim])
@@ -433,12 +442,16 @@ class Model:
             raise NifError("only the full model is trainable")
         if optimizer is None:
             optimizer = Adam()
-        if not isinstance(optimizer, Adam):
-            raise NifError("nif_b200 ships Adam (tf.keras semantics); other optimisers are outside the hot path")
+        if not callable(getattr(optimizer, "apply", None)) or not hasattr(optimizer, "learning_rate"):
+            raise NifError("optimizer must be nif_b200.Adam or one of nif_b200.optimizers (AdaBeliefOptimizer, Lion)")
         if not (isinstance(loss, str) and loss in ("mse", "mean_squared_error") or callable(loss)):
             raise NifError("loss must be 'mse' or a callable(y_true, y_pred) -> scalar tensor")
         self.optimizer, self.loss = optimizer, loss
+        # callable metrics(y_true, y_pred) -> scalar are evaluated on every batch's predictions and averaged per epoch
         self.metrics_fns = list(metrics or [])
+        for mfn in self.metrics_fns:
+            if not callable(mfn):
+                raise NifError("metrics must be callables(y_true, y_pred) -> scalar tensor")
 
     def train_on_batch(self, x, y, sample_weight=None, global_batch: Optional[int] = None) -> float:
         """One optimisation step (what Keras' train_step + apply_gradients do).  Returns the loss of this
@@ -452,48 +465,96 @@ class Model:
         if self.kind == "jacobian":
             return self._train_step_sobolev(inp, tgt, global_batch)
         n = self.net
-        eng = n.engine
         B = inp.shape[0]
         gb = int(global_batch) if global_batch else B
         if self._loss_buf is None:
             self._loss_buf = torch.zeros(1, dtype=torch.float32, device=n.device)
-        if not callable(self.loss) and n._trunk is not None:
+        if self._fusable():
             if B > 0 and self._graph_enabled():
                 return self._train_step_graph(inp, tgt, sw, gb)
             self._loss_buf.zero_()
             self._fused_step(inp, tgt, sw, gb, self.optimizer.apply)
             return self._loss_buf
-        self._loss_buf.zero_()
-        xs = inp[:, n.pi_dim: n.pi_dim + n.si_dim].contiguous()
-        n.grad.zero_()
-        p_in = inp[:, : n.pi_dim]
-        z = n._latent(p_in)
-        # JacRegLatentLayer's add_loss term (this process's share of the global-batch mean)
-        reg = n._jac_reg_loss(p_in) * (B / gb) if isinstance(n.p_jac_reg, (float, int)) else None
-        if not callable(self.loss):
-            packed = self._packed_weights()
-            zc = z.detach().contiguous()
-            u, stash = eng.forward(zc, xs, packed, save=True)
-            dz = eng.mse_backward(zc, xs, packed, u, stash, tgt, sw, 1.0 / gb, self._loss_buf,
-                                  n._gviews[n._last_names[0]], n._gviews[n._last_names[1]], 0.0)
-            if reg is None:
-                z.backward(dz)
-            else:
-                torch.autograd.backward([z, reg], [dz, torch.ones_like(reg)])
-                self._loss_buf += reg.detach()
-            loss = self._loss_buf
-        else:
-            u = ops.fused_shapenet(z, xs, n.w_h, n.b_h, eng)
-            lv = self.loss(tgt, u) * (B / gb)
-            if reg is not None:
-                lv = lv + reg
-            lv.backward()
-            loss = lv.detach().reshape(1)
+        loss = self._loss_and_grad(inp, tgt, self.loss, sw, gb, with_regularisers=True)
         if self.dist is not None:
             self.dist.allreduce_(n.grad)
         l1, l2 = n._kernel_regulariser()
-        self.optimizer.apply(n.theta, n.grad, l1, l2)
+        self._apply_update(self.optimizer.apply, l1, l2)
         return loss
+
+    def _fusable(self) -> bool:
+        """The fully fused step: 'mse' loss, fused trunk kernels, a hyper-network head (not the last-layer-parameterised
+        class, whose ShapeNet is a shared-weight MLP)."""
+        n = self.net
+        return not callable(self.loss) and n._trunk is not None and not getattr(n, "_last_layer_only", False)
+
+    def _loss_and_grad(self, inp: torch.Tensor, tgt: torch.Tensor, loss, sw: Optional[torch.Tensor] = None,
+                       gb: Optional[int] = None, with_regularisers: bool = False) -> torch.Tensor:
+        """Loss of this process's rows (already divided by the global batch) and its gradient with respect to every
+        variable, left in the flat gradient buffer; no update.  `loss` is 'mse' or a callable(y_true, y_pred) (Keras
+        order).  The general path of _train_step and the closure of the L-BFGS fine-tuner."""
+        n = self.net
+        eng = n.engine
+        B = inp.shape[0]
+        gb = int(gb) if gb else B
+        if self._loss_buf is None:
+            self._loss_buf = torch.zeros(1, dtype=torch.float32, device=n.device)
+        self._loss_buf.zero_()
+        n.grad.zero_()
+        p_in = inp[:, : n.pi_dim]
+        xs = inp[:, n.pi_dim: n.pi_dim + n.si_dim].contiguous()
+        extra = []  # differentiable torch terms added to the loss
+        if with_regularisers and isinstance(n.p_jac_reg, (float, int)):
+            extra.append(n._jac_reg_loss(p_in) * (B / gb))  # JacRegLatentLayer's add_loss term, this process's share
+        if getattr(n, "_last_layer_only", False):
+            u = n._forward_train(inp)  # shared-weight ShapeNet: torch autograd over library GEMMs
+            lv = (self._mse_torch(tgt, u, sw) if not callable(loss) else loss(tgt, u)) * (B / gb)
+            for e in extra:
+                lv = lv + e
+            lv.backward()
+            out = lv.detach().reshape(1)
+        else:
+            z = n._latent(p_in)
+            act = self._activity_terms(z.detach(), B, gb) if with_regularisers else None
+            if not callable(loss):
+                packed = self._packed_weights()
+                zc = z.detach().contiguous()
+                u, stash = eng.forward(zc, xs, packed, save=True)
+                dz = eng.mse_backward(zc, xs, packed, u, stash, tgt, sw, 1.0 / gb, self._loss_buf,
+                                      n._gviews[n._last_names[0]], n._gviews[n._last_names[1]], 0.0)
+                if act is not None:
+                    dz = dz + act[1]
+                    n._gviews[n._last_names[0]].add_(act[2])
+                    n._gviews[n._last_names[1]].add_(act[3])
+                    self._loss_buf += act[0]
+                torch.autograd.backward([z] + extra, [dz] + [torch.ones_like(e) for e in extra])
+                for e in extra:
+                    self._loss_buf += e.detach()
+                out = self._loss_buf
+            else:
+                u = ops.fused_shapenet(z, xs, n.w_h, n.b_h, eng)
+                lv = loss(tgt, u) * (B / gb)
+                for e in extra:
+                    lv = lv + e
+                lv.backward()
+                out = lv.detach().reshape(1)
+                if act is not None:
+                    z.backward(act[1])
+                    n._gviews[n._last_names[0]].add_(act[2])
+                    n._gviews[n._last_names[1]].add_(act[3])
+                    out = out + act[0]
+        if with_regularisers:
+            reg = self._reg_loss()
+            if reg is not None:
+                out = out + reg.detach() * (B / gb)
+        return out
+
+    @staticmethod
+    def _mse_torch(y_true, y_pred, sw):
+        per_row = ((y_true - y_pred) ** 2).mean(-1)
+        if sw is not None:
+            per_row = per_row * sw.reshape(-1)
+        return per_row.mean()
 
     def _fused_part1(self, inp, tgt, sw, gb):
         """Trunk forward, hyper-network head + ShapeNet, loss, reverse pass of the head: every gradient of the last
@@ -502,6 +563,7 @@ class Model:
         same body is what a CUDA graph records."""
         n = self.net
         eng = n.engine
+        B = inp.shape[0]
         xs = inp[:, n.pi_dim: n.pi_dim + n.si_dim].contiguous()
         p_in = inp[:, : n.pi_dim].contiguous()
         z, tstash = n._trunk.forward(p_in, n.theta_trunk, save=True)
@@ -509,6 +571,15 @@ class Model:
         u, stash = eng.forward(z, xs, packed, save=True)
         dz = eng.mse_backward(z, xs, packed, u, stash, tgt, sw, 1.0 / gb, self._loss_buf,
                               n._gviews[n._last_names[0]], n._gviews[n._last_names[1]], 0.0)
+        act = self._activity_terms(z, B, gb)
+        if act is not None:
+            dz = dz + act[1]
+            n._gviews[n._last_names[0]].add_(act[2])
+            n._gviews[n._last_names[1]].add_(act[3])
+            self._loss_buf += act[0]
+        reg = self._reg_loss()
+        if reg is not None:
+            self._loss_buf += reg * (B / gb)
         return p_in, tstash, dz
 
     def _fused_part2(self, ctx):
@@ -532,7 +603,7 @@ class Model:
             self.dist.allreduce_finish(h_head)
             self.dist.allreduce_finish(h_trunk)
         l1, l2 = n._kernel_regulariser()
-        apply_update(n.theta, n.grad, l1, l2)
+        self._apply_update(apply_update, l1, l2)
 
     # ---- CUDA-graph replay of the fused step ------------------------------------------------------------------
     # One optimisation step is 17 kernel launches from Python; at tutorial-1 sizes (512 rows) the launches, not the
@@ -548,7 +619,74 @@ class Model:
         g = self.use_graph
         if g is None:
             g = os.environ.get("NIF_B200_GRAPH", "1") != "0"
+        if not hasattr(self.optimizer, "record_apply") or getattr(self.optimizer, "_centralize_in_fit", False):
+            return False  # only Adam records its update into a graph; centralisation adds per-variable launches
         return bool(g)
+
+    # ---- regularisers of the ParameterNet (nif/model.py:107-125) ---------------------------------------------------
+    def _reg_loss(self) -> Optional[torch.Tensor]:
+        """Keras adds every layer's kernel / bias regulariser to the reported loss: l1 * sum|w| or l2 * sum w^2 over every
+        ParameterNet kernel and bias, last layer included (nif/model.py:107-117, 220-230; siren.py:515-518).  All of them
+        live in the flat parameter buffer (its padding entries are zero).  The gradient is folded into the optimiser."""
+        l1, l2 = self.net._kernel_regulariser()
+        th = self.net._reg_theta()
+        if l2:
+            return l2 * (th * th).sum()
+        if l1:
+            return l1 * th.abs().sum()
+        return None
+
+    def _activity_terms(self, z: torch.Tensor, B: int, gb: int):
+        """activity_regularizer of the last ParameterNet layer (nif/model.py:118-125, 229; siren.py:467-469): Keras adds
+        reg(pnet_output) / batch_size with pnet_output = z W_h + b_h the (B, po_dim) tensor.  Returns
+        (loss term of this process's rows, dz [B,K], dW_h [K,P], db_h [P]) or None.
+        L2: closed form in the Gram matrices  G = zt^T zt  and  C = W W^T  (zt = [z,1], W = [W_h; b_h]) --
+            sum_b |zt_b W|^2 = tr(W^T G W),  dW = 2 G W,  dz_b = 2 (C zt_b)[:K] -- nothing of size (B, po_dim) is formed.
+        L1: |.| does not factor: row blocks of pnet_output are formed one at a time by library GEMMs."""
+        n = self.net
+        a1, a2 = n.p_act_l1_reg, n.p_act_l2_reg
+        use_l2 = isinstance(a2, (float, int))
+        use_l1 = isinstance(a1, (float, int)) and not use_l2  # l2 wins (nif/model.py:118-125)
+        if not (use_l1 or use_l2):
+            return None
+        W = torch.cat([n.w_h.detach(), n.b_h.detach()[None, :]], 0)  # [K+1, P]
+        zt = torch.cat([z, torch.ones_like(z[:, :1])], 1)
+        K = z.shape[1]
+        # Keras divides by the batch it sees: the per-replica batch B (each replica adds its own term; the replica losses
+        # are then summed, and the gradient all-reduce sums the replica gradients, so the scale here is 1 / B per replica
+        # times this replica's share B / gb of the global-batch mean -> 1 / gb)
+        scale = 1.0 / gb
+        if use_l2:
+            lam = float(a2)
+            G = zt.T @ zt
+            GW = G @ W
+            term = lam * scale * (W * GW).sum()
+            dWt = (2.0 * lam * scale) * GW
+            Cm = W @ W.T
+            dz = (2.0 * lam * scale) * (zt @ Cm)[:, :K]
+        else:
+            lam = float(a1)
+            term = z.new_zeros(())
+            dWt = torch.zeros_like(W)
+            dz = torch.empty_like(z)
+            step = max(1, (1 << 26) // max(W.shape[1], 1))  # 256 MB of fp32 per block
+            for s0 in range(0, B, step):
+                blk = zt[s0:s0 + step] @ W
+                term = term + blk.abs().sum()
+                sg = torch.sign(blk)
+                dWt += zt[s0:s0 + step].T @ sg
+                dz[s0:s0 + step] = (sg @ W.T)[:, :K]
+            term = lam * scale * term
+            dWt *= lam * scale
+            dz *= lam * scale
+        return term, dz.contiguous(), dWt[:K], dWt[K]
+
+    def _apply_update(self, apply_update, l1, l2):
+        n = self.net
+        if getattr(self.optimizer, "_centralize_in_fit", False):
+            from .optimizers import centralize_
+            centralize_(n)
+        apply_update(n.theta, n.grad, l1, l2)
 
     def _graph_signature(self):
         n, opt = self.net, self.optimizer
@@ -629,6 +767,8 @@ class Model:
 
     def _train_step_sobolev(self, inp: torch.Tensor, tgt: torch.Tensor, global_batch: Optional[int]) -> torch.Tensor:
         n, loss, plan = self.net, self.loss, self._sobolev_plan
+        if isinstance(n.p_jac_reg, (float, int)):
+            raise NifError("jac_reg is not combined with Sobolev training in this build")
         eng = n.engine
         B = inp.shape[0]
         gb = int(global_batch) if global_batch else B
@@ -651,9 +791,9 @@ class Model:
         vc, gc, gy = loss.value_cols, loss.grad_cols, plan["gy"]
         ev = u[:, vc] - tgt[:, vc]
         eg = udot[0][:, gy] - tgt[:, gc]
-        du[:, vc] = (2.0 / gb) * ev
-        dud[:, gy] = (2.0 * loss.coef_grad / gb) * eg
-        lv = ((ev * ev).sum() + loss.coef_grad * (eg * eg).sum()) / gb
+        du[:, vc] = (2.0 / (gb * len(vc))) * ev
+        dud[:, gy] = (2.0 * loss.coef_grad / (gb * len(gc))) * eg
+        lv = ((ev * ev).sum() / len(vc) + loss.coef_grad * (eg * eg).sum() / len(gc)) / gb
         dz = eng.sobolev_backward(zc, xs, xdot[0], packed, stash, du, dud, n._gviews[n._last_names[0]],
                                   n._gviews[n._last_names[1]], 0.0)
         if fused_trunk:
@@ -663,7 +803,7 @@ class Model:
         if self.dist is not None:
             self.dist.allreduce_(n.grad)
         l1, l2 = n._kernel_regulariser()
-        self.optimizer.apply(n.theta, n.grad, l1, l2)
+        self._apply_update(self.optimizer.apply, l1, l2)
         return lv.reshape(1)
 
     def fit(self, x=None, y=None, batch_size=None, epochs=1, verbose=0, callbacks=None, shuffle=True,
@@ -694,16 +834,27 @@ class Model:
             t0 = time.time()
             tot = torch.zeros(1, dtype=torch.float64, device=self.net.device)
             rows = 0
+            mtot, mrows = {}, 0
             for bi, (gb, parts) in enumerate(ds.batches(epoch)):
                 inp = parts[0].to(self.net.device, non_blocking=True)
                 tgt = parts[1].to(self.net.device, non_blocking=True)
                 sw = parts[2].to(self.net.device, non_blocking=True).reshape(-1) if len(parts) > 2 else None
+                if sw is not None and self.kind == "jacobian":
+                    raise NifError("sample_weight is not supported by the Sobolev training step")
+                if self.metrics_fns:  # Keras evaluates metrics on the training forward pass (pre-update weights)
+                    pred = self._forward_batch(inp)
+                    for mfn in self.metrics_fns:
+                        k = getattr(mfn, "__name__", type(mfn).__name__)
+                        mtot[k] = mtot.get(k, 0.0) + torch.as_tensor(mfn(tgt, pred)).double().mean() * inp.shape[0]
+                    mrows += inp.shape[0]
                 loss = self._train_step(inp, tgt, sw, gb)
                 tot += loss.double() * gb  # Keras reports the sample-weighted running mean of batch losses
                 rows += gb
             if self.dist is not None:
                 self.dist.allreduce_(tot)
             logs = {"loss": float(tot) / max(rows, 1), "lr": self.optimizer.learning_rate}
+            for k, v in mtot.items():
+                logs[k] = float(v) / max(mrows, 1)
             if verbose:
                 print(f"Epoch {epoch + 1}/{epochs} - {time.time() - t0:.2f}s - loss: {logs['loss']:.4e}")
             for cb in cbs:

@@ -19,7 +19,7 @@ from ._lib import ACT, NifError
 from .keras_like import Model
 from .ops import FusedShapeNet
 
-__all__ = ["NIF", "NIFMultiScale"]
+__all__ = ["NIF", "NIFMultiScale", "NIFMultiScaleLastLayerParameterized"]
 
 _POLICIES = ("float32", "mixed_float16", "mixed_bfloat16")
 
@@ -66,8 +66,6 @@ class NIF(object):
         self.p_l2_reg = cfg_parameter_net.get("l2_reg", None)
         self.p_act_l1_reg = cfg_parameter_net.get("act_l1_reg", None)
         self.p_act_l2_reg = cfg_parameter_net.get("act_l2_reg", None)
-        if isinstance(self.p_act_l1_reg, (float, int)) or isinstance(self.p_act_l2_reg, (float, int)):
-            raise NotImplementedError("act_l1_reg / act_l2_reg are outside the B200 hot-path scope")
         if mixed_policy not in _POLICIES:
             raise ValueError(f"mixed_policy must be one of {_POLICIES} (float64 has no GPU path)")
         if compute not in ("auto", "fp32", "fp16x3", "bf16"):
@@ -153,7 +151,10 @@ class NIF(object):
         names = [n for n, _ in layout]
         shapes = dict(layout)
         place, off = {}, 0
-        trunk = names[:-2]
+        n_extra = getattr(self, "_n_extra", 0)
+        head = names[len(names) - n_extra - 2: len(names) - n_extra]
+        extra_names = names[len(names) - n_extra:] if n_extra else []
+        trunk = names[: len(names) - n_extra - 2]
         if self._fused_trunk_supported():
             order = [n for n in trunk if n.endswith("/kernel")] + [n for n in trunk if n.endswith("/bias")]
             for n in order:
@@ -166,7 +167,7 @@ class NIF(object):
             for n in trunk:
                 place[n] = off
                 off += (int(np.prod(shapes[n])) + 3) // 4 * 4
-        for n in names[-2:]:  # the last linear layer: 16-byte aligned for the kernels
+        for n in head + extra_names:  # the last linear layer (and what follows): 16-byte aligned for the kernels
             place[n] = off
             off += (int(np.prod(shapes[n])) + 3) // 4 * 4
         return place, off
@@ -197,9 +198,15 @@ class NIF(object):
     def grad_trunk(self) -> torch.Tensor:
         return self.grad[: self._n_trunk]
 
+    def _extra_layout(self) -> List[Tuple[str, Tuple[int, ...]]]:
+        """Variables created after the ParameterNet (none for the hyper-network classes)."""
+        return []
+
     def _init_parameters(self):
+        extra = self._extra_layout()
         layout = self._trunk_layout() + [(self._last_names[0], (self.pi_hidden, self.po_dim)),
-                                         (self._last_names[1], (self.po_dim,))]
+                                         (self._last_names[1], (self.po_dim,))] + extra
+        self._n_extra = len(extra)
         place, total = self._place(layout)
         self._layout: Dict[str, Tuple[int, Tuple[int, ...]]] = {name: (place[name], shape) for name, shape in layout}
         self.n_flat = total
@@ -296,6 +303,11 @@ class NIF(object):
             sq = sq + (zd * zd).sum()
         return float(self.p_jac_reg) * sq / (input_p.shape[0] * self.pi_hidden * self.pi_dim)
 
+    def _reg_theta(self) -> torch.Tensor:
+        """The part of the flat parameter buffer the ParameterNet kernel / bias regularisers act on (all of it: every
+        variable of NIF / NIFMultiScale belongs to the ParameterNet)."""
+        return self.theta
+
     def _kernel_regulariser(self) -> Tuple[float, float]:
         """(l1, l2) applied to every ParameterNet kernel and bias (nif/model.py:107-117); l2 wins."""
         if isinstance(self.p_l2_reg, (float, int)):
@@ -353,9 +365,9 @@ class NIFMultiScale(NIF):
         assert "use_resblock" in cfg_shape_net.keys(), "`use_resblock` should be in cfg_shape_net"
         assert type(cfg_shape_net["use_resblock"]) == bool, "cfg_shape_net['use_resblock'] must be a bool"
         conn = cfg_shape_net.get("connectivity")
-        if conn == "last_layer":
-            raise NotImplementedError("connectivity='last_layer' (NIFMultiScaleLastLayerParameterized) is outside the hot path")
-        if conn != "full":
+        if conn == "last_layer" and not getattr(self, "_last_layer_only", False):
+            raise ValueError("connectivity='last_layer' is the class NIFMultiScaleLastLayerParameterized")
+        if conn not in ("full", "last_layer"):
             raise ValueError("cfg_shape_net missing correct `connectivity`")
         self._variant = "siren_res" if cfg_shape_net["use_resblock"] else "siren"
 
@@ -465,3 +477,135 @@ class NIFMultiScale(NIF):
                 q = f"mlp_hidden_pnet_{i}"
                 h = h + f(h @ V[q + "/kernel"] + V[q + "/bias"])
         return h @ V["bottleneck_pnet/kernel"] + V["bottleneck_pnet/bias"]
+
+
+class NIFMultiScaleLastLayerParameterized(NIFMultiScale):
+    """NIFMultiScale whose ParameterNet parameterises only the LAST layer of the ShapeNet (reference: class
+    NIFMultiScaleLastLayerParameterized, nif/model.py:989-1269): the ShapeNet is a shared-weight SIREN
+    x -> phi(x) in R^{so x pi_hidden} (:1151-1242) and  u = phi(x) . pnet_output + last_layer_bias  (:1244-1269), a
+    DeepONet-style product.  pnet_output = latent @ HyperLinearForSIREN_w + _b with po_dim = pi_hidden (:583-585).
+
+    There are no per-sample weights here, so this class is not the fused hyper-network hot path: the ParameterNet trunk
+    runs on the fused trunk kernels where they apply, the shared-weight ShapeNet and the final product are library GEMMs
+    (torch) differentiated by autograd into the same flat gradient buffer."""
+
+    _last_layer_only = True
+
+    def __init__(self, cfg_shape_net, cfg_parameter_net, mixed_policy="float32", **kw):
+        assert cfg_shape_net["connectivity"] == "last_layer", \
+            "you should assign cfg_shape_net['connectivity'] == 'last_layer'"
+        self.s_l1_reg = cfg_shape_net.get("l1_reg", None)
+        self.s_l2_reg = cfg_shape_net.get("l2_reg", None)
+        super().__init__(cfg_shape_net, cfg_parameter_net, mixed_policy, **kw)
+
+    def _po_dim(self) -> int:
+        return self.pi_hidden  # nif/model.py:583-585
+
+    def _fused_trunk_supported(self) -> bool:
+        return False  # the whole model is differentiated by autograd; keep one mechanism
+
+    def _extra_layout(self):
+        s = self.cfg_shape_net
+        L = [("siren_first_snet_w", (self.si_dim, self.n_sx)), ("siren_first_snet_b", (self.n_sx,))]
+        for i in range(self.l_sx):
+            if s["use_resblock"]:
+                q = f"siren_hidden_resblock_snet_{i}"
+                L += [(q + "_w", (self.n_sx, self.n_sx)), (q + "_b", (self.n_sx,)),
+                      (q + "_w2", (self.n_sx, self.n_sx)), (q + "_b2", (self.n_sx,))]
+            else:
+                q = f"siren_hidden_snet_{i}"
+                L += [(q + "_w", (self.n_sx, self.n_sx)), (q + "_b", (self.n_sx,))]
+        no = self.po_dim * self.so_dim
+        L += [("siren_bottleneck_snet_w", (self.n_sx, no)), ("siren_bottleneck_snet_b", (no,)),
+              ("last_layer_bias_snet", (self.so_dim,))]
+        return L
+
+    def _draw(self, name: str, shape):
+        s = self.cfg_shape_net
+        if name == "HyperLinearForSIREN_b":
+            # connectivity 'last_layer' (nif/layers/siren.py:482-483): every output column counts as a last-layer weight
+            return _uniform(shape, math.sqrt(6.0 / (2 * self.n_sx)), self._gen)
+        if name == "last_layer_bias_snet":
+            return _trunc_normal(shape, 0.1, self._gen)  # BiasAddLayer (nif/layers/mlp.py:245-250)
+        if "_snet" in name:
+            # SIREN layer rules with the ShapeNet's omega_0 (nif/layers/siren.py:178-204); SIREN_ResNet copies (:370-379)
+            w0 = float(s["omega_0"])
+            if name.endswith("_w2") or name.endswith("_b2"):
+                return self._drawn[name[:-1]].clone()
+            first = name.startswith("siren_first")
+            fan_in = self.si_dim if first else self.n_sx
+            if name.endswith("_w"):
+                t = _uniform(shape, 1.0 / fan_in if first else math.sqrt(6.0 / fan_in) / w0, self._gen)
+            else:
+                t = _uniform(shape, 1.0 / math.sqrt(fan_in), self._gen)
+            self._drawn[name] = t
+            return t
+        return super()._draw(name, shape)
+
+    # ---- forward pieces (differentiable torch ops over the flat-buffer views) ----
+    def _phi(self, x: torch.Tensor) -> torch.Tensor:
+        """_call_shape_net_get_phi_x (nif/model.py:1222-1242): x -> [B, so, pi_hidden]."""
+        V, s = self._views, self.cfg_shape_net
+        w0 = float(s["omega_0"])
+        h = torch.sin(w0 * (x @ V["siren_first_snet_w"]) + V["siren_first_snet_b"])
+        for i in range(self.l_sx):
+            if s["use_resblock"]:
+                q = f"siren_hidden_resblock_snet_{i}"
+                g = torch.sin(w0 * (h @ V[q + "_w"]) + V[q + "_b"])
+                h = 0.5 * (h + torch.sin(w0 * (g @ V[q + "_w2"]) + V[q + "_b2"]))
+            else:
+                q = f"siren_hidden_snet_{i}"
+                h = torch.sin(w0 * (h @ V[q + "_w"]) + V[q + "_b"])
+        phi = h @ V["siren_bottleneck_snet_w"] + V["siren_bottleneck_snet_b"]
+        return phi.reshape(-1, self.so_dim, self.pi_hidden)
+
+    def _pnet(self, p_in: torch.Tensor) -> torch.Tensor:
+        return self._latent(p_in) @ self.w_h + self.b_h
+
+    def _u_given(self, x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+        """_call_shape_net_mres_only_para_last_layer (nif/model.py:1244-1269): Dot(axes=(2,1)) + BiasAddLayer."""
+        return torch.einsum("bok,bk->bo", self._phi(x), w) + self._views["last_layer_bias_snet"]
+
+    def _forward_train(self, inp: torch.Tensor) -> torch.Tensor:
+        return self._u_given(inp[:, self.pi_dim: self.pi_dim + self.si_dim], self._pnet(inp[:, : self.pi_dim]))
+
+    def _forward_kind(self, kind: str, x: torch.Tensor, w: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if kind == "full":
+            return self._forward_train(x)
+        if kind == "p_to_lr":
+            return self._pnet(x)  # nif/model.py:1070-1083: in this class the "hidden LR" is the ParameterNet output
+        if kind == "x_to_phi":
+            return self._phi(x)
+        if kind == "x_to_u_given_w":
+            return self._u_given(x, w)
+        raise ValueError(kind)
+
+    def _count_params_kind(self, kind: str) -> int:
+        snet = sum(int(np.prod(sh)) for nm, (_, sh) in self._layout.items() if "_snet" in nm)
+        return {"full": self.count_params(), "p_to_lr": self.count_params() - snet,
+                "x_to_phi": snet - self.so_dim, "x_to_u_given_w": snet}[kind]
+
+    def _reg_theta(self) -> torch.Tensor:
+        """ParameterNet regularisers act on the ParameterNet variables only (the ShapeNet has its own l1_reg / l2_reg keys,
+        nif/model.py:1028-1040, which are not built here)."""
+        first_snet = self._layout["siren_first_snet_w"][0]
+        return self.theta[:first_snet]
+
+    def _kernel_regulariser(self):
+        l1, l2 = super()._kernel_regulariser()
+        if l1 or l2:
+            raise NifError("ParameterNet l1_reg / l2_reg with NIFMultiScaleLastLayerParameterized is not built "
+                           "(the optimiser-side regulariser acts on the whole flat buffer)")
+        if isinstance(self.s_l1_reg, (float, int)) or isinstance(self.s_l2_reg, (float, int)):
+            raise NifError("cfg_shape_net l1_reg / l2_reg is not built")
+        return 0.0, 0.0
+
+    # ---- the reference's public surface ----
+    def model_p_to_w(self) -> Model:
+        raise ValueError("In this class: NIFMultiScaleLastLayerParameterization, `w` is the same as `lr`")
+
+    def model_lr_to_w(self) -> Model:
+        raise ValueError("In this class: NIFMultiScaleLastLayerParameterization, `w` is the same as `lr`")
+
+    def model_x_to_phi(self) -> Model:
+        return Model(self, "x_to_phi")

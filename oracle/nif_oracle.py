@@ -423,6 +423,91 @@ def forward(spec: Spec, prm: Dict[str, Tensor], inputs: Tensor) -> Tensor:
 
 
 # ----------------------------------------------------------------------------
+# NIFMultiScaleLastLayerParameterized (nif/model.py:989-1269)
+# ----------------------------------------------------------------------------
+def last_layer_forward(cfg_s: dict, cfg_p: dict, prm: Dict[str, Tensor], inputs: Tensor):
+    """call() of the last-layer-parameterised class (nif/model.py:1045-1066): ParameterNet -> pnet_output (po_dim =
+    pi_hidden, :583-585); shared-weight SIREN ShapeNet x -> phi [B, so, pi_hidden] (:1222-1242, layers :1151-1220 with
+    SIREN / SIREN_ResNet semantics of nif/layers/siren.py:256-281, 381-410); u = Dot(axes=(2,1))(phi, pnet_output) +
+    last_layer_bias (:1264-1269).  Returns (u, phi, pnet_output)."""
+    pi, si, so = cfg_p["input_dim"], cfg_s["input_dim"], cfg_s["output_dim"]
+    K = cfg_p["latent_dim"]
+    spec = Spec(variant="siren_res" if cfg_s["use_resblock"] else "siren", pi=pi, si=si, so=so, n=cfg_s["units"],
+                l=cfg_s["nlayers"], K=K, n_st=cfg_p["units"], l_st=cfg_p["nlayers"], p_act=cfg_p["activation"],
+                omega0=float(cfg_s["omega_0"]), weight_init_factor=cfg_s["weight_init_factor"],
+                p_resblock=bool(cfg_p.get("use_resblock", False)), p_omega0=float(cfg_p.get("omega_0", 1.0)))
+    z = latent(spec, prm, inputs[:, :pi])
+    pout = z @ prm["HyperLinearForSIREN_w"] + prm["HyperLinearForSIREN_b"]
+    w0 = float(cfg_s["omega_0"])
+    x = inputs[:, pi:pi + si]
+    h = torch.sin(w0 * (x @ prm["siren_first_snet_w"]) + prm["siren_first_snet_b"])
+    for i in range(cfg_s["nlayers"]):
+        if cfg_s["use_resblock"]:
+            q = f"siren_hidden_resblock_snet_{i}"
+            g = torch.sin(w0 * (h @ prm[q + "_w"]) + prm[q + "_b"])
+            h = 0.5 * (h + torch.sin(w0 * (g @ prm[q + "_w2"]) + prm[q + "_b2"]))
+        else:
+            q = f"siren_hidden_snet_{i}"
+            h = torch.sin(w0 * (h @ prm[q + "_w"]) + prm[q + "_b"])
+    phi = (h @ prm["siren_bottleneck_snet_w"] + prm["siren_bottleneck_snet_b"]).reshape(-1, so, K)
+    u = torch.einsum("bok,bk->bo", phi, pout) + prm["last_layer_bias_snet"]
+    return u, phi, pout
+
+
+# ----------------------------------------------------------------------------
+# optimisers of nif/optimizers (restated; the update rules are in the reference tree, the Keras base class is not)
+# ----------------------------------------------------------------------------
+def adabelief_step(p: Tensor, g: Tensor, m: Tensor, v: Tensor, step: int, lr: float = 1e-3, beta_1: float = 0.9,
+                   beta_2: float = 0.999, epsilon: float = 1e-14, weight_decay: float = 0.0, rectify: bool = True,
+                   amsgrad: bool = False, vhat: Optional[Tensor] = None, sma_threshold: float = 5.0, total_steps: int = 0,
+                   warmup_proportion: float = 0.1, min_lr: float = 0.0) -> None:
+    """AdaBeliefOptimizer._resource_apply_dense (nif/optimizers/external_optimizers.py:458-528), in place; `step` is
+    iterations + 1 (:467)."""
+    lr_t = lr
+    if total_steps > 0:  # :470-479
+        warmup_steps = total_steps * warmup_proportion
+        decay_steps = max(total_steps - warmup_steps, 1)
+        decay_rate = (min_lr - lr_t) / decay_steps
+        lr_t = lr_t * (step / warmup_steps) if step <= warmup_steps else lr_t + decay_rate * min(step - warmup_steps, decay_steps)
+    b1p, b2p = beta_1 ** step, beta_2 ** step
+    sma_inf = 2.0 / (1.0 - beta_2) - 1.0
+    sma_t = sma_inf - 2.0 * step * b2p / (1.0 - b2p)
+    m.mul_(beta_1).add_(g, alpha=1.0 - beta_1)                       # :484-486
+    m_corr = m / (1.0 - b1p)
+    v.mul_(beta_2).add_((g - m) ** 2, alpha=1.0 - beta_2).add_(epsilon)  # :489-492
+    if amsgrad:
+        torch.maximum(vhat, v, out=vhat)
+        v_corr = torch.sqrt(vhat / (1.0 - b2p))
+    else:
+        v_corr = torch.sqrt(v / (1.0 - b2p))
+    if rectify:
+        if sma_t >= sma_threshold:
+            r_t = math.sqrt((sma_t - 4.0) / (sma_inf - 4.0) * (sma_t - 2.0) / (sma_inf - 2.0) * sma_inf / sma_t)  # :502-509
+            upd = r_t * m_corr / (v_corr + epsilon)
+        else:
+            upd = m_corr
+    else:
+        upd = m_corr / (v_corr + epsilon)
+    if weight_decay != 0.0:
+        upd = upd + weight_decay * p
+    p.sub_(lr_t * upd)
+
+
+def lion_step(p: Tensor, g: Tensor, m: Tensor, lr: float = 1e-4, beta_1: float = 0.9, beta_2: float = 0.99, wd: float = 0.0):
+    """Lion._resource_apply_dense (nif/optimizers/external_optimizers.py:681-702), in place."""
+    p.sub_(lr * (torch.sign(m * beta_1 + g * (1.0 - beta_1)) + p * wd))
+    m.mul_(beta_2).add_(g, alpha=1.0 - beta_2)
+
+
+def centralize_gradient(g: Tensor) -> Tensor:
+    """get_centralized_gradients (nif/optimizers/gtcf.py:27-32): rank >= 2 gradients lose their mean over every axis but
+    the last."""
+    if g.dim() > 1:
+        return g - g.mean(dim=tuple(range(g.dim() - 1)), keepdim=True)
+    return g
+
+
+# ----------------------------------------------------------------------------
 # initialisers
 # ----------------------------------------------------------------------------
 def _trunc_normal(shape, std, gen, dtype):

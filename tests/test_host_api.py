@@ -86,8 +86,12 @@ def test_cfg_validation_errors_match_reference():
         nif_b200.NIFMultiScale(dict(CFG_S, use_resblock=1), CFG_P, device="cpu")
     with pytest.raises(ValueError):
         nif_b200.NIFMultiScale(dict(CFG_S, connectivity="banana"), CFG_P, device="cpu")
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(ValueError):  # 'last_layer' belongs to NIFMultiScaleLastLayerParameterized
         nif_b200.NIFMultiScale(dict(CFG_S, connectivity="last_layer"), CFG_P, device="cpu")
+    with pytest.raises(AssertionError):  # nif/model.py:1020-1022
+        nif_b200.NIFMultiScaleLastLayerParameterized(CFG_S, CFG_P, device="cpu")
+    ll = nif_b200.NIFMultiScaleLastLayerParameterized(dict(CFG_S, connectivity="last_layer"), CFG_P, device="cpu")
+    assert ll.po_dim == CFG_P["latent_dim"]  # nif/model.py:583-585
     with pytest.raises(ValueError):
         nif_b200.NIFMultiScale(CFG_S, CFG_P, "float64", device="cpu")
 
