@@ -494,7 +494,6 @@ class Model:
         variable, left in the flat gradient buffer; no update.  `loss` is 'mse' or a callable(y_true, y_pred) (Keras
         order).  The general path of _train_step and the closure of the L-BFGS fine-tuner."""
         n = self.net
-        eng = n.engine
         B = inp.shape[0]
         gb = int(gb) if gb else B
         if self._loss_buf is None:
@@ -514,6 +513,7 @@ class Model:
             lv.backward()
             out = lv.detach().reshape(1)
         else:
+            eng = n.engine
             z = n._latent(p_in)
             act = self._activity_terms(z.detach(), B, gb) if with_regularisers else None
             if not callable(loss):
@@ -536,10 +536,12 @@ class Model:
                 lv = loss(tgt, u) * (B / gb)
                 for e in extra:
                     lv = lv + e
-                lv.backward()
+                if act is not None:
+                    torch.autograd.backward([lv, z], [torch.ones_like(lv), act[1]])
+                else:
+                    lv.backward()
                 out = lv.detach().reshape(1)
                 if act is not None:
-                    z.backward(act[1])
                     n._gviews[n._last_names[0]].add_(act[2])
                     n._gviews[n._last_names[1]].add_(act[3])
                     out = out + act[0]
