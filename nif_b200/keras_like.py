@@ -880,9 +880,14 @@ class Model:
     def _ckpt_file(path: str) -> str:
         return path if path.endswith(".npz") else path + ".npz"
 
-    def save_weights(self, path: str):
-        """Keras `save_weights(prefix)` (tutorial/2_multi_scale_NIF.ipynb:629): here one .npz keyed by the
-        reference variable names."""
+    def save_weights(self, path: str, save_format: Optional[str] = None):
+        """Keras `save_weights(prefix)` (tutorial/2_multi_scale_NIF.ipynb:629).  Default: one .npz keyed by the reference
+        variable names.  save_format="tf" writes a TensorFlow checkpoint (`<prefix>.index` + `.data-00000-of-00001`,
+        nif_b200.data.tf_checkpoint) whose object graph carries the same names."""
+        if save_format == "tf":
+            from .data.tf_checkpoint import write_checkpoint
+            write_checkpoint(path, self.net.get_weights())
+            return
         f = self._ckpt_file(path)
         d = os.path.dirname(f)
         if d:
@@ -890,6 +895,19 @@ class Model:
         np.savez(f, **{k.replace("/", "|"): v for k, v in self.net.get_weights().items()})
 
     def load_weights(self, path: str):
+        """An .npz written by save_weights, or a TensorFlow checkpoint prefix as written by the reference's
+        `model.save_weights("…/ckpt")` (tutorial/1_simple_1d_wave.ipynb:501, 1280): variables are matched by the names
+        the reference layers give them (the checkpoint's object graph records them as full_name)."""
+        if not path.endswith(".npz") and os.path.exists(path + ".index"):
+            from .data.tf_checkpoint import load_variables
+            found = load_variables(path)
+            named = {k: v for k, v in found.items() if k in self.net.variables}
+            missing = [k for k in self.net.variables if k not in named]
+            if missing:
+                raise NifError(f"checkpoint {path!r} lacks variables {missing[:4]}{'...' if len(missing) > 4 else ''} "
+                               f"(it holds {sorted(found)[:6]}...)")
+            self.net.set_weights(named)
+            return self
         with np.load(self._ckpt_file(path)) as d:
             self.net.set_weights({k.replace("|", "/"): d[k] for k in d.files})
         return self
