@@ -236,3 +236,26 @@ def test_jac_reg_latent_loss_matches_oracle(cls, cfg_s, cfg_p):
             assert v.grad is None and float(g.abs().max()) == 0.0, k
         else:
             assert float((g.double() - v.grad).abs().max()) <= 2e-5 * float(v.grad.abs().max()) + 1e-12, k
+
+
+def test_pointwise_data_matches_the_reference_file():
+    """PointWiseData against vectors produced by the unmodified nif/data/point_wise_data.py
+    (tests/golden/make_golden_pointwise.py)."""
+    import os
+    from nif_b200.data import PointWiseData as P
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "pointwise", "pointwise.npz"))
+    raw, rawa = g["raw"], g["rawa"]
+    d, m, s = P.standard_normalize(raw.copy())
+    assert np.allclose(d, g["std_data"], atol=1e-12) and np.allclose(m, g["std_mean"]) and np.allclose(s, g["std_std"])
+    d, m, s, w = P.standard_normalize(rawa.copy(), area_weighted=True)
+    assert np.allclose(d, g["stda_data"], atol=1e-12) and np.allclose(m, g["stda_mean"]) and np.allclose(s, g["stda_std"])
+    assert np.allclose(w, g["stda_w"])
+    d, m, s = P.minmax_normalize(raw.copy(), 2, 3, 2)
+    assert np.allclose(d, g["mm_data"], atol=1e-12) and np.allclose(m, g["mm_mean"]) and np.allclose(s, g["mm_std"])
+    d, m, s, w = P.minmax_normalize(rawa.copy(), 2, 3, 2, area_weighted=True)
+    assert np.allclose(d, g["mma_data"], atol=1e-12) and np.allclose(m, g["mma_mean"]) and np.allclose(s, g["mma_std"])
+    assert np.allclose(w, g["mma_w"])
+    obj = P(raw[:, :2], raw[:, 2:5], raw[:, 5:7], rawa[:, -1:])
+    obj.data = obj.data_raw
+    assert np.array_equal(obj.data_raw, g["obj_raw"]) and np.array_equal(obj.parameter, g["obj_parameter"])
+    assert np.array_equal(obj.x, g["obj_x"]) and np.array_equal(obj.u, g["obj_u"])
