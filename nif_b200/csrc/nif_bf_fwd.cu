@@ -365,6 +365,9 @@ static int dispatch_bff(const Plan& pl, BfFwdArgs& a, cudaStream_t st) {
   return save ? launch_bff<NP, true, false>(pl, a, st) : launch_bff<NP, false, false>(pl, a, st);
 }
 
+template <int NP>
+static int launch_bfg(const Plan& pl, BfFwdArgs& a, cudaStream_t st);
+
 // returns NIF_E_UNSUPPORTED (without setting an error) when the shape does not fit these kernels
 int nif_bf_forward_impl(const Plan& pl, long long G, long long B, const float* z, const float* x, int x_shared,
                         const float* packed, float* u, float* save, cudaStream_t st) {
@@ -376,5 +379,266 @@ int nif_bf_forward_impl(const Plan& pl, long long G, long long B, const float* z
   a.tiles_per_group = (B + 127) / 128;
   a.total_tiles = a.tiles_per_group * G;
   a.z = z; a.x = x; a.packed = packed; a.x_shared = x_shared; a.u = u; a.save = save; a.nst = 0;
+  if (pl.K == 0 && !save) {  // explicit weight vectors (grouped sweeps): the two-tile inference kernel
+    const int rc = pl.NP == 128 ? launch_bfg<128>(pl, a, st) : launch_bfg<64>(pl, a, st);
+    if (rc != NIF_E_UNSUPPORTED) return rc;
+  }
   return pl.NP == 128 ? dispatch_bff<128>(pl, a, st) : dispatch_bff<64>(pl, a, st);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// K == 0 inference (grouped latent sweeps, SURVEY 8 a7 / BASELINE config 5): every group is a plain 128-wide SIREN MLP
+// with its own weights, so a layer is ONE tensor-core chunk and the activation epilogue, not the tensor pipe, sets the
+// pace.  Two tiles per CTA share every staged weight chunk and ping-pong: while the 256 epilogue threads finish a layer
+// of one tile, the MMAs of the other tile run.  Layer 0 (si inputs) and every bias come from the fp32 sections of the
+// image on the CUDA cores; sin is the hardware approximation (sin.approx: |error| < 1e-6 for |x| < 100, far inside a
+// bf16 operand's rounding), which leaves one MUFU op, one bias add and half a pack per element.
+// ---------------------------------------------------------------------------------------------------------------------
+__host__ __device__ inline size_t bfg_smem_bytes(int NP, int nst) {
+  return (size_t)2 * 128 * NP * 2 + (size_t)nst * BF_STAGE_BYTES + 256;
+}
+
+#define BFG_THREADS 640  // 16 epilogue warps (four threads per row: 32 lanes x NP/4 columns each), issuer, producer, 2 idle
+
+template <int NP, bool SINE>
+__global__ void __launch_bounds__(BFG_THREADS, 1) nif_bf_group_fwd_kernel(const Plan pl, const BfFwdArgs a) {
+  constexpr int CQ = NP / 4;  // columns per epilogue thread
+  constexpr uint32_t SBO_A = (NP / 8) * 128u;
+  constexpr uint32_t TILE_BYTES = 128u * NP * 2u;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char* A_all = smem;  // tile t at t * TILE_BYTES
+  unsigned char* Bst = smem + 2 * TILE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(Bst + a.nst * BF_STAGE_BYTES);
+  uint64_t* b_full = bars;         // [8]
+  uint64_t* b_empty = bars + 8;    // [8]
+  uint64_t* t_full = bars + 16;    // [2]  accumulator of tile t ready
+  uint64_t* t_free = bars + 18;    // [2]  accumulator of tile t drained
+  uint64_t* a_ready = bars + 20;   // [2]  operand tile of tile t written
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int H = pl.H, n = pl.n, si = pl.si, so = pl.so, KZ = pl.KZ;
+  const int NCHW = bf_nchw(pl);
+  const uint32_t nst = (uint32_t)a.nst;
+  const long long pairs_per_group = (a.tiles_per_group + 1) / 2;
+  const long long total_pairs = pairs_per_group * a.G;
+
+  if (tid == 0) {
+    for (int i = 0; i < 8; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_free[i], 512); mbar_init(&a_ready[i], 512); }
+    mbar_fence_init();
+  }
+  if (warp == 16) tc_alloc(tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  long long my_pairs = 0;
+  if ((long long)blockIdx.x < total_pairs) my_pairs = (total_pairs - blockIdx.x + gridDim.x - 1) / gridDim.x;
+
+  if (warp >= 16) {
+    tc_reg_dec<40>();
+    if (warp == 17) {
+      if (lane == 0) {  // weight stream: per pair H main chunks (chunk 0 of every layer) and so last-layer tiles
+        uint32_t s = 0, ph = 0;
+        auto put = [&](const float* src, uint32_t bytes) {
+          mbar_wait(&b_empty[s], ph ^ 1u);
+          mbar_expect_tx(&b_full[s], bytes);
+          bulk_g2s(Bst + s * BF_STAGE_BYTES, src, bytes, &b_full[s]);
+          if (++s == nst) { s = 0; ph ^= 1u; }
+        };
+        for (long long p = 0; p < my_pairs; ++p) {
+          const long long g = (blockIdx.x + p * gridDim.x) / pairs_per_group;
+          const float* pk = a.packed + g * pl.packed_floats;
+          for (int m = 1; m <= H; ++m) put(pk + pl.off_WF + (long long)(m - 1) * NCHW * bf_chunk_floats(pl), NP * NP * 2u);
+          for (int c = 0; c < so; ++c)
+            put(pk + pl.off_WX + (long long)bf_t_xl(pl, c) * bf_small_floats(pl), (uint32_t)NP * (uint32_t)KZ * 2u);
+        }
+      }
+    } else if (warp == 16) {
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+      uint32_t s = 0, ph = 0, aph = 0, fph0 = 0, fph1 = 0;
+      for (long long p = 0; p < my_pairs; ++p) {
+        for (int st = 0; st < H + so; ++st) {
+          const bool last = st >= H;
+          mbar_wait(&b_full[s], ph);
+          for (int t = 0; t < 2; ++t) {
+            if (!last || st == H) { mbar_wait(&a_ready[t], aph); }
+            uint32_t& fph = t ? fph1 : fph0;
+            mbar_wait(&t_free[t], fph ^ 1u);
+            fph ^= 1u;
+            tc_fence_after();
+            const uint64_t dA = bf_make_desc(smem_u32(A_all + t * TILE_BYTES), SBO_A);
+            const uint64_t dB = bf_make_desc(smem_u32(Bst + s * BF_STAGE_BYTES), SBO_A);
+            if (tc_elect_one()) {
+              const uint32_t idesc = bf_idesc(last ? KZ : NP);
+#pragma unroll
+              for (int ks = 0; ks < NP / 16; ++ks)
+                tc_mma_f16(tmem_u + (uint32_t)t * 128u, dA + (uint64_t)(ks * 16), dB + (uint64_t)(ks * 16), idesc, ks > 0 ? 1u : 0u);
+              tc_commit(&t_full[t]);
+              if (t == 1) tc_commit(&b_empty[s]);
+            }
+            __syncwarp();
+          }
+          if (!last || st == H) aph ^= 1u;
+          if (++s == nst) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else {
+    tc_reg_inc<104>();  // (the pool only holds what the other warp group released: 128 x (96 - 40) >= 512 x (104 - 96))
+    const int qt = warp >> 2;  // column quarter
+    const int r = tid & 127;
+    const uint32_t tm = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    const uint32_t row_off = (uint32_t)(r >> 3) * SBO_A + (uint32_t)(r & 7) * 16u;
+    uint32_t fph[2] = {0, 0};  // t_full phases
+    auto act = [&](float v) -> float {
+      if (SINE) return __sinf(v);
+      return act_f(pl.act, v);
+    };
+    // h values (this thread's CQ columns of tile t) -> operand tile, bf16
+    auto publish = [&](int t, const float (&h)[CQ]) {
+#pragma unroll
+      for (int c = 0; c < CQ / 8; ++c) {
+        *reinterpret_cast<uint4*>(A_all + t * TILE_BYTES + row_off + (uint32_t)(qt * (CQ / 8) + c) * 128u) =
+            make_uint4(bf_pack2(h[8 * c], h[8 * c + 1]), bf_pack2(h[8 * c + 2], h[8 * c + 3]), bf_pack2(h[8 * c + 4], h[8 * c + 5]),
+                       bf_pack2(h[8 * c + 6], h[8 * c + 7]));
+      }
+      fence_async_smem();
+      mbar_arrive(&a_ready[t]);
+    };
+    for (long long p = 0; p < my_pairs; ++p) {
+      const long long pair = blockIdx.x + p * gridDim.x;
+      const long long grp = pair / pairs_per_group;
+      const long long pr = pair - grp * pairs_per_group;
+      const float* pk = a.packed + grp * pl.packed_floats;
+      const float* C_all = pk + pl.off_C;   // [Lm][1][NP] fp32 biases
+      const float* M0 = pk + pl.off_M0;     // [1][si][NP]
+      const float om0 = plan_omega(pl, 0);
+      long long brow[2];
+      bool live[2];
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        brow[t] = (pr * 2 + t) * 128 + r;
+        live[t] = brow[t] < a.B;
+      }
+      // ---- layer 0 on the CUDA cores ----
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        float xv[NIF_MAX_SI];
+        const float* xrow = a.x + ((a.x_shared ? 0 : grp * a.B) + (live[t] ? brow[t] : 0)) * si;
+#pragma unroll
+        for (int i = 0; i < NIF_MAX_SI; ++i) xv[i] = (i < si && live[t]) ? om0 * __ldg(xrow + i) : 0.f;
+        float h[CQ];
+#pragma unroll
+        for (int c = 0; c < CQ / 4; ++c) {
+          const int j0 = qt * CQ + 4 * c;
+          const float4 b4 = ldg4(C_all + j0);
+          float pre[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+          for (int i = 0; i < NIF_MAX_SI; ++i)
+            if (i < si) {
+              const float4 w4 = ldg4(M0 + (long long)i * pl.NP + j0);
+              pre[0] = fmaf(xv[i], w4.x, pre[0]); pre[1] = fmaf(xv[i], w4.y, pre[1]);
+              pre[2] = fmaf(xv[i], w4.z, pre[2]); pre[3] = fmaf(xv[i], w4.w, pre[3]);
+            }
+#pragma unroll
+          for (int e = 0; e < 4; ++e) h[4 * c + e] = (j0 + e < n) ? act(pre[e]) : 0.f;
+        }
+        publish(t, h);
+      }
+      // ---- hidden layers ----
+#pragma unroll 1
+      for (int m = 1; m <= H; ++m) {
+        const float* bm = C_all + (long long)m * pl.NP + qt * CQ;
+        const int res = plan_res(pl, m);
+        const float om = plan_omega(pl, m);
+        // this layer's biases (the same for both tiles), fetched before the accumulator wait
+        float bb[CQ];
+#pragma unroll
+        for (int c = 0; c < CQ / 4; ++c) {
+          const float4 b4 = ldg4(bm + 4 * c);
+          bb[4 * c] = b4.x; bb[4 * c + 1] = b4.y; bb[4 * c + 2] = b4.z; bb[4 * c + 3] = b4.w;
+        }
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          mbar_wait(&t_full[t], fph[t]);
+          fph[t] ^= 1u;
+          tc_fence_after();
+          float h[CQ];
+          if (CQ == 32) {
+            float v[32];
+            tc_ld32(tm + (uint32_t)(t * 128 + qt * CQ), v);
+            tc_wait_ld();
+#pragma unroll
+            for (int e = 0; e < 32; ++e) h[e] = fmaf(om, v[e], bb[e]);
+          } else {
+            float v[16];
+            tc_ld16(tm + (uint32_t)(t * 128 + qt * CQ), v);
+            tc_wait_ld();
+#pragma unroll
+            for (int e = 0; e < 16; ++e) h[e] = fmaf(om, v[e], bb[e]);
+          }
+          tc_fence_before();
+          mbar_arrive(&t_free[t]);
+#pragma unroll
+          for (int e = 0; e < CQ; ++e) h[e] = (qt * CQ + e < n) ? act(h[e]) : 0.f;
+          if (res == 1) {  // NIF hidden layer: out = in + act(pre); the input is this tile's operand (bf16)
+#pragma unroll
+            for (int c = 0; c < CQ / 8; ++c) {
+              const uint4 q4 = *reinterpret_cast<const uint4*>(A_all + t * TILE_BYTES + row_off + (uint32_t)(qt * (CQ / 8) + c) * 128u);
+              const uint32_t w[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 f2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[e]));
+                h[8 * c + 2 * e] += f2.x;
+                h[8 * c + 2 * e + 1] += f2.y;
+              }
+            }
+          }
+          publish(t, h);
+        }
+      }
+      // ---- last layer: y[c] = h . ML[:, c] + CL[c]  (column kappa = 0 of the N = KZ chunk) ----
+      const float* CL = C_all + (long long)(H + 1) * pl.NP;
+      for (int c = 0; c < so; ++c) {
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          mbar_wait(&t_full[t], fph[t]);
+          fph[t] ^= 1u;
+          tc_fence_after();
+          float v[8];
+          tc_ld8(tm + (uint32_t)(t * 128), v);
+          tc_wait_ld();
+          tc_fence_before();
+          mbar_arrive(&t_free[t]);
+          if (qt == 0 && live[t]) a.u[(grp * a.B + brow[t]) * so + c] = v[0] + __ldg(CL + c);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 16) tc_dealloc(tmem, 256);
+}
+
+template <int NP>
+static int launch_bfg(const Plan& pl, BfFwdArgs& a, cudaStream_t st) {
+  int nst = 0;
+  for (int s = 4; s >= 2 && !nst; --s)
+    if (bfg_smem_bytes(NP, s) <= 227 * 1024) nst = s;
+  if (!nst) return NIF_E_UNSUPPORTED;
+  a.nst = nst;
+  const size_t smem = bfg_smem_bytes(NP, nst);
+  auto kern = pl.act == NIF_ACT_SINE ? nif_bf_group_fwd_kernel<NP, true> : nif_bf_group_fwd_kernel<NP, false>;
+  NIF_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int dev = 0, sms = 0;
+  NIF_CUDA_CHECK(cudaGetDevice(&dev));
+  NIF_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const long long total_pairs = (a.tiles_per_group + 1) / 2 * a.G;
+  long long grid = sms;
+  if (grid > total_pairs) grid = total_pairs;
+  if (grid < 1) return NIF_OK;
+  { NIF_PROF("nif_bf_group_fwd_kernel", st); kern<<<(unsigned)grid, BFG_THREADS, smem, st>>>(pl, a); }
+  NIF_CUDA_CHECK(cudaGetLastError());
+  return NIF_OK;
 }

@@ -216,19 +216,25 @@ def shape_net_factored(spec: Spec, x: Tensor, z: Tensor, w_h: Tensor, b_h: Tenso
     zt = [z, 1], M_m / C_m = the column slices of [w_h; b_h].  quant=None is exact arithmetic in the working precision
     (equal to shape_net(hyper_linear(z, w_h, b_h)) up to summation order).
 
+    quant='bf16_main' is 'bf16' with layer 0 and every bias left unrounded: the rounding points of the K = 0 latent-sweep
+    kernel, which takes those thin terms from the fp32 image on the CUDA cores.
+
     quant='bf16' restates what the reference's `mixed_bfloat16` policy (nif/model.py:101-105, 146, 530-533, 954;
     nif/layers/siren.py:519-521: variables cast to the compute dtype, einsum in bf16) permits, at the rounding points of
     the bf16 tensor-core kernels: every matmul operand -- the entries of [w_h; b_h], the activations h, and the latent
     code where it is a matmul operand (layer 0 and the bias sums) -- is rounded to bfloat16; products are accumulated
     in the working precision; the latent contraction, omega_0, the activation and the last layer's bias stay fp32."""
-    q = _bf16 if quant == "bf16" else (lambda t: t)
+    q = _bf16 if quant in ("bf16", "bf16_main") else (lambda t: t)
+    qt = (lambda t: t) if quant == "bf16_main" else q  # "bf16_main": layer 0 and every bias stay fp32 (the K = 0 sweep kernel)
     L = layout(spec.si, spec.so, spec.n, spec.l, spec.variant == "siren_res")
     K1 = z.shape[1] + 1
     W = torch.cat([w_h, b_h[None, :]], 0)  # [K+1, P]
     zt = torch.cat([z, torch.ones(z.shape[0], 1, dtype=z.dtype)], 1)
-    Wq, ztq = q(W), q(zt)
+    Wq, ztq = q(W), qt(zt)
+    Wt = qt(W)
     mats = [Wq[:, o:o + a * c].reshape(K1, a, c) for (o, a, c) in L.w]
-    bias = [Wq[:, o:o + c] for (o, c) in L.b]
+    mats[0] = Wt[:, L.w[0][0]:L.w[0][0] + L.w[0][1] * L.w[0][2]].reshape(K1, L.w[0][1], L.w[0][2])
+    bias = [Wt[:, o:o + c] for (o, c) in L.b]
     sine = spec.variant != "nif"
     f = torch.sin if sine else activation(spec.s_act)
     om = spec.omega0 if sine else 1.0
