@@ -205,6 +205,9 @@ def run_ours(args):
     ms_sus = timed(step_resident, n_sus, 3)
     clocks_sus = sampler2.stop() if sampler2 else None
 
+    # data-parallel update path: NVSwitch multicast fused kernel, or NCCL all-reduce + Adam on every rank
+    update_mode = "single" if world == 1 else ("multimem reduce-scatter+Adam+all-gather kernel" if model._symm is not None
+                                               else "NCCL all-reduce + Adam")
     # ---- replicas agree: after all those steps every rank must hold bit-identical parameters ----
     params_equal = None
     if world > 1:
@@ -281,7 +284,8 @@ def run_ours(args):
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "global_batch": gb, "parallelism": f"dp{world}",
-                   "kernels": eng.kernel_path,
+                   "kernels": eng.kernel_path, "trunk_kernels": getattr(net._trunk, "kernel_path", None),
+                   "dp_update": update_mode,
                    "l2": "inputs rotate through the 1M-point set; per-step working set (activation stash + deltas, "
                          "> 200 MB) exceeds the 126 MB L2, no explicit flush"},
         "clocks": clocks,

@@ -186,6 +186,18 @@ int nif_lion_step(int64_t n, float* p, const float* g, float* m, double lr, doub
  * last axis), subtract from every column its mean over the rows, in place. */
 int nif_centralize_gradient(int64_t rows, int64_t cols, float* g, void* stream);
 
+/* Data-parallel Adam fused with its collective over NVSwitch multicast memory (replaces tf.distribute.MirroredStrategy's
+ * all-reduce + per-replica update, README.md:39-49): for this rank's 1/world slice of the flat buffers, the gradient is
+ * read with multimem.ld_reduce.add from the MULTICAST address g_mc of the replicas' symmetric gradient buffers, the tf.keras
+ * Adam update of nif_adam_step runs on that slice (moments m, v are only maintained for the own slice), and the new
+ * parameters are written with multimem.st through p_mc into every replica.  p is this rank's own parameter buffer.
+ * n: floats of the buffers (multiple of 4).  alpha_dev != NULL: bias-corrected step size from device memory (as
+ * nif_adam_step_dev), else formed from lr and t.  The caller puts a cross-rank barrier before (every replica's gradient
+ * is complete) and after (every slice has landed) the call. */
+int nif_adam_step_multimem(int64_t n, int32_t rank, int32_t world, float* p_mc, const float* g_mc, const float* p, float* m,
+                           float* v, double lr, const float* alpha_dev, double b1, double b2, double eps, int64_t t,
+                           float l1, float l2, float g_scale, void* stream);
+
 /* ParameterNet trunk (everything before the last linear layer): Dense(act) -> nlayers x MLP_SimpleShortCut ->
  * Dense(latent), i.e. _call_parameter_net up to the bottleneck (nif/model.py:326-343, 176-216, 668-720;
  * nif/layers/mlp.py:148-160).  theta is the trunk's weight vector in the column order

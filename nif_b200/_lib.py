@@ -19,7 +19,7 @@ SYMBOLS = (
     "nif_forward_given_w", "nif_mse_backward", "nif_backward", "nif_adam_step", "nif_adam_step_dev", "nif_measure_fp32_peak",
     "nif_trunk_query", "nif_trunk_forward", "nif_trunk_backward", "nif_trunk_kernel_path",
     "nif_sobolev_query", "nif_forward_tangent_save", "nif_sobolev_backward", "nif_crc32c",
-    "nif_profile_begin", "nif_profile_end", "nif_adabelief_step", "nif_lion_step", "nif_centralize_gradient",
+    "nif_profile_begin", "nif_profile_end", "nif_adabelief_step", "nif_lion_step", "nif_centralize_gradient", "nif_adam_step_multimem",
 )
 
 VARIANT = {"nif": 0, "siren": 1, "siren_res": 2}
@@ -107,6 +107,7 @@ def lib() -> C.CDLL:
     L.nif_adabelief_step.argtypes = [I64, VP, VP, VP, VP, VP, D, D, D, D, I64, I32, D, D, F, F, F, VP]
     L.nif_lion_step.argtypes = [I64, VP, VP, VP, D, D, D, D, F, F, F, VP]
     L.nif_centralize_gradient.argtypes = [I64, I64, VP, VP]
+    L.nif_adam_step_multimem.argtypes = [I64, I32, I32, VP, VP, VP, VP, VP, D, VP, D, D, D, I64, F, F, F, VP]
     L.nif_profile_begin.argtypes = []
     L.nif_profile_end.argtypes = [C.c_char_p, C.c_int64]
     L.nif_crc32c.restype = C.c_uint32

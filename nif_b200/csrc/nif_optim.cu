@@ -117,3 +117,80 @@ extern "C" int nif_centralize_gradient(int64_t rows, int64_t cols, float* g, voi
   NIF_CUDA_CHECK(cudaGetLastError());
   return NIF_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Data-parallel update fused with its collective over NVSwitch multicast memory (NVLS): ONE kernel per step does
+//   reduce-scatter   g = multimem.ld_reduce.add over every replica's gradient buffer, for this rank's slice only
+//   Adam             on that slice (each rank keeps the moments of its own slice: the optimiser state is sharded)
+//   all-gather       multimem.st of the updated parameters into every replica's parameter buffer
+// replacing  all-reduce(gradient) -> Adam on every rank  (tf.distribute.MirroredStrategy in the reference, README.md:39-49;
+// NCCL all-reduce + nif_adam_step in the plain data-parallel path).  Every parameter value is computed exactly once, so the
+// replicas stay bit-identical by construction; each rank reads 1/N of the gradient and does 1/N of the update.
+// The caller brackets the launch with cross-rank barriers (gradients complete before; parameters visible after).
+// p_mc / g_mc: MULTICAST addresses of the symmetric parameter / gradient buffers; p, m, v: this rank's own buffers.
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 mc_ld_reduce_add(const float* mc) {
+  float4 r;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(mc) : "memory");
+  return r;
+}
+__device__ __forceinline__ void mc_st(float* mc, float4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ void adam_one_(float& p, float g, float& m, float& v, float alpha, float omb1, float omb2, float eps,
+                                          float l1, float l2, float gs) {
+  g *= gs;
+  if (l1 != 0.f) g += l1 * (p > 0.f ? 1.f : (p < 0.f ? -1.f : 0.f));
+  if (l2 != 0.f) g += 2.f * l2 * p;
+  m += (g - m) * omb1;
+  v += (g * g - v) * omb2;
+  p -= alpha * m / (sqrtf(v) + eps);
+}
+__global__ void __launch_bounds__(256) nif_adam_multimem_kernel(long long i4_begin, long long i4_end, float* __restrict__ p_mc,
+                                                                const float* __restrict__ g_mc, const float* __restrict__ p,
+                                                                float* __restrict__ m, float* __restrict__ v, float alpha,
+                                                                const float* __restrict__ alpha_dev, float omb1, float omb2,
+                                                                float eps, float l1, float l2, float gs) {
+  if (alpha_dev) alpha = __ldg(alpha_dev);
+  const long long stride = 256LL * gridDim.x;
+  for (long long i = i4_begin + blockIdx.x * 256LL + threadIdx.x; i < i4_end; i += stride) {
+    const float4 gg = mc_ld_reduce_add(g_mc + 4 * i);
+    float4 pp = reinterpret_cast<const float4*>(p)[i];
+    float4 mm = reinterpret_cast<float4*>(m)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+    adam_one_(pp.x, gg.x, mm.x, vv.x, alpha, omb1, omb2, eps, l1, l2, gs);
+    adam_one_(pp.y, gg.y, mm.y, vv.y, alpha, omb1, omb2, eps, l1, l2, gs);
+    adam_one_(pp.z, gg.z, mm.z, vv.z, alpha, omb1, omb2, eps, l1, l2, gs);
+    adam_one_(pp.w, gg.w, mm.w, vv.w, alpha, omb1, omb2, eps, l1, l2, gs);
+    reinterpret_cast<float4*>(m)[i] = mm;
+    reinterpret_cast<float4*>(v)[i] = vv;
+    mc_st(p_mc + 4 * i, pp);
+  }
+  __threadfence_system();  // the multicast stores are performed at every replica before the kernel retires
+}
+
+extern "C" int nif_adam_step_multimem(int64_t n, int32_t rank, int32_t world, float* p_mc, const float* g_mc, const float* p,
+                                      float* m, float* v, double lr, const float* alpha_dev, double b1, double b2, double eps,
+                                      int64_t t, float l1, float l2, float g_scale, void* stream) {
+  if (n < 0 || (n & 3) || world < 1 || rank < 0 || rank >= world) {
+    nif_set_error("nif_adam_step_multimem: n=%lld (must be a multiple of 4) rank=%d world=%d", (long long)n, rank, world);
+    return NIF_E_BAD_ARG;
+  }
+  if (n == 0) return NIF_OK;
+  if (!p_mc || !g_mc || !p || !m || !v) { nif_set_error("nif_adam_step_multimem: null buffer"); return NIF_E_BAD_ARG; }
+  if (!alpha_dev && t < 1) { nif_set_error("nif_adam_step_multimem: t=%lld", (long long)t); return NIF_E_BAD_ARG; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long n4 = n / 4, chunk = (n4 + world - 1) / world;
+  const long long b = (long long)rank * chunk, e = b + chunk < n4 ? b + chunk : n4;
+  if (e <= b) return NIF_OK;
+  const double alpha = alpha_dev ? 0.0 : lr * std::sqrt(1.0 - std::pow(b2, (double)t)) / (1.0 - std::pow(b1, (double)t));
+  long long nblk = (e - b + 255) / 256;
+  if (nblk > 148 * 4) nblk = 148 * 4;
+  { NIF_PROF("nif_adam_multimem_kernel", st);
+    nif_adam_multimem_kernel<<<(unsigned)nblk, 256, 0, st>>>(b, e, p_mc, g_mc, p, m, v, (float)alpha, alpha_dev, (float)(1.0 - b1),
+                                                             (float)(1.0 - b2), (float)eps, l1, l2, g_scale); }
+  NIF_CUDA_CHECK(cudaGetLastError());
+  return NIF_OK;
+}

@@ -68,11 +68,42 @@ class DataParallel:
         if self.world > 1:
             dist.barrier()
 
-    def attach(self, model):
-        """Make `model` (a nif_b200 Model) data parallel: replicas start from rank 0's parameters."""
+    def attach(self, model, symmetric=None):
+        """Make `model` (a nif_b200 Model) data parallel: replicas start from rank 0's parameters.
+
+        symmetric (default: env NIF_B200_SYMM, on): move the flat parameter and gradient buffers into NVLink symmetric
+        memory with an NVSwitch multicast mapping, so that the Adam update runs as ONE kernel fused with its collective
+        (nif_adam_step_multimem: reduce-scatter by multimem.ld_reduce, update of this rank's slice, all-gather by
+        multimem.st) instead of NCCL all-reduce + a full update on every rank.  Falls back to the NCCL path when the
+        fabric has no multicast support."""
         self.broadcast_(model.net.theta)
         model.dist = self
+        model._symm = None
+        if symmetric is None:
+            symmetric = os.environ.get("NIF_B200_SYMM", "1") != "0"
+        if symmetric and self.world > 1 and self.backend == "nccl":
+            model._symm = self._make_symmetric(model.net)
         return model
+
+    def _make_symmetric(self, net):
+        try:
+            import torch.distributed._symmetric_memory as symm
+            dev = net.theta.device
+            th = symm.empty(net.n_flat, dtype=torch.float32, device=dev)
+            gr = symm.empty(net.n_flat, dtype=torch.float32, device=dev)
+            hp = symm.rendezvous(th, dist.group.WORLD)
+            hg = symm.rendezvous(gr, dist.group.WORLD)
+            ok = torch.tensor([1 if (net.n_flat % 4 == 0 and hp.multicast_ptr and hg.multicast_ptr) else 0], device=dev)
+        except Exception as e:  # no symmetric-memory support in this build / on this fabric
+            ok = torch.tensor([0], device=net.theta.device)
+            self._symm_error = repr(e)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)  # every rank takes the same path
+        if int(ok) == 0:
+            return None
+        th.copy_(net.theta)
+        gr.zero_()
+        net._rebind(th, gr)
+        return {"hp": hp, "hg": hg, "p_mc": int(hp.multicast_ptr), "g_mc": int(hg.multicast_ptr)}
 
     def shutdown(self):
         if self.world > 1 and dist.is_initialized():

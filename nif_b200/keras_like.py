@@ -52,6 +52,20 @@ class Adam:
         ops.adam_step(theta, grad, self._m, self._v, self.learning_rate, self.iterations, self.beta_1, self.beta_2,
                       self.epsilon, l1, l2, g_scale)
 
+    def apply_multimem(self, theta: torch.Tensor, symm: dict, rank: int, world: int, l1=0.0, l2=0.0, g_scale=1.0):
+        """The data-parallel update fused with its collective over NVSwitch multicast memory (nif_adam_step_multimem);
+        the caller brackets it with cross-rank barriers."""
+        import ctypes as C
+        from . import _lib
+        self._ensure(theta)
+        self.iterations += 1
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        _lib.check(_lib.lib().nif_adam_step_multimem(theta.numel(), rank, world, C.c_void_p(symm["p_mc"]), C.c_void_p(symm["g_mc"]),
+                                                     C.c_void_p(theta.data_ptr()), C.c_void_p(self._m.data_ptr()),
+                                                     C.c_void_p(self._v.data_ptr()), self.learning_rate, None, self.beta_1,
+                                                     self.beta_2, self.epsilon, self.iterations, float(l1), float(l2),
+                                                     float(g_scale), st), "nif_adam_step_multimem")
+
     # graph-replayed steps: the update is recorded once with its step size in device memory (record_apply, inside the
     # capture); before every replay the host forms this step's alpha exactly like nif_adam_step does and stores it.
     def record_apply(self, theta: torch.Tensor, grad: torch.Tensor, l1=0.0, l2=0.0, g_scale=1.0):
@@ -219,6 +233,7 @@ class Model:
         self._loss_buf = None
         self._packed = None
         self.dist = None  # set by nif_b200.distributed.DataParallel
+        self._symm = None  # symmetric-memory handles of the flat buffers (DataParallel.attach), or None
         self.use_graph: Optional[bool] = None  # None: NIF_B200_GRAPH env (default on); see _train_step_graph
         self._graphs: Dict[tuple, dict] = {}
 
@@ -414,21 +429,34 @@ class Model:
             return np.zeros((0, self.net.so_dim), np.float32)
         return torch.cat(outs, 0).numpy()
 
-    def predict_latent_grid(self, latents, coords) -> torch.Tensor:
+    def predict_latent_grid(self, latents, coords, group_chunk: Optional[int] = None, shard: bool = False) -> torch.Tensor:
         """Factored form of model_x_to_u_given_w for sweeps:
         latents [G,K] x coords [N,si] -> u [G,N,so]; per-latent weights are generated once
-        (G x P, a plain GEMM) and the G ShapeNets run as grouped launches over the shared grid."""
+        (G x P, a plain GEMM) and the G ShapeNets run as grouped launches over the shared grid.
+
+        group_chunk: latents per launch (bounds the packed weight images and the output held at once; default: all).
+        shard=True (data parallel, model attached to a DataParallel): this rank evaluates latents[rank::world] only --
+        the sweep partitions over the latent axis with no collective -- and returns its [ceil(G/world), N, so] block."""
         n = self.net
         with torch.no_grad():
             zg = self._dev(latents)
-            w = torch.addmm(n.b_h.detach(), zg, n.w_h.detach())  # [G,P]
+            if shard and self.dist is not None and self.dist.world > 1:
+                zg = zg[self.dist.rank::self.dist.world].contiguous()
             eng0 = getattr(self, "_eng0", None)
             if eng0 is None:
                 eng0 = self._eng0 = n.engine.with_latent(0)
-            packed = eng0.pack(None, w)
             xs = self._dev(coords)
-            u = eng0.forward(None, xs, packed, groups=zg.shape[0], x_shared=True)
-        return u.view(zg.shape[0], xs.shape[0], n.so_dim)
+            G = zg.shape[0]
+            step = int(group_chunk) if group_chunk else max(G, 1)
+            outs = []
+            for s0 in range(0, G, step):
+                w = torch.addmm(n.b_h.detach(), zg[s0:s0 + step], n.w_h.detach())  # [g,P]
+                packed = eng0.pack(None, w)
+                u = eng0.forward(None, xs, packed, groups=w.shape[0], x_shared=True)
+                outs.append(u.view(w.shape[0], xs.shape[0], n.so_dim))
+            if not outs:
+                return torch.empty(0, xs.shape[0], n.so_dim, device=xs.device)
+        return outs[0] if len(outs) == 1 else torch.cat(outs, 0)
 
     # ---- training -----------------------------------------------------------------------------------
     def compile(self, optimizer=None, loss="mse", metrics=None, graph: Optional[bool] = None, **_kw):
@@ -476,11 +504,27 @@ class Model:
             self._fused_step(inp, tgt, sw, gb, self.optimizer.apply)
             return self._loss_buf
         loss = self._loss_and_grad(inp, tgt, self.loss, sw, gb, with_regularisers=True)
+        if self._symm_ready():
+            self._symm_update()
+            return loss
         if self.dist is not None:
             self.dist.allreduce_(n.grad)
         l1, l2 = n._kernel_regulariser()
         self._apply_update(self.optimizer.apply, l1, l2)
         return loss
+
+    def _symm_ready(self) -> bool:
+        return (self.dist is not None and getattr(self, "_symm", None) is not None and isinstance(self.optimizer, Adam)
+                and not getattr(self.optimizer, "_centralize_in_fit", False))
+
+    def _symm_update(self):
+        """barrier (every replica's gradient is complete) -> one kernel: reduce-scatter + Adam + all-gather over NVSwitch
+        multicast memory -> barrier (every parameter slice has landed, every gradient has been read)."""
+        n, s = self.net, self._symm
+        l1, l2 = n._kernel_regulariser()
+        s["hg"].barrier(channel=0)
+        self.optimizer.apply_multimem(n.theta, s, self.dist.rank, self.dist.world, l1, l2)
+        s["hg"].barrier(channel=1)
 
     def _fusable(self) -> bool:
         """The fully fused step: 'mse' loss, fused trunk kernels, a hyper-network head (not the last-layer-parameterised
@@ -594,6 +638,14 @@ class Model:
         Data parallel: the last linear layer's gradient (almost all of the buffer) is summed across ranks while the
         trunk's reverse pass runs; the small trunk gradient follows."""
         n = self.net
+        if self._symm_ready() and apply_update is not None:
+            ctx = part1() if part1 is not None else self._fused_part1(inp, tgt, sw, gb)
+            if part2 is not None:
+                part2()
+            else:
+                self._fused_part2(ctx)
+            self._symm_update()
+            return
         ctx = part1() if part1 is not None else self._fused_part1(inp, tgt, sw, gb)
         h_head = self.dist.allreduce_start(n.grad[n._n_trunk:]) if self.dist is not None else None
         if part2 is not None:
@@ -694,7 +746,7 @@ class Model:
         n, opt = self.net, self.optimizer
         return (n.theta.data_ptr(), n.grad.data_ptr(), opt._m.data_ptr(), opt._v.data_ptr(), opt._alpha_dev.data_ptr(),
                 self._loss_buf.data_ptr(), id(opt), opt.beta_1, opt.beta_2, opt.epsilon, n._kernel_regulariser(),
-                self.dist is not None)
+                self.dist is not None, self._symm_ready())
 
     def _train_step_graph(self, inp, tgt, sw, gb) -> torch.Tensor:
         n, opt = self.net, self.optimizer
@@ -721,6 +773,12 @@ class Model:
                     self._loss_buf.zero_()
                     self._fused_step(ent["inp"], ent["tgt"], ent["sw"], gb, opt.record_apply)
                 ent["graph"] = g
+            elif self._symm_ready():
+                with torch.cuda.graph(g):  # both kernel sequences in one graph; the fused update + barriers stay eager
+                    self._loss_buf.zero_()
+                    ctx = self._fused_part1(ent["inp"], ent["tgt"], ent["sw"], gb)
+                    self._fused_part2(ctx)
+                ent["graph"], ent["ctx"] = g, ctx
             else:
                 g2 = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
@@ -740,6 +798,9 @@ class Model:
         if self.dist is None:
             opt.advance_replay()
             ent["graph"].replay()
+        elif "graph2" not in ent:
+            ent["graph"].replay()
+            self._symm_update()
         else:
             self._fused_step(None, None, None, gb, opt.apply, part1=ent["graph"].replay, part2=ent["graph2"].replay)
         return self._loss_buf

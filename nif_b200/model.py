@@ -190,6 +190,11 @@ class NIF(object):
             if self._trunk.n_theta != self._n_trunk:
                 raise NifError("trunk layout mismatch between host and library")
 
+    def _rebind(self, theta: torch.Tensor, grad: torch.Tensor):
+        """Adopt caller-provided flat buffers (data parallel: buffers in NVLink symmetric memory)."""
+        self.theta, self.grad = theta, grad
+        self._bind_views()
+
     @property
     def theta_trunk(self) -> torch.Tensor:
         return self.theta[: self._n_trunk]

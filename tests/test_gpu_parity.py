@@ -794,4 +794,4 @@ def test_two_rank_nccl_data_parallel_equals_single_process():
                         "127.0.0.1", "--master-port", "29533", os.path.join(root, "tools", "dp_check.py")],
                        capture_output=True, text=True, cwd=root, timeout=600)
     print(r.stdout[-2000:], r.stderr[-2000:])
-    assert r.returncode == 0 and "DP check" in r.stdout and "params equal True" in r.stdout
+    assert r.returncode == 0 and "DP check: all passed" in r.stdout and "params equal True" in r.stdout

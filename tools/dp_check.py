@@ -1,4 +1,6 @@
-"""torchrun --nproc-per-node 2 tools/dp_check.py : data-parallel step == single-process step on the same global batch."""
+"""torchrun --nproc-per-node N tools/dp_check.py : the data-parallel step == the single-process step on the same global
+batch, for both update paths (NVSwitch multicast fused reduce-scatter + Adam + all-gather kernel | NCCL all-reduce + Adam),
+eager and graph-replayed; replicas bit-identical."""
 import sys, torch
 sys.path.insert(0, '.')
 import nif_b200
@@ -14,11 +16,14 @@ rng = np.random.default_rng(0)
 GB = 4096
 X = rng.uniform(-1, 1, (GB, 3)).astype(np.float32); Y = rng.uniform(-1, 1, (GB, 1)).astype(np.float32)
 
-def run(parallel, graph=None, steps=3):
+
+def run(parallel, graph=None, steps=3, symmetric=None):
     net = nif_b200.NIFMultiScale(cfg_s, cfg_p, seed=0, device=dev)
     m = net.build(); m.compile(nif_b200.Adam(1e-3), loss="mse", graph=graph)
+    mode = "single"
     if parallel:
-        dp.attach(m)
+        dp.attach(m, symmetric=symmetric)
+        mode = "multimem" if m._symm is not None else "nccl"
         xs, ys = X[dp.rank::dp.world], Y[dp.rank::dp.world]
     else:
         xs, ys = X, Y
@@ -27,18 +32,28 @@ def run(parallel, graph=None, steps=3):
         l = m._train_step(torch.as_tensor(xs).to(dev), torch.as_tensor(ys).to(dev), None, GB).clone()
         if parallel: dp.allreduce_(l)
         losses.append(float(l))
-    return net.theta.clone(), losses
+    torch.cuda.synchronize()
+    th = net.theta.clone()
+    lo, hi = th.clone(), th.clone()
+    if parallel and dp.world > 1:
+        torch.distributed.all_reduce(lo, op=torch.distributed.ReduceOp.MIN)
+        torch.distributed.all_reduce(hi, op=torch.distributed.ReduceOp.MAX)
+    return th, losses, mode, bool(torch.equal(lo, hi))
 
-th_dp, l_dp = run(True)
-th_1, l_1 = run(False)
-err = float((th_dp - th_1).abs().max() / th_1.abs().max())
+
+th_1, l_1, _, _ = run(False, graph=False)
+for symmetric in (True, False):
+    th_dp, l_dp, mode, same = run(True, graph=False, symmetric=symmetric)
+    err = float((th_dp - th_1).abs().max() / th_1.abs().max())
+    if dp.rank == 0:
+        print(f"DP check [{mode}]: world {dp.world} losses dp {l_dp} single {l_1} max rel param diff after 3 steps {err:.3e} replicas identical {same}")
+    assert err < 1e-5 and same and all(abs(a - b) < 1e-5 * max(1, abs(b)) for a, b in zip(l_dp, l_1)), (mode, err, l_dp, l_1)
+    # graph-replayed data-parallel steps == eager ones, bit for bit
+    th_g, l_g, mode_g, same_g = run(True, graph=True, steps=5, symmetric=symmetric)
+    th_e, l_e, _, _ = run(True, graph=False, steps=5, symmetric=symmetric)
+    if dp.rank == 0:
+        print(f"DP graph vs eager [{mode_g}]: params equal {bool(torch.equal(th_g, th_e))} losses equal {l_g == l_e} replicas identical {same_g}")
+    assert torch.equal(th_g, th_e) and l_g == l_e and same_g
 if dp.rank == 0:
-    print("DP check: world", dp.world, "losses dp", l_dp, "single", l_1, "max rel param diff after 3 steps", err)
-assert err < 1e-5 and all(abs(a - b) < 1e-5 * max(1, abs(b)) for a, b in zip(l_dp, l_1)), (err, l_dp, l_1)
-# the graph-replayed data-parallel step (two graphs around the first all-reduce) == the eager one, bit for bit
-th_g, l_g = run(True, graph=True, steps=5)
-th_e, l_e = run(True, graph=False, steps=5)
-if dp.rank == 0:
-    print("DP graph vs eager: params equal", bool(torch.equal(th_g, th_e)), "losses equal", l_g == l_e)
-assert torch.equal(th_g, th_e) and l_g == l_e
+    print("DP check: all passed; symmetric-memory error:", getattr(dp, "_symm_error", None))
 dp.shutdown()
