@@ -455,55 +455,84 @@ __global__ void __launch_bounds__(BFW_THREADS, 1) nif_bf_bwd_weight_kernel(const
     const float* hsrc = a.save + (long long)h * slot_floats;      // h_m, m = h + 1 -> stash slot h
     const float* dsrc = a.da + (long long)(h + 1) * slot_floats;  // da_m
     const int kk0 = KQ * pg + 2 * CK * q;                         // first latent coordinate of this thread
+    // fp32 row staging of h_m: in the tiled stash a 64-row sub-tile is one contiguous 64 * NP * 4 byte block; the slot's 128
+    // threads fetch it with cp.async (fully coalesced), and the copy of sub-tile t+2 flies while sub-tile t is converted.
+    // Row r of the block reads its column quads at (r >> 5) * 32 NP * 4 + quad * 512 + (r & 31) * 16: consecutive rows hit
+    // consecutive banks.  (Loading the rows straight from L2 in batches paid one L2 round trip per batch: 5000 cycles per
+    // sub-tile against 1024 of MMA time.)
+    constexpr uint32_t STAGE_BYTES = 64u * NP * 4u;
+    unsigned char* stg = smem + 2 * SLOT_BYTES + sl * STAGE_BYTES;
+    const int ts = tid & 127;  // thread index inside the slot
+    auto stage_rows = [&](long long t) {
+      const unsigned char* src = reinterpret_cast<const unsigned char*>(hsrc + bf_tiled_row(r0 + t * 64, NP));
+#pragma unroll
+      for (int i = 0; i < (int)(STAGE_BYTES / 2048); ++i) {
+        const uint32_t off = (uint32_t)(ts + i * 128) * 16u;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(stg + off)), "l"(src + off) : "memory");
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if (sl < nsub) stage_rows(sl);
+    // this thread's row data that comes straight from global memory -- its latent coordinates and its half of da_m --
+    // is fetched one sub-tile ahead
+    float ztn[2 * CK];
+    float4 dqn[NP / 8];
+    auto fetch_row = [&](long long t) {
+      const long long b = r0 + t * 64 + r;
+      const bool live = t < nsub && b < r1;
+#pragma unroll
+      for (int kl = 0; kl < 2 * CK; ++kl) {
+        const int kk = kk0 + kl;
+        ztn[kl] = 0.f;
+        if (live) ztn[kl] = (kk < K) ? __ldg(&a.z[b * K + kk]) : (kk == K ? 1.f : 0.f);
+      }
+      const float* drow = dsrc + bf_tiled_row(live ? b : r0, NP) + (long long)(q * (NP / 8)) * 128;  // quads of columns q*NP/2 ..
+#pragma unroll
+      for (int c = 0; c < NP / 8; ++c) dqn[c] = live ? ldg4(drow + c * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    fetch_row(sl);
     long long n_mine = 0;
     for (long long t = sl; t < nsub; t += 2, ++n_mine) {
       const long long b = r0 + t * 64 + r;
       const bool live = b < r1;
       float zt[2 * CK];
+      float4 dq[NP / 8];
 #pragma unroll
-      for (int kl = 0; kl < 2 * CK; ++kl) {
-        const int kk = kk0 + kl;
-        zt[kl] = 0.f;
-        if (live) zt[kl] = (kk < K) ? __ldg(&a.z[b * K + kk]) : (kk == K ? 1.f : 0.f);
-      }
-      const float* hrow = hsrc + bf_tiled_row(b, NP);
-      const float* drow = dsrc + bf_tiled_row(b, NP) + (long long)(q * (NP / 8)) * 128;  // quads of columns q*NP/2 ..
+      for (int kl = 0; kl < 2 * CK; ++kl) zt[kl] = ztn[kl];
+#pragma unroll
+      for (int c = 0; c < NP / 8; ++c) dq[c] = dqn[c];
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      named_bar_sync(1 + sl, 128);  // every thread's part of the block has landed
       // wait until the MMAs that read this slot two sub-tiles ago have completed
       mbar_wait(&slot_empty[sl], (uint32_t)((n_mine & 1) ^ 1));
-      // A: groups of 8 consecutive i, all of this thread's latent coordinates; loads batched 4 groups at a time
-#pragma unroll 1
-      for (int ig0 = 0; ig0 < NP / 8; ig0 += 4) {
-        float4 p[8];
+      // A: groups of 8 consecutive i, all of this thread's latent coordinates
+#pragma unroll 4
+      for (int ig = 0; ig < NP / 8; ++ig) {
+        float4 p0 = make_float4(0.f, 0.f, 0.f, 0.f), p1 = p0;
+        if (live) {
+          p0 = *reinterpret_cast<const float4*>(stg + (r >> 5) * (32 * NP * 4) + (2 * ig) * 512 + (r & 31) * 16);
+          p1 = *reinterpret_cast<const float4*>(stg + (r >> 5) * (32 * NP * 4) + (2 * ig + 1) * 512 + (r & 31) * 16);
+        }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) p[u] = live ? ldg4(hrow + (2 * ig0 + u) * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int ig = ig0 + u;
-          const float4 p0 = p[2 * u], p1 = p[2 * u + 1];
-#pragma unroll
-          for (int kl = 0; kl < 2 * CK; ++kl) {
-            const float zk = zt[kl];
-            // slab 2q + kl / CK, rows (kl % CK) * NP + 8 ig ..
-            const uint32_t mg = (uint32_t)((kl % CK) * (NP / 8) + ig);
-            *reinterpret_cast<uint4*>(slot + (uint32_t)(2 * q + kl / CK) * BFW_A_BYTES + mg * 1024u + koff) =
-                make_uint4(bf_pack2(zk * p0.x, zk * p0.y), bf_pack2(zk * p0.z, zk * p0.w), bf_pack2(zk * p1.x, zk * p1.y),
-                           bf_pack2(zk * p1.z, zk * p1.w));
-          }
+        for (int kl = 0; kl < 2 * CK; ++kl) {
+          const float zk = zt[kl];
+          // slab 2q + kl / CK, rows (kl % CK) * NP + 8 ig ..
+          const uint32_t mg = (uint32_t)((kl % CK) * (NP / 8) + ig);
+          *reinterpret_cast<uint4*>(slot + (uint32_t)(2 * q + kl / CK) * BFW_A_BYTES + mg * 1024u + koff) =
+              make_uint4(bf_pack2(zk * p0.x, zk * p0.y), bf_pack2(zk * p0.z, zk * p0.w), bf_pack2(zk * p1.x, zk * p1.y),
+                         bf_pack2(zk * p1.z, zk * p1.w));
         }
       }
+      named_bar_sync(1 + sl, 128);  // every thread of the slot is done with the staged block
+      if (t + 2 < nsub) stage_rows(t + 2);
+      fetch_row(t + 2);
       // B: this thread's half of the columns j
-#pragma unroll 1
-      for (int jg0 = 0; jg0 < NP / 16; jg0 += 4) {
-        float4 p[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) p[u] = live ? ldg4(drow + (2 * jg0 + u) * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const float4 p0 = p[2 * u], p1 = p[2 * u + 1];
-          const uint32_t mg = (uint32_t)(q * (NP / 16) + jg0 + u);
-          *reinterpret_cast<uint4*>(Bt + mg * 1024u + koff) =
-              make_uint4(bf_pack2(p0.x, p0.y), bf_pack2(p0.z, p0.w), bf_pack2(p1.x, p1.y), bf_pack2(p1.z, p1.w));
-        }
+      for (int u = 0; u < NP / 16; ++u) {
+        const float4 p0 = dq[2 * u], p1 = dq[2 * u + 1];
+        const uint32_t mg = (uint32_t)(q * (NP / 16) + u);
+        *reinterpret_cast<uint4*>(Bt + mg * 1024u + koff) =
+            make_uint4(bf_pack2(p0.x, p0.y), bf_pack2(p0.z, p0.w), bf_pack2(p1.x, p1.y), bf_pack2(p1.z, p1.w));
       }
       fence_async_smem();
       mbar_arrive(&slot_full[sl]);
@@ -548,7 +577,7 @@ int nif_bf_bwd_weight_impl(const Plan& pl, long long B, const float* z, const fl
   a.z = z; a.save = save; a.da = da; a.part = part;
   const int CK = 128 / pl.NP, KQ = 4 * CK;
   const int NG = (pl.K + 1 + KQ - 1) / KQ;
-  const size_t smem = 2 * (size_t)(4 * BFW_A_BYTES + pl.NP * 128u);
+  const size_t smem = 2 * (size_t)(4 * BFW_A_BYTES + pl.NP * 128u) + 2 * (size_t)(64 * pl.NP * 4);  // slots + row staging
   dim3 grid((unsigned)(pl.H * NG), (unsigned)S);
   if (pl.NP == 128) {
     NIF_CUDA_CHECK(cudaFuncSetAttribute(nif_bf_bwd_weight_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -556,6 +585,213 @@ int nif_bf_bwd_weight_impl(const Plan& pl, long long B, const float* z, const fl
   } else {
     NIF_CUDA_CHECK(cudaFuncSetAttribute(nif_bf_bwd_weight_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     { NIF_PROF("nif_bf_bwd_weight_kernel", st); nif_bf_bwd_weight_kernel<64><<<grid, BFW_THREADS, smem, st>>>(pl, a); }
+  }
+  NIF_CUDA_CHECK(cudaGetLastError());
+  return NIF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Thin weight-gradient terms (bias rows of every layer, first matrix, last matrix) on the tensor cores:
+//   out[kappa][q] = sum_b zt[b][kappa] F[b][q],   F = on-the-fly features of row b (column space Q of nif_bwd_edge_kernel:
+//   [(H+1) NP: da_m[j]] [so: du[c]] [si NP: omega x[i] da_0[j]] [NP so: h_{H+1}[i] du[c]])
+// A batch-reduction GEMM with M = kappa (one 128-row tile: K + 1 <= 128), N = a block of 128 feature columns, K = batch.
+//   A = zt^T  [128 kappa x 64 b], K-major, generated by warps 0-3 (thread = kappa: 64 coalesced loads, 8 stores)
+//   B = F^T   [128 q x 64 b], MN-major, generated by warps 4-7 / 8-11 (one slot each; two threads per row)
+// One CTA = (feature block, batch split); the accumulator stays in TMEM; partials in the layout nif_unpack_grad_kernel sums.
+// Feature blocks: m = 0..H (da_m) | i < si (omega x_i da_0) | c < so (du_c h_{H+1}) | one block holding du.
+// ---------------------------------------------------------------------------------------------------
+struct BfEdgeArgs {
+  long long B, rows_per_split;
+  int S, Q;
+  const float *z, *x, *save, *da, *du;
+  float* part;  // [S][K+1][Q]
+};
+#define BFE_THREADS 416
+
+template <int NP>
+__global__ void __launch_bounds__(BFE_THREADS, 1) nif_bf_bwd_edge_kernel(const Plan pl, const BfEdgeArgs a) {
+  constexpr uint32_t A_BYTES = 16384u;      // [128 kappa x 64 b] bf16, K-major (SBO 1024, LBO 128)
+  constexpr uint32_t B_BYTES = NP * 128u;   // [NP q x 64 b] bf16, MN-major
+  constexpr uint32_t SLOT_BYTES = A_BYTES + B_BYTES;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ uint64_t slot_full[2], slot_empty[2], done_bar;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int K = pl.K, K1 = pl.K + 1, H = pl.H, si = pl.si, so = pl.so;
+  const int blk = blockIdx.x, s = blockIdx.y;
+  const long long r0 = (long long)s * a.rows_per_split;
+  long long r1 = r0 + a.rows_per_split;
+  if (r1 > a.B) r1 = a.B;
+  const long long nsub = r1 > r0 ? (r1 - r0 + 63) / 64 : 0;
+
+  if (tid == 0) {
+    mbar_init(&slot_full[0], 256); mbar_init(&slot_full[1], 256);
+    mbar_init(&slot_empty[0], 1); mbar_init(&slot_empty[1], 1);
+    mbar_init(&done_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 12) tc_alloc(&tmem_slot, 128);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const long long slot_floats = bf_slot_floats(a.B, NP);
+
+  if (warp == 12) {
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+    const uint32_t idesc = bf_idesc(NP, 0, 1);  // A K-major, B MN-major
+    for (long long t = 0; t < nsub; ++t) {
+      const int sl = (int)(t & 1);
+      mbar_wait(&slot_full[sl], (uint32_t)((t >> 1) & 1));
+      tc_fence_after();
+      if (tc_elect_one()) {
+        const uint32_t base = smem_u32(smem + sl * SLOT_BYTES);
+        const uint64_t dA = tc_make_desc(base, 1024u);
+        const uint64_t dB = bfw_make_desc(base + A_BYTES);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          tc_mma_f16(tmem_u, dA + (uint64_t)(ks * 16), dB + (uint64_t)(ks * 16), idesc, (t > 0 || ks > 0) ? 1u : 0u);
+        tc_commit(&slot_empty[sl]);
+      }
+      __syncwarp();
+    }
+    if (tc_elect_one()) tc_commit(&done_bar);
+    __syncwarp();
+  } else if (warp < 4) {
+    // ---------------- A generators: thread = kappa; every sub-tile (both slots) ----------------
+    const int kk = tid;  // 0..127
+    const bool zreal = kk < K;
+    const float fill = kk == K ? 1.f : 0.f;
+    float zn[64];
+    auto fetch = [&](long long t) {
+#pragma unroll
+      for (int e = 0; e < 64; ++e) {
+        const long long b = r0 + t * 64 + e;
+        zn[e] = (t < nsub && b < r1) ? (zreal ? __ldg(&a.z[b * K + kk]) : fill) : 0.f;
+      }
+    };
+    fetch(0);
+    for (long long t = 0; t < nsub; ++t) {
+      const int sl = (int)(t & 1);
+      uint4 w[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        w[c] = make_uint4(bf_pack2(zn[8 * c], zn[8 * c + 1]), bf_pack2(zn[8 * c + 2], zn[8 * c + 3]),
+                          bf_pack2(zn[8 * c + 4], zn[8 * c + 5]), bf_pack2(zn[8 * c + 6], zn[8 * c + 7]));
+      fetch(t + 1);
+      mbar_wait(&slot_empty[sl], (uint32_t)(((t >> 1) & 1) ^ 1));
+      unsigned char* At = smem + sl * SLOT_BYTES;
+      const uint32_t roff = (uint32_t)(kk >> 3) * 1024u + (uint32_t)(kk & 7) * 16u;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(At + roff + c * 128) = w[c];
+      fence_async_smem();
+      mbar_arrive(&slot_full[sl]);
+    }
+    // ---------------- final epilogue: TMEM lane = kappa ----------------
+    mbar_wait(&done_bar, 0);
+    tc_fence_after();
+    {
+      const uint32_t tm = tmem + ((uint32_t)(warp * 32) << 16);
+      float* prow = a.part + ((long long)s * K1 + (kk < K1 ? kk : 0)) * a.Q;
+      const long long qA = (long long)(H + 1) * NP, qB = qA + so, qC = qB + (long long)si * NP;
+#pragma unroll 1
+      for (int c0 = 0; c0 < NP; c0 += 32) {
+        float v[32];
+        tc_ld32(tm + (uint32_t)c0, v);  // warp-collective: every lane executes it, only rows kappa < K + 1 are stored
+        tc_wait_ld();
+        if (kk < K1) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const int j = c0 + e;
+            const float val = nsub ? v[e] : 0.f;
+            if (blk <= H) prow[(long long)blk * NP + j] = val;                                   // dC_m[j]
+            else if (blk < H + 1 + si) prow[qB + (long long)(blk - H - 1) * NP + j] = val;        // dM_0[i][j]
+            else if (blk < H + 1 + si + so) prow[qC + (long long)j * so + (blk - H - 1 - si)] = val;  // dM_last[i = j][c]
+            else if (j < so) prow[qA + j] = val;                                                 // dC_last[c]
+          }
+        }
+      }
+    }
+  } else {
+    // ---------------- B generators: slot sl; thread (q2, r): row r of the sub-tile, feature columns 64 q2 .. ----------------
+    const int sl = (warp - 4) >> 2;
+    const int ts = (tid - 128) & 127;
+    const int q2 = ts >> 6, r = ts & 63;
+    constexpr int NQ = NP / 8;  // quads (of 4 columns) per thread: NP / 2 columns
+    const uint32_t koff = (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 16u;
+    // source of this block's features: a tiled slot (da_m / da_0 / h_{H+1}) times an optional per-row factor
+    const float* src = nullptr;
+    int kind = 0, col = 0;  // 0: plain  1: * omega x[i]  2: * du[c]  3: the du block
+    if (blk <= H) { src = a.da + (long long)blk * slot_floats; }
+    else if (blk < H + 1 + si) { src = a.da; kind = 1; col = blk - H - 1; }
+    else if (blk < H + 1 + si + so) { src = a.save + (long long)H * slot_floats; kind = 2; col = blk - H - 1 - si; }
+    else { kind = 3; }
+    const float om0 = plan_omega(pl, 0);
+    float4 fn[NQ];
+    float mul_n = 1.f;
+    auto fetch = [&](long long t) {
+      const long long b = r0 + t * 64 + r;
+      const bool live = t < nsub && b < r1;
+      mul_n = 1.f;
+      if (kind == 3) {
+#pragma unroll
+        for (int c = 0; c < NQ; ++c) fn[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (live && q2 == 0) {
+          float d[NIF_MAX_SO];
+#pragma unroll
+          for (int c = 0; c < NIF_MAX_SO; ++c) d[c] = c < so ? __ldg(&a.du[b * so + c]) : 0.f;
+          fn[0] = make_float4(d[0], d[1], d[2], d[3]);
+          fn[1] = make_float4(d[4], d[5], d[6], d[7]);
+        }
+        return;
+      }
+      const float* row = src + bf_tiled_row(live ? b : r0, NP) + (long long)(q2 * NQ) * 128;
+#pragma unroll
+      for (int c = 0; c < NQ; ++c) fn[c] = live ? ldg4(row + c * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (live && kind == 1) mul_n = om0 * __ldg(&a.x[b * si + col]);
+      if (live && kind == 2) mul_n = __ldg(&a.du[b * so + col]);
+    };
+    fetch(sl);
+    long long n_mine = 0;
+    for (long long t = sl; t < nsub; t += 2, ++n_mine) {
+      float4 f[NQ];
+      const float mul = mul_n;
+#pragma unroll
+      for (int c = 0; c < NQ; ++c) f[c] = fn[c];
+      fetch(t + 2);
+      mbar_wait(&slot_empty[sl], (uint32_t)((n_mine & 1) ^ 1));
+      unsigned char* Bt = smem + sl * SLOT_BYTES + A_BYTES;
+#pragma unroll
+      for (int u = 0; u < NQ / 2; ++u) {
+        const float4 p0 = f[2 * u], p1 = f[2 * u + 1];
+        const uint32_t mg = (uint32_t)(q2 * (NQ / 2) + u);
+        *reinterpret_cast<uint4*>(Bt + mg * 1024u + koff) =
+            make_uint4(bf_pack2(mul * p0.x, mul * p0.y), bf_pack2(mul * p0.z, mul * p0.w), bf_pack2(mul * p1.x, mul * p1.y),
+                       bf_pack2(mul * p1.z, mul * p1.w));
+      }
+      fence_async_smem();
+      mbar_arrive(&slot_full[sl]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 12) tc_dealloc(tmem, 128);
+}
+
+int nif_bf_bwd_edge_impl(const Plan& pl, long long B, const float* z, const float* x, const float* save, const float* da,
+                         const float* du, int S, long long rows_per_split, int Q, float* part, cudaStream_t st) {
+  if (!nif_plan_uses_bf(pl) || pl.K < 1 || pl.K + 1 > 128) return NIF_E_UNSUPPORTED;
+  BfEdgeArgs a;
+  a.B = B; a.rows_per_split = rows_per_split; a.S = S; a.Q = Q;
+  a.z = z; a.x = x; a.save = save; a.da = da; a.du = du; a.part = part;
+  const size_t smem = 2 * (size_t)(16384 + pl.NP * 128);
+  dim3 grid((unsigned)(pl.H + 1 + pl.si + pl.so + 1), (unsigned)S);
+  if (pl.NP == 128) {
+    NIF_CUDA_CHECK(cudaFuncSetAttribute(nif_bf_bwd_edge_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    { NIF_PROF("nif_bf_bwd_edge_kernel", st); nif_bf_bwd_edge_kernel<128><<<grid, BFE_THREADS, smem, st>>>(pl, a); }
+  } else {
+    NIF_CUDA_CHECK(cudaFuncSetAttribute(nif_bf_bwd_edge_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    { NIF_PROF("nif_bf_bwd_edge_kernel", st); nif_bf_bwd_edge_kernel<64><<<grid, BFE_THREADS, smem, st>>>(pl, a); }
   }
   NIF_CUDA_CHECK(cudaGetLastError());
   return NIF_OK;

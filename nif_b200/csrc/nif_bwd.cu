@@ -749,6 +749,23 @@ int nif_bf_bwd_data_impl(const Plan& pl, long long B, const float* z, const floa
                          const float* save, const float* du, float* da, float* dz, cudaStream_t st);
 int nif_bf_bwd_weight_impl(const Plan& pl, long long B, const float* z, const float* save, const float* da, int S,
                            long long rows_per_split, float* part, cudaStream_t st);
+int nif_bf_bwd_edge_impl(const Plan& pl, long long B, const float* z, const float* x, const float* save, const float* da,
+                         const float* du, int S, long long rows_per_split, int Q, float* part, cudaStream_t st);
+// batch splits of the bf16 thin-term kernel: (H + 1 + si + so + 1) feature blocks per split, whole waves of CTAs
+static int nif_bf_edge_splits(const Plan& pl, long long B) {
+  const long long items = pl.H + 1 + pl.si + pl.so + 1;
+  long long s_max = (B + 511) / 512;
+  if (s_max < 1) s_max = 1;
+  if (s_max > 96) s_max = 96;
+  long long best = 1;
+  double best_eff = 0.0;
+  for (long long S = 1; S <= s_max; ++S) {
+    const long long ctas = items * S, waves = (ctas + 147) / 148;
+    const double eff = (double)ctas / (double)(waves * 148);
+    if (eff > best_eff + 1e-9) { best_eff = eff; best = S; }
+  }
+  return (int)best;
+}
 
 static long long round_up(long long v, long long m) { return (v + m - 1) / m * m; }
 // batch splits of the bf16 weight-gradient kernel: one CTA per SM and every CTA costs the same, so the count that
@@ -765,11 +782,14 @@ static int nif_bf_wgt_splits(const Plan& pl, long long B) {
     s_min = (B + rows - 1) / rows;
     if (s_max < s_min) s_max = s_min;
   }
+  // every split writes (and the un-packing kernel reads) a full partial image: the smallest count that fills its last
+  // wave to 90 %, else the best fill found
   long long best = s_min;
   double best_eff = 0.0;
   for (long long S = s_min; S <= s_max; ++S) {
     const long long ctas = items * S, waves = (ctas + 147) / 148;
     const double eff = (double)ctas / (double)(waves * 148);
+    if (eff >= 0.9) return (int)S;
     if (eff > best_eff + 1e-9) { best_eff = eff; best = S; }
   }
   return (int)best;
@@ -859,6 +879,10 @@ GradWs nif_grad_ws_layout(const Plan& pl, long long B) {
   w.S_e = (int)((B + w.rows_e - 1) / w.rows_e);
   if (w.S_e < 1) w.S_e = 1;
   w.S_e_ws = w.S_e;  // partials the workspace holds (S_e stays the CUDA-core kernel's split count)
+  if (nif_plan_uses_bf(pl) && pl.K >= 1) {  // room for the bf16 thin-term kernel's splits
+    const int s_bf = nif_bf_edge_splits(pl, B);
+    if (s_bf > w.S_e_ws) w.S_e_ws = s_bf;
+  }
   if (nif_plan_uses_tc(pl)) {  // room for the tensor-core thin-term kernel's splits (accumulation cap)
     const int s_tc = nif_tc_edge_splits(pl, B);
     if (s_tc > w.S_e_ws) w.S_e_ws = s_tc;
@@ -938,12 +962,24 @@ int nif_backward_impl(const Plan& pl, long long B, const float* z, const float* 
     if (rcb == NIF_OK) {
       rcb = nif_bf_bwd_weight_impl(pl, B, z, save, ws + w.da, w.S_h, w.rows_h, ws + w.part_h, st);
       if (rcb != NIF_OK) return rcb;
-      EdgeArgs e;
-      e.B = B; e.rows_per_split = w.rows_e; e.S = w.S_e; e.Q = w.Q;
-      e.z = z; e.x = x; e.save = save; e.da = ws + w.da; e.du = du; e.part = ws + w.part_e; e.no_bias = 0; e.tiled = 1;
-      e.q_begin = 0; e.q_end = w.Q;
-      NIF_CUDA_CHECK(launch_edge(pl, e, w, st));
-      return nif_unpack_grad_impl(pl, w.S_h, ws + w.part_h, w.S_e, ws + w.part_e, w.Q, dw_h, db_h, beta, st);
+      int S_e_used = w.S_e;
+      {  // thin terms: tensor-core batch reduction; shapes it does not cover use the CUDA-core kernel
+        int S_bf = nif_bf_edge_splits(pl, B);
+        if (S_bf > w.S_e_ws) S_bf = w.S_e_ws;
+        const long long rows_bf = round_up((B + S_bf - 1) / S_bf, 64);
+        S_bf = (int)((B + rows_bf - 1) / rows_bf);
+        rcb = nif_bf_bwd_edge_impl(pl, B, z, x, save, ws + w.da, du, S_bf, rows_bf, w.Q, ws + w.part_e, st);
+        if (rcb == NIF_OK) S_e_used = S_bf;
+        else if (rcb != NIF_E_UNSUPPORTED) return rcb;
+        else {
+          EdgeArgs e;
+          e.B = B; e.rows_per_split = w.rows_e; e.S = w.S_e; e.Q = w.Q;
+          e.z = z; e.x = x; e.save = save; e.da = ws + w.da; e.du = du; e.part = ws + w.part_e; e.no_bias = 0; e.tiled = 1;
+          e.q_begin = 0; e.q_end = w.Q;
+          NIF_CUDA_CHECK(launch_edge(pl, e, w, st));
+        }
+      }
+      return nif_unpack_grad_impl(pl, w.S_h, ws + w.part_h, S_e_used, ws + w.part_e, w.Q, dw_h, db_h, beta, st);
     }
     if (rcb != NIF_E_UNSUPPORTED) return rcb;
   }
