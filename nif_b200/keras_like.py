@@ -620,8 +620,16 @@ class Model:
         B = inp.shape[0]
         xs = inp[:, n.pi_dim: n.pi_dim + n.si_dim].contiguous()
         p_in = inp[:, : n.pi_dim].contiguous()
+        # the re-laid weight image depends on the parameters only: it is built on a second stream while the trunk runs
+        # (a fork / join that a CUDA graph records as two parallel branches)
+        cur = torch.cuda.current_stream()
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream(device=n.device)
+        self._side.wait_stream(cur)
+        with torch.cuda.stream(self._side):
+            packed = self._packed_weights()
         z, tstash = n._trunk.forward(p_in, n.theta_trunk, save=True)
-        packed = self._packed_weights()
+        cur.wait_stream(self._side)
         u, stash = eng.forward(z, xs, packed, save=True)
         dz = eng.mse_backward(z, xs, packed, u, stash, tgt, sw, 1.0 / gb, self._loss_buf,
                               n._gviews[n._last_names[0]], n._gviews[n._last_names[1]], 0.0)
