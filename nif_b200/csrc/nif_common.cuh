@@ -44,11 +44,6 @@ struct Plan {
   // KZ = K+1 rounded up to 16; LPC = outputs per XL tile (2 if 2*KZ <= 128 else 1); NLC = ceil(so / LPC).
   int KZ, LPC, NLC;
   long long off_TCX, off_TCS2;
-  // coefficient table of the thin dz terms (nif_dz_edge_kernel):  GE[slab][f][kappa], kappa < KG = K rounded up to 4,
-  // slabs = (H+1) bias-row slabs C_m[kappa][f] | si first-matrix slabs M0[kappa][i][f] | so last-matrix slabs
-  // ML[kappa][f][c] | one slab CL[kappa][f < so]
-  int KG;
-  long long off_GE;
   // wide_last (trunk plans): the last matrix [n x so] is wide (so up to 256); its gradient runs through the
   // hidden-matrix batch-reduction GEMM as matrix index H (rows h_{H+1}, columns = the seed du padded to NP)
   // instead of the column-per-thread edge kernel.
@@ -61,7 +56,9 @@ struct Plan {
 };
 __host__ __device__ inline long long plan_x0_floats(const Plan& p) { return 64LL * p.KZ; }            // one X0 / XC chunk [hi|lo]
 __host__ __device__ inline long long plan_xl_floats(const Plan& p) { return (long long)p.LPC * p.KZ * 64; }       // one XL chunk [hi|lo]
-__host__ __device__ inline int plan_n_small(const Plan& p) { return p.si + 1 + p.H + p.NLC; }        // number of small tiles
+// small tiles: X0[si+1], XC[H], XL[NLC] (forward), then BCt[m] m = 0..H and B0t[i] i < si (reverse data pass: [KZ (kappa) x 64 (j)]
+// tiles of C_m[kappa][j] and M0[kappa][i][j], the thin dz terms)
+__host__ __device__ inline int plan_n_small(const Plan& p) { return p.si + 1 + p.H + p.NLC + p.H + 1 + p.si; }
 #define NIF_TC_CHUNK_FLOATS 8192   // [hi | lo] x 128 x 64 fp16 = 32 KB, counted in floats
 
 __host__ __device__ inline int plan_w_off(const Plan& p, int m) {  // reference column offset of matrix m

@@ -36,17 +36,14 @@ void nif_plan_layout(Plan* pp) {
   p.KZ = (p.K + 1 + 15) / 16 * 16;
   p.LPC = (2 * p.KZ <= 128) ? 2 : 1;
   p.NLC = (p.so + p.LPC - 1) / p.LPC;
-  p.off_TCF = p.off_TCB = p.off_TCS = p.off_TCX = p.off_TCS2 = p.off_GE = 0;
-  p.KG = 0;
+  p.off_TCF = p.off_TCB = p.off_TCS = p.off_TCX = p.off_TCS2 = 0;
   if (p.tc) {
     off = (off + 31) / 32 * 32;
     p.off_TCF = off; off += (long long)p.H * p.NCH * NIF_TC_CHUNK_FLOATS;
     p.off_TCB = off; off += (long long)p.H * p.NCH * NIF_TC_CHUNK_FLOATS;
     p.off_TCS = off; off += up4((long long)p.H * p.KP);
-    p.off_TCX = off; off += (p.si + 1 + p.H) * plan_x0_floats(p) + p.NLC * plan_xl_floats(p);
+    p.off_TCX = off; off += (p.si + 1 + p.H) * plan_x0_floats(p) + p.NLC * plan_xl_floats(p) + (p.H + 1 + p.si) * plan_x0_floats(p);
     p.off_TCS2 = off; off += up4(plan_n_small(p));
-    p.KG = (p.K + 3) / 4 * 4;
-    p.off_GE = off; off += (long long)(p.H + 1 + p.si + p.so + 1) * 64 * p.KG;
   }
   p.off_WF = p.off_WB = p.off_WX = 0;
   if (p.bf) {
@@ -116,9 +113,16 @@ __device__ __forceinline__ float tcx_value(const Plan& pl, const float* __restri
     return src_at(pl, w_h, b_h, 0, col, plan_b_off(pl, m) + row);
   }
   const int q = T - (pl.si + 1 + pl.H);  // XL[q]: row = c_l * KZ + kappa, col = i
-  const int cl = row / pl.KZ, kk = row % pl.KZ, c = pl.LPC * q + cl;
-  if (kk >= K1 || c >= pl.so || col >= n) return 0.f;
-  return src_at(pl, w_h, b_h, 0, kk, plan_w_off(pl, pl.H + 1) + col * pl.so + c);
+  if (q < pl.NLC) {
+    const int cl = row / pl.KZ, kk = row % pl.KZ, c = pl.LPC * q + cl;
+    if (kk >= K1 || c >= pl.so || col >= n) return 0.f;
+    return src_at(pl, w_h, b_h, 0, kk, plan_w_off(pl, pl.H + 1) + col * pl.so + c);
+  }
+  // reverse-pass tiles, row = kappa, col = j:  BCt[m] = C_m[kappa][j],  B0t[i] = M0[kappa][i][j]
+  if (row >= K1 || col >= n) return 0.f;
+  const int t2 = q - pl.NLC;
+  if (t2 <= pl.H) return src_at(pl, w_h, b_h, 0, row, plan_b_off(pl, t2) + col);
+  return src_at(pl, w_h, b_h, 0, row, (t2 - pl.H - 1) * n + col);
 }
 
 __global__ void __launch_bounds__(256) nif_pack_kernel(const Plan pl, long long G, const float* __restrict__ w_h,
@@ -203,6 +207,7 @@ __global__ void __launch_bounds__(256) nif_pack_kernel(const Plan pl, long long 
       // small forward operand tiles; float slot -> (tile, hi/lo, row, col pair)
       r -= pl.off_TCX;
       const long long nz = (long long)(pl.si + 1 + pl.H) * plan_x0_floats(pl);
+      const long long nl = (long long)pl.NLC * plan_xl_floats(pl);
       int T, lo, row, col;
       if (r < nz) {
         T = (int)(r / plan_x0_floats(pl));
@@ -211,11 +216,19 @@ __global__ void __launch_bounds__(256) nif_pack_kernel(const Plan pl, long long 
         const int rg = t / (4 * pl.KZ); t %= 4 * pl.KZ;   // 8-row group: KZ/8 chunks x 32 float slots
         const int kc = t / 32; t %= 32;
         row = rg * 8 + t / 4; col = kc * 8 + (t % 4) * 2;
-      } else {
+      } else if (r < nz + nl) {
         r -= nz;
         T = pl.si + 1 + pl.H + (int)(r / plan_xl_floats(pl));
         int t = (int)(r % plan_xl_floats(pl));
         lo = t / (pl.LPC * pl.KZ * 32); t %= pl.LPC * pl.KZ * 32;  // hi tile: LPC*KZ rows x 64 fp16
+        const int rg = t / 256; t %= 256;
+        const int kc = t / 32; t %= 32;
+        row = rg * 8 + t / 4; col = kc * 8 + (t % 4) * 2;
+      } else {  // reverse-pass tiles [KZ rows x 64]: 8-row group = 8 k-chunks x 32 float slots
+        r -= nz + nl;
+        T = pl.si + 1 + pl.H + pl.NLC + (int)(r / plan_x0_floats(pl));
+        int t = (int)(r % plan_x0_floats(pl));
+        lo = t / (pl.KZ * 32); t %= pl.KZ * 32;
         const int rg = t / 256; t %= 256;
         const int kc = t / 32; t %= 32;
         row = rg * 8 + t / 4; col = kc * 8 + (t % 4) * 2;
@@ -226,16 +239,6 @@ __global__ void __launch_bounds__(256) nif_pack_kernel(const Plan pl, long long 
       if (!lo) out = __floats2half2_rn(a0, a1);
       else out = __floats2half2_rn(a0 - __half2float(__float2half_rn(a0)), a1 - __half2float(__float2half_rn(a1)));
       v = __uint_as_float(*reinterpret_cast<uint32_t*>(&out));
-    } else if (r >= pl.off_GE && r < pl.off_GE + (long long)(H + 1 + pl.si + pl.so + 1) * 64 * pl.KG) {
-      r -= pl.off_GE;
-      const int k = (int)(r % pl.KG); r /= pl.KG;
-      const int f = (int)(r % 64); const int sb = (int)(r / 64);
-      if (k < pl.K) {
-        if (sb <= H) { if (f < n) v = src_at(pl, w_h, b_h, g, k, plan_b_off(pl, sb) + f); }
-        else if (sb < H + 1 + pl.si) { if (f < n) v = src_at(pl, w_h, b_h, g, k, (sb - H - 1) * n + f); }
-        else if (sb < H + 1 + pl.si + pl.so) { if (f < n) v = src_at(pl, w_h, b_h, g, k, plan_w_off(pl, H + 1) + f * pl.so + (sb - H - 1 - pl.si)); }
-        else if (f < pl.so) v = src_at(pl, w_h, b_h, g, k, plan_b_off(pl, H + 1) + f);
-      }
     } else {
       continue;  // scale tables are written by nif_pack_scales_kernel before this kernel runs
     }
@@ -253,7 +256,9 @@ __global__ void __launch_bounds__(256) nif_pack_scales_kernel(const Plan pl, con
   const int n = pl.n;
   float m = 0.f;
   if (small) {
-    const int rows = (T <= pl.si + pl.H) ? 64 : pl.LPC * pl.KZ, cols = (T <= pl.si + pl.H) ? pl.KZ : 64;
+    const bool fwd_jk = T <= pl.si + pl.H;                      // X0 / XC: [64 (j) x KZ]
+    const bool is_xl = !fwd_jk && T < pl.si + 1 + pl.H + pl.NLC;  // XL: [LPC * KZ x 64]; else BCt / B0t: [KZ x 64]
+    const int rows = fwd_jk ? 64 : (is_xl ? pl.LPC * pl.KZ : pl.KZ), cols = fwd_jk ? pl.KZ : 64;
     for (int e = threadIdx.x; e < rows * cols; e += 256) m = fmaxf(m, fabsf(tcx_value(pl, w_h, b_h, T, e / cols, e % cols)));
   } else if (kk <= pl.K)
     for (int e = threadIdx.x; e < n * n; e += 256) m = fmaxf(m, fabsf(src_at(pl, w_h, b_h, 0, kk, plan_w_off(pl, h + 1) + e)));

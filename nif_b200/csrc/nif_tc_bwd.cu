@@ -6,8 +6,11 @@
 //   dh_m[b][i]   = omega * sum_kappa zt[b][kappa] T[b][kappa][i]            epilogue, thread = row
 //   dz[b][kappa] += omega * sum_i T[b][kappa][i] h_m[b][i]                  epilogue, thread = row (no shuffles)
 //   da_{m-1}     = dh_m * act'(pre_{m-1})                                   -> global stash + next operand tile
-// The thin dz terms (bias rows of every layer, first and last matrix) are added by nif_dz_edge_kernel, which
-// only needs the stashed da_m / h / x rows.
+// The thin dz terms are tensor-core chunks of the same kernel, over operand tiles that are in shared memory anyway:
+//   bias rows     dz[kappa] += (da_m @ BCt[m])[kappa]                       A = da_m tile,     N = KZ     (m = H .. 0)
+//   first matrix  dz[kappa] += omega x[i] (da_0 @ B0t[i])[kappa]            A = da_0 tile,     N = KZ
+//   last matrix   dz[kappa] += du[c] ((h_{H+1} @ XL[q])[c_l, kappa] + CL[kappa][c])   A = h_{H+1} tile, N = LPC KZ
+// (round 1 ran them in a separate CUDA-core kernel, nif_dz_edge_kernel: 111 us of the 1.5 ms step for 1 % of its flops).
 // Also records max|da_m| per layer and max|zt|, max|h_m| (atomicMax on the float bits) for the operand scales
 // of the weight-gradient GEMM.
 #include "nif_tc.cuh"
@@ -22,6 +25,11 @@ struct TcBwdArgs {
   unsigned* maxes;  // [0..H] max|da_m| bits, [H+1] max|zt| bits, [H+2 .. 2H+2] max|h_m| bits (m = 1..H+1)
   int nst;          // weight-stream stages (3 where shared memory allows, else 2)
 };
+
+// slots of the maxima buffer beyond [0, 2H + 2): operand-scale bounds for nif_tc_bwd_edge_kernel
+#define NIF_MAX_X 192    // + i : max |x[:, i]|
+#define NIF_MAX_DU 200   // + c : max |du[:, c]|
+#define NIF_MAX_HL 208   //       max |h_{H+1}|
 
 #define TCB_THREADS 384  // 8 epilogue warps + MMA warp + producer warp + 2 idle warps (register donors)
 #define TCB_MAX_STAGES 3
@@ -61,39 +69,51 @@ __device__ __forceinline__ void tcb_issue(const Plan& pl, const TcBwdArgs& a, un
   uint64_t* t_empty = t_full + 4;
   uint64_t* a_ready = t_empty + 4;
   const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0) + (uint32_t)T * 256u;
-  const uint32_t idesc = tc_idesc_f16(128);
+  const uint32_t idesc_main = tc_idesc_f16(128);
+  const uint32_t idesc_kz = tc_idesc_f16(pl.KZ);
+  const uint32_t idesc_last = tc_idesc_f16(pl.LPC * pl.KZ);
+  const uint32_t lo_kz = (uint32_t)(pl.KZ * 128) >> 4;             // lo half of a [KZ x 64] tile, in descriptor units
+  const uint32_t lo_last = (uint32_t)(pl.LPC * pl.KZ * 128) >> 4;  // lo half of an XL tile
   const uint64_t da_hi = tc_make_desc(smem_u32(A_all + T * 2 * TC_TILE_BYTES));
   const uint64_t da_lo = tc_make_desc(smem_u32(A_all + T * 2 * TC_TILE_BYTES + TC_TILE_BYTES));
-  const uint64_t db0_hi = tc_make_desc(smem_u32(Bst));
-  const uint64_t db0_lo = tc_make_desc(smem_u32(Bst + TC_TILE_BYTES));
-  const uint32_t H = (uint32_t)pl.H, NCH = (uint32_t)pl.NCH;
-  uint32_t g = 0, L = 0;     // chunk and layer counters
+  const uint64_t db0 = tc_make_desc(smem_u32(Bst));
+  const uint32_t H = (uint32_t)pl.H, NCH = (uint32_t)pl.NCH, NLC = (uint32_t)pl.NLC, si = (uint32_t)pl.si;
+  uint32_t g = 0, ar = 0;    // chunk counter; operand-tile publications consumed
   uint32_t s = 0, sph = 0;   // weight-stream stage and its phase
   const int lane = threadIdx.x & 31;
   (void)lane;
 #ifdef NIF_TRACE
   int trace_n = 0;
 #endif
-  for (long long p = 0; p < my_pairs; ++p)
-    for (uint32_t h = 0; h < H; ++h, ++L)
-      for (uint32_t c = 0; c < NCH; ++c, ++g) {
-        const uint32_t as = g & 1u;  // accumulator stage: the MMAs of chunk g+1 run while chunk g is drained
-        if (c == 0) mbar_wait(&a_ready[T], L & 1u);
-        mbar_wait(&t_empty[2 * T + as], ((g >> 1) & 1u) ^ 1u);
-        if (T == 0 && lane == 0) TRACE(2, g * 8 + 2);
-        mbar_wait(&b_full[s], sph);
-        if (T == 0 && lane == 0) TRACE(2, g * 8 + 1);
-        tc_fence_after();
-        const uint64_t boff = (uint64_t)(s * (TCB_STAGE_BYTES >> 4));
-        if (tc_elect_one()) {
-          tc_mma_split_k64(tmem_u + as * 128u, da_hi, da_lo, db0_hi + boff, db0_lo + boff, idesc);
-          tc_commit(&t_full[2 * T + as]);
-          tc_commit(&b_empty[s]);
-        }
-        __syncwarp();
-        if (T == 0 && lane == 0) TRACE(2, g * 8 + 3);
-        if (++s == nst) { s = 0; sph ^= 1u; }
-      }
+  // one chunk: K = 64 (4 k-steps, three products); lo_off: distance of the B tile's lo half
+  auto chunk = [&](bool wait_a, uint32_t idesc, uint32_t lo_off) {
+    const uint32_t as = g & 1u;  // accumulator stage: the MMAs of chunk g+1 run while chunk g is drained
+    if (wait_a) { mbar_wait(&a_ready[T], ar & 1u); ++ar; }
+    mbar_wait(&t_empty[2 * T + as], ((g >> 1) & 1u) ^ 1u);
+    if (T == 0 && lane == 0) TRACE(2, g * 8 + 2);
+    mbar_wait(&b_full[s], sph);
+    if (T == 0 && lane == 0) TRACE(2, g * 8 + 1);
+    tc_fence_after();
+    const uint64_t boff = (uint64_t)(s * (TCB_STAGE_BYTES >> 4));
+    if (tc_elect_one()) {
+      tc_mma_split_k64(tmem_u + as * 128u, da_hi, da_lo, db0 + boff, db0 + boff + lo_off, idesc);
+      tc_commit(&t_full[2 * T + as]);
+      tc_commit(&b_empty[s]);
+    }
+    __syncwarp();
+    if (T == 0 && lane == 0) TRACE(2, g * 8 + 3);
+    ++g;
+    if (++s == nst) { s = 0; sph ^= 1u; }
+  };
+  for (long long p = 0; p < my_pairs; ++p) {
+    for (uint32_t q = 0; q < NLC; ++q) chunk(q == 0, idesc_last, lo_last);   // last matrix: A = h_{H+1} tile
+    for (uint32_t h = 0; h < H; ++h) {
+      chunk(true, idesc_kz, lo_kz);                                           // bias rows: A = da_m tile (just published)
+      for (uint32_t c = 0; c < NCH; ++c) chunk(false, idesc_main, (uint32_t)(TC_TILE_BYTES >> 4));
+    }
+    chunk(true, idesc_kz, lo_kz);                                             // bias rows of layer 0: A = da_0 tile
+    for (uint32_t i = 0; i < si; ++i) chunk(false, idesc_kz, lo_kz);          // first matrix
+  }
 }
 
 __global__ void __launch_bounds__(TCB_THREADS, 1) nif_tc_bwd_data_kernel(const Plan pl, const TcBwdArgs a) {
@@ -112,7 +132,8 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) nif_tc_bwd_data_kernel(const P
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_ready + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int K = pl.K, K1 = pl.K + 1, KP = pl.KP, NCH = pl.NCH, H = pl.H, n = pl.n, so = pl.so;
+  const int K = pl.K, K1 = pl.K + 1, KP = pl.KP, NCH = pl.NCH, H = pl.H, n = pl.n, so = pl.so, si = pl.si;
+  const int KZ = pl.KZ, NLC = pl.NLC, LPC = pl.LPC;
 #ifdef NIF_TRACE
   int trace_n = 0;
 #endif
@@ -141,19 +162,33 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) nif_tc_bwd_data_kernel(const P
   if (warp >= 8) {
   tc_reg_dec<56>();  // MMA / producer / idle warps donate registers: 128 x (168 - 56) freed = 256 x (224 - 168) claimed below
   if (warp == 9) {
-    if (lane == 0) {  // weight-stream producer: hidden matrices in reverse order
+    if (lane == 0) {  // weight-stream producer: the chunk schedule of tcb_issue
       long long g = 0;
       const float* src0 = a.packed + pl.off_TCB;
-      for (long long t = 0; t < my_pairs; ++t)
-        for (int h = H - 1; h >= 0; --h)
-          for (int c = 0; c < NCH; ++c, ++g) {
-            const int s = (int)(g % nst);
-            mbar_wait(&b_empty[s], (uint32_t)(((g / nst) & 1) ^ 1));
-            TRACE(3, g);
-            mbar_expect_tx(&b_full[s], TCB_STAGE_BYTES);
-            bulk_g2s(Bst + s * TCB_STAGE_BYTES, src0 + ((long long)h * NCH + c) * NIF_TC_CHUNK_FLOATS,
-                     TCB_STAGE_BYTES, &b_full[s]);
-          }
+      const float* tcx = a.packed + pl.off_TCX;
+      const uint32_t small_bytes = (uint32_t)pl.KZ * 256u;                 // [KZ x 64] hi | lo
+      const uint32_t last_bytes = (uint32_t)(pl.LPC * pl.KZ) * 256u;       // XL tile hi | lo
+      const int NLC = pl.NLC, si = pl.si;
+      const long long t_xl = (long long)(si + 1 + H) * plan_x0_floats(pl);                      // first XL tile
+      const long long t_bc = t_xl + (long long)NLC * plan_xl_floats(pl);                        // first BCt tile
+      const long long t_b0 = t_bc + (long long)(H + 1) * plan_x0_floats(pl);                    // first B0t tile
+      auto put = [&](const float* src, uint32_t bytes) {
+        const int s = (int)(g % nst);
+        mbar_wait(&b_empty[s], (uint32_t)(((g / nst) & 1) ^ 1));
+        TRACE(3, g);
+        mbar_expect_tx(&b_full[s], bytes);
+        bulk_g2s(Bst + s * TCB_STAGE_BYTES, src, bytes, &b_full[s]);
+        ++g;
+      };
+      for (long long t = 0; t < my_pairs; ++t) {
+        for (int q = 0; q < NLC; ++q) put(tcx + t_xl + (long long)q * plan_xl_floats(pl), last_bytes);
+        for (int h = H - 1; h >= 0; --h) {
+          put(tcx + t_bc + (long long)(h + 1) * plan_x0_floats(pl), small_bytes);
+          for (int c = 0; c < NCH; ++c) put(src0 + ((long long)h * NCH + c) * NIF_TC_CHUNK_FLOATS, TCB_STAGE_BYTES);
+        }
+        put(tcx + t_bc, small_bytes);
+        for (int i = 0; i < si; ++i) put(tcx + t_b0 + (long long)i * plan_x0_floats(pl), small_bytes);
+      }
     }
   } else if (warp == 8) {
     tcb_issue<0>(pl, a, smem, bars, tmem, my_pairs);
@@ -195,13 +230,66 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) nif_tc_bwd_data_kernel(const P
         for (int kk = 0; kk < K1; ++kk) zmax = fmaxf(zmax, fabsf(zs[kk * 128 + r]));
         warp_atomic_max(&a.maxes[H + 1], live ? zmax : 0.f);
       }
+      const float* invX = a.packed + pl.off_TCS2;  // inverse scales of the small tiles
+      const int T_xl = si + 1 + H, T_bc = T_xl + NLC, T_b0 = T_bc + H + 1;
+      // accumulator stage g & 1 of this tile: wait for its MMAs; returns its TMEM address
+      auto chunk_begin = [&]() -> uint32_t {
+        if (r == 0) TRACE(wg, g * 4 + 0);
+        mbar_wait(&t_full[2 * wg + (int)(g & 1)], (uint32_t)((g >> 1) & 1));
+        if (r == 0) TRACE(wg, g * 4 + 1);
+        tc_fence_after();
+        return tm + (uint32_t)(g & 1) * 128u;
+      };
+      auto chunk_end = [&]() {
+        tc_fence_before();
+        mbar_arrive(&t_empty[2 * wg + (int)(g & 1)]);
+        if (r == 0) TRACE(wg, g * 4 + 2);
+        ++g;
+      };
+      // an N = KZ chunk: dz[kappa] += coef * D[col0 + kappa]
+      auto drain_kz = [&](float coef, uint32_t col0) {
+        const uint32_t td = chunk_begin();
+        for (int k0 = 0; k0 < KZ; k0 += 16) {
+          float v[16];
+          tc_ld16(td + col0 + (uint32_t)k0, v);
+          tc_wait_ld();
+#pragma unroll
+          for (int e = 0; e < 16; ++e)
+            if (k0 + e < K1) dzs[(k0 + e) * 128 + r] = fmaf(coef, v[e], dzs[(k0 + e) * 128 + r]);
+        }
+      };
+
+      float dy[NIF_MAX_SO];
+#pragma unroll
+      for (int c = 0; c < NIF_MAX_SO; ++c) dy[c] = (c < so && live) ? __ldg(&a.du[b * so + c]) : 0.f;
+      // ---- operand tile h_{H+1} (the last matrix's dz terms) and the bounds the thin weight-gradient kernel scales with ----
+      float inv_hl;
+      {
+        float hl[64];
+        const float* hsrc = a.save + (long long)H * slot_floats + nif_tiled_row(b);
+        float hmax = 0.f;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (live) q = ldg4(hsrc + c * 128);
+          hl[4 * c] = q.x; hl[4 * c + 1] = q.y; hl[4 * c + 2] = q.z; hl[4 * c + 3] = q.w;
+          hmax = fmaxf(fmaxf(hmax, fabsf(q.x)), fmaxf(fabsf(q.y), fmaxf(fabsf(q.z), fabsf(q.w))));
+        }
+        warp_atomic_max(&a.maxes[NIF_MAX_HL], hmax);
+        float sc_h;
+        tc_row_scale(hmax, sc_h, inv_hl);
+        tc_store_row_split(A_hi, A_lo, r, hl, sc_h);
+        fence_async_smem();
+        mbar_arrive(&a_ready[wg]);
+        for (int i = 0; i < si; ++i) warp_atomic_max(&a.maxes[NIF_MAX_X + i], live ? fabsf(__ldg(&a.x[b * si + i])) : 0.f);
+#pragma unroll
+        for (int c = 0; c < NIF_MAX_SO; ++c)
+          if (c < so) warp_atomic_max(&a.maxes[NIF_MAX_DU + c], fabsf(dy[c]));
+      }
 
       float acc[64];
       // ---- last matrix (n -> so): dh_{H+1}[i] = sum_kappa zt[kappa] sum_c ML[kappa][i][c] du[c]  (CUDA cores) ----
       {
-        float dy[NIF_MAX_SO];
-#pragma unroll
-        for (int c = 0; c < NIF_MAX_SO; ++c) dy[c] = (c < so && live) ? __ldg(&a.du[b * so + c]) : 0.f;
 #pragma unroll
         for (int i = 0; i < 64; ++i) acc[i] = 0.f;
         const float* ML = a.packed + pl.off_ML;
@@ -229,6 +317,33 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) nif_tc_bwd_data_kernel(const P
         }
       }
 
+      // ---- last matrix, its dz terms: dz[kappa] += du[c] * ((h_{H+1} @ ML[kappa])[c] + CL[kappa][c]) ----
+      {
+        const float* CL = a.packed + pl.off_C + (long long)(H + 1) * K1 * 64;
+        for (int q = 0; q < NLC; ++q) {
+          const float sL = inv_hl * __ldg(&invX[T_xl + q]);
+          const uint32_t td = chunk_begin();
+          for (int cl = 0; cl < LPC; ++cl) {
+            const int c = LPC * q + cl;
+            float dyc = 0.f;
+#pragma unroll
+            for (int cc = 0; cc < NIF_MAX_SO; ++cc) if (cc == c) dyc = dy[cc];
+            for (int k0 = 0; k0 < KZ; k0 += 16) {
+              float v[16];
+              tc_ld16(td + (uint32_t)(cl * KZ + k0), v);
+              tc_wait_ld();
+#pragma unroll
+              for (int e = 0; e < 16; ++e) {
+                const int kk = k0 + e;
+                if (kk < K1 && c < so)
+                  dzs[kk * 128 + r] = fmaf(dyc, fmaf(sL, v[e], __ldg(&CL[(long long)kk * 64 + c])), dzs[kk * 128 + r]);
+              }
+            }
+          }
+          chunk_end();
+        }
+      }
+
       // ---- layers H .. 0: da_m = dh_{m+1} * d_m; hidden matrices on the tensor cores ----
       for (int m = H; m >= 0; --m) {
         const float* dsv = a.save + (long long)(H + 1 + m) * slot_floats + nif_tiled_row(b);  // d_m row (tiled)
@@ -246,13 +361,23 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) nif_tc_bwd_data_kernel(const P
         }
         warp_atomic_max(&a.maxes[m], amax);
         if (r == 0) TRACE(wg, g * 4 + 3);  // da_m formed and stored
-        if (m == 0) break;
 
         float sc_a, inv_a;
         tc_row_scale(amax, sc_a, inv_a);
         tc_store_row_split(A_hi, A_lo, r, dav, sc_a);
         fence_async_smem();
         mbar_arrive(&a_ready[wg]);
+        // bias rows of layer m: dz[kappa] += sum_j C_m[kappa][j] da_m[j]
+        drain_kz(inv_a * __ldg(&invX[T_bc + m]), 0u);
+        chunk_end();
+        if (m == 0) {  // first matrix: dz[kappa] += omega x[i] sum_j M0[kappa][i][j] da_0[j]
+          const float om0 = plan_omega(pl, 0);
+          for (int i = 0; i < si; ++i) {
+            drain_kz(om0 * (live ? __ldg(&a.x[b * si + i]) : 0.f) * inv_a * __ldg(&invX[T_b0 + i]), 0u);
+            chunk_end();
+          }
+          break;
+        }
 
         // this layer's input row h_m (for the dz dot products)
         float hm[64];
@@ -279,18 +404,14 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) nif_tc_bwd_data_kernel(const P
         float sBn[2] = {om_inv * __ldg(&invBm[0]), om_inv * __ldg(&invBm[1])};
         float zkn[2] = {zs[r], zs[128 + r]};
 #pragma unroll 1
-        for (int c = 0; c < NCH; ++c, ++g) {
+        for (int c = 0; c < NCH; ++c) {
           const float sBc[2] = {sBn[0], sBn[1]}, zkc[2] = {zkn[0], zkn[1]};
           if (c + 1 < NCH) {
             sBn[0] = om_inv * __ldg(&invBm[2 * c + 2]); sBn[1] = om_inv * __ldg(&invBm[2 * c + 3]);
             zkn[0] = zs[(2 * c + 2) * 128 + r];
             zkn[1] = 2 * c + 3 < K1 ? zs[(2 * c + 3) * 128 + r] : 0.f;  // the padding coordinate of an odd K + 1
           }
-          if (r == 0) TRACE(wg, g * 4 + 0);
-          mbar_wait(&t_full[2 * wg + (int)(g & 1)], (uint32_t)((g >> 1) & 1));
-          if (r == 0) TRACE(wg, g * 4 + 1);
-          tc_fence_after();
-          const uint32_t td = tm + (uint32_t)(g & 1) * 128u;
+          const uint32_t td = chunk_begin();
 #pragma unroll
           for (int kl = 0; kl < 2; ++kl) {
             const int kk = 2 * c + kl;
@@ -314,9 +435,7 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) nif_tc_bwd_data_kernel(const P
             }
             if (kk < K1) dzs[kk * 128 + r] += sB * (s0 + s1);
           }
-          tc_fence_before();
-          mbar_arrive(&t_empty[2 * wg + (int)(g & 1)]);
-          if (r == 0) TRACE(wg, g * 4 + 2);
+          chunk_end();
         }
       }
 
@@ -328,166 +447,6 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) nif_tc_bwd_data_kernel(const P
   tc_fence_before();
   __syncthreads();
   if (warp == 8) tc_dealloc(tmem, 512);
-}
-
-// ---------------------------------------------------------------------------------------------------
-// thin dz terms, thread = row (CUDA cores; ~1 % of the reverse-pass FLOPs):
-//   dz[b][kappa] += sum_m sum_j C_m[kappa][j] da_m[b][j]                                  (bias rows, m = 0..H)
-//                 + sum_j da_0[b][j] * omega * sum_i x[b][i] M0[kappa][i][j]              (first matrix)
-//                 + sum_c du[b][c] * ( CL[kappa][c] + sum_i h_{H+1}[b][i] ML[kappa][i][c] ) (last matrix)
-// ---------------------------------------------------------------------------------------------------
-struct DzEdgeArgs {
-  long long B;
-  const float *x, *packed, *save, *da, *du;
-  float* dz;
-  unsigned* maxes;  // + NIF_MAX_X / NIF_MAX_DU / NIF_MAX_HL: operand-scale bounds for nif_tc_bwd_edge_kernel
-};
-// slots of the maxima buffer written here (the data pass owns [0, 2H + 2))
-#define NIF_MAX_X 192    // + i : max |x[:, i]|
-#define NIF_MAX_DU 200   // + c : max |du[:, c]|
-#define NIF_MAX_HL 208   //       max |h_{H+1}|
-
-// dz_edge[b][:] = F[b][:] @ G  with per-row features F (Q of them) and a shared coefficient matrix G [Q][K]:
-//   q in [0,(H+1)*64)            F = da_m[b][j]                 G = C_m[kappa][j]
-//   next si*64                   F = omega * x[b][i] da_0[b][j] G = M0[kappa][i][j]
-//   next 64*so                   F = h_{H+1}[b][i] du[b][c]     G = ML[kappa][i][c]
-//   next so                      F = du[b][c]                   G = CL[kappa][c]
-// G is staged through shared memory in slabs of 64 features; every thread keeps its K outputs in registers
-// (KT of them per pass over the features).
-// Every thread owns DZE_R = 2 rows (b and b + blockDim.x), so each coefficient read feeds two FMAs.  (One row per
-// thread -- twice the warps at 105 instead of 167 registers -- measured the same 112 us: the kernel is bound by its
-// instruction count, not by latency.)  The coefficient table GE[slab][f][kappa] is re-laid by nif_pack so that a slab
-// is staged into shared memory with coalesced vector loads.
-#define DZE_R 2
-template <int KT>
-__global__ void __launch_bounds__(128) nif_dz_edge_kernel(const Plan pl, const DzEdgeArgs a, int k0) {
-  __shared__ __align__(16) float Gs[64 * KT];
-  const int K = pl.K, H = pl.H, si = pl.si, so = pl.so, KG = pl.KG;
-  const long long b0 = blockIdx.x * (128LL * DZE_R) + threadIdx.x;
-  long long bb[DZE_R];
-  bool live[DZE_R];
-#pragma unroll
-  for (int w = 0; w < DZE_R; ++w) {
-    live[w] = b0 + 128 * w < a.B;
-    bb[w] = live[w] ? b0 + 128 * w : 0;
-  }
-  const float* GE = a.packed + pl.off_GE + k0;
-  const float om0 = plan_omega(pl, 0);
-  const long long slot_floats = nif_tiled_rows(a.B) * 64;  // da and the stash are in the tiled layout
-  float acc[DZE_R][KT];
-#pragma unroll
-  for (int w = 0; w < DZE_R; ++w)
-#pragma unroll
-    for (int k = 0; k < KT; ++k) acc[w][k] = 0.f;
-
-  if (k0 == 0) {  // bounds of the thin-term operands (rows this thread owns; dead rows repeat row 0)
-    for (int i = 0; i < si; ++i)
-    {
-      float mx = 0.f;
-#pragma unroll
-      for (int w = 0; w < DZE_R; ++w) mx = fmaxf(mx, fabsf(__ldg(&a.x[bb[w] * si + i])));
-      warp_atomic_max(&a.maxes[NIF_MAX_X + i], mx);
-    }
-    for (int c = 0; c < so; ++c)
-    {
-      float mx = 0.f;
-#pragma unroll
-      for (int w = 0; w < DZE_R; ++w) mx = fmaxf(mx, fabsf(__ldg(&a.du[bb[w] * so + c])));
-      warp_atomic_max(&a.maxes[NIF_MAX_DU + c], mx);
-    }
-  }
-  float hl_max = 0.f;
-  const int nslab = (H + 1) + si + so + 1;  // slabs of (up to) 64 features
-  for (int sb = 0; sb < nslab; ++sb) {
-    __syncthreads();  // the previous slab has been consumed
-    for (int idx = threadIdx.x; idx < 64 * KT / 4; idx += 128) {
-      const int f = idx / (KT / 4), k4 = idx - f * (KT / 4);
-      *reinterpret_cast<float4*>(&Gs[f * KT + 4 * k4]) = ldg4(GE + ((long long)sb * 64 + f) * KG + 4 * k4);
-    }
-    __syncthreads();
-    const float* src[DZE_R];
-    float mul[DZE_R];
-#pragma unroll
-    for (int w = 0; w < DZE_R; ++w) mul[w] = 1.f;
-    int nf = 64;
-#pragma unroll
-    for (int w = 0; w < DZE_R; ++w) {
-      if (sb <= H) src[w] = a.da + (long long)sb * slot_floats + nif_tiled_row(bb[w]);
-      else if (sb < H + 1 + si) { src[w] = a.da + nif_tiled_row(bb[w]); mul[w] = om0 * a.x[bb[w] * si + (sb - H - 1)]; }
-      else if (sb < H + 1 + si + so) { src[w] = a.save + (long long)H * slot_floats + nif_tiled_row(bb[w]); mul[w] = a.du[bb[w] * so + (sb - H - 1 - si)]; }
-      else { src[w] = a.du + bb[w] * so; nf = so; }
-    }
-    if (nf == 64) {
-      // groups of 16 features per row (two 256-bit loads); the next group's loads are issued before the current
-      // group is consumed
-      float cur[DZE_R][16], nxt[DZE_R][16];
-      auto load16 = [&](int g4, float (&dst)[DZE_R][16]) {  // features 16 g4 .. 16 g4 + 15 = column quads 4 g4 .. 4 g4 + 3
-#pragma unroll
-        for (int w = 0; w < DZE_R; ++w)
-#pragma unroll
-          for (int qd = 0; qd < 4; ++qd) {
-            const float4 v = ldg4(src[w] + (4 * g4 + qd) * 128);
-            dst[w][4 * qd] = v.x; dst[w][4 * qd + 1] = v.y; dst[w][4 * qd + 2] = v.z; dst[w][4 * qd + 3] = v.w;
-          }
-      };
-      load16(0, cur);
-#pragma unroll 1
-      for (int g4 = 0; g4 < 4; ++g4) {
-        if (g4 < 3) load16(g4 + 1, nxt);
-        if (k0 == 0 && sb == H + 1 + si) {  // the h_{H+1} rows pass through here: record their magnitude
-#pragma unroll
-          for (int e = 0; e < 16; ++e)
-#pragma unroll
-            for (int w = 0; w < DZE_R; ++w) hl_max = fmaxf(hl_max, fabsf(cur[w][e]));
-        }
-#pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          float fw[DZE_R];
-#pragma unroll
-          for (int w = 0; w < DZE_R; ++w) fw[w] = cur[w][e] * mul[w];
-          const float* Gf = Gs + (16 * g4 + e) * KT;
-#pragma unroll
-          for (int k = 0; k < KT; k += 4) {
-            const float4 g = *reinterpret_cast<const float4*>(Gf + k);
-#pragma unroll
-            for (int w = 0; w < DZE_R; ++w) {
-              acc[w][k] = fmaf(fw[w], g.x, acc[w][k]); acc[w][k + 1] = fmaf(fw[w], g.y, acc[w][k + 1]);
-              acc[w][k + 2] = fmaf(fw[w], g.z, acc[w][k + 2]); acc[w][k + 3] = fmaf(fw[w], g.w, acc[w][k + 3]);
-            }
-          }
-        }
-        if (g4 < 3) {
-#pragma unroll
-          for (int w = 0; w < DZE_R; ++w)
-#pragma unroll
-            for (int e = 0; e < 16; ++e) cur[w][e] = nxt[w][e];
-        }
-      }
-    } else {
-      for (int f = 0; f < nf; ++f) {
-        float fw[DZE_R];
-#pragma unroll
-        for (int w = 0; w < DZE_R; ++w) fw[w] = src[w][f];
-#pragma unroll
-        for (int k = 0; k < KT; k += 4) {
-          const float4 g = *reinterpret_cast<const float4*>(&Gs[f * KT + k]);
-#pragma unroll
-          for (int w = 0; w < DZE_R; ++w) {
-            acc[w][k] = fmaf(fw[w], g.x, acc[w][k]); acc[w][k + 1] = fmaf(fw[w], g.y, acc[w][k + 1]);
-            acc[w][k + 2] = fmaf(fw[w], g.z, acc[w][k + 2]); acc[w][k + 3] = fmaf(fw[w], g.w, acc[w][k + 3]);
-          }
-        }
-      }
-    }
-  }
-  if (k0 == 0) warp_atomic_max(&a.maxes[NIF_MAX_HL], hl_max);
-#pragma unroll
-  for (int w = 0; w < DZE_R; ++w)
-    if (live[w]) {
-#pragma unroll
-      for (int k = 0; k < KT; ++k)
-        if (k0 + k < K) a.dz[bb[w] * K + k0 + k] += acc[w][k];
-    }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -510,19 +469,6 @@ int nif_tc_bwd_data_impl(const Plan& pl, long long B, const float* z, const floa
   if (grid > a.total_pairs) grid = a.total_pairs;
   { NIF_PROF("nif_tc_bwd_data_kernel", st); nif_tc_bwd_data_kernel<<<(unsigned)grid, TCB_THREADS, smem, st>>>(pl, a); }
   NIF_CUDA_CHECK(cudaGetLastError());
-  DzEdgeArgs e;
-  e.B = B; e.x = x; e.packed = packed; e.save = save; e.da = da; e.du = du; e.dz = dz; e.maxes = maxes;
-  for (int k0 = 0; k0 < pl.K;) {  // up to 32 latent coordinates per pass (the table is KG = ceil4(K) wide)
-    const int left = pl.KG - k0;
-    const unsigned grid = (unsigned)((B + 128 * DZE_R - 1) / (128 * DZE_R));
-    int kt;
-    if (left >= 32) { kt = 32; { NIF_PROF("nif_dz_edge_kernel", st); nif_dz_edge_kernel<32><<<grid, 128, 0, st>>>(pl, e, k0); } }
-    else if (left >= 16) { kt = 16; { NIF_PROF("nif_dz_edge_kernel", st); nif_dz_edge_kernel<16><<<grid, 128, 0, st>>>(pl, e, k0); } }
-    else if (left >= 8) { kt = 8; { NIF_PROF("nif_dz_edge_kernel", st); nif_dz_edge_kernel<8><<<grid, 128, 0, st>>>(pl, e, k0); } }
-    else { kt = 4; { NIF_PROF("nif_dz_edge_kernel", st); nif_dz_edge_kernel<4><<<grid, 128, 0, st>>>(pl, e, k0); } }
-    NIF_CUDA_CHECK(cudaGetLastError());
-    k0 += kt;
-  }
   return NIF_OK;
 }
 
