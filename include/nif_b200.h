@@ -114,16 +114,24 @@ int nif_forward_tangent2(const nif_desc_t* d, int64_t B, const float* z, const f
 /* Sobolev training: JacobianLayer INSIDE the loss (tutorial/8_NIF_with_Sobolov_training.ipynb cell 20:
  * JacobianLayer(model, y_index, x_index) -> concat [u, du/dt, du/dx] -> Sobolov_MSE on u and du/dx), where Keras
  * differentiates the tape of nif/layers/gradient.py:207-231 a second time.  Here: forward-mode tangents with a stash,
- * then a reverse-over-forward pass.  Direction 0 of xdot is the one whose derivative enters the loss (it must be a
- * ShapeNet-input direction: zdot of direction 0 is taken as zero by the reverse pass); further directions (e.g. d/dt
- * with its zdot, a monitored metric in the tutorial) are forward-only.
- * save: [save_floats_per_row * B] from nif_sobolev_query; ws: [ws_floats]. */
+ * then a reverse-over-forward pass over every stashed direction.  A direction is (xdot [B,si], zdot [B,K]): a ShapeNet
+ * input column has xdot = e_c, zdot = 0; a ParameterNet input column (d/dt) has xdot = 0 and zdot = the trunk tangent
+ * of the latent code, and the pass then also returns dL/dzdot for the caller's trunk.
+ * nif_forward_tangent_save stashes all n_dir directions: save is [save_floats_per_row * B] from
+ * nif_sobolev_query_dirs(n_dir) (nif_sobolev_query = one direction); ws: [ws_floats]. */
 int nif_sobolev_query(const nif_desc_t* d, int64_t B, int64_t* save_floats_per_row, int64_t* ws_floats);
+int nif_sobolev_query_dirs(const nif_desc_t* d, int64_t B, int32_t n_dir, int64_t* save_floats_per_row,
+                           int64_t* ws_floats);
 int nif_forward_tangent_save(const nif_desc_t* d, int64_t B, const float* z, const float* x,
                              const float* packed, int32_t n_dir, const float* zdot, const float* xdot,
                              float* u, float* udot, float* save, void* stream);
-/* du [B,so] = dL/du, dudot [B,so] = dL/d(udot of direction 0), xdot [B,si] = direction 0.
- * dw_h / db_h written (beta == 0) or accumulated (beta == 1), dz [B,K] written. */
+/* du [B,so] = dL/du, dudot [n_dir,B,so] = dL/d(udot), xdot [n_dir,B,si], zdot [n_dir,B,K] or NULL (no direction moves the
+ * latent code).  dw_h / db_h written (beta == 0) or accumulated (beta == 1), dz [B,K] written, dzdot [n_dir,B,K] written
+ * when zdot is given.  nif_sobolev_backward: one ShapeNet-input direction. */
+int nif_sobolev_backward_dirs(const nif_desc_t* d, int64_t B, const float* z, const float* x, int32_t n_dir,
+                              const float* zdot, const float* xdot, const float* packed, const float* save,
+                              const float* du, const float* dudot, float* dw_h, float* db_h, float beta, float* dz,
+                              float* dzdot, float* ws, void* stream);
 int nif_sobolev_backward(const nif_desc_t* d, int64_t B, const float* z, const float* x, const float* xdot,
                          const float* packed, const float* save, const float* du, const float* dudot,
                          float* dw_h, float* db_h, float beta, float* dz, float* ws, void* stream);

@@ -18,10 +18,12 @@ SYMBOLS = (
     "nif_last_error", "nif_version", "nif_query_sizes", "nif_pack", "nif_forward", "nif_forward_tangent", "nif_forward_tangent2",
     "nif_forward_given_w", "nif_mse_backward", "nif_backward", "nif_adam_step", "nif_adam_step_dev", "nif_measure_fp32_peak",
     "nif_trunk_query", "nif_trunk_forward", "nif_trunk_backward", "nif_trunk_kernel_path",
-    "nif_sobolev_query", "nif_forward_tangent_save", "nif_sobolev_backward", "nif_crc32c",
+    "nif_sobolev_query", "nif_sobolev_query_dirs", "nif_forward_tangent_save", "nif_sobolev_backward", "nif_sobolev_backward_dirs",
+    "nif_crc32c",
     "nif_profile_begin", "nif_profile_end", "nif_adabelief_step", "nif_lion_step", "nif_centralize_gradient", "nif_adam_step_multimem",
 )
 
+NIF_MAX_DIR = 4  # csrc/nif_common.cuh
 VARIANT = {"nif": 0, "siren": 1, "siren_res": 2}
 ACT = {None: 0, "linear": 0, "sine": 1, "swish": 2, "tanh": 3, "relu": 4, "sigmoid": 5}
 
@@ -94,6 +96,8 @@ def lib() -> C.CDLL:
     L.nif_sobolev_query.argtypes = [DP, I64, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.nif_forward_tangent_save.argtypes = [DP, I64, VP, VP, VP, I32, VP, VP, VP, VP, VP, VP]
     L.nif_sobolev_backward.argtypes = [DP, I64, VP, VP, VP, VP, VP, VP, VP, VP, VP, F, VP, VP, VP]
+    L.nif_sobolev_query_dirs.argtypes = [DP, I64, I32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    L.nif_sobolev_backward_dirs.argtypes = [DP, I64, VP, VP, I32, VP, VP, VP, VP, VP, VP, VP, VP, F, VP, VP, VP, VP]
     TP, I64P = C.POINTER(TrunkDesc), C.POINTER(C.c_int64)
     L.nif_trunk_query.argtypes = [TP, I64, I64P, I64P, I64P, I64P]
     L.nif_trunk_kernel_path.argtypes = [TP]

@@ -8,9 +8,10 @@ int nif_forward_impl(const Plan& pl, long long G, long long B, const float* z, c
                      const float* packed, float* u, float* save, cudaStream_t st);
 int nif_tangent_impl(const Plan& pl, long long B, const float* z, const float* x, const float* packed, int n_dir,
                      const float* zdot, const float* xdot, float* u, float* udot, float* save, cudaStream_t st);
-int nif_sobolev_backward_impl(const Plan& pl, long long B, const float* z, const float* x, const float* xdot,
-                              const float* packed, const float* save, const float* du, const float* dud, float* dw_h,
-                              float* db_h, float beta, float* dz, float* ws, cudaStream_t st);
+int nif_sobolev_backward_impl(const Plan& pl, long long B, const float* z, const float* x, int n_dir, const float* zdot,
+                              const float* xdot, const float* packed, const float* save, const float* du,
+                              const float* dud, float* dw_h, float* db_h, float beta, float* dz, float* dzdot, float* ws,
+                              cudaStream_t st);
 int nif_given_w_impl(const Plan& pl, long long B, const float* x, const float* w, float* u, cudaStream_t st);
 int nif_backward_impl(const Plan& pl, long long B, const float* z, const float* x, const float* packed,
                       const float* save, const float* du, float* dw_h, float* db_h, float beta, float* dz,
@@ -123,14 +124,22 @@ extern "C" int nif_forward_tangent2(const nif_desc_t* d, int64_t B, const float*
   return nif_tangent2_impl(pl, B, z, x, packed, zdot, xdot, zddot, u, udot, uddot, static_cast<cudaStream_t>(stream));
 }
 
-extern "C" int nif_sobolev_query(const nif_desc_t* d, int64_t B, int64_t* save_floats_per_row, int64_t* ws_floats) {
+extern "C" int nif_sobolev_query_dirs(const nif_desc_t* d, int64_t B, int32_t n_dir, int64_t* save_floats_per_row,
+                                      int64_t* ws_floats) {
   Plan pl;
   int rc = nif_make_plan(d, &pl);
   if (rc) return rc;
-  if (B < 0) { nif_set_error("nif_sobolev_query: B=%lld", (long long)B); return NIF_E_BAD_ARG; }
-  if (save_floats_per_row) *save_floats_per_row = 4LL * (pl.H + 1) * pl.NP;
-  if (ws_floats) *ws_floats = nif_grad_ws_layout(pl, B).total + (long long)(pl.H + 1) * B * pl.NP;
+  if (B < 0 || n_dir < 1 || n_dir > NIF_MAX_DIR) {
+    nif_set_error("nif_sobolev_query: B=%lld n_dir=%d (max %d)", (long long)B, n_dir, NIF_MAX_DIR);
+    return NIF_E_BAD_ARG;
+  }
+  if (save_floats_per_row) *save_floats_per_row = (2LL + 2 * n_dir) * (pl.H + 1) * pl.NP;
+  if (ws_floats) *ws_floats = nif_grad_ws_layout(pl, B).total + 2LL * (pl.H + 1) * B * pl.NP;
   return NIF_OK;
+}
+
+extern "C" int nif_sobolev_query(const nif_desc_t* d, int64_t B, int64_t* save_floats_per_row, int64_t* ws_floats) {
+  return nif_sobolev_query_dirs(d, B, 1, save_floats_per_row, ws_floats);
 }
 
 extern "C" int nif_forward_tangent_save(const nif_desc_t* d, int64_t B, const float* z, const float* x,
@@ -150,19 +159,37 @@ extern "C" int nif_forward_tangent_save(const nif_desc_t* d, int64_t B, const fl
   return nif_tangent_impl(pl, B, z, x, packed, n_dir, zdot, xdot, u, udot, save, static_cast<cudaStream_t>(stream));
 }
 
-extern "C" int nif_sobolev_backward(const nif_desc_t* d, int64_t B, const float* z, const float* x, const float* xdot,
-                                    const float* packed, const float* save, const float* du, const float* dudot,
-                                    float* dw_h, float* db_h, float beta, float* dz, float* ws, void* stream) {
+extern "C" int nif_sobolev_backward_dirs(const nif_desc_t* d, int64_t B, const float* z, const float* x, int32_t n_dir,
+                                         const float* zdot, const float* xdot, const float* packed, const float* save,
+                                         const float* du, const float* dudot, float* dw_h, float* db_h, float beta,
+                                         float* dz, float* dzdot, float* ws, void* stream) {
   Plan pl;
   int rc = nif_make_plan(d, &pl);
   if (rc) return rc;
-  if (B < 0) { nif_set_error("nif_sobolev_backward: B=%lld", (long long)B); return NIF_E_BAD_ARG; }
+  if (B < 0 || n_dir < 1 || n_dir > NIF_MAX_DIR) {
+    nif_set_error("nif_sobolev_backward: B=%lld n_dir=%d (max %d)", (long long)B, n_dir, NIF_MAX_DIR);
+    return NIF_E_BAD_ARG;
+  }
+  if (pl.wide_last) {
+    nif_set_error("nif_sobolev_backward: trunk plans have no reverse-over-forward pass");
+    return NIF_E_UNSUPPORTED;
+  }
   if (B == 0) return NIF_OK;
   if (pl.K > 0) { NIF_REQUIRE_PTR(z); NIF_REQUIRE_PTR(dw_h); NIF_REQUIRE_PTR(dz); }
   NIF_REQUIRE_PTR(x); NIF_REQUIRE_PTR(xdot); NIF_REQUIRE_PTR(packed); NIF_REQUIRE_PTR(save); NIF_REQUIRE_PTR(du);
   NIF_REQUIRE_PTR(dudot); NIF_REQUIRE_PTR(db_h); NIF_REQUIRE_PTR(ws);
-  return nif_sobolev_backward_impl(pl, B, z, x, xdot, packed, save, du, dudot, dw_h, db_h, beta, dz, ws,
-                                   static_cast<cudaStream_t>(stream));
+  NIF_OPTIONAL_PTR(zdot);
+  if (pl.K == 0) zdot = nullptr;
+  if (zdot) NIF_REQUIRE_PTR(dzdot);
+  return nif_sobolev_backward_impl(pl, B, z, x, n_dir, zdot, xdot, packed, save, du, dudot, dw_h, db_h, beta, dz, dzdot,
+                                   ws, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int nif_sobolev_backward(const nif_desc_t* d, int64_t B, const float* z, const float* x, const float* xdot,
+                                    const float* packed, const float* save, const float* du, const float* dudot,
+                                    float* dw_h, float* db_h, float beta, float* dz, float* ws, void* stream) {
+  return nif_sobolev_backward_dirs(d, B, z, x, 1, nullptr, xdot, packed, save, du, dudot, dw_h, db_h, beta, dz, nullptr, ws,
+                                   stream);
 }
 
 extern "C" int nif_forward_given_w(const nif_desc_t* d, int64_t B, const float* x, const float* w, float* u,

@@ -28,6 +28,16 @@ struct BwdArgs {
   const float* ext_add;  // [H+1] slots added to da_m (primal-adjoint pass consumes what the tangent pass wrote)
   int no_bias;           // tangent-adjoint pass: bias rows do not enter pre_m', drop their dz terms
   int dz_accumulate;     // dz += instead of =
+  int ext_accumulate;    // ext_out += instead of = (second and later directions)
+  // directions that move the latent code (d/d ParameterNet input): pre_m' also holds F_m = sum_k zdot_k (w h_m M_k + C_k).
+  // "Local" pass (da_in != null): the latent operand is zdot (bias coordinate zt_last = 0), the activations are the
+  // primal h_m, and each layer takes its adjoint da_m' from da_in[m] (left by the tangent-adjoint pass) instead of the
+  // chain: dz = dL/dzdot, and dh_out[m] += w sum_k zdot_k M_{m+1,k} da'_{m+1}, the source the primal pass adds to
+  // dh_{m+1} through dh_add[m].
+  const float* da_in;
+  float* dh_out;
+  const float* dh_add;
+  float zt_last;         // value of the bias coordinate of zt: 1, or 0 in the local pass
 };
 
 template <class C>
@@ -41,7 +51,11 @@ __host__ __device__ inline size_t bwd_smem_bytes(int K, int si, int so) {
 template <class C, bool RES, bool EXT>
 __global__ void __launch_bounds__(C::NT, 1) nif_bwd_data_kernel(const Plan pl, const BwdArgs a_in) {
   BwdArgs a = a_in;
-  if (!EXT) { a.h_stash = a.save; a.e_stash = nullptr; a.ext_out = nullptr; a.ext_add = nullptr; a.no_bias = 0; a.dz_accumulate = 0; }
+  if (!EXT) {
+    a.h_stash = a.save; a.e_stash = nullptr; a.ext_out = nullptr; a.ext_add = nullptr; a.no_bias = 0; a.dz_accumulate = 0;
+    a.ext_accumulate = 0; a.da_in = nullptr; a.dh_out = nullptr; a.dh_add = nullptr; a.zt_last = 1.f;
+  }
+  const bool local = EXT && a.da_in != nullptr;
   constexpr int NP = C::NP, TB = C::TB, MP = C::MP, MJ = C::MJ, NT = C::NT;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* stage = reinterpret_cast<float*>(smem_raw);
@@ -109,7 +123,7 @@ __global__ void __launch_bounds__(C::NT, 1) nif_bwd_data_kernel(const Plan pl, c
       const long long b = row0 + p;
       zs[kk * TB + p] = (b < a.B) ? __ldg(&a.z[b * K + kk]) : 0.f;
     }
-    for (int p = tid; p < TB; p += NT) zs[K * TB + p] = 1.f;
+    for (int p = tid; p < TB; p += NT) zs[K * TB + p] = a.zt_last;
     for (int idx = tid; idx < TB * K1; idx += NT) dzs[idx] = 0.f;
     for (int idx = tid; idx < TB * si; idx += NT) {
       const int p = idx / si, i = idx - p * si;
@@ -239,6 +253,32 @@ __global__ void __launch_bounds__(C::NT, 1) nif_bwd_data_kernel(const Plan pl, c
       const float* dsv = a.save + (long long)(H + 1 + m) * a.B * NP;  // d_m
       float* dag = a.da + (long long)m * a.B * NP;
       float daf[MP][MJ];
+      if (EXT && a.dh_add) {  // sources of dh_{m+1} left by the local passes
+#pragma unroll
+        for (int r = 0; r < MP; ++r)
+#pragma unroll
+          for (int gj = 0; gj < C::GJ; ++gj)
+            if (brow[r] < a.B) {
+              const float4 sv = ldg4(&a.dh_add[(long long)m * a.B * NP + brow[r] * NP + gj * C::JSTR + tj * 4]);
+              acc[r][gj * 4 + 0] += sv.x; acc[r][gj * 4 + 1] += sv.y; acc[r][gj * 4 + 2] += sv.z; acc[r][gj * 4 + 3] += sv.w;
+            }
+      }
+      if (local) {
+#pragma unroll
+        for (int r = 0; r < MP; ++r)
+#pragma unroll
+          for (int gj = 0; gj < C::GJ; ++gj) {
+            float4 gv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (brow[r] < a.B) {
+              const long long o = (long long)m * a.B * NP + brow[r] * NP + gj * C::JSTR + tj * 4;
+              float4 sv = *reinterpret_cast<const float4*>(&a.dh_out[o]);
+              sv.x += acc[r][gj * 4 + 0]; sv.y += acc[r][gj * 4 + 1]; sv.z += acc[r][gj * 4 + 2]; sv.w += acc[r][gj * 4 + 3];
+              *reinterpret_cast<float4*>(&a.dh_out[o]) = sv;
+              gv = ldg4(&a.da_in[o]);
+            }
+            daf[r][gj * 4 + 0] = gv.x; daf[r][gj * 4 + 1] = gv.y; daf[r][gj * 4 + 2] = gv.z; daf[r][gj * 4 + 3] = gv.w;
+          }
+      } else {
 #pragma unroll
       for (int r = 0; r < MP; ++r) {
 #pragma unroll
@@ -255,13 +295,16 @@ __global__ void __launch_bounds__(C::NT, 1) nif_bwd_data_kernel(const Plan pl, c
           }
           if (EXT && a.ext_out && brow[r] < a.B) {
             const float4 ev = ldg4(&a.e_stash[(long long)m * a.B * NP + brow[r] * NP + gj * C::JSTR + tj * 4]);
-            *reinterpret_cast<float4*>(&a.ext_out[(long long)m * a.B * NP + brow[r] * NP + gj * C::JSTR + tj * 4]) =
-                make_float4(acc[r][gj * 4 + 0] * ev.x, acc[r][gj * 4 + 1] * ev.y, acc[r][gj * 4 + 2] * ev.z, acc[r][gj * 4 + 3] * ev.w);
+            float4* xo = reinterpret_cast<float4*>(&a.ext_out[(long long)m * a.B * NP + brow[r] * NP + gj * C::JSTR + tj * 4]);
+            float4 xv = make_float4(acc[r][gj * 4 + 0] * ev.x, acc[r][gj * 4 + 1] * ev.y, acc[r][gj * 4 + 2] * ev.z, acc[r][gj * 4 + 3] * ev.w);
+            if (a.ext_accumulate) { const float4 o = *xo; xv.x += o.x; xv.y += o.y; xv.z += o.z; xv.w += o.w; }
+            *xo = xv;
           }
           if (brow[r] < a.B)
             *reinterpret_cast<float4*>(&dag[brow[r] * NP + gj * C::JSTR + tj * 4]) =
                 make_float4(daf[r][gj * 4], daf[r][gj * 4 + 1], daf[r][gj * 4 + 2], daf[r][gj * 4 + 3]);
         }
+      }
       }
       if (m >= 1) {
         // residual bookkeeping (mirror of the forward epilogue)
@@ -269,7 +312,8 @@ __global__ void __launch_bounds__(C::NT, 1) nif_bwd_data_kernel(const Plan pl, c
         for (int r = 0; r < MP; ++r)
 #pragma unroll
           for (int c = 0; c < MJ; ++c) {
-            if (RES) {
+            if (local) acc[r][c] = 0.f;  // no chain: every layer's term is a source of the primal pass
+            else if (RES) {
               if (res == 3) { carry[RES ? r : 0][RES ? c : 0] = 0.5f * acc[r][c]; acc[r][c] = 0.f; }
               else if (res == 2) acc[r][c] = carry[RES ? r : 0][RES ? c : 0];
               else acc[r][c] = 0.f;
@@ -375,7 +419,8 @@ static int launch_bwd_data(const Plan& pl, const BwdArgs& a, cudaStream_t st) {
     return NIF_E_UNSUPPORTED;
   }
   const bool res = pl.variant == NIF_VARIANT_SIREN_RES;
-  const bool ext = a.h_stash != a.save || a.ext_add || a.ext_out || a.no_bias || a.dz_accumulate;
+  const bool ext = a.h_stash != a.save || a.ext_add || a.ext_out || a.no_bias || a.dz_accumulate || a.da_in || a.dh_add ||
+                   a.zt_last != 1.f;
   auto kern = ext ? (res ? nif_bwd_data_kernel<C, true, true> : nif_bwd_data_kernel<C, false, true>)
                   : (res ? nif_bwd_data_kernel<C, true, false> : nif_bwd_data_kernel<C, false, false>);
   NIF_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -400,6 +445,7 @@ struct WgtArgs {
   int S;
   const float *z, *save, *da;
   float* part;  // [S][H][K+1][NP][NP]
+  float zt_last;  // bias coordinate of zt (1; 0 when z is a latent tangent)
 };
 
 // KQ latent coordinates per thread: 4, or 1 for plans whose latent vector is just [1] (K = 0: the trunk)
@@ -458,7 +504,7 @@ __global__ void __launch_bounds__((TS / 4) * (TS / 4)) nif_bwd_weight_kernel(con
         const int rr = e / 4, q = e % 4;
         const long long b = rb + rr;
         const int kk = kg * KQ + q;
-        if (b < r1 && q < KQ) pz[u] = (kk < K) ? __ldg(&a.z[b * K + kk]) : (kk == K ? 1.f : 0.f);
+        if (b < r1 && q < KQ) pz[u] = (kk < K) ? __ldg(&a.z[b * K + kk]) : (kk == K ? a.zt_last : 0.f);
       }
     }
   };
@@ -538,6 +584,7 @@ struct EdgeArgs {
   int no_bias;  // tangent-adjoint pass: the bias-row columns are zero
   int tiled;    // da / save are in the tiled layout of the tensor-core paths (nif_common.cuh)
   int q_begin, q_end;  // columns handled by this launch (the tensor-core thin-term kernel takes the rest)
+  float zt_last = 1.f; // bias coordinate of zt (0 when z is a latent tangent)
 };
 
 // Register-tiled batch reduction: a thread owns 4 columns x 4 latent coordinates; a CTA owns 64 columns x KG groups
@@ -642,7 +689,7 @@ __global__ void __launch_bounds__(16 * KG * RS) nif_bwd_edge_kernel(const Plan p
     for (int u = 0; u < ZPT; ++u) {
       const int e = tid + u * NTH;
       const int kk = k0 + e % KC;
-      float v = (kk < K) ? pz[u] : (kk == K ? 1.f : 0.f);
+      float v = (kk < K) ? pz[u] : (kk == K ? a.zt_last : 0.f);
       if (rb + e / KC >= r1) v = 0.f;
       if (e < RC * KC) Zs[buf][e / KC][e % KC] = v;
     }
@@ -916,13 +963,14 @@ static cudaError_t launch_edge(const Plan& pl, const EdgeArgs& e, const GradWs& 
 // hidden-matrix GEMM (CUDA cores) + thin terms + un-packing, for stashes whose da_m already sit in ws.
 // Used by the trunk, whose parameter gradients are the same batch reductions with zt = [1].
 int nif_weight_grads_impl(const Plan& pl, long long B, const float* z, const float* x, const float* save, const float* du,
-                          float* dw_h, float* db_h, float beta, float* ws, cudaStream_t st, int no_bias = 0) {
+                          float* dw_h, float* db_h, float beta, float* ws, cudaStream_t st, int no_bias = 0,
+                          float zt_last = 1.f) {
   const GradWs w = nif_grad_ws_layout(pl, B);
   const int Hm = pl.H + pl.wide_last;
   if (Hm > 0) {
     WgtArgs g;
     g.B = B; g.rows_per_split = w.rows_h; g.S = w.S_h;
-    g.z = z; g.save = save; g.da = ws + w.da; g.part = ws + w.part_h;
+    g.z = z; g.save = save; g.da = ws + w.da; g.part = ws + w.part_h; g.zt_last = zt_last;
     const int K1 = pl.K + 1;
     const int kq = K1 == 1 ? 1 : 4;
     const int kgn = (K1 + kq - 1) / kq;
@@ -941,7 +989,7 @@ int nif_weight_grads_impl(const Plan& pl, long long B, const float* z, const flo
   EdgeArgs e;
   e.B = B; e.rows_per_split = w.rows_e; e.S = w.S_e; e.Q = w.Q;
   e.z = z; e.x = x; e.save = save; e.da = ws + w.da; e.du = du; e.part = ws + w.part_e; e.no_bias = no_bias; e.tiled = 0;
-  e.q_begin = 0; e.q_end = w.Q;
+  e.q_begin = 0; e.q_end = w.Q; e.zt_last = zt_last;
   NIF_CUDA_CHECK(launch_edge(pl, e, w, st));
   return nif_unpack_grad_impl(pl, w.S_h, ws + w.part_h, w.S_e, ws + w.part_e, w.Q, dw_h, db_h, beta, st);
 }
@@ -957,6 +1005,7 @@ int nif_backward_impl(const Plan& pl, long long B, const float* z, const float* 
   a.da = ws + w.da;
   a.dz = dz;
   a.h_stash = save; a.e_stash = nullptr; a.ext_out = nullptr; a.ext_add = nullptr; a.no_bias = 0; a.dz_accumulate = 0;
+  a.ext_accumulate = 0; a.da_in = nullptr; a.dh_out = nullptr; a.dh_add = nullptr; a.zt_last = 1.f;
   if (pl.bf) {  // bf16 tensor-core reverse pass: data kernel, weight-gradient GEMM, thin terms on the CUDA cores
     int rcb = nif_bf_bwd_data_impl(pl, B, z, x, packed, save, du, ws + w.da, dz, st);
     if (rcb == NIF_OK) {
@@ -1042,38 +1091,63 @@ int nif_backward_impl(const Plan& pl, long long B, const float* z, const float* 
 // batch-reduction kernels; the second pass accumulates.  Runs on the fp32 CUDA-core kernels.
 // ws: nif_grad_ws_layout(pl, B).total + (H+1) * B * NP floats.
 // ---------------------------------------------------------------------------------------------------
-int nif_sobolev_backward_impl(const Plan& pl, long long B, const float* z, const float* x, const float* xdot,
-                              const float* packed, const float* save, const float* du, const float* dud, float* dw_h,
-                              float* db_h, float beta, float* dz, float* ws, cudaStream_t st) {
+int nif_sobolev_backward_impl(const Plan& pl, long long B, const float* z, const float* x, int n_dir, const float* zdot,
+                              const float* xdot, const float* packed, const float* save, const float* du,
+                              const float* dud, float* dw_h, float* db_h, float beta, float* dz, float* dzdot, float* ws,
+                              cudaStream_t st) {
+  // n_dir directions (xdot [n_dir][B][si], zdot [n_dir][B][K] or null = the latent code does not move, dud
+  // [n_dir][B][so], dzdot [n_dir][B][K] out).  save: slots [0, 2(H+1)) h, d; direction d: [2(H+1)(1+d), ...) h', e.
+  // Per direction: the tangent adjoint (chain through G = sum_k zt_k w h' M_k), then -- when zdot moves -- the local pass
+  // over F = sum_k zdot_k (w h M_k + C_k) with the adjoints the first pass left in ws.da; last the primal adjoint,
+  // which picks up X (through act'') and S (through F's h_m).
   if (B <= 0) return NIF_OK;
   const GradWs w = nif_grad_ws_layout(pl, B);
-  float* X = ws + w.total;
   const long long slot = B * (long long)pl.NP;
-  const float* h_dot = save + 2LL * (pl.H + 1) * slot;
-  const float* e_st = save + 3LL * (pl.H + 1) * slot;
-  for (int pass = 0; pass < 2; ++pass) {
+  float* X = ws + w.total;
+  float* S = X + (pl.H + 1) * slot;
+  if (zdot) NIF_CUDA_CHECK(cudaMemsetAsync(S, 0, sizeof(float) * (pl.H + 1) * slot, st));
+  auto run = [&](BwdArgs& a) -> int {
+    switch (pl.NP) {
+      case 32: a.total_tiles = (B + Cfg32::TB - 1) / Cfg32::TB; return launch_bwd_data<Cfg32>(pl, a, st);
+      case 64: a.total_tiles = (B + Cfg64::TB - 1) / Cfg64::TB; return launch_bwd_data<Cfg64>(pl, a, st);
+      case 128: a.total_tiles = (B + Cfg128::TB - 1) / Cfg128::TB; return launch_bwd_data<Cfg128>(pl, a, st);
+    }
+    nif_set_error("unsupported padded width %d", pl.NP);
+    return NIF_E_UNSUPPORTED;
+  };
+  for (int d = 0; d <= n_dir; ++d) {
+    const bool primal = d == n_dir;
     BwdArgs a;
     a.B = B;
-    a.z = z; a.packed = packed; a.save = save;
+    a.packed = packed; a.save = save;
     a.da = ws + w.da;
-    a.dz = dz;
-    if (pass == 0) {  // tangent adjoint
-      a.x = xdot; a.du = dud; a.h_stash = h_dot; a.e_stash = e_st; a.ext_out = X; a.ext_add = nullptr;
-      a.no_bias = 1; a.dz_accumulate = 0;
-    } else {          // primal adjoint
+    a.ext_accumulate = 0; a.da_in = nullptr; a.dh_out = nullptr; a.dh_add = nullptr; a.zt_last = 1.f;
+    a.z = z; a.dz = dz;
+    if (!primal) {  // tangent adjoint of direction d
+      a.x = xdot + (long long)d * B * pl.si; a.du = dud + (long long)d * B * pl.so;
+      a.h_stash = save + (2LL + 2 * d) * (pl.H + 1) * slot; a.e_stash = a.h_stash + (pl.H + 1) * slot;
+      a.ext_out = X; a.ext_add = nullptr; a.ext_accumulate = d > 0;
+      a.no_bias = 1; a.dz_accumulate = d > 0;
+    } else {        // primal adjoint
       a.x = x; a.du = du; a.h_stash = save; a.e_stash = nullptr; a.ext_out = nullptr; a.ext_add = X;
+      a.dh_add = zdot ? S : nullptr;
       a.no_bias = 0; a.dz_accumulate = 1;
     }
-    int rc;
-    switch (pl.NP) {
-      case 32: a.total_tiles = (B + Cfg32::TB - 1) / Cfg32::TB; rc = launch_bwd_data<Cfg32>(pl, a, st); break;
-      case 64: a.total_tiles = (B + Cfg64::TB - 1) / Cfg64::TB; rc = launch_bwd_data<Cfg64>(pl, a, st); break;
-      case 128: a.total_tiles = (B + Cfg128::TB - 1) / Cfg128::TB; rc = launch_bwd_data<Cfg128>(pl, a, st); break;
-      default: nif_set_error("unsupported padded width %d", pl.NP); return NIF_E_UNSUPPORTED;
+    int rc = run(a);
+    if (rc != NIF_OK) return rc;
+    rc = nif_weight_grads_impl(pl, B, z, a.x, a.h_stash, a.du, dw_h, db_h, d == 0 ? beta : 1.0f, ws, st, a.no_bias);
+    if (rc != NIF_OK) return rc;
+    if (!primal && zdot) {  // local pass: ws.da still holds da'_m of this direction
+      const float* zd = zdot + (long long)d * B * pl.K;
+      BwdArgs l = a;
+      l.z = zd; l.zt_last = 0.f; l.x = x; l.h_stash = save; l.e_stash = nullptr; l.ext_out = nullptr; l.ext_add = nullptr;
+      l.no_bias = 0; l.dz = dzdot + (long long)d * B * pl.K; l.dz_accumulate = 0;
+      l.da_in = ws + w.da; l.dh_out = S;
+      rc = run(l);
+      if (rc != NIF_OK) return rc;
+      rc = nif_weight_grads_impl(pl, B, zd, x, save, a.du, dw_h, db_h, 1.0f, ws, st, 0, 0.f);
+      if (rc != NIF_OK) return rc;
     }
-    if (rc != NIF_OK) return rc;
-    rc = nif_weight_grads_impl(pl, B, z, a.x, a.h_stash, a.du, dw_h, db_h, pass == 0 ? beta : 1.0f, ws, st, a.no_bias);
-    if (rc != NIF_OK) return rc;
   }
   return NIF_OK;
 }

@@ -29,7 +29,8 @@ struct TanArgs {
   // optional stash for the reverse-over-forward pass (Sobolev training), slots of [B][NP]:
   //   [0, H]            h_{m+1}                       [H+1, 2H+1]     d_m = alpha act'(pre_m)
   //   [2H+2, 3H+2]      h'_{m+1} of direction 0       [3H+3, 4H+3]    e_m = alpha act''(pre_m) pre_m' of direction 0
-  float* save;
+  float* save;    // slots [0, 2(H+1)): h_{m+1}, d_m
+  float* save_t;  // tangent slots of this launch's first direction: per direction (H+1) h'_{m+1}, (H+1) e_m
 };
 
 using TCfg32 = TileCfg<32, 128, 1, 1>;
@@ -184,26 +185,30 @@ __global__ void __launch_bounds__(C::NT, 1) nif_tangent_kernel(const Plan pl, co
 #pragma unroll
           for (int e = 0; e < 4; ++e) { outv[0][r][c4 + e] = f4[e]; outv[1][r][c4 + e] = d4[e]; }
         }
-      if (a.save) {  // d_m and e_m (before the residual bookkeeping below overwrites outv)
+      if (a.save) {  // d_m and e_m of every direction (before the residual bookkeeping below overwrites outv)
         float* sd = a.save + (long long)(H + 1 + m) * a.B * NP;
-        float* se = a.save + (long long)(3 * (H + 1) + m) * a.B * NP;
 #pragma unroll
         for (int r = 0; r < MP; ++r) {
           const long long b = row0 + row_of<C>(tp, r);
           if (b < a.B) {
 #pragma unroll
             for (int gj = 0; gj < C::GJ; ++gj) {
-              float dq[4], eq[4];
+              float dq[4], dd[4];
 #pragma unroll
               for (int f = 0; f < 4; ++f) {
                 const int c = gj * 4 + f;
                 const bool livec = col_of<C>(tj, c) < n;
                 dq[f] = livec ? alpha * outv[1][r][c] : 0.f;
-                eq[f] = livec ? alpha * act_dd(pl.act, acc[0][r][c], outv[0][r][c], outv[1][r][c]) * acc[1][r][c] : 0.f;
+                dd[f] = livec ? alpha * act_dd(pl.act, acc[0][r][c], outv[0][r][c], outv[1][r][c]) : 0.f;
               }
               const int j0 = gj * C::JSTR + tj * 4;
               *reinterpret_cast<float4*>(&sd[b * NP + j0]) = make_float4(dq[0], dq[1], dq[2], dq[3]);
-              *reinterpret_cast<float4*>(&se[b * NP + j0]) = make_float4(eq[0], eq[1], eq[2], eq[3]);
+#pragma unroll
+              for (int s = 1; s < (SEC ? 2 : NS); ++s) {
+                float* se = a.save_t + (long long)((2 * s - 1) * (H + 1) + m) * a.B * NP;
+                *reinterpret_cast<float4*>(&se[b * NP + j0]) = make_float4(dd[0] * acc[s][r][gj * 4], dd[1] * acc[s][r][gj * 4 + 1],
+                                                                            dd[2] * acc[s][r][gj * 4 + 2], dd[3] * acc[s][r][gj * 4 + 3]);
+              }
             }
           }
         }
@@ -229,10 +234,10 @@ __global__ void __launch_bounds__(C::NT, 1) nif_tangent_kernel(const Plan pl, co
             outv[s][r][c] = o;
           }
         }
-      if (a.save) {  // h_{m+1} and h'_{m+1}
+      if (a.save) {  // h_{m+1} and h'_{m+1} of every direction
 #pragma unroll
-        for (int s = 0; s < 2; ++s) {
-          float* sh = a.save + (long long)(s * 2 * (H + 1) + m) * a.B * NP;
+        for (int s = 0; s < (SEC ? 2 : NS); ++s) {
+          float* sh = (s == 0 ? a.save : a.save_t + (long long)(2 * (s - 1) * (H + 1)) * a.B * NP) + (long long)m * a.B * NP;
 #pragma unroll
           for (int r = 0; r < MP; ++r) {
             const long long b = row0 + row_of<C>(tp, r);
@@ -442,7 +447,8 @@ int nif_tangent_impl(const Plan& pl, long long B, const float* z, const float* x
     a.xdot = xdot ? xdot + (long long)d0 * B * pl.si : nullptr;
     a.u = u;
     a.udot = udot + (long long)d0 * B * pl.so;
-    a.save = d0 == 0 ? save : nullptr;  // the stash describes direction 0
+    a.save = save;  // (the primal slots are rewritten with the same values by every pair)
+    a.save_t = save ? save + (2LL + 2 * d0) * (pl.H + 1) * B * pl.NP : nullptr;
     a.zddot = nullptr; a.uddot = nullptr;
     const int nd = (n_dir - d0) >= 2 ? 2 : 1;
     const int rc = nd == 2 ? dispatch_tan<2>(pl, a, st) : dispatch_tan<1>(pl, a, st);
@@ -459,7 +465,7 @@ int nif_tangent2_impl(const Plan& pl, long long B, const float* z, const float* 
   a.B = B;
   a.total_tiles = 0;
   a.z = z; a.x = x; a.packed = packed; a.zdot = zdot; a.xdot = xdot; a.zddot = zddot;
-  a.u = u; a.udot = udot; a.uddot = uddot; a.save = nullptr;
+  a.u = u; a.udot = udot; a.uddot = uddot; a.save = nullptr; a.save_t = nullptr;
   switch (pl.NP) {
     case 32: return launch_tan<TCfg32, 3, true>(pl, a, st);
     case 64: return launch_tan<TCfg64, 3, true>(pl, a, st);

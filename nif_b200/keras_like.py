@@ -875,28 +875,36 @@ class Model:
 
     # ---- Sobolev training (JacobianLayer inside the loss) ---------------------------------------------------
     def _plan_sobolev(self, loss: "SobolevMSE"):
-        """Map the loss columns onto (ShapeNet outputs, one ShapeNet-input direction)."""
+        """Map the loss columns onto tangent directions (one per differentiated input column) and ShapeNet outputs."""
         n = self.net
         ny, nx = len(self.jac_y), len(self.jac_x)
         for c in loss.value_cols:
             if not 0 <= c < n.so_dim:
                 raise NifError(f"value column {c} is not one of the {n.so_dim} model outputs")
-        xcol, gy = None, []
+        dirs, pairs = [], []  # input column of each direction; (direction, output) of each grad column
         for c in loss.grad_cols:
             k = c - n.so_dim
             if not 0 <= k < ny * nx:
                 raise NifError(f"grad column {c} is outside the Jacobian block of the model output")
             a, cc = divmod(k, nx)
-            if xcol is not None and self.jac_x[cc] != xcol:
-                raise NifError("SobolevMSE: all grad columns must differentiate w.r.t. the same input")
-            xcol = self.jac_x[cc]
-            gy.append(self.jac_y[a])
-        if xcol is None or xcol < n.pi_dim:
-            raise NifError("SobolevMSE needs grad columns w.r.t. a ShapeNet input (x), as in tutorial 8; derivatives "
-                           "w.r.t. ParameterNet inputs are forward-only (monitoring) in this build")
-        return {"x": xcol - n.pi_dim, "gy": gy}
+            col = self.jac_x[cc]
+            if not 0 <= col < n.pi_dim + n.si_dim:
+                raise NifError(f"x_index {col} outside the {n.pi_dim + n.si_dim} model inputs")
+            if col not in dirs:
+                dirs.append(col)
+            pairs.append((dirs.index(col), self.jac_y[a]))
+        if not dirs:
+            raise NifError("SobolevMSE needs at least one grad column")
+        from . import _lib
+        if len(dirs) > _lib.NIF_MAX_DIR:
+            raise NifError(f"SobolevMSE: at most {_lib.NIF_MAX_DIR} differentiated inputs")
+        return {"dirs": dirs, "pairs": pairs, "latent_moves": any(c < n.pi_dim for c in dirs)}
 
     def _train_step_sobolev(self, inp: torch.Tensor, tgt: torch.Tensor, global_batch: Optional[int]) -> torch.Tensor:
+        """JacobianLayer inside the loss (tutorial 8): forward-mode tangents with a stash, then the reverse-over-forward
+        pass of the library.  Grad columns w.r.t. ShapeNet inputs are directions on x; grad columns w.r.t. ParameterNet
+        inputs (du/dt) are directions on the latent code, whose tangent -- and the adjoint that comes back for it -- go
+        through the trunk by reverse-over-forward autograd."""
         n, loss, plan = self.net, self.loss, self._sobolev_plan
         if isinstance(n.p_jac_reg, (float, int)):
             raise NifError("jac_reg is not combined with Sobolev training in this build")
@@ -905,32 +913,54 @@ class Model:
         gb = int(global_batch) if global_batch else B
         xs = inp[:, n.pi_dim: n.pi_dim + n.si_dim].contiguous()
         p_in = inp[:, : n.pi_dim].contiguous()
-        fused_trunk = n._trunk is not None
+        dirs, pairs = plan["dirs"], plan["pairs"]
+        D = len(dirs)
+        fused_trunk = n._trunk is not None and not plan["latent_moves"]
+        xdot = torch.zeros(D, B, n.si_dim, device=inp.device)
+        zdot, zds = None, []
         if fused_trunk:
             z, tstash = n._trunk.forward(p_in, n.theta_trunk, save=True)
         else:
             n.grad.zero_()
+            z = None
+            if plan["latent_moves"]:
+                zdot = torch.zeros(D, B, n.pi_hidden, device=inp.device)
+        for d, col in enumerate(dirs):
+            if col >= n.pi_dim:
+                xdot[d, :, col - n.pi_dim] = 1.0
+            else:
+                e = torch.zeros_like(p_in)
+                e[:, col] = 1.0
+                zz, zd = torch.func.jvp(n._latent, (p_in,), (e,))
+                z = zz if z is None else z
+                zds.append((d, zd))
+                zdot[d] = zd.detach()
+        if z is None:
             z = n._latent(p_in)
         zc = z.detach().contiguous()
         packed = self._packed_weights()
-        xdot = torch.zeros(1, B, n.si_dim, device=inp.device)
-        xdot[0, :, plan["x"]] = 1.0
-        u, udot, stash = eng.forward_tangent(zc, xs, packed, None, xdot, save=True)
+        u, udot, stash = eng.forward_tangent(zc, xs, packed, zdot, xdot, save=True)
         # seeds of the batch-mean loss (O(B) elementwise; everything heavier is in the library)
         du = torch.zeros_like(u)
-        dud = torch.zeros_like(u)
-        vc, gc, gy = loss.value_cols, loss.grad_cols, plan["gy"]
+        dud = torch.zeros_like(udot)
+        vc, gc = loss.value_cols, loss.grad_cols
         ev = u[:, vc] - tgt[:, vc]
-        eg = udot[0][:, gy] - tgt[:, gc]
         du[:, vc] = (2.0 / (gb * len(vc))) * ev
-        dud[:, gy] = (2.0 * loss.coef_grad / (gb * len(gc))) * eg
-        lv = ((ev * ev).sum() / len(vc) + loss.coef_grad * (eg * eg).sum() / len(gc)) / gb
-        dz = eng.sobolev_backward(zc, xs, xdot[0], packed, stash, du, dud, n._gviews[n._last_names[0]],
-                                  n._gviews[n._last_names[1]], 0.0)
+        sq_g = 0.0
+        for (d, yc), c in zip(pairs, gc):
+            eg = udot[d][:, yc] - tgt[:, c]
+            dud[d][:, yc] += (2.0 * loss.coef_grad / (gb * len(gc))) * eg
+            sq_g = sq_g + (eg * eg).sum()
+        lv = ((ev * ev).sum() / len(vc) + loss.coef_grad * sq_g / len(gc)) / gb
+        out = eng.sobolev_backward(zc, xs, xdot, packed, stash, du, dud, n._gviews[n._last_names[0]],
+                                   n._gviews[n._last_names[1]], 0.0, zdot=zdot)
         if fused_trunk:
-            n._trunk.backward(p_in, n.theta_trunk, tstash, dz, n.grad_trunk, 0.0)
+            n._trunk.backward(p_in, n.theta_trunk, tstash, out, n.grad_trunk, 0.0)
+        elif zdot is None:
+            z.backward(out)
         else:
-            z.backward(dz)
+            dz, dzdot = out
+            torch.autograd.backward([z] + [zd for _, zd in zds], [dz] + [dzdot[d] for d, _ in zds])
         if self.dist is not None:
             self.dist.allreduce_(n.grad)
         l1, l2 = n._kernel_regulariser()

@@ -134,8 +134,7 @@ class FusedShapeNet:
     def forward_tangent(self, z, x, packed, zdot: Optional[torch.Tensor], xdot: Optional[torch.Tensor],
                         save: bool = False):
         """(u, udot[n_dir,B,so]) for tangent directions zdot [n_dir,B,K] / xdot [n_dir,B,si].
-        save=True also returns the stash for sobolev_backward (direction 0 must then be a ShapeNet-input
-        direction, i.e. given through xdot)."""
+        save=True also returns the stash of every direction for sobolev_backward."""
         x = _f32c(x, "x")
         B = x.shape[0]
         z = _f32c(z, "z") if self.K > 0 else None
@@ -150,9 +149,9 @@ class FusedShapeNet:
                   "nif_forward_tangent")
             return u, udot
         if xdot is None:
-            raise NifError("forward_tangent(save=True) needs xdot: direction 0 must act on the ShapeNet inputs")
+            xdot = torch.zeros(n_dir, B, self.si, dtype=torch.float32, device=x.device)
         per_row = C.c_int64(0)
-        check(_lib.lib().nif_sobolev_query(C.byref(self.desc), B, C.byref(per_row), None), "nif_sobolev_query")
+        check(_lib.lib().nif_sobolev_query_dirs(C.byref(self.desc), B, n_dir, C.byref(per_row), None), "nif_sobolev_query_dirs")
         stash = torch.empty(int(per_row.value) * B, dtype=torch.float32, device=x.device)
         check(_lib.lib().nif_forward_tangent_save(C.byref(self.desc), B, _ptr(z), _ptr(x), _ptr(packed), n_dir,
                                                   _ptr(zdot), _ptr(xdot), _ptr(u), _ptr(udot), _ptr(stash), _stream()),
@@ -181,21 +180,44 @@ class FusedShapeNet:
               "nif_forward_tangent2")
         return u, udot, uddot
 
-    def sobolev_backward(self, z, x, xdot0, packed, stash, du, dudot0, dw_h, db_h, beta: float = 0.0):
-        """Reverse-over-forward pass: seeds du = dL/du [B,so] and dudot0 = dL/d(udot of direction 0) [B,so];
-        xdot0 [B,si] is direction 0 of the forward_tangent(save=True) call.  Fills dw_h / db_h, returns dz."""
-        x, xdot0 = _f32c(x, "x"), _f32c(xdot0, "xdot0")
+    def sobolev_backward(self, z, x, xdot, packed, stash, du, dudot, dw_h, db_h, beta: float = 0.0, zdot=None):
+        """Reverse-over-forward pass over the directions of the forward_tangent(save=True) call: seeds du = dL/du [B,so]
+        and dudot = dL/d(udot) [n_dir,B,so]; xdot [n_dir,B,si] and zdot [n_dir,B,K] (None: no direction moves the latent
+        code) are the directions of that call ([B,*] is read as one direction).  Fills dw_h / db_h; returns dz, or
+        (dz, dzdot [n_dir,B,K]) when zdot is given."""
+        x, xdot = _f32c(x, "x"), _f32c(xdot, "xdot")
         B = x.shape[0]
-        du, dudot0 = _f32c(du, "du"), _f32c(dudot0, "dudot0")
+        du, dudot = _f32c(du, "du"), _f32c(dudot, "dudot")
+        if xdot.dim() == 2:
+            xdot = xdot.unsqueeze(0)
+        if dudot.dim() == 2:
+            dudot = dudot.unsqueeze(0)
+        n_dir = xdot.shape[0]
+        if tuple(xdot.shape) != (n_dir, B, self.si) or tuple(dudot.shape) != (n_dir, B, self.so):
+            raise NifError(f"xdot / dudot must be [{n_dir},{B},{self.si}] / [{n_dir},{B},{self.so}], got "
+                           f"{tuple(xdot.shape)} / {tuple(dudot.shape)}")
+        dzdot = None
+        if zdot is not None and self.K > 0:
+            zdot = _f32c(zdot, "zdot")
+            if tuple(zdot.shape) != (n_dir, B, self.K):
+                raise NifError(f"zdot must be [{n_dir},{B},{self.K}], got {tuple(zdot.shape)}")
+            dzdot = torch.empty(n_dir, B, self.K, dtype=torch.float32, device=x.device)
+        else:
+            zdot = None
+        per_row = C.c_int64(0)
+        check(_lib.lib().nif_sobolev_query_dirs(C.byref(self.desc), B, n_dir, C.byref(per_row), None), "nif_sobolev_query_dirs")
+        if stash.numel() < per_row.value * B:
+            raise NifError(f"the stash does not hold {n_dir} directions")
         dz = torch.empty(B, self.K, dtype=torch.float32, device=x.device) if self.K > 0 else None
         wsn = C.c_int64(0)
-        check(_lib.lib().nif_sobolev_query(C.byref(self.desc), B, None, C.byref(wsn)), "nif_sobolev_query")
+        check(_lib.lib().nif_sobolev_query_dirs(C.byref(self.desc), B, n_dir, None, C.byref(wsn)), "nif_sobolev_query_dirs")
         if self._ws is None or self._ws.numel() < wsn.value or self._ws.device != x.device:
             self._ws = torch.empty(int(wsn.value), dtype=torch.float32, device=x.device)
-        check(_lib.lib().nif_sobolev_backward(C.byref(self.desc), B, _ptr(z), _ptr(x), _ptr(xdot0), _ptr(packed),
-                                              _ptr(stash), _ptr(du), _ptr(dudot0), _ptr(dw_h), _ptr(db_h), float(beta),
-                                              _ptr(dz), _ptr(self._ws), _stream()), "nif_sobolev_backward")
-        return dz
+        check(_lib.lib().nif_sobolev_backward_dirs(C.byref(self.desc), B, _ptr(z), _ptr(x), n_dir, _ptr(zdot), _ptr(xdot),
+                                                   _ptr(packed), _ptr(stash), _ptr(du), _ptr(dudot), _ptr(dw_h), _ptr(db_h),
+                                                   float(beta), _ptr(dz), _ptr(dzdot), _ptr(self._ws), _stream()),
+              "nif_sobolev_backward_dirs")
+        return (dz, dzdot) if zdot is not None else dz
 
     def given_w(self, x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
         """model_x_to_u_given_w: every row of `w` is a full weight vector (nif/model.py:435-464, 956-986)."""

@@ -707,6 +707,31 @@ def sobolev_loss_and_grads(spec: Spec, prm: Dict[str, Tensor], inputs: Tensor, t
     return loss.detach(), grads, got[0].detach(), y.detach(), dy.detach()
 
 
+def sobolev_loss_and_grads_pairs(spec: Spec, prm: Dict[str, Tensor], inputs: Tensor, target_u: Tensor, target_g: Tensor,
+                                 pairs, coef_grad: float):
+    """The same tape with any set of Jacobian entries in the loss: pairs = [(output index, input column)], target_g
+    [B, len(pairs)]; input columns < spec.pi are ParameterNet inputs (du/dt of tutorial 8's JacobianLayer output, which
+    the tutorial only monitors but Keras would differentiate just the same).
+        loss = mean_b mean_c (u - t_u)^2 + coef_grad * mean_b mean_pairs (du_y/dinput_c - t_g)^2
+    Returns (loss, {name: grad}, u, [B, len(pairs)] derivatives)."""
+    leaves = {k: v.detach().clone().requires_grad_(True) for k, v in prm.items()}
+    inp = inputs.detach().clone().requires_grad_(True)
+    p_in = inp[:, : spec.pi]
+    x = inp[:, spec.pi : spec.pi + spec.si]
+    wn, bn = last_layer_names(spec)
+    z = latent(spec, leaves, p_in)
+    y = shape_net(spec, x, hyper_linear(z, leaves[wn], leaves[bn]))
+    rows = {}
+    for yc in sorted({a for a, _ in pairs}):  # one reverse pass per output index, like the reference
+        (rows[yc],) = torch.autograd.grad(y[:, yc].sum(), inp, create_graph=True, retain_graph=True)
+    dy = torch.stack([rows[a][:, c] for a, c in pairs], 1)
+    loss = ((y - target_u) ** 2).mean(-1).mean() + coef_grad * ((dy - target_g) ** 2).mean(-1).mean()
+    names = list(leaves)
+    got = torch.autograd.grad(loss, [leaves[k] for k in names], allow_unused=True)
+    grads = {k: (g if g is not None else torch.zeros_like(leaves[k])) for k, g in zip(names, got)}
+    return loss.detach(), grads, y.detach(), dy.detach()
+
+
 # ----------------------------------------------------------------------------
 # a whole training step in the reference's materialised dataflow (CPU baseline)
 # ----------------------------------------------------------------------------

@@ -344,6 +344,110 @@ def test_sobolev_reverse_over_forward(variant, si, so, n, l, K, B, xc, act):
     assert rel_err(dw.cpu(), 2 * g64[wn]) < 1e-4 and rel_err(db.cpu(), 2 * g64[bn]) < 1e-4
 
 
+@pytest.mark.parametrize("variant,si,so,n,l,K,B,pairs,act", [
+    ("siren", 1, 1, 64, 4, 32, 300, [(0, 0)], None),                  # C4 shape, du/dt alone in the loss
+    ("siren", 1, 1, 64, 4, 32, 300, [(0, 0), (0, 1)], None),          # du/dt and du/dx (tutorial 8's full Jacobian)
+    ("siren", 2, 2, 30, 2, 3, 257, [(1, 0), (0, 2), (1, 1)], None),   # padded width, two outputs, three directions
+    ("siren_res", 2, 1, 64, 1, 3, 70, [(0, 0), (0, 1)], None),        # res-blocks
+    ("nif", 2, 2, 30, 2, 2, 150, [(0, 0), (1, 0), (1, 2)], "swish"),  # swish + residual, two outputs along d/dt
+    ("siren", 3, 3, 128, 1, 4, 100, [(2, 0)], None),                  # width 128
+])
+def test_sobolev_with_parameter_net_directions(variant, si, so, n, l, K, B, pairs, act):
+    """Jacobian entries w.r.t. ParameterNet inputs inside the loss: the direction moves the latent code (zdot = trunk
+    tangent), pre_m' gains sum_k zdot_k (w h_m M_k + C_k), and the reverse-over-forward pass returns dL/dzdot as well.
+    Gradients of every variable -- the trunk's through (dz, dzdot) and reverse-over-forward autograd of the oracle's own
+    trunk -- vs autograd-of-autograd over the oracle."""
+    spec, prm, inputs, target, _ = _random_problem(variant, si, so, n, l, K, B, seed=11 * K + n, act=act or "swish")
+    assert spec.pi == 1
+    dev = torch.device("cuda:0")
+    wn, bn = O.last_layer_names(spec)
+    g = torch.Generator().manual_seed(6)
+    tgt_g = torch.randn(B, len(pairs), generator=g, dtype=torch.float64)
+    coef = 0.37
+    l64, g64, y64, dy64 = O.sobolev_loss_and_grads_pairs(spec, prm, inputs, target, tgt_g, pairs, coef)
+    prm32 = {k: v.float() for k, v in prm.items()}
+    l32, g32, y32, dy32 = O.sobolev_loss_and_grads_pairs(spec, prm32, inputs.float(), target.float(), tgt_g.float(),
+                                                         pairs, coef)
+    eng = _engine(spec)
+    cols = []
+    for _, c in pairs:
+        if c not in cols:
+            cols.append(c)
+    D = len(cols)
+    # latent code and its tangent along the ParameterNet input, with a tape for the way back (float64, CPU)
+    leaves = {k: v.detach().clone().requires_grad_(True) for k, v in prm.items()}
+    p_in = inputs[:, : spec.pi].detach()
+    z64, zd64 = torch.func.jvp(lambda p: O.latent(spec, leaves, p), (p_in,), (torch.ones_like(p_in),))
+    z = z64.detach().float().to(dev)
+    x = inputs[:, spec.pi:].float().contiguous().to(dev)
+    zdot = torch.zeros(D, B, K, device=dev)
+    xdot = torch.zeros(D, B, si, device=dev)
+    for d, c in enumerate(cols):
+        if c < spec.pi:
+            zdot[d] = zd64.detach().float().to(dev)
+        else:
+            xdot[d, :, c - spec.pi] = 1.0
+    w_h, b_h = prm[wn].float().to(dev), prm[bn].float().to(dev)
+    packed = eng.pack(w_h, b_h)
+    u, udot, stash = eng.forward_tangent(z, x, packed, zdot, xdot, save=True)
+    u_ref, udot_ref = eng.forward_tangent(z, x, packed, zdot, xdot)
+    assert torch.equal(u, u_ref) and torch.equal(udot, udot_ref), "stash on/off must not change the outputs"
+    got_dy = torch.stack([udot[cols.index(c)][:, a] for a, c in pairs], 1)
+    assert _gate(rel_err(u.cpu(), y64), rel_err(y32, y64))
+    assert _gate(rel_err(got_dy.cpu(), dy64), rel_err(dy32, dy64), floor=2e-5)
+    du = (2.0 / (B * so)) * (u - target.float().to(dev))
+    dud = torch.zeros_like(udot)
+    for i, (a, c) in enumerate(pairs):
+        dud[cols.index(c)][:, a] += (2.0 * coef / (B * len(pairs))) * (got_dy[:, i] - tgt_g[:, i].float().to(dev))
+    dw = torch.full_like(w_h, float("nan"))
+    db = torch.full_like(b_h, float("nan"))
+    dz, dzdot = eng.sobolev_backward(z, x, xdot, packed, stash, du, dud, dw, db, 0.0, zdot=zdot)
+    torch.cuda.synchronize()
+    tdir = [d for d, c in enumerate(cols) if c < spec.pi]
+    torch.autograd.backward([z64, zd64], [dz.cpu().double(), sum(dzdot[d] for d in tdir).cpu().double()])
+    for name in prm:
+        got = dw.cpu() if name == wn else db.cpu() if name == bn else leaves[name].grad
+        if got is None:
+            got = torch.zeros_like(prm[name])
+        e = rel_err(got, g64[name])
+        assert _gate(e, rel_err(g32[name], g64[name]), floor=2e-5), f"{name} err {e:.3e} (cpu32 {rel_err(g32[name], g64[name]):.3e})"
+
+
+def test_sobolev_training_with_dudt_in_the_loss():
+    """Tutorial 8's model with BOTH Jacobian columns in the loss (du/dt differentiates through the ParameterNet): three
+    Adam steps against autograd-of-autograd over the oracle."""
+    import nif_b200
+    cfg_s = {"use_resblock": False, "connectivity": "full", "input_dim": 1, "output_dim": 1, "units": 30, "nlayers": 2,
+             "weight_init_factor": 0.01, "omega_0": 30.0}
+    cfg_p = {"use_resblock": False, "input_dim": 1, "latent_dim": 2, "units": 30, "nlayers": 2, "activation": "swish"}
+    spec = O.spec_from_cfg("NIFMultiScale", cfg_s, cfg_p)
+    prm0 = O.init_params(spec, 4)
+    net = nif_b200.NIFMultiScale(cfg_s, cfg_p, seed=0, device="cuda:0")
+    net.set_weights({k: v.numpy() for k, v in prm0.items()})
+    coef = 1e-2
+    model = nif_b200.JacobianLayer(net.build(), y_index=[0], x_index=[0, 1]).as_model()
+    model.compile(nif_b200.Adam(1e-3), loss=nif_b200.SobolevMSE(coef, value_cols=[0], grad_cols=[1, 2]))
+    prm = {k: v.double().clone() for k, v in prm0.items()}
+    m_ = {k: torch.zeros_like(v) for k, v in prm.items()}
+    v_ = {k: torch.zeros_like(v) for k, v in prm.items()}
+    rng = np.random.default_rng(10)
+    B = 300
+    for step in range(1, 4):
+        X = rng.uniform(-1, 1, (B, 2)).astype(np.float32)
+        Y3 = rng.uniform(-1, 1, (B, 3)).astype(np.float32)
+        Y3[:, 1:] *= 5.0
+        l_gpu = model.train_on_batch(X, Y3)
+        Xd, Yd = torch.as_tensor(X).double(), torch.as_tensor(Y3).double()
+        l_ref, g, _, _ = O.sobolev_loss_and_grads_pairs(spec, prm, Xd, Yd[:, :1], Yd[:, 1:3], [(0, 0), (0, 1)], coef)
+        for k in prm:
+            O.adam_tf(prm[k], g[k], m_[k], v_[k], step, 1e-3)
+        assert abs(l_gpu - float(l_ref)) <= 1e-4 * max(1.0, abs(float(l_ref))), (step, l_gpu, float(l_ref))
+    got = net.get_weights()
+    diffs = np.concatenate([np.abs(got[k] - v.numpy()).ravel() for k, v in prm.items()])
+    assert float(np.quantile(diffs, 0.999)) < 1e-4, float(np.quantile(diffs, 0.999))
+    assert float(diffs.max()) < 4 * 2e-3
+
+
 # --------------------------------------------------------------------------------------------------
 # tensor-core path (tcgen05, FP16x3): same gates as the fp32 CUDA-core path
 # --------------------------------------------------------------------------------------------------
