@@ -116,6 +116,7 @@ __global__ void __launch_bounds__(TCE_THREADS, 1) nif_tc_bwd_edge_kernel(const P
     {  // MMA issuer: the whole warp runs the loop (uniform operands), one elected lane issues -- see tc_elect_one
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
       const uint32_t idesc = (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(KZ >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t idesc2 = (1u << 4) | (1u << 15) | (1u << 16) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
       for (long long t = 0; t < nsub; ++t) {
         const int sl = (int)(t & 1);
         mbar_wait(&slot_full[sl], (uint32_t)((t >> 1) & 1));
@@ -129,9 +130,10 @@ __global__ void __launch_bounds__(TCE_THREADS, 1) nif_tc_bwd_edge_kernel(const P
         for (int ks = 0; ks < 4; ++ks) {  // 16 rows (k) per instruction
           const uint64_t adv = (uint64_t)(ks * 16);
           const uint32_t accf = (t > 0 || ks > 0) ? 1u : 0u;
-          tc_mma_f16(d2, a_lo + adv, b_hi + adv, idesc, accf);
-          tc_mma_f16(d2, a_hi + adv, b_lo + adv, idesc, 1u);
-          tc_mma_f16(d1, a_hi + adv, b_hi + adv, idesc, accf);
+          // one N = 128 instruction over the adjacent [B_hi | B_lo] tiles: [d1 | d2] += a_hi x [b_hi | b_lo] (columns
+          // KZ..63 of either half are never read)
+          tc_mma_f16(d1, a_hi + adv, b_hi + adv, idesc2, accf);
+          tc_mma_f16(d2, a_lo + adv, b_hi + adv, idesc, 1u);
         }
         tc_commit(&slot_empty[sl]);
         }
