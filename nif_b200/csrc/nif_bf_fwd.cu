@@ -542,7 +542,7 @@ __global__ void __launch_bounds__(BFG_THREADS, 1) nif_bf_group_fwd_kernel(const 
               pre[2] = fmaf(xv[i], w4.z, pre[2]); pre[3] = fmaf(xv[i], w4.w, pre[3]);
             }
 #pragma unroll
-          for (int e = 0; e < 4; ++e) h[4 * c + e] = (j0 + e < n) ? act(pre[e]) : 0.f;
+          for (int e = 0; e < 4; ++e) h[4 * c + e] = (SINE || j0 + e < n) ? act(pre[e]) : 0.f;  // (padding: sin(0) = 0)
         }
         publish(t, h);
       }
@@ -580,8 +580,9 @@ __global__ void __launch_bounds__(BFG_THREADS, 1) nif_bf_group_fwd_kernel(const 
           }
           tc_fence_before();
           mbar_arrive(&t_free[t]);
+          // padded columns have zero weights and biases: sin(0) = 0 without a mask (2.5 of 7 instructions per element)
 #pragma unroll
-          for (int e = 0; e < CQ; ++e) h[e] = (qt * CQ + e < n) ? act(h[e]) : 0.f;
+          for (int e = 0; e < CQ; ++e) h[e] = (SINE || qt * CQ + e < n) ? act(h[e]) : 0.f;
           if (res == 1) {  // NIF hidden layer: out = in + act(pre); the input is this tile's operand (bf16)
 #pragma unroll
             for (int c = 0; c < CQ / 8; ++c) {
