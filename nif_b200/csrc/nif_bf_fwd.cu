@@ -16,6 +16,8 @@
 // latent-sweep inference of SURVEY 8 a7 (model_x_to_u_given_w, nif/model.py:435-464, 956-986, in factored form).
 #include "nif_bf.cuh"
 
+NIF_TRACE_READER(nif_debug_read_trace_bfg)
+
 struct BfFwdArgs {
   long long G, B, tiles_per_group, total_tiles;
   const float *z, *x, *packed;
@@ -421,6 +423,13 @@ __global__ void __launch_bounds__(BFG_THREADS, 1) nif_bf_group_fwd_kernel(const 
   const uint32_t nst = (uint32_t)a.nst;
   const long long pairs_per_group = (a.tiles_per_group + 1) / 2;
   const long long total_pairs = pairs_per_group * a.G;
+#ifdef NIF_TRACE
+  int trace_n = 0;
+  // roles: 0 = epilogue thread 0 (warp 0, column quarter 0), 1 = epilogue thread 416 (warp 13, quarter 3), 2 = MMA issuer
+#define BFG_TRACE(tag) do { if (tid == 0) TRACE(0, tag); else if (tid == 416) TRACE(1, tag); } while (0)
+#else
+#define BFG_TRACE(tag) do {} while (0)
+#endif
 
   if (tid == 0) {
     for (int i = 0; i < 8; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
@@ -469,6 +478,7 @@ __global__ void __launch_bounds__(BFG_THREADS, 1) nif_bf_group_fwd_kernel(const 
             tc_fence_after();
             const uint64_t dA = bf_make_desc(smem_u32(A_all + t * TILE_BYTES), SBO_A);
             const uint64_t dB = bf_make_desc(smem_u32(Bst + s * BF_STAGE_BYTES), SBO_A);
+            if (lane == 0) TRACE(2, (st * 2 + t) * 8 + 0);
             if (tc_elect_one()) {
               const uint32_t idesc = bf_idesc(last ? KZ : NP);
 #pragma unroll
@@ -561,9 +571,11 @@ __global__ void __launch_bounds__(BFG_THREADS, 1) nif_bf_group_fwd_kernel(const 
         }
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
+          BFG_TRACE((m * 2 + t) * 8 + 0);
           mbar_wait(&t_full[t], fph[t]);
           fph[t] ^= 1u;
           tc_fence_after();
+          BFG_TRACE((m * 2 + t) * 8 + 1);
           float h[CQ];
           if (CQ == 32) {
             float v[32];
@@ -580,6 +592,7 @@ __global__ void __launch_bounds__(BFG_THREADS, 1) nif_bf_group_fwd_kernel(const 
           }
           tc_fence_before();
           mbar_arrive(&t_free[t]);
+          BFG_TRACE((m * 2 + t) * 8 + 2);
           // padded columns have zero weights and biases: sin(0) = 0 without a mask (2.5 of 7 instructions per element)
 #pragma unroll
           for (int e = 0; e < CQ; ++e) h[e] = (SINE || qt * CQ + e < n) ? act(h[e]) : 0.f;
@@ -596,7 +609,12 @@ __global__ void __launch_bounds__(BFG_THREADS, 1) nif_bf_group_fwd_kernel(const 
               }
             }
           }
+#ifdef NIF_TRACE
+          asm volatile("" ::"f"(h[0]), "f"(h[CQ - 1]), "f"(h[CQ / 2]) : "memory");
+#endif
+          BFG_TRACE((m * 2 + t) * 8 + 3);
           publish(t, h);
+          BFG_TRACE((m * 2 + t) * 8 + 4);
         }
       }
       // ---- last layer: y[c] = h . ML[:, c] + CL[c]  (column kappa = 0 of the N = KZ chunk) ----
