@@ -40,6 +40,16 @@ xd[0, :, 0] = 1
 u, ud = eng.forward_tangent(z, x, packed, None, xd)
 torch.cuda.synchronize()
 print("tangent |udot|", float(ud.abs().max()))
+# reverse-over-forward over two directions, one of them moving the latent code (nif_sobolev_backward_dirs)
+xd2 = torch.zeros(2, 200, 2, device=dev)
+xd2[1, :, 1] = 1
+zd2 = torch.zeros(2, 200, 3, device=dev)
+zd2[0] = (torch.rand(200, 3, generator=g) - 0.5).to(dev)
+u, ud, stash = eng.forward_tangent(z, x, packed, zd2, xd2, save=True)
+dw, db = torch.empty(3, eng.po_dim, device=dev), torch.empty(eng.po_dim, device=dev)
+dz, dzd = eng.sobolev_backward(z, x, xd2, packed, stash, u * 1e-3, ud * 1e-3, dw, db, 0.0, zdot=zd2)
+torch.cuda.synchronize()
+print("tangent sobolev |dz|", float(dz.abs().max()), "|dzdot|", float(dzd.abs().max()))
 eng0 = FusedShapeNet("siren", 3, 1, 128, 2, 0, None, 30.0, compute="bf16")
 wv = (torch.rand(2, eng0.po_dim, generator=g) - 0.5).mul(0.05).to(dev)
 ug = eng0.forward(None, (torch.rand(200, 3, generator=g) * 2 - 1).to(dev), eng0.pack(None, wv), groups=2, x_shared=True)
