@@ -88,8 +88,8 @@ class SobolevMSE:
     """The `Sobolov_MSE` loss of tutorial 8 (tutorial/8_NIF_with_Sobolov_training.ipynb:815-820) for a model built
     with JacobianLayer.as_model(): per row  sum_{c in value_cols} (t_c - p_c)^2 + coef_grad * sum_{c in grad_cols}
     (t_c - p_c)^2, averaged over the batch.  Columns index the concatenated output [y | dy/dx flattened]; the
-    tutorial uses value_cols=[0], grad_cols=[2] (u and du/dx; du/dt is only monitored).  Every grad column must be a
-    derivative with respect to the SAME ShapeNet input (that is what the reverse-over-forward kernels differentiate).
+    tutorial uses value_cols=[0], grad_cols=[2] (u and du/dx; du/dt is only monitored).  Grad columns may differentiate
+    with respect to any inputs, ShapeNet coordinates and ParameterNet inputs alike (up to four distinct ones).
     Like the tutorial's `Sobolov_MSE`, each group is a MEAN over its columns (tf.reduce_mean(..., axis=-1))."""
 
     def __init__(self, coef_grad=1e-3, value_cols=(0,), grad_cols=(2,)):
@@ -465,8 +465,8 @@ class Model:
         self.use_graph = graph
         self._graphs = {}
         if self.kind == "jacobian":
-            if not isinstance(loss, SobolevMSE):
-                raise NifError("a JacobianLayer model trains with nif_b200.SobolevMSE (tutorial 8's Sobolov_MSE)")
+            # SobolevMSE names its columns; 'mse' or any callable(y_true, y_pred) sees the whole concatenated output
+            # [y | dy/dx], so every requested Jacobian entry becomes a direction / seed of the reverse-over-forward pass
             self._sobolev_plan = self._plan_sobolev(loss)
         elif self.kind != "full":
             raise NifError("only the full model is trainable")
@@ -878,11 +878,16 @@ class Model:
         """Map the loss columns onto tangent directions (one per differentiated input column) and ShapeNet outputs."""
         n = self.net
         ny, nx = len(self.jac_y), len(self.jac_x)
-        for c in loss.value_cols:
-            if not 0 <= c < n.so_dim:
-                raise NifError(f"value column {c} is not one of the {n.so_dim} model outputs")
+        general = not isinstance(loss, SobolevMSE)
+        if general:  # every Jacobian entry of the model output may enter the loss
+            grad_cols = list(range(n.so_dim, n.so_dim + ny * nx))
+        else:
+            grad_cols = loss.grad_cols
+            for c in loss.value_cols:
+                if not 0 <= c < n.so_dim:
+                    raise NifError(f"value column {c} is not one of the {n.so_dim} model outputs")
         dirs, pairs = [], []  # input column of each direction; (direction, output) of each grad column
-        for c in loss.grad_cols:
+        for c in grad_cols:
             k = c - n.so_dim
             if not 0 <= k < ny * nx:
                 raise NifError(f"grad column {c} is outside the Jacobian block of the model output")
@@ -897,8 +902,9 @@ class Model:
             raise NifError("SobolevMSE needs at least one grad column")
         from . import _lib
         if len(dirs) > _lib.NIF_MAX_DIR:
-            raise NifError(f"SobolevMSE: at most {_lib.NIF_MAX_DIR} differentiated inputs")
-        return {"dirs": dirs, "pairs": pairs, "latent_moves": any(c < n.pi_dim for c in dirs)}
+            raise NifError(f"a loss on a JacobianLayer model differentiates at most {_lib.NIF_MAX_DIR} inputs")
+        return {"dirs": dirs, "pairs": pairs, "grad_cols": grad_cols, "general": general,
+                "latent_moves": any(c < n.pi_dim for c in dirs)}
 
     def _train_step_sobolev(self, inp: torch.Tensor, tgt: torch.Tensor, global_batch: Optional[int]) -> torch.Tensor:
         """JacobianLayer inside the loss (tutorial 8): forward-mode tangents with a stash, then the reverse-over-forward
@@ -941,17 +947,32 @@ class Model:
         packed = self._packed_weights()
         u, udot, stash = eng.forward_tangent(zc, xs, packed, zdot, xdot, save=True)
         # seeds of the batch-mean loss (O(B) elementwise; everything heavier is in the library)
-        du = torch.zeros_like(u)
         dud = torch.zeros_like(udot)
-        vc, gc = loss.value_cols, loss.grad_cols
-        ev = u[:, vc] - tgt[:, vc]
-        du[:, vc] = (2.0 / (gb * len(vc))) * ev
-        sq_g = 0.0
-        for (d, yc), c in zip(pairs, gc):
-            eg = udot[d][:, yc] - tgt[:, c]
-            dud[d][:, yc] += (2.0 * loss.coef_grad / (gb * len(gc))) * eg
-            sq_g = sq_g + (eg * eg).sum()
-        lv = ((ev * ev).sum() / len(vc) + loss.coef_grad * sq_g / len(gc)) / gb
+        if plan["general"]:
+            # 'mse' or a callable(y_true, y_pred) on the concatenated output [u | du/dx...] (a PDE residual, say): its
+            # derivative with respect to that output is the seed, taken by autograd over the O(B) loss expression
+            with torch.enable_grad():
+                yp = torch.cat([u] + [udot[d][:, yc: yc + 1] for d, yc in pairs], -1).requires_grad_(True)
+                lv = self._mse_torch(tgt, yp, None) if isinstance(loss, str) else loss(tgt, yp)
+                if lv.dim() > 0:
+                    lv = lv.mean()
+                lv = lv * (B / gb)
+                (dy,) = torch.autograd.grad(lv, yp)
+            lv = lv.detach()
+            du = dy[:, : n.so_dim].contiguous()
+            for k, (d, yc) in enumerate(pairs):
+                dud[d][:, yc] += dy[:, n.so_dim + k]
+        else:
+            du = torch.zeros_like(u)
+            vc, gc = loss.value_cols, loss.grad_cols
+            ev = u[:, vc] - tgt[:, vc]
+            du[:, vc] = (2.0 / (gb * len(vc))) * ev
+            sq_g = 0.0
+            for (d, yc), c in zip(pairs, gc):
+                eg = udot[d][:, yc] - tgt[:, c]
+                dud[d][:, yc] += (2.0 * loss.coef_grad / (gb * len(gc))) * eg
+                sq_g = sq_g + (eg * eg).sum()
+            lv = ((ev * ev).sum() / len(vc) + loss.coef_grad * sq_g / len(gc)) / gb
         out = eng.sobolev_backward(zc, xs, xdot, packed, stash, du, dud, n._gviews[n._last_names[0]],
                                    n._gviews[n._last_names[1]], 0.0, zdot=zdot)
         if fused_trunk:

@@ -732,6 +732,26 @@ def sobolev_loss_and_grads_pairs(spec: Spec, prm: Dict[str, Tensor], inputs: Ten
     return loss.detach(), grads, y.detach(), dy.detach()
 
 
+def jacobian_model_loss_and_grads(spec: Spec, prm: Dict[str, Tensor], inputs: Tensor, y_true: Tensor, loss_fn, y_index,
+                                  x_index):
+    """Any loss on the output of a JacobianLayer-wrapped model (README.md:119-131: Model([x], [y, dydx]); a PDE residual
+    is such a loss): y_pred = [y | dy[y_index]/dx[x_index] flattened], loss_fn(y_true, y_pred) -> scalar, differentiated by
+    the outer tape with respect to every parameter.  Returns (loss, {name: grad}, y_pred)."""
+    leaves = {k: v.detach().clone().requires_grad_(True) for k, v in prm.items()}
+    inp = inputs.detach().clone().requires_grad_(True)
+    y = forward(spec, leaves, inp)
+    cols = []
+    for a in y_index:  # one reverse pass per output index (nif/layers/gradient.py:207-231)
+        (g,) = torch.autograd.grad(y[:, a].sum(), inp, create_graph=True, retain_graph=True)
+        cols.append(g[:, list(x_index)])
+    y_pred = torch.cat([y] + cols, -1)
+    loss = loss_fn(y_true, y_pred)
+    names = list(leaves)
+    got = torch.autograd.grad(loss, [leaves[k] for k in names], allow_unused=True)
+    grads = {k: (g if g is not None else torch.zeros_like(leaves[k])) for k, g in zip(names, got)}
+    return loss.detach(), grads, y_pred.detach()
+
+
 # ----------------------------------------------------------------------------
 # a whole training step in the reference's materialised dataflow (CPU baseline)
 # ----------------------------------------------------------------------------

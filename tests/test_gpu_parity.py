@@ -448,6 +448,49 @@ def test_sobolev_training_with_dudt_in_the_loss():
     assert float(diffs.max()) < 4 * 2e-3
 
 
+def test_pde_residual_loss_on_jacobian_model():
+    """A callable loss over the whole output of a JacobianLayer model -- here the advection residual u_t + c u_x next to
+    a data term, the physics-informed usage the reference's README points at -- and plain 'mse' over [u, u_t, u_x]: three
+    Adam steps each against autograd-of-autograd over the oracle."""
+    import nif_b200
+    cfg_s = {"use_resblock": False, "connectivity": "full", "input_dim": 1, "output_dim": 1, "units": 30, "nlayers": 2,
+             "weight_init_factor": 0.01, "omega_0": 30.0}
+    cfg_p = {"use_resblock": False, "input_dim": 1, "latent_dim": 2, "units": 30, "nlayers": 2, "activation": "swish"}
+    spec = O.spec_from_cfg("NIFMultiScale", cfg_s, cfg_p)
+
+    def residual(y_true, y_pred):
+        r = y_pred[:, 1] + 0.7 * y_pred[:, 2]
+        return ((y_true[:, 0] - y_pred[:, 0]) ** 2).mean() + 1e-2 * (r * r).mean()
+
+    def mse(y_true, y_pred):
+        return ((y_true - y_pred) ** 2).mean(-1).mean()
+
+    for loss_gpu, loss_ref in ((residual, residual), ("mse", mse)):
+        prm0 = O.init_params(spec, 5)
+        net = nif_b200.NIFMultiScale(cfg_s, cfg_p, seed=0, device="cuda:0")
+        net.set_weights({k: v.numpy() for k, v in prm0.items()})
+        model = nif_b200.JacobianLayer(net.build(), y_index=[0], x_index=[0, 1]).as_model()
+        model.compile(nif_b200.Adam(1e-3), loss=loss_gpu)
+        prm = {k: v.double().clone() for k, v in prm0.items()}
+        m_ = {k: torch.zeros_like(v) for k, v in prm.items()}
+        v_ = {k: torch.zeros_like(v) for k, v in prm.items()}
+        rng = np.random.default_rng(12)
+        B = 257
+        for step in range(1, 4):
+            X = rng.uniform(-1, 1, (B, 2)).astype(np.float32)
+            Y3 = rng.uniform(-1, 1, (B, 3)).astype(np.float32)
+            l_gpu = model.train_on_batch(X, Y3)
+            l_ref, g, _ = O.jacobian_model_loss_and_grads(spec, prm, torch.as_tensor(X).double(), torch.as_tensor(Y3).double(),
+                                                          loss_ref, [0], [0, 1])
+            for k in prm:
+                O.adam_tf(prm[k], g[k], m_[k], v_[k], step, 1e-3)
+            assert abs(l_gpu - float(l_ref)) <= 1e-4 * max(1.0, abs(float(l_ref))), (loss_gpu, step, l_gpu, float(l_ref))
+        got = net.get_weights()
+        diffs = np.concatenate([np.abs(got[k] - v.numpy()).ravel() for k, v in prm.items()])
+        assert float(np.quantile(diffs, 0.999)) < 1e-4, (loss_gpu, float(np.quantile(diffs, 0.999)))
+        assert float(diffs.max()) < 4 * 2e-3
+
+
 # --------------------------------------------------------------------------------------------------
 # tensor-core path (tcgen05, FP16x3): same gates as the fp32 CUDA-core path
 # --------------------------------------------------------------------------------------------------
