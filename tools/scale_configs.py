@@ -5,6 +5,7 @@
   C3  turbulence ShapeNet 6x128 SIREN, latent 64, mixed_bfloat16, data parallel WEAK scaling (65 536 rows per GPU, one NCCL
       all-reduce of the flat gradient per step), rows/s of the whole job
   C5  latent sweep 6x128: G latents x 64^3 grid points, the latent axis sharded over the ranks (no collective), evals/s
+  C2  STRONG scaling: bench.py's model at a fixed global batch of 65 536 rows split over the ranks
 Timing: CUDA events, barrier + synchronize on both sides, max over ranks."""
 import json
 import sys
@@ -71,6 +72,20 @@ ms5 = timed(lambda: m5.predict_latent_grid(lat, grid, shard=True), 5)
 out.append({"config": f"C5 latent sweep 6x128 mixed_bfloat16: {G} latents x {side}^3 grid, latent axis sharded over the ranks",
             "n_gpus": world, "ms_per_call": ms5, "evals_per_s": G * grid.shape[0] / ms5 * 1e3,
             "full_sweep_4096x256^3_seconds_at_this_rate": 4096 * 256**3 / (G * grid.shape[0] / ms5 * 1e3)})
+# ---- C2 STRONG scaling: the bench.py model at a FIXED global batch of 65 536 rows, split over the ranks ----
+import bench  # noqa: E402
+net2 = nif_b200.NIFMultiScale(bench.CFG_S, bench.CFG_P, "float32", seed=0, device=dev)
+m2 = net2.build(); m2.compile(nif_b200.Adam(1e-3), loss="mse")
+if world > 1:
+    dp.attach(m2)
+GB2 = 65536
+b2 = GB2 // world
+X2 = torch.as_tensor(rng.uniform(-1, 1, (b2, 3)).astype(np.float32)).to(dev)
+Y2 = torch.as_tensor(rng.uniform(-1, 1, (b2, 1)).astype(np.float32)).to(dev)
+ms2 = timed(lambda: m2._train_step(X2, Y2, None, GB2), 50, 5)
+out.append({"config": f"C2 strong scaling: global batch {GB2} rows split over the ranks ({b2} rows per GPU)", "n_gpus": world,
+            "scaling": "strong", "ms_per_step": ms2, "rows_per_s": GB2 / ms2 * 1e3,
+            "dp_update": "single" if world == 1 else ("multimem" if m2._symm is not None else "nccl")})
 if rank == 0:
     for o in out:
         print(json.dumps(o))
