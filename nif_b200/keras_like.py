@@ -84,6 +84,24 @@ class Adam:
         self._alpha_dev.fill_(alpha)  # by-value launch argument of a fill kernel: stream-ordered, no host buffer to race on
 
 
+class _nvtx:
+    """NVTX range around a phase of the step when NIF_B200_NVTX=1 (Nsight Systems / `ncu --nvtx` filters); a no-op
+    otherwise.  The kernels themselves are named; the ranges say which phase of which step launched them."""
+    ON = os.environ.get("NIF_B200_NVTX", "0") == "1"
+
+    def __init__(self, name: str):
+        self.name = name
+
+    def __enter__(self):
+        if self.ON:
+            torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *exc):
+        if self.ON:
+            torch.cuda.nvtx.range_pop()
+        return False
+
+
 class SobolevMSE:
     """The `Sobolov_MSE` loss of tutorial 8 (tutorial/8_NIF_with_Sobolov_training.ipynb:815-820) for a model built
     with JacobianLayer.as_model(): per row  sum_{c in value_cols} (t_c - p_c)^2 + coef_grad * sum_{c in grad_cols}
@@ -655,25 +673,32 @@ class Model:
         trunk's reverse pass runs; the small trunk gradient follows."""
         n = self.net
         if self._symm_ready() and apply_update is not None:
+            with _nvtx("nif.step.forward+head_reverse"):
+                ctx = part1() if part1 is not None else self._fused_part1(inp, tgt, sw, gb)
+            with _nvtx("nif.step.trunk_reverse"):
+                if part2 is not None:
+                    part2()
+                else:
+                    self._fused_part2(ctx)
+            with _nvtx("nif.step.multimem_update"):
+                self._symm_update()
+            return
+        with _nvtx("nif.step.forward+head_reverse"):
             ctx = part1() if part1 is not None else self._fused_part1(inp, tgt, sw, gb)
+        h_head = self.dist.allreduce_start(n.grad[n._n_trunk:]) if self.dist is not None else None
+        with _nvtx("nif.step.trunk_reverse"):
             if part2 is not None:
                 part2()
             else:
                 self._fused_part2(ctx)
-            self._symm_update()
-            return
-        ctx = part1() if part1 is not None else self._fused_part1(inp, tgt, sw, gb)
-        h_head = self.dist.allreduce_start(n.grad[n._n_trunk:]) if self.dist is not None else None
-        if part2 is not None:
-            part2()
-        else:
-            self._fused_part2(ctx)
         if self.dist is not None:
-            h_trunk = self.dist.allreduce_start(n.grad_trunk)
-            self.dist.allreduce_finish(h_head)
-            self.dist.allreduce_finish(h_trunk)
+            with _nvtx("nif.step.allreduce"):
+                h_trunk = self.dist.allreduce_start(n.grad_trunk)
+                self.dist.allreduce_finish(h_head)
+                self.dist.allreduce_finish(h_trunk)
         l1, l2 = n._kernel_regulariser()
-        self._apply_update(apply_update, l1, l2)
+        with _nvtx("nif.step.update"):
+            self._apply_update(apply_update, l1, l2)
 
     # ---- CUDA-graph replay of the fused step ------------------------------------------------------------------
     # One optimisation step is 17 kernel launches from Python; at tutorial-1 sizes (512 rows) the launches, not the
