@@ -582,8 +582,12 @@ class Model:
         else:
             eng = n.engine
             # mixed_bfloat16: the ParameterNet's Dense / SIREN layers compute in bfloat16 too (nif/model.py:101-105)
-            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=(n.compute_Dtype == "bfloat16")):
-                z = n._latent(p_in)
+            n._first_order_only = not extra  # no jac_reg term: the trunk is differentiated once
+            try:
+                with torch.autocast("cuda", dtype=torch.bfloat16, enabled=(n.compute_Dtype == "bfloat16")):
+                    z = n._latent(p_in)
+            finally:
+                n._first_order_only = False
             z = z.float()
             act = self._activity_terms(z.detach(), B, gb) if with_regularisers else None
             if not callable(loss):

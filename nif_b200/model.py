@@ -264,8 +264,15 @@ class NIF(object):
         return {k: v.detach().cpu().numpy().copy() for k, v in self._views.items()}
 
     # ---- ParameterNet trunk (everything before the last linear; plain torch ops) ----------------------
+    # set around calls that differentiate the trunk once only (the plain training step): swish runs as the single silu
+    # kernel (one forward, one backward instead of two and four); silu's backward has no forward-mode rule, so the paths
+    # that differentiate the trunk twice (jac_reg, Hessians, du/dt in the loss) keep the composite form
+    _first_order_only = False
+
     def _act(self, name):
         if name == "swish":
+            if self._first_order_only:
+                return torch.nn.functional.silu
             return lambda v: v * torch.sigmoid(v)
         if name == "tanh":
             return torch.tanh
