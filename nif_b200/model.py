@@ -35,6 +35,30 @@ def _uniform(shape, bound, gen):
     return ((torch.rand(shape, dtype=torch.float64, generator=gen) * 2 - 1) * b).float()
 
 
+class _TrunkLinear(torch.autograd.Function):
+    """y = h @ W + b of a ParameterNet Dense layer for the paths that differentiate the trunk once.  Same arithmetic as
+    the plain torch expression under the model's policy (bf16 operands and products under mixed_bfloat16, fp32 bias
+    add), but the bias gradient is a GEMV with a row of ones instead of torch's column reduction (69 -> 12 microseconds
+    per layer at 65 536 x 128) and the bf16 operand copies are made once and kept for the reverse pass."""
+
+    @staticmethod
+    def forward(ctx, h, W, b, bf16):
+        if bf16:
+            h, W = h.to(torch.bfloat16), W.to(torch.bfloat16)
+        ctx.save_for_backward(h, W)
+        with torch.autocast("cuda", enabled=False):
+            return (h @ W).float() + b
+
+    @staticmethod
+    def backward(ctx, dy):
+        h, W = ctx.saved_tensors
+        g = dy.to(h.dtype)
+        dh = (g @ W.t()).float() if ctx.needs_input_grad[0] else None
+        dW = (h.t() @ g).float()
+        db = (dy.new_ones(1, dy.shape[0]) @ dy.float()).reshape(-1)
+        return dh, dW, db, None
+
+
 class NIF(object):
     """Neural Implicit Flow with a swish/tanh/... ShapeNet with residual hidden layers
     (reference: class NIF, nif/model.py:48-480).
@@ -284,15 +308,20 @@ class NIF(object):
             return lambda v: v
         raise ValueError(f"ParameterNet activation {name!r} is not supported")
 
+    def _lin(self, h, W, b):
+        if self._first_order_only and h.is_cuda:
+            return _TrunkLinear.apply(h, W, b, torch.is_autocast_enabled())
+        return h @ W + b
+
     def _latent(self, input_p: torch.Tensor) -> torch.Tensor:
         """_call_parameter_net up to the bottleneck (nif/model.py:326-343; MLP_SimpleShortCut mlp.py:148-160)."""
         V = self._views
         f = self._act(self.cfg_parameter_net["activation"])
-        h = f(input_p @ V["first_dense_pnet/kernel"] + V["first_dense_pnet/bias"])
+        h = f(self._lin(input_p, V["first_dense_pnet/kernel"], V["first_dense_pnet/bias"]))
         for i in range(self.l_st):
             q = f"hidden_mlpshortcut_pnet_{i}"
-            h = h + f(h @ V[q + "/kernel"] + V[q + "/bias"])
-        return h @ V["bottleneck_pnet/kernel"] + V["bottleneck_pnet/bias"]
+            h = h + f(self._lin(h, V[q + "/kernel"], V[q + "/bias"]))
+        return self._lin(h, V["bottleneck_pnet/kernel"], V["bottleneck_pnet/bias"])
 
     @property
     def w_h(self) -> torch.Tensor:
@@ -479,16 +508,16 @@ class NIFMultiScale(NIF):
                     h = torch.sin(w0 * (h @ V[q + "_w"]) + V[q + "_b"])
             return h @ V["siren_bottleneck_pnet_w"] + V["siren_bottleneck_pnet_b"]
         f = self._act(p["activation"])
-        h = f(input_p @ V["mlp_first_pnet/kernel"] + V["mlp_first_pnet/bias"])
+        h = f(self._lin(input_p, V["mlp_first_pnet/kernel"], V["mlp_first_pnet/bias"]))
         for i in range(self.l_st):
             if res:  # MLP_ResNet (nif/layers/mlp.py:62-79)
                 q = f"mlp_hidden_resblock_pnet_{i}"
-                h1 = f(h @ V[q + "_dense_1/kernel"] + V[q + "_dense_1/bias"])
-                h = f(h + h1 @ V[q + "_dense_2/kernel"] + V[q + "_dense_2/bias"])
+                h1 = f(self._lin(h, V[q + "_dense_1/kernel"], V[q + "_dense_1/bias"]))
+                h = f(h + self._lin(h1, V[q + "_dense_2/kernel"], V[q + "_dense_2/bias"]))
             else:  # MLP_SimpleShortCut (nif/layers/mlp.py:148-160)
                 q = f"mlp_hidden_pnet_{i}"
-                h = h + f(h @ V[q + "/kernel"] + V[q + "/bias"])
-        return h @ V["bottleneck_pnet/kernel"] + V["bottleneck_pnet/bias"]
+                h = h + f(self._lin(h, V[q + "/kernel"], V[q + "/bias"]))
+        return self._lin(h, V["bottleneck_pnet/kernel"], V["bottleneck_pnet/bias"])
 
 
 class NIFMultiScaleLastLayerParameterized(NIFMultiScale):
