@@ -15,6 +15,8 @@
 // with both operands generated on the fly (MN-major bf16), accumulators resident in TMEM over the batch split.
 #include "nif_bf.cuh"
 
+NIF_TRACE_READER(nif_debug_read_trace_bfe)
+
 struct BfBwdArgs {
   long long B, total_tiles;
   const float *z, *x, *packed, *save, *du;
@@ -595,7 +597,7 @@ int nif_bf_bwd_weight_impl(const Plan& pl, long long B, const float* z, const fl
 //   out[kappa][q] = sum_b zt[b][kappa] F[b][q],   F = on-the-fly features of row b (column space Q of nif_bwd_edge_kernel:
 //   [(H+1) NP: da_m[j]] [so: du[c]] [si NP: omega x[i] da_0[j]] [NP so: h_{H+1}[i] du[c]])
 // A batch-reduction GEMM with M = kappa (one 128-row tile: K + 1 <= 128), N = a block of 128 feature columns, K = batch.
-//   A = zt^T  [128 kappa x 64 b], K-major, generated by warps 0-3 (thread = kappa: 64 coalesced loads, 8 stores)
+//   A = zt^T  [128 kappa x 64 b], MN-major, generated by warps 0-3 (two threads per batch row: vector loads of z, 16-byte stores)
 //   B = F^T   [128 q x 64 b], MN-major, generated by warps 4-7 / 8-11 (one slot each; two threads per row)
 // One CTA = (feature block, batch split); the accumulator stays in TMEM; partials in the layout nif_unpack_grad_kernel sums.
 // Feature blocks: m = 0..H (da_m) | i < si (omega x_i da_0) | c < so (du_c h_{H+1}) | one block holding du.
@@ -610,7 +612,7 @@ struct BfEdgeArgs {
 
 template <int NP>
 __global__ void __launch_bounds__(BFE_THREADS, 1) nif_bf_bwd_edge_kernel(const Plan pl, const BfEdgeArgs a) {
-  constexpr uint32_t A_BYTES = 16384u;      // [128 kappa x 64 b] bf16, K-major (SBO 1024, LBO 128)
+  constexpr uint32_t A_BYTES = 16384u;      // [128 kappa x 64 b] bf16, MN-major
   constexpr uint32_t B_BYTES = NP * 128u;   // [NP q x 64 b] bf16, MN-major
   constexpr uint32_t SLOT_BYTES = A_BYTES + B_BYTES;
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -623,6 +625,12 @@ __global__ void __launch_bounds__(BFE_THREADS, 1) nif_bf_bwd_edge_kernel(const P
   long long r1 = r0 + a.rows_per_split;
   if (r1 > a.B) r1 = a.B;
   const long long nsub = r1 > r0 ? (r1 - r0 + 63) / 64 : 0;
+#ifdef NIF_TRACE
+  int trace_n = 0;
+#define BFE_TRACE(role, tag) do { if (blockIdx.y == 0) TRACE(role, tag); } while (0)
+#else
+#define BFE_TRACE(role, tag) do {} while (0)
+#endif
 
   if (tid == 0) {
     mbar_init(&slot_full[0], 256); mbar_init(&slot_full[1], 256);
@@ -639,14 +647,15 @@ __global__ void __launch_bounds__(BFE_THREADS, 1) nif_bf_bwd_edge_kernel(const P
 
   if (warp == 12) {
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
-    const uint32_t idesc = bf_idesc(NP, 0, 1);  // A K-major, B MN-major
+    const uint32_t idesc = bf_idesc(NP, 1, 1);  // A and B MN-major
     for (long long t = 0; t < nsub; ++t) {
       const int sl = (int)(t & 1);
       mbar_wait(&slot_full[sl], (uint32_t)((t >> 1) & 1));
       tc_fence_after();
+      if ((tid & 31) == 0) BFE_TRACE(2, (int)t * 8 + 7);
       if (tc_elect_one()) {
         const uint32_t base = smem_u32(smem + sl * SLOT_BYTES);
-        const uint64_t dA = tc_make_desc(base, 1024u);
+        const uint64_t dA = bfw_make_desc(base);
         const uint64_t dB = bfw_make_desc(base + A_BYTES);
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks)
@@ -658,35 +667,66 @@ __global__ void __launch_bounds__(BFE_THREADS, 1) nif_bf_bwd_edge_kernel(const P
     if (tc_elect_one()) tc_commit(&done_bar);
     __syncwarp();
   } else if (warp < 4) {
-    // ---------------- A generators: thread = kappa; every sub-tile (both slots) ----------------
-    const int kk = tid;  // 0..127
-    const bool zreal = kk < K;
-    const float fill = kk == K ? 1.f : 0.f;
-    float zn[64];
+    // ---------------- A generators: thread (hf, r) = batch row r of the sub-tile, kappa groups g = hf, hf + 2, ...; every
+    // sub-tile (both slots).  A = zt^T is MN-major like B, so a thread owns a ROW of z: (K + 1) / 8 vector loads and 16-byte
+    // stores per row, instead of 64 scalar loads and a long predicate chain per kappa (the device timeline showed this
+    // warp group, not the MMAs, setting the pace: 2600 of 3250 cycles per sub-tile).  kappa groups past K are zeroed once.
+    const int hf = tid >> 6, r = tid & 63;
+    const int K8 = (K1 + 7) / 8;  // kappa groups that hold values (<= 16)
+    const uint32_t koff = (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 16u;
+    const bool vec = (K & 3) == 0;  // rows of z are 16-byte aligned
+    for (int e = tid; e < 2 * (int)(A_BYTES / 16); e += 128) {
+      const int sl = e / (int)(A_BYTES / 16), o = e % (int)(A_BYTES / 16);
+      *reinterpret_cast<uint4*>(smem + sl * SLOT_BYTES + o * 16) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    named_bar_sync(1, 128);
+    float zn[8][8];
     auto fetch = [&](long long t) {
+      const long long b = r0 + t * 64 + r;
+      const bool live = t < nsub && b < r1;
+      const float* zrow = a.z + (live ? b : r0) * K;
 #pragma unroll
-      for (int e = 0; e < 64; ++e) {
-        const long long b = r0 + t * 64 + e;
-        zn[e] = (t < nsub && b < r1) ? (zreal ? __ldg(&a.z[b * K + kk]) : fill) : 0.f;
+      for (int u = 0; u < 8; ++u) {
+        const int g = hf + 2 * u;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) zn[u][e] = 0.f;
+        if (g < K8 && live) {
+          if (vec && 8 * g + 8 <= K) {
+            const float4 p0 = ldg4(zrow + 8 * g), p1 = ldg4(zrow + 8 * g + 4);
+            zn[u][0] = p0.x; zn[u][1] = p0.y; zn[u][2] = p0.z; zn[u][3] = p0.w;
+            zn[u][4] = p1.x; zn[u][5] = p1.y; zn[u][6] = p1.z; zn[u][7] = p1.w;
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int kk = 8 * g + e;
+              zn[u][e] = kk < K ? __ldg(zrow + kk) : (kk == K ? 1.f : 0.f);
+            }
+          }
+        }
       }
     };
     fetch(0);
     for (long long t = 0; t < nsub; ++t) {
       const int sl = (int)(t & 1);
+      if (tid == 0) BFE_TRACE(0, (int)t * 8 + 0);
       uint4 w[8];
 #pragma unroll
-      for (int c = 0; c < 8; ++c)
-        w[c] = make_uint4(bf_pack2(zn[8 * c], zn[8 * c + 1]), bf_pack2(zn[8 * c + 2], zn[8 * c + 3]),
-                          bf_pack2(zn[8 * c + 4], zn[8 * c + 5]), bf_pack2(zn[8 * c + 6], zn[8 * c + 7]));
+      for (int u = 0; u < 8; ++u)
+        w[u] = make_uint4(bf_pack2(zn[u][0], zn[u][1]), bf_pack2(zn[u][2], zn[u][3]), bf_pack2(zn[u][4], zn[u][5]),
+                          bf_pack2(zn[u][6], zn[u][7]));
+      if (tid == 0) BFE_TRACE(0, (int)t * 8 + 1);
       fetch(t + 1);
       mbar_wait(&slot_empty[sl], (uint32_t)(((t >> 1) & 1) ^ 1));
+      if (tid == 0) BFE_TRACE(0, (int)t * 8 + 2);
       unsigned char* At = smem + sl * SLOT_BYTES;
-      const uint32_t roff = (uint32_t)(kk >> 3) * 1024u + (uint32_t)(kk & 7) * 16u;
 #pragma unroll
-      for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(At + roff + c * 128) = w[c];
+      for (int u = 0; u < 8; ++u)
+        if (hf + 2 * u < K8) *reinterpret_cast<uint4*>(At + (uint32_t)(hf + 2 * u) * 1024u + koff) = w[u];
       fence_async_smem();
       mbar_arrive(&slot_full[sl]);
+      if (tid == 0) BFE_TRACE(0, (int)t * 8 + 3);
     }
+    const int kk = tid;  // final epilogue: TMEM lane = kappa
     // ---------------- final epilogue: TMEM lane = kappa ----------------
     mbar_wait(&done_bar, 0);
     tc_fence_after();
@@ -754,12 +794,14 @@ __global__ void __launch_bounds__(BFE_THREADS, 1) nif_bf_bwd_edge_kernel(const P
     fetch(sl);
     long long n_mine = 0;
     for (long long t = sl; t < nsub; t += 2, ++n_mine) {
+      if (tid == 128) BFE_TRACE(1, (int)t * 8 + 4);
       float4 f[NQ];
       const float mul = mul_n;
 #pragma unroll
       for (int c = 0; c < NQ; ++c) f[c] = fn[c];
       fetch(t + 2);
       mbar_wait(&slot_empty[sl], (uint32_t)((n_mine & 1) ^ 1));
+      if (tid == 128) BFE_TRACE(1, (int)t * 8 + 5);
       unsigned char* Bt = smem + sl * SLOT_BYTES + A_BYTES;
 #pragma unroll
       for (int u = 0; u < NQ / 2; ++u) {
@@ -771,6 +813,7 @@ __global__ void __launch_bounds__(BFE_THREADS, 1) nif_bf_bwd_edge_kernel(const P
       }
       fence_async_smem();
       mbar_arrive(&slot_full[sl]);
+      if (tid == 128) BFE_TRACE(1, (int)t * 8 + 6);
     }
   }
   tc_fence_before();
