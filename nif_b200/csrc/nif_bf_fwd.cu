@@ -63,6 +63,9 @@ __global__ void __launch_bounds__(BFF_THREADS, 1) nif_bf_fwd_kernel(const Plan p
   const int NCHW = bf_nchw(pl);
   const uint32_t nst = (uint32_t)a.nst;
   const uint32_t small_bytes = (uint32_t)NP * (uint32_t)KZ * 2u;
+#ifdef NIF_TRACE
+  int trace_n = 0;  // tools/bff_trace.py: roles 0 = epilogue thread 0, 2 = MMA issuer, 3 = weight-stream producer
+#endif
 
   if (tid == 0) {
     for (int i = 0; i < 8; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
@@ -87,6 +90,7 @@ __global__ void __launch_bounds__(BFF_THREADS, 1) nif_bf_fwd_kernel(const Plan p
         uint32_t s = 0, ph = 0;
         auto put = [&](const float* src, uint32_t bytes) {
           mbar_wait(&b_empty[s], ph ^ 1u);
+          TRACE(3, 0);
           mbar_expect_tx(&b_full[s], bytes);
           bulk_g2s(Bst + s * BF_STAGE_BYTES, src, bytes, &b_full[s]);
           if (++s == nst) { s = 0; ph ^= 1u; }
@@ -117,8 +121,11 @@ __global__ void __launch_bounds__(BFF_THREADS, 1) nif_bf_fwd_kernel(const Plan p
       auto chunk = [&](bool a_main, bool wait_a, int ksteps, uint32_t b_sbo, int N) {
         const uint32_t as = g & 1u;
         if (wait_a) { mbar_wait(&a_ready[0], ar & 1u); ++ar; }
+        if (lane == 0) TRACE(2, g * 8 + 0);
         mbar_wait(&t_empty[as], ((g >> 1) & 1u) ^ 1u);
+        if (lane == 0) TRACE(2, g * 8 + 1);
         mbar_wait(&b_full[s], ph);
+        if (lane == 0) TRACE(2, g * 8 + 2);
         tc_fence_after();
         const uint64_t db = bf_make_desc(smem_u32(Bst + s * BF_STAGE_BYTES), b_sbo);
         const uint64_t dA = a_main ? da : dz;
@@ -179,13 +186,16 @@ __global__ void __launch_bounds__(BFF_THREADS, 1) nif_bf_fwd_kernel(const Plan p
       float hcur[CH];  // output of the layer being finished (this thread's columns)
 
       auto chunk_begin = [&]() -> uint32_t {
+        if (tid == 0) TRACE(0, g * 8 + 3);
         mbar_wait(&t_full[g & 1u], (g >> 1) & 1u);
         tc_fence_after();
+        if (tid == 0) TRACE(0, g * 8 + 4);
         return tm + (g & 1u) * 128u;
       };
       auto chunk_end = [&]() {
         tc_fence_before();
         mbar_arrive(&t_empty[g & 1u]);
+        if (tid == 0) TRACE(0, g * 8 + 5);
         ++g;
       };
       // acc[e] (+)= coef * D[col0 + e], e < CH
