@@ -153,3 +153,36 @@ def test_mixed_bfloat16_policy_selects_the_bf16_kernels_and_trains():
     # the float32 policy on the same architecture runs elsewhere (fp32-grade kernels)
     net32 = nif_b200.NIFMultiScale(cfg_s, cfg_p, "float32", seed=0, device=dev)
     assert net32.engine.kernel_path != "bf16"
+
+
+@pytest.mark.parametrize("policy", ["mixed_bfloat16", "float32"])
+def test_torch_trunk_fast_path_equals_the_composite_ops(policy):
+    """A 128-wide ParameterNet trunk runs as torch ops.  Where it is differentiated once, swish is the single silu kernel
+    and the Dense layers go through model._TrunkLinear (bias gradient as a GEMV, bf16 operand copies kept): same latent code
+    and the same gradients as the composite expression under the same policy."""
+    import nif_b200
+    dev = torch.device("cuda:0")
+    cfg_s = {"use_resblock": False, "connectivity": "full", "input_dim": 2, "output_dim": 1, "units": 64, "nlayers": 2,
+             "weight_init_factor": 0.01, "omega_0": 30.0}
+    cfg_p = {"use_resblock": False, "input_dim": 1, "latent_dim": 16, "units": 128, "nlayers": 3, "activation": "swish"}
+    net = nif_b200.NIFMultiScale(cfg_s, cfg_p, policy, seed=0, device=dev)
+    assert net._trunk is None  # not one of the fused trunk shapes
+    g = torch.Generator().manual_seed(3)
+    p_in = (torch.rand(3000, 1, generator=g) * 2 - 1).to(dev)
+    dz = torch.randn(3000, 16, generator=g).to(dev)
+    out = {}
+    for fast in (True, False):
+        net.grad.zero_()
+        net._first_order_only = fast
+        try:
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=(policy == "mixed_bfloat16")):
+                z = net._latent(p_in)
+        finally:
+            net._first_order_only = False
+        z.float().backward(dz)
+        out[fast] = (z.detach().float().clone(), net.grad.clone())
+    # bf16: an fp32 difference of one ulp between silu(x) and x * sigmoid(x) can flip the bf16 rounding of an activation (one
+    # bf16 ulp = 4e-3 of that element) ahead of the next matmul: the two paths agree to bf16 rounding noise, not bit for bit
+    tol = GATE_EMU if policy == "mixed_bfloat16" else 1e-5
+    assert rel_err(out[True][0].cpu(), out[False][0].cpu()) < tol
+    assert rel_err(out[True][1].cpu(), out[False][1].cpu()) < tol
