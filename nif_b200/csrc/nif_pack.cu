@@ -125,13 +125,20 @@ __device__ __forceinline__ float tcx_value(const Plan& pl, const float* __restri
   return src_at(pl, w_h, b_h, 0, row, (t2 - pl.H - 1) * n + col);
 }
 
+// The thin sections of the image (M0, ML, C, the small tensor-core tiles): one thread per float slot.  The hidden
+// matrices (MH, MHT and the main tensor-core tiles) are written by nif_pack_mats_kernel, one block per matrix.
+// Slots visited per group: [off_M0, end1) and [off_TCX, end2)  (end1 = off_TCF | off_WF | packed_floats).
 __global__ void __launch_bounds__(256) nif_pack_kernel(const Plan pl, long long G, const float* __restrict__ w_h,
-                                                       const float* __restrict__ b_h, float* __restrict__ packed) {
-  const long long total = G * pl.packed_floats;
+                                                       const float* __restrict__ b_h, float* __restrict__ packed,
+                                                       long long end1, long long end2) {
+  const long long len1 = end1 - pl.off_M0, len2 = end2 > 0 ? end2 - pl.off_TCX : 0;
+  const long long per_group = len1 + len2, total = G * per_group;
   const int K1 = pl.K + 1, NP = pl.NP, n = pl.n, H = pl.H;
-  for (long long e = blockIdx.x * 256LL + threadIdx.x; e < total; e += 256LL * gridDim.x) {
-    const long long g = e / pl.packed_floats;
-    long long r = e - g * pl.packed_floats;
+  for (long long e0 = blockIdx.x * 256LL + threadIdx.x; e0 < total; e0 += 256LL * gridDim.x) {
+    const long long g = e0 / per_group;
+    const long long q = e0 - g * per_group;
+    long long r = q < len1 ? pl.off_M0 + q : pl.off_TCX + (q - len1);
+    const long long e = g * pl.packed_floats + r;
     float v = 0.f;
     if (pl.bf && r >= pl.off_WF) continue;  // bf16 operand tiles: written by nif_pack_bf_kernel
     if (r < pl.off_MHT) {  // MH [H (+1 if wide_last)][K1][NP][NP]
@@ -246,22 +253,116 @@ __global__ void __launch_bounds__(256) nif_pack_kernel(const Plan pl, long long 
   }
 }
 
-// one block per (hidden matrix, kappa): inverse power-of-two scale of the slab so that max|M| * 2^e is in [2^13, 2^14)
+// ---------------------------------------------------------------------------------------------------
+// Hidden matrices: one block per (group, matrix h, latent coordinate kappa).  The n x n block of the reference layout is
+// read once (coalesced) into shared memory and written as MH[h][kappa] (row-major, zero padded to NP x NP), MHT (its
+// transpose) and -- for the FP16x3 tensor-core plans -- the forward and reverse operand tiles [hi | lo] of chunk kappa / 2
+// with the slab's power-of-two scale (which the block computes itself: max |M| over the matrix).  The per-element kernel
+// this replaces spent ~150 instructions of index arithmetic per float: 80 -> ~15 microseconds at C2, where it sits in
+// front of every step of a small batch.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) nif_pack_mats_kernel(const Plan pl, const float* __restrict__ w_h,
+                                                            const float* __restrict__ b_h, float* __restrict__ packed_all) {
+  extern __shared__ float Ms[];  // [NP][NP + 1]
+  const int K1 = pl.K + 1, NP = pl.NP, n = pl.n, H = pl.H, HT = pl.H + pl.wide_last;
+  const int KPAD = pl.tc ? pl.KP : K1;  // the tensor-core image also holds (zero) tiles of the padding coordinates
+  const int LD = NP + 1;
+  int bid = blockIdx.x;
+  const int kk = bid % KPAD; bid /= KPAD;
+  const int h = bid % HT;
+  const long long g = bid / HT;
+  float* packed = packed_all + g * pl.packed_floats;
+  const int tid = threadIdx.x;
+  const bool real = kk < K1;
+  const int rows = n, cols = h < H ? n : pl.so;
+  const float* src = nullptr;
+  if (real) src = (kk < pl.K ? w_h + (long long)kk * pl.P : b_h + g * pl.P) + plan_w_off(pl, h + 1);
+  float mx = 0.f;
+  for (int e = tid; e < NP * NP; e += 256) {
+    const int i = e / NP, j = e - i * NP;
+    float v = 0.f;
+    if (real && i < rows && j < cols) v = __ldg(&src[i * cols + j]);
+    Ms[i * LD + j] = v;
+    mx = fmaxf(mx, fabsf(v));
+  }
+  __shared__ float red[256];
+  __shared__ float sc_s;
+  red[tid] = mx;
+  __syncthreads();
+  if (pl.tc && h < H) {
+    for (int o = 128; o >= 1; o >>= 1) {
+      if (tid < o) red[tid] = fmaxf(red[tid], red[tid + o]);
+      __syncthreads();
+    }
+    if (tid == 0) {
+      float inv = 1.0f;
+      const float m = red[0];
+      if (m > 0.f && m < 3.0e38f) {
+        int ex = (int)((__float_as_uint(m) >> 23) & 0xFF) - 127;  // floor(log2(max)) for normal numbers
+        ex = max(-100, min(100, ex));
+        inv = __uint_as_float((uint32_t)(127 + ex - 13) << 23);    // 2^(ex-13): scaled max lands in [2^13, 2^14)
+      }
+      packed[pl.off_TCS + h * pl.KP + kk] = inv;
+      sc_s = 1.0f / inv;  // exact power of two
+    }
+    __syncthreads();
+  }
+  if (real) {
+    float* mh = packed + pl.off_MH + ((long long)h * K1 + kk) * NP * NP;
+    float* mht = packed + pl.off_MHT + ((long long)h * K1 + kk) * NP * NP;
+    for (int e = tid; e < NP * NP / 4; e += 256) {
+      const int i = e / (NP / 4), j4 = (e - i * (NP / 4)) * 4;
+      *reinterpret_cast<float4*>(&mh[i * NP + j4]) = make_float4(Ms[i * LD + j4], Ms[i * LD + j4 + 1], Ms[i * LD + j4 + 2], Ms[i * LD + j4 + 3]);
+      // transposed: row i of MHT is column i of M
+      *reinterpret_cast<float4*>(&mht[i * NP + j4]) = make_float4(Ms[j4 * LD + i], Ms[(j4 + 1) * LD + i], Ms[(j4 + 2) * LD + i], Ms[(j4 + 3) * LD + i]);
+    }
+  }
+  if (pl.tc && h < H) {
+    // operand tiles (NP == 64): 16-byte units (row nrow = 64 (kappa % 2) + a, 8 consecutive k) in memory order
+    const float sc = sc_s;
+    const int c = kk >> 1, half = kk & 1;
+    float* tf = packed + pl.off_TCF + ((long long)h * pl.NCH + c) * NIF_TC_CHUNK_FLOATS;
+    float* tb = packed + pl.off_TCB + ((long long)h * pl.NCH + c) * NIF_TC_CHUNK_FLOATS;
+    for (int u = tid; u < 512; u += 256) {
+      const int rg = u >> 6, kc = (u >> 3) & 7, rq = u & 7;
+      const int a = rg * 8 + rq;
+      const int slot = (((half * 8 + rg) * 8 + kc) * 8 + rq) * 4;  // float slot of the unit inside a [128 x 64] fp16 tile
+      uint32_t fh[4], fl[4], bh[4], bl[4];
+#pragma unroll
+      for (int q2 = 0; q2 < 4; ++q2) {
+        const int k0 = kc * 8 + 2 * q2;
+        // forward tile: rows are j = a, K = i;   reverse tile: rows are i = a, K = j
+        const float f0 = Ms[k0 * LD + a] * sc, f1 = Ms[(k0 + 1) * LD + a] * sc;
+        const float b0 = Ms[a * LD + k0] * sc, b1 = Ms[a * LD + k0 + 1] * sc;
+        __half2 o = __floats2half2_rn(f0, f1);
+        fh[q2] = *reinterpret_cast<uint32_t*>(&o);
+        o = __floats2half2_rn(f0 - __half2float(__float2half_rn(f0)), f1 - __half2float(__float2half_rn(f1)));
+        fl[q2] = *reinterpret_cast<uint32_t*>(&o);
+        o = __floats2half2_rn(b0, b1);
+        bh[q2] = *reinterpret_cast<uint32_t*>(&o);
+        o = __floats2half2_rn(b0 - __half2float(__float2half_rn(b0)), b1 - __half2float(__float2half_rn(b1)));
+        bl[q2] = *reinterpret_cast<uint32_t*>(&o);
+      }
+      *reinterpret_cast<uint4*>(&tf[slot]) = make_uint4(fh[0], fh[1], fh[2], fh[3]);
+      *reinterpret_cast<uint4*>(&tf[4096 + slot]) = make_uint4(fl[0], fl[1], fl[2], fl[3]);
+      *reinterpret_cast<uint4*>(&tb[slot]) = make_uint4(bh[0], bh[1], bh[2], bh[3]);
+      *reinterpret_cast<uint4*>(&tb[4096 + slot]) = make_uint4(bl[0], bl[1], bl[2], bl[3]);
+    }
+  }
+}
+
+// one block per small tensor-core tile: inverse power-of-two scale of the tile so that max|.| * 2^e is in [2^13, 2^14)
+// (the scales of the main slabs are computed by nif_pack_mats_kernel, which reads those matrices anyway)
 __global__ void __launch_bounds__(256) nif_pack_scales_kernel(const Plan pl, const float* __restrict__ w_h,
                                                               const float* __restrict__ b_h, float* __restrict__ packed) {
-  const int nmain = pl.H * pl.KP;
-  const bool small = (int)blockIdx.x >= nmain;
-  const int h = blockIdx.x / pl.KP, kk = blockIdx.x % pl.KP;
-  const int T = blockIdx.x - nmain;
-  const int n = pl.n;
+  const int T = blockIdx.x;
   float m = 0.f;
-  if (small) {
+  {
     const bool fwd_jk = T <= pl.si + pl.H;                      // X0 / XC: [64 (j) x KZ]
     const bool is_xl = !fwd_jk && T < pl.si + 1 + pl.H + pl.NLC;  // XL: [LPC * KZ x 64]; else BCt / B0t: [KZ x 64]
     const int rows = fwd_jk ? 64 : (is_xl ? pl.LPC * pl.KZ : pl.KZ), cols = fwd_jk ? pl.KZ : 64;
     for (int e = threadIdx.x; e < rows * cols; e += 256) m = fmaxf(m, fabsf(tcx_value(pl, w_h, b_h, T, e / cols, e % cols)));
-  } else if (kk <= pl.K)
-    for (int e = threadIdx.x; e < n * n; e += 256) m = fmaxf(m, fabsf(src_at(pl, w_h, b_h, 0, kk, plan_w_off(pl, h + 1) + e)));
+  }
   __shared__ float red[256];
   red[threadIdx.x] = m;
   __syncthreads();
@@ -277,8 +378,7 @@ __global__ void __launch_bounds__(256) nif_pack_scales_kernel(const Plan pl, con
       ex = max(-100, min(100, ex));
       inv = __uint_as_float((uint32_t)(127 + ex - 13) << 23);    // 2^(ex-13): scaled max lands in [2^13, 2^14)
     }
-    if (small) packed[pl.off_TCS2 + T] = inv;
-    else packed[pl.off_TCS + h * pl.KP + kk] = inv;
+    packed[pl.off_TCS2 + T] = inv;
   }
 }
 
@@ -289,13 +389,24 @@ int nif_pack_impl(const Plan& pl, long long G, const float* w_h, const float* b_
     if (rc) return rc;
   }
   if (pl.tc) {
-    { NIF_PROF("nif_pack_scales_kernel", st); nif_pack_scales_kernel<<<(unsigned)(pl.H * pl.KP + plan_n_small(pl)), 256, 0, st>>>(pl, w_h, b_h, packed); }
+    { NIF_PROF("nif_pack_scales_kernel", st); nif_pack_scales_kernel<<<(unsigned)plan_n_small(pl), 256, 0, st>>>(pl, w_h, b_h, packed); }
     NIF_CUDA_CHECK(cudaGetLastError());
   }
-  const long long total = G * pl.packed_floats;
+  const int HT = pl.H + pl.wide_last;
+  if (HT > 0) {
+    const size_t smem = (size_t)pl.NP * (pl.NP + 1) * sizeof(float);
+    NIF_CUDA_CHECK(cudaFuncSetAttribute(nif_pack_mats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long nb = G * HT * (pl.tc ? pl.KP : pl.K + 1);
+    { NIF_PROF("nif_pack_mats_kernel", st); nif_pack_mats_kernel<<<(unsigned)nb, 256, smem, st>>>(pl, w_h, b_h, packed); }
+    NIF_CUDA_CHECK(cudaGetLastError());
+  }
+  const long long end1 = pl.tc ? pl.off_TCF : (pl.bf ? pl.off_WF : pl.packed_floats);
+  const long long end2 = pl.tc ? pl.off_TCS2 : 0;
+  const long long total = G * ((end1 - pl.off_M0) + (end2 > 0 ? end2 - pl.off_TCX : 0));
   long long nblk = (total + 255) / 256;
   if (nblk > 148 * 16) nblk = 148 * 16;
-  { NIF_PROF("nif_pack_kernel", st); nif_pack_kernel<<<(unsigned)nblk, 256, 0, st>>>(pl, G, w_h, b_h, packed); }
+  if (nblk < 1) nblk = 1;
+  { NIF_PROF("nif_pack_kernel", st); nif_pack_kernel<<<(unsigned)nblk, 256, 0, st>>>(pl, G, w_h, b_h, packed, end1, end2); }
   NIF_CUDA_CHECK(cudaGetLastError());
   return NIF_OK;
 }
