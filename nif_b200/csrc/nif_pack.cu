@@ -417,11 +417,14 @@ __global__ void __launch_bounds__(256) nif_unpack_grad_kernel(const Plan pl, int
                                                               float* __restrict__ dw_h, float* __restrict__ db_h,
                                                               float beta) {
   const int K1 = pl.K + 1, NP = pl.NP, n = pl.n, H = pl.H, P = pl.P;
-  const long long total = (long long)K1 * P;
+  // (the hidden matrices, columns [w_hid0, w_last0), are summed by nif_unpack_mats_kernel: this kernel visits the rest)
+  const int hid = H * n * n, PT = P - hid;
+  const long long total = (long long)K1 * PT;
   for (long long e = blockIdx.x * 256LL + threadIdx.x; e < total; e += 256LL * gridDim.x) {
-    const int kk = (int)(e / P);
-    const int col = (int)(e - (long long)kk * P);
-    const int w_hid0 = pl.si * n, w_last0 = w_hid0 + H * n * n, b0 = w_last0 + n * pl.so;
+    const int kk = (int)(e / PT);
+    const int tcol = (int)(e - (long long)kk * PT);
+    const int w_hid0 = pl.si * n, w_last0 = w_hid0 + hid, b0 = w_last0 + n * pl.so;
+    const int col = tcol < w_hid0 ? tcol : tcol + hid;
     float v = 0.f;
     if (col >= w_hid0 && col < w_last0) {
       const int r = col - w_hid0;
@@ -461,9 +464,56 @@ __global__ void __launch_bounds__(256) nif_unpack_grad_kernel(const Plan pl, int
   }
 }
 
+// hidden matrices: one block per (matrix h, kappa): sum the batch-split partials of the NP x NP tile (coalesced), write the
+// n x n block of the reference layout (contiguous in dw_h / db_h)
+__global__ void __launch_bounds__(256) nif_unpack_mats_kernel(const Plan pl, int S_h, const float* __restrict__ part_h,
+                                                              float* __restrict__ dw_h, float* __restrict__ db_h, float beta) {
+  const int K1 = pl.K + 1, NP = pl.NP, n = pl.n, P = pl.P;
+  const int RB = (n + 15) / 16;  // blocks of 16 rows per matrix (enough blocks in flight to hide the partial-sum latency)
+  int bid = blockIdx.x;
+  const int rb = bid % RB; bid /= RB;
+  const int kk = bid % K1, h = bid / K1;
+  const int i0 = rb * 16, i1 = min(n, i0 + 16);
+  const long long stride = (long long)(pl.H + pl.wide_last) * K1 * NP * NP;
+  const float* src = part_h + ((long long)h * K1 + kk) * NP * NP;
+  float* dst = ((kk < pl.K) ? dw_h + (long long)kk * P : db_h) + pl.si * n + h * n * n;
+  if ((n & 3) == 0) {  // rows of both layouts are 16-byte aligned (P's sections are multiples of n)
+    const int n4 = n / 4;
+    for (int e = i0 * n4 + threadIdx.x; e < i1 * n4; e += 256) {
+      const int i = e / n4, j4 = (e - i * n4) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int s = 0; s < S_h; ++s) {
+        const float4 p = __ldg(reinterpret_cast<const float4*>(src + s * stride + i * NP + j4));
+        v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
+      }
+      float* d = dst + i * n + j4;
+      if (((reinterpret_cast<uintptr_t>(d)) & 15) == 0) {
+        float4* d4 = reinterpret_cast<float4*>(d);
+        if (beta != 0.f) { const float4 o = *d4; v.x += beta * o.x; v.y += beta * o.y; v.z += beta * o.z; v.w += beta * o.w; }
+        *d4 = v;
+      } else {
+        const float vv[4] = {v.x, v.y, v.z, v.w};
+        for (int q = 0; q < 4; ++q) d[q] = (beta != 0.f) ? (d[q] * beta + vv[q]) : vv[q];
+      }
+    }
+  } else {
+    for (int e = i0 * n + threadIdx.x; e < i1 * n; e += 256) {
+      const int i = e / n, j = e - i * n;
+      float v = 0.f;
+      for (int s = 0; s < S_h; ++s) v += src[s * stride + i * NP + j];
+      float* d = dst + e;
+      *d = (beta != 0.f) ? (*d * beta + v) : v;
+    }
+  }
+}
+
 int nif_unpack_grad_impl(const Plan& pl, int S_h, const float* part_h, int S_e, const float* part_e, int Q,
                          float* dw_h, float* db_h, float beta, cudaStream_t st) {
-  const long long total = (long long)(pl.K + 1) * pl.P;
+  if (pl.H > 0) {
+    { NIF_PROF("nif_unpack_mats_kernel", st); nif_unpack_mats_kernel<<<(unsigned)(pl.H * (pl.K + 1) * ((pl.n + 15) / 16)), 256, 0, st>>>(pl, S_h, part_h, dw_h, db_h, beta); }
+    NIF_CUDA_CHECK(cudaGetLastError());
+  }
+  const long long total = (long long)(pl.K + 1) * (pl.P - (long long)pl.H * pl.n * pl.n);
   long long nblk = (total + 255) / 256;
   if (nblk > 148 * 16) nblk = 148 * 16;
   { NIF_PROF("nif_unpack_grad_kernel", st); nif_unpack_grad_kernel<<<(unsigned)nblk, 256, 0, st>>>(pl, S_h, part_h, S_e, part_e, Q, dw_h, db_h, beta); }
