@@ -30,5 +30,7 @@ cols = [('gpu__time_duration.sum', 'us'), ('launch__registers_per_thread', 'regs
         ('lts__t_bytes.sum', 'l2')]
 print(' '.join(f"{n:>8s}" for _, n in cols), 'kernel   [units: rd/wr %s, l2 %s]' % (
     units[idx['dram__bytes_read.sum']], units[idx.get('lts__t_bytes.sum', 0)]))
+tscale = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6, "nsecond": 1e-3, "usecond": 1.0, "msecond": 1e3, "second": 1e6}.get(units[idx['gpu__time_duration.sum']], 1.0)
 for row in rows:
-    print(' '.join(f"{f(row, c):8.1f}" for c, _ in cols), row[idx['Kernel Name']][:44])
+    vals = [f(row, c) * (tscale if c == 'gpu__time_duration.sum' else 1.0) for c, _ in cols]
+    print(' '.join(f"{v:8.1f}" for v in vals), row[idx['Kernel Name']][:44])
