@@ -126,10 +126,11 @@ int nif_forward_tangent_save(const nif_desc_t* d, int64_t B, const float* z, con
                              const float* packed, int32_t n_dir, const float* zdot, const float* xdot,
                              float* u, float* udot, float* save, void* stream);
 /* du [B,so] = dL/du, dudot [n_dir,B,so] = dL/d(udot), xdot [n_dir,B,si], zdot [n_dir,B,K] or NULL (no direction moves the
- * latent code).  dw_h / db_h written (beta == 0) or accumulated (beta == 1), dz [B,K] written, dzdot [n_dir,B,K] written
+ * latent code); zdot_dirs: bit d set = direction d moves the latent code (the others skip that part of the pass and get
+ * dzdot = 0).  dw_h / db_h written (beta == 0) or accumulated (beta == 1), dz [B,K] written, dzdot [n_dir,B,K] written
  * when zdot is given.  nif_sobolev_backward: one ShapeNet-input direction. */
 int nif_sobolev_backward_dirs(const nif_desc_t* d, int64_t B, const float* z, const float* x, int32_t n_dir,
-                              const float* zdot, const float* xdot, const float* packed, const float* save,
+                              const float* zdot, uint32_t zdot_dirs, const float* xdot, const float* packed, const float* save,
                               const float* du, const float* dudot, float* dw_h, float* db_h, float beta, float* dz,
                               float* dzdot, float* ws, void* stream);
 int nif_sobolev_backward(const nif_desc_t* d, int64_t B, const float* z, const float* x, const float* xdot,

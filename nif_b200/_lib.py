@@ -97,7 +97,7 @@ def lib() -> C.CDLL:
     L.nif_forward_tangent_save.argtypes = [DP, I64, VP, VP, VP, I32, VP, VP, VP, VP, VP, VP]
     L.nif_sobolev_backward.argtypes = [DP, I64, VP, VP, VP, VP, VP, VP, VP, VP, VP, F, VP, VP, VP]
     L.nif_sobolev_query_dirs.argtypes = [DP, I64, I32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
-    L.nif_sobolev_backward_dirs.argtypes = [DP, I64, VP, VP, I32, VP, VP, VP, VP, VP, VP, VP, VP, F, VP, VP, VP, VP]
+    L.nif_sobolev_backward_dirs.argtypes = [DP, I64, VP, VP, I32, VP, C.c_uint32, VP, VP, VP, VP, VP, VP, VP, F, VP, VP, VP, VP]
     TP, I64P = C.POINTER(TrunkDesc), C.POINTER(C.c_int64)
     L.nif_trunk_query.argtypes = [TP, I64, I64P, I64P, I64P, I64P]
     L.nif_trunk_kernel_path.argtypes = [TP]

@@ -9,7 +9,7 @@ int nif_forward_impl(const Plan& pl, long long G, long long B, const float* z, c
 int nif_tangent_impl(const Plan& pl, long long B, const float* z, const float* x, const float* packed, int n_dir,
                      const float* zdot, const float* xdot, float* u, float* udot, float* save, cudaStream_t st);
 int nif_sobolev_backward_impl(const Plan& pl, long long B, const float* z, const float* x, int n_dir, const float* zdot,
-                              const float* xdot, const float* packed, const float* save, const float* du,
+                              unsigned zdot_dirs, const float* xdot, const float* packed, const float* save, const float* du,
                               const float* dud, float* dw_h, float* db_h, float beta, float* dz, float* dzdot, float* ws,
                               cudaStream_t st);
 int nif_given_w_impl(const Plan& pl, long long B, const float* x, const float* w, float* u, cudaStream_t st);
@@ -160,7 +160,7 @@ extern "C" int nif_forward_tangent_save(const nif_desc_t* d, int64_t B, const fl
 }
 
 extern "C" int nif_sobolev_backward_dirs(const nif_desc_t* d, int64_t B, const float* z, const float* x, int32_t n_dir,
-                                         const float* zdot, const float* xdot, const float* packed, const float* save,
+                                         const float* zdot, uint32_t zdot_dirs, const float* xdot, const float* packed, const float* save,
                                          const float* du, const float* dudot, float* dw_h, float* db_h, float beta,
                                          float* dz, float* dzdot, float* ws, void* stream) {
   Plan pl;
@@ -181,14 +181,14 @@ extern "C" int nif_sobolev_backward_dirs(const nif_desc_t* d, int64_t B, const f
   NIF_OPTIONAL_PTR(zdot);
   if (pl.K == 0) zdot = nullptr;
   if (zdot) NIF_REQUIRE_PTR(dzdot);
-  return nif_sobolev_backward_impl(pl, B, z, x, n_dir, zdot, xdot, packed, save, du, dudot, dw_h, db_h, beta, dz, dzdot,
-                                   ws, static_cast<cudaStream_t>(stream));
+  return nif_sobolev_backward_impl(pl, B, z, x, n_dir, zdot, zdot_dirs, xdot, packed, save, du, dudot, dw_h, db_h, beta, dz,
+                                   dzdot, ws, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int nif_sobolev_backward(const nif_desc_t* d, int64_t B, const float* z, const float* x, const float* xdot,
                                     const float* packed, const float* save, const float* du, const float* dudot,
                                     float* dw_h, float* db_h, float beta, float* dz, float* ws, void* stream) {
-  return nif_sobolev_backward_dirs(d, B, z, x, 1, nullptr, xdot, packed, save, du, dudot, dw_h, db_h, beta, dz, nullptr, ws,
+  return nif_sobolev_backward_dirs(d, B, z, x, 1, nullptr, 0u, xdot, packed, save, du, dudot, dw_h, db_h, beta, dz, nullptr, ws,
                                    stream);
 }
 

@@ -1092,7 +1092,7 @@ int nif_backward_impl(const Plan& pl, long long B, const float* z, const float* 
 // ws: nif_grad_ws_layout(pl, B).total + (H+1) * B * NP floats.
 // ---------------------------------------------------------------------------------------------------
 int nif_sobolev_backward_impl(const Plan& pl, long long B, const float* z, const float* x, int n_dir, const float* zdot,
-                              const float* xdot, const float* packed, const float* save, const float* du,
+                              unsigned zdot_dirs, const float* xdot, const float* packed, const float* save, const float* du,
                               const float* dud, float* dw_h, float* db_h, float beta, float* dz, float* dzdot, float* ws,
                               cudaStream_t st) {
   // n_dir directions (xdot [n_dir][B][si], zdot [n_dir][B][K] or null = the latent code does not move, dud
@@ -1105,7 +1105,13 @@ int nif_sobolev_backward_impl(const Plan& pl, long long B, const float* z, const
   const long long slot = B * (long long)pl.NP;
   float* X = ws + w.total;
   float* S = X + (pl.H + 1) * slot;
-  if (zdot) NIF_CUDA_CHECK(cudaMemsetAsync(S, 0, sizeof(float) * (pl.H + 1) * slot, st));
+  // zdot_dirs: bit d set = direction d moves the latent code (its zdot rows are not identically zero); the others skip the
+  // local pass and get dzdot = 0
+  if (zdot) {
+    NIF_CUDA_CHECK(cudaMemsetAsync(S, 0, sizeof(float) * (pl.H + 1) * slot, st));
+    for (int d = 0; d < n_dir; ++d)
+      if (!((zdot_dirs >> d) & 1u)) NIF_CUDA_CHECK(cudaMemsetAsync(dzdot + (long long)d * B * pl.K, 0, sizeof(float) * B * pl.K, st));
+  }
   auto run = [&](BwdArgs& a) -> int {
     switch (pl.NP) {
       case 32: a.total_tiles = (B + Cfg32::TB - 1) / Cfg32::TB; return launch_bwd_data<Cfg32>(pl, a, st);
@@ -1137,7 +1143,7 @@ int nif_sobolev_backward_impl(const Plan& pl, long long B, const float* z, const
     if (rc != NIF_OK) return rc;
     rc = nif_weight_grads_impl(pl, B, z, a.x, a.h_stash, a.du, dw_h, db_h, d == 0 ? beta : 1.0f, ws, st, a.no_bias);
     if (rc != NIF_OK) return rc;
-    if (!primal && zdot) {  // local pass: ws.da still holds da'_m of this direction
+    if (!primal && zdot && ((zdot_dirs >> d) & 1u)) {  // local pass: ws.da still holds da'_m of this direction
       const float* zd = zdot + (long long)d * B * pl.K;
       BwdArgs l = a;
       l.z = zd; l.zt_last = 0.f; l.x = x; l.h_stash = save; l.e_stash = nullptr; l.ext_out = nullptr; l.ext_add = nullptr;

@@ -1003,7 +1003,7 @@ class Model:
                 sq_g = sq_g + (eg * eg).sum()
             lv = ((ev * ev).sum() / len(vc) + loss.coef_grad * sq_g / len(gc)) / gb
         out = eng.sobolev_backward(zc, xs, xdot, packed, stash, du, dud, n._gviews[n._last_names[0]],
-                                   n._gviews[n._last_names[1]], 0.0, zdot=zdot)
+                                   n._gviews[n._last_names[1]], 0.0, zdot=zdot, zdot_dirs=[d for d, _ in zds])
         if fused_trunk:
             n._trunk.backward(p_in, n.theta_trunk, tstash, out, n.grad_trunk, 0.0)
         elif zdot is None:

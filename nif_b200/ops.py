@@ -180,11 +180,13 @@ class FusedShapeNet:
               "nif_forward_tangent2")
         return u, udot, uddot
 
-    def sobolev_backward(self, z, x, xdot, packed, stash, du, dudot, dw_h, db_h, beta: float = 0.0, zdot=None):
+    def sobolev_backward(self, z, x, xdot, packed, stash, du, dudot, dw_h, db_h, beta: float = 0.0, zdot=None,
+                         zdot_dirs=None):
         """Reverse-over-forward pass over the directions of the forward_tangent(save=True) call: seeds du = dL/du [B,so]
         and dudot = dL/d(udot) [n_dir,B,so]; xdot [n_dir,B,si] and zdot [n_dir,B,K] (None: no direction moves the latent
         code) are the directions of that call ([B,*] is read as one direction).  Fills dw_h / db_h; returns dz, or
-        (dz, dzdot [n_dir,B,K]) when zdot is given."""
+        (dz, dzdot [n_dir,B,K]) when zdot is given.  zdot_dirs: indices of the directions whose zdot is not identically zero
+        (default: all of them)"""
         x, xdot = _f32c(x, "x"), _f32c(xdot, "xdot")
         B = x.shape[0]
         du, dudot = _f32c(du, "du"), _f32c(dudot, "dudot")
@@ -213,7 +215,11 @@ class FusedShapeNet:
         check(_lib.lib().nif_sobolev_query_dirs(C.byref(self.desc), B, n_dir, None, C.byref(wsn)), "nif_sobolev_query_dirs")
         if self._ws is None or self._ws.numel() < wsn.value or self._ws.device != x.device:
             self._ws = torch.empty(int(wsn.value), dtype=torch.float32, device=x.device)
-        check(_lib.lib().nif_sobolev_backward_dirs(C.byref(self.desc), B, _ptr(z), _ptr(x), n_dir, _ptr(zdot), _ptr(xdot),
+        mask = 0
+        if zdot is not None:
+            for d in (range(n_dir) if zdot_dirs is None else zdot_dirs):
+                mask |= 1 << int(d)
+        check(_lib.lib().nif_sobolev_backward_dirs(C.byref(self.desc), B, _ptr(z), _ptr(x), n_dir, _ptr(zdot), mask, _ptr(xdot),
                                                    _ptr(packed), _ptr(stash), _ptr(du), _ptr(dudot), _ptr(dw_h), _ptr(db_h),
                                                    float(beta), _ptr(dz), _ptr(dzdot), _ptr(self._ws), _stream()),
               "nif_sobolev_backward_dirs")

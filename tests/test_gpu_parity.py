@@ -401,9 +401,10 @@ def test_sobolev_with_parameter_net_directions(variant, si, so, n, l, K, B, pair
         dud[cols.index(c)][:, a] += (2.0 * coef / (B * len(pairs))) * (got_dy[:, i] - tgt_g[:, i].float().to(dev))
     dw = torch.full_like(w_h, float("nan"))
     db = torch.full_like(b_h, float("nan"))
-    dz, dzdot = eng.sobolev_backward(z, x, xdot, packed, stash, du, dud, dw, db, 0.0, zdot=zdot)
-    torch.cuda.synchronize()
     tdir = [d for d, c in enumerate(cols) if c < spec.pi]
+    dz, dzdot = eng.sobolev_backward(z, x, xdot, packed, stash, du, dud, dw, db, 0.0, zdot=zdot, zdot_dirs=tdir)
+    torch.cuda.synchronize()
+    assert all(float(dzdot[d].abs().max()) == 0.0 for d in range(D) if d not in tdir)  # skipped directions: zero
     torch.autograd.backward([z64, zd64], [dz.cpu().double(), sum(dzdot[d] for d in tdir).cpu().double()])
     for name in prm:
         got = dw.cpu() if name == wn else db.cpu() if name == bn else leaves[name].grad
