@@ -504,8 +504,15 @@ class Model:
     def train_on_batch(self, x, y, sample_weight=None, global_batch: Optional[int] = None) -> float:
         """One optimisation step (what Keras' train_step + apply_gradients do).  Returns the loss of this
         process's rows already divided by the global batch (sum over ranks = global loss)."""
-        loss = self._train_step(self._dev(x), self._dev(y), None if sample_weight is None else self._dev(sample_weight),
-                                global_batch)
+        if (self.kind == "full" and self.optimizer is not None and self._fusable() and self._graph_enabled()
+                and all(isinstance(t, torch.Tensor) and t.dtype == torch.float32 and t.device.type == "cpu" and t.is_contiguous()
+                        for t in (x, y) + (() if sample_weight is None else (sample_weight,)))):
+            # host batches of a graph-replayed step go straight into the graph's input buffers (one host-to-device copy
+            # each, no device temporary and device-to-device copy in between)
+            loss = self._train_step(x, y, sample_weight, global_batch)
+        else:
+            loss = self._train_step(self._dev(x), self._dev(y), None if sample_weight is None else self._dev(sample_weight),
+                                    global_batch)
         return float(loss)
 
     def _train_step(self, inp: torch.Tensor, tgt: torch.Tensor, sw: Optional[torch.Tensor],
@@ -517,6 +524,8 @@ class Model:
         gb = int(global_batch) if global_batch else B
         if self._loss_buf is None:
             self._loss_buf = torch.zeros(1, dtype=torch.float32, device=n.device)
+        if inp.device.type != "cuda" and not (self._fusable() and B > 0 and self._graph_enabled()):
+            inp, tgt, sw = self._dev(inp), self._dev(tgt), (None if sw is None else self._dev(sw))
         if self._fusable():
             if B > 0 and self._graph_enabled():
                 return self._train_step_graph(inp, tgt, sw, gb)
@@ -800,6 +809,8 @@ class Model:
         ent = self._graphs.get(key)
         if ent is not None and ent.get("sig") not in (None, self._graph_signature()):
             ent = None  # parameters / optimiser state were re-created: the recorded pointers are stale
+        if (ent is None or ent["sig"] is None) and inp.device.type != "cuda":  # eager visit / recording: device tensors
+            inp, tgt, sw = self._dev(inp), self._dev(tgt), (None if sw is None else self._dev(sw))
         if ent is None:
             # first visit of this shape: run it eagerly (this also sizes the persistent workspaces the graph will use)
             while len(self._graphs) >= self.GRAPH_CACHE:
