@@ -155,13 +155,15 @@ __global__ void __launch_bounds__(TCE_THREADS, 1) nif_tc_bwd_edge_kernel(const P
     const Blk d = describe(2 * blockIdx.x + q);
     float scA, invA;
     tc_row_scale(d.bound, scA, invA);
-    long long n_mine = 0;
-    for (long long t = sl; t < nsub; t += 2, ++n_mine) {
+    // Row data of the NEXT sub-tile of this slot is requested as soon as the registers of the current one are free (features
+    // after the A stores, latent coordinates after the B stores), so no L2 round trip sits between two sub-tiles: the loop
+    // used to pay four of them in series (features, then each group of latent coordinates) per sub-tile.
+    float4 fq[16];
+    float mulv = 0.f;
+    auto fetch_f = [&](long long t) {
       const long long b = r0 + t * 64 + r;
-      const bool live = b < r1 && d.on;
-      // this row's 64 features of block q (coalesced quads of the tiled source) and its latent coordinates
-      float4 fq[16];
-      float mulv = d.cst;
+      const bool live = t < nsub && b < r1 && d.on;
+      mulv = d.cst;
       if (live && d.mul) mulv *= __ldg(&d.mul[b * d.mul_stride]);
       if (d.src) {
 #pragma unroll
@@ -176,6 +178,38 @@ __global__ void __launch_bounds__(TCE_THREADS, 1) nif_tc_bwd_edge_kernel(const P
         fq[0] = make_float4(dv[0], dv[1], dv[2], dv[3]);
         fq[1] = make_float4(dv[4], dv[5], dv[6], dv[7]);
       }
+    };
+    // the zt operand: groups of 8 latent coordinates, even groups by q = 0, odd groups by q = 1 (KZ <= 64: at most 4 each)
+    float zv[4][8];
+    const bool zvec = (K & 3) == 0;  // rows of z are 16-byte aligned
+    auto fetch_z = [&](long long t) {
+      const long long b = r0 + t * 64 + r;
+      const bool rowlive = t < nsub && b < r1;
+      const float* zrow = a.z + (rowlive ? b : r0) * K;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int g = q + 2 * u;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) zv[u][e] = 0.f;
+        if (g < KZ / 8 && rowlive) {
+          if (zvec && 8 * g + 8 <= K) {
+            const float4 p0 = ldg4(zrow + 8 * g), p1 = ldg4(zrow + 8 * g + 4);
+            zv[u][0] = p0.x; zv[u][1] = p0.y; zv[u][2] = p0.z; zv[u][3] = p0.w;
+            zv[u][4] = p1.x; zv[u][5] = p1.y; zv[u][6] = p1.z; zv[u][7] = p1.w;
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int kk = 8 * g + e;
+              zv[u][e] = (kk < K) ? __ldg(zrow + kk) : (kk == K ? 1.f : 0.f);
+            }
+          }
+        }
+      }
+    };
+    fetch_f(sl);
+    fetch_z(sl);
+    long long n_mine = 0;
+    for (long long t = sl; t < nsub; t += 2, ++n_mine) {
       // wait until the MMAs that read this slot two sub-tiles ago have completed
       mbar_wait(&slot_empty[sl], (uint32_t)((n_mine & 1) ^ 1));
 #pragma unroll
@@ -188,22 +222,19 @@ __global__ void __launch_bounds__(TCE_THREADS, 1) nif_tc_bwd_edge_kernel(const P
         *reinterpret_cast<uint4*>(A_hi + off) = hi;
         *reinterpret_cast<uint4*>(A_lo + off) = lo;
       }
-      // the zt operand: groups of 8 latent coordinates, even groups by q = 0, odd groups by q = 1
-      const bool rowlive = b < r1;
-      for (int g = q; g < KZ / 8; g += 2) {
-        float zv[8];
+      fetch_f(t + 2);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int kk = 8 * g + e;
-          zv[e] = 0.f;
-          if (rowlive) zv[e] = (kk < K) ? __ldg(&a.z[b * K + kk]) : (kk == K ? 1.f : 0.f);
+      for (int u = 0; u < 4; ++u) {
+        const int g = q + 2 * u;
+        if (g < KZ / 8) {
+          uint4 hi, lo;
+          tce_split8(zv[u], scB, hi, lo);
+          const uint32_t off = (uint32_t)g * 1024u + koff;
+          *reinterpret_cast<uint4*>(B_hi + off) = hi;
+          *reinterpret_cast<uint4*>(B_lo + off) = lo;
         }
-        uint4 hi, lo;
-        tce_split8(zv, scB, hi, lo);
-        const uint32_t off = (uint32_t)g * 1024u + koff;
-        *reinterpret_cast<uint4*>(B_hi + off) = hi;
-        *reinterpret_cast<uint4*>(B_lo + off) = lo;
       }
+      fetch_z(t + 2);
       fence_async_smem();
       mbar_arrive(&slot_full[sl]);
     }
