@@ -259,3 +259,36 @@ def test_pointwise_data_matches_the_reference_file():
     obj.data = obj.data_raw
     assert np.array_equal(obj.data_raw, g["obj_raw"]) and np.array_equal(obj.parameter, g["obj_parameter"])
     assert np.array_equal(obj.x, g["obj_x"]) and np.array_equal(obj.u, g["obj_u"])
+
+
+def test_jacobian_model_loss_planning():
+    """compile() of a JacobianLayer model maps the loss onto tangent directions: one per differentiated input column, in the
+    order the grad columns name them; ParameterNet inputs move the latent code; 'mse' / a callable see every Jacobian entry;
+    more than four differentiated inputs, or columns outside the output, are rejected (host logic, no GPU)."""
+    cfg_s = {"use_resblock": False, "connectivity": "full", "input_dim": 2, "output_dim": 2, "units": 30, "nlayers": 2,
+             "weight_init_factor": 0.01, "omega_0": 30.0}
+    cfg_p = {"use_resblock": False, "input_dim": 1, "latent_dim": 2, "units": 30, "nlayers": 2, "activation": "swish"}
+    net = nif_b200.NIFMultiScale(cfg_s, cfg_p, seed=0, device="cpu")
+    # output columns: [u0, u1 | du0/dt, du0/dx, du0/dy, du1/dt, du1/dx, du1/dy]
+    model = nif_b200.JacobianLayer(net.build(), y_index=[0, 1], x_index=[0, 1, 2]).as_model()
+    model.compile(nif_b200.Adam(1e-3), loss=nif_b200.SobolevMSE(0.1, value_cols=[0, 1], grad_cols=[3, 7]))
+    plan = model._sobolev_plan
+    assert plan["dirs"] == [1, 2] and plan["pairs"] == [(0, 0), (1, 1)] and not plan["latent_moves"] and not plan["general"]
+    model.compile(nif_b200.Adam(1e-3), loss=nif_b200.SobolevMSE(0.1, value_cols=[0], grad_cols=[5, 2, 4]))
+    plan = model._sobolev_plan
+    # columns 5, 2, 4 = du1/dt, du0/dt, du0/dy: directions t (a ParameterNet input) and y
+    assert plan["dirs"] == [0, 2] and plan["pairs"] == [(0, 1), (0, 0), (1, 0)] and plan["latent_moves"]
+    for loss in ("mse", lambda yt, yp: ((yt - yp) ** 2).mean()):
+        model.compile(nif_b200.Adam(1e-3), loss=loss)
+        plan = model._sobolev_plan
+        assert plan["general"] and plan["dirs"] == [0, 1, 2] and plan["latent_moves"]
+        assert plan["pairs"] == [(0, 0), (1, 0), (2, 0), (0, 1), (1, 1), (2, 1)]
+    with pytest.raises(nif_b200._lib.NifError):
+        model.compile(nif_b200.Adam(1e-3), loss=nif_b200.SobolevMSE(0.1, value_cols=[0], grad_cols=[8]))
+    with pytest.raises(nif_b200._lib.NifError):
+        model.compile(nif_b200.Adam(1e-3), loss=nif_b200.SobolevMSE(0.1, value_cols=[2], grad_cols=[3]))
+    cfg_s5 = dict(cfg_s, input_dim=4)
+    net5 = nif_b200.NIFMultiScale(cfg_s5, cfg_p, seed=0, device="cpu")
+    wide = nif_b200.JacobianLayer(net5.build(), y_index=[0], x_index=[0, 1, 2, 3, 4]).as_model()
+    with pytest.raises(nif_b200._lib.NifError):
+        wide.compile(nif_b200.Adam(1e-3), loss="mse")  # five differentiated inputs
