@@ -84,6 +84,20 @@ def test_null_arguments_of_the_later_entry_points():
     assert L.nif_forward_tangent(C.byref(d), 8, None, None, None, 5, None, None, None, None, None) == -2  # n_dir > 4
     assert L.nif_sobolev_backward(C.byref(d), 8, None, None, None, None, None, None, None, None, None, 0.0, None, None,
                                   None) == -2
+    # the multi-direction Sobolev pair: direction count in [1, 4], sizes grow with the directions, empty batch is a no-op
+    assert L.nif_sobolev_backward_dirs(C.byref(d), 8, None, None, 0, None, 0, None, None, None, None, None, None, None, 0.0,
+                                       None, None, None, None) == -2
+    assert L.nif_sobolev_backward_dirs(C.byref(d), 8, None, None, 5, None, 0, None, None, None, None, None, None, None, 0.0,
+                                       None, None, None, None) == -2
+    assert L.nif_sobolev_backward_dirs(C.byref(d), 8, None, None, 2, None, 0, None, None, None, None, None, None, None, 0.0,
+                                       None, None, None, None) == -2  # null pointers
+    assert L.nif_sobolev_backward_dirs(C.byref(d), 0, None, None, 2, None, 0, None, None, None, None, None, None, None, 0.0,
+                                       None, None, None, None) == 0
+    s1, s3, w1, w3 = C.c_int64(0), C.c_int64(0), C.c_int64(0), C.c_int64(0)
+    assert L.nif_sobolev_query_dirs(C.byref(d), 1024, 1, C.byref(s1), C.byref(w1)) == 0
+    assert L.nif_sobolev_query_dirs(C.byref(d), 1024, 3, C.byref(s3), C.byref(w3)) == 0
+    assert L.nif_sobolev_query_dirs(C.byref(d), 1024, 9, C.byref(s3), C.byref(w3)) == -2
+    assert s1.value == 4 * 5 * 64 and s3.value == 8 * 5 * 64 and w3.value == w1.value  # (2 + 2 n_dir)(H + 1) NP per row
     t = _lib.TrunkDesc(1, 32, 64, 4, 2)
     assert L.nif_trunk_forward(C.byref(t), 8, None, None, None, None, None, None) == -2
     bad = _lib.TrunkDesc(1, 32, 65, 4, 2)  # wider than the fused trunk kernels
