@@ -155,6 +155,13 @@ int nif_mse_backward(const nif_desc_t* d, int64_t B, const float* z, const float
                      const float* target, const float* sample_weight, float inv_global_batch,
                      float* loss, float* dw_h, float* db_h, float beta, float* dz,
                      float* ws, void* stream);
+/* The same call, and dz_ready_event (a cudaEvent_t, may be NULL) is recorded on `stream` once the kernels that produce dz
+ * have been enqueued: the caller can start the ParameterNet trunk's reverse pass on another stream while the
+ * weight-gradient kernels of this call run. */
+int nif_mse_backward_ev(const nif_desc_t* d, int64_t B, const float* z, const float* x, const float* packed,
+                        const float* u, const float* save, const float* target, const float* sample_weight,
+                        float inv_global_batch, float* loss, float* dw_h, float* db_h, float beta, float* dz,
+                        float* ws, void* dz_ready_event, void* stream);
 
 /* Same reverse pass with a caller-supplied seed du [B,so] (for custom losses). */
 int nif_backward(const nif_desc_t* d, int64_t B, const float* z, const float* x,

@@ -16,7 +16,7 @@ CSRC = os.path.join(_HERE, "csrc")
 # every symbol include/nif_b200.h declares
 SYMBOLS = (
     "nif_last_error", "nif_version", "nif_query_sizes", "nif_pack", "nif_forward", "nif_forward_tangent", "nif_forward_tangent2",
-    "nif_forward_given_w", "nif_mse_backward", "nif_backward", "nif_adam_step", "nif_adam_step_dev", "nif_measure_fp32_peak",
+    "nif_forward_given_w", "nif_mse_backward", "nif_mse_backward_ev", "nif_backward", "nif_adam_step", "nif_adam_step_dev", "nif_measure_fp32_peak",
     "nif_trunk_query", "nif_trunk_forward", "nif_trunk_backward", "nif_trunk_kernel_path",
     "nif_sobolev_query", "nif_sobolev_query_dirs", "nif_forward_tangent_save", "nif_sobolev_backward", "nif_sobolev_backward_dirs",
     "nif_crc32c",
@@ -89,6 +89,7 @@ def lib() -> C.CDLL:
     L.nif_forward_tangent2.argtypes = [DP, I64, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP]
     L.nif_forward_given_w.argtypes = [DP, I64, VP, VP, VP, VP]
     L.nif_mse_backward.argtypes = [DP, I64, VP, VP, VP, VP, VP, VP, VP, F, VP, VP, VP, F, VP, VP, VP]
+    L.nif_mse_backward_ev.argtypes = [DP, I64, VP, VP, VP, VP, VP, VP, VP, F, VP, VP, VP, F, VP, VP, VP, VP]
     L.nif_backward.argtypes = [DP, I64, VP, VP, VP, VP, VP, VP, VP, F, VP, VP, VP]
     L.nif_adam_step.argtypes = [I64, VP, VP, VP, VP, C.c_double, C.c_double, C.c_double, C.c_double, I64, F, F, F, VP]
     L.nif_adam_step_dev.argtypes = [I64, VP, VP, VP, VP, VP, C.c_double, C.c_double, C.c_double, F, F, F, VP]

@@ -15,10 +15,11 @@ int nif_sobolev_backward_impl(const Plan& pl, long long B, const float* z, const
 int nif_given_w_impl(const Plan& pl, long long B, const float* x, const float* w, float* u, cudaStream_t st);
 int nif_backward_impl(const Plan& pl, long long B, const float* z, const float* x, const float* packed,
                       const float* save, const float* du, float* dw_h, float* db_h, float beta, float* dz,
-                      float* ws, cudaStream_t st);
+                      float* ws, cudaStream_t st, cudaEvent_t dz_ev);
 int nif_mse_backward_impl(const Plan& pl, long long B, const float* z, const float* x, const float* packed,
                           const float* u, const float* save, const float* target, const float* sw, float inv_gb,
-                          float* loss, float* dw_h, float* db_h, float beta, float* dz, float* ws, cudaStream_t st);
+                          float* loss, float* dw_h, float* db_h, float beta, float* dz, float* ws, cudaStream_t st,
+                          cudaEvent_t dz_ev);
 int nif_adam_impl(long long n, float* p, const float* g, float* m, float* v, double lr, double b1, double b2,
                   double eps, long long t, float l1, float l2, float gs, cudaStream_t st);
 GradWs nif_grad_ws_layout(const Plan& pl, long long B);
@@ -205,10 +206,10 @@ extern "C" int nif_forward_given_w(const nif_desc_t* d, int64_t B, const float* 
   return nif_given_w_impl(pl, B, x, w, u, static_cast<cudaStream_t>(stream));
 }
 
-extern "C" int nif_mse_backward(const nif_desc_t* d, int64_t B, const float* z, const float* x, const float* packed,
-                                const float* u, const float* save, const float* target, const float* sample_weight,
-                                float inv_global_batch, float* loss, float* dw_h, float* db_h, float beta,
-                                float* dz, float* ws, void* stream) {
+extern "C" int nif_mse_backward_ev(const nif_desc_t* d, int64_t B, const float* z, const float* x, const float* packed,
+                                   const float* u, const float* save, const float* target, const float* sample_weight,
+                                   float inv_global_batch, float* loss, float* dw_h, float* db_h, float beta,
+                                   float* dz, float* ws, void* dz_ready_event, void* stream) {
   Plan pl;
   int rc = nif_make_plan(d, &pl);
   if (rc) return rc;
@@ -220,7 +221,15 @@ extern "C" int nif_mse_backward(const nif_desc_t* d, int64_t B, const float* z, 
   if (!loss) { nif_set_error("nif_mse_backward: loss is null"); return NIF_E_BAD_ARG; }
   NIF_REQUIRE_PTR(db_h); NIF_REQUIRE_PTR(ws);
   return nif_mse_backward_impl(pl, B, z, x, packed, u, save, target, sample_weight, inv_global_batch, loss, dw_h,
-                               db_h, beta, dz, ws, static_cast<cudaStream_t>(stream));
+                               db_h, beta, dz, ws, static_cast<cudaStream_t>(stream), static_cast<cudaEvent_t>(dz_ready_event));
+}
+
+extern "C" int nif_mse_backward(const nif_desc_t* d, int64_t B, const float* z, const float* x, const float* packed,
+                                const float* u, const float* save, const float* target, const float* sample_weight,
+                                float inv_global_batch, float* loss, float* dw_h, float* db_h, float beta,
+                                float* dz, float* ws, void* stream) {
+  return nif_mse_backward_ev(d, B, z, x, packed, u, save, target, sample_weight, inv_global_batch, loss, dw_h, db_h, beta, dz,
+                             ws, nullptr, stream);
 }
 
 extern "C" int nif_backward(const nif_desc_t* d, int64_t B, const float* z, const float* x, const float* packed,
@@ -235,7 +244,7 @@ extern "C" int nif_backward(const nif_desc_t* d, int64_t B, const float* z, cons
   NIF_REQUIRE_PTR(x); NIF_REQUIRE_PTR(packed); NIF_REQUIRE_PTR(save); NIF_REQUIRE_PTR(du);
   NIF_REQUIRE_PTR(db_h); NIF_REQUIRE_PTR(ws);
   return nif_backward_impl(pl, B, z, x, packed, save, du, dw_h, db_h, beta, dz, ws,
-                           static_cast<cudaStream_t>(stream));
+                           static_cast<cudaStream_t>(stream), nullptr);
 }
 
 extern "C" int nif_adam_step(int64_t n, float* p, const float* g, float* m, float* v, double lr, double b1,

@@ -994,9 +994,11 @@ int nif_weight_grads_impl(const Plan& pl, long long B, const float* z, const flo
   return nif_unpack_grad_impl(pl, w.S_h, ws + w.part_h, w.S_e, ws + w.part_e, w.Q, dw_h, db_h, beta, st);
 }
 
+// dz_ev (optional): recorded on `st` as soon as the data pass has been enqueued, i.e. when dz is final: the caller may start
+// the ParameterNet trunk's reverse pass on another stream while the weight-gradient kernels of this call run
 int nif_backward_impl(const Plan& pl, long long B, const float* z, const float* x, const float* packed,
                       const float* save, const float* du, float* dw_h, float* db_h, float beta, float* dz,
-                      float* ws, cudaStream_t st) {
+                      float* ws, cudaStream_t st, cudaEvent_t dz_ev) {
   const GradWs w = nif_grad_ws_layout(pl, B);
   if (B <= 0) return NIF_OK;
   BwdArgs a;
@@ -1009,6 +1011,7 @@ int nif_backward_impl(const Plan& pl, long long B, const float* z, const float* 
   if (pl.bf) {  // bf16 tensor-core reverse pass: data kernel, weight-gradient GEMM, thin terms on the CUDA cores
     int rcb = nif_bf_bwd_data_impl(pl, B, z, x, packed, save, du, ws + w.da, dz, st);
     if (rcb == NIF_OK) {
+      if (dz_ev) { NIF_CUDA_CHECK(cudaEventRecord(dz_ev, st)); dz_ev = nullptr; }
       rcb = nif_bf_bwd_weight_impl(pl, B, z, save, ws + w.da, w.S_h, w.rows_h, ws + w.part_h, st);
       if (rcb != NIF_OK) return rcb;
       int S_e_used = w.S_e;
@@ -1044,6 +1047,7 @@ int nif_backward_impl(const Plan& pl, long long B, const float* z, const float* 
     default: nif_set_error("unsupported padded width %d", pl.NP); return NIF_E_UNSUPPORTED;
   }
   if (rc != NIF_OK) return rc;
+  if (dz_ev) NIF_CUDA_CHECK(cudaEventRecord(dz_ev, st));
 
   bool wgt_done = false;
   int S_used = w.S_h, S_e_used = w.S_e;
@@ -1161,7 +1165,7 @@ int nif_sobolev_backward_impl(const Plan& pl, long long B, const float* z, const
 int nif_mse_backward_impl(const Plan& pl, long long B, const float* z, const float* x, const float* packed,
                           const float* u, const float* save, const float* target, const float* sw, float inv_gb,
                           float* loss, float* dw_h, float* db_h, float beta, float* dz, float* ws,
-                          cudaStream_t st) {
+                          cudaStream_t st, cudaEvent_t dz_ev) {
   const GradWs w = nif_grad_ws_layout(pl, B);
   if (B <= 0) return NIF_OK;
   int nblk = (int)((B + 255) / 256);
@@ -1170,5 +1174,5 @@ int nif_mse_backward_impl(const Plan& pl, long long B, const float* z, const flo
   NIF_CUDA_CHECK(cudaGetLastError());
   { NIF_PROF("nif_loss_final_kernel", st); nif_loss_final_kernel<<<1, 32, 0, st>>>(nblk, ws + w.loss_part, loss); }
   NIF_CUDA_CHECK(cudaGetLastError());
-  return nif_backward_impl(pl, B, z, x, packed, save, ws + w.du, dw_h, db_h, beta, dz, ws, st);
+  return nif_backward_impl(pl, B, z, x, packed, save, ws + w.du, dw_h, db_h, beta, dz, ws, st, dz_ev);
 }

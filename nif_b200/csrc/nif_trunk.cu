@@ -16,7 +16,7 @@ int nif_forward_impl(const Plan& pl, long long G, long long B, const float* z, c
                      const float* packed, float* u, float* save, cudaStream_t st);
 int nif_backward_impl(const Plan& pl, long long B, const float* z, const float* x, const float* packed,
                       const float* save, const float* du, float* dw_h, float* db_h, float beta, float* dz,
-                      float* ws, cudaStream_t st);
+                      float* ws, cudaStream_t st, cudaEvent_t dz_ev);
 
 int nif_make_trunk_plan(int pi, int K, int n_st, int l_st, int act, Plan* out) {
   if (pi < 1 || pi > NIF_MAX_SI || K < 1 || K > 64 || n_st < 1 || n_st > 64 || l_st < 0 || l_st > 64 ||
@@ -54,5 +54,5 @@ int nif_trunk_backward_impl(const Plan& pl, long long B, const float* p_in, cons
                             cudaStream_t st) {
   if (B <= 0) return NIF_OK;
   (void)theta;  // `packed` was built from it by the forward call of this step
-  return nif_backward_impl(pl, B, nullptr, p_in, packed, save, dz, nullptr, g_theta, beta, nullptr, ws, st);
+  return nif_backward_impl(pl, B, nullptr, p_in, packed, save, dz, nullptr, g_theta, beta, nullptr, ws, st, nullptr);
 }

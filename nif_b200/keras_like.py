@@ -662,9 +662,30 @@ class Model:
         z, tstash = n._trunk.forward(p_in, n.theta_trunk, save=True)
         cur.wait_stream(self._side)
         u, stash = eng.forward(z, xs, packed, save=True)
-        dz = eng.mse_backward(z, xs, packed, u, stash, tgt, sw, 1.0 / gb, self._loss_buf,
-                              n._gviews[n._last_names[0]], n._gviews[n._last_names[1]], 0.0)
         act = self._activity_terms(z, B, gb)
+        # The trunk's reverse pass needs dz only, which the first kernel of the head's reverse pass produces: it starts on the
+        # second stream as soon as dz is final and runs next to the weight-gradient kernels (they leave SMs idle: 135 CTAs
+        # on 148 SMs at C2).  Not when dz is modified afterwards (activity regularisers) or when the two kernel sequences
+        # are recorded as separate graphs around an NCCL all-reduce.
+        overlap = (act is None and (self.dist is None or self._symm_ready())
+                   and os.environ.get("NIF_B200_OVERLAP_TRUNK", "1") != "0")
+        ev = None
+        if overlap:
+            ev = getattr(self, "_dz_event", None)
+            if ev is None:
+                with torch.cuda.stream(self._side):  # (created by its first record, outside any capture of the main stream)
+                    ev = self._dz_event = torch.cuda.Event()
+                    ev.record()
+        dz = eng.mse_backward(z, xs, packed, u, stash, tgt, sw, 1.0 / gb, self._loss_buf,
+                              n._gviews[n._last_names[0]], n._gviews[n._last_names[1]], 0.0, dz_event=ev)
+        if overlap:
+            self._side.wait_event(ev)
+            with torch.cuda.stream(self._side):
+                n._trunk.backward(p_in, n.theta_trunk, tstash, dz, n.grad_trunk, 0.0)
+            reg = self._reg_loss()
+            if reg is not None:
+                self._loss_buf += reg * (B / gb)
+            return p_in, tstash, dz, True
         if act is not None:
             dz = dz + act[1]
             n._gviews[n._last_names[0]].add_(act[2])
@@ -673,11 +694,14 @@ class Model:
         reg = self._reg_loss()
         if reg is not None:
             self._loss_buf += reg * (B / gb)
-        return p_in, tstash, dz
+        return p_in, tstash, dz, False
 
     def _fused_part2(self, ctx):
         n = self.net
-        p_in, tstash, dz = ctx
+        p_in, tstash, dz, launched = ctx
+        if launched:  # the trunk's reverse pass is already running on the second stream: join
+            torch.cuda.current_stream().wait_stream(self._side)
+            return
         n._trunk.backward(p_in, n.theta_trunk, tstash, dz, n.grad_trunk, 0.0)
 
     def _fused_step(self, inp, tgt, sw, gb, apply_update, part1=None, part2=None):

@@ -247,16 +247,18 @@ class FusedShapeNet:
         return dz
 
     def mse_backward(self, z, x, packed, u, stash, target, sample_weight, inv_global_batch: float, loss, dw_h, db_h,
-                     beta: float = 0.0):
-        """Keras 'mse' + reverse pass.  `loss` is a 1-element tensor that is accumulated into."""
+                     beta: float = 0.0, dz_event: Optional["torch.cuda.Event"] = None):
+        """Keras 'mse' + reverse pass.  `loss` is a 1-element tensor that is accumulated into.  dz_event (already created:
+        recorded at least once) is recorded on the current stream as soon as dz is final."""
         B = x.shape[0]
         target = _f32c(target, "target")
         sw = _f32c(sample_weight, "sample_weight") if sample_weight is not None else None
         dz = torch.empty(B, self.K, dtype=torch.float32, device=x.device) if self.K > 0 else None
         ws = self._workspace(B, x.device)
-        check(_lib.lib().nif_mse_backward(C.byref(self.desc), B, _ptr(z), _ptr(x), _ptr(packed), _ptr(u), _ptr(stash),
-                                          _ptr(target), _ptr(sw), float(inv_global_batch), _ptr(loss), _ptr(dw_h),
-                                          _ptr(db_h), float(beta), _ptr(dz), _ptr(ws), _stream()),
+        ev = C.c_void_p(dz_event.cuda_event) if dz_event is not None else None
+        check(_lib.lib().nif_mse_backward_ev(C.byref(self.desc), B, _ptr(z), _ptr(x), _ptr(packed), _ptr(u), _ptr(stash),
+                                             _ptr(target), _ptr(sw), float(inv_global_batch), _ptr(loss), _ptr(dw_h),
+                                             _ptr(db_h), float(beta), _ptr(dz), _ptr(ws), ev, _stream()),
               "nif_mse_backward")
         return dz
 
