@@ -73,7 +73,8 @@ __global__ void __launch_bounds__(BFF_THREADS, 1) nif_bf_fwd_kernel(const Plan p
     mbar_init(&a_ready[0], 256);
     mbar_fence_init();
   }
-  if (warp == 8) tc_alloc(tmem_slot, 256);
+  // columns [0, 256): two accumulator stages; [256, 256 + NP / 2): the h operand tile (A of the main and last-layer chunks)
+  if (warp == 8) tc_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -128,12 +129,16 @@ __global__ void __launch_bounds__(BFF_THREADS, 1) nif_bf_fwd_kernel(const Plan p
         if (lane == 0) TRACE(2, g * 8 + 2);
         tc_fence_after();
         const uint64_t db = bf_make_desc(smem_u32(Bst + s * BF_STAGE_BYTES), b_sbo);
-        const uint64_t dA = a_main ? da : dz;
         const uint32_t d = tmem_u + as * 128u;
         const uint32_t idesc = bf_idesc(N);
         if (tc_elect_one()) {
-          for (int ks = 0; ks < ksteps; ++ks)
-            tc_mma_f16(d, dA + (uint64_t)(ks * 16), db + (uint64_t)(ks * 16), idesc, ks > 0 ? 1u : 0u);
+          if (a_main) {  // A = the h tile in tensor memory: its 32 KB are not re-read from shared memory for every chunk
+            for (int ks = 0; ks < ksteps; ++ks)
+              tc_mma_f16_ts(d, tmem_u + 256u + (uint32_t)(ks * 8), db + (uint64_t)(ks * 16), idesc, ks > 0 ? 1u : 0u);
+          } else {
+            for (int ks = 0; ks < ksteps; ++ks)
+              tc_mma_f16(d, dz + (uint64_t)(ks * 16), db + (uint64_t)(ks * 16), idesc, ks > 0 ? 1u : 0u);
+          }
           tc_commit(&t_full[as]);
           tc_commit(&b_empty[s]);
         }
@@ -212,14 +217,13 @@ __global__ void __launch_bounds__(BFF_THREADS, 1) nif_bf_fwd_kernel(const Plan p
       // the h operand tile of the next tensor-core layer (every MMA that read the previous contents has completed:
       // this thread observed the t_full of the last chunk that used it)
       auto publish_h = [&]() {
+        uint32_t w[CH / 2];
 #pragma unroll
-        for (int c = 0; c < CH / 8; ++c) {
-          uint32_t w[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) w[e] = bf_pack2(hcur[8 * c + 2 * e], hcur[8 * c + 2 * e + 1]);
-          *reinterpret_cast<uint4*>(A_tile + row_off + (uint32_t)(half * (CH / 8) + c) * 128u) = make_uint4(w[0], w[1], w[2], w[3]);
-        }
-        fence_async_smem();
+        for (int e = 0; e < CH / 2; ++e) w[e] = bf_pack2(hcur[2 * e], hcur[2 * e + 1]);
+        if constexpr (CH / 2 == 32) tc_st32(tm + 256u + (uint32_t)(half * (CH / 2)), w);
+        else tc_st16(tm + 256u + (uint32_t)(half * (CH / 2)), w);
+        tc_wait_st();
+        tc_fence_before();
         mbar_arrive(&a_ready[0]);
       };
       // activation / residual / stash of layer m; `pre` holds this thread's pre-activations, result in hcur.
@@ -335,7 +339,7 @@ __global__ void __launch_bounds__(BFF_THREADS, 1) nif_bf_fwd_kernel(const Plan p
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) tc_dealloc(tmem, 256);
+  if (warp == 8) tc_dealloc(tmem, 512);
 }
 
 static int bf_pick_stages(size_t fixed_bytes) {
