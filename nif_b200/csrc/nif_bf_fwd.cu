@@ -29,7 +29,8 @@ struct BfFwdArgs {
 #define BFF_THREADS 384
 
 __host__ __device__ inline size_t bff_smem_bytes(int NP, int KZ, int so, int nst) {
-  return (size_t)128 * NP * 2 + (size_t)128 * KZ * 2 + (size_t)nst * BF_STAGE_BYTES + (size_t)2 * so * 128 * 4 + 256;
+  (void)NP;
+  return (size_t)128 * KZ * 2 + (size_t)nst * BF_STAGE_BYTES + (size_t)2 * so * 128 * 4 + 256;
 }
 
 // Chunk schedule of one tile (identical for producer, MMA issuer and epilogue):
@@ -44,8 +45,7 @@ __global__ void __launch_bounds__(BFF_THREADS, 1) nif_bf_fwd_kernel(const Plan p
   constexpr uint32_t SBO_A = (NP / 8) * 128u;
   constexpr uint32_t MAIN_BYTES = 128u * NP * 2u;
   extern __shared__ __align__(1024) unsigned char smem[];
-  unsigned char* A_tile = smem;
-  unsigned char* Z_tile = smem + 128 * NP * 2;
+  unsigned char* Z_tile = smem;  // (the h operand tile lives in tensor memory)
   const uint32_t zbytes = 128u * (uint32_t)pl.KZ * 2u;
   const uint32_t sbo_z = (uint32_t)(pl.KZ / 8) * 128u;
   unsigned char* Bst = Z_tile + zbytes;
@@ -113,7 +113,6 @@ __global__ void __launch_bounds__(BFF_THREADS, 1) nif_bf_fwd_kernel(const Plan p
     } else if (warp == 8) {
       // ---------------- MMA issuer: the whole warp runs the loop, one elected lane issues (see tc_elect_one) ----------
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
-      const uint64_t da = bf_make_desc(smem_u32(A_tile), SBO_A);
       const uint64_t dz = bf_make_desc(smem_u32(Z_tile), sbo_z);
       uint32_t g = 0;          // chunk counter (accumulator stage / phase)
       uint32_t s = 0, ph = 0;  // weight-stream stage and phase
