@@ -135,7 +135,7 @@ extern "C" int nif_sobolev_query_dirs(const nif_desc_t* d, int64_t B, int32_t n_
     return NIF_E_BAD_ARG;
   }
   if (save_floats_per_row) *save_floats_per_row = (2LL + 2 * n_dir) * (pl.H + 1) * pl.NP;
-  if (ws_floats) *ws_floats = nif_grad_ws_layout(pl, B).total + 2LL * (pl.H + 1) * B * pl.NP;
+  if (ws_floats) *ws_floats = nif_grad_ws_layout(pl, B).total + 2LL * (pl.H + 1) * nif_tiled_rows(B) * pl.NP;
   return NIF_OK;
 }
 

@@ -781,14 +781,19 @@ __global__ void nif_loss_final_kernel(int nparts, const float* __restrict__ part
 // ---------------------------------------------------------------------------------------------------
 int nif_unpack_grad_impl(const Plan& pl, int S_h, const float* part_h, int S_e, const float* part_e, int Q,
                          float* dw_h, float* db_h, float beta, cudaStream_t st);
+struct TcBwdExt {  // hooks of the reverse-over-forward passes (nif_tc_bwd.cu)
+  const float *h_stash, *e_stash, *ext_add;
+  float* ext_out;
+  int no_bias, dz_accumulate, ext_accumulate;
+};
 int nif_tc_bwd_data_impl(const Plan& pl, long long B, const float* z, const float* x, const float* packed,
                          const float* save, const float* du, float* da, float* dz, unsigned* maxes,
-                         cudaStream_t st);
+                         cudaStream_t st, const TcBwdExt* ext = nullptr);
 int nif_tc_bwd_weight_impl(const Plan& pl, long long B, const float* z, const float* save, const float* da,
                            const unsigned* maxes, int S, long long rows_per_split, float* part, cudaStream_t st);
 int nif_tc_bwd_edge_impl(const Plan& pl, long long B, const float* z, const float* x, const float* save, const float* da,
                          const float* du, const unsigned* maxes, int S, long long rows_per_split, int Q, float* part,
-                         cudaStream_t st);
+                         cudaStream_t st, int no_bias = 0);
 
 
 bool nif_plan_uses_bf(const Plan& pl);
@@ -994,6 +999,44 @@ int nif_weight_grads_impl(const Plan& pl, long long B, const float* z, const flo
   return nif_unpack_grad_impl(pl, w.S_h, ws + w.part_h, w.S_e, ws + w.part_e, w.Q, dw_h, db_h, beta, st);
 }
 
+// Batch reductions of a tensor-core reverse pass whose da_m and maxima sit in ws: hidden-matrix GEMM, thin terms,
+// un-packing.  hsave: the stash whose h_m slots pair with da_m (the primal stash, or the tangent activations h'_m of a
+// reverse-over-forward pass, then with no_bias = 1 and x = xdot).
+static int nif_tc_weight_grads(const Plan& pl, long long B, const float* z, const float* x, const float* hsave,
+                               const float* du, float* dw_h, float* db_h, float beta, float* ws, cudaStream_t st,
+                               int no_bias) {
+  const GradWs w = nif_grad_ws_layout(pl, B);
+  int S_used = w.S_h, S_e_used = w.S_e;
+  {
+    // one CTA per SM: as many batch splits as fit one wave (never more than the workspace was sized for)
+    int S = nif_tc_wgt_splits(pl, B);  // whole waves, bounded accumulation chains (see nif_grad_ws_layout)
+    if (S > w.S_h) S = w.S_h;
+    long long rows = round_up((B + S - 1) / S, 64);
+    S = (int)((B + rows - 1) / rows);
+    const int rcw = nif_tc_bwd_weight_impl(pl, B, z, hsave, ws + w.da, reinterpret_cast<const unsigned*>(ws + w.maxes),
+                                           S, rows, ws + w.part_h, st);
+    if (rcw != NIF_OK) return rcw;
+    S_used = S;
+  }
+  {
+    EdgeArgs e;
+    e.B = B; e.rows_per_split = w.rows_e; e.S = w.S_e; e.Q = w.Q;
+    e.z = z; e.x = x; e.save = hsave; e.da = ws + w.da; e.du = du; e.part = ws + w.part_e; e.no_bias = no_bias; e.tiled = 1;
+    e.q_begin = 0; e.q_end = w.Q;
+    // thin terms on the tensor cores: one wave of CTAs (column-block pairs x batch splits)
+    int S_tc = nif_tc_edge_splits(pl, B);
+    if (S_tc > w.S_e_ws) S_tc = w.S_e_ws;
+    const long long rows_tc = round_up((B + S_tc - 1) / S_tc, 64);
+    S_tc = (int)((B + rows_tc - 1) / rows_tc);
+    const int rce = nif_tc_bwd_edge_impl(pl, B, z, x, hsave, ws + w.da, du, reinterpret_cast<const unsigned*>(ws + w.maxes),
+                                         S_tc, rows_tc, w.Q, ws + w.part_e, st, no_bias);
+    if (rce == NIF_OK) S_e_used = S_tc;
+    else if (rce != NIF_E_UNSUPPORTED) return rce;
+    else NIF_CUDA_CHECK(launch_edge(pl, e, w, st));
+  }
+  return nif_unpack_grad_impl(pl, S_used, ws + w.part_h, S_e_used, ws + w.part_e, w.Q, dw_h, db_h, beta, st);
+}
+
 // dz_ev (optional): recorded on `st` as soon as the data pass has been enqueued, i.e. when dz is final: the caller may start
 // the ParameterNet trunk's reverse pass on another stream while the weight-gradient kernels of this call run
 int nif_backward_impl(const Plan& pl, long long B, const float* z, const float* x, const float* packed,
@@ -1049,38 +1092,9 @@ int nif_backward_impl(const Plan& pl, long long B, const float* z, const float* 
   if (rc != NIF_OK) return rc;
   if (dz_ev) NIF_CUDA_CHECK(cudaEventRecord(dz_ev, st));
 
-  bool wgt_done = false;
-  int S_used = w.S_h, S_e_used = w.S_e;
-  if (tc_data && pl.H > 0) {  // tensor-core weight-gradient GEMM (needs the maxima recorded by the TC data pass)
-    // one CTA per SM: as many batch splits as fit one wave (never more than the workspace was sized for)
-    int S = nif_tc_wgt_splits(pl, B);  // whole waves, bounded accumulation chains (see nif_grad_ws_layout)
-    if (S > w.S_h) S = w.S_h;
-    long long rows = round_up((B + S - 1) / S, 64);
-    S = (int)((B + rows - 1) / rows);
-    const int rcw = nif_tc_bwd_weight_impl(pl, B, z, save, ws + w.da, reinterpret_cast<const unsigned*>(ws + w.maxes),
-                                           S, rows, ws + w.part_h, st);
-    if (rcw == NIF_OK) { wgt_done = true; S_used = S; }
-    else if (rcw != NIF_E_UNSUPPORTED) return rcw;
-  }
-  if (!wgt_done)  // CUDA-core hidden-matrix GEMM + thin terms + un-packing
-    return nif_weight_grads_impl(pl, B, z, x, save, du, dw_h, db_h, beta, ws, st);
-  {
-    EdgeArgs e;
-    e.B = B; e.rows_per_split = w.rows_e; e.S = w.S_e; e.Q = w.Q;
-    e.z = z; e.x = x; e.save = save; e.da = ws + w.da; e.du = du; e.part = ws + w.part_e; e.no_bias = 0; e.tiled = 1;
-    e.q_begin = 0; e.q_end = w.Q;
-    // thin terms on the tensor cores: one wave of CTAs (column-block pairs x batch splits)
-    int S_tc = nif_tc_edge_splits(pl, B);
-    if (S_tc > w.S_e_ws) S_tc = w.S_e_ws;
-    const long long rows_tc = round_up((B + S_tc - 1) / S_tc, 64);
-    S_tc = (int)((B + rows_tc - 1) / rows_tc);
-    const int rce = nif_tc_bwd_edge_impl(pl, B, z, x, save, ws + w.da, du, reinterpret_cast<const unsigned*>(ws + w.maxes),
-                                         S_tc, rows_tc, w.Q, ws + w.part_e, st);
-    if (rce == NIF_OK) S_e_used = S_tc;
-    else if (rce != NIF_E_UNSUPPORTED) return rce;
-    else NIF_CUDA_CHECK(launch_edge(pl, e, w, st));
-  }
-  return nif_unpack_grad_impl(pl, S_used, ws + w.part_h, S_e_used, ws + w.part_e, w.Q, dw_h, db_h, beta, st);
+  if (tc_data && pl.H > 0)  // tensor-core batch reductions (they need the maxima the TC data pass recorded)
+    return nif_tc_weight_grads(pl, B, z, x, save, du, dw_h, db_h, beta, ws, st, 0);
+  return nif_weight_grads_impl(pl, B, z, x, save, du, dw_h, db_h, beta, ws, st);  // CUDA cores
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1106,6 +1120,34 @@ int nif_sobolev_backward_impl(const Plan& pl, long long B, const float* z, const
   // which picks up X (through act'') and S (through F's h_m).
   if (B <= 0) return NIF_OK;
   const GradWs w = nif_grad_ws_layout(pl, B);
+  if (!zdot && nif_plan_tc_sobolev(pl)) {
+    // Tensor-core form (ShapeNet-input directions only; the stash is tiled, written by the same branch of
+    // nif_tangent_impl): per direction the tangent adjoint -- nif_tc_bwd_data_kernel<ext> with h' as activations, xdot
+    // as input and the bias rows dropped; it leaves X_m = dh'_{m+1} e_m in the workspace -- then the primal adjoint,
+    // which adds X_m to da_m; each followed by the FP16x3 batch reductions.
+    const long long tslot = nif_tiled_rows(B) * 64;
+    float* Xt = ws + w.total;
+    unsigned* maxes = reinterpret_cast<unsigned*>(ws + w.maxes);
+    for (int d = 0; d <= n_dir; ++d) {
+      const bool primal = d == n_dir;
+      TcBwdExt e;
+      const float *xin, *seed;
+      if (!primal) {
+        xin = xdot + (long long)d * B * pl.si; seed = dud + (long long)d * B * pl.so;
+        e.h_stash = save + (2LL + 2 * d) * (pl.H + 1) * tslot; e.e_stash = e.h_stash + (pl.H + 1) * tslot;
+        e.ext_out = Xt; e.ext_add = nullptr; e.ext_accumulate = d > 0; e.no_bias = 1; e.dz_accumulate = d > 0;
+      } else {
+        xin = x; seed = du;
+        e.h_stash = save; e.e_stash = nullptr; e.ext_out = nullptr; e.ext_add = Xt; e.ext_accumulate = 0; e.no_bias = 0;
+        e.dz_accumulate = 1;
+      }
+      int rc = nif_tc_bwd_data_impl(pl, B, z, xin, packed, save, seed, ws + w.da, dz, maxes, st, &e);
+      if (rc != NIF_OK) return rc;
+      rc = nif_tc_weight_grads(pl, B, z, xin, e.h_stash, seed, dw_h, db_h, d == 0 ? beta : 1.0f, ws, st, e.no_bias);
+      if (rc != NIF_OK) return rc;
+    }
+    return NIF_OK;
+  }
   const long long slot = B * (long long)pl.NP;
   float* X = ws + w.total;
   float* S = X + (pl.H + 1) * slot;

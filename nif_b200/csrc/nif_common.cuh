@@ -253,6 +253,8 @@ __host__ __device__ inline int nif_tiled_col(int j) { return (j >> 2) * 128 + (j
 __host__ __device__ inline long long nif_tiled_row_np(long long b, int NP) { return (b >> 5) * (32LL * NP) + (b & 31) * 4; }
 // static shape test shared by forward and reverse: does this plan run on the tensor-core kernels (tiled stash)?
 bool nif_plan_uses_tc(const Plan& pl);
+// ... and its Sobolev step (forward tangents with a stash, reverse-over-forward) for ShapeNet-input directions
+bool nif_plan_tc_sobolev(const Plan& pl);
 
 // reverse-pass workspace layout (offsets in floats), shared by nif_bwd.cu / nif_api.cu / nif_trunk.cu
 struct GradWs {

@@ -435,8 +435,27 @@ static int dispatch_tan(const Plan& pl, const TanArgs& a, cudaStream_t st) {
   return NIF_E_UNSUPPORTED;
 }
 
+int nif_tc_forward_impl(const Plan& pl, long long B, const float* z, const float* x, const float* packed, float* u,
+                        float* save, cudaStream_t st);
+int nif_tc_forward_tangent_impl(const Plan& pl, long long B, const float* z, const float* xdot, const float* packed,
+                                const float* psave, float* udot, float* tsave, cudaStream_t st);
+
 int nif_tangent_impl(const Plan& pl, long long B, const float* z, const float* x, const float* packed, int n_dir,
                      const float* zdot, const float* xdot, float* u, float* udot, float* save, cudaStream_t st) {
+  if (save && !zdot && xdot && nif_plan_tc_sobolev(pl)) {
+    // Sobolev stash on the tensor cores (tiled slots of nif_tiled_rows(B) x 64 floats): the primal forward with its
+    // stash, then one tangent launch per direction that reads d_m / h_{m+1} from it.  nif_sobolev_backward_impl takes
+    // the same branch (same predicate, same zdot), so the two agree on the layout.
+    int rc = nif_tc_forward_impl(pl, B, z, x, packed, u, save, st);
+    if (rc != NIF_OK) return rc;
+    const long long slot = nif_tiled_rows(B) * 64;
+    for (int d = 0; d < n_dir; ++d) {
+      rc = nif_tc_forward_tangent_impl(pl, B, z, xdot + (long long)d * B * pl.si, packed, save,
+                                       udot + (long long)d * B * pl.so, save + (2LL + 2 * d) * (pl.H + 1) * slot, st);
+      if (rc != NIF_OK) return rc;
+    }
+    return NIF_OK;
+  }
   // directions are processed two at a time (the primal is recomputed per pair)
   for (int d0 = 0; d0 < n_dir; d0 += 2) {
     TanArgs a;

@@ -24,6 +24,14 @@ struct TcBwdArgs {
   float* dz;        // [B][K]
   unsigned* maxes;  // [0..H] max|da_m| bits, [H+1] max|zt| bits, [H+2 .. 2H+2] max|h_m| bits (m = 1..H+1)
   int nst;          // weight-stream stages (3 where shared memory allows, else 2)
+  // Reverse-over-forward passes (EXT instantiation; the same hooks as BwdArgs of the CUDA-core kernel, nif_bwd.cu):
+  const float* h_stash;  // the h_m slots this pass pairs with its da_m (save, or the tangent activations h'_m); d_m stays save's
+  const float* e_stash;  // [H+1] slots e_m; with ext_out: ext_out[m] = dh_{m+1} * e_m (tangent-adjoint pass)
+  float* ext_out;
+  const float* ext_add;  // [H+1] slots added to da_m (the primal-adjoint pass consumes what the tangent pass wrote)
+  int no_bias;           // tangent-adjoint pass: the bias rows do not enter pre'_m, their dz terms are dropped
+  int dz_accumulate;     // dz += instead of =
+  int ext_accumulate;    // ext_out += instead of = (second and later directions)
 };
 
 // slots of the maxima buffer beyond [0, 2H + 2): operand-scale bounds for nif_tc_bwd_edge_kernel
@@ -116,6 +124,7 @@ __device__ __forceinline__ void tcb_issue(const Plan& pl, const TcBwdArgs& a, un
   }
 }
 
+template <bool EXT>
 __global__ void __launch_bounds__(TCB_THREADS, 1) nif_tc_bwd_data_kernel(const Plan pl, const TcBwdArgs a) {
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char* A_all = smem;
@@ -266,7 +275,7 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) nif_tc_bwd_data_kernel(const P
       float inv_hl;
       {
         float hl[64];
-        const float* hsrc = a.save + (long long)H * slot_floats + nif_tiled_row(b);
+        const float* hsrc = (EXT ? a.h_stash : a.save) + (long long)H * slot_floats + nif_tiled_row(b);
         float hmax = 0.f;
 #pragma unroll
         for (int c = 0; c < 16; ++c) {
@@ -335,8 +344,10 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) nif_tc_bwd_data_kernel(const P
 #pragma unroll
               for (int e = 0; e < 16; ++e) {
                 const int kk = k0 + e;
-                if (kk < K1 && c < so)
-                  dzs[kk * 128 + r] = fmaf(dyc, fmaf(sL, v[e], __ldg(&CL[(long long)kk * 64 + c])), dzs[kk * 128 + r]);
+                if (kk < K1 && c < so) {
+                  const float cl = (EXT && a.no_bias) ? 0.f : __ldg(&CL[(long long)kk * 64 + c]);
+                  dzs[kk * 128 + r] = fmaf(dyc, fmaf(sL, v[e], cl), dzs[kk * 128 + r]);
+                }
               }
             }
           }
@@ -356,6 +367,20 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) nif_tc_bwd_data_kernel(const P
           if (live) dv = ldg4(dsv + c * 128);
           dav[4 * c] = acc[4 * c] * dv.x; dav[4 * c + 1] = acc[4 * c + 1] * dv.y;
           dav[4 * c + 2] = acc[4 * c + 2] * dv.z; dav[4 * c + 3] = acc[4 * c + 3] * dv.w;
+          if (EXT && live) {
+            const long long eo = (long long)m * slot_floats + nif_tiled_row(b) + c * 128;
+            if (a.ext_add) {  // + dh'_{m+1} * e_m, written by the tangent-adjoint pass
+              const float4 xv = ldg4(a.ext_add + eo);
+              dav[4 * c] += xv.x; dav[4 * c + 1] += xv.y; dav[4 * c + 2] += xv.z; dav[4 * c + 3] += xv.w;
+            }
+            if (a.ext_out) {
+              const float4 ev = ldg4(a.e_stash + eo);
+              float4 xv = make_float4(acc[4 * c] * ev.x, acc[4 * c + 1] * ev.y, acc[4 * c + 2] * ev.z, acc[4 * c + 3] * ev.w);
+              float4* xo = reinterpret_cast<float4*>(a.ext_out + eo);
+              if (a.ext_accumulate) { const float4 o = *xo; xv.x += o.x; xv.y += o.y; xv.z += o.z; xv.w += o.w; }
+              *xo = xv;
+            }
+          }
           if (live) *reinterpret_cast<float4*>(dag + c * 128) = make_float4(dav[4 * c], dav[4 * c + 1], dav[4 * c + 2], dav[4 * c + 3]);
           amax = fmaxf(fmaxf(amax, fabsf(dav[4 * c])), fmaxf(fabsf(dav[4 * c + 1]), fmaxf(fabsf(dav[4 * c + 2]), fabsf(dav[4 * c + 3]))));
         }
@@ -368,7 +393,7 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) nif_tc_bwd_data_kernel(const P
         fence_async_smem();
         mbar_arrive(&a_ready[wg]);
         // bias rows of layer m: dz[kappa] += sum_j C_m[kappa][j] da_m[j]
-        drain_kz(inv_a * __ldg(&invX[T_bc + m]), 0u);
+        drain_kz((EXT && a.no_bias) ? 0.f : inv_a * __ldg(&invX[T_bc + m]), 0u);
         chunk_end();
         if (m == 0) {  // first matrix: dz[kappa] += omega x[i] sum_j M0[kappa][i][j] da_0[j]
           const float om0 = plan_omega(pl, 0);
@@ -382,7 +407,7 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) nif_tc_bwd_data_kernel(const P
         // this layer's input row h_m (for the dz dot products)
         float hm[64];
         {
-          const float* hsrc = a.save + (long long)(m - 1) * slot_floats + nif_tiled_row(b);
+          const float* hsrc = (EXT ? a.h_stash : a.save) + (long long)(m - 1) * slot_floats + nif_tiled_row(b);
           float hmax = 0.f;
 #pragma unroll
           for (int c = 0; c < 16; ++c) {
@@ -440,7 +465,11 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) nif_tc_bwd_data_kernel(const P
       }
 
       if (live) {
-        for (int kk = 0; kk < K; ++kk) a.dz[b * K + kk] = dzs[kk * 128 + r];
+        if (EXT && a.dz_accumulate) {
+          for (int kk = 0; kk < K; ++kk) a.dz[b * K + kk] += dzs[kk * 128 + r];
+        } else {
+          for (int kk = 0; kk < K; ++kk) a.dz[b * K + kk] = dzs[kk * 128 + r];
+        }
       }
     }
   }
@@ -450,24 +479,38 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) nif_tc_bwd_data_kernel(const P
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Hooks of the reverse-over-forward passes (null = the plain reverse pass); see TcBwdArgs.
+struct TcBwdExt {
+  const float *h_stash, *e_stash, *ext_add;
+  float* ext_out;
+  int no_bias, dz_accumulate, ext_accumulate;
+};
+
 int nif_tc_bwd_data_impl(const Plan& pl, long long B, const float* z, const float* x, const float* packed,
                          const float* save, const float* du, float* da, float* dz, unsigned* maxes,
-                         cudaStream_t st) {
+                         cudaStream_t st, const TcBwdExt* ext = nullptr) {
   if (!nif_plan_uses_tc(pl)) return NIF_E_UNSUPPORTED;
   TcBwdArgs a;
+  a.h_stash = save; a.e_stash = nullptr; a.ext_out = nullptr; a.ext_add = nullptr;
+  a.no_bias = 0; a.dz_accumulate = 0; a.ext_accumulate = 0;
+  if (ext) {
+    a.h_stash = ext->h_stash ? ext->h_stash : save; a.e_stash = ext->e_stash; a.ext_out = ext->ext_out; a.ext_add = ext->ext_add;
+    a.no_bias = ext->no_bias; a.dz_accumulate = ext->dz_accumulate; a.ext_accumulate = ext->ext_accumulate;
+  }
   a.nst = tcb_smem_bytes(pl.K, 3) <= 227 * 1024 ? 3 : 2;
   const size_t smem = tcb_smem_bytes(pl.K, a.nst);
   a.B = B;
   a.total_pairs = (B + 255) / 256;
   a.z = z; a.x = x; a.packed = packed; a.save = save; a.du = du; a.da = da; a.dz = dz; a.maxes = maxes;
   NIF_CUDA_CHECK(cudaMemsetAsync(maxes, 0, sizeof(unsigned) * 256, st));
-  NIF_CUDA_CHECK(cudaFuncSetAttribute(nif_tc_bwd_data_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  auto kern = ext ? nif_tc_bwd_data_kernel<true> : nif_tc_bwd_data_kernel<false>;
+  NIF_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int dev = 0, sms = 0;
   NIF_CUDA_CHECK(cudaGetDevice(&dev));
   NIF_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   long long grid = sms;
   if (grid > a.total_pairs) grid = a.total_pairs;
-  { NIF_PROF("nif_tc_bwd_data_kernel", st); nif_tc_bwd_data_kernel<<<(unsigned)grid, TCB_THREADS, smem, st>>>(pl, a); }
+  { NIF_PROF(ext ? "nif_tc_bwd_data_kernel<ext>" : "nif_tc_bwd_data_kernel", st); kern<<<(unsigned)grid, TCB_THREADS, smem, st>>>(pl, a); }
   NIF_CUDA_CHECK(cudaGetLastError());
   return NIF_OK;
 }

@@ -20,6 +20,7 @@ struct TcEdgeArgs {
   const float *z, *x, *save, *da, *du;
   const unsigned* maxes;  // see nif_tc_bwd_data_kernel / nif_dz_edge_kernel
   float* part;
+  int no_bias;  // tangent-adjoint pass (save = the tangent activations, x = xdot): the bias-row columns are zero
 };
 
 #define TCE_THREADS 288
@@ -92,6 +93,7 @@ __global__ void __launch_bounds__(TCE_THREADS, 1) nif_tc_bwd_edge_kernel(const P
       d.src = a.da + (long long)blk * slot_floats;
       d.bound = __uint_as_float(a.maxes[blk]);
       d.q0 = blk * 64;
+      if (a.no_bias) d.cst = 0.f;
     } else if (blk < H + 1 + si) {
       const int i = blk - H - 1;
       d.src = a.da; d.mul = a.x + i; d.mul_stride = si; d.cst = plan_omega(pl, 0);
@@ -106,6 +108,7 @@ __global__ void __launch_bounds__(TCE_THREADS, 1) nif_tc_bwd_edge_kernel(const P
       d.src = nullptr;
       for (int c = 0; c < so; ++c) d.bound = fmaxf(d.bound, __uint_as_float(a.maxes[NIF_MAX_DU + c]));
       d.q0 = (H + 1) * 64; d.ncol = so;
+      if (a.no_bias) d.cst = 0.f;
     }
     return d;
   };
@@ -272,9 +275,10 @@ __global__ void __launch_bounds__(TCE_THREADS, 1) nif_tc_bwd_edge_kernel(const P
 // Writes every column of part_e for S batch splits of rows_per_split rows (a multiple of 64).
 int nif_tc_bwd_edge_impl(const Plan& pl, long long B, const float* z, const float* x, const float* save, const float* da,
                          const float* du, const unsigned* maxes, int S, long long rows_per_split, int Q, float* part,
-                         cudaStream_t st) {
+                         cudaStream_t st, int no_bias = 0) {
   if (!nif_plan_uses_tc(pl) || pl.KZ > 64) return NIF_E_UNSUPPORTED;
   TcEdgeArgs a;
+  a.no_bias = no_bias;
   a.B = B; a.rows_per_split = rows_per_split; a.S = S; a.Q = Q;
   a.z = z; a.x = x; a.save = save; a.da = da; a.du = du; a.maxes = maxes; a.part = part;
   const size_t smem = 2 * (size_t)TCE_SLOT_BYTES;

@@ -28,6 +28,7 @@ struct TcFwdArgs {
   long long B, total_pairs;
   const float *z, *x, *packed;
   float *u, *save;
+  const float* psave;  // tangent mode: the primal stash (h_{m+1}, d_m) of the same rows
 };
 
 #define TCF_THREADS 384  // 8 epilogue warps + MMA warp + producer warp + 2 idle warps (register donors)
@@ -44,8 +45,13 @@ __host__ __device__ inline size_t tcf_smem_bytes(int KP, int KZ, int si) {
          2 * (size_t)KP * 128 * 4 + 2 * (size_t)si * 128 * 4 + 256;
 }
 
-// SINE: the activation is sine (SIREN variants), inlined; otherwise the out-of-line activation switch is called
-template <bool SAVE, bool SINE>
+// SINE: the activation is sine (SIREN variants), inlined; otherwise the out-of-line activation switch is called.
+// TAN: forward-mode tangent of a sine network without residual layers along one ShapeNet-input direction (a.x = xdot):
+// the same chunk schedule with the constant terms dropped (xt' = [omega xdot, 0], no bias sums), and the epilogue
+//   h'_{m+1} = d_m * pre'_m,   e_m = act''(pre_m) * pre'_m = -h_{m+1} * pre'_m
+// with d_m = cos(pre_m) and h_{m+1} = sin(pre_m) read from the primal stash; a.save receives h' (slots 0..H) and e
+// (slots H+1..2H+1), a.u the tangent of the output (JacobianLayer inside the loss, nif/layers/gradient.py:207-231).
+template <bool SAVE, bool SINE, bool TAN = false>
 __global__ void __launch_bounds__(TCF_THREADS, 1) nif_tc_fwd_kernel(const Plan pl, const TcFwdArgs a) {
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char* A_all = smem;                                  // tile t: hi at t*32K, lo at t*32K + 16K
@@ -248,6 +254,24 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) nif_tc_fwd_kernel(const Plan p
         const int res = plan_res(pl, m);  // 0 or 1 on this path (res-blocks use the CUDA-core kernel)
         float* sh = a.save + (long long)m * slot_floats + nif_tiled_row(b);            // h_{m+1}, tiled layout
         float* sd = a.save + (long long)(H + 1 + m) * slot_floats + nif_tiled_row(b);  // d_m
+        if (TAN) {  // (padded columns: the primal stash holds d = h = 0 there)
+          const float* ph = a.psave + (long long)m * slot_floats + nif_tiled_row(b);
+          const float* pd = a.psave + (long long)(H + 1 + m) * slot_floats + nif_tiled_row(b);
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 dv = live ? ldg4(pd + c * 128) : z4;
+            const float4 hv = live ? ldg4(ph + c * 128) : z4;
+            const float4 ev = make_float4(-hv.x * pre[4 * c], -hv.y * pre[4 * c + 1], -hv.z * pre[4 * c + 2], -hv.w * pre[4 * c + 3]);
+            hcur[4 * c] = dv.x * pre[4 * c]; hcur[4 * c + 1] = dv.y * pre[4 * c + 1];
+            hcur[4 * c + 2] = dv.z * pre[4 * c + 2]; hcur[4 * c + 3] = dv.w * pre[4 * c + 3];
+            if (live) {
+              *reinterpret_cast<float4*>(sh + c * 128) = make_float4(hcur[4 * c], hcur[4 * c + 1], hcur[4 * c + 2], hcur[4 * c + 3]);
+              *reinterpret_cast<float4*>(sd + c * 128) = ev;
+            }
+          }
+          return;
+        }
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           float hold[8];
@@ -317,7 +341,7 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) nif_tc_fwd_kernel(const Plan p
           // layer 0:  pre0[j] = sum_i' xt[i'] * (zt @ X0[i'])[j],  xt = [omega x, 1]
           const float om = plan_omega(pl, 0);
           for (int i = 0; i <= si; ++i) {
-            const float coef = inv_z * __ldg(&invX[i]) * (i < si ? om * xs[i * 128 + r] : 1.f);
+            const float coef = inv_z * __ldg(&invX[i]) * (i < si ? om * xs[i * 128 + r] : (TAN ? 0.f : 1.f));
             const uint32_t td = chunk_begin();
             drain64(td, acc, coef, i == 0);
             chunk_end();
@@ -325,7 +349,7 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) nif_tc_fwd_kernel(const Plan p
         } else {
           publish_h();
           {
-            const float coef = inv_z * __ldg(&invX[si + m]);
+            const float coef = TAN ? 0.f : inv_z * __ldg(&invX[si + m]);
             const uint32_t td = chunk_begin();  // bias sum: acc[j] = sum_kappa zt[kappa] C_m[kappa][j]
             drain64(td, acc, coef, true);
             chunk_end();
@@ -380,7 +404,7 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) nif_tc_fwd_kernel(const Plan p
               for (int e = 0; e < 16; ++e) {
                 const int kk = k0 + e;
                 if (kk < K1 && c < so)
-                  y = fmaf(zs[kk * 128 + r], fmaf(sL, v1[e], __ldg(&CL[(long long)kk * 64 + c])), y);
+                  y = fmaf(zs[kk * 128 + r], TAN ? sL * v1[e] : fmaf(sL, v1[e], __ldg(&CL[(long long)kk * 64 + c])), y);
               }
             }
             if (live && c < so) a.u[b * so + c] = y;
@@ -395,10 +419,10 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) nif_tc_fwd_kernel(const Plan p
   if (warp == 8) tc_dealloc(tmem, 512);
 }
 
-template <bool SAVE, bool SINE>
+template <bool SAVE, bool SINE, bool TAN = false>
 static int launch_tcf(const Plan& pl, const TcFwdArgs& a, cudaStream_t st) {
   const size_t smem = tcf_smem_bytes(pl.KP, pl.KZ, pl.si);
-  auto kern = nif_tc_fwd_kernel<SAVE, SINE>;
+  auto kern = nif_tc_fwd_kernel<SAVE, SINE, TAN>;
   NIF_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int dev = 0, sms = 0;
   NIF_CUDA_CHECK(cudaGetDevice(&dev));
@@ -406,7 +430,7 @@ static int launch_tcf(const Plan& pl, const TcFwdArgs& a, cudaStream_t st) {
   long long grid = sms;
   if (grid > a.total_pairs) grid = a.total_pairs;
   if (grid < 1) return NIF_OK;
-  { NIF_PROF("nif_tc_fwd_kernel", st); kern<<<(unsigned)grid, TCF_THREADS, smem, st>>>(pl, a); }
+  { NIF_PROF(TAN ? "nif_tc_fwd_kernel<tangent>" : "nif_tc_fwd_kernel", st); kern<<<(unsigned)grid, TCF_THREADS, smem, st>>>(pl, a); }
   NIF_CUDA_CHECK(cudaGetLastError());
   return NIF_OK;
 }
@@ -427,7 +451,28 @@ int nif_tc_forward_impl(const Plan& pl, long long B, const float* z, const float
   TcFwdArgs a;
   a.B = B;
   a.total_pairs = (B + 255) / 256;
-  a.z = z; a.x = x; a.packed = packed; a.u = u; a.save = save;
+  a.z = z; a.x = x; a.packed = packed; a.u = u; a.save = save; a.psave = nullptr;
   if (pl.act == NIF_ACT_SINE) return save ? launch_tcf<true, true>(pl, a, st) : launch_tcf<false, true>(pl, a, st);
   return save ? launch_tcf<true, false>(pl, a, st) : launch_tcf<false, false>(pl, a, st);
+}
+
+// Shapes whose Sobolev step (forward tangents with a stash + reverse-over-forward) runs on the tensor-core kernels: the
+// tangent epilogue derives act'' from the stashed sine, and the residual bookkeeping is not carried through it.
+bool nif_plan_tc_sobolev(const Plan& pl) {
+  if (!nif_plan_uses_tc(pl) || pl.act != NIF_ACT_SINE) return false;
+  for (int m = 0; m <= pl.H; ++m)
+    if (plan_res(pl, m) != 0 || plan_alpha(pl, m) != 1.0f) return false;
+  return true;
+}
+
+// Tangent of the network along one ShapeNet-input direction xdot [B][si] (the latent code does not move), given the
+// primal stash of nif_tc_forward_impl (tiled): udot [B][so], tsave = (H+1) slots h' + (H+1) slots e (tiled).
+int nif_tc_forward_tangent_impl(const Plan& pl, long long B, const float* z, const float* xdot, const float* packed,
+                                const float* psave, float* udot, float* tsave, cudaStream_t st) {
+  if (!nif_plan_tc_sobolev(pl)) return NIF_E_UNSUPPORTED;
+  TcFwdArgs a;
+  a.B = B;
+  a.total_pairs = (B + 255) / 256;
+  a.z = z; a.x = xdot; a.packed = packed; a.u = udot; a.save = tsave; a.psave = psave;
+  return launch_tcf<true, true, true>(pl, a, st);
 }

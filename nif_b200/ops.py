@@ -152,7 +152,8 @@ class FusedShapeNet:
             xdot = torch.zeros(n_dir, B, self.si, dtype=torch.float32, device=x.device)
         per_row = C.c_int64(0)
         check(_lib.lib().nif_sobolev_query_dirs(C.byref(self.desc), B, n_dir, C.byref(per_row), None), "nif_sobolev_query_dirs")
-        stash = torch.empty(int(per_row.value) * B, dtype=torch.float32, device=x.device)
+        # (rows rounded up to 64: the tensor-core path tiles the stash in row groups)
+        stash = torch.empty(int(per_row.value) * ((B + 63) // 64 * 64), dtype=torch.float32, device=x.device)
         check(_lib.lib().nif_forward_tangent_save(C.byref(self.desc), B, _ptr(z), _ptr(x), _ptr(packed), n_dir,
                                                   _ptr(zdot), _ptr(xdot), _ptr(u), _ptr(udot), _ptr(stash), _stream()),
               "nif_forward_tangent_save")

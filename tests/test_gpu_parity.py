@@ -501,6 +501,76 @@ def _engine_tc(spec):
                          compute="fp16x3")
 
 
+@pytest.mark.parametrize("si,so,n,l,K,B,pairs", [
+    (1, 1, 64, 4, 32, 300, [(0, 1)]),                    # C4 shape: du/dx of the 1-D travelling wave
+    (2, 2, 48, 2, 5, 1000, [(0, 1), (1, 2), (1, 1)]),    # two directions, two outputs, padded width, several tiles
+    (3, 1, 64, 1, 3, 77, [(0, 3), (0, 1)]),              # one hidden matrix, ragged tile, directions out of order
+    (2, 1, 64, 2, 8, 128, [(0, 2)]),                     # exactly one tile
+])
+def test_sobolev_on_the_tensor_cores(si, so, n, l, K, B, pairs):
+    """Sobolev step of a SIREN ShapeNet with ShapeNet-input directions on the tcgen05 kernels: forward tangents as a
+    mode of the forward kernel (nif_tc_fwd_kernel<tangent>), both adjoint passes through nif_tc_bwd_data_kernel<ext> and
+    the FP16x3 batch reductions.  Every variable's gradient vs autograd-of-autograd over the fp64 oracle, and the
+    kernel table must name the tensor-core kernels (no fall-through to the CUDA-core pass)."""
+    from nif_b200.ops import kernel_profile
+    spec, prm, inputs, target, _ = _random_problem("siren", si, so, n, l, K, B, seed=13 * K + n)
+    dev = torch.device("cuda:0")
+    wn, bn = O.last_layer_names(spec)
+    g = torch.Generator().manual_seed(8)
+    tgt_g = torch.randn(B, len(pairs), generator=g, dtype=torch.float64)
+    coef = 0.37
+    l64, g64, y64, dy64 = O.sobolev_loss_and_grads_pairs(spec, prm, inputs, target, tgt_g, pairs, coef)
+    prm32 = {k: v.float() for k, v in prm.items()}
+    l32, g32, y32, dy32 = O.sobolev_loss_and_grads_pairs(spec, prm32, inputs.float(), target.float(), tgt_g.float(),
+                                                         pairs, coef)
+    eng = _engine_tc(spec)
+    assert eng.kernel_path == "fp16x3"
+    cols = []
+    for _, c in pairs:
+        assert c >= spec.pi
+        if c not in cols:
+            cols.append(c)
+    D = len(cols)
+    leaves = {k: v.detach().clone().requires_grad_(True) for k, v in prm.items()}
+    z64 = O.latent(spec, leaves, inputs[:, : spec.pi].detach())
+    z = z64.detach().float().to(dev)
+    x = inputs[:, spec.pi:].float().contiguous().to(dev)
+    xdot = torch.zeros(D, B, si, device=dev)
+    for d, c in enumerate(cols):
+        xdot[d, :, c - spec.pi] = 1.0
+    w_h, b_h = prm[wn].float().to(dev), prm[bn].float().to(dev)
+    packed = eng.pack(w_h, b_h)
+    dw = torch.full_like(w_h, float("nan"))
+    db = torch.full_like(b_h, float("nan"))
+    with kernel_profile() as prof:
+        u, udot, stash = eng.forward_tangent(z, x, packed, None, xdot, save=True)
+        got_dy = torch.stack([udot[cols.index(c)][:, a] for a, c in pairs], 1)
+        du = (2.0 / (B * so)) * (u - target.float().to(dev))
+        dud = torch.zeros_like(udot)
+        for i, (a, c) in enumerate(pairs):
+            dud[cols.index(c)][:, a] += (2.0 * coef / (B * len(pairs))) * (got_dy[:, i] - tgt_g[:, i].float().to(dev))
+        dz = eng.sobolev_backward(z, x, xdot, packed, stash, du, dud, dw, db, 0.0)
+        torch.cuda.synchronize()
+    names = {k: c for k, c, _ in prof.table}
+    assert names.get("nif_tc_fwd_kernel<tangent>") == D and names.get("nif_tc_bwd_data_kernel<ext>") == D + 1, names
+    assert names.get("nif_tc_bwd_weight_kernel") == D + 1 and not any(k.startswith("nif_bwd_") or k.startswith("nif_tangent") for k in names), names
+    # the CUDA-core tangent kernel (no stash) is an independent implementation of the same outputs
+    u_ref, udot_ref = eng.forward_tangent(z, x, packed, None, xdot)
+    assert rel_err(u.cpu(), u_ref.cpu()) < 1e-5 and rel_err(udot.cpu(), udot_ref.cpu()) < 2e-5
+    assert _gate(rel_err(u.cpu(), y64), rel_err(y32, y64))
+    assert _gate(rel_err(got_dy.cpu(), dy64), rel_err(dy32, dy64), floor=2e-5)
+    z64.backward(dz.cpu().double())
+    for name in prm:
+        got = dw.cpu() if name == wn else db.cpu() if name == bn else leaves[name].grad
+        if got is None:
+            got = torch.zeros_like(prm[name])
+        e = rel_err(got, g64[name])
+        assert _gate(e, rel_err(g32[name], g64[name]), floor=2e-5), f"{name} err {e:.3e} (cpu32 {rel_err(g32[name], g64[name]):.3e})"
+    # accumulate semantics
+    eng.sobolev_backward(z, x, xdot, packed, stash, du, dud, dw, db, 1.0)
+    assert rel_err(dw.cpu(), 2 * g64[wn]) < 1e-4 and rel_err(db.cpu(), 2 * g64[bn]) < 1e-4
+
+
 @pytest.mark.parametrize(
     "variant,si,so,n,l,K,B",
     [
