@@ -117,8 +117,10 @@ int nif_forward_tangent2(const nif_desc_t* d, int64_t B, const float* z, const f
  * then a reverse-over-forward pass over every stashed direction.  A direction is (xdot [B,si], zdot [B,K]): a ShapeNet
  * input column has xdot = e_c, zdot = 0; a ParameterNet input column (d/dt) has xdot = 0 and zdot = the trunk tangent
  * of the latent code, and the pass then also returns dL/dzdot for the caller's trunk.
- * nif_forward_tangent_save stashes all n_dir directions: save is [save_floats_per_row * B] from
- * nif_sobolev_query_dirs(n_dir) (nif_sobolev_query = one direction); ws: [ws_floats]. */
+ * nif_forward_tangent_save stashes all n_dir directions: save is [save_floats_per_row * B64] from
+ * nif_sobolev_query_dirs(n_dir) (nif_sobolev_query = one direction), B64 = B rounded up to a multiple of 64; ws: [ws_floats].
+ * SIREN ShapeNets served by the tensor-core kernels (kernel_path 2, no res-blocks) with zdot == NULL run the whole pair on
+ * them: the tangent forward as a mode of the forward kernel, both adjoint passes through the reverse kernels. */
 int nif_sobolev_query(const nif_desc_t* d, int64_t B, int64_t* save_floats_per_row, int64_t* ws_floats);
 int nif_sobolev_query_dirs(const nif_desc_t* d, int64_t B, int32_t n_dir, int64_t* save_floats_per_row,
                            int64_t* ws_floats);
@@ -239,6 +241,20 @@ int nif_trunk_forward(const nif_trunk_desc_t* d, int64_t B, const float* p_in, c
 int nif_trunk_backward(const nif_trunk_desc_t* d, int64_t B, const float* p_in, const float* theta,
                        const float* save, const float* dz, float* g_theta, float beta, const float* packed,
                        float* ws, void* stream);
+
+/* Wide ParameterNet trunks (units > 64) under mixed_bfloat16: the Dense products are library GEMMs on bf16 operands;
+ * these two entry points are everything between two GEMMs of a layer, fused, with the rounding points of the policy
+ * (bf16 GEMM operands and products, fp32 elsewhere; nif/model.py:101-105, 326-343, nif/layers/mlp.py:148-160).
+ *   forward :  h_out [B,n] = (h_in ? h_in : 0) + act( float(y_bf16 [B,n]) + bias [n] ),  h_out_bf16 = bf16(h_out) (optional)
+ *   backward:  t = (dh_in ? dh_in : 0) + (pend_bf16 ? float(pend_bf16) : 0)      -- pend: the product g_above @ W_above^T
+ *              g_bf16 = bf16(t * act'(float(y_bf16) + bias)),  db [n] = sum_b t * act'(...) (fp32),  dh_out = t (optional,
+ *              may alias dh_in)
+ * n: a multiple of 8 that divides 2048, <= 256; act: NIF_ACT_* except SINE; ws: nif_trunk_ew_ws_floats(n) floats. */
+int nif_trunk_ew_forward(int64_t B, int32_t n, int32_t act, const void* y_bf16, const float* bias, const float* h_in,
+                         float* h_out, void* h_out_bf16, void* stream);
+int nif_trunk_ew_ws_floats(int32_t n);
+int nif_trunk_ew_backward(int64_t B, int32_t n, int32_t act, const void* y_bf16, const float* bias, const float* dh_in,
+                          const void* pend_bf16, float* dh_out, void* g_bf16, float* db, float* ws, void* stream);
 
 /* Utility used by the benchmark: sustained FP32 FMA rate of this GPU (TFLOP/s),
  * measured with CUDA events; blocks until done. */

@@ -18,6 +18,7 @@ SYMBOLS = (
     "nif_last_error", "nif_version", "nif_query_sizes", "nif_pack", "nif_forward", "nif_forward_tangent", "nif_forward_tangent2",
     "nif_forward_given_w", "nif_mse_backward", "nif_mse_backward_ev", "nif_backward", "nif_adam_step", "nif_adam_step_dev", "nif_measure_fp32_peak",
     "nif_trunk_query", "nif_trunk_forward", "nif_trunk_backward", "nif_trunk_kernel_path",
+    "nif_trunk_ew_forward", "nif_trunk_ew_ws_floats", "nif_trunk_ew_backward",
     "nif_sobolev_query", "nif_sobolev_query_dirs", "nif_forward_tangent_save", "nif_sobolev_backward", "nif_sobolev_backward_dirs",
     "nif_crc32c",
     "nif_profile_begin", "nif_profile_end", "nif_adabelief_step", "nif_lion_step", "nif_centralize_gradient", "nif_adam_step_multimem",
@@ -104,6 +105,9 @@ def lib() -> C.CDLL:
     L.nif_trunk_kernel_path.argtypes = [TP]
     L.nif_trunk_forward.argtypes = [TP, I64, VP, VP, VP, VP, VP, VP]
     L.nif_trunk_backward.argtypes = [TP, I64, VP, VP, VP, VP, VP, F, VP, VP, VP]
+    L.nif_trunk_ew_forward.argtypes = [I64, I32, I32, VP, VP, VP, VP, VP, VP]
+    L.nif_trunk_ew_ws_floats.argtypes = [I32]
+    L.nif_trunk_ew_backward.argtypes = [I64, I32, I32, VP, VP, VP, VP, VP, VP, VP, VP, VP]
     for name in SYMBOLS:
         getattr(L, name)  # raises AttributeError if the build is stale
         if name not in ("nif_last_error", "nif_crc32c"):

@@ -29,9 +29,7 @@ struct TcBwdArgs {
   const float* e_stash;  // [H+1] slots e_m; with ext_out: ext_out[m] = dh_{m+1} * e_m (tangent-adjoint pass)
   float* ext_out;
   const float* ext_add;  // [H+1] slots added to da_m (the primal-adjoint pass consumes what the tangent pass wrote)
-  int no_bias;           // tangent-adjoint pass: the bias rows do not enter pre'_m, their dz terms are dropped
   int dz_accumulate;     // dz += instead of =
-  int ext_accumulate;    // ext_out += instead of = (second and later directions)
 };
 
 // slots of the maxima buffer beyond [0, 2H + 2): operand-scale bounds for nif_tc_bwd_edge_kernel
@@ -124,8 +122,13 @@ __device__ __forceinline__ void tcb_issue(const Plan& pl, const TcBwdArgs& a, un
   }
 }
 
-template <bool EXT>
+// MODE: 0 = the plain reverse pass; reverse-over-forward passes (compile-time, so that the extra loads of the layer loop
+// are straight-line code the compiler can batch): 1 = tangent adjoint (writes ext_out, bias rows dropped), 2 = the same,
+// accumulating into ext_out (second and later directions), 3 = primal adjoint (adds ext_add)
+template <int MODE>
 __global__ void __launch_bounds__(TCB_THREADS, 1) nif_tc_bwd_data_kernel(const Plan pl, const TcBwdArgs a) {
+  constexpr bool EXT = MODE != 0;
+  constexpr bool NO_BIAS = MODE == 1 || MODE == 2;
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char* A_all = smem;
   unsigned char* Bst = smem + 4 * TC_TILE_BYTES;
@@ -345,7 +348,7 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) nif_tc_bwd_data_kernel(const P
               for (int e = 0; e < 16; ++e) {
                 const int kk = k0 + e;
                 if (kk < K1 && c < so) {
-                  const float cl = (EXT && a.no_bias) ? 0.f : __ldg(&CL[(long long)kk * 64 + c]);
+                  const float cl = NO_BIAS ? 0.f : __ldg(&CL[(long long)kk * 64 + c]);
                   dzs[kk * 128 + r] = fmaf(dyc, fmaf(sL, v[e], cl), dzs[kk * 128 + r]);
                 }
               }
@@ -369,15 +372,14 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) nif_tc_bwd_data_kernel(const P
           dav[4 * c + 2] = acc[4 * c + 2] * dv.z; dav[4 * c + 3] = acc[4 * c + 3] * dv.w;
           if (EXT && live) {
             const long long eo = (long long)m * slot_floats + nif_tiled_row(b) + c * 128;
-            if (a.ext_add) {  // + dh'_{m+1} * e_m, written by the tangent-adjoint pass
+            if (MODE == 3) {  // + dh'_{m+1} * e_m, written by the tangent-adjoint pass
               const float4 xv = ldg4(a.ext_add + eo);
               dav[4 * c] += xv.x; dav[4 * c + 1] += xv.y; dav[4 * c + 2] += xv.z; dav[4 * c + 3] += xv.w;
-            }
-            if (a.ext_out) {
+            } else {
               const float4 ev = ldg4(a.e_stash + eo);
               float4 xv = make_float4(acc[4 * c] * ev.x, acc[4 * c + 1] * ev.y, acc[4 * c + 2] * ev.z, acc[4 * c + 3] * ev.w);
               float4* xo = reinterpret_cast<float4*>(a.ext_out + eo);
-              if (a.ext_accumulate) { const float4 o = *xo; xv.x += o.x; xv.y += o.y; xv.z += o.z; xv.w += o.w; }
+              if (MODE == 2) { const float4 o = *xo; xv.x += o.x; xv.y += o.y; xv.z += o.z; xv.w += o.w; }
               *xo = xv;
             }
           }
@@ -393,7 +395,7 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) nif_tc_bwd_data_kernel(const P
         fence_async_smem();
         mbar_arrive(&a_ready[wg]);
         // bias rows of layer m: dz[kappa] += sum_j C_m[kappa][j] da_m[j]
-        drain_kz((EXT && a.no_bias) ? 0.f : inv_a * __ldg(&invX[T_bc + m]), 0u);
+        drain_kz(NO_BIAS ? 0.f : inv_a * __ldg(&invX[T_bc + m]), 0u);
         chunk_end();
         if (m == 0) {  // first matrix: dz[kappa] += omega x[i] sum_j M0[kappa][i][j] da_0[j]
           const float om0 = plan_omega(pl, 0);
@@ -491,11 +493,10 @@ int nif_tc_bwd_data_impl(const Plan& pl, long long B, const float* z, const floa
                          cudaStream_t st, const TcBwdExt* ext = nullptr) {
   if (!nif_plan_uses_tc(pl)) return NIF_E_UNSUPPORTED;
   TcBwdArgs a;
-  a.h_stash = save; a.e_stash = nullptr; a.ext_out = nullptr; a.ext_add = nullptr;
-  a.no_bias = 0; a.dz_accumulate = 0; a.ext_accumulate = 0;
+  a.h_stash = save; a.e_stash = nullptr; a.ext_out = nullptr; a.ext_add = nullptr; a.dz_accumulate = 0;
   if (ext) {
     a.h_stash = ext->h_stash ? ext->h_stash : save; a.e_stash = ext->e_stash; a.ext_out = ext->ext_out; a.ext_add = ext->ext_add;
-    a.no_bias = ext->no_bias; a.dz_accumulate = ext->dz_accumulate; a.ext_accumulate = ext->ext_accumulate;
+    a.dz_accumulate = ext->dz_accumulate;
   }
   a.nst = tcb_smem_bytes(pl.K, 3) <= 227 * 1024 ? 3 : 2;
   const size_t smem = tcb_smem_bytes(pl.K, a.nst);
@@ -503,7 +504,12 @@ int nif_tc_bwd_data_impl(const Plan& pl, long long B, const float* z, const floa
   a.total_pairs = (B + 255) / 256;
   a.z = z; a.x = x; a.packed = packed; a.save = save; a.du = du; a.da = da; a.dz = dz; a.maxes = maxes;
   NIF_CUDA_CHECK(cudaMemsetAsync(maxes, 0, sizeof(unsigned) * 256, st));
-  auto kern = ext ? nif_tc_bwd_data_kernel<true> : nif_tc_bwd_data_kernel<false>;
+  auto kern = nif_tc_bwd_data_kernel<0>;
+  if (ext) {  // the two passes of nif_sobolev_backward_impl
+    if (ext->ext_out && ext->no_bias && ext->e_stash && !ext->ext_add) kern = ext->ext_accumulate ? nif_tc_bwd_data_kernel<2> : nif_tc_bwd_data_kernel<1>;
+    else if (ext->ext_add && !ext->ext_out && !ext->no_bias) kern = nif_tc_bwd_data_kernel<3>;
+    else { nif_set_error("nif_tc_bwd_data: unsupported combination of reverse-over-forward hooks"); return NIF_E_UNSUPPORTED; }
+  }
   NIF_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int dev = 0, sms = 0;
   NIF_CUDA_CHECK(cudaGetDevice(&dev));

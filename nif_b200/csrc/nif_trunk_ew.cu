@@ -134,13 +134,22 @@ __global__ void __launch_bounds__(256) nif_trunk_ew_bwd_kernel(const TrunkEwBwdA
   }
 }
 
-// db[j] = sum over the blocks' partials (fixed order)
-__global__ void nif_trunk_ew_db_kernel(int nblk, int n, const float* part, float* db) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n) return;
+// db[j] = sum over the blocks' partials (fixed order): a block = 32 columns x 8 groups of partials, a warp reads 128
+// contiguous bytes per partial row; the 8 group sums are added in shared memory
+__global__ void __launch_bounds__(256) nif_trunk_ew_db_kernel(int nblk, int n, const float* part, float* db) {
+  __shared__ float red[8][32];
+  const int j = blockIdx.x * 32 + (threadIdx.x & 31), grp = threadIdx.x >> 5;
   float acc = 0.f;
-  for (int k = 0; k < nblk; ++k) acc += part[(long long)k * n + j];
-  db[j] = acc;
+  if (j < n)
+    for (int k = grp; k < nblk; k += 8) acc += part[(long long)k * n + j];
+  red[grp][threadIdx.x & 31] = acc;
+  __syncthreads();
+  if (grp == 0 && j < n) {
+    float t = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) t += red[q][threadIdx.x];
+    db[j] = t;
+  }
 }
 
 #define NIF_TRUNK_EW_BLOCKS 592  // 4 per SM
@@ -211,7 +220,7 @@ extern "C" int nif_trunk_ew_backward(int64_t B, int32_t n, int32_t act, const vo
   if (blocks > NIF_TRUNK_EW_BLOCKS) blocks = NIF_TRUNK_EW_BLOCKS;
   { NIF_PROF("nif_trunk_ew_bwd_kernel", st); nif_trunk_ew_bwd_kernel<<<(unsigned)blocks, 256, 0, st>>>(a); }
   NIF_CUDA_CHECK(cudaGetLastError());
-  { NIF_PROF("nif_trunk_ew_db_kernel", st); nif_trunk_ew_db_kernel<<<(n + 127) / 128, 128, 0, st>>>((int)blocks, n, ws, db); }
+  { NIF_PROF("nif_trunk_ew_db_kernel", st); nif_trunk_ew_db_kernel<<<(n + 31) / 32, 256, 0, st>>>((int)blocks, n, ws, db); }
   NIF_CUDA_CHECK(cudaGetLastError());
   return NIF_OK;
 }

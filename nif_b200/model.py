@@ -59,6 +59,85 @@ class _TrunkLinear(torch.autograd.Function):
         return dh, dW, db, None
 
 
+class _WideTrunk(torch.autograd.Function):
+    """The whole MLP trunk -- first Dense, l_st x MLP_SimpleShortCut, bottleneck Dense (nif/model.py:326-343,
+    nif/layers/mlp.py:148-160) -- of a wide ParameterNet (units > 64) under mixed_bfloat16, for the paths that
+    differentiate it once.  The Dense products are library GEMMs on bf16 operands; everything between two GEMMs of a layer
+    (cast, bias, activation, shortcut, cast; the reverse pass's activation derivative, bias gradient, shortcut sum) is one
+    kernel of the library (nif_trunk_ew_forward / nif_trunk_ew_backward) with the rounding points of _TrunkLinear: bf16 at
+    the GEMM operands and products, fp32 elsewhere.  Keeps two bf16 tensors per layer (operand and product) for the reverse
+    pass; the pre-activation is recomputed from the product."""
+
+    @staticmethod
+    def forward(ctx, p_in, act, *wb):  # wb = (W_first, b_first, W_hidden_0, b_hidden_0, ..., W_bottleneck, b_bottleneck)
+        from . import _lib
+        from .ops import _f32c, _stream
+        L = _lib.lib()
+        B = p_in.shape[0]
+        bf = torch.bfloat16
+        with torch.autocast("cuda", enabled=False):
+            Ws = [w.to(bf) for w in wb[0::2]]
+            bs = [_f32c(b, "bias") for b in wb[1::2]]
+            n = Ws[0].shape[1]
+            ins, ys, h32 = [p_in.to(bf)], [], None
+            for i in range(len(Ws) - 1):
+                y = ins[-1] @ Ws[i]
+                h_out = torch.empty(B, n, dtype=torch.float32, device=p_in.device)
+                h16 = torch.empty(B, n, dtype=bf, device=p_in.device)
+                _lib.check(L.nif_trunk_ew_forward(B, n, act, y.data_ptr(), bs[i].data_ptr(),
+                                                  None if h32 is None else h32.data_ptr(), h_out.data_ptr(), h16.data_ptr(),
+                                                  _stream()), "nif_trunk_ew_forward")
+                ys.append(y)
+                ins.append(h16)
+                h32 = h_out
+            z = (ins[-1] @ Ws[-1]).float() + bs[-1]
+        ctx.save_for_backward(*ins, *ys, *Ws, *bs[:-1])
+        ctx.act, ctx.nl = act, len(Ws)
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        from . import _lib
+        from .ops import _stream
+        L = _lib.lib()
+        nl, act = ctx.nl, ctx.act
+        t = ctx.saved_tensors
+        ins, ys, Ws, bs = t[:nl], t[nl: 2 * nl - 1], t[2 * nl - 1: 3 * nl - 1], t[3 * nl - 1:]
+        B, n = ys[0].shape
+        dev = dz.device
+        grads = [None] * (2 * nl)
+        with torch.autocast("cuda", enabled=False):
+            dz = dz.float()
+            g = dz.to(torch.bfloat16)
+            grads[2 * nl - 2] = (ins[-1].t() @ g).float()
+            grads[2 * nl - 1] = (dz.new_ones(1, B) @ dz).reshape(-1)
+            pend = g @ Ws[-1].t()
+            ws = torch.empty(int(L.nif_trunk_ew_ws_floats(n)), dtype=torch.float32, device=dev)
+            dh = None
+            for i in range(nl - 2, -1, -1):
+                gi = torch.empty(B, n, dtype=torch.bfloat16, device=dev)
+                db = torch.empty(n, dtype=torch.float32, device=dev)
+                dh_out = None if i == 0 else (dh if dh is not None else torch.empty(B, n, dtype=torch.float32, device=dev))
+                _lib.check(L.nif_trunk_ew_backward(B, n, act, ys[i].data_ptr(), bs[i].data_ptr(),
+                                                   None if dh is None else dh.data_ptr(), pend.data_ptr(),
+                                                   None if dh_out is None else dh_out.data_ptr(), gi.data_ptr(),
+                                                   db.data_ptr(), ws.data_ptr(), _stream()), "nif_trunk_ew_backward")
+                dh = dh_out
+                grads[2 * i] = (ins[i].t() @ gi).float()
+                grads[2 * i + 1] = db
+                if i > 0:
+                    pend = gi @ Ws[i].t()
+        return (None, None, *grads)
+
+
+def _wide_trunk_ok(net, input_p: torch.Tensor, units: int, act) -> bool:
+    """_WideTrunk serves: the once-differentiated training step of a mixed_bfloat16 model on the GPU whose MLP trunk is
+    wider than the tensor-core trunk kernels go (they stop at 64 units)."""
+    return (net._first_order_only and getattr(net, "_use_wide_trunk", True) and input_p.is_cuda
+            and torch.is_autocast_enabled() and units > 64 and units <= 256
+            and units % 8 == 0 and 2048 % units == 0 and act in ACT and act != "sine")
+
+
 class NIF(object):
     """Neural Implicit Flow with a swish/tanh/... ShapeNet with residual hidden layers
     (reference: class NIF, nif/model.py:48-480).
@@ -316,6 +395,10 @@ class NIF(object):
     def _latent(self, input_p: torch.Tensor) -> torch.Tensor:
         """_call_parameter_net up to the bottleneck (nif/model.py:326-343; MLP_SimpleShortCut mlp.py:148-160)."""
         V = self._views
+        if _wide_trunk_ok(self, input_p, int(self.cfg_parameter_net["units"]), self.cfg_parameter_net["activation"]):
+            names = ["first_dense_pnet"] + [f"hidden_mlpshortcut_pnet_{i}" for i in range(self.l_st)] + ["bottleneck_pnet"]
+            wb = [V[q + s] for q in names for s in ("/kernel", "/bias")]
+            return _WideTrunk.apply(input_p, ACT[self.cfg_parameter_net["activation"]], *wb)
         f = self._act(self.cfg_parameter_net["activation"])
         h = f(self._lin(input_p, V["first_dense_pnet/kernel"], V["first_dense_pnet/bias"]))
         for i in range(self.l_st):
@@ -507,6 +590,10 @@ class NIFMultiScale(NIF):
                     q = f"siren_hidden_pnet_{i}"
                     h = torch.sin(w0 * (h @ V[q + "_w"]) + V[q + "_b"])
             return h @ V["siren_bottleneck_pnet_w"] + V["siren_bottleneck_pnet_b"]
+        if not res and _wide_trunk_ok(self, input_p, int(p["units"]), p["activation"]):
+            names = ["mlp_first_pnet"] + [f"mlp_hidden_pnet_{i}" for i in range(self.l_st)] + ["bottleneck_pnet"]
+            wb = [V[q + s] for q in names for s in ("/kernel", "/bias")]
+            return _WideTrunk.apply(input_p, ACT[p["activation"]], *wb)
         f = self._act(p["activation"])
         h = f(self._lin(input_p, V["mlp_first_pnet/kernel"], V["mlp_first_pnet/bias"]))
         for i in range(self.l_st):
