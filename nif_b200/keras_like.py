@@ -971,10 +971,72 @@ class Model:
                 "latent_moves": any(c < n.pi_dim for c in dirs)}
 
     def _train_step_sobolev(self, inp: torch.Tensor, tgt: torch.Tensor, global_batch: Optional[int]) -> torch.Tensor:
+        """One optimisation step of a JacobianLayer model: loss and gradients (_sobolev_loss_and_grad), then the update.
+        With the latent code at rest (ShapeNet-input directions only) the step is recorded in a CUDA graph per batch
+        shape and replayed, like the general step."""
+        n = self.net
+        B = inp.shape[0]
+        if (B > 0 and inp.is_cuda and not self._sobolev_plan["latent_moves"] and self._graph_enabled()
+                and isinstance(self.loss, (str, SobolevMSE))  # (a user callable may do anything, e.g. synchronise)
+                and os.environ.get("NIF_B200_GRAPH_GENERAL", "1") != "0"):
+            return self._sobolev_step_graph(inp, tgt, int(global_batch) if global_batch else B)
+        lv = self._sobolev_loss_and_grad(inp, tgt, global_batch)
+        if self.dist is not None:
+            self.dist.allreduce_(n.grad)
+        l1, l2 = n._kernel_regulariser()
+        self._apply_update(self.optimizer.apply, l1, l2)
+        return lv
+
+    def _sobolev_step_graph(self, inp, tgt, gb) -> torch.Tensor:
+        n, opt = self.net, self.optimizer
+        if self._loss_buf is None:
+            self._loss_buf = torch.zeros(1, dtype=torch.float32, device=n.device)
+        opt.prepare_replay(n.theta)
+        key = ("sobolev", inp.shape[0], gb)
+        ent = self._graphs.get(key)
+        if ent is not None and ent.get("sig") not in (None, self._graph_signature()):
+            ent = None
+        single = self.dist is None
+        l1, l2 = n._kernel_regulariser()
+
+        def eager_update():
+            if self.dist is not None:
+                self.dist.allreduce_(n.grad)
+            self._apply_update(opt.apply, l1, l2)
+
+        if ent is None:  # first visit: eager (sizes workspaces, warms up the library handles)
+            while len(self._graphs) >= self.GRAPH_CACHE:
+                self._graphs.pop(next(iter(self._graphs)))
+            self._graphs[key] = {"sig": None}
+            lv = self._sobolev_loss_and_grad(inp, tgt, gb)
+            eager_update()
+            return lv
+        if ent["sig"] is None:
+            ent["inp"], ent["tgt"] = torch.empty_like(inp), torch.empty_like(tgt)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                ent["out"] = self._sobolev_loss_and_grad(ent["inp"], ent["tgt"], gb)
+                if single:
+                    self._apply_update(opt.record_apply, l1, l2)
+            ent["graph"] = g
+            ent["keep"] = (n.engine._ws, getattr(n._trunk, "_ws", None), getattr(n._trunk, "_packed", None), self._packed,
+                           self._loss_buf, n.theta, n.grad, opt._m, opt._v, opt._alpha_dev)
+            ent["sig"] = self._graph_signature()
+        ent["inp"].copy_(inp, non_blocking=True)
+        ent["tgt"].copy_(tgt, non_blocking=True)
+        if single:
+            opt.advance_replay()
+            ent["graph"].replay()
+        else:
+            ent["graph"].replay()
+            eager_update()
+        return ent["out"]
+
+    def _sobolev_loss_and_grad(self, inp: torch.Tensor, tgt: torch.Tensor, global_batch: Optional[int]) -> torch.Tensor:
         """JacobianLayer inside the loss (tutorial 8): forward-mode tangents with a stash, then the reverse-over-forward
         pass of the library.  Grad columns w.r.t. ShapeNet inputs are directions on x; grad columns w.r.t. ParameterNet
         inputs (du/dt) are directions on the latent code, whose tangent -- and the adjoint that comes back for it -- go
-        through the trunk by reverse-over-forward autograd."""
+        through the trunk by reverse-over-forward autograd.  Leaves every gradient in the flat buffer; returns the loss."""
         n, loss, plan = self.net, self.loss, self._sobolev_plan
         if isinstance(n.p_jac_reg, (float, int)):
             raise NifError("jac_reg is not combined with Sobolev training in this build")
@@ -1029,8 +1091,11 @@ class Model:
         else:
             du = torch.zeros_like(u)
             vc, gc = loss.value_cols, loss.grad_cols
-            ev = u[:, vc] - tgt[:, vc]
-            du[:, vc] = (2.0 / (gb * len(vc))) * ev
+            if plan.get("vc_idx") is None or plan["vc_idx"].device != u.device:  # (a device index: no host copy per step)
+                plan["vc_idx"] = torch.as_tensor(list(vc), dtype=torch.long, device=u.device)
+            vci = plan["vc_idx"]
+            ev = u.index_select(1, vci) - tgt.index_select(1, vci)
+            du.index_copy_(1, vci, (2.0 / (gb * len(vc))) * ev)
             sq_g = 0.0
             for (d, yc), c in zip(pairs, gc):
                 eg = udot[d][:, yc] - tgt[:, c]
@@ -1046,10 +1111,6 @@ class Model:
         else:
             dz, dzdot = out
             torch.autograd.backward([z] + [zd for _, zd in zds], [dz] + [dzdot[d] for d, _ in zds])
-        if self.dist is not None:
-            self.dist.allreduce_(n.grad)
-        l1, l2 = n._kernel_regulariser()
-        self._apply_update(self.optimizer.apply, l1, l2)
         return lv.reshape(1)
 
     def fit(self, x=None, y=None, batch_size=None, epochs=1, verbose=0, callbacks=None, shuffle=True,

@@ -100,13 +100,15 @@ if want("C4"):
     ms = ev_time(lambda: m._train_step(X, Y, None, B), 5)
     F, P = flops_step(1, 1, 1, 64, 4, 32, 64, 4, tangents=1, tangents_p=0)
     from nif_b200.ops import kernel_profile  # noqa: E402
+    m.use_graph = False  # the per-kernel events need eager launches
+    ms_eager = ev_time(lambda: m._train_step(X, Y, None, B), 5)
     with kernel_profile() as prof:
         for _ in range(3):
             m._train_step(X, Y, None, B)
     table = [{"kernel": k, "us_per_step": t * 1e3 / 3, "launches_per_step": c / 3} for k, c, t in sorted(prof.table, key=lambda r: -r[2])]
     out.append({"config": f"C4 Sobolev training ShapeNet 4x64, latent 32, batch 65536, loss on u and du/dx (kernels: "
                           f"{net.engine.kernel_path}; tangent forward and both adjoint passes)", "po_dim": P, "ms_per_step": ms,
-                "points_per_s": B / ms * 1e3, "library_kernels": table,
+                "points_per_s": B / ms * 1e3, "ms_per_step_eager_launches": ms_eager, "library_kernels": table,
                 "library_kernels_us": sum(r["us_per_step"] for r in table)})
 
 # ---- C5: latent-sweep inference, ShapeNet 3->6x128->1, G latents x N grid points (scaled: 64 x 64^3 per call) ----
