@@ -379,6 +379,8 @@ class Model:
                 raise IndexError(f"x_index {c} outside the {n.pi_dim + n.si_dim} model inputs")
         if z is None:
             z = self._latent_nograd(p_in)
+        if all(c >= n.pi_dim for c in x_index):
+            zdot = None  # the latent code does not move
         u, udot = n.engine.forward_tangent(z.contiguous(), xs, self._packed_weights(), zdot, xdot)  # udot [nd, B, so]
         J = udot.permute(1, 2, 0)[:, y_index, :]  # [B, |y|, |x|]
         return u, J.contiguous()

@@ -69,6 +69,9 @@ class FusedShapeNet:
         # which kernels the library will run for this descriptor (shapes a tensor-core path lacks fall through to
         # the CUDA-core kernels): "fp32" | "fp16x3" | "bf16"
         self.kernel_path = {v: k for k, v in self.COMPUTE.items()}[int(s.kernel_path)]
+        # forward tangents along ShapeNet inputs (and the Sobolev step) on the tensor-core kernels: sine, no residual layers
+        # (nif_plan_tc_sobolev in csrc/nif_tc_fwd.cu)
+        self.tc_sobolev = self.kernel_path == "fp16x3" and variant == "siren"
         self._ws = None
 
     def with_latent(self, K: int) -> "FusedShapeNet":
@@ -143,6 +146,23 @@ class FusedShapeNet:
         xdot = _f32c(xdot, "xdot") if xdot is not None else None
         u = torch.empty(B, self.so, dtype=torch.float32, device=x.device)
         udot = torch.empty(n_dir, B, self.so, dtype=torch.float32, device=x.device)
+        if not save and zdot is None and xdot is not None and self.tc_sobolev and B > 0:
+            # ShapeNet-input directions of a SIREN ShapeNet the tensor-core kernels serve: the library runs the stashing
+            # pair (forward kernel + its tangent mode) on them; here the stash is scratch, so the rows go in blocks
+            per_row = C.c_int64(0)
+            check(_lib.lib().nif_sobolev_query_dirs(C.byref(self.desc), B, n_dir, C.byref(per_row), None), "nif_sobolev_query_dirs")
+            blk = min(B, 65536)
+            scratch = torch.empty(int(per_row.value) * ((blk + 63) // 64 * 64), dtype=torch.float32, device=x.device)
+            for s in range(0, B, blk):
+                e = min(B, s + blk)
+                ub = u[s:e]
+                ud = torch.empty(n_dir, e - s, self.so, dtype=torch.float32, device=x.device)
+                xd = xdot[:, s:e].contiguous()
+                check(_lib.lib().nif_forward_tangent_save(C.byref(self.desc), e - s, _ptr(z[s:e]) if z is not None else None,
+                                                          _ptr(x[s:e]), _ptr(packed), n_dir, None, _ptr(xd), _ptr(ub),
+                                                          _ptr(ud), _ptr(scratch), _stream()), "nif_forward_tangent_save")
+                udot[:, s:e] = ud
+            return u, udot
         if not save:
             check(_lib.lib().nif_forward_tangent(C.byref(self.desc), B, _ptr(z), _ptr(x), _ptr(packed), n_dir,
                                                  _ptr(zdot), _ptr(xdot), _ptr(u), _ptr(udot), _stream()),

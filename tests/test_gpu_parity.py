@@ -554,8 +554,13 @@ def test_sobolev_on_the_tensor_cores(si, so, n, l, K, B, pairs):
     names = {k: c for k, c, _ in prof.table}
     assert names.get("nif_tc_fwd_kernel<tangent>") == D and names.get("nif_tc_bwd_data_kernel<ext>") == D + 1, names
     assert names.get("nif_tc_bwd_weight_kernel") == D + 1 and not any(k.startswith("nif_bwd_") or k.startswith("nif_tangent") for k in names), names
-    # the CUDA-core tangent kernel (no stash) is an independent implementation of the same outputs
-    u_ref, udot_ref = eng.forward_tangent(z, x, packed, None, xdot)
+    # the CUDA-core tangent kernel (an explicit zdot selects it) is an independent implementation of the same outputs
+    with kernel_profile() as prof2:
+        u_ref, udot_ref = eng.forward_tangent(z, x, packed, torch.zeros(D, B, K, device=dev), xdot)
+        u_tc, udot_tc = eng.forward_tangent(z, x, packed, None, xdot)  # no stash asked for: still the tensor-core pair
+    names2 = {k: c for k, c, _ in prof2.table}
+    assert names2.get("nif_tc_fwd_kernel<tangent>") == D and sum(c for k, c in names2.items() if k.startswith("nif_tangent")) >= 1, names2
+    assert torch.equal(u_tc, u) and torch.equal(udot_tc, udot)
     assert rel_err(u.cpu(), u_ref.cpu()) < 1e-5 and rel_err(udot.cpu(), udot_ref.cpu()) < 2e-5
     assert _gate(rel_err(u.cpu(), y64), rel_err(y32, y64))
     assert _gate(rel_err(got_dy.cpu(), dy64), rel_err(dy32, dy64), floor=2e-5)
