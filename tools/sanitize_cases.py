@@ -2,6 +2,7 @@
 FP16x3 tensor-core forward / reverse / weight / thin-term kernels, the bf16 kernels (padded widths 64 and 128), the
 tensor-core trunk, the CUDA-core tile kernels, tangents, Adam.  Prints one line per family; shapes are tiny because the
 sanitizer runs the kernels 10-100x slower."""
+import os
 import sys
 
 import torch
@@ -30,6 +31,40 @@ def head(variant, si, so, n, l, K, B, compute):
     return eng, z, x, packed
 
 
+def tc_sobolev_and_wide_trunk():
+    """Sobolev step on the tensor cores (tangent mode of the forward kernel, reverse-over-forward modes of the data kernel,
+    two directions so that the accumulating mode runs too) and the fused elementwise kernels of a wide bf16 trunk."""
+    import ctypes as C
+    from nif_b200 import _lib
+    eng, z, x, packed = head("siren", 2, 1, 64, 2, 5, 300, "fp16x3")
+    xd = torch.zeros(2, 300, 2, device=dev)
+    xd[0, :, 0] = 1
+    xd[1, :, 1] = 1
+    u, ud, stash = eng.forward_tangent(z, x, packed, None, xd, save=True)
+    dw, db = torch.empty(5, eng.po_dim, device=dev), torch.empty(eng.po_dim, device=dev)
+    dz = eng.sobolev_backward(z, x, xd, packed, stash, u * 1e-3, ud * 1e-3, dw, db, 0.0)
+    u2, ud2 = eng.forward_tangent(z, x, packed, None, xd)
+    torch.cuda.synchronize()
+    print("tangent sobolev tensor cores |dz|", float(dz.abs().max()), "|dw|", float(dw.abs().max()), "same outputs", bool(torch.equal(ud, ud2)))
+    L = _lib.lib()
+    B, n = 333, 128
+    y = torch.randn(B, n, generator=g).to(dev).to(torch.bfloat16)
+    bias = torch.randn(n, generator=g).to(dev)
+    h = torch.randn(B, n, generator=g).to(dev)
+    ho, hb = torch.empty_like(h), torch.empty(B, n, dtype=torch.bfloat16, device=dev)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _lib.check(L.nif_trunk_ew_forward(B, n, 2, y.data_ptr(), bias.data_ptr(), h.data_ptr(), ho.data_ptr(), hb.data_ptr(), st), "ew fwd")
+    gq, dbb = torch.empty_like(hb), torch.empty(n, device=dev)
+    ws = torch.empty(int(L.nif_trunk_ew_ws_floats(n)), device=dev)
+    _lib.check(L.nif_trunk_ew_backward(B, n, 2, y.data_ptr(), bias.data_ptr(), h.data_ptr(), hb.data_ptr(), h.data_ptr(),
+                                       gq.data_ptr(), dbb.data_ptr(), ws.data_ptr(), st), "ew bwd")
+    torch.cuda.synchronize()
+    print("trunk elementwise |h|", float(ho.abs().max()), "|db|", float(dbb.abs().max()))
+
+
+if os.environ.get("NIF_SANITIZE_ONLY") == "new":  # the kernels added last (the other families: the full run's logs)
+    tc_sobolev_and_wide_trunk()
+    sys.exit(0)
 head("siren", 2, 1, 64, 2, 5, 300, "fp16x3")
 head("nif", 2, 2, 48, 2, 3, 200, "fp16x3")
 head("siren", 2, 1, 64, 2, 5, 300, "bf16")
@@ -67,3 +102,4 @@ m, v = torch.zeros_like(theta), torch.zeros_like(theta)
 adam_step(theta, gt, m, v, 1e-3, 1)
 torch.cuda.synchronize()
 print("adam ok")
+tc_sobolev_and_wide_trunk()
