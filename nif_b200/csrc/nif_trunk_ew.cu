@@ -134,20 +134,21 @@ __global__ void __launch_bounds__(256) nif_trunk_ew_bwd_kernel(const TrunkEwBwdA
   }
 }
 
-// db[j] = sum over the blocks' partials (fixed order): a block = 32 columns x 8 groups of partials, a warp reads 128
-// contiguous bytes per partial row; the 8 group sums are added in shared memory
-__global__ void __launch_bounds__(256) nif_trunk_ew_db_kernel(int nblk, int n, const float* part, float* db) {
-  __shared__ float red[8][32];
-  const int j = blockIdx.x * 32 + (threadIdx.x & 31), grp = threadIdx.x >> 5;
+// db[j] = sum over the blocks' partials (fixed order): a block = 32 columns x 32 groups of partials, a warp reads 128
+// contiguous bytes per partial row; the group sums are added in shared memory
+__global__ void __launch_bounds__(1024) nif_trunk_ew_db_kernel(int nblk, int n, const float* part, float* db) {
+  __shared__ float red[32][33];
+  const int c = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + c;
   float acc = 0.f;
   if (j < n)
-    for (int k = grp; k < nblk; k += 8) acc += part[(long long)k * n + j];
-  red[grp][threadIdx.x & 31] = acc;
+    for (int k = grp; k < nblk; k += 32) acc += part[(long long)k * n + j];
+  red[grp][c] = acc;
   __syncthreads();
   if (grp == 0 && j < n) {
     float t = 0.f;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) t += red[q][threadIdx.x];
+    for (int q = 0; q < 32; ++q) t += red[q][c];
     db[j] = t;
   }
 }
@@ -220,7 +221,7 @@ extern "C" int nif_trunk_ew_backward(int64_t B, int32_t n, int32_t act, const vo
   if (blocks > NIF_TRUNK_EW_BLOCKS) blocks = NIF_TRUNK_EW_BLOCKS;
   { NIF_PROF("nif_trunk_ew_bwd_kernel", st); nif_trunk_ew_bwd_kernel<<<(unsigned)blocks, 256, 0, st>>>(a); }
   NIF_CUDA_CHECK(cudaGetLastError());
-  { NIF_PROF("nif_trunk_ew_db_kernel", st); nif_trunk_ew_db_kernel<<<(n + 31) / 32, 256, 0, st>>>((int)blocks, n, ws, db); }
+  { NIF_PROF("nif_trunk_ew_db_kernel", st); nif_trunk_ew_db_kernel<<<(n + 31) / 32, 1024, 0, st>>>((int)blocks, n, ws, db); }
   NIF_CUDA_CHECK(cudaGetLastError());
   return NIF_OK;
 }
