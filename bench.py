@@ -1,11 +1,14 @@
 #!/usr/bin/env python
 """Headline benchmark: point-evals/s (forward + loss + backward + Adam) of the NIF hot path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--batch B]
 
 Workload (BASELINE.json configs[1], SURVEY 8 "C2"): NIFMultiScale, ShapeNet 2 -> 4x64 SIREN -> 1
 (omega_0 30), ParameterNet 1 -> 64 x4 swish shortcut MLP -> latent 32, po_dim 16 897, 1 M synthetic
-(t, x0, x1) points, fp32.  One step = one optimisation step over one batch of 65 536 points per GPU.
+(t, x0, x1) points, fp32.  One step = one optimisation step over one batch of 113 664 points per GPU: the forward and
+reverse kernels run one persistent CTA per SM on pairs of 128-row tiles, so a batch that is a multiple of 148 SMs x 256
+rows = 37 888 fills their last wave (3 pairs per SM here; the 65 536 rows of the earlier rounds leave 13 % of it empty:
+60.4 M rows/s against 68.4 M, profiles/r02w_wave_batches.json; `--batch 65536` reproduces that configuration).
 N > 1 (torchrun, one rank per GPU): weak scaling, per-GPU batch fixed, one NCCL all-reduce of the flat
 gradient buffer per step.
 
@@ -31,7 +34,7 @@ CFG_S = {"use_resblock": False, "connectivity": "full", "input_dim": 2, "output_
          "weight_init_factor": 0.01, "omega_0": 30.0}
 CFG_P = {"use_resblock": False, "input_dim": 1, "latent_dim": 32, "units": 64, "nlayers": 4, "activation": "swish"}
 N_POINTS = 1_000_000
-BATCH = 65_536
+BATCH = 113_664  # 148 SMs x 3 pairs of 128-row tiles (see above); --batch overrides
 METRIC = "point-evals/sec (fwd+bwd+Adam)"
 WORKLOAD = ("C2 tutorial-2 multi-scale NIF: ShapeNet 2->4x64->1 SIREN (omega0 30), ParameterNet 1->64x4 swish->latent 32, "
             "po_dim 16897, 1M points/GPU, fp32")
@@ -250,11 +253,17 @@ def run_ours(args):
     peak_burst = float(peaks.get("bf16_tflops", 1590.0))
     peak_sus = float(peaks.get("bf16_tflops_sustained", 1590.0 * 0.88))
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    traffic_by_kernel = {}
-    try:  # DRAM bytes per launch from the committed `ncu --set full` capture of one step
-        traffic_by_kernel = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_kernels.json")))
-    except (OSError, ValueError):
-        pass
+    traffic_by_kernel, traffic_file = {}, None
+    # DRAM bytes per launch from the committed `ncu --set full` capture of one step AT THIS BATCH (the captures record
+    # their batch; r02_ncu_kernels.json is the 65 536-row one of the earlier rounds)
+    for fn, fb in (("r02x_ncu_kernels.json", None), ("r02_ncu_kernels.json", 65536)):
+        try:
+            t = json.load(open(os.path.join(ROOT, "profiles", fn)))
+        except (OSError, ValueError):
+            continue
+        if int(t.pop("_batch", fb or 0)) == BATCH:
+            traffic_by_kernel, traffic_file = t, fn
+            break
     tot_ms = sum(ms for _, _, ms in prof.table) or 1.0
     table = []
     for name, cnt, ms in sorted(prof.table, key=lambda r: -r[2]):
@@ -286,6 +295,8 @@ def run_ours(args):
         "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "global_batch": gb, "parallelism": f"dp{world}",
                    "kernels": eng.kernel_path, "trunk_kernels": getattr(net._trunk, "kernel_path", None),
                    "dp_update": update_mode,
+                   "batch_note": "148 SMs x 3 pairs of 128-row tiles: fills the last wave of the persistent forward / "
+                                 "reverse kernels (65 536 rows, the batch of the earlier rounds: --batch 65536)",
                    "l2": "inputs rotate through the 1M-point set; per-step working set (activation stash + deltas, "
                          "> 200 MB) exceeds the 126 MB L2, no explicit flush"},
         "clocks": clocks,
@@ -301,8 +312,9 @@ def run_ours(args):
                      "peak": peak_burst, "unit": "TFLOP/s",
                      "frac": (dom["tflops"] / peak_burst) if "tflops" in dom else None,
                      "traffic": dom.get("dram_bytes_per_launch"),
-                     "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full "
-                                     "(profiles/r02_ncu_kernels.json)",
+                     "traffic_note": (f"dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full "
+                                      f"(profiles/{traffic_file})") if traffic_file else
+                                     "no ncu --set full capture at this batch under profiles/",
                      "peak_source": f"bf16_tflops (burst, dense 16-bit MMA), {peak_src}",
                      "note": "achieved = ALGORITHMIC flops per launch / launch time; the fp32-grade FP16x3 split issues 3 "
                              "tensor-core MACs per algorithmic MAC, so 1/3 of peak is this path's ceiling",
@@ -324,14 +336,19 @@ def run_ours(args):
 
 
 def main():
+    global BATCH
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH, help="rows per step and GPU")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    if args.batch < 1 or args.batch > N_POINTS:
+        raise SystemExit(f"--batch must be in 1..{N_POINTS}")
+    BATCH = args.batch
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -1,6 +1,6 @@
 """DRAM bytes per launch of every nif_* kernel from an `ncu --page raw --csv` export (what bench.py's roofline.traffic reads).
 
-    python tools/ncu_kernels_json.py gpurun_out/X_raw.csv profiles/r02_ncu_kernels.json
+    python tools/ncu_kernels_json.py gpurun_out/X_raw.csv profiles/r02x_ncu_kernels.json [batch]
 """
 import csv
 import json
@@ -22,5 +22,7 @@ for row in rows:
         tot += float(row[ix[m]].replace(",", "")) * scale[units[ix[m]]]
     acc.setdefault(name, []).append(tot)
 out = {k: sum(v) / len(v) for k, v in acc.items()}  # mean over the launches of the capture
+if len(sys.argv) > 3:
+    out["_batch"] = int(sys.argv[3])  # rows per step of the captured run (bench.py only uses a capture of its own batch)
 json.dump(out, open(sys.argv[2], "w"), indent=1)
 print(json.dumps(out, indent=1))

@@ -14,5 +14,6 @@ NIF_B200_GRAPH=0 ncu --set full --clock-control none --import-source on -s 60 -c
     python tools/step_prof.py 4 > gpurun_out/${TAG}_full.log 2>&1
 ncu -i gpurun_out/${TAG}_step_full.ncu-rep --page raw --csv > gpurun_out/${TAG}_raw.csv 2>/dev/null
 python tools/ncu_summary.py gpurun_out/${TAG}_raw.csv > gpurun_out/${TAG}_ncu_step.txt 2>&1; cat gpurun_out/${TAG}_ncu_step.txt
+python tools/ncu_kernels_json.py gpurun_out/${TAG}_raw.csv gpurun_out/${TAG}_ncu_kernels.json $(python -c "import bench; print(bench.BATCH)") > /dev/null 2>&1
 fi
 nproc; nvidia-smi --query-gpu=name,clocks.max.sm --format=csv
