@@ -95,8 +95,8 @@ __global__ void __launch_bounds__(256) nif_trunk_ew_bwd_kernel(const TrunkEwBwdA
     for (long long row = (long long)blockIdx.x * lanes + rl; row < a.B; row += (long long)gridDim.x * lanes) {
       const long long off = row * a.n + 8 * cv;
       float t[8], y[8], gq[8];
-      if (a.dh_in) {
-        const float4 t0 = ldg4(a.dh_in + off), t1 = ldg4(a.dh_in + off + 4);
+      if (a.dh_in) {  // (plain loads: dh_out may alias dh_in, so this is not read-only data)
+        const float4 t0 = *reinterpret_cast<const float4*>(a.dh_in + off), t1 = *reinterpret_cast<const float4*>(a.dh_in + off + 4);
         t[0] = t0.x; t[1] = t0.y; t[2] = t0.z; t[3] = t0.w; t[4] = t1.x; t[5] = t1.y; t[6] = t1.z; t[7] = t1.w;
       } else {
 #pragma unroll
