@@ -5,10 +5,10 @@
 
 Workload (BASELINE.json configs[1], SURVEY 8 "C2"): NIFMultiScale, ShapeNet 2 -> 4x64 SIREN -> 1
 (omega_0 30), ParameterNet 1 -> 64 x4 swish shortcut MLP -> latent 32, po_dim 16 897, 1 M synthetic
-(t, x0, x1) points, fp32.  One step = one optimisation step over one batch of 113 664 points per GPU: the forward and
-reverse kernels run one persistent CTA per SM on pairs of 128-row tiles, so a batch that is a multiple of 148 SMs x 256
-rows = 37 888 fills their last wave (3 pairs per SM here; the 65 536 rows of the earlier rounds leave 13 % of it empty:
-60.4 M rows/s against 68.4 M, profiles/r02w_wave_batches.json; `--batch 65536` reproduces that configuration).
+(t, x0, x1) points, fp32.  One step = one optimisation step over one batch of 65 536 points per GPU (the throughput batch
+SURVEY 8(d) fixes for C2).  `--batch B` measures another batch: the forward and reverse kernels run one persistent CTA per SM
+on pairs of 128-row tiles, so a multiple of 148 SMs x 256 rows = 37 888 fills their last wave -- 113 664 rows: 66.5-69.1 M
+rows/s against 60.4-60.8 M at 65 536, whose last wave is 13 % empty (profiles/r02w_wave_batches.json, r02x_*, r02y_*).
 N > 1 (torchrun, one rank per GPU): weak scaling, per-GPU batch fixed, one NCCL all-reduce of the flat
 gradient buffer per step.
 
@@ -34,7 +34,7 @@ CFG_S = {"use_resblock": False, "connectivity": "full", "input_dim": 2, "output_
          "weight_init_factor": 0.01, "omega_0": 30.0}
 CFG_P = {"use_resblock": False, "input_dim": 1, "latent_dim": 32, "units": 64, "nlayers": 4, "activation": "swish"}
 N_POINTS = 1_000_000
-BATCH = 113_664  # 148 SMs x 3 pairs of 128-row tiles (see above); --batch overrides
+BATCH = 65_536  # SURVEY 8(d); --batch overrides (113 664 = 148 SMs x 3 pairs of 128-row tiles fills the kernels' last wave)
 METRIC = "point-evals/sec (fwd+bwd+Adam)"
 WORKLOAD = ("C2 tutorial-2 multi-scale NIF: ShapeNet 2->4x64->1 SIREN (omega0 30), ParameterNet 1->64x4 swish->latent 32, "
             "po_dim 16897, 1M points/GPU, fp32")
@@ -255,8 +255,8 @@ def run_ours(args):
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     traffic_by_kernel, traffic_file = {}, None
     # DRAM bytes per launch from the committed `ncu --set full` capture of one step AT THIS BATCH (the captures record
-    # their batch; r02_ncu_kernels.json is the 65 536-row one of the earlier rounds)
-    for fn, fb in (("r02x_ncu_kernels.json", None), ("r02_ncu_kernels.json", 65536)):
+    # their batch: r02_ncu_kernels.json is the 65 536-row one, r02x_ncu_kernels.json the 113 664-row one)
+    for fn, fb in (("r02_ncu_kernels.json", 65536), ("r02x_ncu_kernels.json", None)):
         try:
             t = json.load(open(os.path.join(ROOT, "profiles", fn)))
         except (OSError, ValueError):
@@ -295,8 +295,9 @@ def run_ours(args):
         "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "global_batch": gb, "parallelism": f"dp{world}",
                    "kernels": eng.kernel_path, "trunk_kernels": getattr(net._trunk, "kernel_path", None),
                    "dp_update": update_mode,
-                   "batch_note": "148 SMs x 3 pairs of 128-row tiles: fills the last wave of the persistent forward / "
-                                 "reverse kernels (65 536 rows, the batch of the earlier rounds: --batch 65536)",
+                   "batch_note": "65 536 rows: SURVEY 8(d)'s throughput batch for C2 (256 tile pairs on 148 SMs: the last "
+                                 "wave of the persistent forward / reverse kernels is 13 % empty; --batch 113664 = 148 x 3 "
+                                 "pairs fills it: profiles/r02x_bench_1gpu.json, r02y_bench_*.json)",
                    "l2": "inputs rotate through the 1M-point set; per-step working set (activation stash + deltas, "
                          "> 200 MB) exceeds the 126 MB L2, no explicit flush"},
         "clocks": clocks,
