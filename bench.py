@@ -295,9 +295,10 @@ def run_ours(args):
         "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "global_batch": gb, "parallelism": f"dp{world}",
                    "kernels": eng.kernel_path, "trunk_kernels": getattr(net._trunk, "kernel_path", None),
                    "dp_update": update_mode,
-                   "batch_note": "65 536 rows: SURVEY 8(d)'s throughput batch for C2 (256 tile pairs on 148 SMs: the last "
-                                 "wave of the persistent forward / reverse kernels is 13 % empty; --batch 113664 = 148 x 3 "
-                                 "pairs fills it: profiles/r02x_bench_1gpu.json, r02y_bench_*.json)",
+                   "batch_note": ("65 536 rows: SURVEY 8(d)'s throughput batch for C2 (256 tile pairs on 148 SMs: the last "
+                                  "wave of the persistent forward / reverse kernels is 13 % empty; --batch 113664 = 148 x 3 "
+                                  "pairs fills it: profiles/r02x_bench_1gpu.json, r02y_bench_*.json)") if BATCH == 65536 else
+                                 f"--batch {BATCH} (the default is SURVEY 8(d)'s 65 536 rows)",
                    "l2": "inputs rotate through the 1M-point set; per-step working set (activation stash + deltas, "
                          "> 200 MB) exceeds the 126 MB L2, no explicit flush"},
         "clocks": clocks,
